@@ -1,0 +1,200 @@
+/* olf_abi.h -- C-ABI of the B200-native ORB + line stereo front end ("olf" = ORB-Line Front end).
+ *
+ * This is the drop-in boundary for the ONE hot path of robotseu/ORB_Line_SLAM that this repo
+ * accelerates.  The reference has no FFI layer of its own: its boundary is a set of C++
+ * class surfaces (ORBextractor, Lineextractor, ORBmatcher, LineMatcher free functions, Frame::Compute*).
+ * The C++ shim in orb_line_slam_b200/shim/ re-creates those surfaces with identical signatures and forwards
+ * to the entry points below; each entry point cites the reference interface it replaces.
+ *
+ * Conventions: C linkage, POD in/out, no exceptions.  Return value 0 = OLF_OK, negative = error code.
+ * Output buffers are caller-allocated with an explicit capacity; counts are returned through int*.
+ * A handle owns its CUDA stream(s), device pyramids and scratch.  Distinct handles may be used
+ * concurrently from different host threads; one handle is not re-entrant (same as the reference:
+ * ORBextractor is stateful through mvImagePyramid, include/ORBextractor.h:92).
+ * Image pointers are HOST pointers unless the function name ends in _dev.
+ */
+#ifndef OLF_ABI_H
+#define OLF_ABI_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OLF_OK              0
+#define OLF_ERR_ARG        -1   /* bad argument (null pointer, non-positive size, size mismatch)        */
+#define OLF_ERR_CUDA       -2   /* CUDA runtime error; olf_last_error() has the text                   */
+#define OLF_ERR_CAPACITY   -3   /* caller buffer or internal pool too small                            */
+#define OLF_ERR_NO_DEVICE  -4   /* no CUDA device / extension built without one -- never a CPU fallback */
+#define OLF_ERR_INTERNAL   -5
+
+#define OLF_DESC_BYTES     32   /* 256-bit rBRIEF / binary LBD descriptor                              */
+#define OLF_GRID_COLS      64   /* FRAME_GRID_COLS include/Frame.h:52                                  */
+#define OLF_GRID_ROWS      48   /* FRAME_GRID_ROWS include/Frame.h:51                                  */
+#define OLF_TH_HIGH       100   /* ORBmatcher::TH_HIGH src/ORBmatcher.cc:39                            */
+#define OLF_TH_LOW         50   /* ORBmatcher::TH_LOW  src/ORBmatcher.cc:40                            */
+#define OLF_HISTO_LENGTH   30   /* ORBmatcher::HISTO_LENGTH src/ORBmatcher.cc:41                       */
+#define OLF_MAX_LEVELS     16
+
+/* cv::KeyPoint fields the reference fills (src/ORBextractor.cc:839-848, 1097-1103); class_id stays -1. */
+typedef struct olf_keypoint {
+    float x, y;        /* pt, level-0 coordinates                      */
+    float size;        /* (int)(31*scale[octave])                      */
+    float angle;       /* degrees, cv::fastAtan2                       */
+    float response;    /* FAST score                                   */
+    int   octave;
+} olf_keypoint;
+
+/* cv::line_descriptor::KeyLine, field for field (descriptor_custom.hpp:105-145). */
+typedef struct olf_keyline {
+    float angle;
+    int   class_id;
+    int   octave;
+    float pt_x, pt_y;
+    float response;
+    float size;
+    float startPointX, startPointY, endPointX, endPointY;
+    float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+    float lineLength;
+    int   numOfPixels;
+} olf_keyline;
+
+/* Lineextractor ctor arguments (include/LineExtractor.h:43-45) + the Config:: value it reads. */
+typedef struct olf_line_params {
+    int    lsd_nfeatures;      /* keep top-N by response; 0 = keep all (src/LineExtractor.cc:56) */
+    double min_line_length;    /* relative to min(cols,rows)          (src/LineExtractor.cc:53)  */
+    int    lsd_refine;         /* only 0 (LSD_REFINE_NONE) is supported: Examples/PL yaml files   */
+    double lsd_scale;          /* 1.2 */
+    double lsd_sigma_scale;    /* 0.6 */
+    double lsd_quant;          /* 2.0 */
+    double lsd_ang_th;         /* 22.5 */
+    double lsd_log_eps;        /* unused with refine 0 */
+    double lsd_density_th;     /* unused with refine 0 */
+    int    lsd_n_bins;         /* 1024 */
+} olf_line_params;
+
+/* Config:: values read by the line matchers (src/LineMatcher.cpp:106,163,201,262,282; src/Frame.cc:923,954-957,1007,1043) */
+typedef struct olf_line_match_params {
+    int    best_lr_matches;    /* Config::bestLRMatches()  default 1    */
+    double min_ratio_12_l;     /* Config::minRatio12L()    default 0.9  */
+    double line_sim_th;        /* Config::lineSimTh()      default 0.75 */
+    int    matching_s_ws;      /* Config::matchingSWs()    default 10   */
+    double min_disp;           /* Config::minDisp()        default 1.0  */
+    double line_horiz_th;      /* Config::lineHorizTh()    default 0.1  */
+    double stereo_overlap_th;  /* Config::stereoOverlapTh() default 0.75 */
+    double ls_min_disp_ratio;  /* Config::lsMinDispRatio() default 0.7  */
+} olf_line_match_params;
+
+/* Pinhole + stereo constants of Frame (src/Frame.cc:182-196) */
+typedef struct olf_camera {
+    float fx, fy, cx, cy;
+    float bf;                  /* Frame::mbf */
+    float min_x, max_x, min_y, max_y;   /* Frame::mnMinX.. (image bounds; 0,w,0,h when rectified) */
+} olf_camera;
+
+typedef struct olf_orb olf_orb;
+typedef struct olf_line olf_line;
+
+const char* olf_last_error(void);
+int olf_device_count(void);
+
+/* ---- ORBextractor (include/ORBextractor.h:52-118; src/ORBextractor.cc:412-472, 1045-1134) ---------------- */
+olf_orb* olf_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device);
+void     olf_orb_destroy(olf_orb* h);
+/* ORBextractor::operator() : image -> keypoints + N x 32 descriptors (src/ORBextractor.cc:1045-1107). */
+int olf_orb_extract(olf_orb* h, const uint8_t* img, int width, int height, int stride,
+                    olf_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* same, image already resident on the device (the bench's HBM-resident leg) */
+int olf_orb_extract_dev(olf_orb* h, const uint8_t* d_img, int width, int height, int stride,
+                        olf_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* ORBextractor::mvImagePyramid[level] read-back (src/Frame.cc:709,799,811,816 read it). */
+int olf_orb_level_size(const olf_orb* h, int level, int* width, int* height);
+int olf_orb_get_level(olf_orb* h, int level, uint8_t* dst, int dst_stride);
+/* GetScaleFactors() etc. (include/ORBextractor.h:68-90): out[nlevels] */
+int olf_orb_scale_factors(const olf_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2);
+int olf_orb_features_per_level(const olf_orb* h, int* out);
+/* debug/parity: FAST candidates of the last extract, before the quadtree (src/ORBextractor.cc:791-831):
+ * per candidate {level, x, y, score} with x,y relative to the level image. */
+int olf_orb_last_candidates(olf_orb* h, int* lvl_x_y_score /*cap x 4*/, int cap, int* n);
+
+/* ---- Lineextractor (include/LineExtractor.h:40-72; src/LineExtractor.cc:31-67) ---------------------------- */
+olf_line* olf_line_create(const olf_line_params* p, int device);
+void      olf_line_destroy(olf_line* h);
+/* Lineextractor::operator(): LSD detect -> top-N by response -> LBD (src/LineExtractor.cc:54-66). */
+int olf_line_extract(olf_line* h, const uint8_t* img, int width, int height, int stride,
+                     olf_keyline* kls, uint8_t* desc, int cap, int* n);
+int olf_line_extract_dev(olf_line* h, const uint8_t* d_img, int width, int height, int stride,
+                         olf_keyline* kls, uint8_t* desc, int cap, int* n);
+/* cv::LineSegmentDetector::detect as configured by LSDDetectorC::detectImpl (LSDDetector_custom.cpp:246-262):
+ * raw Vec4f segments (x1,y1,x2,y2) in seed order, before the KeyLine filter. */
+int olf_lsd_detect(olf_line* h, const uint8_t* img, int width, int height, int stride,
+                   float* segs /*cap x 4*/, int cap, int* n);
+/* BinaryDescriptor::compute on caller-supplied keylines (binary_descriptor_custom.cpp:539-687). */
+int olf_lbd_compute(olf_line* h, const uint8_t* img, int width, int height, int stride,
+                    const olf_keyline* kls, int n, uint8_t* desc);
+
+/* ---- Hamming matchers --------------------------------------------------------------------------------- */
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(d1,d2,2) as used by matchNNR (src/LineMatcher.cpp:47-49):
+ * two nearest train rows per query, ties -> lowest train index.  idx1/dist1 = -1/INT_MAX-like 256*2 when n2 < 2. */
+int olf_knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                     int* idx0, int* dist0, int* idx1, int* dist1, int device);
+/* matchNNR (src/LineMatcher.cpp:42-62): matches12[n1], returns count through *nmatches. */
+int olf_match_nnr(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int* matches12, int* nmatches, int device);
+/* match(desc1,desc2,nnr,matches12) (src/LineMatcher.cpp:104-132): adds the mutual check when best_lr_matches. */
+int olf_match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int best_lr_matches,
+                    int* matches12, int* nmatches, int device);
+
+/* ---- Frame::ComputeStereoMatches (src/Frame.cc:702-876) -------------------------------------------------- */
+/* Needs both extractors' pyramids (mvImagePyramid) which stay on the device inside the handles. */
+int olf_stereo_points(olf_orb* left, olf_orb* right,
+                      const olf_keypoint* kps_l, const uint8_t* desc_l, int n_l,
+                      const olf_keypoint* kps_r, const uint8_t* desc_r, int n_r,
+                      float bf, float fx, float* u_right /*n_l*/, float* depth /*n_l*/);
+
+/* ---- Frame::ComputeStereoMatches_Lines + matchGrid(lines) (src/Frame.cc:878-1000; src/LineMatcher.cpp:220-299) */
+int olf_stereo_lines(const olf_keyline* kls_l, const uint8_t* desc_l, int n_l,
+                     const olf_keyline* kls_r, const uint8_t* desc_r, int n_r,
+                     int img_width, int img_height, const olf_line_match_params* p,
+                     int* matches12 /*n_l, raw matchGrid output*/,
+                     float* disp_s_e /*n_l x 2, mvDisparity_l*/, double* le /*n_l x 3, mvle_l*/, int device);
+
+/* ---- ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono, match12) (src/ORBmatcher.cc:1474-1618) - */
+typedef struct olf_sbp_last_args {
+    /* current frame (the one being filled) */
+    const olf_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_u_right; int n_cur;
+    olf_camera cam;
+    const float* scale_factors; int nlevels;
+    float Rcw[9]; float tcw[3];          /* CurrentFrame.mTcw */
+    float Rlw[9]; float tlw[3];          /* LastFrame.mTcw    */
+    /* last frame: one entry per keypoint i */
+    const olf_keypoint* last_kps; int n_last;
+    const uint8_t* last_has_point;       /* mvpMapPoints[i] != NULL && !mvbOutlier[i]       */
+    const uint8_t* last_point_observed;  /* pMP->Observations() > 0                         */
+    const float*   last_world_pos;       /* n_last x 3, pMP->GetWorldPos()                  */
+    const uint8_t* last_point_desc;      /* n_last x 32, pMP->GetDescriptor()               */
+    float th; int mono; int check_orientation;
+} olf_sbp_last_args;
+/* assigned_cur[i] (n_last) = index of the current keypoint map point i was written to (before the
+ * rotation-consistency pass) or -1; cur_point[j] (n_cur) = final index into last-frame points held by
+ * current keypoint j or -1 (after ComputeThreeMaxima pruning); *nmatches = return value of the reference. */
+int olf_search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device);
+
+/* ---- ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:47-131) ------- */
+typedef struct olf_sbp_map_args {
+    const olf_keypoint* cur_kps; const uint8_t* cur_desc; const float* cur_u_right; int n_cur;
+    const uint8_t* cur_occupied;         /* F.mvpMapPoints[idx] && Observations()>0 on entry */
+    olf_camera cam;
+    const float* scale_factors; int nlevels;
+    int n_points;                        /* map points with mbTrackInView && !isBad()        */
+    const float* proj_x; const float* proj_y; const float* proj_xr;   /* mTrackProjX/Y/XR     */
+    const int*   pred_level;             /* mnTrackScaleLevel                                */
+    const float* view_cos;               /* mTrackViewCos                                    */
+    const uint8_t* point_observed;       /* Observations()>0 (so that a write blocks later)  */
+    const uint8_t* point_desc;           /* n_points x 32                                    */
+    float th; float nn_ratio;
+} olf_sbp_map_args;
+int olf_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur /*n_points*/, int* nmatches, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OLF_ABI_H */

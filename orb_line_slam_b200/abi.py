@@ -1,0 +1,236 @@
+"""ctypes mirror of include/olf_abi.h: POD layouts shared by the product wrapper and the tests."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+
+OLF_OK, OLF_ERR_ARG, OLF_ERR_CUDA, OLF_ERR_CAPACITY, OLF_ERR_NO_DEVICE, OLF_ERR_INTERNAL = 0, -1, -2, -3, -4, -5
+
+# olf_keypoint / olf_keyline as numpy structured dtypes (C layout, no padding: all 4-byte fields)
+KEYPOINT = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4")])
+KEYLINE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+                    ("response", "<f4"), ("size", "<f4"),
+                    ("startPointX", "<f4"), ("startPointY", "<f4"), ("endPointX", "<f4"), ("endPointY", "<f4"),
+                    ("sPointInOctaveX", "<f4"), ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+                    ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+assert KEYPOINT.itemsize == 24 and KEYLINE.itemsize == 68
+
+
+class LineParams(C.Structure):
+    """olf_line_params; defaults = Examples/PL/*.yaml (lsd_* keys) of the reference."""
+    _fields_ = [("lsd_nfeatures", C.c_int), ("min_line_length", C.c_double), ("lsd_refine", C.c_int),
+                ("lsd_scale", C.c_double), ("lsd_sigma_scale", C.c_double), ("lsd_quant", C.c_double),
+                ("lsd_ang_th", C.c_double), ("lsd_log_eps", C.c_double), ("lsd_density_th", C.c_double),
+                ("lsd_n_bins", C.c_int)]
+
+    def __init__(self, lsd_nfeatures=500, min_line_length=0.025, lsd_refine=0, lsd_scale=1.2, lsd_sigma_scale=0.6,
+                 lsd_quant=2.0, lsd_ang_th=22.5, lsd_log_eps=1.0, lsd_density_th=0.6, lsd_n_bins=1024):
+        super().__init__(lsd_nfeatures, min_line_length, lsd_refine, lsd_scale, lsd_sigma_scale, lsd_quant,
+                         lsd_ang_th, lsd_log_eps, lsd_density_th, lsd_n_bins)
+
+
+class LineMatchParams(C.Structure):
+    """olf_line_match_params; defaults = src/Config.cpp:42-87 of the reference."""
+    _fields_ = [("best_lr_matches", C.c_int), ("min_ratio_12_l", C.c_double), ("line_sim_th", C.c_double),
+                ("matching_s_ws", C.c_int), ("min_disp", C.c_double), ("line_horiz_th", C.c_double),
+                ("stereo_overlap_th", C.c_double), ("ls_min_disp_ratio", C.c_double)]
+
+    def __init__(self, best_lr_matches=1, min_ratio_12_l=0.9, line_sim_th=0.75, matching_s_ws=10, min_disp=1.0,
+                 line_horiz_th=0.1, stereo_overlap_th=0.75, ls_min_disp_ratio=0.7):
+        super().__init__(best_lr_matches, min_ratio_12_l, line_sim_th, matching_s_ws, min_disp, line_horiz_th,
+                         stereo_overlap_th, ls_min_disp_ratio)
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
+_P = C.c_void_p
+
+
+class SbpLastArgs(C.Structure):
+    _fields_ = [("cur_kps", _P), ("cur_desc", _P), ("cur_u_right", _P), ("n_cur", C.c_int),
+                ("cam", Camera), ("scale_factors", _P), ("nlevels", C.c_int),
+                ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Rlw", C.c_float * 9), ("tlw", C.c_float * 3),
+                ("last_kps", _P), ("n_last", C.c_int), ("last_has_point", _P), ("last_point_observed", _P),
+                ("last_world_pos", _P), ("last_point_desc", _P),
+                ("th", C.c_float), ("mono", C.c_int), ("check_orientation", C.c_int)]
+
+
+class SbpMapArgs(C.Structure):
+    _fields_ = [("cur_kps", _P), ("cur_desc", _P), ("cur_u_right", _P), ("n_cur", C.c_int), ("cur_occupied", _P),
+                ("cam", Camera), ("scale_factors", _P), ("nlevels", C.c_int),
+                ("n_points", C.c_int), ("proj_x", _P), ("proj_y", _P), ("proj_xr", _P), ("pred_level", _P),
+                ("view_cos", _P), ("point_observed", _P), ("point_desc", _P), ("th", C.c_float), ("nn_ratio", C.c_float)]
+
+
+def ptr(a):
+    """void* of a contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def as_u8_image(img):
+    img = np.ascontiguousarray(img)
+    if img.dtype != np.uint8 or img.ndim != 2:
+        raise TypeError("image must be a 2-D uint8 array (CV_8UC1)")
+    return img
+
+
+class FrontEndApi:
+    """Binds the olf_* (product) or orc_* (oracle) symbol family of a loaded shared library.
+
+    The product library takes a trailing `device` argument on handle constructors and stateless matchers;
+    the oracle does not.  Everything else is identical, which is what lets the parity tests call both alike.
+    """
+
+    def __init__(self, lib: C.CDLL, prefix: str, device: int | None):
+        self.lib, self.prefix, self.device = lib, prefix, device
+        self._dev = () if device is None else (C.c_int(device),)
+
+    def fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def check(self, rc, what):
+        if rc != OLF_OK:
+            msg = ""
+            if self.prefix == "olf_":
+                self.lib.olf_last_error.restype = C.c_char_p
+                msg = (self.lib.olf_last_error() or b"").decode()
+            raise RuntimeError(f"{self.prefix}{what} failed with code {rc} {msg}")
+
+    # ---- ORB ----
+    def orb_create(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        f = self.fn("orb_create"); f.restype = C.c_void_p
+        h = f(C.c_int(nfeatures), C.c_float(scale_factor), C.c_int(nlevels), C.c_int(ini_th), C.c_int(min_th), *self._dev)
+        if not h:
+            raise RuntimeError(self.prefix + "orb_create failed")
+        return C.c_void_p(h)
+
+    def orb_destroy(self, h):
+        f = self.fn("orb_destroy"); f.restype = None; f(h)
+
+    def orb_extract(self, h, img, cap=8192):
+        img = as_u8_image(img)
+        kps = np.zeros(cap, dtype=KEYPOINT); desc = np.zeros((cap, 32), dtype=np.uint8); n = C.c_int(0)
+        rc = self.fn("orb_extract")(h, ptr(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(img.strides[0]),
+                                    ptr(kps), ptr(desc), C.c_int(cap), C.byref(n))
+        self.check(rc, "orb_extract")
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def orb_level(self, h, level):
+        w, hh = C.c_int(0), C.c_int(0)
+        self.check(self.fn("orb_level_size")(h, C.c_int(level), C.byref(w), C.byref(hh)), "orb_level_size")
+        out = np.zeros((hh.value, w.value), dtype=np.uint8)
+        self.check(self.fn("orb_get_level")(h, C.c_int(level), ptr(out), C.c_int(w.value)), "orb_get_level")
+        return out
+
+    def orb_scale_factors(self, h, nlevels=8):
+        s = np.zeros(nlevels, np.float32); i = np.zeros(nlevels, np.float32)
+        s2 = np.zeros(nlevels, np.float32); i2 = np.zeros(nlevels, np.float32)
+        self.check(self.fn("orb_scale_factors")(h, ptr(s), ptr(i), ptr(s2), ptr(i2)), "orb_scale_factors")
+        return s, i, s2, i2
+
+    def orb_features_per_level(self, h, nlevels=8):
+        o = np.zeros(nlevels, np.int32)
+        self.check(self.fn("orb_features_per_level")(h, ptr(o)), "orb_features_per_level")
+        return o
+
+    def orb_last_candidates(self, h, cap=400000):
+        o = np.zeros((cap, 4), np.int32); n = C.c_int(0)
+        self.check(self.fn("orb_last_candidates")(h, ptr(o), C.c_int(cap), C.byref(n)), "orb_last_candidates")
+        return o[:n.value].copy()
+
+    # ---- lines ----
+    def line_create(self, params: LineParams | None = None):
+        params = params or LineParams()
+        f = self.fn("line_create"); f.restype = C.c_void_p
+        h = f(C.byref(params), *self._dev)
+        if not h:
+            raise RuntimeError(self.prefix + "line_create failed")
+        return C.c_void_p(h)
+
+    def line_destroy(self, h):
+        f = self.fn("line_destroy"); f.restype = None; f(h)
+
+    def lsd_detect(self, h, img, cap=65536):
+        img = as_u8_image(img)
+        segs = np.zeros((cap, 4), np.float32); n = C.c_int(0)
+        rc = self.fn("lsd_detect")(h, ptr(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(img.strides[0]),
+                                   ptr(segs), C.c_int(cap), C.byref(n))
+        self.check(rc, "lsd_detect")
+        return segs[:n.value].copy()
+
+    def line_extract(self, h, img, cap=65536):
+        img = as_u8_image(img)
+        kls = np.zeros(cap, dtype=KEYLINE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int(0)
+        rc = self.fn("line_extract")(h, ptr(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(img.strides[0]),
+                                     ptr(kls), ptr(desc), C.c_int(cap), C.byref(n))
+        self.check(rc, "line_extract")
+        return kls[:n.value].copy(), desc[:n.value].copy()
+
+    def lbd_compute(self, h, img, kls):
+        img = as_u8_image(img); kls = np.ascontiguousarray(kls, dtype=KEYLINE)
+        desc = np.zeros((len(kls), 32), np.uint8)
+        rc = self.fn("lbd_compute")(h, ptr(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(img.strides[0]),
+                                    ptr(kls), C.c_int(len(kls)), ptr(desc))
+        self.check(rc, "lbd_compute")
+        return desc
+
+    # ---- matchers ----
+    def knn2_hamming(self, d1, d2):
+        d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+        n1, n2 = len(d1), len(d2)
+        o = [np.zeros(n1, np.int32) for _ in range(4)]
+        rc = self.fn("knn2_hamming")(ptr(d1), C.c_int(n1), ptr(d2), C.c_int(n2), ptr(o[0]), ptr(o[1]), ptr(o[2]), ptr(o[3]), *self._dev)
+        self.check(rc, "knn2_hamming")
+        return tuple(o)      # idx0, dist0, idx1, dist1
+
+    def match_nnr(self, d1, d2, nnr):
+        d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+        m = np.zeros(len(d1), np.int32); n = C.c_int(0)
+        rc = self.fn("match_nnr")(ptr(d1), C.c_int(len(d1)), ptr(d2), C.c_int(len(d2)), C.c_float(nnr), ptr(m), C.byref(n), *self._dev)
+        self.check(rc, "match_nnr")
+        return m, n.value
+
+    def match_lines(self, d1, d2, nnr, best_lr=True):
+        d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+        m = np.zeros(len(d1), np.int32); n = C.c_int(0)
+        rc = self.fn("match_lines")(ptr(d1), C.c_int(len(d1)), ptr(d2), C.c_int(len(d2)), C.c_float(nnr), C.c_int(int(best_lr)),
+                                    ptr(m), C.byref(n), *self._dev)
+        self.check(rc, "match_lines")
+        return m, n.value
+
+    def stereo_points(self, hl, hr, kl, dl, kr, dr, bf, fx):
+        kl = np.ascontiguousarray(kl, KEYPOINT); kr = np.ascontiguousarray(kr, KEYPOINT)
+        dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+        u = np.zeros(len(kl), np.float32); d = np.zeros(len(kl), np.float32)
+        rc = self.fn("stereo_points")(hl, hr, ptr(kl), ptr(dl), C.c_int(len(kl)), ptr(kr), ptr(dr), C.c_int(len(kr)),
+                                      C.c_float(bf), C.c_float(fx), ptr(u), ptr(d))
+        self.check(rc, "stereo_points")
+        return u, d
+
+    def stereo_lines(self, kl, dl, kr, dr, w, h, params: LineMatchParams | None = None):
+        params = params or LineMatchParams()
+        kl = np.ascontiguousarray(kl, KEYLINE); kr = np.ascontiguousarray(kr, KEYLINE)
+        dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+        m = np.zeros(len(kl), np.int32); disp = np.zeros((len(kl), 2), np.float32); le = np.zeros((len(kl), 3), np.float64)
+        rc = self.fn("stereo_lines")(ptr(kl), ptr(dl), C.c_int(len(kl)), ptr(kr), ptr(dr), C.c_int(len(kr)), C.c_int(w), C.c_int(h),
+                                     C.byref(params), ptr(m), ptr(disp), ptr(le), *self._dev)
+        self.check(rc, "stereo_lines")
+        return m, disp, le
+
+    def search_by_projection_last(self, args: SbpLastArgs, keep):
+        n_last, n_cur = args.n_last, args.n_cur
+        a = np.zeros(n_last, np.int32); c = np.zeros(n_cur, np.int32); n = C.c_int(0)
+        rc = self.fn("search_by_projection_last")(C.byref(args), ptr(a), ptr(c), C.byref(n), *self._dev)
+        self.check(rc, "search_by_projection_last")
+        return a, c, n.value
+
+    def search_by_projection_map(self, args: SbpMapArgs, keep):
+        a = np.zeros(args.n_points, np.int32); n = C.c_int(0)
+        rc = self.fn("search_by_projection_map")(C.byref(args), ptr(a), C.byref(n), *self._dev)
+        self.check(rc, "search_by_projection_map")
+        return a, n.value
