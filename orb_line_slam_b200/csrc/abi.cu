@@ -1,0 +1,50 @@
+// extern "C" surface of libolf.so: thin forwarding layer over the C++ implementations (see include/olf_abi.h).
+#include "common.cuh"
+#include "orb.h"
+#include <mutex>
+
+namespace olf {
+static thread_local std::string g_err;
+void set_last_error(const std::string& s) { g_err = s; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_err = buf;
+    cudaGetLastError();
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? OLF_ERR_NO_DEVICE : OLF_ERR_CUDA;
+}
+}  // namespace olf
+using namespace olf;
+
+extern "C" {
+const char* olf_last_error(void) { return g_err.c_str(); }
+int olf_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+olf_orb* olf_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device) {
+    return (olf_orb*)orb_create(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, device);
+}
+void olf_orb_destroy(olf_orb* h) { orb_destroy((OrbImpl*)h); }
+int olf_orb_extract(olf_orb* h, const uint8_t* img, int width, int height, int stride, olf_keypoint* kps, uint8_t* desc, int cap, int* n) {
+    return orb_extract((OrbImpl*)h, img, width, height, stride, false, kps, desc, cap, n);
+}
+int olf_orb_extract_dev(olf_orb* h, const uint8_t* d_img, int width, int height, int stride, olf_keypoint* kps, uint8_t* desc, int cap, int* n) {
+    return orb_extract((OrbImpl*)h, d_img, width, height, stride, true, kps, desc, cap, n);
+}
+int olf_orb_level_size(const olf_orb* h, int level, int* width, int* height) { return orb_level_size((const OrbImpl*)h, level, width, height); }
+int olf_orb_get_level(olf_orb* h, int level, uint8_t* dst, int dst_stride) { return orb_get_level((OrbImpl*)h, level, dst, dst_stride); }
+int olf_orb_scale_factors(const olf_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2) {
+    if (!h) return OLF_ERR_ARG;
+    const float *s, *is, *s2, *is2; int nl;
+    orb_scale_tables((const OrbImpl*)h, &s, &is, &s2, &is2, nullptr, &nl);
+    for (int i = 0; i < nl; ++i) { if (scale) scale[i] = s[i]; if (inv_scale) inv_scale[i] = is[i]; if (sigma2) sigma2[i] = s2[i]; if (inv_sigma2) inv_sigma2[i] = is2[i]; }
+    return OLF_OK;
+}
+int olf_orb_features_per_level(const olf_orb* h, int* out) {
+    if (!h || !out) return OLF_ERR_ARG;
+    const int* f; int nl;
+    orb_scale_tables((const OrbImpl*)h, nullptr, nullptr, nullptr, nullptr, &f, &nl);
+    for (int i = 0; i < nl; ++i) out[i] = f[i];
+    return OLF_OK;
+}
+int olf_orb_last_candidates(olf_orb* h, int* out, int cap, int* n) { return orb_last_candidates((OrbImpl*)h, out, cap, n); }
+}
