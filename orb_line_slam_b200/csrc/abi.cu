@@ -1,6 +1,7 @@
 // extern "C" surface of libolf.so: thin forwarding layer over the C++ implementations (see include/olf_abi.h).
 #include "common.cuh"
 #include "orb.h"
+#include "line.h"
 #include <mutex>
 
 namespace olf {
@@ -47,4 +48,20 @@ int olf_orb_features_per_level(const olf_orb* h, int* out) {
     return OLF_OK;
 }
 int olf_orb_last_candidates(olf_orb* h, int* out, int cap, int* n) { return orb_last_candidates((OrbImpl*)h, out, cap, n); }
+
+olf_line* olf_line_create(const olf_line_params* p, int device) { return (olf_line*)line_create(p, device); }
+void olf_line_destroy(olf_line* h) { line_destroy((LineImpl*)h); }
+int olf_line_extract(olf_line* h, const uint8_t* img, int width, int height, int stride, olf_keyline* kls, uint8_t* desc, int cap, int* n) {
+    return line_extract((LineImpl*)h, img, width, height, stride, false, kls, desc, cap, n);
+}
+int olf_line_extract_dev(olf_line* h, const uint8_t* d_img, int width, int height, int stride, olf_keyline* kls, uint8_t* desc, int cap, int* n) {
+    return line_extract((LineImpl*)h, d_img, width, height, stride, true, kls, desc, cap, n);
+}
+int olf_lsd_detect(olf_line* h, const uint8_t* img, int width, int height, int stride, float* segs, int cap, int* n) {
+    return line_lsd_detect((LineImpl*)h, img, width, height, stride, false, segs, cap, n);
+}
+int olf_lbd_compute(olf_line* h, const uint8_t* img, int width, int height, int stride, const olf_keyline* kls, int n, uint8_t* desc) {
+    return line_lbd_compute((LineImpl*)h, img, width, height, stride, kls, n, desc);
+}
+int olf_line_last_stats(const olf_line* h, int* out8) { if (!h || !out8) return OLF_ERR_ARG; line_last_stats((const LineImpl*)h, out8); return OLF_OK; }
 }

@@ -1,0 +1,739 @@
+// Line half of the front end on sm_100a: LSD (cv::LineSegmentDetector, refine NONE) + LBD binary descriptors.
+// Replaces Lineextractor::operator() (reference src/LineExtractor.cc:31-67), LSDDetectorC::detectImpl
+// (Thirdparty/line_descriptor/src/LSDDetector_custom.cpp:227-308, which calls the un-vendored cv LSD) and
+// BinaryDescriptor::compute (binary_descriptor_custom.cpp:350-412, 539-687, 1026-1372).
+//
+// LSD stages: blur 7x7 sigma 0.6 -> resize x1.2 (INTER_LINEAR_EXACT) -> gradient/angle -> gradient-bin histogram ->
+// seeds grouped by bin -> parallel region growing (fixed-point iteration, lsd_core.h) -> rectangle fit.
+// Host steps between GPU phases: libm cos/sin of the O(#regions) rectangle angles, KeyLine construction
+// (atan2, sort by response, top-N) -- all O(#segments), the per-pixel work never leaves the device.
+#include "common.cuh"
+#include "img_kernels.cuh"
+#include "lsd_core.h"
+#include "line.h"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace cg = cooperative_groups;
+
+namespace olf {
+using namespace lsd;
+
+// ---- cv::resize INTER_LINEAR_EXACT 8UC1 -------------------------------------------------------
+struct ExCoef { int s; int c0, c1; };
+__global__ void k_resize_exact(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                               uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
+                               const ExCoef* __restrict__ cx, const ExCoef* __restrict__ cy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const ExCoef a = cx[x], b = cy[y];
+    const int x1 = min(a.s + 1, sw - 1), y1 = min(b.s + 1, sh - 1);
+    const uint8_t* r0 = src + (size_t)b.s * spitch;
+    const uint8_t* r1 = src + (size_t)y1 * spitch;
+    const unsigned t0 = (unsigned)(r0[a.s] * a.c0 + r0[x1] * a.c1);
+    const unsigned t1 = (unsigned)(r1[a.s] * a.c0 + r1[x1] * a.c1);
+    const unsigned acc = t0 * (unsigned)b.c0 + t1 * (unsigned)b.c1;
+    dst[(size_t)y * dpitch + x] = (uint8_t)((acc + (1u << 15)) >> 16);
+}
+
+// ---- ll_angle: gradient, level-line angle, max gradient ---------------------------------
+// n2_thresh = smallest gx^2+gy^2 whose norm sqrt(n2/4.0) exceeds rho (computed exactly on the host).
+__global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, int W, int H, int pitch, int n2_thresh,
+                                                  float* __restrict__ ang, short2_t* __restrict__ dabc,
+                                                  u64* __restrict__ claim0, u64* __restrict__ claim1, int* __restrict__ n2max) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    int n2 = 0;
+    if (x < W && y < H) {
+        const int q = y * W + x;
+        float a = -1.f;
+        short2_t d; d.x = 0; d.y = 0;
+        if (x < W - 1 && y < H - 1) {
+            const uint8_t* r0 = img + (size_t)y * pitch + x;
+            const uint8_t* r1 = r0 + pitch;
+            const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
+            const int gx = DA + BC, gy = DA - BC;
+            d.x = (short)DA; d.y = (short)BC;
+            const int v = gx * gx + gy * gy;
+            if (v >= n2_thresh) { a = olf::lsd::fast_atan2_deg((float)gx, (float)-gy); n2 = v; }
+        }
+        ang[q] = a; dabc[q] = d; claim0[q] = kClaimNone; claim1[q] = kClaimNone;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n2 = max(n2, __shfl_xor_sync(0xffffffffu, n2, o));
+    if ((threadIdx.x & 31) == 0 && n2 > 0) atomicMax(n2max, n2);
+}
+
+__device__ __forceinline__ int lsd_bin(short2_t d, double bin_coef) {
+    const int gx = d.x + d.y, gy = d.x - d.y;
+    return (int)__dmul_rn(__dsqrt_rn(__ddiv_rn((double)(gx * gx + gy * gy), 4.0)), bin_coef);
+}
+__device__ __forceinline__ double lsd_bin_coef(int n2max, int n_bins) {
+    const double max_grad = __dsqrt_rn(__ddiv_rn((double)n2max, 4.0));
+    return max_grad > 0 ? __ddiv_rn((double)(n_bins - 1), max_grad) : 0.0;
+}
+
+// histogram of gradient bins over defined pixels
+__global__ void __launch_bounds__(256) k_lsd_hist(const float* __restrict__ ang, const short2_t* __restrict__ dabc, int S,
+                                                  const int* __restrict__ n2max, int n_bins, unsigned* __restrict__ hist) {
+    extern __shared__ unsigned sh[];
+    for (int i = threadIdx.x; i < n_bins; i += 256) sh[i] = 0;
+    __syncthreads();
+    const double coef = lsd_bin_coef(*n2max, n_bins);
+    for (int q = blockIdx.x * 256 + threadIdx.x; q < S; q += gridDim.x * 256)
+        if (ang[q] >= 0.f) atomicAdd(&sh[lsd_bin(dabc[q], coef)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins; i += 256) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// one block: bin offsets (descending bin order) and the wave plan (whole bins, cumulative targets doubling)
+struct LsdPlan { int n_seeds; int n_waves; int wave_start[64]; };
+__global__ void k_lsd_plan(const unsigned* __restrict__ hist, int n_bins, int first_wave, unsigned* __restrict__ bin_start,
+                           unsigned* __restrict__ cursor, LsdPlan* __restrict__ plan) {
+    if (threadIdx.x != 0) return;
+    unsigned acc = 0;
+    int nw = 0;
+    long long target = first_wave;
+    plan->wave_start[0] = 0;
+    for (int b = n_bins - 1; b >= 0; --b) {
+        bin_start[b] = acc; cursor[b] = 0;
+        acc += hist[b];
+        if ((long long)acc - plan->wave_start[nw] >= target && nw < 61) { plan->wave_start[++nw] = (int)acc; target *= 2; }
+    }
+    if (plan->wave_start[nw] != (int)acc) plan->wave_start[++nw] = (int)acc;
+    plan->n_seeds = (int)acc; plan->n_waves = nw;
+}
+
+__global__ void __launch_bounds__(256) k_lsd_scatter(const float* __restrict__ ang, const short2_t* __restrict__ dabc, int S,
+                                                     const int* __restrict__ n2max, int n_bins, const unsigned* __restrict__ bin_start,
+                                                     unsigned* __restrict__ cursor, int* __restrict__ seed_pix, u64* __restrict__ seed_prio) {
+    const double coef = lsd_bin_coef(*n2max, n_bins);
+    for (int q = blockIdx.x * 256 + threadIdx.x; q < S; q += gridDim.x * 256)
+        if (ang[q] >= 0.f) {
+            const int b = lsd_bin(dabc[q], coef);
+            const unsigned pos = bin_start[b] + atomicAdd(&cursor[b], 1u);
+            seed_pix[pos] = q;
+            seed_prio[pos] = make_prio(n_bins - 1 - b, q);
+        }
+}
+
+// ---- region growing: persistent cooperative kernel, one thread per seed per round (see lsd_core.h) ----------
+struct LsdRegion { u64 prio; unsigned off; int count; double reg_angle; };
+struct GrowState {
+    GrowArgs A;
+    const int* seed_pix; const u64* seed_prio;
+    unsigned* head[2]; int* cnt[2]; double* regang;
+    const LsdPlan* plan;
+    unsigned* changed;          // [max_rounds] zero-initialised
+    unsigned max_rounds;
+    int min_reg_size;
+    unsigned* final_pool; unsigned* final_ctr;
+    LsdRegion* regs; unsigned* nreg; unsigned reg_cap;
+    int* status;                // [0] error flag, [1] rounds used, [2] waves
+};
+
+__global__ void __launch_bounds__(256) k_lsd_grow(const GrowState G) {
+    cg::grid_group grid = cg::this_grid();
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int n_waves = G.plan->n_waves;
+    unsigned round = 1;
+    for (int wv = 0; wv < n_waves; ++wv) {
+        const int lo = G.plan->wave_start[wv], hi = G.plan->wave_start[wv + 1];
+        for (int i = lo + tid; i < hi; i += nth) { G.cnt[0][i] = 0; G.cnt[1][i] = 0; }
+        for (;;) {
+            if (tid == 0) *G.A.pool_ctr[round & 1] = 0;
+            grid.sync();
+            bool any_change = false;
+            for (int i = lo + tid; i < hi; i += nth) {
+                const GrowResult r = grow_seed(G.A, round, G.seed_pix[i], G.seed_prio[i], G.head[(round - 1) & 1][i], G.cnt[(round - 1) & 1][i]);
+                G.head[round & 1][i] = r.head; G.cnt[round & 1][i] = r.count; G.regang[i] = r.reg_angle;
+                if (r.overflow) G.status[0] = OLF_ERR_CAPACITY;
+                any_change |= !r.same_as_prev;
+            }
+            if (__syncthreads_or(any_change) && threadIdx.x == 0) G.changed[round] = 1;
+            __threadfence();
+            grid.sync();
+            const bool changed = ((volatile unsigned*)G.changed)[round] != 0;
+            if (!changed || round + 2 >= G.max_rounds || ((volatile int*)G.status)[0] != 0) break;
+            ++round;
+        }
+        // finalise the wave: stamp the regions for good, keep the pixel lists of accepted regions
+        for (int i = lo + tid; i < hi; i += nth) {
+            const int c = G.cnt[round & 1][i];
+            if (c == 0) continue;
+            const u64 prio = G.seed_prio[i];
+            const bool accept = c >= G.min_reg_size;
+            unsigned off = 0;
+            if (accept) off = atomicAdd(G.final_ctr, (unsigned)c);
+            ListReader rd; rd.init(G.A.pool[round & 1], G.head[round & 1][i]);
+            for (int k = 0; k < c; ++k) {
+                const unsigned p = rd.next();
+                G.A.claim[0][p] = prio; G.A.claim[1][p] = prio;
+                if (accept) G.final_pool[off + k] = p;
+            }
+            if (accept) {
+                const unsigned r = atomicAdd(G.nreg, 1u);
+                if (r < G.reg_cap) { LsdRegion R; R.prio = prio; R.off = off; R.count = c; R.reg_angle = G.regang[i]; G.regs[r] = R; }
+                else G.status[0] = OLF_ERR_CAPACITY;
+            }
+        }
+        ++round;
+        __threadfence();
+        grid.sync();
+        if (((volatile int*)G.status)[0] != 0) break;
+    }
+    if (tid == 0) { G.status[1] = (int)round; G.status[2] = n_waves; }
+}
+
+// ---- region2rect ---------------------------------------------------------------------------
+struct RectRec { double x, y, theta; u64 prio; };
+__global__ void __launch_bounds__(128) k_lsd_rect_a(const LsdRegion* __restrict__ regs, const unsigned* __restrict__ nreg, unsigned cap,
+                                                    const unsigned* __restrict__ final_pool, const short2_t* __restrict__ dabc, int W,
+                                                    double prec, RectRec* __restrict__ out_host) {
+    const unsigned n = min(*nreg, cap);
+    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const LsdRegion R = regs[r];
+    const RectA a = region_rect_a(final_pool + R.off, R.count, dabc, W, R.reg_angle, prec);
+    RectRec o; o.x = a.x; o.y = a.y; o.theta = a.theta; o.prio = R.prio;
+    out_host[r] = o;
+}
+// warp per region: extreme projections on the (host-libm) direction -> segment end points (Vec4f)
+__global__ void __launch_bounds__(256) k_lsd_rect_b(const LsdRegion* __restrict__ regs, int n, const unsigned* __restrict__ final_pool, int W,
+                                                    const RectRec* __restrict__ rect, const double2* __restrict__ dir, double scale,
+                                                    float4* __restrict__ seg_host) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const LsdRegion R = regs[r];
+    const double cx = rect[r].x, cy = rect[r].y, dx = dir[r].x, dy = dir[r].y;
+    double l_min = 0, l_max = 0;
+    for (int k = lane; k < R.count; k += 32) {
+        const double l = region_proj(final_pool[R.off + k], W, cx, cy, dx, dy);
+        l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        l_max = fmax(l_max, __shfl_xor_sync(0xffffffffu, l_max, o));
+        l_min = fmin(l_min, __shfl_xor_sync(0xffffffffu, l_min, o));
+    }
+    if (lane == 0) {
+        double v[4] = {__dadd_rn(cx, __dmul_rn(l_min, dx)), __dadd_rn(cy, __dmul_rn(l_min, dy)),
+                       __dadd_rn(cx, __dmul_rn(l_max, dx)), __dadd_rn(cy, __dmul_rn(l_max, dy))};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = __dadd_rn(v[k], 0.5); if (scale != 1.0) v[k] = __ddiv_rn(v[k], scale); }
+        seg_host[r] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+    }
+}
+
+// ---- LBD (binary_descriptor_custom.cpp:350-412, 1026-1372) ---------------------------------------------------------
+// cv::Sobel 8U->16S ksize 3, BORDER_REFLECT_101; dx and dy packed as short2 per pixel
+__global__ void __launch_bounds__(256) k_sobel3(const uint8_t* __restrict__ img, int w, int h, int pitch, short2_t* __restrict__ out) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    const uint8_t* a = img + (size_t)reflect101(y - 1, h) * pitch;
+    const uint8_t* b = img + (size_t)y * pitch;
+    const uint8_t* c = img + (size_t)reflect101(y + 1, h) * pitch;
+    short2_t o;
+    o.x = (short)((a[xp] - a[xm]) + 2 * (b[xp] - b[xm]) + (c[xp] - c[xm]));
+    o.y = (short)((c[xm] + 2 * c[x] + c[xp]) - (a[xm] + 2 * a[x] + a[xp]));
+    out[(size_t)y * w + x] = o;
+}
+
+struct LbdLine { float sx, sy, ex, ey, dL0, dL1; int num_px; };      // dL = (float)cos/sin((double)angle), host libm
+__constant__ float c_gaussG[63];
+__constant__ float c_gaussL[21];
+
+// thread per (line, row of the line support region): the reference's sequential float sums along the row (:1146-1186)
+__global__ void __launch_bounds__(256) k_lbd_rows(const LbdLine* __restrict__ lines, int n, const short2_t* __restrict__ grad,
+                                                  int imw, int imh, float4* __restrict__ rowsum) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 63) return;
+    const int li = t / 63, hID = t % 63;
+    const LbdLine L = lines[li];
+    const short imageWidth = (short)(imw - 1), imageHeight = (short)(imh - 1);
+    const short lengthOfLSP = (short)L.num_px;
+    const short halfWidth = (lengthOfLSP - 1) / 2, halfHeight = 31;
+    const float midX = fmul(fadd(L.sx, L.ex), 0.5f), midY = fmul(fadd(L.sy, L.ey), 0.5f);
+    const float dO0 = -L.dL1, dO1 = L.dL0;
+    float sCorX0 = fadd(fadd(fmul(-L.dL0, (float)halfWidth), fmul(L.dL1, (float)halfHeight)), midX);
+    float sCorY0 = fadd(fsub(fmul(-L.dL1, (float)halfWidth), fmul(L.dL0, (float)halfHeight)), midY);
+    for (int r = 0; r < hID; ++r) { sCorX0 = fsub(sCorX0, L.dL1); sCorY0 = fadd(sCorY0, L.dL0); }
+    float sCorX = sCorX0, sCorY = sCorY0;
+    float pL = 0, nL = 0, pO = 0, nO = 0;
+    for (short wID = 0; wID < lengthOfLSP; wID++) {
+        short tc = (short)(int)roundf(sCorX);
+        const short xCor = (tc < 0) ? 0 : (tc > imageWidth) ? imageWidth : tc;
+        tc = (short)(int)roundf(sCorY);
+        const short yCor = (tc < 0) ? 0 : (tc > imageHeight) ? imageHeight : tc;
+        const short2_t g = grad[(size_t)yCor * imw + xCor];
+        const float gDL = fadd(fmul((float)g.x, L.dL0), fmul((float)g.y, L.dL1));
+        const float gDO = fadd(fmul((float)g.x, dO0), fmul((float)g.y, dO1));
+        if (gDL > 0) pL = fadd(pL, gDL); else nL = fsub(nL, gDL);
+        if (gDO > 0) pO = fadd(pO, gDO); else nO = fsub(nO, gDO);
+        sCorX = fadd(sCorX, L.dL0);
+        sCorY = fadd(sCorY, L.dL1);
+    }
+    rowsum[t] = make_float4(pL, nL, pO, nO);
+}
+
+__constant__ unsigned char c_lbd_comb[64];
+// thread per line: fold the 63 rows into 9 bands in reference order, mean/std, normalise, clamp, binarise (:1188-1341, :401-412)
+__global__ void __launch_bounds__(64) k_lbd_fold(const float4* __restrict__ rowsum, int n, uint8_t* __restrict__ desc_host) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    float band[8][9];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int b = 0; b < 9; ++b) band[k][b] = 0.f;
+    auto fold = [&](int b, float c, float pL, float nL, float pL2, float nL2, float pO, float nO, float pO2, float nO2) {
+        const float cc = fmul(c, c);
+        band[0][b] = fadd(band[0][b], fmul(c, pL));  band[1][b] = fadd(band[1][b], fmul(c, nL));
+        band[2][b] = fadd(band[2][b], fmul(cc, pL2)); band[3][b] = fadd(band[3][b], fmul(cc, nL2));
+        band[4][b] = fadd(band[4][b], fmul(c, pO));  band[5][b] = fadd(band[5][b], fmul(c, nO));
+        band[6][b] = fadd(band[6][b], fmul(cc, pO2)); band[7][b] = fadd(band[7][b], fmul(cc, nO2));
+    };
+#pragma unroll 1
+    for (int hID = 0; hID < 63; ++hID) {
+        const float4 rs = rowsum[(size_t)li * 63 + hID];
+        const float cg_ = c_gaussG[hID];
+        const float pL = fmul(cg_, rs.x), nL = fmul(cg_, rs.y), pO = fmul(cg_, rs.z), nO = fmul(cg_, rs.w);
+        const float pL2 = fmul(pL, pL), nL2 = fmul(nL, nL), pO2 = fmul(pO, pO), nO2 = fmul(nO, nO);
+        const int b = hID / 7, m = hID % 7;
+        // dynamic band index -> keep the register array addressable with a switch-free loop
+#pragma unroll
+        for (int bb = 0; bb < 9; ++bb) {
+            if (bb == b) fold(bb, c_gaussL[m + 7], pL, nL, pL2, nL2, pO, nO, pO2, nO2);
+        }
+#pragma unroll
+        for (int bb = 0; bb < 9; ++bb) {
+            if (bb == b - 1) fold(bb, c_gaussL[m + 14], pL, nL, pL2, nL2, pO, nO, pO2, nO2);
+        }
+#pragma unroll
+        for (int bb = 0; bb < 9; ++bb) {
+            if (bb == b + 1) fold(bb, c_gaussL[m], pL, nL, pL2, nL2, pO, nO, pO2, nO2);
+        }
+    }
+    float des[72];
+    const float invN2 = (float)(1.0 / 14.0), invN3 = (float)(1.0 / 21.0);
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const float invN = (b == 0 || b == 8) ? invN2 : invN3;
+        float t = fmul(band[0][b], invN);
+        des[b * 8] = t;     des[b * 8 + 4] = __fsqrt_rn(fsub(fmul(band[2][b], invN), fmul(t, t)));
+        t = fmul(band[1][b], invN);
+        des[b * 8 + 1] = t; des[b * 8 + 5] = __fsqrt_rn(fsub(fmul(band[3][b], invN), fmul(t, t)));
+        t = fmul(band[4][b], invN);
+        des[b * 8 + 2] = t; des[b * 8 + 6] = __fsqrt_rn(fsub(fmul(band[6][b], invN), fmul(t, t)));
+        t = fmul(band[5][b], invN);
+        des[b * 8 + 3] = t; des[b * 8 + 7] = __fsqrt_rn(fsub(fmul(band[7][b], invN), fmul(t, t)));
+    }
+    float tM = 0, tS = 0;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tM = fadd(tM, fmul(des[b * 8 + k], des[b * 8 + k]));
+#pragma unroll
+        for (int k = 4; k < 8; ++k) tS = fadd(tS, fmul(des[b * 8 + k], des[b * 8 + k]));
+    }
+    tM = fdiv(1.f, __fsqrt_rn(tM));
+    tS = fdiv(1.f, __fsqrt_rn(tS));
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) des[b * 8 + k] = fmul(des[b * 8 + k], tM);
+#pragma unroll
+        for (int k = 4; k < 8; ++k) des[b * 8 + k] = fmul(des[b * 8 + k], tS);
+    }
+#pragma unroll
+    for (int i = 0; i < 72; ++i) if ((double)des[i] > 0.4) des[i] = (float)0.4;
+    float t = 0;
+#pragma unroll
+    for (int i = 0; i < 72; ++i) t = fadd(t, fmul(des[i], des[i]));
+    t = fdiv(1.f, __fsqrt_rn(t));
+#pragma unroll
+    for (int i = 0; i < 72; ++i) des[i] = fmul(des[i], t);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const int a = c_lbd_comb[2 * c], b = c_lbd_comb[2 * c + 1];
+        unsigned r = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // a, b are compile-time unknown: select through unrolled compares to keep des[] in registers
+            float fa = 0.f, fb = 0.f;
+#pragma unroll
+            for (int bb = 0; bb < 9; ++bb) { if (bb == a) fa = des[bb * 8 + i]; if (bb == b) fb = des[bb * 8 + i]; }
+            if (fa > fb) r += (1u << i);
+        }
+        desc_host[(size_t)li * 32 + c] = (uint8_t)r;
+    }
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+static const unsigned char LBD_COMB[64] = {0,1, 0,2, 0,3, 0,4, 0,5, 0,6, 1,2, 1,3, 1,4, 1,5, 1,6, 2,3, 2,4, 2,5, 2,6, 2,7,
+                                           2,8, 3,4, 3,5, 3,6, 3,7, 3,8, 4,5, 4,6, 4,7, 4,8, 5,6, 5,7, 5,8, 6,7, 6,8, 7,8};
+
+struct LineImpl {
+    int device = 0;
+    olf_line_params P;
+    cudaStream_t stream = nullptr;
+    // derived LSD constants
+    double prec, rho; int n2_thresh; int blur_k; int blur_q[4];
+    // size-dependent
+    int img_w = 0, img_h = 0, ipitch = 0, W = 0, H = 0, wpitch = 0, S = 0, min_reg_size = 0;
+    PinBuf<uint8_t> img_stage;
+    DevBuf<uint8_t> img, blurred, scaled, lbd_blur;
+    DevBuf<ExCoef> coef; size_t coef_y_off = 0;
+    DevBuf<float> ang; DevBuf<short2_t> dabc;
+    DevBuf<u64> claim0, claim1, seed_prio;
+    DevBuf<int> seed_pix, cnt0, cnt1, n2max, status;
+    DevBuf<unsigned> head0, head1, hist, bin_start, cursor, pool0, pool1, ctrs, changed, final_pool;
+    DevBuf<double> regang;
+    DevBuf<LsdPlan> plan;
+    DevBuf<LsdRegion> regs;
+    DevBuf<float2_t> tab_seed, tab_acc;
+    unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
+    int grow_blocks = 0;
+    PinBuf<RectRec> rect_host; PinBuf<double2> dir_host; PinBuf<float4> seg_host; PinBuf<int> status_host; PinBuf<unsigned> nreg_host;
+    // LBD
+    DevBuf<short2_t> grad;
+    PinBuf<LbdLine> lbd_lines; DevBuf<float4> rowsum; PinBuf<uint8_t> desc_host;
+    int lbd_cap = 0;
+    int last_stats[8] = {0};
+};
+
+static void build_exact_coefs(int src, int dst, double scale, std::vector<ExCoef>& out) {
+    out.resize(dst);
+    for (int d = 0; d < dst; ++d) {
+        const double s = (d + 0.5) / scale - 0.5;
+        if (s < 0) { out[d] = {0, 256, 0}; continue; }
+        if (s >= src - 1) { out[d] = {src - 1, 256, 0}; continue; }
+        const int o = (int)std::floor(s);
+        const int c1 = (int)lrint((s - o) * 256.0);
+        out[d] = {o, 256 - c1, c1};
+    }
+}
+static void gauss_kernel_q8(int n, double sigma, int* q) {
+    std::vector<double> k(n);
+    double sum = 0, c = (n - 1) * 0.5;
+    for (int i = 0; i < n; ++i) { const double x = i - c; k[i] = std::exp(-(x * x) / (2.0 * sigma * sigma)); sum += k[i]; }
+    double carry = 0; int acc = 0;
+    for (int i = 0; i < n / 2; ++i) {
+        const double adj = k[i] / sum * 256.0 + carry;
+        const int v = (int)lrint(adj);
+        carry = adj - v; q[i] = v; acc += 2 * v;
+    }
+    q[n / 2] = 256 - acc;
+}
+
+LineImpl* line_create(const olf_line_params* p, int device) {
+    if (!p || p->lsd_refine != 0 || p->lsd_n_bins < 1 || p->lsd_n_bins > 1024 || p->lsd_scale <= 0 || p->lsd_ang_th <= 0 || p->lsd_ang_th >= 180) {
+        set_last_error("olf_line_create: unsupported parameters (refine must be 0, n_bins <= 1024)"); return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        set_last_error("olf_line_create: no such CUDA device (this library has no CPU path)"); return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return nullptr; }
+    LineImpl* h = new LineImpl();
+    h->device = device; h->P = *p;
+    h->prec = M_PI * p->lsd_ang_th / 180.0;
+    h->rho = p->lsd_quant / std::sin(h->prec);
+    // smallest integer n2 with sqrt(n2/4.0) > rho  (norm <= rho -> NOTDEF)
+    { int v = 0; while (v < (1 << 20) && std::sqrt(v / 4.0) <= h->rho) ++v; h->n2_thresh = std::max(v, 1); }
+    if (p->lsd_scale != 1.0) {
+        const double sigma = (p->lsd_scale < 1) ? (p->lsd_sigma_scale / p->lsd_scale) : p->lsd_sigma_scale;
+        const unsigned hk = (unsigned)(std::ceil(sigma * std::sqrt(2 * 3.0 * std::log(10.0))));
+        h->blur_k = 1 + 2 * (int)hk;
+        if (h->blur_k != 7 && h->blur_k != 5 && h->blur_k != 3) { set_last_error("olf_line_create: unsupported LSD pre-blur kernel size"); delete h; return nullptr; }
+        int q[8] = {0}; gauss_kernel_q8(h->blur_k, sigma, q);
+        for (int i = 0; i < 4; ++i) h->blur_q[i] = q[i];
+    } else h->blur_k = 0;
+    // trig tables keyed by (DA, BC), from host libm; 2 x 2 MB
+    std::vector<float2_t> ts((size_t)kTabDim * kTabDim), ta((size_t)kTabDim * kTabDim);
+    for (int DA = -255; DA <= 255; ++DA)
+        for (int BC = -255; BC <= 255; ++BC) {
+            const int gx = DA + BC, gy = DA - BC;
+            // host restatement of cv::fastAtan2 (identical source to the device one)
+            const double a = (double)olf::lsd::fast_atan2_deg((float)gx, (float)-gy) * kDegToRads;
+            const size_t i = (size_t)(DA + 255) * kTabDim + (BC + 255);
+            ts[i] = float2_t{(float)std::cos(a), (float)std::sin(a)};
+            ta[i] = float2_t{(float)std::cos((double)(float)a), (float)std::sin((double)(float)a)};
+        }
+    // LBD weights (BinaryDescriptor ctor :217-259, integer divisions preserved)
+    float gG[63], gL[21];
+    {
+        const int wb = 7, nb = 9;
+        double u = (wb * 3 - 1) / 2, sigma = (wb * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < wb * 3; i++) { const double dis = i - u; gL[i] = (float)std::exp(dis * dis * inv); }
+        u = (nb * wb - 1) / 2; sigma = u; inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < nb * wb; i++) { const double dis = i - u; gG[i] = (float)std::exp(dis * dis * inv); }
+    }
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && h->tab_seed.ensure(ts.size()) == OLF_OK && h->tab_acc.ensure(ta.size()) == OLF_OK;
+    ok = ok && cudaMemcpy(h->tab_seed.p, ts.data(), ts.size() * sizeof(float2_t), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->tab_acc.p, ta.data(), ta.size() * sizeof(float2_t), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpyToSymbol(c_gaussG, gG, sizeof(gG)) == cudaSuccess && cudaMemcpyToSymbol(c_gaussL, gL, sizeof(gL)) == cudaSuccess;
+    ok = ok && cudaMemcpyToSymbol(c_lbd_comb, LBD_COMB, sizeof(LBD_COMB)) == cudaSuccess;
+    int coop = 0, sms = 0, per_sm = 0;
+    ok = ok && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && coop;
+    ok = ok && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_grow, 256, 0) == cudaSuccess && per_sm > 0;
+    if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
+    h->grow_blocks = sms * std::min(per_sm, 2);
+    return h;
+}
+
+void line_destroy(LineImpl* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->img_stage.release(); h->img.release(); h->blurred.release(); h->scaled.release(); h->lbd_blur.release(); h->coef.release();
+    h->ang.release(); h->dabc.release(); h->claim0.release(); h->claim1.release(); h->seed_prio.release(); h->seed_pix.release();
+    h->cnt0.release(); h->cnt1.release(); h->n2max.release(); h->status.release(); h->head0.release(); h->head1.release();
+    h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool0.release(); h->pool1.release(); h->ctrs.release();
+    h->changed.release(); h->final_pool.release(); h->regang.release(); h->plan.release(); h->regs.release();
+    h->tab_seed.release(); h->tab_acc.release(); h->rect_host.release(); h->dir_host.release(); h->seg_host.release();
+    h->status_host.release(); h->nreg_host.release(); h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
+    delete h;
+}
+
+static int line_ensure_size(LineImpl* h, int w, int hgt) {
+    if (h->img_w == w && h->img_h == hgt) return OLF_OK;
+    int rc;
+    const double sc = h->P.lsd_scale;
+    h->ipitch = align_up(w, 64);
+    h->W = (sc != 1.0) ? (int)lrint(w * sc) : w;
+    h->H = (sc != 1.0) ? (int)lrint(hgt * sc) : hgt;
+    if (h->W < 3 || h->H < 3) { set_last_error("image too small for LSD"); return OLF_ERR_ARG; }
+    h->wpitch = align_up(h->W, 64);
+    h->S = h->W * h->H;
+    const double logNT = 5 * (std::log10((double)h->W) + std::log10((double)h->H)) / 2 + std::log10(11.0);
+    h->min_reg_size = (int)(unsigned)(-logNT / std::log10(h->P.lsd_ang_th / 180.0));
+    const size_t ib = (size_t)h->ipitch * hgt + 256, wb = (size_t)h->wpitch * h->H + 256, S = h->S;
+    if ((rc = h->img_stage.ensure((size_t)w * hgt)) || (rc = h->img.ensure(ib)) || (rc = h->blurred.ensure(ib)) || (rc = h->lbd_blur.ensure(ib)) ||
+        (rc = h->scaled.ensure(wb)) || (rc = h->grad.ensure((size_t)w * hgt))) return rc;
+    std::vector<ExCoef> cx, cy;
+    build_exact_coefs(w, h->W, sc, cx); build_exact_coefs(hgt, h->H, sc, cy);
+    h->coef_y_off = cx.size();
+    cx.insert(cx.end(), cy.begin(), cy.end());
+    if ((rc = h->coef.ensure(cx.size()))) return rc;
+    OLF_CUDA(cudaMemcpy(h->coef.p, cx.data(), cx.size() * sizeof(ExCoef), cudaMemcpyHostToDevice));
+    h->pool_chunks = (unsigned)std::max<size_t>(S / 2, 1u << 16);       // 16 px of list space per image pixel per round
+    h->reg_cap = (unsigned)(S / std::max(h->min_reg_size, 1) + 16);
+    if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || (rc = h->claim0.ensure(S)) || (rc = h->claim1.ensure(S)) ||
+        (rc = h->seed_prio.ensure(S)) || (rc = h->seed_pix.ensure(S)) || (rc = h->cnt0.ensure(S)) || (rc = h->cnt1.ensure(S)) ||
+        (rc = h->head0.ensure(S)) || (rc = h->head1.ensure(S)) || (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) ||
+        (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
+        (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->changed.ensure(h->max_rounds)) || (rc = h->plan.ensure(1)) ||
+        (rc = h->pool0.ensure((size_t)h->pool_chunks * kChunk)) || (rc = h->pool1.ensure((size_t)h->pool_chunks * kChunk)) ||
+        (rc = h->regs.ensure(h->reg_cap)) || (rc = h->rect_host.ensure(h->reg_cap)) || (rc = h->dir_host.ensure(h->reg_cap)) ||
+        (rc = h->seg_host.ensure(h->reg_cap)) || (rc = h->status_host.ensure(4)) || (rc = h->nreg_host.ensure(1))) return rc;
+    h->img_w = w; h->img_h = hgt;
+    return OLF_OK;
+}
+
+static LevelTable single_level(int w, int hgt, int pitch) {
+    LevelTable T; memset(&T, 0, sizeof(T));
+    T.n = 1; T.w[0] = w; T.h[0] = hgt; T.pitch[0] = pitch; T.off[0] = 0;
+    T.tiles_x[0] = (w + TILE_W - 1) / TILE_W; T.tile_start[0] = 0;
+    T.tile_start[1] = T.tiles_x[0] * ((hgt + TILE_H - 1) / TILE_H);
+    return T;
+}
+
+static int line_upload(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device) {
+    int rc = line_ensure_size(h, w, hgt);
+    if (rc) return rc;
+    if (on_device) OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, img, stride, w, hgt, cudaMemcpyDeviceToDevice, h->stream));
+    else {
+        for (int y = 0; y < hgt; ++y) memcpy(h->img_stage.p + (size_t)y * w, img + (size_t)y * stride, w);
+        OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, h->img_stage.p, w, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    }
+    return OLF_OK;
+}
+
+// LSD on the uploaded image; returns segments sorted in seed order (host vector)
+static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
+    cudaStream_t s = h->stream;
+    const int w = h->img_w, hgt = h->img_h, W = h->W, H = h->H, S = h->S;
+    const uint8_t* work = h->img.p; int wp = h->ipitch;
+    if (h->blur_k) {
+        const LevelTable T = single_level(w, hgt, h->ipitch);
+        const int nt = T.tile_start[1];
+        if (h->blur_k == 7) k_blur_q8<7><<<nt, 256, 0, s>>>(h->img.p, h->blurred.p, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], h->blur_q[3]);
+        else if (h->blur_k == 5) k_blur_q8<5><<<nt, 256, 0, s>>>(h->img.p, h->blurred.p, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], 0);
+        else k_blur_q8<3><<<nt, 256, 0, s>>>(h->img.p, h->blurred.p, T, h->blur_q[0], h->blur_q[1], 0, 0);
+        dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+        k_resize_exact<<<g, b, 0, s>>>(h->blurred.p, w, hgt, h->ipitch, h->scaled.p, W, H, h->wpitch, h->coef.p, h->coef.p + h->coef_y_off);
+        work = h->scaled.p; wp = h->wpitch;
+    }
+    OLF_CUDA(cudaMemsetAsync(h->n2max.p, 0, sizeof(int), s));
+    OLF_CUDA(cudaMemsetAsync(h->hist.p, 0, 1024 * sizeof(unsigned), s));
+    OLF_CUDA(cudaMemsetAsync(h->ctrs.p, 0, 4 * sizeof(unsigned), s));
+    OLF_CUDA(cudaMemsetAsync(h->status.p, 0, 4 * sizeof(int), s));
+    OLF_CUDA(cudaMemsetAsync(h->changed.p, 0, h->max_rounds * sizeof(unsigned), s));
+    {
+        dim3 g((W + 31) / 32, (H + 7) / 8);
+        k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->claim0.p, h->claim1.p, h->n2max.p);
+    }
+    const int nb = h->P.lsd_n_bins;
+    k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
+    k_lsd_plan<<<1, 32, 0, s>>>(h->hist.p, nb, 2048, h->bin_start.p, h->cursor.p, h->plan.p);
+    k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p);
+    GrowState G;
+    G.A.W = W; G.A.H = H; G.A.ang = h->ang.p; G.A.dabc = h->dabc.p; G.A.tab_seed = h->tab_seed.p; G.A.tab_acc = h->tab_acc.p;
+    G.A.claim[0] = h->claim0.p; G.A.claim[1] = h->claim1.p; G.A.pool[0] = h->pool0.p; G.A.pool[1] = h->pool1.p;
+    G.A.pool_ctr[0] = h->ctrs.p; G.A.pool_ctr[1] = h->ctrs.p + 1; G.A.pool_chunks = h->pool_chunks; G.A.prec = h->prec;
+    G.seed_pix = h->seed_pix.p; G.seed_prio = h->seed_prio.p;
+    G.head[0] = h->head0.p; G.head[1] = h->head1.p; G.cnt[0] = h->cnt0.p; G.cnt[1] = h->cnt1.p; G.regang = h->regang.p;
+    G.plan = h->plan.p; G.changed = h->changed.p; G.max_rounds = h->max_rounds; G.min_reg_size = h->min_reg_size;
+    G.final_pool = h->final_pool.p; G.final_ctr = h->ctrs.p + 2; G.regs = h->regs.p; G.nreg = h->ctrs.p + 3; G.reg_cap = h->reg_cap;
+    G.status = h->status.p;
+    void* args[] = {(void*)&G};
+    OLF_CUDA(cudaLaunchCooperativeKernel((const void*)k_lsd_grow, dim3(h->grow_blocks), dim3(256), args, 0, s));
+    k_lsd_rect_a<<<(h->reg_cap + 127) / 128, 128, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
+    OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(cudaStreamSynchronize(s));
+    h->last_stats[0] = h->status_host.p[1]; h->last_stats[1] = h->status_host.p[2];
+    if (h->status_host.p[0] != 0) { set_last_error("LSD region growing: internal pool overflow"); return OLF_ERR_CAPACITY; }
+    if (h->status_host.p[1] + 2 >= (int)h->max_rounds) { set_last_error("LSD region growing did not converge"); return OLF_ERR_INTERNAL; }
+    const int n = (int)*h->nreg_host.p;
+    h->last_stats[2] = n;
+    segs.clear();
+    if (n == 0) return OLF_OK;
+    // libm cos/sin of the O(#regions) rectangle angles, then the projection pass on the device
+    for (int i = 0; i < n; ++i) { const double t = h->rect_host.p[i].theta; h->dir_host.p[i] = make_double2(std::cos(t), std::sin(t)); }
+    k_lsd_rect_b<<<(n + 7) / 8, 256, 0, s>>>(h->regs.p, n, h->final_pool.p, W, h->rect_host.d, h->dir_host.d, h->P.lsd_scale, h->seg_host.d);
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(cudaStreamSynchronize(s));
+    // seed order = ascending priority key
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    const RectRec* rr = h->rect_host.p;
+    std::sort(order.begin(), order.end(), [rr](int a, int b) { return rr[a].prio < rr[b].prio; });
+    segs.resize(n);
+    for (int i = 0; i < n; ++i) segs[i] = h->seg_host.p[order[i]];
+    return OLF_OK;
+}
+
+// checkLineExtremes + KeyLine construction (LSDDetector_custom.cpp:76-102, 264-308), numOctaves = 1
+static void make_keylines(const std::vector<float4>& segs, int w, int hgt, double min_length, std::vector<olf_keyline>& out) {
+    out.clear();
+    int class_counter = -1;
+    for (const float4& sg : segs) {
+        float e[4] = {sg.x, sg.y, sg.z, sg.w};
+        if (e[0] < 0) e[0] = 0;
+        if (e[0] >= w) e[0] = (float)w - 1.0f;
+        if (e[2] < 0) e[2] = 0;
+        if (e[2] >= w) e[2] = (float)w - 1.0f;
+        if (e[1] < 0) e[1] = 0;
+        if (e[1] >= hgt) e[1] = (float)hgt - 1.0f;
+        if (e[3] < 0) e[3] = 0;
+        if (e[3] >= hgt) e[3] = (float)hgt - 1.0f;
+        const double length = (float)std::sqrt(std::pow((double)(e[0] - e[2]), 2) + std::pow((double)(e[1] - e[3]), 2));
+        if (!(length > min_length)) continue;
+        olf_keyline kl;
+        kl.startPointX = e[0]; kl.startPointY = e[1]; kl.endPointX = e[2]; kl.endPointY = e[3];
+        kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1]; kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
+        kl.lineLength = (float)length;
+        const int x1 = (int)lrintf(e[0]), y1 = (int)lrintf(e[1]), x2 = (int)lrintf(e[2]), y2 = (int)lrintf(e[3]);
+        kl.numOfPixels = std::max(std::abs(x2 - x1), std::abs(y2 - y1)) + 1;        // cv::LineIterator(...).count, 8-connected
+        kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+        kl.class_id = ++class_counter;
+        kl.octave = 0;
+        kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);
+        kl.response = kl.lineLength / (float)std::max(w, hgt);
+        kl.pt_x = (kl.endPointX + kl.startPointX) / 2; kl.pt_y = (kl.endPointY + kl.startPointY) / 2;
+        out.push_back(kl);
+    }
+}
+
+// LBD of `n` keylines on the uploaded image: blur 5x5 sigma 1 + Sobel, row sums, fold + binarise
+static int lbd_run(LineImpl* h, const olf_keyline* kls, int n, uint8_t* desc) {
+    if (n == 0) return OLF_OK;
+    cudaStream_t s = h->stream;
+    const int w = h->img_w, hgt = h->img_h;
+    int rc;
+    if (n > h->lbd_cap) {
+        const int cap = std::max(2 * n, 1024);
+        if ((rc = h->lbd_lines.ensure(cap)) || (rc = h->rowsum.ensure((size_t)cap * 63)) || (rc = h->desc_host.ensure((size_t)cap * 32))) return rc;
+        h->lbd_cap = cap;
+    }
+    for (int i = 0; i < n; ++i) {
+        const olf_keyline& k = kls[i];
+        LbdLine L;
+        L.sx = k.sPointInOctaveX; L.sy = k.sPointInOctaveY; L.ex = k.ePointInOctaveX; L.ey = k.ePointInOctaveY;
+        L.dL0 = (float)std::cos((double)k.angle); L.dL1 = (float)std::sin((double)k.angle);       // :1130-1131
+        L.num_px = k.numOfPixels;
+        h->lbd_lines.p[i] = L;
+    }
+    const LevelTable T = single_level(w, hgt, h->ipitch);
+    k_blur_q8<5><<<T.tile_start[1], 256, 0, s>>>(h->img.p, h->lbd_blur.p, T, 14, 62, 104, 0);       // 5x5 sigma 1 (:358)
+    dim3 g((w + 31) / 32, (hgt + 7) / 8);
+    k_sobel3<<<g, 256, 0, s>>>(h->lbd_blur.p, w, hgt, h->ipitch, h->grad.p);
+    k_lbd_rows<<<(n * 63 + 255) / 256, 256, 0, s>>>(h->lbd_lines.d, n, h->grad.p, w, hgt, h->rowsum.p);
+    k_lbd_fold<<<(n + 63) / 64, 64, 0, s>>>(h->rowsum.p, n, h->desc_host.d);
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(cudaStreamSynchronize(s));
+    memcpy(desc, h->desc_host.p, (size_t)n * 32);
+    return OLF_OK;
+}
+
+int line_lsd_detect(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, float* segs, int cap, int* n) {
+    if (!h || !img || !n || w <= 0 || hgt <= 0 || stride < w) { set_last_error("olf_lsd_detect: bad arguments"); return OLF_ERR_ARG; }
+    OLF_CUDA(cudaSetDevice(h->device));
+    int rc = line_upload(h, img, w, hgt, stride, on_device);
+    if (rc) return rc;
+    std::vector<float4> sg;
+    if ((rc = lsd_run(h, sg))) return rc;
+    *n = (int)sg.size();
+    if (*n > cap) { set_last_error("olf_lsd_detect: segment capacity too small"); return OLF_ERR_CAPACITY; }
+    if (*n) memcpy(segs, sg.data(), sg.size() * sizeof(float4));
+    return OLF_OK;
+}
+
+int line_lbd_compute(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, const olf_keyline* kls, int n, uint8_t* desc) {
+    if (!h || !img || w <= 0 || hgt <= 0 || stride < w || n < 0) { set_last_error("olf_lbd_compute: bad arguments"); return OLF_ERR_ARG; }
+    if (n == 0) return OLF_OK;                           // "keypoint list is empty": descriptors untouched (:556-560)
+    OLF_CUDA(cudaSetDevice(h->device));
+    int rc = line_upload(h, img, w, hgt, stride, false);
+    if (rc) return rc;
+    return lbd_run(h, kls, n, desc);
+}
+
+// Lineextractor::operator() (src/LineExtractor.cc:31-67)
+int line_extract(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, olf_keyline* kls, uint8_t* desc, int cap, int* n) {
+    if (!h || !img || !n || w <= 0 || hgt <= 0 || stride < w) { set_last_error("olf_line_extract: bad arguments"); return OLF_ERR_ARG; }
+    *n = 0;
+    OLF_CUDA(cudaSetDevice(h->device));
+    int rc = line_upload(h, img, w, hgt, stride, on_device);
+    if (rc) return rc;
+    std::vector<float4> sg;
+    if ((rc = lsd_run(h, sg))) return rc;
+    std::vector<olf_keyline> k;
+    make_keylines(sg, w, hgt, h->P.min_line_length * std::min(w, hgt), k);
+    const int nf = h->P.lsd_nfeatures;
+    if ((int)k.size() > nf && nf != 0) {
+        // canonical: stable sort by response
+        std::stable_sort(k.begin(), k.end(), [](const olf_keyline& a, const olf_keyline& b) { return a.response > b.response; });
+        k.resize(nf);
+        for (int i = 0; i < nf; i++) k[i].class_id = i;
+    }
+    if ((int)k.size() > cap) { set_last_error("olf_line_extract: keyline capacity too small"); return OLF_ERR_CAPACITY; }
+    *n = (int)k.size();
+    if (k.empty()) return OLF_OK;
+    memcpy(kls, k.data(), k.size() * sizeof(olf_keyline));
+    return lbd_run(h, k.data(), (int)k.size(), desc);
+}
+
+void line_last_stats(const LineImpl* h, int* out8) { for (int i = 0; i < 8; ++i) out8[i] = h->last_stats[i]; }
+
+}  // namespace olf

@@ -6,24 +6,13 @@
 // between the two GPU phases; candidates and orientations reach it through mapped pinned memory (no extra copy).
 #include "common.cuh"
 #include "orb.h"
+#include "img_kernels.cuh"
 #include "../../include/olf_brief_pattern.h"
 #include <algorithm>
 #include <cmath>
 #include <list>
 
 namespace olf {
-
-// ------------------------------------------------------------------------------------------------------
-// level table passed by value to the multi-level kernels
-struct LevelTable {
-    int n;
-    int w[OLF_MAX_LEVELS], h[OLF_MAX_LEVELS], pitch[OLF_MAX_LEVELS];
-    unsigned off[OLF_MAX_LEVELS];            // byte offset of the level in the pyramid / score / blur buffers
-    int tiles_x[OLF_MAX_LEVELS], tile_start[OLF_MAX_LEVELS + 1];   // 64x16 tiles (score, blur kernels)
-    // FAST cell grid (src/ORBextractor.cc:783-789)
-    int ncols[OLF_MAX_LEVELS], nrows[OLF_MAX_LEVELS], wcell[OLF_MAX_LEVELS], hcell[OLF_MAX_LEVELS];
-    int cell_start[OLF_MAX_LEVELS + 1];
-};
 
 // ---- pyramid: cv::resize INTER_LINEAR 8UC1, one launch per level ---------------------------
 // coefficient tables (x: dst_w entries, y: dst_h entries) of {src index, c0, c1} are built on the host once per size.
@@ -46,25 +35,6 @@ __global__ void k_resize_linear(const uint8_t* __restrict__ src, int sw, int sh,
 
 // ---- FAST-9/16 threshold-free score map, all levels in one launch --------------------------
 // score = max over the 16 cyclic 9-arcs of min(d) / min(-d), minus 1; stored 0 when < min_th (never consulted then).
-#define TILE_W 64
-#define TILE_H 16
-__device__ __forceinline__ bool has_run9(unsigned m) {           // cyclic run of >= 9 set bits in a 16-bit mask
-    unsigned v = m | (m << 16);
-    unsigned r = v & (v >> 1);
-    r &= r >> 2;
-    r &= r >> 4;          // runs of 8
-    r &= v >> 8;          // runs of 9
-    return r != 0;
-}
-__device__ __forceinline__ void locate_tile(const LevelTable& T, int b, int& level, int& tx, int& ty) {
-    level = 0;
-#pragma unroll 1
-    while (level + 1 < T.n && b >= T.tile_start[level + 1]) ++level;
-    const int t = b - T.tile_start[level];
-    tx = t % T.tiles_x[level];
-    ty = t / T.tiles_x[level];
-}
-
 __global__ void __launch_bounds__(256) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
                                                     const __grid_constant__ LevelTable T, int min_th) {
     __shared__ uint8_t tile[TILE_H + 6][TILE_W + 8];
@@ -265,46 +235,6 @@ __global__ void __launch_bounds__(256) k_ic_angle(const uint8_t* __restrict__ py
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
         if (lane == 0) angle_host[k] = fast_atan2_deg((float)m01, (float)m10);
-    }
-}
-
-// ---- fixed-point separable Gaussian blur on 8U, all levels in one launch ---------------------
-// H pass 8.8 (u16), V pass 16.16, rounding (acc + 2^15) >> 16, BORDER_REFLECT_101 at the level edge.
-template <int K>
-__global__ void __launch_bounds__(256) k_blur_q8(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                 const __grid_constant__ LevelTable T, const int q0, const int q1, const int q2, const int q3) {
-    constexpr int R = K / 2;
-    __shared__ uint8_t tile[TILE_H + 2 * R][TILE_W + 2 * R + 2];
-    __shared__ uint16_t hbuf[TILE_H + 2 * R][TILE_W];
-    const int q[4] = {q0, q1, q2, q3};       // q[i] = weight at distance R-i from the centre... stored outer->centre
-    int level, tx, ty;
-    locate_tile(T, blockIdx.x, level, tx, ty);
-    const int w = T.w[level], h = T.h[level], pitch = T.pitch[level];
-    const uint8_t* img = src + T.off[level];
-    uint8_t* out = dst + T.off[level];
-    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-    for (int i = threadIdx.x; i < (TILE_H + 2 * R) * (TILE_W + 2 * R); i += 256) {
-        const int r = i / (TILE_W + 2 * R), c = i % (TILE_W + 2 * R);
-        const int gx = reflect101(min(x0 + c - R, w - 1 + R), w), gy = reflect101(min(y0 + r - R, h - 1 + R), h);
-        tile[r][c] = img[(size_t)gy * pitch + gx];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (TILE_H + 2 * R) * TILE_W; i += 256) {
-        const int r = i / TILE_W, c = i % TILE_W;
-        unsigned a = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) { const int dk = k < R ? k : K - 1 - k; a += (unsigned)q[dk] * tile[r][c + k]; }
-        hbuf[r][c] = (uint16_t)a;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < TILE_H * TILE_W; i += 256) {
-        const int r = i / TILE_W, c = i % TILE_W;
-        const int x = x0 + c, y = y0 + r;
-        if (x >= w || y >= h) continue;
-        unsigned a = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) { const int dk = k < R ? k : K - 1 - k; a += (unsigned)q[dk] * hbuf[r + k][c]; }
-        out[(size_t)y * pitch + x] = (uint8_t)((a + (1u << 15)) >> 16);
     }
 }
 

@@ -1,0 +1,79 @@
+"""GPU parity: olf_lsd_detect / olf_line_extract / olf_lbd_compute (CUDA) vs the CPU oracle.
+Segments (Vec4f), KeyLine fields and LBD descriptor bytes must be identical (north_star: bit-exact LSD indices and
+descriptor bits; end points are compared bit-exact too, which is stricter than the 1e-5 it allows)."""
+import numpy as np
+import pytest
+from orc import oracle
+import orb_line_slam_b200 as olf
+from orb_line_slam_b200 import LineParams, KEYLINE
+from orb_line_slam_b200.synth import random_image, Scene
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(320, 240, 1), (320, 240, 2), (640, 480, 3), (200, 150, 4), (97, 131, 5), (752, 480, 6), (1241, 376, 7)]
+
+
+def _segs(img, params):
+    o, g = oracle(), olf.api(0)
+    ho, hg = o.line_create(params), g.line_create(params)
+    try:
+        return o.lsd_detect(ho, img), g.lsd_detect(hg, img)
+    finally:
+        o.line_destroy(ho); g.line_destroy(hg)
+
+
+@pytest.mark.parametrize("w,h,seed", SIZES)
+def test_lsd_segments_parity(w, h, seed):
+    so, sg = _segs(random_image(w, h, seed), LineParams())
+    assert so.shape == sg.shape and len(so) > 0
+    assert np.array_equal(so, sg)
+
+
+@pytest.mark.parametrize("nbins", [16, 64, 1024])
+def test_lsd_segments_parity_bins(nbins):
+    so, sg = _segs(random_image(400, 300, 40 + nbins), LineParams(lsd_n_bins=nbins))
+    assert so.shape == sg.shape and np.array_equal(so, sg)
+
+
+def test_lsd_scale_one_and_flat():
+    so, sg = _segs(random_image(320, 240, 8), LineParams(lsd_scale=1.0))
+    assert so.shape == sg.shape and np.array_equal(so, sg)
+    so, sg = _segs(np.full((120, 160), 90, np.uint8), LineParams())
+    assert len(so) == 0 and len(sg) == 0
+
+
+def _cmp_extract(img, params):
+    o, g = oracle(), olf.api(0)
+    ho, hg = o.line_create(params), g.line_create(params)
+    try:
+        ko, do = o.line_extract(ho, img)
+        kg, dg = g.line_extract(hg, img)
+        assert len(ko) == len(kg)
+        for f in KEYLINE.names:
+            assert np.array_equal(ko[f], kg[f]), f"keyline field {f}"
+        assert np.array_equal(do, dg), "LBD descriptor bytes differ"
+        return len(kg)
+    finally:
+        o.line_destroy(ho); g.line_destroy(hg)
+
+
+@pytest.mark.parametrize("w,h,seed", SIZES[:5])
+def test_line_extract_parity(w, h, seed):
+    _cmp_extract(random_image(w, h, seed), LineParams(lsd_nfeatures=60))
+    _cmp_extract(random_image(w, h, seed + 100), LineParams(lsd_nfeatures=0))
+
+
+def test_line_extract_parity_720p_scene():
+    L, R = Scene("zed720", 0).stereo(0)
+    assert _cmp_extract(L, LineParams(lsd_nfeatures=500)) == 500
+    assert _cmp_extract(R, LineParams(lsd_nfeatures=1000, min_line_length=0.05)) > 100
+
+
+def test_lbd_compute_parity_on_given_keylines():
+    o, g = oracle(), olf.api(0)
+    img = random_image(640, 480, 21)
+    ho, hg = o.line_create(LineParams(lsd_nfeatures=0)), g.line_create(LineParams(lsd_nfeatures=0))
+    kl, d = o.line_extract(ho, img)
+    assert np.array_equal(g.lbd_compute(hg, img, kl), d)
+    assert g.lbd_compute(hg, img, kl[:0]).shape == (0, 32)
+    o.line_destroy(ho); g.line_destroy(hg)
