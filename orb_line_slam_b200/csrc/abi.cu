@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "orb.h"
 #include "line.h"
+#include "match.h"
 #include <mutex>
 
 namespace olf {
@@ -64,4 +65,28 @@ int olf_lbd_compute(olf_line* h, const uint8_t* img, int width, int height, int 
     return line_lbd_compute((LineImpl*)h, img, width, height, stride, kls, n, desc);
 }
 int olf_line_last_stats(const olf_line* h, int* out8) { if (!h || !out8) return OLF_ERR_ARG; line_last_stats((const LineImpl*)h, out8); return OLF_OK; }
+
+int olf_knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0, int* dist0, int* idx1, int* dist1, int device) {
+    return knn2_hamming(d1, n1, d2, n2, idx0, dist0, idx1, dist1, device);
+}
+int olf_match_nnr(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int* matches12, int* nmatches, int device) {
+    return match_lines(d1, n1, d2, n2, nnr, 0, matches12, nmatches, device);
+}
+int olf_match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int best_lr_matches, int* matches12, int* nmatches, int device) {
+    return match_lines(d1, n1, d2, n2, nnr, best_lr_matches, matches12, nmatches, device);
+}
+int olf_stereo_points(olf_orb* left, olf_orb* right, const olf_keypoint* kps_l, const uint8_t* desc_l, int n_l,
+                      const olf_keypoint* kps_r, const uint8_t* desc_r, int n_r, float bf, float fx, float* u_right, float* depth) {
+    return stereo_points((OrbImpl*)left, (OrbImpl*)right, kps_l, desc_l, n_l, kps_r, desc_r, n_r, bf, fx, u_right, depth);
+}
+int olf_stereo_lines(const olf_keyline* kls_l, const uint8_t* desc_l, int n_l, const olf_keyline* kls_r, const uint8_t* desc_r, int n_r,
+                     int img_width, int img_height, const olf_line_match_params* p, int* matches12, float* disp_s_e, double* le, int device) {
+    return stereo_lines(kls_l, desc_l, n_l, kls_r, desc_r, n_r, img_width, img_height, p, matches12, disp_s_e, le, device);
+}
+int olf_search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device) {
+    return search_by_projection_last(a, assigned_cur, cur_point, nmatches, device);
+}
+int olf_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches, int device) {
+    return search_by_projection_map(a, assigned_cur, nmatches, device);
+}
 }

@@ -1,0 +1,790 @@
+// Matching half of the front end on sm_100a.
+//   olf_knn2_hamming / olf_match_nnr / olf_match_lines : cv::BFMatcher(NORM_HAMMING).knnMatch + matchNNR + match
+//                                                        (reference src/LineMatcher.cpp:42-132)
+//   olf_stereo_points : Frame::ComputeStereoMatches     (src/Frame.cc:702-876)
+//   olf_stereo_lines  : Frame::ComputeStereoMatches_Lines + matchGrid(lines) + GridStructure + LineIterator
+//                       (src/Frame.cc:878-1048, src/LineMatcher.cpp:220-299, src/gridStructure.cpp, src/LineIterator.cpp)
+//   olf_search_by_projection_last / _map : ORBmatcher::SearchByProjection (src/ORBmatcher.cc:47-139, 1474-1618, 1749-1790)
+//                       with Frame::PosInGrid / GetFeaturesInArea (src/Frame.cc:517-582)
+// All Hamming distances are warp-parallel POPC work; the order-dependent parts of the reference (running
+// `distances[i2]` cross-check, "already holds a MapPoint" blocking) are reproduced exactly: either by walking the
+// dependent index sequentially inside one thread per independent chain, or by iterating the assignment operator to
+// its (unique, well-founded) fixed point.
+#include "common.cuh"
+#include "orb.h"
+#include "match.h"
+#include <algorithm>
+#include <climits>
+#include <cmath>
+
+namespace olf {
+
+// ---- per-thread scratch: one stream + growing device / pinned arenas per device -------------------------------
+struct Arena {
+    DevBuf<uint8_t> dev; PinBuf<uint8_t> pin;
+    size_t dev_off = 0, pin_off = 0;
+    void reset() { dev_off = pin_off = 0; }
+};
+struct MatchCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    Arena a;
+};
+static thread_local MatchCtx g_ctx[16];
+
+static int get_ctx(int device, MatchCtx** out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || device >= 16) {
+        cudaGetLastError();
+        set_last_error("no such CUDA device (this library has no CPU path)");
+        return OLF_ERR_NO_DEVICE;
+    }
+    OLF_CUDA(cudaSetDevice(device));
+    MatchCtx& c = g_ctx[device];
+    if (!c.stream) { OLF_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); c.device = device; }
+    c.a.reset();
+    *out = &c;
+    return OLF_OK;
+}
+// Two-pass use: first call plan(bytes) for everything, then ensure(), then take().
+struct Planner {
+    size_t dev = 0, pin = 0;
+    size_t d(size_t bytes) { size_t o = dev; dev += align_up_sz(bytes, 256); return o; }
+    size_t p(size_t bytes) { size_t o = pin; pin += align_up_sz(bytes, 256); return o; }
+};
+static int arena_ensure(MatchCtx* c, const Planner& pl) {
+    int rc;
+    if ((rc = c->a.dev.ensure(pl.dev + 256))) return rc;
+    if ((rc = c->a.pin.ensure(pl.pin + 256))) return rc;
+    return OLF_OK;
+}
+template <typename T> static T* dptr(MatchCtx* c, size_t off) { return (T*)(c->a.dev.p + off); }
+template <typename T> static T* hptr(MatchCtx* c, size_t off) { return (T*)(c->a.pin.p + off); }
+template <typename T> static T* hdptr(MatchCtx* c, size_t off) { return (T*)(c->a.pin.d + off); }     // device alias of pinned
+
+// ======================================================================================================
+// brute-force kNN(2), ties -> lowest train index
+// ======================================================================================================
+#define KNN_Q 128      // queries per block (one per thread)
+#define KNN_T 128      // train descriptors per smem tile
+struct Knn2 { int d0, i0, d1, i1; };
+__device__ __forceinline__ void knn_update(Knn2& k, int d, int j) {
+    if (d < k.d0) { k.d1 = k.d0; k.i1 = k.i0; k.d0 = d; k.i0 = j; }
+    else if (d < k.d1) { k.d1 = d; k.i1 = j; }
+}
+__global__ void __launch_bounds__(KNN_Q) k_knn2_partial(const uint4* __restrict__ q, int n1, const uint4* __restrict__ t, int n2,
+                                                        int per_split, Knn2* __restrict__ part) {
+    __shared__ uint4 tile[KNN_T * 2];
+    const int qi = blockIdx.x * KNN_Q + threadIdx.x;
+    const int t0 = blockIdx.y * per_split, t1 = min(t0 + per_split, n2);
+    uint4 a = make_uint4(0, 0, 0, 0), b = a;
+    if (qi < n1) { a = q[2 * qi]; b = q[2 * qi + 1]; }
+    Knn2 k; k.d0 = INT_MAX; k.d1 = INT_MAX; k.i0 = -1; k.i1 = -1;
+    for (int base = t0; base < t1; base += KNN_T) {
+        const int cnt = min(KNN_T, t1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += KNN_Q) tile[i] = t[2 * (size_t)base + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const uint4 c = tile[2 * j], e = tile[2 * j + 1];
+            const int d = __popc(a.x ^ c.x) + __popc(a.y ^ c.y) + __popc(a.z ^ c.z) + __popc(a.w ^ c.w) +
+                          __popc(b.x ^ e.x) + __popc(b.y ^ e.y) + __popc(b.z ^ e.z) + __popc(b.w ^ e.w);
+            knn_update(k, d, base + j);
+        }
+    }
+    if (qi < n1) part[(size_t)blockIdx.y * n1 + qi] = k;
+}
+__global__ void k_knn2_merge(const Knn2* __restrict__ part, int n1, int splits, int* __restrict__ i0, int* __restrict__ d0,
+                             int* __restrict__ i1, int* __restrict__ d1) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= n1) return;
+    Knn2 k = part[qi];
+    for (int s = 1; s < splits; ++s) {
+        const Knn2 p = part[(size_t)s * n1 + qi];
+        if (p.i0 >= 0) knn_update(k, p.d0, p.i0);
+        if (p.i1 >= 0) knn_update(k, p.d1, p.i1);
+    }
+    i0[qi] = k.i0; d0[qi] = k.d0; i1[qi] = k.i1; d1[qi] = k.d1;
+}
+// matchNNR acceptance (src/LineMatcher.cpp:54-59) + optional mutual check (src/LineMatcher.cpp:120-127)
+__global__ void k_nnr_accept(const int* __restrict__ i0, const int* __restrict__ d0, const int* __restrict__ d1, int n1, int n2, float nnr, int* __restrict__ m12) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    int m = -1;
+    if (n2 >= 2 && (float)d0[i] < fmul((float)d1[i], nnr)) m = i0[i];
+    m12[i] = m;
+}
+__global__ void k_mutual(int* __restrict__ m12, const int* __restrict__ m21, int n1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const int j = m12[i];
+    if (j >= 0 && m21[j] != i) m12[i] = -1;
+}
+
+static void launch_knn2(cudaStream_t s, const uint4* dq, int n1, const uint4* dt, int n2, Knn2* part, int* i0, int* d0, int* i1, int* d1, int splits, int per_split) {
+    dim3 g((n1 + KNN_Q - 1) / KNN_Q, splits);
+    k_knn2_partial<<<g, KNN_Q, 0, s>>>(dq, n1, dt, n2, per_split, part);
+    k_knn2_merge<<<(n1 + 127) / 128, 128, 0, s>>>(part, n1, splits, i0, d0, i1, d1);
+}
+static void knn_splits(int n1, int n2, int* splits, int* per_split) {
+    const int qb = std::max((n1 + KNN_Q - 1) / KNN_Q, 1);
+    int sp = std::max(1, std::min((592 + qb - 1) / qb, (n2 + 255) / 256));
+    int per = (std::max(n2, 1) + sp - 1) / sp;
+    per = (per + KNN_T - 1) / KNN_T * KNN_T;
+    sp = (std::max(n2, 1) + per - 1) / per;
+    *splits = sp; *per_split = per;
+}
+
+int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0, int* dist0, int* idx1, int* dist1, int device) {
+    if (n1 < 0 || n2 < 0 || (n1 && !d1) || (n2 && !d2)) { set_last_error("olf_knn2_hamming: bad arguments"); return OLF_ERR_ARG; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    if (n1 == 0) return OLF_OK;
+    int splits, per; knn_splits(n1, n2, &splits, &per);
+    Planner pl;
+    const size_t o_q = pl.d((size_t)n1 * 32), o_t = pl.d((size_t)std::max(n2, 1) * 32), o_part = pl.d((size_t)splits * n1 * sizeof(Knn2)), o_out = pl.d((size_t)4 * n1 * 4);
+    const size_t p_q = pl.p((size_t)n1 * 32), p_t = pl.p((size_t)std::max(n2, 1) * 32), p_out = pl.p((size_t)4 * n1 * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->stream;
+    memcpy(hptr<uint8_t>(c, p_q), d1, (size_t)n1 * 32);
+    if (n2) memcpy(hptr<uint8_t>(c, p_t), d2, (size_t)n2 * 32);
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_q), hptr<uint8_t>(c, p_q), (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    if (n2) OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_t), hptr<uint8_t>(c, p_t), (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    int* o = dptr<int>(c, o_out);
+    launch_knn2(s, dptr<uint4>(c, o_q), n1, dptr<uint4>(c, o_t), n2, dptr<Knn2>(c, o_part), o, o + n1, o + 2 * n1, o + 3 * n1, splits, per);
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_out), o, (size_t)4 * n1 * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(cudaStreamSynchronize(s));
+    const int* ho = hptr<int>(c, p_out);
+    memcpy(idx0, ho, n1 * 4); memcpy(dist0, ho + n1, n1 * 4); memcpy(idx1, ho + 2 * n1, n1 * 4); memcpy(dist1, ho + 3 * n1, n1 * 4);
+    return OLF_OK;
+}
+
+int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int mutual, int* m12, int* nmatches, int device) {
+    if (n1 < 0 || n2 < 0 || (n1 && !d1) || (n2 && !d2) || !nmatches) { set_last_error("olf_match: bad arguments"); return OLF_ERR_ARG; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    *nmatches = 0;
+    if (n1 == 0) return OLF_OK;
+    if (n2 == 0) { for (int i = 0; i < n1; ++i) m12[i] = -1; return OLF_OK; }
+    int s12, p12, s21, p21;
+    knn_splits(n1, n2, &s12, &p12); knn_splits(n2, n1, &s21, &p21);
+    Planner pl;
+    const size_t o_q = pl.d((size_t)n1 * 32), o_t = pl.d((size_t)n2 * 32);
+    const size_t o_part = pl.d(std::max((size_t)s12 * n1, (size_t)s21 * n2) * sizeof(Knn2));
+    const size_t o_a = pl.d((size_t)4 * n1 * 4), o_b = pl.d((size_t)4 * n2 * 4), o_m12 = pl.d((size_t)n1 * 4), o_m21 = pl.d((size_t)n2 * 4);
+    const size_t p_q = pl.p((size_t)n1 * 32), p_t = pl.p((size_t)n2 * 32), p_m = pl.p((size_t)n1 * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->stream;
+    memcpy(hptr<uint8_t>(c, p_q), d1, (size_t)n1 * 32); memcpy(hptr<uint8_t>(c, p_t), d2, (size_t)n2 * 32);
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_q), hptr<uint8_t>(c, p_q), (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_t), hptr<uint8_t>(c, p_t), (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    int* a = dptr<int>(c, o_a); int* b = dptr<int>(c, o_b);
+    launch_knn2(s, dptr<uint4>(c, o_q), n1, dptr<uint4>(c, o_t), n2, dptr<Knn2>(c, o_part), a, a + n1, a + 2 * n1, a + 3 * n1, s12, p12);
+    k_nnr_accept<<<(n1 + 127) / 128, 128, 0, s>>>(a, a + n1, a + 3 * n1, n1, n2, nnr, dptr<int>(c, o_m12));
+    if (mutual) {
+        launch_knn2(s, dptr<uint4>(c, o_t), n2, dptr<uint4>(c, o_q), n1, dptr<Knn2>(c, o_part), b, b + n2, b + 2 * n2, b + 3 * n2, s21, p21);
+        k_nnr_accept<<<(n2 + 127) / 128, 128, 0, s>>>(b, b + n2, b + 3 * n2, n2, n1, nnr, dptr<int>(c, o_m21));
+        k_mutual<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_m12), dptr<int>(c, o_m21), n1);
+    }
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_m), dptr<int>(c, o_m12), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(cudaStreamSynchronize(s));
+    const int* hm = hptr<int>(c, p_m);
+    int cnt = 0;
+    for (int i = 0; i < n1; ++i) { m12[i] = hm[i]; cnt += hm[i] >= 0; }
+    *nmatches = cnt;
+    return OLF_OK;
+}
+
+// ======================================================================================================
+// Frame::ComputeStereoMatches (src/Frame.cc:702-876): warp per left keypoint
+// ======================================================================================================
+struct PyrView { const uint8_t* pyr; int w[OLF_MAX_LEVELS], h[OLF_MAX_LEVELS], pitch[OLF_MAX_LEVELS]; unsigned off[OLF_MAX_LEVELS]; float scale[OLF_MAX_LEVELS], inv_scale[OLF_MAX_LEVELS]; };
+__device__ __forceinline__ int px_reflect(const PyrView& P, int l, int x, int y) {
+    return P.pyr[P.off[l] + (size_t)reflect101(y, P.h[l]) * P.pitch[l] + reflect101(x, P.w[l])];
+}
+__global__ void __launch_bounds__(256) k_stereo_points(const olf_keypoint* __restrict__ kl, const uint32_t* __restrict__ dl, int N,
+                                                       const olf_keypoint* __restrict__ kr, const uint32_t* __restrict__ dr, int Nr,
+                                                       const __grid_constant__ PyrView PL, const __grid_constant__ PyrView PR,
+                                                       float mbf, float fx, float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sad) {
+    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (iL >= N) return;
+    const olf_keypoint kpL = kl[iL];
+    const int levelL = kpL.octave;
+    const float uL = kpL.x, vL = kpL.y;
+    const int rowi = (int)vL;                                   // vRowIndices[vL]: float -> size_t truncation
+    const float mb = fdiv(mbf, fx);
+    const float maxD = fdiv(mbf, mb);
+    const float minU = fsub(uL, maxD), maxU = uL;               // minD = 0
+    uint32_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = dl[(size_t)iL * 8 + k];
+    // best right keypoint on this row: lexicographic min of (dist, iR), dist < TH_HIGH
+    unsigned best = ((unsigned)OLF_TH_HIGH << 20);              // key = dist << 20 | iR  (iR < 2^20)
+    if (!(maxU < 0) && rowi >= 0 && rowi < PL.h[0]) {
+        for (int iR = lane; iR < Nr; iR += 32) {
+            const olf_keypoint k = kr[iR];
+            const float r = fmul(2.0f, PL.scale[k.octave]);
+            const int maxr = (int)ceilf(fadd(k.y, r)), minr = (int)floorf(fsub(k.y, r));
+            if (rowi < minr || rowi > maxr) continue;
+            if (k.octave < levelL - 1 || k.octave > levelL + 1) continue;
+            if (!(k.x >= minU && k.x <= maxU)) continue;
+            const int d = hamming256(a, dr + (size_t)iR * 8);
+            const unsigned key = ((unsigned)d << 20) | (unsigned)iR;
+            best = min(best, key);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    const int bestDist = (int)(best >> 20);
+    float out_u = -1.f, out_d = -1.f; int out_s = -1;
+    if (bestDist < (OLF_TH_HIGH + OLF_TH_LOW) / 2) {
+        const int bestIdxR = (int)(best & 0xFFFFF);
+        const float uR0 = kr[bestIdxR].x;
+        const float sf = PL.inv_scale[levelL];
+        const float scaleduL = roundf(fmul(kpL.x, sf)), scaledvL = roundf(fmul(kpL.y, sf)), scaleduR0 = roundf(fmul(uR0, sf));
+        const int cxL = (int)scaleduL, cyL = (int)scaledvL, cxR = (int)scaleduR0;
+        const float iniu = fsub(fadd(scaleduR0, 5.f), 5.f);
+        const float endu = fadd(fadd(fadd(scaleduR0, 5.f), 5.f), 1.f);
+        if (!(iniu < 0 || endu >= (float)PR.w[levelL])) {
+            // 11 SAD windows of 11x11 (minus centre), integer sums (exact in any order)
+            int acc[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) acc[k] = 0;
+            const int cL = px_reflect(PL, levelL, cxL, cyL);
+            int cR[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) cR[k] = px_reflect(PR, levelL, cxR + k - 5, cyL);
+            for (int p = lane; p < 121; p += 32) {
+                const int dy = p / 11 - 5, dx = p % 11 - 5;
+                const int va = px_reflect(PL, levelL, cxL + dx, cyL + dy) - cL;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) {
+                    const int vb = px_reflect(PR, levelL, cxR + k - 5 + dx, cyL + dy) - cR[k];
+                    acc[k] += abs(va - vb);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 11; ++k)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            int bestS = INT_MAX, bestinc = 0;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) if (acc[k] < bestS) { bestS = acc[k]; bestinc = k - 5; }
+            if (!(bestinc == -5 || bestinc == 5)) {
+                float d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+                for (int k = 1; k < 10; ++k) if (k - 5 == bestinc) { d1 = (float)acc[k - 1]; d2 = (float)acc[k]; d3 = (float)acc[k + 1]; }
+                const float deltaR = fdiv(fsub(d1, d3), fmul(2.0f, fsub(fadd(d1, d3), fmul(2.0f, d2))));
+                if (!(deltaR < -1 || deltaR > 1)) {
+                    float bestuR = fmul(PL.scale[levelL], fadd(fadd(scaleduR0, (float)bestinc), deltaR));
+                    float disparity = fsub(uL, bestuR);
+                    if (disparity >= 0 && disparity < maxD) {
+                        if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                        out_d = fdiv(mbf, disparity);
+                        out_u = bestuR;
+                        out_s = bestS;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { uRight[iL] = out_u; depth[iL] = out_d; sad[iL] = out_s; }
+}
+// median SAD outlier rejection (src/Frame.cc:861-875): one block; rank counting for the size/2-th order statistic
+__global__ void __launch_bounds__(1024) k_stereo_median(float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad, int N) {
+    __shared__ int s_cnt, s_median;
+    if (threadIdx.x == 0) { s_cnt = 0; s_median = -1; }
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < N; i += 1024) local += sad[i] >= 0;
+    atomicAdd(&s_cnt, local);
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt == 0) return;
+    const int k = cnt / 2;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const int v = sad[i];
+        if (v < 0) continue;
+        int less = 0, leq = 0;
+        for (int j = 0; j < N; ++j) { const int u = sad[j]; if (u >= 0) { less += u < v; leq += u <= v; } }
+        if (less <= k && k < leq) s_median = v;
+    }
+    __syncthreads();
+    const float thDist = fmul(0x1.0cccccp+1f /* 1.5f*1.4f */, (float)s_median);
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const int v = sad[i];
+        if (v >= 0 && !((float)v < thDist)) { uRight[i] = -1.f; depth[i] = -1.f; }
+    }
+}
+
+static PyrView make_view(const OrbDeviceView& v) {
+    PyrView p; memset(&p, 0, sizeof(p));
+    p.pyr = v.pyr;
+    for (int l = 0; l < v.nlevels; ++l) { p.w[l] = v.w[l]; p.h[l] = v.h[l]; p.pitch[l] = v.pitch[l]; p.off[l] = v.off[l]; p.scale[l] = v.scale[l]; p.inv_scale[l] = v.inv_scale[l]; }
+    return p;
+}
+
+int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const uint8_t* dl, int N, const olf_keypoint* kr, const uint8_t* dr, int Nr,
+                  float bf, float fx, float* uRight, float* depth) {
+    if (!left || !right || N < 0 || Nr < 0 || (N && (!kl || !dl || !uRight || !depth)) || (Nr && (!kr || !dr))) { set_last_error("olf_stereo_points: bad arguments"); return OLF_ERR_ARG; }
+    const OrbDeviceView vl = orb_device_view(left), vr = orb_device_view(right);
+    if (vl.device != vr.device || !vl.pyr || !vr.pyr || vl.nlevels != vr.nlevels) { set_last_error("olf_stereo_points: extractors must have run on the same device"); return OLF_ERR_ARG; }
+    if (Nr >= (1 << 20)) { set_last_error("olf_stereo_points: too many right keypoints"); return OLF_ERR_CAPACITY; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(vl.device, &c))) return rc;
+    if (N == 0) return OLF_OK;
+    Planner pl;
+    const size_t o_kl = pl.d((size_t)N * sizeof(olf_keypoint)), o_dl = pl.d((size_t)N * 32), o_kr = pl.d((size_t)std::max(Nr, 1) * sizeof(olf_keypoint)), o_dr = pl.d((size_t)std::max(Nr, 1) * 32);
+    const size_t o_u = pl.d((size_t)N * 4), o_d = pl.d((size_t)N * 4), o_s = pl.d((size_t)N * 4);
+    const size_t p_in = pl.p((size_t)(N + Nr) * (sizeof(olf_keypoint) + 32)), p_out = pl.p((size_t)2 * N * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->stream;
+    uint8_t* hp = hptr<uint8_t>(c, p_in);
+    uint8_t* h_kl = hp; uint8_t* h_dl = h_kl + (size_t)N * sizeof(olf_keypoint); uint8_t* h_kr = h_dl + (size_t)N * 32; uint8_t* h_dr = h_kr + (size_t)Nr * sizeof(olf_keypoint);
+    memcpy(h_kl, kl, (size_t)N * sizeof(olf_keypoint)); memcpy(h_dl, dl, (size_t)N * 32);
+    if (Nr) { memcpy(h_kr, kr, (size_t)Nr * sizeof(olf_keypoint)); memcpy(h_dr, dr, (size_t)Nr * 32); }
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_kl), h_kl, (size_t)N * sizeof(olf_keypoint), cudaMemcpyHostToDevice, s));
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_dl), h_dl, (size_t)N * 32, cudaMemcpyHostToDevice, s));
+    if (Nr) {
+        OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_kr), h_kr, (size_t)Nr * sizeof(olf_keypoint), cudaMemcpyHostToDevice, s));
+        OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_dr), h_dr, (size_t)Nr * 32, cudaMemcpyHostToDevice, s));
+    }
+    // the extractors' entry points synchronise their own streams before returning, so the pyramids are complete
+    k_stereo_points<<<(N + 7) / 8, 256, 0, s>>>(dptr<olf_keypoint>(c, o_kl), dptr<uint32_t>(c, o_dl), N, dptr<olf_keypoint>(c, o_kr), dptr<uint32_t>(c, o_dr), Nr,
+                                                 make_view(vl), make_view(vr), bf, fx, dptr<float>(c, o_u), dptr<float>(c, o_d), dptr<int>(c, o_s));
+    k_stereo_median<<<1, 1024, 0, s>>>(dptr<float>(c, o_u), dptr<float>(c, o_d), dptr<int>(c, o_s), N);
+    float* ho = hptr<float>(c, p_out);
+    OLF_CUDA(cudaMemcpyAsync(ho, dptr<float>(c, o_u), (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(ho + N, dptr<float>(c, o_d), (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(cudaStreamSynchronize(s));
+    memcpy(uRight, ho, (size_t)N * 4); memcpy(depth, ho + N, (size_t)N * 4);
+    return OLF_OK;
+}
+
+// ======================================================================================================
+// Frame::ComputeStereoMatches_Lines (src/Frame.cc:878-1000) + matchGrid(lines) (src/LineMatcher.cpp:220-299)
+// ======================================================================================================
+#define LCELLS 128
+// thread per right line: normalised direction + Bresenham raster (src/LineIterator.cpp:34-77) into grid cells
+__global__ void k_lines_raster(const olf_keyline* __restrict__ kr, int n2, double inv_w, double inv_h,
+                               double2* __restrict__ dir2, short2* __restrict__ cells, int* __restrict__ ncells) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const olf_keyline k = kr[i];
+    const double vx = __dmul_rn((double)fsub(k.endPointX, k.startPointX), inv_w), vy = __dmul_rn((double)fsub(k.endPointY, k.startPointY), inv_h);
+    const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+    dir2[i] = make_double2(__ddiv_rn(vx, mag), __ddiv_rn(vy, mag));
+    double x1 = __dmul_rn((double)k.startPointX, inv_w), y1 = __dmul_rn((double)k.startPointY, inv_h);
+    double x2 = __dmul_rn((double)k.endPointX, inv_w), y2 = __dmul_rn((double)k.endPointY, inv_h);
+    const bool steep = fabs(y2 - y1) > fabs(x2 - x1);
+    if (steep) { double t = x1; x1 = y1; y1 = t; t = x2; x2 = y2; y2 = t; }
+    if (x1 > x2) { double t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    const double dx = __dsub_rn(x2, x1), dy = fabs(__dsub_rn(y2, y1));
+    double error = __ddiv_rn(dx, 2.0);
+    const int ystep = (y1 < y2) ? 1 : -1;
+    int x = (int)x1, y = (int)y1;
+    const int maxX = (int)x2;
+    int n = 0;
+    while (x <= maxX) {
+        const int px = steep ? y : x, py = steep ? x : y;
+        if (px >= 0 && px < OLF_GRID_COLS && py >= 0 && py < OLF_GRID_ROWS && n < LCELLS) cells[(size_t)i * LCELLS + n++] = make_short2((short)px, (short)py);
+        error = __dsub_rn(error, dy);
+        if (error < 0) { y += ystep; error = __dadd_rn(error, dx); }
+        x++;
+    }
+    ncells[i] = n;
+}
+// thread per (i1, i2): candidate test (grid windows around both end points) + direction test + Hamming; -1 = not a candidate
+__global__ void __launch_bounds__(256) k_lines_cand(const olf_keyline* __restrict__ kl, const uint32_t* __restrict__ dl, int n1,
+                                                    const uint32_t* __restrict__ dr, int n2, double inv_w, double inv_h,
+                                                    const double2* __restrict__ dir2, const short2* __restrict__ cells, const int* __restrict__ ncells,
+                                                    int ws, double sim_th, int* __restrict__ cand) {
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y;
+    if (i2 >= n2) return;
+    const olf_keyline k = kl[i1];
+    const int spx = (int)__dmul_rn((double)k.startPointX, inv_w), spy = (int)__dmul_rn((double)k.startPointY, inv_h);
+    const int epx = (int)__dmul_rn((double)k.endPointX, inv_w), epy = (int)__dmul_rn((double)k.endPointY, inv_h);
+    // GridStructure::get windows: x in [max(0,x-ws), min(cols, x+1)), y in [max(0,y), min(rows, y+1))
+    const int ax0 = max(0, spx - ws), ax1 = min(OLF_GRID_COLS, spx + 1), ay0 = max(0, spy), ay1 = min(OLF_GRID_ROWS, spy + 1);
+    const int bx0 = max(0, epx - ws), bx1 = min(OLF_GRID_COLS, epx + 1), by0 = max(0, epy), by1 = min(OLF_GRID_ROWS, epy + 1);
+    bool in = false;
+    const int nc = ncells[i2];
+    for (int c = 0; c < nc && !in; ++c) {
+        const short2 p = cells[(size_t)i2 * LCELLS + c];
+        in = (p.x >= ax0 && p.x < ax1 && p.y >= ay0 && p.y < ay1) || (p.x >= bx0 && p.x < bx1 && p.y >= by0 && p.y < by1);
+    }
+    int d = -1;
+    if (in) {
+        double vx = (double)(epx - spx), vy = (double)(epy - spy);
+        const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+        vx = __ddiv_rn(vx, mag); vy = __ddiv_rn(vy, mag);
+        const double2 o = dir2[i2];
+        const double dot = __dadd_rn(__dmul_rn(vx, o.x), __dmul_rn(vy, o.y));
+        if (!(fabs(dot) < sim_th)) d = hamming256(dl + (size_t)i1 * 8, dr + (size_t)i2 * 8);
+    }
+    cand[(size_t)i1 * n2 + i2] = d;
+}
+// thread per right line: walk i1 ascending, keep the running best distance (distances[i2], matches_21[i2]); a pair
+// "passes" only if it improves it (src/LineMatcher.cpp:267-272).  Non-passing candidates are erased (-1).
+__global__ void k_lines_pass(int* __restrict__ cand, int n1, int n2, int* __restrict__ m21) {
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i2 >= n2) return;
+    int best = INT_MAX, who = -1;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int d = cand[(size_t)i1 * n2 + i2];
+        if (d < 0) continue;
+        if (d < best) { best = d; who = i1; } else cand[(size_t)i1 * n2 + i2] = -1;
+    }
+    m21[i2] = who;
+}
+// thread per left line: best / second best over passing candidates in ascending i2, ratio test (:274-286)
+__global__ void k_lines_best(const int* __restrict__ cand, int n1, int n2, double min_ratio, int* __restrict__ m12) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i1 >= n1) return;
+    int best_d = INT_MAX, best_d2 = INT_MAX, best_idx = -1;
+    for (int i2 = 0; i2 < n2; ++i2) {
+        const int d = cand[(size_t)i1 * n2 + i2];
+        if (d < 0) continue;
+        if (d < best_d) { best_d2 = best_d; best_d = d; best_idx = i2; }
+        else if (d < best_d2) best_d2 = d;
+    }
+    m12[i1] = ((double)best_d < __dmul_rn((double)best_d2, min_ratio)) ? best_idx : -1;
+}
+// thread per left line: mutual check (:288-296) + geometric filters (src/Frame.cc:934-958, 1002-1048), all double
+__global__ void k_lines_geom(const olf_keyline* __restrict__ kl, const olf_keyline* __restrict__ kr, int n1, int* __restrict__ m12, const int* __restrict__ m21,
+                             int mutual, olf_line_match_params P, float* __restrict__ disp, double* __restrict__ le) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i1 >= n1) return;
+    disp[2 * i1] = -1.f; disp[2 * i1 + 1] = -1.f; le[3 * i1] = 0; le[3 * i1 + 1] = 0; le[3 * i1 + 2] = 0;
+    int i2 = m12[i1];
+    if (mutual && i2 >= 0 && m21[i2] != i1) { i2 = -1; m12[i1] = -1; }
+    if (i2 < 0) return;
+    const double spl0 = kl[i1].startPointX, spl1 = kl[i1].startPointY, epl0 = kl[i1].endPointX, epl1 = kl[i1].endPointY;
+    // le_l = sp_l x ep_l (third components 1.0), normalised by the norm of its first two entries
+    double l0 = __dsub_rn(__dmul_rn(spl1, 1.0), __dmul_rn(1.0, epl1));
+    double l1 = __dsub_rn(__dmul_rn(1.0, epl0), __dmul_rn(spl0, 1.0));
+    double l2 = __dsub_rn(__dmul_rn(spl0, epl1), __dmul_rn(spl1, epl0));
+    const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(l0, l0), __dmul_rn(l1, l1)));
+    l0 = __ddiv_rn(l0, nrm); l1 = __ddiv_rn(l1, nrm); l2 = __ddiv_rn(l2, nrm);
+    double spr0 = kr[i2].startPointX, spr1 = kr[i2].startPointY, epr0 = kr[i2].endPointX, epr1 = kr[i2].endPointY;
+    double overlap = 1.0;
+    if (fabs(__dsub_rn(epl1, spl1)) > P.line_horiz_th) {
+        const double sln = fmin(spl1, epl1), eln = fmax(spl1, epl1), spn = fmin(spr1, epr1), epn = fmax(spr1, epr1);
+        const double length = __dsub_rn(eln, spn);
+        if ((epn < sln) || (spn > eln)) overlap = 0.0;
+        else if ((epn > eln) && (spn < sln)) overlap = __dsub_rn(eln, sln);
+        else overlap = __dsub_rn(fmin(eln, epn), fmax(sln, spn));
+        if (length > (double)0.01f) overlap = __ddiv_rn(overlap, length); else overlap = 0.0;
+        if (overlap > 1.0) overlap = 1.0;
+    }
+    const double spr1_old = spr1;
+    const double nx = __ddiv_rn(__dadd_rn(__dmul_rn(spr0, __dsub_rn(spl1, epr1)), __dmul_rn(epr0, __dsub_rn(spr1, spl1))), __dsub_rn(spr1, epr1));
+    spr0 = nx; spr1 = spl1;
+    const double mx = __ddiv_rn(__dadd_rn(__dmul_rn(spr0, __dsub_rn(epl1, epr1)), __dmul_rn(epr0, __dsub_rn(spr1, epl1))), __dsub_rn(spr1, epr1));
+    const double epr1_old = epr1;
+    epr0 = mx; epr1 = epl1;
+    (void)spr1_old; (void)epr1_old;
+    double disp_s = __dsub_rn(spl0, spr0), disp_e = __dsub_rn(epl0, epr0);
+    if (__ddiv_rn(fmin(disp_s, disp_e), fmax(disp_s, disp_e)) < P.ls_min_disp_ratio) { disp_s = -1.0; disp_e = -1.0; }
+    if (disp_s >= P.min_disp && disp_e >= P.min_disp && fabs(__dsub_rn(spl1, epl1)) > P.line_horiz_th &&
+        fabs(__dsub_rn(spr1, epr1)) > P.line_horiz_th && overlap > P.stereo_overlap_th) {
+        disp[2 * i1] = (float)disp_s; disp[2 * i1 + 1] = (float)disp_e;
+        le[3 * i1] = l0; le[3 * i1 + 1] = l1; le[3 * i1 + 2] = l2;
+    }
+}
+
+int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_keyline* kr, const uint8_t* dr, int n2, int img_w, int img_h,
+                 const olf_line_match_params* P, int* matches12, float* disp, double* le, int device) {
+    if (!P || n1 < 0 || n2 < 0 || img_w <= 0 || img_h <= 0 || (n1 && (!kl || !dl || !matches12 || !disp || !le)) || (n2 && (!kr || !dr))) {
+        set_last_error("olf_stereo_lines: bad arguments"); return OLF_ERR_ARG;
+    }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    for (int i = 0; i < n1; ++i) { matches12[i] = -1; disp[2 * i] = disp[2 * i + 1] = -1.f; le[3 * i] = le[3 * i + 1] = le[3 * i + 2] = 0; }
+    if (n1 == 0 || n2 == 0) return OLF_OK;
+    const double inv_w = OLF_GRID_COLS / (double)img_w, inv_h = OLF_GRID_ROWS / (double)img_h;
+    Planner pl;
+    const size_t o_kl = pl.d((size_t)n1 * sizeof(olf_keyline)), o_dl = pl.d((size_t)n1 * 32), o_kr = pl.d((size_t)n2 * sizeof(olf_keyline)), o_dr = pl.d((size_t)n2 * 32);
+    const size_t o_dir = pl.d((size_t)n2 * sizeof(double2)), o_cells = pl.d((size_t)n2 * LCELLS * sizeof(short2)), o_nc = pl.d((size_t)n2 * 4);
+    const size_t o_cand = pl.d((size_t)n1 * n2 * 4), o_m12 = pl.d((size_t)n1 * 4), o_m21 = pl.d((size_t)n2 * 4), o_disp = pl.d((size_t)n1 * 8), o_le = pl.d((size_t)n1 * 24);
+    const size_t p_in = pl.p((size_t)(n1 + n2) * (sizeof(olf_keyline) + 32)), p_m = pl.p((size_t)n1 * 4), p_disp = pl.p((size_t)n1 * 8), p_le = pl.p((size_t)n1 * 24);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->stream;
+    uint8_t* h_kl = hptr<uint8_t>(c, p_in); uint8_t* h_dl = h_kl + (size_t)n1 * sizeof(olf_keyline); uint8_t* h_kr = h_dl + (size_t)n1 * 32; uint8_t* h_dr = h_kr + (size_t)n2 * sizeof(olf_keyline);
+    memcpy(h_kl, kl, (size_t)n1 * sizeof(olf_keyline)); memcpy(h_dl, dl, (size_t)n1 * 32); memcpy(h_kr, kr, (size_t)n2 * sizeof(olf_keyline)); memcpy(h_dr, dr, (size_t)n2 * 32);
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_kl), h_kl, (size_t)n1 * sizeof(olf_keyline), cudaMemcpyHostToDevice, s));
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_dl), h_dl, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_kr), h_kr, (size_t)n2 * sizeof(olf_keyline), cudaMemcpyHostToDevice, s));
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_dr), h_dr, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    k_lines_raster<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<olf_keyline>(c, o_kr), n2, inv_w, inv_h, dptr<double2>(c, o_dir), dptr<short2>(c, o_cells), dptr<int>(c, o_nc));
+    k_lines_cand<<<dim3((n2 + 255) / 256, n1), 256, 0, s>>>(dptr<olf_keyline>(c, o_kl), dptr<uint32_t>(c, o_dl), n1, dptr<uint32_t>(c, o_dr), n2, inv_w, inv_h,
+                                                            dptr<double2>(c, o_dir), dptr<short2>(c, o_cells), dptr<int>(c, o_nc), P->matching_s_ws, P->line_sim_th, dptr<int>(c, o_cand));
+    if (P->best_lr_matches) k_lines_pass<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_cand), n1, n2, dptr<int>(c, o_m21));
+    k_lines_best<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_cand), n1, n2, P->min_ratio_12_l, dptr<int>(c, o_m12));
+    k_lines_geom<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<olf_keyline>(c, o_kl), dptr<olf_keyline>(c, o_kr), n1, dptr<int>(c, o_m12), dptr<int>(c, o_m21), P->best_lr_matches, *P,
+                                                  dptr<float>(c, o_disp), dptr<double>(c, o_le));
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_m), dptr<int>(c, o_m12), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(hptr<float>(c, p_disp), dptr<float>(c, o_disp), (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(hptr<double>(c, p_le), dptr<double>(c, o_le), (size_t)n1 * 24, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(cudaStreamSynchronize(s));
+    memcpy(matches12, hptr<int>(c, p_m), (size_t)n1 * 4); memcpy(disp, hptr<float>(c, p_disp), (size_t)n1 * 8); memcpy(le, hptr<double>(c, p_le), (size_t)n1 * 24);
+    return OLF_OK;
+}
+
+// ======================================================================================================
+// ORBmatcher::SearchByProjection: candidate lists (warp per query) + fixed-point resolution of the blocking rule
+// ======================================================================================================
+#define SBP_K 128
+struct SbpQuery { float u, v, radius, ur; int min_level, max_level; int valid; };
+struct GridParams { float min_x, min_y, inv_w, inv_h; };
+typedef unsigned long long u64;
+
+// Candidates of query i = Frame::GetFeaturesInArea(u, v, radius, min_level, max_level) (src/Frame.cc:517-570) minus
+// those failing the stereo check |ur - uRight[j]| > radius.  The reference enumerates cells ix-outer / iy-inner and
+// keypoints in ascending index inside a cell, and keeps the FIRST minimum, so the preference order is the
+// lexicographic key (dist, ix, iy, j).  Lists are written sorted by that key.
+__global__ void __launch_bounds__(256) k_sbp_candidates(const SbpQuery* __restrict__ q, const uint32_t* __restrict__ qdesc, int nq,
+                                                        const olf_keypoint* __restrict__ kps, const uint32_t* __restrict__ desc, const float* __restrict__ uRight, int n_cur,
+                                                        GridParams G, int max_dist, u64* __restrict__ lists, int* __restrict__ counts) {
+    __shared__ u64 sh[8][SBP_K];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + w;
+    if (i >= nq) return;
+    const SbpQuery Q = q[i];
+    int n = 0;
+    if (Q.valid) {
+        const int nMinCellX = max(0, (int)floorf(fmul(fsub(fsub(Q.u, G.min_x), Q.radius), G.inv_w)));
+        const int nMaxCellX = min(OLF_GRID_COLS - 1, (int)ceilf(fmul(fadd(fsub(Q.u, G.min_x), Q.radius), G.inv_w)));
+        const int nMinCellY = max(0, (int)floorf(fmul(fsub(fsub(Q.v, G.min_y), Q.radius), G.inv_h)));
+        const int nMaxCellY = min(OLF_GRID_ROWS - 1, (int)ceilf(fmul(fadd(fsub(Q.v, G.min_y), Q.radius), G.inv_h)));
+        const bool ok = !(nMinCellX >= OLF_GRID_COLS) && !(nMaxCellX < 0) && !(nMinCellY >= OLF_GRID_ROWS) && !(nMaxCellY < 0);
+        const bool check_levels = (Q.min_level > 0) || (Q.max_level >= 0);
+        uint32_t a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = qdesc[(size_t)i * 8 + k];
+        for (int base = 0; base < n_cur && ok; base += 32) {
+            const int j = base + lane;
+            bool take = false; u64 key = 0;
+            if (j < n_cur) {
+                const olf_keypoint kp = kps[j];
+                const int posX = (int)roundf(fmul(fsub(kp.x, G.min_x), G.inv_w)), posY = (int)roundf(fmul(fsub(kp.y, G.min_y), G.inv_h));   // PosInGrid
+                take = !(posX < 0 || posX >= OLF_GRID_COLS || posY < 0 || posY >= OLF_GRID_ROWS) &&
+                       posX >= nMinCellX && posX <= nMaxCellX && posY >= nMinCellY && posY <= nMaxCellY;
+                if (take && check_levels) { if (kp.octave < Q.min_level) take = false; if (Q.max_level >= 0 && kp.octave > Q.max_level) take = false; }
+                if (take) take = fabsf(fsub(kp.x, Q.u)) < Q.radius && fabsf(fsub(kp.y, Q.v)) < Q.radius;
+                if (take) { const float ur = uRight[j]; if (ur > 0 && fabsf(fsub(Q.ur, ur)) > Q.radius) take = false; }
+                if (take) {
+                    const int d = hamming256(a, desc + (size_t)j * 8);
+                    if (d > max_dist) take = false;
+                    key = ((u64)d << 40) | ((u64)posX << 32) | ((u64)posY << 24) | (u64)j;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (take) { const int p = n + __popc(m & ((1u << lane) - 1)); if (p < SBP_K) sh[w][p] = key; }
+            n += __popc(m);
+        }
+    }
+    __syncwarp();
+    const int stored = min(n, SBP_K);
+    // rank sort (keys are distinct: they embed j)
+    for (int e = lane; e < stored; e += 32) {
+        const u64 key = sh[w][e];
+        int rank = 0;
+        for (int f = 0; f < stored; ++f) rank += sh[w][f] < key;
+        lists[(size_t)i * SBP_K + rank] = key;
+    }
+    if (lane == 0) counts[i] = n;          // n > SBP_K flags an overflow to the host
+}
+
+// One block.  Iterates  assign[i] = first candidate of i not owned by an earlier observed point  to its fixed point.
+// mode 0 (last frame, src/ORBmatcher.cc:1536-1593): best only, accept dist <= TH_HIGH (lists are pre-filtered).
+// mode 1 (local map, src/ORBmatcher.cc:79-127): best + second best with level / ratio test.
+__global__ void __launch_bounds__(1024) k_sbp_resolve(const u64* __restrict__ lists, const int* __restrict__ counts, int nq, int n_cur,
+                                                      const uint8_t* __restrict__ observed, const uint8_t* __restrict__ occupied,
+                                                      const olf_keypoint* __restrict__ kps, int mode, float nn_ratio,
+                                                      int* __restrict__ owner_a, int* __restrict__ owner_b, int* __restrict__ assign, int* __restrict__ rounds_out) {
+    __shared__ int s_changed;
+    int* own_prev = owner_a; int* own_new = owner_b;
+    for (int j = threadIdx.x; j < n_cur; j += 1024) { own_prev[j] = (occupied && occupied[j]) ? -1 : INT_MAX; }
+    for (int i = threadIdx.x; i < nq; i += 1024) assign[i] = -1;
+    __syncthreads();
+    int rounds = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_changed = 0;
+        for (int j = threadIdx.x; j < n_cur; j += 1024) own_new[j] = (occupied && occupied[j]) ? -1 : INT_MAX;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nq; i += 1024) {
+            const int cnt = min(counts[i], SBP_K);
+            int sel = -1;
+            if (mode == 0) {
+                for (int e = 0; e < cnt; ++e) { const int j = (int)(lists[(size_t)i * SBP_K + e] & 0xFFFFFF); if (!(own_prev[j] < i)) { sel = j; break; } }
+            } else {
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1, found = 0;
+                for (int e = 0; e < cnt && found < 2; ++e) {
+                    const u64 key = lists[(size_t)i * SBP_K + e];
+                    const int j = (int)(key & 0xFFFFFF), d = (int)(key >> 40);
+                    if (own_prev[j] < i) continue;
+                    if (found == 0) { if (d < bestDist) { bestDist = d; bestLevel = kps[j].octave; bestIdx = j; } }
+                    else if (d < bestDist2) { bestDist2 = d; bestLevel2 = kps[j].octave; }
+                    ++found;
+                }
+                if (bestIdx >= 0 && bestDist <= OLF_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > fmul(nn_ratio, (float)bestDist2))) sel = bestIdx;
+            }
+            if (sel != assign[i]) { assign[i] = sel; s_changed = 1; }
+            if (sel >= 0 && observed[i]) atomicMin(&own_new[sel], i);
+        }
+        __syncthreads();
+        ++rounds;
+        const int changed = s_changed;
+        int* t = own_prev; own_prev = own_new; own_new = t;
+        __syncthreads();
+        if (!changed || rounds > 4 * nq + 8) break;
+    }
+    if (threadIdx.x == 0) *rounds_out = rounds;
+}
+
+static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t* qdesc, const uint8_t* observed, const uint8_t* occupied,
+                      const olf_keypoint* cur_kps, const uint8_t* cur_desc, const float* cur_u_right, int n_cur, const olf_camera& cam,
+                      int mode, int max_dist, float nn_ratio, int* assign_out) {
+    const int nq = (int)q.size();
+    int rc;
+    if (n_cur >= (1 << 24)) { set_last_error("olf_search_by_projection: too many keypoints"); return OLF_ERR_CAPACITY; }
+    Planner pl;
+    const size_t o_q = pl.d((size_t)nq * sizeof(SbpQuery)), o_qd = pl.d((size_t)nq * 32), o_obs = pl.d(nq), o_occ = pl.d(std::max(n_cur, 1));
+    const size_t o_k = pl.d((size_t)n_cur * sizeof(olf_keypoint)), o_d = pl.d((size_t)n_cur * 32), o_u = pl.d((size_t)n_cur * 4);
+    const size_t o_lists = pl.d((size_t)nq * SBP_K * 8), o_cnt = pl.d((size_t)nq * 4), o_oa = pl.d((size_t)n_cur * 4), o_ob = pl.d((size_t)n_cur * 4), o_as = pl.d((size_t)nq * 4), o_r = pl.d(4);
+    const size_t p_in = pl.p((size_t)nq * (sizeof(SbpQuery) + 33) + (size_t)n_cur * (sizeof(olf_keypoint) + 37) + 64), p_out = pl.p((size_t)nq * 8 + 16);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->stream;
+    uint8_t* hp = hptr<uint8_t>(c, p_in);
+    size_t off = 0;
+    auto up = [&](size_t dev_off, const void* src, size_t bytes) -> int {
+        if (!bytes) return OLF_OK;
+        memcpy(hp + off, src, bytes);
+        cudaError_t e = cudaMemcpyAsync(c->a.dev.p + dev_off, hp + off, bytes, cudaMemcpyHostToDevice, s);
+        off += bytes;
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+        return OLF_OK;
+    };
+    if ((rc = up(o_q, q.data(), (size_t)nq * sizeof(SbpQuery))) || (rc = up(o_qd, qdesc, (size_t)nq * 32)) || (rc = up(o_obs, observed, nq)) ||
+        (rc = up(o_k, cur_kps, (size_t)n_cur * sizeof(olf_keypoint))) || (rc = up(o_d, cur_desc, (size_t)n_cur * 32)) || (rc = up(o_u, cur_u_right, (size_t)n_cur * 4))) return rc;
+    if (occupied && (rc = up(o_occ, occupied, n_cur))) return rc;
+    GridParams G; G.min_x = cam.min_x; G.min_y = cam.min_y;
+    G.inv_w = (float)OLF_GRID_COLS / (cam.max_x - cam.min_x); G.inv_h = (float)OLF_GRID_ROWS / (cam.max_y - cam.min_y);       // src/Frame.cc:185-186
+    k_sbp_candidates<<<(nq + 7) / 8, 256, 0, s>>>(dptr<SbpQuery>(c, o_q), dptr<uint32_t>(c, o_qd), nq, dptr<olf_keypoint>(c, o_k), dptr<uint32_t>(c, o_d), dptr<float>(c, o_u), n_cur,
+                                                  G, max_dist, dptr<u64>(c, o_lists), dptr<int>(c, o_cnt));
+    k_sbp_resolve<<<1, 1024, 0, s>>>(dptr<u64>(c, o_lists), dptr<int>(c, o_cnt), nq, n_cur, dptr<uint8_t>(c, o_obs), occupied ? dptr<uint8_t>(c, o_occ) : nullptr,
+                                     dptr<olf_keypoint>(c, o_k), mode, nn_ratio, dptr<int>(c, o_oa), dptr<int>(c, o_ob), dptr<int>(c, o_as), dptr<int>(c, o_r));
+    int* ho = hptr<int>(c, p_out);
+    OLF_CUDA(cudaMemcpyAsync(ho, dptr<int>(c, o_as), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(ho + nq, dptr<int>(c, o_cnt), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < nq; ++i) {
+        if (ho[nq + i] > SBP_K) { set_last_error("olf_search_by_projection: more than 128 candidates in one search window"); return OLF_ERR_CAPACITY; }
+        assign_out[i] = ho[i];
+    }
+    return OLF_OK;
+}
+
+static void mat3_mul_vec(const float* R, const float* v, float* o) { for (int r = 0; r < 3; ++r) o[r] = R[3 * r] * v[0] + R[3 * r + 1] * v[1] + R[3 * r + 2] * v[2]; }
+
+int search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches_out, int device) {
+    if (!a || !assigned_cur || !cur_point || !nmatches_out || a->n_cur < 0 || a->n_last < 0 || !a->scale_factors) { set_last_error("olf_search_by_projection_last: bad arguments"); return OLF_ERR_ARG; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    for (int j = 0; j < a->n_cur; ++j) cur_point[j] = -1;
+    for (int i = 0; i < a->n_last; ++i) assigned_cur[i] = -1;
+    *nmatches_out = 0;
+    if (a->n_cur == 0 || a->n_last == 0) return OLF_OK;
+    // host part of the reference function: motion direction and per-point projection (:1485-1531), float ops in order
+    float twc[3], tlc[3];
+    for (int r = 0; r < 3; ++r) twc[r] = -(a->Rcw[r] * a->tcw[0] + a->Rcw[3 + r] * a->tcw[1] + a->Rcw[6 + r] * a->tcw[2]);
+    mat3_mul_vec(a->Rlw, twc, tlc);
+    for (int r = 0; r < 3; ++r) tlc[r] = tlc[r] + a->tlw[r];
+    const float mb = a->cam.bf / a->cam.fx;
+    const bool bForward = tlc[2] > mb && !a->mono, bBackward = -tlc[2] > mb && !a->mono;
+    std::vector<SbpQuery> q(a->n_last);
+    for (int i = 0; i < a->n_last; ++i) {
+        SbpQuery& Q = q[i];
+        memset(&Q, 0, sizeof(Q));
+        if (!a->last_has_point[i]) continue;
+        float x3Dc[3];
+        mat3_mul_vec(a->Rcw, a->last_world_pos + 3 * i, x3Dc);
+        for (int r = 0; r < 3; ++r) x3Dc[r] = x3Dc[r] + a->tcw[r];
+        const float invzc = (float)(1.0 / x3Dc[2]);
+        if (invzc < 0) continue;
+        const float u = a->cam.fx * x3Dc[0] * invzc + a->cam.cx, v = a->cam.fy * x3Dc[1] * invzc + a->cam.cy;
+        if (u < a->cam.min_x || u > a->cam.max_x) continue;
+        if (v < a->cam.min_y || v > a->cam.max_y) continue;
+        const int oct = a->last_kps[i].octave;
+        Q.u = u; Q.v = v; Q.radius = a->th * a->scale_factors[oct]; Q.ur = u - a->cam.bf * invzc;
+        if (bForward) { Q.min_level = oct; Q.max_level = -1; }
+        else if (bBackward) { Q.min_level = 0; Q.max_level = oct; }
+        else { Q.min_level = oct - 1; Q.max_level = oct + 1; }
+        Q.valid = 1;
+    }
+    if ((rc = sbp_common(c, q, a->last_point_desc, a->last_point_observed, nullptr, a->cur_kps, a->cur_desc, a->cur_u_right, a->n_cur, a->cam, 0, OLF_TH_HIGH, 0.f, assigned_cur))) return rc;
+    // bookkeeping of the reference on the resolved assignments (:1564-1615): last writer wins, rotation histogram pruning
+    int nmatches = 0;
+    std::vector<int> rot[OLF_HISTO_LENGTH];
+    const float factor = 1.0f / OLF_HISTO_LENGTH;
+    for (int i = 0; i < a->n_last; ++i) {
+        const int j = assigned_cur[i];
+        if (j < 0) continue;
+        cur_point[j] = i; nmatches++;
+        if (a->check_orientation) {
+            float r = a->last_kps[i].angle - a->cur_kps[j].angle;
+            if (r < 0.0) r += 360.0f;
+            int bin = (int)roundf(r * factor);
+            if (bin == OLF_HISTO_LENGTH) bin = 0;
+            rot[bin].push_back(j);
+        }
+    }
+    if (a->check_orientation) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;          // ComputeThreeMaxima (:1749-1790)
+        for (int i = 0; i < OLF_HISTO_LENGTH; i++) {
+            const int sz = (int)rot[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; } else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < OLF_HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j : rot[i]) { cur_point[j] = -1; nmatches--; }
+    }
+    *nmatches_out = nmatches;
+    return OLF_OK;
+}
+
+int search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches_out, int device) {
+    if (!a || !assigned_cur || !nmatches_out || a->n_cur < 0 || a->n_points < 0 || !a->scale_factors) { set_last_error("olf_search_by_projection_map: bad arguments"); return OLF_ERR_ARG; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    for (int i = 0; i < a->n_points; ++i) assigned_cur[i] = -1;
+    *nmatches_out = 0;
+    if (a->n_cur == 0 || a->n_points == 0) return OLF_OK;
+    const bool bFactor = a->th != 1.0;
+    std::vector<SbpQuery> q(a->n_points);
+    for (int i = 0; i < a->n_points; ++i) {
+        SbpQuery& Q = q[i];
+        const int lvl = a->pred_level[i];
+        float r = (a->view_cos[i] > 0.998) ? 2.5f : 4.0f;          // RadiusByViewingCos (:133-139)
+        if (bFactor) r *= a->th;
+        Q.u = a->proj_x[i]; Q.v = a->proj_y[i]; Q.radius = r * a->scale_factors[lvl]; Q.ur = a->proj_xr[i];
+        Q.min_level = lvl - 1; Q.max_level = lvl; Q.valid = 1;
+    }
+    if ((rc = sbp_common(c, q, a->point_desc, a->point_observed, a->cur_occupied, a->cur_kps, a->cur_desc, a->cur_u_right, a->n_cur, a->cam, 1, 256, a->nn_ratio, assigned_cur))) return rc;
+    int n = 0;
+    for (int i = 0; i < a->n_points; ++i) n += assigned_cur[i] >= 0;
+    *nmatches_out = n;
+    return OLF_OK;
+}
+
+}  // namespace olf

@@ -1,0 +1,15 @@
+// internal C++ interface of the matching half (see match.cu)
+#pragma once
+#include <cstdint>
+#include "../../include/olf_abi.h"
+namespace olf {
+struct OrbImpl;
+int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0, int* dist0, int* idx1, int* dist1, int device);
+int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int mutual, int* m12, int* nmatches, int device);
+int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const uint8_t* dl, int N, const olf_keypoint* kr, const uint8_t* dr, int Nr,
+                  float bf, float fx, float* uRight, float* depth);
+int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_keyline* kr, const uint8_t* dr, int n2, int img_w, int img_h,
+                 const olf_line_match_params* P, int* matches12, float* disp, double* le, int device);
+int search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device);
+int search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches, int device);
+}

@@ -1,0 +1,124 @@
+"""GPU parity of the matchers vs the CPU oracle: kNN(2) Hamming, matchNNR/match, stereo points (Hamming + SAD +
+parabola), stereo lines (grid-constrained), SearchByProjection (last frame / local map).
+Integer outputs bit-exact; uRight / depth / disparities compared bit-exact as well (same IEEE op sequence)."""
+import numpy as np
+import pytest
+from orc import oracle
+import orb_line_slam_b200 as olf
+from orb_line_slam_b200.frame import FrontEnd
+from orb_line_slam_b200.synth import Scene, CAMERAS, pose_f32
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_desc(n, seed, entropy_bits=256):
+    rng = np.random.RandomState(seed)
+    d = rng.randint(0, 256, (n, 32)).astype(np.uint8)
+    if entropy_bits < 256:      # few distinct bits -> many distance ties (exercises the lowest-index tie-break)
+        d[:, entropy_bits // 8:] = 0
+    return d
+
+
+@pytest.mark.parametrize("n1,n2,bits", [(500, 500, 256), (1, 1, 256), (1, 5, 256), (7, 2, 256), (3, 0, 256), (0, 4, 256),
+                                        (2000, 1500, 256), (700, 900, 16), (129, 4097, 8), (8192, 8192, 256)])
+def test_knn2(n1, n2, bits):
+    o, g = oracle(), olf.api(0)
+    a, b = _rand_desc(n1, n1 * 7 + n2, bits), _rand_desc(n2, n2 * 3 + 1, bits)
+    ro, rg = o.knn2_hamming(a, b), g.knn2_hamming(a, b)
+    for x, y, name in zip(ro, rg, ("idx0", "dist0", "idx1", "dist1")):
+        assert np.array_equal(x, y), name
+
+
+@pytest.mark.parametrize("n1,n2,nnr,mutual,bits", [(500, 480, 0.9, True, 256), (500, 480, 0.75, False, 256), (300, 310, 0.9, True, 24),
+                                                   (5, 1, 0.9, True, 256), (1, 1, 0.9, False, 256), (0, 3, 0.9, True, 256)])
+def test_match_lines(n1, n2, nnr, mutual, bits):
+    o, g = oracle(), olf.api(0)
+    a, b = _rand_desc(n1, 11 + n1, bits), _rand_desc(n2, 13 + n2, bits)
+    if n1 > 10:      # plant true correspondences so that matches exist
+        b[: min(n1, n2) // 2] = a[: min(n1, n2) // 2] ^ (np.random.RandomState(5).randint(0, 256, (min(n1, n2) // 2, 32)) < 8).astype(np.uint8)
+    mo, no = o.match_lines(a, b, nnr, mutual)
+    mg, ng = g.match_lines(a, b, nnr, mutual)
+    assert no == ng and np.array_equal(mo, mg)
+    mo, no = o.match_nnr(a, b, nnr)
+    mg, ng = g.match_nnr(a, b, nnr)
+    assert no == ng and np.array_equal(mo, mg)
+
+
+@pytest.fixture(scope="module")
+def frames():
+    """Two consecutive stereo frames through both implementations (scene 'euroc' 640x480, C1 of BASELINE.json)."""
+    cam = "euroc"
+    sc = Scene(cam, 3)
+    o, g = oracle(), olf.api(0)
+    fo = FrontEnd(o, CAMERAS[cam], nfeatures=1000, nlines=200)
+    fg = FrontEnd(g, CAMERAS[cam], nfeatures=1000, nlines=200)
+    out = {"o": [], "g": [], "fo": fo, "fg": fg}
+    for f in range(2):
+        L, R = sc.stereo(f)
+        out["o"].append(fo.process(L, R, pose_f32(f)))
+        out["g"].append(fg.process(L, R, pose_f32(f)))
+    yield out
+    fo.close(); fg.close()
+
+
+def test_stereo_frame_parity(frames):
+    for a, b in zip(frames["o"], frames["g"]):
+        assert np.array_equal(a.kps, b.kps) and np.array_equal(a.desc, b.desc)
+        assert np.array_equal(a.kps_r, b.kps_r) and np.array_equal(a.desc_r, b.desc_r)
+        assert (a.u_right >= 0).sum() > 50
+        assert np.array_equal(a.u_right, b.u_right), "mvuRight"
+        assert np.array_equal(a.depth, b.depth), "mvDepth"
+        assert np.array_equal(a.kls, b.kls) and np.array_equal(a.ldesc, b.ldesc)
+        assert (a.line_matches >= 0).sum() > 10
+        assert np.array_equal(a.line_matches, b.line_matches), "matchGrid(lines)"
+        assert np.array_equal(a.line_disp, b.line_disp), "mvDisparity_l"
+        assert np.array_equal(a.line_le, b.line_le), "mvle_l"
+
+
+@pytest.mark.parametrize("th,mono,obs_mode", [(7.0, False, "all"), (14.0, False, "alt"), (7.0, True, "none"), (30.0, False, "alt")])
+def test_search_by_projection_last(frames, th, mono, obs_mode):
+    fo, fg = frames["fo"], frames["fg"]
+    last, cur = frames["o"][0], frames["o"][1]
+    n = len(last.kps)
+    obs = {"all": np.ones(n, np.uint8), "none": np.zeros(n, np.uint8), "alt": (np.arange(n) % 2).astype(np.uint8)}[obs_mode]
+    ao, ko = fo.sbp_last_args(cur, last, th, mono, True, obs)
+    ag, kg = fg.sbp_last_args(cur, last, th, mono, True, obs)
+    ro = fo.api.search_by_projection_last(ao, ko)
+    rg = fg.api.search_by_projection_last(ag, kg)
+    assert ro[2] > 20
+    assert np.array_equal(ro[0], rg[0]), "per-point assignment"
+    assert np.array_equal(ro[1], rg[1]), "CurrentFrame.mvpMapPoints after rotation check"
+    assert ro[2] == rg[2]
+
+
+@pytest.mark.parametrize("th,occ", [(1.0, False), (3.0, True), (8.0, True)])
+def test_search_by_projection_map(frames, th, occ):
+    fo, fg = frames["fo"], frames["fg"]
+    last, cur = frames["o"][0], frames["o"][1]
+    occupied = (np.arange(len(cur.kps)) % 5 == 0).astype(np.uint8) if occ else None
+    ao, ko = fo.sbp_map_args(cur, last, th, 0.8, occupied)
+    ag, kg = fg.sbp_map_args(cur, last, th, 0.8, occupied)
+    ro = fo.api.search_by_projection_map(ao, ko)
+    rg = fg.api.search_by_projection_map(ag, kg)
+    assert ro[1] > 10
+    assert np.array_equal(ro[0], rg[0]) and ro[1] == rg[1]
+
+
+def test_track_720p(frames):
+    """C2-shaped: 1280x720, 2000 ORB + 500 lines, full frame + frame-to-frame tracking matchers."""
+    cam = "zed720"
+    sc = Scene(cam, 0)
+    fo = FrontEnd(oracle(), CAMERAS[cam], 2000, 500)
+    fg = FrontEnd(olf.api(0), CAMERAS[cam], 2000, 500)
+    po, pg = [], []
+    for f in range(2):
+        L, R = sc.stereo(f)
+        po.append(fo.process(L, R, pose_f32(f))); pg.append(fg.process(L, R, pose_f32(f)))
+    for a, b in zip(po, pg):
+        assert np.array_equal(a.u_right, b.u_right) and np.array_equal(a.depth, b.depth)
+        assert np.array_equal(a.line_matches, b.line_matches) and np.array_equal(a.line_disp, b.line_disp)
+    to, tg = fo.track(po[1], po[0]), fg.track(pg[1], pg[0])
+    assert to["nmatches"] == tg["nmatches"] and to["nmatches"] > 100
+    for k in ("assigned", "cur_point", "line_matches"):
+        assert np.array_equal(to[k], tg[k]), k
+    fo.close(); fg.close()
