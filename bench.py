@@ -1,0 +1,287 @@
+#!/usr/bin/env python3
+"""bench.py -- stereo frames/sec of the ORB+line front end (extract + match) on 1..8 B200.
+
+A "step" = one 1280x720 stereo frame through the whole hot path:
+  ExtractORB(L), ExtractORB(R), ExtractLine(L), ExtractLine(R), ComputeStereoMatches, ComputeStereoMatches_Lines,
+  ORBmatcher::SearchByProjection(cur,last) and LineMatcher::match(last,cur)          [configs[1] of BASELINE.json]
+`value`  : frames/s with the images already resident in HBM (olf_frontend_process, on_device=1);
+`e2e`    : the same through the host-buffer entry points (host->device copies inside the timed region);
+results always come back to host memory (that is the API: Tracking.cc consumes host vectors).
+`--impl reference` times the CPU restatement of the reference path (oracle/, single thread like the north star's
+"single-thread CPU ExtractORB+ExtractLine+SearchByProjection") on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+import argparse, json, os, pathlib, subprocess, sys, threading, time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np
+
+WORKLOAD = dict(workload="1280x720 stereo synthetic seq, 2000 ORB + 500 LBD per eye, extract + stereo match + frame-to-frame match",
+                camera="zed720", nfeatures=2000, nlines=500, min_line_length=0.025)
+METRIC = "stereo frames/sec (extract+match, 1280x720)"
+N_BASE_FRAMES = 8            # distinct rendered poses
+N_DISTINCT = 80              # distinct stereo pairs (base frames + per-frame noise): 147 MB of input > 126 MB L2
+
+
+def make_sequence(n_distinct: int):
+    """Seeded synthetic stereo sequence.  Rendering is the slow part, so N_BASE_FRAMES poses are rendered
+    and every further pair is a base pair with fresh N(0,2) sensor noise -> all pairs are distinct images."""
+    from orb_line_slam_b200.synth import Scene, pose_f32
+    sc = Scene(WORKLOAD["camera"], 0)
+    base = [sc.stereo(f) for f in range(N_BASE_FRAMES)]
+    seq, poses = [], []
+    for i in range(n_distinct):
+        L, R = base[i % N_BASE_FRAMES]
+        if i >= N_BASE_FRAMES:
+            rng = np.random.RandomState(7000 + i)
+            L = np.clip(L.astype(np.int16) + np.rint(rng.normal(0, 2, L.shape)).astype(np.int16), 0, 255).astype(np.uint8)
+            R = np.clip(R.astype(np.int16) + np.rint(rng.normal(0, 2, R.shape)).astype(np.int16), 0, 255).astype(np.uint8)
+        seq.append((np.ascontiguousarray(L), np.ascontiguousarray(R)))
+        poses.append(pose_f32(i % N_BASE_FRAMES))
+    return sc, seq, poses
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def run_steps(pipes, frontends, track_fe, seq_imgs, poses, first, count, on_device, dev_imgs):
+    """Process frames [first, first+count) on len(pipes) concurrent rigs; frame f's tracking step waits for frame f-1."""
+    P = len(pipes)
+    done = [threading.Event() for _ in range(count + 1)]
+    blocks = [None] * (count + 1)
+    views = [None] * (count + 1)
+    stats = {"matches": 0, "line_matches": 0, "kps": 0, "lines": 0, "d2h": 0}
+    done[0].set()                      # the frame before the first one: nothing to track against
+    errors = []
+    lock = threading.Lock()
+
+    def worker(p):
+        try:
+            nat = pipes[p]
+            for k in range(p, count, P):
+                f = first + k
+                i = f % len(seq_imgs)
+                blk = nat.new_block()
+                if on_device:
+                    nat.process(dev_imgs[i][0], dev_imgs[i][1], blk, on_device=True)
+                else:
+                    nat.process(seq_imgs[i][0], seq_imgs[i][1], blk, on_device=False)
+                v = nat.view(blk, poses[i])
+                blocks[k + 1], views[k + 1] = blk, v
+                done[k].wait()
+                t = None
+                if views[k] is not None:           # TrackWithMotionModelWithLine matchers (src/Tracking.cc:1296,1308)
+                    t = track_fe[p].track(v, views[k])
+                with lock:
+                    if t is not None:
+                        stats["matches"] += t["nmatches"]; stats["line_matches"] += t.get("n_line_matches", 0)
+                    stats["kps"] += len(v.kps) + len(v.kps_r); stats["lines"] += len(v.kls) + len(v.kls_r)
+                    stats["d2h"] += (len(v.kps) + len(v.kps_r)) * 56 + len(v.kps) * 8 + (len(v.kls) + len(v.kls_r)) * 100 + len(v.kls) * 36
+                views[k] = None
+                done[k + 1].set()
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+            for d in done:
+                d.set()
+
+    ths = [threading.Thread(target=worker, args=(p,)) for p in range(P)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errors:
+        raise errors[0]
+    return stats
+
+
+def cpu_reference(frames, seq, poses, warm=1):
+    """Single-thread CPU restatement of the reference path (oracle) on `frames` frames; returns (fps, stats)."""
+    from orc import oracle
+    from orb_line_slam_b200.frame import FrontEnd
+    from orb_line_slam_b200.synth import CAMERAS
+    fe = FrontEnd(oracle(), CAMERAS[WORKLOAD["camera"]], WORKLOAD["nfeatures"], WORKLOAD["nlines"], WORKLOAD["min_line_length"])
+    last = None
+    t0 = None
+    for k in range(warm + frames):
+        if k == warm:
+            t0 = time.perf_counter()
+        L, R = seq[k % len(seq)]
+        cur = fe.process(L, R, poses[k % len(seq)])
+        if last is not None:
+            fe.track(cur, last)
+        last = cur
+    dt = time.perf_counter() - t0
+    fe.close()
+    return frames / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=24)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pipelines", type=int, default=0, help="concurrent stereo rigs per GPU (0 = auto)")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sc, seq, poses = make_sequence(N_BASE_FRAMES)
+        frames = max(4, min(args.steps, args.cpu_frames))
+        fps, dt = cpu_reference(frames, seq, poses, warm=min(args.warmup, 2))
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": frames, "warmup": min(args.warmup, 2),
+                "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": dict(WORKLOAD, note="CPU restatement of the reference path (oracle/, the reference itself needs OpenCV C++/Eigen/Pangolin and cannot be built here)"),
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port", "sample": f"{frames} consecutive frames of the bench sequence, single thread"},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import orb_line_slam_b200 as olf
+    from orb_line_slam_b200.frame import FrontEnd
+    from orb_line_slam_b200.synth import CAMERAS
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = olf.load_library()
+    import ctypes
+    lib.olf_kernel_launch_count.restype = ctypes.c_longlong
+    api = olf.api(local)
+    cam = CAMERAS[WORKLOAD["camera"]]
+    P = args.pipelines or max(2, min(8, (os.cpu_count() or 8) // (5 * max(1, world if world > 1 else 1))))
+    sc, seq, poses = make_sequence(N_DISTINCT)
+    # weak scaling: every rank runs the same number of frames of its own slice of the sequence
+    shift = rank * 11
+    seq = seq[shift:] + seq[:shift]; poses = poses[shift:] + poses[:shift]
+    dev_imgs = [(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()) for L, R in seq]
+    dev_ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in dev_imgs]
+    host_pinned = [(torch.from_numpy(L).pin_memory().numpy(), torch.from_numpy(R).pin_memory().numpy()) for L, R in seq]
+    fes = [FrontEnd(api, cam, WORKLOAD["nfeatures"], WORKLOAD["nlines"], WORKLOAD["min_line_length"]) for _ in range(P)]
+    # the call-by-call FrontEnd objects only serve the tracking matchers; extraction goes through the native rigs
+    pipes = [fe.native(WORKLOAD["nfeatures"], WORKLOAD["nlines"]) for fe in fes]
+    gather_buf = None
+    if world > 1:
+        nbytes = int(pipes[0].off.total)
+        gather_buf = (torch.empty(nbytes, dtype=torch.uint8, device="cuda"), torch.empty(world * nbytes, dtype=torch.uint8, device="cuda"))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(count, first, on_device):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.olf_kernel_launch_count()
+        ev0.record()
+        st = run_steps(pipes, pipes, fes, host_pinned, poses, first, count, on_device, dev_ptrs)
+        if dist is not None:
+            # trivial NCCL gather of the fixed-capacity keypoint/descriptor block of the rank's last frame
+            dist.all_gather_into_tensor(gather_buf[1], gather_buf[0])
+        torch.cuda.synchronize()
+        ev1.record(); torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        return ms, st, lib.olf_kernel_launch_count() - l0
+
+    timed(args.warmup, 0, True)                                   # warm-up (also sizes every internal buffer)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, st, launches = timed(args.steps, args.warmup, True)       # HBM-resident inputs
+    clocks = sampler.stop() if sampler else None
+    timed(min(args.warmup, 8), 0, False)
+    ms_e2e, st_e2e, _ = timed(args.steps, args.warmup, False)     # host buffers in, host results out
+    # live timing of the dominant kernel (k_lsd_grow): CUDA events on its own stream inside the library
+    grow_us = []
+    stats8 = (ctypes.c_int * 8)()
+    lib.olf_frontend_line.restype = ctypes.c_void_p
+    for nat in pipes:
+        for eye in range(2):
+            lh = lib.olf_frontend_line(nat.handle, eye)
+            if lh and lib.olf_line_last_stats(ctypes.c_void_p(lh), stats8) == 0:
+                grow_us.append(stats8[3])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        S = 1536 * 864
+        alg_bytes = 6 * S                                          # read angle+used once per px (5S), write used (S)
+        grow_ms = float(np.mean(grow_us)) / 1000.0 if grow_us else None
+        achieved = (alg_bytes / (grow_ms * 1e-3) / 1e9) if grow_ms else None
+        fps = world * args.steps / (ms / 1000.0)
+        fps_e2e = world * args.steps / (ms_e2e / 1000.0)
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": dict(WORKLOAD, pipelines_per_gpu=P, l2="inputs larger than L2: 80 distinct stereo pairs = 147 MB cycled",
+                               host_cores=os.cpu_count(), per_frame={k: v / max(args.steps, 1) for k, v in st.items()}),
+                "clocks": clocks,
+                "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 4 * 1280 * 720, "d2h_bytes_per_step": int(st_e2e["d2h"] / max(args.steps, 1)),
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "k_lsd_grow", "bound": "hbm", "achieved": achieved, "peak": peak,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)", "unit": "GB/s",
+                             "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel_ms": grow_ms,
+                             "algorithmic_bytes_per_launch": alg_bytes,
+                             "note": "latency-bound sequential region growing; HBM fraction is honest but not the limiter (see DESIGN.md)"}}
+        if not args.no_cpu_baseline:
+            frames = args.cpu_frames
+            cfps, dt = cpu_reference(frames, [(a, b) for a, b in host_pinned[:N_BASE_FRAMES]], poses[:N_BASE_FRAMES], warm=1)
+            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": 1, "kind": "port",
+                                    "sample": f"{frames} consecutive frames of the same sequence through oracle/ (single thread, {dt:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    for nat in pipes:
+        nat.close()
+    for fe in fes:
+        fe.close()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

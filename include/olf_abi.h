@@ -96,6 +96,8 @@ typedef struct olf_line olf_line;
 
 const char* olf_last_error(void);
 int olf_device_count(void);
+/* kernels launched by this library since load (bench.py reports the delta as gpu_launches) */
+long long olf_kernel_launch_count(void);
 
 /* ---- ORBextractor (include/ORBextractor.h:52-118; src/ORBextractor.cc:412-472, 1045-1134) ---------------- */
 olf_orb* olf_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device);
@@ -193,6 +195,46 @@ typedef struct olf_sbp_map_args {
     float th; float nn_ratio;
 } olf_sbp_map_args;
 int olf_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur /*n_points*/, int* nmatches, int device);
+
+/* ---- whole stereo frame: Frame::Frame(stereo+lines) (src/Frame.cc:136-221) ----------------------------------- */
+/* One rig = 2 ORB extractors + 2 line extractors on one device; olf_frontend_process runs ExtractORB(L|R) and
+ * ExtractLine(L|R) on 4 host threads (src/Frame.cc:164-171), then ComputeStereoMatches and
+ * ComputeStereoMatches_Lines, and fills ONE fixed-capacity POD block (the unit the multi-GPU driver gathers). */
+typedef struct olf_frontend_params {
+    int   nfeatures; float scale_factor; int nlevels; int ini_th_fast; int min_th_fast;   /* ORBextractor ctor */
+    int   has_lines;                       /* Config::hasLines() (src/LineExtractor.cc:37, src/Frame.cc:203) */
+    olf_line_params line;
+    olf_line_match_params line_match;
+    olf_camera cam;
+    int   cap_points;                      /* capacity per eye (>= nfeatures + 64: the quadtree may exceed nfeatures) */
+    int   cap_lines;
+} olf_frontend_params;
+
+typedef struct olf_frame_header {          /* first bytes of the result block */
+    int n_l, n_r;                          /* keypoints left / right  (Frame::N)        */
+    int m_l, m_r;                          /* keylines  left / right  (Frame::N_l)      */
+    int cap_points, cap_lines;
+    int status;                            /* OLF_OK or the first error of the frame    */
+    int reserved;
+} olf_frame_header;
+/* Block layout after the header (all offsets 64-byte aligned, see olf_frame_offsets):
+ *  kps_l[cap_p] desc_l[cap_p*32] kps_r[cap_p] desc_r[cap_p*32] u_right[cap_p] depth[cap_p]
+ *  kls_l[cap_l] ldesc_l[cap_l*32] kls_r[cap_l] ldesc_r[cap_l*32] lmatch[cap_l] ldisp[cap_l*2] lle[cap_l*3 doubles] */
+typedef struct olf_frame_offsets {
+    uint64_t kps_l, desc_l, kps_r, desc_r, u_right, depth, kls_l, ldesc_l, kls_r, ldesc_r, lmatch, ldisp, lle, total;
+} olf_frame_offsets;
+typedef struct olf_frontend olf_frontend;
+int  olf_frame_layout(int cap_points, int cap_lines, olf_frame_offsets* out);
+olf_frontend* olf_frontend_create(const olf_frontend_params* p, int device);
+void olf_frontend_destroy(olf_frontend* h);
+/* images: host pointers (on_device = 0) or device pointers (on_device = 1); result: host block of layout.total bytes */
+int  olf_frontend_process(olf_frontend* h, const uint8_t* img_l, const uint8_t* img_r, int width, int height, int stride,
+                          int on_device, void* result);
+/* the extractors of the rig (e.g. for olf_orb_get_level) */
+olf_orb*  olf_frontend_orb(olf_frontend* h, int eye);
+olf_line* olf_frontend_line(olf_frontend* h, int eye);
+/* last-call statistics: out[0..1] LSD rounds L/R, out[2..3] LSD waves L/R */
+int  olf_line_last_stats(const olf_line* h, int* out8);
 
 #ifdef __cplusplus
 }

@@ -163,20 +163,25 @@ static inline void gaussian_blur_q8(const Image8& src, const std::vector<int>& q
     std::vector<uint16_t> tmp((size_t)w * h);
     for (int y = 0; y < h; ++y) {
         const uint8_t* s = src.row(y);
+        uint16_t* t = tmp.data() + (size_t)y * w;
         for (int x = 0; x < w; ++x) {
             uint32_t a = 0;
-            for (int k = 0; k < n; ++k) a += (uint32_t)q[k] * s[reflect101(x + k - r, w)];
-            tmp[(size_t)y * w + x] = (uint16_t)a;
+            if (x >= r && x < w - r) { for (int k = 0; k < n; ++k) a += (uint32_t)q[k] * s[x + k - r]; }
+            else { for (int k = 0; k < n; ++k) a += (uint32_t)q[k] * s[reflect101(x + k - r, w)]; }
+            t[x] = (uint16_t)a;
         }
     }
     dst = Image8(w, h);
+    std::vector<uint32_t> acc(w);
     for (int y = 0; y < h; ++y) {
-        uint8_t* o = dst.row(y);
-        for (int x = 0; x < w; ++x) {
-            uint32_t a = 0;
-            for (int k = 0; k < n; ++k) a += (uint32_t)q[k] * tmp[(size_t)reflect101(y + k - r, h) * w + x];
-            o[x] = (uint8_t)((a + (1u << 15)) >> 16);
+        std::fill(acc.begin(), acc.end(), 0u);
+        for (int k = 0; k < n; ++k) {
+            const uint16_t* t = tmp.data() + (size_t)reflect101(y + k - r, h) * w;
+            const uint32_t qk = (uint32_t)q[k];
+            for (int x = 0; x < w; ++x) acc[x] += qk * t[x];
         }
+        uint8_t* o = dst.row(y);
+        for (int x = 0; x < w; ++x) o[x] = (uint8_t)((acc[x] + (1u << 15)) >> 16);
     }
 }
 
@@ -217,12 +222,34 @@ static inline int fast_score_px(const uint8_t* p, int stride) {
     int s = std::max(A, B) - 1;
     return s < 0 ? 0 : s;
 }
-// full-image score map; border of 3 px = 0.
-static inline void fast_score_map(const uint8_t* img, int w, int h, int stride, std::vector<uint8_t>& score) {
+// full-image score map; border of 3 px = 0.  Scores below `th` are never consulted by FAST(th) and are stored as 0,
+// which allows the usual early rejection (any 9-arc contains one pixel of every opposite pair).
+static inline void fast_score_map(const uint8_t* img, int w, int h, int stride, std::vector<uint8_t>& score, int th = 1) {
     score.assign((size_t)w * h, 0);
-    for (int y = 3; y < h - 3; ++y)
-        for (int x = 3; x < w - 3; ++x)
-            score[(size_t)y * w + x] = (uint8_t)fast_score_px(img + (size_t)y * stride + x, stride);
+    int off[16];
+    for (int k = 0; k < 16; ++k) off[k] = FAST_DY[k] * stride + FAST_DX[k];
+    for (int y = 3; y < h - 3; ++y) {
+        const uint8_t* row = img + (size_t)y * stride;
+        uint8_t* srow = score.data() + (size_t)y * w;
+        for (int x = 3; x < w - 3; ++x) {
+            const uint8_t* p = row + x;
+            const int v = p[0], lo = v - th, hi = v + th;
+            int a = p[off[0]], b = p[off[8]];
+            if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
+            a = p[off[4]]; b = p[off[12]];
+            if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
+            a = p[off[2]]; b = p[off[10]];
+            if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
+            a = p[off[6]]; b = p[off[14]];
+            if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
+            unsigned mpos = 0, mneg = 0;
+            for (int k = 0; k < 16; ++k) { const int q = p[off[k]]; mpos |= (unsigned)(q < lo) << k; mneg |= (unsigned)(q > hi) << k; }
+            auto run9 = [](unsigned m) { unsigned u = m | (m << 16); unsigned r = u & (u >> 1); r &= r >> 2; r &= r >> 4; r &= u >> 8; return r != 0; };
+            if (!run9(mpos) && !run9(mneg)) continue;
+            const int s = fast_score_px(p, stride);
+            srow[x] = (uint8_t)(s >= th ? s : 0);
+        }
+    }
 }
 struct FastKp { int x, y, score; };
 // cv::FAST(window, th, nonmax=true) on a w x h window (row-major output, window-local coords)
@@ -230,7 +257,7 @@ static inline void fast_detect(const uint8_t* img, int w, int h, int stride, int
     out.clear();
     if (w < 7 || h < 7) return;
     std::vector<uint8_t> sc;
-    fast_score_map(img, w, h, stride, sc);
+    fast_score_map(img, w, h, stride, sc, th);
     auto S = [&](int x, int y) -> int {
         if (x < 3 || y < 3 || x >= w - 3 || y >= h - 3) return 0;
         int s = sc[(size_t)y * w + x];

@@ -48,6 +48,23 @@ class Camera(C.Structure):
 _P = C.c_void_p
 
 
+class FrontendParams(C.Structure):
+    """olf_frontend_params"""
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("ini_th_fast", C.c_int),
+                ("min_th_fast", C.c_int), ("has_lines", C.c_int), ("line", LineParams), ("line_match", LineMatchParams),
+                ("cam", Camera), ("cap_points", C.c_int), ("cap_lines", C.c_int)]
+
+
+class FrameHeader(C.Structure):
+    _fields_ = [("n_l", C.c_int), ("n_r", C.c_int), ("m_l", C.c_int), ("m_r", C.c_int), ("cap_points", C.c_int),
+                ("cap_lines", C.c_int), ("status", C.c_int), ("reserved", C.c_int)]
+
+
+class FrameOffsets(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("kps_l", "desc_l", "kps_r", "desc_r", "u_right", "depth", "kls_l", "ldesc_l",
+                                          "kls_r", "ldesc_r", "lmatch", "ldisp", "lle", "total")]
+
+
 class SbpLastArgs(C.Structure):
     _fields_ = [("cur_kps", _P), ("cur_desc", _P), ("cur_u_right", _P), ("n_cur", C.c_int),
                 ("cam", Camera), ("scale_factors", _P), ("nlevels", C.c_int),
@@ -221,6 +238,31 @@ class FrontEndApi:
                                      C.byref(params), ptr(m), ptr(disp), ptr(le), *self._dev)
         self.check(rc, "stereo_lines")
         return m, disp, le
+
+    # ---- whole frame (product library only) ----
+    def frame_layout(self, cap_points, cap_lines) -> "FrameOffsets":
+        o = FrameOffsets()
+        self.check(self.fn("frame_layout")(C.c_int(cap_points), C.c_int(cap_lines), C.byref(o)), "frame_layout")
+        return o
+
+    def frontend_create(self, params: "FrontendParams"):
+        f = self.fn("frontend_create"); f.restype = C.c_void_p
+        h = f(C.byref(params), *self._dev)
+        if not h:
+            self.check(OLF_ERR_INTERNAL, "frontend_create")
+        return C.c_void_p(h)
+
+    def frontend_destroy(self, h):
+        f = self.fn("frontend_destroy"); f.restype = None; f(h)
+
+    def frontend_process(self, h, img_l, img_r, width, height, stride, on_device, result: np.ndarray):
+        """img_l / img_r: numpy uint8 images (host) or integer device addresses (on_device=True)."""
+        if on_device:
+            pl, pr = C.c_void_p(int(img_l)), C.c_void_p(int(img_r))
+        else:
+            pl, pr = ptr(img_l), ptr(img_r)
+        rc = self.fn("frontend_process")(h, pl, pr, C.c_int(width), C.c_int(height), C.c_int(stride), C.c_int(int(on_device)), ptr(result))
+        self.check(rc, "frontend_process")
 
     def search_by_projection_last(self, args: SbpLastArgs, keep):
         n_last, n_cur = args.n_last, args.n_cur

@@ -4,9 +4,13 @@
 #include "line.h"
 #include "match.h"
 #include <mutex>
+#include <atomic>
 
 namespace olf {
 static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_total() { return g_launches.load(); }
 void set_last_error(const std::string& s) { g_err = s; }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     char buf[512];
@@ -20,6 +24,7 @@ using namespace olf;
 
 extern "C" {
 const char* olf_last_error(void) { return g_err.c_str(); }
+long long olf_kernel_launch_count(void) { return launches_total(); }
 int olf_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
 olf_orb* olf_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device) {

@@ -11,6 +11,7 @@
 namespace olf {
 
 void set_last_error(const std::string& s);
+void count_launches(int n);            // bookkeeping for bench.py's gpu_launches (kernels launched by this library)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define OLF_CUDA(call)                                                         \

@@ -43,6 +43,7 @@ __global__ void k_resize_exact(const uint8_t* __restrict__ src, int sw, int sh, 
 // n2_thresh = smallest gx^2+gy^2 whose norm sqrt(n2/4.0) exceeds rho (computed exactly on the host).
 __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, int W, int H, int pitch, int n2_thresh,
                                                   float* __restrict__ ang, short2_t* __restrict__ dabc,
+                                                  const float2_t* __restrict__ tab_acc, float2_t* __restrict__ cs,
                                                   u64* __restrict__ claim0, u64* __restrict__ claim1, int* __restrict__ n2max) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -60,7 +61,9 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
             const int v = gx * gx + gy * gy;
             if (v >= n2_thresh) { a = olf::lsd::fast_atan2_deg((float)gx, (float)-gy); n2 = v; }
         }
-        ang[q] = a; dabc[q] = d; claim0[q] = kClaimNone; claim1[q] = kClaimNone;
+        float2_t c; c.x = 0.f; c.y = 0.f;
+        if (a >= 0.f) c = tab_acc[tab_index(d)];
+        ang[q] = a; dabc[q] = d; cs[q] = c; claim0[q] = kClaimNone; claim1[q] = kClaimNone;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n2 = max(n2, __shfl_xor_sync(0xffffffffu, n2, o));
@@ -184,6 +187,349 @@ __global__ void __launch_bounds__(256) k_lsd_grow(const GrowState G) {
         __threadfence();
         grid.sync();
         if (((volatile int*)G.status)[0] != 0) break;
+    }
+    if (tid == 0) { G.status[1] = (int)round; G.status[2] = n_waves; }
+}
+
+// ---- region growing, warp-cooperative: one WARP per seed per round ----------------------------------------------
+// Same operator as grow_seed() in lsd_core.h (which stays the executable specification, emulated on the host by
+// tests/emul), restructured so that nothing on the sequential critical path of a region is a dependent global load:
+//   * up to 3 queue entries x 9 neighbours are examined per step; each of 27 lanes fetches its neighbour's angle, both
+//     claim words and (cos, sin) in parallel (one L2 latency per step instead of ~30);
+//   * the order-dependent accept decisions (running region angle) are then replayed in the reference's scan order on
+//     warp-uniform registers, visiting only lanes whose prefetched data make them potential accepts;
+//   * pixel lists live in 31-entry chunks: the chunk being written / read / compared sits in one register per lane and
+//     moves to and from global memory as one coalesced 128-byte transaction;
+//   * claims are atomicMin by lane 0; their return values are awaited once per step, which makes the warp's own claims
+//     visible to the next step's (L2) loads -- no duplicate can enter a list.
+#define GW_WARPS 8
+struct GrowStateW {
+    GrowState G;
+    const float2_t* cs;         // per pixel (cos, sin) as accumulated by the reference: tab_acc[(DA,BC)]
+    unsigned* work_ctr;         // [2*max_rounds + 64] zero-initialised work counters (one per round / finalise pass)
+    // per seed and round parity: the aligned candidates that were refused because a NON-final higher-priority claim held
+    // them (one chunk at most; count 255 = too many, always re-grow).  Together with the pixel list they are the complete
+    // set of external facts a growth depended on, which is what lets an unchanged region be verified instead of re-grown.
+    unsigned* blk_chunk[2]; int* blk_cnt[2];
+    int* dbg;                   // optional per-round trace (see OLF_LSD_TRACE)
+};
+
+__device__ __forceinline__ bool blocked_vals(u64 e_prev, u64 e_cur, u64 sf_prev, u64 sf_cur, u64 prio) {
+    u64 sf = e_prev >> 40;
+    if (sf == 0) return true;
+    if (sf == sf_prev && (e_prev & kPrioMask) < prio) return true;
+    sf = e_cur >> 40;
+    if (sf == 0) return true;
+    if (sf == sf_cur && (e_cur & kPrioMask) <= prio) return true;
+    return false;
+}
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ double shfl_f64(double v, int src) { return __longlong_as_double((long long)shfl_u64((u64)__double_as_longlong(v), src)); }
+
+// returns true if the seed's outcome differs from the previous round
+__device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int seed, u64 prio, int lane) {
+    const GrowState& G = S.G;
+    const GrowArgs& A = G.A;
+    const int cur = round & 1, prv = (round - 1) & 1;
+    const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
+    const u64 mine = (sf_cur << 40) | prio;
+    u64* claim_cur = A.claim[cur];
+    const u64* claim_prev = A.claim[prv];
+    unsigned* pool = A.pool[cur];
+    const unsigned* ppool = A.pool[prv];
+    const unsigned prev_head = __ldcg(&G.head[prv][i]);
+    const int prev_cnt = __ldcg(&G.cnt[prv][i]);
+    // claim the seed pixel (authoritative check through the atomic's return value)
+    int dead = 0;
+    unsigned first_chunk = 0;
+    if (lane == 0) {
+        const u64 ep = __ldcg(&claim_prev[seed]);
+        u64 sf = ep >> 40;
+        dead = (sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio);
+        if (!dead) {
+            const u64 old = atomicMin(&claim_cur[seed], mine);
+            sf = old >> 40;
+            dead = (sf == 0) || (sf == sf_cur && (old & kPrioMask) < prio);
+        }
+    }
+    dead = __shfl_sync(0xffffffffu, dead, 0);
+    if (dead) {
+        if (lane == 0) { G.cnt[cur][i] = 0; G.head[cur][i] = kNull; }
+        return prev_cnt != 0;
+    }
+    // ---- verify instead of re-grow: last round's run is still exact iff every pixel it accepted is still free of
+    // higher-priority claims and every aligned candidate it was refused (by a non-final claim) is still held.
+    if (prev_cnt > 0) {
+        const int bc = __ldcg(&S.blk_cnt[prv][i]);
+        bool ok = bc != 255;
+        if (ok) {
+            unsigned chunk = prev_head;
+            for (int k = 0; k < prev_cnt && ok; k += kChunk - 1) {
+                const unsigned v = __ldcg(&ppool[(size_t)chunk * kChunk + lane]);
+                bool bad = false;
+                if (lane < kChunk - 1 && k + lane < prev_cnt) {
+                    const u64 ep = __ldcg(&claim_prev[v]);
+                    bad = ((ep >> 40) == sf_prev) && ((ep & kPrioMask) < prio);
+                }
+                ok = !__any_sync(0xffffffffu, bad);
+                chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
+            }
+        }
+        if (ok && bc > 0) {
+            const unsigned v = __ldcg(&ppool[(size_t)__ldcg(&S.blk_chunk[prv][i]) * kChunk + lane]);
+            bool bad = false;
+            if (lane < bc) {
+                const u64 ep = __ldcg(&claim_prev[v]);
+                const u64 sf = ep >> 40;
+                bad = !((sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio));      // no longer held -> must re-grow
+            }
+            ok = !__any_sync(0xffffffffu, bad);
+        }
+        if (ok) {                                                   // carry the region over: re-stamp its claims for this round
+            unsigned chunk = prev_head;
+            for (int k = 0; k < prev_cnt; k += kChunk - 1) {
+                const unsigned v = __ldcg(&ppool[(size_t)chunk * kChunk + lane]);
+                if (lane < kChunk - 1 && k + lane < prev_cnt && v != (unsigned)seed) atomicMin(&claim_cur[v], mine);
+                chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
+            }
+            if (lane == 0) {
+                G.head[cur][i] = prev_head; G.cnt[cur][i] = prev_cnt;
+                S.blk_chunk[cur][i] = __ldcg(&S.blk_chunk[prv][i]); S.blk_cnt[cur][i] = bc;
+            }
+            return false;
+        }
+    }
+    if (lane == 0) first_chunk = atomicAdd(A.pool_ctr[cur], 1u);
+    first_chunk = __shfl_sync(0xffffffffu, first_chunk, 0);
+    if (first_chunk >= A.pool_chunks) { if (lane == 0) { G.status[0] = OLF_ERR_CAPACITY; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; } return true; }
+    // writer / reader / comparer state (warp-uniform scalars + one payload register per lane)
+    const unsigned w_head = first_chunk;
+    unsigned w_chunk = first_chunk; int w_n = 0; unsigned w_val = 0;
+    unsigned r_chunk = first_chunk; int r_n = 0; unsigned r_val = 0;
+    unsigned pv_val = (prev_cnt > 0 && prev_head != kNull) ? __ldcg(&ppool[(size_t)prev_head * kChunk + lane]) : kNull;
+    int pv_n = 0;
+    bool same = prev_cnt > 0;
+    int count = 0;
+    bool overflow = false;
+    unsigned b_chunk = kNull; int b_n = 0;                           // refused-candidate record (lazily allocated chunk)
+    auto record_blocked = [&](unsigned pix) {
+        if (b_n == 255) return;
+        if (b_chunk == kNull) {
+            unsigned nc = 0;
+            if (lane == 0) nc = atomicAdd(A.pool_ctr[cur], 1u);
+            nc = __shfl_sync(0xffffffffu, nc, 0);
+            if (nc >= A.pool_chunks) { overflow = true; return; }
+            b_chunk = nc;
+        }
+        if (b_n >= kChunk - 1) { b_n = 255; return; }
+        if (lane == 0) pool[(size_t)b_chunk * kChunk + b_n] = pix;
+        ++b_n;
+    };
+    auto push = [&](unsigned pix) {
+        if (w_n == kChunk - 1) {                                   // flush the full chunk, chain a new one
+            unsigned nc = 0;
+            if (lane == 0) nc = atomicAdd(A.pool_ctr[cur], 1u);
+            nc = __shfl_sync(0xffffffffu, nc, 0);
+            if (nc >= A.pool_chunks) { overflow = true; return; }
+            const unsigned outv = (lane == kChunk - 1) ? nc : w_val;
+            pool[(size_t)w_chunk * kChunk + lane] = outv;
+            if (r_chunk == w_chunk) r_val = outv;                  // the reader keeps the chunk it is still consuming
+            w_chunk = nc; w_n = 0;
+        }
+        if (lane == w_n) w_val = pix;
+        ++w_n;
+        if (same) {                                                // lock-step comparison with last round's list
+            if (count >= prev_cnt) same = false;
+            else {
+                if (__shfl_sync(0xffffffffu, pv_val, pv_n) != pix) same = false;
+                if (++pv_n == kChunk - 1) {
+                    const unsigned nxt = __shfl_sync(0xffffffffu, pv_val, kChunk - 1);
+                    pv_val = (nxt != kNull) ? __ldcg(&ppool[(size_t)nxt * kChunk + lane]) : kNull;
+                    pv_n = 0;
+                }
+            }
+        }
+        ++count;
+    };
+    push((unsigned)seed);
+    double reg_angle = d_mul((double)__ldg(&A.ang[seed]), kDegToRads);
+    const float2_t t0 = A.tab_seed[tab_index(A.dabc[seed])];
+    float sumdx = t0.x, sumdy = t0.y;
+    unsigned pend = 0;
+    int i_rd = 0;
+    while (i_rd < count && !overflow) {
+        const int nb = min(3, count - i_rd);
+        // entry pixels of this step (uniform), taken from the chunk registers
+        int ent[3] = {-1, -1, -1};
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            if (e < nb) {
+                if (r_n == kChunk - 1) {                           // lazily step to the next chunk (the old one is flushed by now)
+                    r_chunk = __shfl_sync(0xffffffffu, r_val, kChunk - 1); r_n = 0;
+                    if (r_chunk != w_chunk) r_val = __ldcg(&pool[(size_t)r_chunk * kChunk + lane]);
+                }
+                ent[e] = (int)((r_chunk == w_chunk) ? __shfl_sync(0xffffffffu, w_val, r_n) : __shfl_sync(0xffffffffu, r_val, r_n));
+                ++r_n;
+            }
+        }
+        // lane -> (entry, neighbour) in the reference's scan order: yy outer, xx inner
+        const int e = lane / 9, nidx = lane - e * 9;
+        const int p = e == 0 ? ent[0] : (e == 1 ? ent[1] : ent[2]);
+        bool valid = lane < 27 && e < nb;
+        int q = -1 - lane;
+        float aq = -1.f; float2_t csq; csq.x = 0.f; csq.y = 0.f;
+        bool pot = false, held = false;
+        if (valid) {
+            const int px = p % A.W, py = p / A.W;
+            const int xx = px + (nidx % 3) - 1, yy = py + (nidx / 3) - 1;
+            valid = xx >= 0 && xx < A.W && yy >= 0 && yy < A.H;
+            if (valid) {
+                q = yy * A.W + xx;
+                aq = __ldg(&A.ang[q]);
+                const u64 ep = __ldcg(&claim_prev[q]);
+                const u64 ec = __ldcg(&claim_cur[q]);
+                csq = S.cs[q];
+                if (aq >= 0.f) {
+                    const u64 sp = ep >> 40, sc = ec >> 40;
+                    const bool fin = sp == 0 || sc == 0;                                       // finalised region: never comes back
+                    const bool own = sc == sf_cur && (ec & kPrioMask) == prio;                // already in this region
+                    held = (sp == sf_prev && (ep & kPrioMask) < prio) || (sc == sf_cur && (ec & kPrioMask) < prio);
+                    pot = !fin && !own;
+                }
+            }
+        }
+        const unsigned held_m = __ballot_sync(0xffffffffu, held);
+        const unsigned dup = __match_any_sync(0xffffffffu, q);     // lanes looking at the same pixel
+        unsigned m = __ballot_sync(0xffffffffu, pot);
+        unsigned accepted = 0;
+        while (m) {
+            const int c = __ffs(m) - 1;
+            m &= m - 1;
+            if (__shfl_sync(0xffffffffu, dup, c) & accepted) continue;            // already taken earlier in this step
+            const float a_c = __shfl_sync(0xffffffffu, aq, c);
+            double n_theta = d_sub(reg_angle, d_mul((double)a_c, kDegToRads));   // isAligned
+            if (n_theta < 0) n_theta = -n_theta;
+            if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
+            if (!(n_theta <= A.prec)) continue;
+            const int qc = __shfl_sync(0xffffffffu, q, c);
+            if ((held_m >> c) & 1u) { record_blocked((unsigned)qc); if (overflow) break; continue; }   // aligned but held by a higher-priority seed
+            accepted |= 1u << c;
+            const float cx = __shfl_sync(0xffffffffu, csq.x, c), cy = __shfl_sync(0xffffffffu, csq.y, c);
+            if (lane == 0) { const u64 old = atomicMin(&claim_cur[qc], mine); pend += (unsigned)(old >> 63); }
+            push((unsigned)qc);
+            if (overflow) break;
+            sumdx = f_add(sumdx, cx);
+            sumdy = f_add(sumdy, cy);
+            reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads);
+        }
+        // wait for this step's claims: the next step's loads must observe them
+        pend = __shfl_sync(0xffffffffu, pend, 0);
+        i_rd += nb;
+    }
+    if (overflow) { if (lane == 0) { G.status[0] = OLF_ERR_CAPACITY; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; } return true; }
+    // flush the partial chunk
+    if (lane < w_n || lane == kChunk - 1) pool[(size_t)w_chunk * kChunk + lane] = (lane == kChunk - 1) ? kNull : w_val;
+    if (lane == 0) { G.head[cur][i] = w_head; G.cnt[cur][i] = count; G.regang[i] = reg_angle; S.blk_chunk[cur][i] = b_chunk; S.blk_cnt[cur][i] = b_n; }
+    return !(same && count == prev_cnt) || (pend == 0xFFFFFFFFu);
+}
+
+__global__ void __launch_bounds__(GW_WARPS * 32) k_lsd_grow_w(const GrowStateW S) {
+    cg::grid_group grid = cg::this_grid();
+    const GrowState& G = S.G;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int n_waves = G.plan->n_waves;
+    unsigned round = 1;
+    unsigned pass = 0;                                   // index into the zero-initialised work counters
+    for (int wv = 0; wv < n_waves; ++wv) {
+        const int lo = G.plan->wave_start[wv], hi = G.plan->wave_start[wv + 1];
+        for (int i = lo + tid; i < hi; i += nth) { G.cnt[0][i] = 0; G.cnt[1][i] = 0; }
+        if (tid == 0) *G.A.pool_ctr[0] = 0;                          // one bump pool per wave (lists may be carried over rounds)
+        for (;;) {
+            __threadfence();
+            grid.sync();
+            const int cur = round & 1, prv = (round - 1) & 1;
+            const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
+            bool any_change = false;
+            // seeds are handed out in batches of `bsz` (one per lane for the cheap liveness test); small waves use small
+            // batches so that the live seeds of a batch do not queue up behind each other inside one warp
+            const int nwarps = (int)(nth >> 5);
+            const int bsz = max(1, min(32, (hi - lo) / (2 * nwarps)));
+            for (;;) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&S.work_ctr[pass], (unsigned)bsz);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lo + (int)base >= hi) break;
+                const int i = lo + (int)base + lane;
+                int seed = 0; u64 prio = 0; bool alive = false;
+                if (i < hi && lane < bsz) {
+                    seed = G.seed_pix[i]; prio = G.seed_prio[i];
+                    alive = !blocked_vals(__ldcg(&G.A.claim[prv][seed]), __ldcg(&G.A.claim[cur][seed]), sf_prev, sf_cur, prio);
+                    if (!alive) { if (__ldcg(&G.cnt[prv][i]) != 0) any_change = true; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, alive);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int s_seed = __shfl_sync(0xffffffffu, seed, src);
+                    const u64 s_prio = shfl_u64(prio, src);
+                    if (grow_seed_warp(S, round, lo + (int)base + src, s_seed, s_prio, lane)) any_change = true;
+                }
+            }
+            if (__syncthreads_or(any_change) && threadIdx.x == 0) G.changed[round] = 1;
+            __threadfence();
+            grid.sync();
+            ++pass;
+            const bool changed = __ldcg(&G.changed[round]) != 0;
+            if (!changed || round + 2 >= G.max_rounds || __ldcg(&G.status[0]) != 0) break;
+            ++round;
+        }
+        // finalise the wave (warp per live seed): stamp the regions for good, keep the lists of accepted regions
+        {
+            const int cur = round & 1;
+            const unsigned* pool = G.A.pool[cur];
+            for (;;) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&S.work_ctr[pass], 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lo + (int)base >= hi) break;
+                const int i = lo + (int)base + lane;
+                const int c_l = (i < hi) ? __ldcg(&G.cnt[cur][i]) : 0;
+                unsigned m = __ballot_sync(0xffffffffu, c_l > 0);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int si = lo + (int)base + src;
+                    const int c = __shfl_sync(0xffffffffu, c_l, src);
+                    const u64 prio = G.seed_prio[si];
+                    const bool accept = c >= G.min_reg_size;
+                    unsigned off = 0;
+                    if (accept && lane == 0) off = atomicAdd(G.final_ctr, (unsigned)c);
+                    off = __shfl_sync(0xffffffffu, off, 0);
+                    unsigned chunk = __ldcg(&G.head[cur][si]);
+                    for (int k = 0; k < c; k += kChunk - 1) {
+                        const unsigned v = __ldcg(&pool[(size_t)chunk * kChunk + lane]);
+                        if (lane < kChunk - 1 && k + lane < c) {
+                            G.A.claim[0][v] = prio; G.A.claim[1][v] = prio;
+                            if (accept) G.final_pool[off + k + lane] = v;
+                        }
+                        chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
+                    }
+                    if (accept && lane == 0) {
+                        const unsigned r = atomicAdd(G.nreg, 1u);
+                        if (r < G.reg_cap) { LsdRegion R; R.prio = prio; R.off = off; R.count = c; R.reg_angle = __ldcg(&G.regang[si]); G.regs[r] = R; }
+                        else G.status[0] = OLF_ERR_CAPACITY;
+                    }
+                }
+            }
+        }
+        ++round; ++pass;
+        __threadfence();
+        grid.sync();
+        if (__ldcg(&G.status[0]) != 0) break;
     }
     if (tid == 0) { G.status[1] = (int)round; G.status[2] = n_waves; }
 }
@@ -397,7 +743,10 @@ struct LineImpl {
     DevBuf<double> regang;
     DevBuf<LsdPlan> plan;
     DevBuf<LsdRegion> regs;
-    DevBuf<float2_t> tab_seed, tab_acc;
+    DevBuf<float2_t> tab_seed, tab_acc, cs;
+    DevBuf<unsigned> work_ctr, blk_chunk0, blk_chunk1;
+    DevBuf<int> blk_cnt0, blk_cnt1;
+    bool scalar_grow = false;
     unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
     int grow_blocks = 0;
     PinBuf<RectRec> rect_host; PinBuf<double2> dir_host; PinBuf<float4> seg_host; PinBuf<int> status_host; PinBuf<unsigned> nreg_host;
@@ -405,6 +754,7 @@ struct LineImpl {
     DevBuf<short2_t> grad;
     PinBuf<LbdLine> lbd_lines; DevBuf<float4> rowsum; PinBuf<uint8_t> desc_host;
     int lbd_cap = 0;
+    cudaEvent_t ev_grow0 = nullptr, ev_grow1 = nullptr;
     int last_stats[8] = {0};
 };
 
@@ -476,6 +826,7 @@ LineImpl* line_create(const olf_line_params* p, int device) {
         for (int i = 0; i < nb * wb; i++) { const double dis = i - u; gG[i] = (float)std::exp(dis * dis * inv); }
     }
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev_grow0) == cudaSuccess && cudaEventCreate(&h->ev_grow1) == cudaSuccess;
     ok = ok && h->tab_seed.ensure(ts.size()) == OLF_OK && h->tab_acc.ensure(ta.size()) == OLF_OK;
     ok = ok && cudaMemcpy(h->tab_seed.p, ts.data(), ts.size() * sizeof(float2_t), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(h->tab_acc.p, ta.data(), ta.size() * sizeof(float2_t), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -484,9 +835,11 @@ LineImpl* line_create(const olf_line_params* p, int device) {
     int coop = 0, sms = 0, per_sm = 0;
     ok = ok && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && coop;
     ok = ok && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_grow, 256, 0) == cudaSuccess && per_sm > 0;
+    h->scalar_grow = getenv("OLF_LSD_SCALAR") != nullptr;         // A/B switch: thread-per-seed reference kernel
+    if (h->scalar_grow) ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_grow, 256, 0) == cudaSuccess && per_sm > 0;
+    else ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_grow_w, GW_WARPS * 32, 0) == cudaSuccess && per_sm > 0;
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
-    h->grow_blocks = sms * std::min(per_sm, 2);
+    h->grow_blocks = sms * std::min(per_sm, h->scalar_grow ? 2 : 4);
     return h;
 }
 
@@ -494,12 +847,15 @@ void line_destroy(LineImpl* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->ev_grow0) cudaEventDestroy(h->ev_grow0);
+    if (h->ev_grow1) cudaEventDestroy(h->ev_grow1);
     h->img_stage.release(); h->img.release(); h->blurred.release(); h->scaled.release(); h->lbd_blur.release(); h->coef.release();
     h->ang.release(); h->dabc.release(); h->claim0.release(); h->claim1.release(); h->seed_prio.release(); h->seed_pix.release();
     h->cnt0.release(); h->cnt1.release(); h->n2max.release(); h->status.release(); h->head0.release(); h->head1.release();
     h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool0.release(); h->pool1.release(); h->ctrs.release();
     h->changed.release(); h->final_pool.release(); h->regang.release(); h->plan.release(); h->regs.release();
-    h->tab_seed.release(); h->tab_acc.release(); h->rect_host.release(); h->dir_host.release(); h->seg_host.release();
+    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->work_ctr.release();
+    h->blk_chunk0.release(); h->blk_chunk1.release(); h->blk_cnt0.release(); h->blk_cnt1.release(); h->rect_host.release(); h->dir_host.release(); h->seg_host.release();
     h->status_host.release(); h->nreg_host.release(); h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
 }
@@ -533,6 +889,8 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
         (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->changed.ensure(h->max_rounds)) || (rc = h->plan.ensure(1)) ||
         (rc = h->pool0.ensure((size_t)h->pool_chunks * kChunk)) || (rc = h->pool1.ensure((size_t)h->pool_chunks * kChunk)) ||
+        (rc = h->cs.ensure(S)) || (rc = h->work_ctr.ensure(2 * h->max_rounds + 64)) ||
+        (rc = h->blk_chunk0.ensure(S)) || (rc = h->blk_chunk1.ensure(S)) || (rc = h->blk_cnt0.ensure(S)) || (rc = h->blk_cnt1.ensure(S)) ||
         (rc = h->regs.ensure(h->reg_cap)) || (rc = h->rect_host.ensure(h->reg_cap)) || (rc = h->dir_host.ensure(h->reg_cap)) ||
         (rc = h->seg_host.ensure(h->reg_cap)) || (rc = h->status_host.ensure(4)) || (rc = h->nreg_host.ensure(1))) return rc;
     h->img_w = w; h->img_h = hgt;
@@ -578,9 +936,10 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     OLF_CUDA(cudaMemsetAsync(h->ctrs.p, 0, 4 * sizeof(unsigned), s));
     OLF_CUDA(cudaMemsetAsync(h->status.p, 0, 4 * sizeof(int), s));
     OLF_CUDA(cudaMemsetAsync(h->changed.p, 0, h->max_rounds * sizeof(unsigned), s));
+    OLF_CUDA(cudaMemsetAsync(h->work_ctr.p, 0, (2 * h->max_rounds + 64) * sizeof(unsigned), s));
     {
         dim3 g((W + 31) / 32, (H + 7) / 8);
-        k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->claim0.p, h->claim1.p, h->n2max.p);
+        k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->tab_acc.p, h->cs.p, h->claim0.p, h->claim1.p, h->n2max.p);
     }
     const int nb = h->P.lsd_n_bins;
     k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
@@ -595,14 +954,24 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     G.plan = h->plan.p; G.changed = h->changed.p; G.max_rounds = h->max_rounds; G.min_reg_size = h->min_reg_size;
     G.final_pool = h->final_pool.p; G.final_ctr = h->ctrs.p + 2; G.regs = h->regs.p; G.nreg = h->ctrs.p + 3; G.reg_cap = h->reg_cap;
     G.status = h->status.p;
+    GrowStateW GW; GW.G = G; GW.cs = h->cs.p; GW.work_ctr = h->work_ctr.p;
+    GW.G.A.pool[1] = GW.G.A.pool[0]; GW.G.A.pool_ctr[1] = GW.G.A.pool_ctr[0];      // warp kernel: one bump pool per wave
+    GW.blk_chunk[0] = h->blk_chunk0.p; GW.blk_chunk[1] = h->blk_chunk1.p; GW.blk_cnt[0] = h->blk_cnt0.p; GW.blk_cnt[1] = h->blk_cnt1.p;
+    GW.dbg = nullptr;
     void* args[] = {(void*)&G};
-    OLF_CUDA(cudaLaunchCooperativeKernel((const void*)k_lsd_grow, dim3(h->grow_blocks), dim3(256), args, 0, s));
+    void* args_w[] = {(void*)&GW};
+    OLF_CUDA(cudaEventRecord(h->ev_grow0, s));
+    if (h->scalar_grow) OLF_CUDA(cudaLaunchCooperativeKernel((const void*)k_lsd_grow, dim3(h->grow_blocks), dim3(256), args, 0, s));
+    else OLF_CUDA(cudaLaunchCooperativeKernel((const void*)k_lsd_grow_w, dim3(h->grow_blocks), dim3(GW_WARPS * 32), args_w, 0, s));
+    OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
+    count_launches((h->blur_k ? 2 : 0) + 6);
     k_lsd_rect_a<<<(h->reg_cap + 127) / 128, 128, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
     OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(cudaStreamSynchronize(s));
     h->last_stats[0] = h->status_host.p[1]; h->last_stats[1] = h->status_host.p[2];
+    { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev_grow0, h->ev_grow1) == cudaSuccess) h->last_stats[3] = (int)(ms * 1000.f); }
     if (h->status_host.p[0] != 0) { set_last_error("LSD region growing: internal pool overflow"); return OLF_ERR_CAPACITY; }
     if (h->status_host.p[1] + 2 >= (int)h->max_rounds) { set_last_error("LSD region growing did not converge"); return OLF_ERR_INTERNAL; }
     const int n = (int)*h->nreg_host.p;
@@ -612,6 +981,7 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     // libm cos/sin of the O(#regions) rectangle angles, then the projection pass on the device
     for (int i = 0; i < n; ++i) { const double t = h->rect_host.p[i].theta; h->dir_host.p[i] = make_double2(std::cos(t), std::sin(t)); }
     k_lsd_rect_b<<<(n + 7) / 8, 256, 0, s>>>(h->regs.p, n, h->final_pool.p, W, h->rect_host.d, h->dir_host.d, h->P.lsd_scale, h->seg_host.d);
+    count_launches(1);
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(cudaStreamSynchronize(s));
     // seed order = ascending priority key
@@ -681,6 +1051,7 @@ static int lbd_run(LineImpl* h, const olf_keyline* kls, int n, uint8_t* desc) {
     k_sobel3<<<g, 256, 0, s>>>(h->lbd_blur.p, w, hgt, h->ipitch, h->grad.p);
     k_lbd_rows<<<(n * 63 + 255) / 256, 256, 0, s>>>(h->lbd_lines.d, n, h->grad.p, w, hgt, h->rowsum.p);
     k_lbd_fold<<<(n + 63) / 64, 64, 0, s>>>(h->rowsum.p, n, h->desc_host.d);
+    count_launches(4);
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(cudaStreamSynchronize(s));
     memcpy(desc, h->desc_host.p, (size_t)n * 32);
@@ -734,6 +1105,7 @@ int line_extract(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bo
     return lbd_run(h, k.data(), (int)k.size(), desc);
 }
 
+// [0] rounds, [1] waves, [2] accepted regions, [3] k_lsd_grow device time in microseconds (CUDA events on its stream)
 void line_last_stats(const LineImpl* h, int* out8) { for (int i = 0; i < 8; ++i) out8[i] = h->last_stats[i]; }
 
 }  // namespace olf

@@ -126,6 +126,7 @@ static void launch_knn2(cudaStream_t s, const uint4* dq, int n1, const uint4* dt
     dim3 g((n1 + KNN_Q - 1) / KNN_Q, splits);
     k_knn2_partial<<<g, KNN_Q, 0, s>>>(dq, n1, dt, n2, per_split, part);
     k_knn2_merge<<<(n1 + 127) / 128, 128, 0, s>>>(part, n1, splits, i0, d0, i1, d1);
+    count_launches(2);
 }
 static void knn_splits(int n1, int n2, int* splits, int* per_split) {
     const int qb = std::max((n1 + KNN_Q - 1) / KNN_Q, 1);
@@ -183,6 +184,7 @@ int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr,
     int* a = dptr<int>(c, o_a); int* b = dptr<int>(c, o_b);
     launch_knn2(s, dptr<uint4>(c, o_q), n1, dptr<uint4>(c, o_t), n2, dptr<Knn2>(c, o_part), a, a + n1, a + 2 * n1, a + 3 * n1, s12, p12);
     k_nnr_accept<<<(n1 + 127) / 128, 128, 0, s>>>(a, a + n1, a + 3 * n1, n1, n2, nnr, dptr<int>(c, o_m12));
+    count_launches(mutual ? 3 : 1);
     if (mutual) {
         launch_knn2(s, dptr<uint4>(c, o_t), n2, dptr<uint4>(c, o_q), n1, dptr<Knn2>(c, o_part), b, b + n2, b + 2 * n2, b + 3 * n2, s21, p21);
         k_nnr_accept<<<(n2 + 127) / 128, 128, 0, s>>>(b, b + n2, b + 3 * n2, n2, n1, nnr, dptr<int>(c, o_m21));
@@ -356,6 +358,7 @@ int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const u
     k_stereo_points<<<(N + 7) / 8, 256, 0, s>>>(dptr<olf_keypoint>(c, o_kl), dptr<uint32_t>(c, o_dl), N, dptr<olf_keypoint>(c, o_kr), dptr<uint32_t>(c, o_dr), Nr,
                                                  make_view(vl), make_view(vr), bf, fx, dptr<float>(c, o_u), dptr<float>(c, o_d), dptr<int>(c, o_s));
     k_stereo_median<<<1, 1024, 0, s>>>(dptr<float>(c, o_u), dptr<float>(c, o_d), dptr<int>(c, o_s), N);
+    count_launches(2);
     float* ho = hptr<float>(c, p_out);
     OLF_CUDA(cudaMemcpyAsync(ho, dptr<float>(c, o_u), (size_t)N * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(ho + N, dptr<float>(c, o_d), (size_t)N * 4, cudaMemcpyDeviceToHost, s));
@@ -523,6 +526,7 @@ int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_key
     k_lines_raster<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<olf_keyline>(c, o_kr), n2, inv_w, inv_h, dptr<double2>(c, o_dir), dptr<short2>(c, o_cells), dptr<int>(c, o_nc));
     k_lines_cand<<<dim3((n2 + 255) / 256, n1), 256, 0, s>>>(dptr<olf_keyline>(c, o_kl), dptr<uint32_t>(c, o_dl), n1, dptr<uint32_t>(c, o_dr), n2, inv_w, inv_h,
                                                             dptr<double2>(c, o_dir), dptr<short2>(c, o_cells), dptr<int>(c, o_nc), P->matching_s_ws, P->line_sim_th, dptr<int>(c, o_cand));
+    count_launches(P->best_lr_matches ? 5 : 4);
     if (P->best_lr_matches) k_lines_pass<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_cand), n1, n2, dptr<int>(c, o_m21));
     k_lines_best<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_cand), n1, n2, P->min_ratio_12_l, dptr<int>(c, o_m12));
     k_lines_geom<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<olf_keyline>(c, o_kl), dptr<olf_keyline>(c, o_kr), n1, dptr<int>(c, o_m12), dptr<int>(c, o_m21), P->best_lr_matches, *P,
@@ -680,6 +684,7 @@ static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t
                                                   G, max_dist, dptr<u64>(c, o_lists), dptr<int>(c, o_cnt));
     k_sbp_resolve<<<1, 1024, 0, s>>>(dptr<u64>(c, o_lists), dptr<int>(c, o_cnt), nq, n_cur, dptr<uint8_t>(c, o_obs), occupied ? dptr<uint8_t>(c, o_occ) : nullptr,
                                      dptr<olf_keypoint>(c, o_k), mode, nn_ratio, dptr<int>(c, o_oa), dptr<int>(c, o_ob), dptr<int>(c, o_as), dptr<int>(c, o_r));
+    count_launches(2);
     int* ho = hptr<int>(c, p_out);
     OLF_CUDA(cudaMemcpyAsync(ho, dptr<int>(c, o_as), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(ho + nq, dptr<int>(c, o_cnt), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));

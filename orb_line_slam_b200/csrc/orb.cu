@@ -545,6 +545,7 @@ static int orb_enqueue_phase1(OrbImpl* h, const uint8_t* img, int w, int hgt, in
     OLF_CUDA(cudaMemcpyAsync(h->total_host.p, h->total.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     // ORB blur: 7x7 sigma 2 -> [18,34,48,56,48,34,18] (:1088)
     k_blur_q8<7><<<h->ntiles, 256, 0, s>>>(h->pyr.p, h->blur.p, T, 18, 34, 48, 56);
+    count_launches((h->nlevels - 1) + 2 + (h->ncells > 0 ? 3 : 0));
     OLF_CUDA(cudaGetLastError());
     return OLF_OK;
 }
@@ -605,6 +606,7 @@ int orb_extract(OrbImpl* h, const uint8_t* img, int w, int hgt, int stride, bool
     memcpy(h->kept_host.p, kept.data(), kept.size() * sizeof(KeptKp));
     OLF_CUDA(cudaMemcpyAsync(h->kept.p, h->kept_host.p, kept.size() * sizeof(KeptKp), cudaMemcpyHostToDevice, h->stream));
     k_rbrief<<<(total + 7) / 8, 256, 0, h->stream>>>(h->blur.p, T, h->kept.p, total, h->desc.p);
+    count_launches(1);
     OLF_CUDA(cudaMemcpyAsync(h->desc_host.p, h->desc.p, (size_t)total * 32, cudaMemcpyDeviceToHost, h->stream));
     OLF_CUDA(cudaStreamSynchronize(h->stream));
     OLF_CUDA(cudaGetLastError());

@@ -8,7 +8,8 @@ from __future__ import annotations
 import ctypes as C
 from dataclasses import dataclass, field
 import numpy as np
-from .abi import FrontEndApi, LineParams, LineMatchParams, Camera, SbpLastArgs, SbpMapArgs, KEYPOINT, KEYLINE, ptr
+from .abi import (FrontEndApi, LineParams, LineMatchParams, Camera, SbpLastArgs, SbpMapArgs, KEYPOINT, KEYLINE, ptr,
+                  FrontendParams, FrameHeader, FrameOffsets)
 
 
 @dataclass
@@ -66,6 +67,14 @@ class FrontEnd:
         if pose is not None:
             f.Rcw, f.tcw = pose
         return f
+
+    # ---- native whole-frame path (olf_frontend_*; product library only) ----
+    def native(self, nfeatures=2000, nlines=500, cap_points=None, cap_lines=None):
+        """Create the native rig (4 host threads + 4 streams inside libolf.so) that fills one POD block per frame."""
+        cap_points = cap_points or (nfeatures + 256)
+        cap_lines = cap_lines or max(nlines, 64) if nlines else 4096
+        p = FrontendParams(nfeatures, 1.2, 8, 20, 7, int(self.has_lines), self.lp, self.lmp, self.cam, cap_points, cap_lines)
+        return NativeFrontEnd(self.api, p, self.w, self.h)
 
     # ---- tracking matchers (src/Tracking.cc:1296-1308) ----
     def sbp_last_args(self, cur: StereoFrame, last: StereoFrame, th=7.0, mono=False, check_orientation=True, observed=None):
@@ -143,3 +152,43 @@ class FrontEnd:
             m, nl = self.api.match_lines(last.ldesc, cur.ldesc, nnr_lines, bool(self.lmp.best_lr_matches))
             out.update(line_matches=m, n_line_matches=nl)
         return out
+
+
+class NativeFrontEnd:
+    """olf_frontend_*: Frame::Frame(stereo+lines) in one native call; results land in a fixed-capacity POD block."""
+
+    def __init__(self, api: FrontEndApi, params: FrontendParams, w, h):
+        self.api, self.params, self.w, self.h = api, params, w, h
+        self.off = api.frame_layout(params.cap_points, params.cap_lines)
+        self.handle = api.frontend_create(params)
+
+    def close(self):
+        self.api.frontend_destroy(self.handle)
+
+    def new_block(self) -> np.ndarray:
+        return np.zeros(int(self.off.total), dtype=np.uint8)
+
+    def process(self, img_l, img_r, block: np.ndarray, on_device=False, stride=None):
+        self.api.frontend_process(self.handle, img_l, img_r, self.w, self.h, stride or self.w, on_device, block)
+        return block
+
+    def view(self, block: np.ndarray, pose=None) -> StereoFrame:
+        """Zero-copy numpy views into a result block."""
+        o, cp, cl = self.off, self.params.cap_points, self.params.cap_lines
+        hd = FrameHeader.from_buffer(block)
+
+        def arr(off, dtype, count, shape=None):
+            a = np.frombuffer(block, dtype=dtype, count=count, offset=int(off))
+            return a.reshape(shape) if shape else a
+        f = StereoFrame(arr(o.kps_l, KEYPOINT, cp)[:hd.n_l], arr(o.desc_l, np.uint8, cp * 32, (cp, 32))[:hd.n_l],
+                        arr(o.kps_r, KEYPOINT, cp)[:hd.n_r], arr(o.desc_r, np.uint8, cp * 32, (cp, 32))[:hd.n_r],
+                        arr(o.u_right, np.float32, cp)[:hd.n_l], arr(o.depth, np.float32, cp)[:hd.n_l])
+        if self.params.has_lines:
+            f.kls = arr(o.kls_l, KEYLINE, cl)[:hd.m_l]; f.ldesc = arr(o.ldesc_l, np.uint8, cl * 32, (cl, 32))[:hd.m_l]
+            f.kls_r = arr(o.kls_r, KEYLINE, cl)[:hd.m_r]; f.ldesc_r = arr(o.ldesc_r, np.uint8, cl * 32, (cl, 32))[:hd.m_r]
+            f.line_matches = arr(o.lmatch, np.int32, cl)[:hd.m_l]
+            f.line_disp = arr(o.ldisp, np.float32, cl * 2, (cl, 2))[:hd.m_l]
+            f.line_le = arr(o.lle, np.float64, cl * 3, (cl, 3))[:hd.m_l]
+        if pose is not None:
+            f.Rcw, f.tcw = pose
+        return f

@@ -122,3 +122,20 @@ def test_track_720p(frames):
     for k in ("assigned", "cur_point", "line_matches"):
         assert np.array_equal(to[k], tg[k]), k
     fo.close(); fg.close()
+
+
+def test_native_frontend_block(frames):
+    """olf_frontend_process (4 host threads, one POD block) == the call-by-call path == oracle."""
+    cam = "euroc"
+    sc = Scene(cam, 3)
+    fg = frames["fg"]
+    nat = fg.native(1000, 200)
+    blk = nat.new_block()
+    for f in range(2):
+        L, R = sc.stereo(f)
+        nat.process(L, R, blk)
+        v = nat.view(blk)
+        ref = frames["o"][f]
+        for name in ("kps", "desc", "kps_r", "desc_r", "u_right", "depth", "kls", "ldesc", "kls_r", "ldesc_r", "line_matches", "line_disp", "line_le"):
+            assert np.array_equal(getattr(v, name), getattr(ref, name)), name
+    nat.close()
