@@ -13,6 +13,8 @@ results always come back to host memory (that is the API: Tracking.cc consumes h
 from __future__ import annotations
 import argparse, json, os, pathlib, subprocess, sys, threading, time
 
+# more hardware work queues than the default 8: every rig drives 4 extractor streams (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
@@ -191,7 +193,8 @@ def main():
     lib.olf_kernel_launch_count.restype = ctypes.c_longlong
     api = olf.api(local)
     cam = CAMERAS[WORKLOAD["camera"]]
-    P = args.pipelines or max(2, min(8, (os.cpu_count() or 8) // (5 * max(1, world if world > 1 else 1))))
+    # concurrent stereo rigs per GPU: the LSD grow phases are latency-bound, so frames in flight are what fills the GPU
+    P = args.pipelines or max(2, min(8, (os.cpu_count() or 16) // (2 * max(1, world))))
     sc, seq, poses = make_sequence(N_DISTINCT)
     # weak scaling: every rank runs the same number of frames of its own slice of the sequence
     shift = rank * 11

@@ -11,6 +11,19 @@ static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches_total() { return g_launches.load(); }
+cudaError_t stream_sync(cudaStream_t s) {
+    static const bool spin = [] { const char* e = getenv("OLF_SYNC"); return e && std::string(e) == "spin"; }();
+    if (spin) return cudaStreamSynchronize(s);
+    static thread_local cudaEvent_t ev[16] = {nullptr};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 16) return cudaStreamSynchronize(s);
+    if (!ev[dev]) { e = cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    e = cudaEventRecord(ev[dev], s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev[dev]);
+}
 void set_last_error(const std::string& s) { g_err = s; }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     char buf[512];
@@ -69,6 +82,7 @@ int olf_lsd_detect(olf_line* h, const uint8_t* img, int width, int height, int s
 int olf_lbd_compute(olf_line* h, const uint8_t* img, int width, int height, int stride, const olf_keyline* kls, int n, uint8_t* desc) {
     return line_lbd_compute((LineImpl*)h, img, width, height, stride, kls, n, desc);
 }
+int olf_line_trace(olf_line* h, int* out, int max_rounds) { return line_trace((LineImpl*)h, out, max_rounds); }
 int olf_line_last_stats(const olf_line* h, int* out8) { if (!h || !out8) return OLF_ERR_ARG; line_last_stats((const LineImpl*)h, out8); return OLF_OK; }
 
 int olf_knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0, int* dist0, int* idx1, int* dist1, int device) {

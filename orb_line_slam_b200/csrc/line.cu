@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_lsd_hist(const float* __restrict__ ang,
 
 // one block: bin offsets (descending bin order) and the wave plan (whole bins, cumulative targets doubling)
 struct LsdPlan { int n_seeds; int n_waves; int wave_start[64]; };
-__global__ void k_lsd_plan(const unsigned* __restrict__ hist, int n_bins, int first_wave, unsigned* __restrict__ bin_start,
+__global__ void k_lsd_plan(const unsigned* __restrict__ hist, int n_bins, int first_wave, int wave_growth, unsigned* __restrict__ bin_start,
                            unsigned* __restrict__ cursor, LsdPlan* __restrict__ plan) {
     if (threadIdx.x != 0) return;
     unsigned acc = 0;
@@ -104,7 +104,7 @@ __global__ void k_lsd_plan(const unsigned* __restrict__ hist, int n_bins, int fi
     for (int b = n_bins - 1; b >= 0; --b) {
         bin_start[b] = acc; cursor[b] = 0;
         acc += hist[b];
-        if ((long long)acc - plan->wave_start[nw] >= target && nw < 61) { plan->wave_start[++nw] = (int)acc; target *= 2; }
+        if ((long long)acc - plan->wave_start[nw] >= target && nw < 61) { plan->wave_start[++nw] = (int)acc; target *= wave_growth; }
     }
     if (plan->wave_start[nw] != (int)acc) plan->wave_start[++nw] = (int)acc;
     plan->n_seeds = (int)acc; plan->n_waves = nw;
@@ -203,6 +203,8 @@ __global__ void __launch_bounds__(256) k_lsd_grow(const GrowState G) {
 //   * claims are atomicMin by lane 0; their return values are awaited once per step, which makes the warp's own claims
 //     visible to the next step's (L2) loads -- no duplicate can enter a list.
 #define GW_WARPS 8
+#define GW_HASH_BITS 8
+#define GW_HASH (1 << GW_HASH_BITS)
 struct GrowStateW {
     GrowState G;
     const float2_t* cs;         // per pixel (cos, sin) as accumulated by the reference: tab_acc[(DA,BC)]
@@ -211,6 +213,7 @@ struct GrowStateW {
     // them (one chunk at most; count 255 = too many, always re-grow).  Together with the pixel list they are the complete
     // set of external facts a growth depended on, which is what lets an unchanged region be verified instead of re-grown.
     unsigned* blk_chunk[2]; int* blk_cnt[2];
+    int fast_align; float c_hi2, c_lo2;   // lazy alignment test: cos^2(prec -/+ 0.1 deg)
     int* dbg;                   // optional per-round trace (see OLF_LSD_TRACE)
 };
 
@@ -230,7 +233,9 @@ __device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __longlong_as_double((long long)shfl_u64((u64)__double_as_longlong(v), src)); }
 
 // returns true if the seed's outcome differs from the previous round
-__device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int seed, u64 prio, int lane) {
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TRACE_REC 8
+__device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int seed, u64 prio, int lane, volatile unsigned* hs) {
     const GrowState& G = S.G;
     const GrowArgs& A = G.A;
     const int cur = round & 1, prv = (round - 1) & 1;
@@ -295,6 +300,7 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
                 if (lane < kChunk - 1 && k + lane < prev_cnt && v != (unsigned)seed) atomicMin(&claim_cur[v], mine);
                 chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
             }
+            if (S.dbg && lane == 0) atomicAdd(&S.dbg[round * TRACE_REC + 4], 1);
             if (lane == 0) {
                 G.head[cur][i] = prev_head; G.cnt[cur][i] = prev_cnt;
                 S.blk_chunk[cur][i] = __ldcg(&S.blk_chunk[prv][i]); S.blk_cnt[cur][i] = bc;
@@ -358,11 +364,32 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
     double reg_angle = d_mul((double)__ldg(&A.ang[seed]), kDegToRads);
     const float2_t t0 = A.tab_seed[tab_index(A.dabc[seed])];
     float sumdx = t0.x, sumdy = t0.y;
-    unsigned pend = 0;
-    int i_rd = 0;
-    while (i_rd < count && !overflow) {
-        const int nb = min(3, count - i_rd);
-        // entry pixels of this step (uniform), taken from the chunk registers
+    float u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
+    bool dirty = false;                                              // reg_angle is stale w.r.t. (sumdx, sumdy)
+    // ---- software-pipelined BFS: while the accept decisions of step k are replayed, the neighbour data of step k+1 are
+    // already in flight.  Claims are fire-and-forget reductions (RED): nothing on the critical path waits for L2.  The warp's
+    // own accepts since the last fence live in a small shared-memory hash set `hs`; loads are issued only after a fence has
+    // made every older own claim visible, so "already mine" is always decidable from (loaded claim word) OR (hash set hit).
+    struct Pf { int q; float aq; u64 ep, ec; float cx, cy; };
+    int n_since_fence = 0;
+    int i_issue = 0;                                                 // queue entries whose neighbour loads have been issued
+    for (int k = lane; k < GW_HASH; k += 32) hs[k] = kNull;
+    __syncwarp();
+    auto hs_insert = [&](unsigned pix) {                             // lane 0 only
+        unsigned slot = (pix * 2654435761u) >> (32 - GW_HASH_BITS);
+        while (hs[slot] != kNull) slot = (slot + 1) & (GW_HASH - 1);
+        hs[slot] = pix;
+    };
+    auto hs_contains = [&](unsigned pix) -> bool {
+        unsigned slot = (pix * 2654435761u) >> (32 - GW_HASH_BITS);
+        for (;;) {
+            const unsigned v = hs[slot];
+            if (v == pix) return true;
+            if (v == kNull) return false;
+            slot = (slot + 1) & (GW_HASH - 1);
+        }
+    };
+    auto issue = [&](int nb) -> Pf {
         int ent[3] = {-1, -1, -1};
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
@@ -378,160 +405,249 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
         // lane -> (entry, neighbour) in the reference's scan order: yy outer, xx inner
         const int e = lane / 9, nidx = lane - e * 9;
         const int p = e == 0 ? ent[0] : (e == 1 ? ent[1] : ent[2]);
-        bool valid = lane < 27 && e < nb;
-        int q = -1 - lane;
-        float aq = -1.f; float2_t csq; csq.x = 0.f; csq.y = 0.f;
-        bool pot = false, held = false;
-        if (valid) {
-            const int px = p % A.W, py = p / A.W;
+        Pf f; f.q = -1 - lane; f.aq = -1.f; f.ep = kClaimNone; f.ec = kClaimNone; f.cx = 0.f; f.cy = 0.f;
+        if (lane < 27 && e < nb) {
+            const int py = p / A.W, px = p - py * A.W;
             const int xx = px + (nidx % 3) - 1, yy = py + (nidx / 3) - 1;
-            valid = xx >= 0 && xx < A.W && yy >= 0 && yy < A.H;
-            if (valid) {
-                q = yy * A.W + xx;
-                aq = __ldg(&A.ang[q]);
-                const u64 ep = __ldcg(&claim_prev[q]);
-                const u64 ec = __ldcg(&claim_cur[q]);
-                csq = S.cs[q];
-                if (aq >= 0.f) {
-                    const u64 sp = ep >> 40, sc = ec >> 40;
-                    const bool fin = sp == 0 || sc == 0;                                       // finalised region: never comes back
-                    const bool own = sc == sf_cur && (ec & kPrioMask) == prio;                // already in this region
-                    held = (sp == sf_prev && (ep & kPrioMask) < prio) || (sc == sf_cur && (ec & kPrioMask) < prio);
-                    pot = !fin && !own;
-                }
+            if (xx >= 0 && xx < A.W && yy >= 0 && yy < A.H) {
+                f.q = yy * A.W + xx;
+                f.aq = __ldg(&A.ang[f.q]);
+                f.ep = __ldcg(&claim_prev[f.q]);
+                f.ec = __ldcg(&claim_cur[f.q]);
+                const float2_t c = S.cs[f.q];
+                f.cx = c.x; f.cy = c.y;
             }
         }
-        const unsigned held_m = __ballot_sync(0xffffffffu, held);
-        const unsigned dup = __match_any_sync(0xffffffffu, q);     // lanes looking at the same pixel
-        unsigned m = __ballot_sync(0xffffffffu, pot);
-        unsigned accepted = 0;
-        while (m) {
-            const int c = __ffs(m) - 1;
-            m &= m - 1;
-            if (__shfl_sync(0xffffffffu, dup, c) & accepted) continue;            // already taken earlier in this step
-            const float a_c = __shfl_sync(0xffffffffu, aq, c);
-            double n_theta = d_sub(reg_angle, d_mul((double)a_c, kDegToRads));   // isAligned
-            if (n_theta < 0) n_theta = -n_theta;
-            if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
-            if (!(n_theta <= A.prec)) continue;
-            const int qc = __shfl_sync(0xffffffffu, q, c);
-            if ((held_m >> c) & 1u) { record_blocked((unsigned)qc); if (overflow) break; continue; }   // aligned but held by a higher-priority seed
-            accepted |= 1u << c;
-            const float cx = __shfl_sync(0xffffffffu, csq.x, c), cy = __shfl_sync(0xffffffffu, csq.y, c);
-            if (lane == 0) { const u64 old = atomicMin(&claim_cur[qc], mine); pend += (unsigned)(old >> 63); }
+        i_issue += nb;
+        return f;
+    };
+    Pf cf = issue(1);                                                // step 0: the seed
+    bool have_cur = true;
+#ifdef OLF_LSD_PROFILE
+#define PCLK() clock64()
+#else
+#define PCLK() 0ll
+#endif
+    long long tA = 0, tB0 = 0, tB1 = 0, tC = 0, tE = 0, tS = 0, tL = 0, tP = 0; int n_steps = 0, n_pot = 0, n_pipe = 0, n_accepts = 0;
+    while (have_cur && !overflow) {
+        const long long c0 = PCLK();
+        // [A] issue the next step's loads if the queue already holds its entries (not across a pending fence)
+        const bool need_fence = n_since_fence > GW_HASH / 2 - 32;
+        Pf nf; bool have_next = false;
+        if (count - i_issue > 0 && !need_fence) {
+            nf = issue(min(3, count - i_issue));
+            have_next = true;
+        }
+        const long long c1 = PCLK();
+        // [B] replay the accept decisions of the current step in scan order.  Every lane evaluates isAligned() for its own
+        // candidate against the warp-uniform region state; the lowest aligned lane is the next pixel the reference would take;
+        // after an accept the state changes and the remaining (higher) lanes are re-evaluated.  Candidates that are not aligned
+        // at their turn never come back (lanes below the last decision are dropped), exactly as in the sequential scan.
+        bool pot = false, held = false;
+        if (cf.q >= 0 && cf.aq >= 0.f) {
+            const u64 sp = cf.ep >> 40, sc = cf.ec >> 40;
+            const bool fin = sp == 0 || sc == 0;                                            // finalised region: never comes back
+            const bool own = sc == sf_cur && (cf.ec & kPrioMask) == prio;                   // already in this region
+            held = (sp == sf_prev && (cf.ep & kPrioMask) < prio) || (sc == sf_cur && (cf.ec & kPrioMask) < prio);
+            pot = !fin && !own && !hs_contains((unsigned)cf.q);
+        }
+        const long long c2 = PCLK();
+        n_pot += __popc(__ballot_sync(0xffffffffu, pot)); ++n_steps; n_pipe += have_next;
+        const double a_rad = d_mul((double)cf.aq, kDegToRads);
+        unsigned live = 0xffffffffu;                                                        // lanes not yet passed by the scan
+        bool state_changed = true;
+        unsigned al = 0;
+        for (;;) {
+            const long long e0 = PCLK();
+            if (state_changed) {
+                // isAligned(reg_angle, a) with reg_angle = fastAtan2(sumdy, sumdx) evaluated lazily: the sign
+                // of cos(angular distance) - cos(prec -/+ 0.1 deg) decides all but the candidates within 0.1 deg of the threshold
+                int st = 0;
+                if (pot && ((live >> lane) & 1u)) {
+                    const float dot = f_add(f_mul(sumdx, cf.cx), f_mul(sumdy, cf.cy)), d2 = f_mul(dot, dot);
+                    if (S.fast_align && u2 > 1e-3f && dot > 0.f && d2 >= f_mul(S.c_hi2, u2)) st = 1;
+                    else if (S.fast_align && u2 > 1e-3f && (dot <= 0.f || d2 <= f_mul(S.c_lo2, u2))) st = 0;
+                    else st = 2;
+                }
+                if (__any_sync(0xffffffffu, st == 2)) {
+                    if (dirty) { reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads); dirty = false; }
+                    if (st == 2) {
+                        double n_theta = d_sub(reg_angle, a_rad);
+                        if (n_theta < 0) n_theta = -n_theta;
+                        if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
+                        st = (n_theta <= A.prec) ? 1 : 0;
+                    }
+                }
+                al = __ballot_sync(0xffffffffu, st == 1);
+                state_changed = false;
+            }
+            al &= live;
+            const long long e1 = PCLK(); tE += e1 - e0;
+            if (!al) break;
+            const int c = __ffs(al) - 1;
+            live = (c == 31) ? 0u : (0xffffffffu << (c + 1));                               // the scan has passed lanes <= c
+            const int qc = __shfl_sync(0xffffffffu, cf.q, c);
+            if (__shfl_sync(0xffffffffu, (int)held, c)) { record_blocked((unsigned)qc); if (overflow) break; continue; }   // aligned but held by a higher-priority seed
+            const float cx = __shfl_sync(0xffffffffu, cf.cx, c), cy = __shfl_sync(0xffffffffu, cf.cy, c);
+            if (cf.q == qc) pot = false;                                                    // the same pixel seen from another entry
+            const long long e2 = PCLK(); tS += e2 - e1;
+            if (lane == 0) { atomicMin(&claim_cur[qc], mine); hs_insert((unsigned)qc); }   // RED: no return value is consumed
+            ++n_since_fence;
+            const long long e3 = PCLK(); tL += e3 - e2;
             push((unsigned)qc);
+            const long long e4 = PCLK(); tP += e4 - e3; ++n_accepts;
             if (overflow) break;
             sumdx = f_add(sumdx, cx);
             sumdy = f_add(sumdy, cy);
-            reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads);
+            u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
+            dirty = true;
+            state_changed = true;
         }
-        // wait for this step's claims: the next step's loads must observe them
-        pend = __shfl_sync(0xffffffffu, pend, 0);
-        i_rd += nb;
+        __syncwarp();                                                             // hash-set inserts visible to all lanes
+        const long long c3 = PCLK();
+        // [C] rotate; if nothing was prefetched, fence when due (every own claim reaches L2, the hash set restarts) and issue now
+        if (have_next) cf = nf;
+        else if (count - i_issue > 0 && !overflow) {
+            if (need_fence) {
+                __threadfence();
+                for (int k = lane; k < GW_HASH; k += 32) hs[k] = kNull;
+                __syncwarp();
+                n_since_fence = 0;
+            }
+            cf = issue(min(3, count - i_issue));
+        }
+        else have_cur = false;
+        const long long c4 = PCLK();
+        tA += c1 - c0; tB0 += c2 - c1; tB1 += c3 - c2; tC += c4 - c3;
     }
+#ifdef OLF_LSD_PROFILE
+    if (S.dbg && lane == 0 && count >= 900) {
+        int* d = S.dbg + 200 * TRACE_REC;
+        d[0] = count; d[1] = n_steps; d[2] = n_pot; d[3] = n_pipe; d[4] = (int)tA; d[5] = (int)tB0; d[6] = (int)tB1; d[7] = (int)tC;
+        d[8] = n_accepts; d[9] = (int)tE; d[10] = (int)tS; d[11] = (int)tL; d[12] = (int)tP;
+    }
+#endif
+    const unsigned pend = 0;
+    if (dirty) reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads);
+#ifdef OLF_LSD_PROFILE
+    if (S.dbg && lane == 0 && count >= 900) {
+        int* d = S.dbg + 200 * TRACE_REC;
+        d[0] = count; d[1] = n_steps; d[2] = n_pot; d[3] = n_pipe; d[4] = (int)tA; d[5] = (int)tB0; d[6] = (int)tB1; d[7] = (int)tC;
+        d[8] = n_accepts; d[9] = (int)tE; d[10] = (int)tS; d[11] = (int)tL; d[12] = (int)tP;
+    }
+#endif
     if (overflow) { if (lane == 0) { G.status[0] = OLF_ERR_CAPACITY; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; } return true; }
     // flush the partial chunk
     if (lane < w_n || lane == kChunk - 1) pool[(size_t)w_chunk * kChunk + lane] = (lane == kChunk - 1) ? kNull : w_val;
     if (lane == 0) { G.head[cur][i] = w_head; G.cnt[cur][i] = count; G.regang[i] = reg_angle; S.blk_chunk[cur][i] = b_chunk; S.blk_cnt[cur][i] = b_n; }
+    if (S.dbg && lane == 0) { atomicAdd(&S.dbg[round * TRACE_REC + 5], 1); atomicAdd(&S.dbg[round * TRACE_REC + 6], count); atomicMax(&S.dbg[round * TRACE_REC + 7], count); }
     return !(same && count == prev_cnt) || (pend == 0xFFFFFFFFu);
 }
 
-__global__ void __launch_bounds__(GW_WARPS * 32) k_lsd_grow_w(const GrowStateW S) {
-    cg::grid_group grid = cg::this_grid();
+// One launch = one phase of the wave/round state machine (ROUND: every live seed of the wave verifies or re-grows;
+// FINALIZE: the converged wave is stamped for good).  The last block to finish advances the state, so a fixed batch of
+// back-to-back launches walks through all phases without any host round trip; launches after `done` return at once.
+// Ordinary (non-cooperative) launches: no co-residency requirement, so the grow phases of the left/right eyes and of
+// several frames in flight interleave freely with every other kernel on the device.
+struct PhaseState { int wave; unsigned round; int mode; int done; unsigned pass; unsigned ticket; int launches; int pad; };
+
+__global__ void __launch_bounds__(GW_WARPS * 32, 3) k_lsd_phase(const GrowStateW S, PhaseState* __restrict__ st) {
+    __shared__ unsigned hash_sets[GW_WARPS][GW_HASH];
+    __shared__ bool s_last;
     const GrowState& G = S.G;
+    const int wv = st->wave; const unsigned round = st->round; const int mode = st->mode; const unsigned pass = st->pass;
+    if (st->done) return;
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    const int n_waves = G.plan->n_waves;
-    unsigned round = 1;
-    unsigned pass = 0;                                   // index into the zero-initialised work counters
-    for (int wv = 0; wv < n_waves; ++wv) {
-        const int lo = G.plan->wave_start[wv], hi = G.plan->wave_start[wv + 1];
-        for (int i = lo + tid; i < hi; i += nth) { G.cnt[0][i] = 0; G.cnt[1][i] = 0; }
-        if (tid == 0) *G.A.pool_ctr[0] = 0;                          // one bump pool per wave (lists may be carried over rounds)
+    const int lo = G.plan->wave_start[wv], hi = G.plan->wave_start[wv + 1];
+    const int cur = round & 1, prv = (round - 1) & 1;
+    if (mode == 0) {
+        const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
+        bool any_change = false;
+        if (S.dbg && tid == 0) { S.dbg[round * TRACE_REC + 0] = wv; S.dbg[round * TRACE_REC + 1] = hi - lo; S.dbg[round * TRACE_REC + 2] = (int)(gtime() & 0x7fffffff); }
+        // seeds are handed out in batches of `bsz` (one per lane for the cheap liveness test); small waves use small
+        // batches so that the live seeds of a batch do not queue up behind each other inside one warp
+        const int nwarps = (int)(nth >> 5);
+        const int bsz = max(1, min(32, (hi - lo) / (2 * nwarps)));
         for (;;) {
-            __threadfence();
-            grid.sync();
-            const int cur = round & 1, prv = (round - 1) & 1;
-            const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
-            bool any_change = false;
-            // seeds are handed out in batches of `bsz` (one per lane for the cheap liveness test); small waves use small
-            // batches so that the live seeds of a batch do not queue up behind each other inside one warp
-            const int nwarps = (int)(nth >> 5);
-            const int bsz = max(1, min(32, (hi - lo) / (2 * nwarps)));
-            for (;;) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&S.work_ctr[pass], (unsigned)bsz);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (lo + (int)base >= hi) break;
-                const int i = lo + (int)base + lane;
-                int seed = 0; u64 prio = 0; bool alive = false;
-                if (i < hi && lane < bsz) {
-                    seed = G.seed_pix[i]; prio = G.seed_prio[i];
-                    alive = !blocked_vals(__ldcg(&G.A.claim[prv][seed]), __ldcg(&G.A.claim[cur][seed]), sf_prev, sf_cur, prio);
-                    if (!alive) { if (__ldcg(&G.cnt[prv][i]) != 0) any_change = true; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; }
-                }
-                unsigned m = __ballot_sync(0xffffffffu, alive);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int s_seed = __shfl_sync(0xffffffffu, seed, src);
-                    const u64 s_prio = shfl_u64(prio, src);
-                    if (grow_seed_warp(S, round, lo + (int)base + src, s_seed, s_prio, lane)) any_change = true;
-                }
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&S.work_ctr[pass], (unsigned)bsz);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lo + (int)base >= hi) break;
+            const int i = lo + (int)base + lane;
+            int seed = 0; u64 prio = 0; bool alive = false;
+            if (i < hi && lane < bsz) {
+                seed = G.seed_pix[i]; prio = G.seed_prio[i];
+                alive = !blocked_vals(__ldcg(&G.A.claim[prv][seed]), __ldcg(&G.A.claim[cur][seed]), sf_prev, sf_cur, prio);
+                if (!alive) { if (__ldcg(&G.cnt[prv][i]) != 0) any_change = true; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; }
             }
-            if (__syncthreads_or(any_change) && threadIdx.x == 0) G.changed[round] = 1;
-            __threadfence();
-            grid.sync();
-            ++pass;
-            const bool changed = __ldcg(&G.changed[round]) != 0;
-            if (!changed || round + 2 >= G.max_rounds || __ldcg(&G.status[0]) != 0) break;
-            ++round;
+            unsigned m = __ballot_sync(0xffffffffu, alive);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int s_seed = __shfl_sync(0xffffffffu, seed, src);
+                const u64 s_prio = shfl_u64(prio, src);
+                if (grow_seed_warp(S, round, lo + (int)base + src, s_seed, s_prio, lane, hash_sets[threadIdx.x >> 5])) any_change = true;
+            }
         }
+        if (__syncthreads_or(any_change) && threadIdx.x == 0) G.changed[round] = 1;
+    } else {
         // finalise the wave (warp per live seed): stamp the regions for good, keep the lists of accepted regions
-        {
-            const int cur = round & 1;
-            const unsigned* pool = G.A.pool[cur];
-            for (;;) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&S.work_ctr[pass], 32u);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (lo + (int)base >= hi) break;
-                const int i = lo + (int)base + lane;
-                const int c_l = (i < hi) ? __ldcg(&G.cnt[cur][i]) : 0;
-                unsigned m = __ballot_sync(0xffffffffu, c_l > 0);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int si = lo + (int)base + src;
-                    const int c = __shfl_sync(0xffffffffu, c_l, src);
-                    const u64 prio = G.seed_prio[si];
-                    const bool accept = c >= G.min_reg_size;
-                    unsigned off = 0;
-                    if (accept && lane == 0) off = atomicAdd(G.final_ctr, (unsigned)c);
-                    off = __shfl_sync(0xffffffffu, off, 0);
-                    unsigned chunk = __ldcg(&G.head[cur][si]);
-                    for (int k = 0; k < c; k += kChunk - 1) {
-                        const unsigned v = __ldcg(&pool[(size_t)chunk * kChunk + lane]);
-                        if (lane < kChunk - 1 && k + lane < c) {
-                            G.A.claim[0][v] = prio; G.A.claim[1][v] = prio;
-                            if (accept) G.final_pool[off + k + lane] = v;
-                        }
-                        chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
+        const unsigned* pool = G.A.pool[cur];
+        for (;;) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&S.work_ctr[pass], 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lo + (int)base >= hi) break;
+            const int i = lo + (int)base + lane;
+            const int c_l = (i < hi) ? __ldcg(&G.cnt[cur][i]) : 0;
+            unsigned m = __ballot_sync(0xffffffffu, c_l > 0);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int si = lo + (int)base + src;
+                const int c = __shfl_sync(0xffffffffu, c_l, src);
+                const u64 prio = G.seed_prio[si];
+                const bool accept = c >= G.min_reg_size;
+                unsigned off = 0;
+                if (accept && lane == 0) off = atomicAdd(G.final_ctr, (unsigned)c);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                unsigned chunk = __ldcg(&G.head[cur][si]);
+                for (int k = 0; k < c; k += kChunk - 1) {
+                    const unsigned v = __ldcg(&pool[(size_t)chunk * kChunk + lane]);
+                    if (lane < kChunk - 1 && k + lane < c) {
+                        G.A.claim[0][v] = prio; G.A.claim[1][v] = prio;
+                        if (accept) G.final_pool[off + k + lane] = v;
                     }
-                    if (accept && lane == 0) {
-                        const unsigned r = atomicAdd(G.nreg, 1u);
-                        if (r < G.reg_cap) { LsdRegion R; R.prio = prio; R.off = off; R.count = c; R.reg_angle = __ldcg(&G.regang[si]); G.regs[r] = R; }
-                        else G.status[0] = OLF_ERR_CAPACITY;
-                    }
+                    chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
+                }
+                if (accept && lane == 0) {
+                    const unsigned r = atomicAdd(G.nreg, 1u);
+                    if (r < G.reg_cap) { LsdRegion R; R.prio = prio; R.off = off; R.count = c; R.reg_angle = __ldcg(&G.regang[si]); G.regs[r] = R; }
+                    else G.status[0] = OLF_ERR_CAPACITY;
                 }
             }
         }
-        ++round; ++pass;
-        __threadfence();
-        grid.sync();
-        if (__ldcg(&G.status[0]) != 0) break;
     }
-    if (tid == 0) { G.status[1] = (int)round; G.status[2] = n_waves; }
+    // last block to finish advances the state machine
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    const int err = __ldcg(&G.status[0]);
+    st->ticket = 0; st->launches += 1; st->pass = pass + 1;
+    if (mode == 0) {
+        if (S.dbg) S.dbg[round * TRACE_REC + 3] = (int)(gtime() & 0x7fffffff);
+        const bool changed = __ldcg(&G.changed[round]) != 0;
+        if (!changed || round + 2 >= G.max_rounds || err != 0) st->mode = 1; else st->round = round + 1;
+    } else {
+        st->mode = 0; st->round = round + 1; st->wave = wv + 1;
+        *G.A.pool_ctr[0] = 0;                                       // one bump pool per wave (lists may be carried over rounds)
+        if (wv + 1 >= G.plan->n_waves || err != 0) { st->done = 1; G.status[1] = (int)(round + 1); G.status[2] = G.plan->n_waves; G.status[3] = 1; }
+    }
+    __threadfence();
 }
 
 // ---- region2rect ---------------------------------------------------------------------------
@@ -745,8 +861,12 @@ struct LineImpl {
     DevBuf<LsdRegion> regs;
     DevBuf<float2_t> tab_seed, tab_acc, cs;
     DevBuf<unsigned> work_ctr, blk_chunk0, blk_chunk1;
+    DevBuf<PhaseState> phase;
+    int phase_batch = 40;
     DevBuf<int> blk_cnt0, blk_cnt1;
-    bool scalar_grow = false;
+    bool scalar_grow = false, trace = false;
+    int first_wave = 4096, wave_growth = 16;
+    DevBuf<int> dbg;
     unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
     int grow_blocks = 0;
     PinBuf<RectRec> rect_host; PinBuf<double2> dir_host; PinBuf<float4> seg_host; PinBuf<int> status_host; PinBuf<unsigned> nreg_host;
@@ -835,11 +955,22 @@ LineImpl* line_create(const olf_line_params* p, int device) {
     int coop = 0, sms = 0, per_sm = 0;
     ok = ok && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && coop;
     ok = ok && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+    if (const char* e = getenv("OLF_LSD_FIRST_WAVE")) h->first_wave = std::max(1, atoi(e));
+    if (const char* e = getenv("OLF_LSD_WAVE_GROWTH")) h->wave_growth = std::max(2, atoi(e));
+    h->trace = getenv("OLF_LSD_TRACE") != nullptr;                // per-round trace of the grow kernel (tools/lsd_trace.py)
     h->scalar_grow = getenv("OLF_LSD_SCALAR") != nullptr;         // A/B switch: thread-per-seed reference kernel
     if (h->scalar_grow) ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_grow, 256, 0) == cudaSuccess && per_sm > 0;
-    else ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_grow_w, GW_WARPS * 32, 0) == cudaSuccess && per_sm > 0;
+    else ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_phase, GW_WARPS * 32, 0) == cudaSuccess && per_sm > 0;
+    ok = ok && h->phase.ensure(1) == OLF_OK;
+    if (const char* e = getenv("OLF_LSD_PHASE_BATCH")) h->phase_batch = std::max(4, atoi(e));
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
-    h->grow_blocks = sms * std::min(per_sm, h->scalar_grow ? 2 : 4);
+    {   // blocks per SM of the persistent grow kernel: the kernel is latency-bound (one warp walks the longest region), so a
+        // small grid loses little and lets the left/right eyes and several frames in flight share the GPU
+        int bps = 2;
+        if (const char* e = getenv("OLF_LSD_BPS")) bps = std::max(1, atoi(e));
+        h->grow_blocks = sms * std::min(per_sm, bps);
+        if (const char* e = getenv("OLF_LSD_BLOCKS")) h->grow_blocks = std::max(1, std::min(atoi(e), sms * per_sm));
+    }
     return h;
 }
 
@@ -855,7 +986,7 @@ void line_destroy(LineImpl* h) {
     h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool0.release(); h->pool1.release(); h->ctrs.release();
     h->changed.release(); h->final_pool.release(); h->regang.release(); h->plan.release(); h->regs.release();
     h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->work_ctr.release();
-    h->blk_chunk0.release(); h->blk_chunk1.release(); h->blk_cnt0.release(); h->blk_cnt1.release(); h->rect_host.release(); h->dir_host.release(); h->seg_host.release();
+    h->blk_chunk0.release(); h->blk_chunk1.release(); h->blk_cnt0.release(); h->blk_cnt1.release(); h->phase.release(); h->rect_host.release(); h->dir_host.release(); h->seg_host.release();
     h->status_host.release(); h->nreg_host.release(); h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
 }
@@ -889,7 +1020,7 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
         (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->changed.ensure(h->max_rounds)) || (rc = h->plan.ensure(1)) ||
         (rc = h->pool0.ensure((size_t)h->pool_chunks * kChunk)) || (rc = h->pool1.ensure((size_t)h->pool_chunks * kChunk)) ||
-        (rc = h->cs.ensure(S)) || (rc = h->work_ctr.ensure(2 * h->max_rounds + 64)) ||
+        (rc = h->dbg.ensure((size_t)h->max_rounds * TRACE_REC)) || (rc = h->cs.ensure(S)) || (rc = h->work_ctr.ensure(2 * h->max_rounds + 64)) ||
         (rc = h->blk_chunk0.ensure(S)) || (rc = h->blk_chunk1.ensure(S)) || (rc = h->blk_cnt0.ensure(S)) || (rc = h->blk_cnt1.ensure(S)) ||
         (rc = h->regs.ensure(h->reg_cap)) || (rc = h->rect_host.ensure(h->reg_cap)) || (rc = h->dir_host.ensure(h->reg_cap)) ||
         (rc = h->seg_host.ensure(h->reg_cap)) || (rc = h->status_host.ensure(4)) || (rc = h->nreg_host.ensure(1))) return rc;
@@ -943,7 +1074,7 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     }
     const int nb = h->P.lsd_n_bins;
     k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
-    k_lsd_plan<<<1, 32, 0, s>>>(h->hist.p, nb, 2048, h->bin_start.p, h->cursor.p, h->plan.p);
+    k_lsd_plan<<<1, 32, 0, s>>>(h->hist.p, nb, h->first_wave, h->wave_growth, h->bin_start.p, h->cursor.p, h->plan.p);
     k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p);
     GrowState G;
     G.A.W = W; G.A.H = H; G.A.ang = h->ang.p; G.A.dabc = h->dabc.p; G.A.tab_seed = h->tab_seed.p; G.A.tab_acc = h->tab_acc.p;
@@ -957,19 +1088,48 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     GrowStateW GW; GW.G = G; GW.cs = h->cs.p; GW.work_ctr = h->work_ctr.p;
     GW.G.A.pool[1] = GW.G.A.pool[0]; GW.G.A.pool_ctr[1] = GW.G.A.pool_ctr[0];      // warp kernel: one bump pool per wave
     GW.blk_chunk[0] = h->blk_chunk0.p; GW.blk_chunk[1] = h->blk_chunk1.p; GW.blk_cnt[0] = h->blk_cnt0.p; GW.blk_cnt[1] = h->blk_cnt1.p;
-    GW.dbg = nullptr;
+    {
+        const double margin = 0.1 * M_PI / 180.0;
+        GW.fast_align = (h->prec + margin < 80.0 * M_PI / 180.0) && !getenv("OLF_LSD_EXACT_ALIGN");
+        GW.c_hi2 = (float)(std::cos(h->prec - margin) * std::cos(h->prec - margin));
+        GW.c_lo2 = (float)(std::cos(h->prec + margin) * std::cos(h->prec + margin));
+    }
+    GW.dbg = h->trace ? h->dbg.p : nullptr;
+    if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
     void* args[] = {(void*)&G};
     void* args_w[] = {(void*)&GW};
     OLF_CUDA(cudaEventRecord(h->ev_grow0, s));
     if (h->scalar_grow) OLF_CUDA(cudaLaunchCooperativeKernel((const void*)k_lsd_grow, dim3(h->grow_blocks), dim3(256), args, 0, s));
-    else OLF_CUDA(cudaLaunchCooperativeKernel((const void*)k_lsd_grow_w, dim3(h->grow_blocks), dim3(GW_WARPS * 32), args_w, 0, s));
+    else {
+        (void)args_w;
+        PhaseState init; memset(&init, 0, sizeof(init)); init.round = 1;
+        // seeds of later waves must start with "no previous list"
+        OLF_CUDA(cudaMemsetAsync(h->cnt0.p, 0, (size_t)S * sizeof(int), s));
+        OLF_CUDA(cudaMemsetAsync(h->cnt1.p, 0, (size_t)S * sizeof(int), s));
+        OLF_CUDA(cudaMemcpyAsync(h->phase.p, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+        for (int k = 0; k < h->phase_batch; ++k) k_lsd_phase<<<h->grow_blocks, GW_WARPS * 32, 0, s>>>(GW, h->phase.p);
+        count_launches(h->phase_batch);
+    }
     OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
     count_launches((h->blur_k ? 2 : 0) + 6);
     k_lsd_rect_a<<<(h->reg_cap + 127) / 128, 128, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
     OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(cudaStreamSynchronize(s));
+    OLF_CUDA(stream_sync(s));
+    if (!h->scalar_grow) {
+        // the fixed batch of phase launches normally covers all rounds; otherwise keep going (rare)
+        for (int guard = 0; guard < 400; ++guard) {
+            if (h->status_host.p[3] || h->status_host.p[0]) break;
+            for (int k = 0; k < h->phase_batch; ++k) k_lsd_phase<<<h->grow_blocks, GW_WARPS * 32, 0, s>>>(GW, h->phase.p);
+            count_launches(h->phase_batch + 1);
+            OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
+            k_lsd_rect_a<<<(h->reg_cap + 127) / 128, 128, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
+            OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+            OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            OLF_CUDA(stream_sync(s));
+        }
+    }
     h->last_stats[0] = h->status_host.p[1]; h->last_stats[1] = h->status_host.p[2];
     { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev_grow0, h->ev_grow1) == cudaSuccess) h->last_stats[3] = (int)(ms * 1000.f); }
     if (h->status_host.p[0] != 0) { set_last_error("LSD region growing: internal pool overflow"); return OLF_ERR_CAPACITY; }
@@ -983,7 +1143,7 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     k_lsd_rect_b<<<(n + 7) / 8, 256, 0, s>>>(h->regs.p, n, h->final_pool.p, W, h->rect_host.d, h->dir_host.d, h->P.lsd_scale, h->seg_host.d);
     count_launches(1);
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(cudaStreamSynchronize(s));
+    OLF_CUDA(stream_sync(s));
     // seed order = ascending priority key
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
@@ -1053,7 +1213,7 @@ static int lbd_run(LineImpl* h, const olf_keyline* kls, int n, uint8_t* desc) {
     k_lbd_fold<<<(n + 63) / 64, 64, 0, s>>>(h->rowsum.p, n, h->desc_host.d);
     count_launches(4);
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(cudaStreamSynchronize(s));
+    OLF_CUDA(stream_sync(s));
     memcpy(desc, h->desc_host.p, (size_t)n * 32);
     return OLF_OK;
 }
@@ -1107,5 +1267,11 @@ int line_extract(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bo
 
 // [0] rounds, [1] waves, [2] accepted regions, [3] k_lsd_grow device time in microseconds (CUDA events on its stream)
 void line_last_stats(const LineImpl* h, int* out8) { for (int i = 0; i < 8; ++i) out8[i] = h->last_stats[i]; }
+int line_trace(LineImpl* h, int* out, int max_rounds) {
+    if (!h || !h->trace || !h->dbg.p) return OLF_ERR_ARG;
+    const int n = std::min<int>(max_rounds, (int)h->max_rounds);
+    OLF_CUDA(cudaMemcpy(out, h->dbg.p, (size_t)n * TRACE_REC * sizeof(int), cudaMemcpyDeviceToHost));
+    return OLF_OK;
+}
 
 }  // namespace olf

@@ -156,7 +156,7 @@ int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0
     launch_knn2(s, dptr<uint4>(c, o_q), n1, dptr<uint4>(c, o_t), n2, dptr<Knn2>(c, o_part), o, o + n1, o + 2 * n1, o + 3 * n1, splits, per);
     OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_out), o, (size_t)4 * n1 * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(cudaStreamSynchronize(s));
+    OLF_CUDA(stream_sync(s));
     const int* ho = hptr<int>(c, p_out);
     memcpy(idx0, ho, n1 * 4); memcpy(dist0, ho + n1, n1 * 4); memcpy(idx1, ho + 2 * n1, n1 * 4); memcpy(dist1, ho + 3 * n1, n1 * 4);
     return OLF_OK;
@@ -192,7 +192,7 @@ int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr,
     }
     OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_m), dptr<int>(c, o_m12), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(cudaStreamSynchronize(s));
+    OLF_CUDA(stream_sync(s));
     const int* hm = hptr<int>(c, p_m);
     int cnt = 0;
     for (int i = 0; i < n1; ++i) { m12[i] = hm[i]; cnt += hm[i] >= 0; }
@@ -363,7 +363,7 @@ int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const u
     OLF_CUDA(cudaMemcpyAsync(ho, dptr<float>(c, o_u), (size_t)N * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(ho + N, dptr<float>(c, o_d), (size_t)N * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(cudaStreamSynchronize(s));
+    OLF_CUDA(stream_sync(s));
     memcpy(uRight, ho, (size_t)N * 4); memcpy(depth, ho + N, (size_t)N * 4);
     return OLF_OK;
 }
@@ -535,7 +535,7 @@ int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_key
     OLF_CUDA(cudaMemcpyAsync(hptr<float>(c, p_disp), dptr<float>(c, o_disp), (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(hptr<double>(c, p_le), dptr<double>(c, o_le), (size_t)n1 * 24, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(cudaStreamSynchronize(s));
+    OLF_CUDA(stream_sync(s));
     memcpy(matches12, hptr<int>(c, p_m), (size_t)n1 * 4); memcpy(disp, hptr<float>(c, p_disp), (size_t)n1 * 8); memcpy(le, hptr<double>(c, p_le), (size_t)n1 * 24);
     return OLF_OK;
 }
@@ -689,7 +689,7 @@ static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t
     OLF_CUDA(cudaMemcpyAsync(ho, dptr<int>(c, o_as), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(ho + nq, dptr<int>(c, o_cnt), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(cudaStreamSynchronize(s));
+    OLF_CUDA(stream_sync(s));
     for (int i = 0; i < nq; ++i) {
         if (ho[nq + i] > SBP_K) { set_last_error("olf_search_by_projection: more than 128 candidates in one search window"); return OLF_ERR_CAPACITY; }
         assign_out[i] = ho[i];

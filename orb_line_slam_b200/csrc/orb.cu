@@ -559,7 +559,7 @@ int orb_extract(OrbImpl* h, const uint8_t* img, int w, int hgt, int stride, bool
     OLF_CUDA(cudaSetDevice(h->device));
     int rc = orb_enqueue_phase1(h, img, w, hgt, stride, on_device);
     if (rc) return rc;
-    OLF_CUDA(cudaStreamSynchronize(h->stream));
+    OLF_CUDA(stream_sync(h->stream));
     const int ncand = *h->total_host.p;
     if (ncand > h->cand_cap) { set_last_error("FAST candidate buffer overflow"); return OLF_ERR_CAPACITY; }
     h->last_ncand = ncand;
@@ -608,7 +608,7 @@ int orb_extract(OrbImpl* h, const uint8_t* img, int w, int hgt, int stride, bool
     k_rbrief<<<(total + 7) / 8, 256, 0, h->stream>>>(h->blur.p, T, h->kept.p, total, h->desc.p);
     count_launches(1);
     OLF_CUDA(cudaMemcpyAsync(h->desc_host.p, h->desc.p, (size_t)total * 32, cudaMemcpyDeviceToHost, h->stream));
-    OLF_CUDA(cudaStreamSynchronize(h->stream));
+    OLF_CUDA(stream_sync(h->stream));
     OLF_CUDA(cudaGetLastError());
     memcpy(desc, h->desc_host.p, (size_t)total * 32);
     return OLF_OK;
