@@ -53,7 +53,7 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
@@ -79,46 +79,51 @@ class ClockSampler:
 
 
 def run_steps(pipes, frontends, track_fe, seq_imgs, poses, first, count, on_device, dev_imgs):
-    """Process frames [first, first+count) on len(pipes) concurrent rigs; frame f's tracking step waits for frame f-1."""
+    """Process frames [first, first+count) on len(pipes) concurrent rigs (Frame::Frame each); one tracker thread consumes
+    the finished frames in order and runs the frame-to-frame matchers of TrackWithMotionModelWithLine on (f, f-1)."""
     P = len(pipes)
-    done = [threading.Event() for _ in range(count + 1)]
-    blocks = [None] * (count + 1)
-    views = [None] * (count + 1)
+    done = [threading.Event() for _ in range(count)]
+    views = [None] * count
     stats = {"matches": 0, "line_matches": 0, "kps": 0, "lines": 0, "d2h": 0}
-    done[0].set()                      # the frame before the first one: nothing to track against
     errors = []
-    lock = threading.Lock()
 
     def worker(p):
         try:
             nat = pipes[p]
             for k in range(p, count, P):
-                f = first + k
-                i = f % len(seq_imgs)
+                i = (first + k) % len(seq_imgs)
                 blk = nat.new_block()
                 if on_device:
                     nat.process(dev_imgs[i][0], dev_imgs[i][1], blk, on_device=True)
                 else:
                     nat.process(seq_imgs[i][0], seq_imgs[i][1], blk, on_device=False)
-                v = nat.view(blk, poses[i])
-                blocks[k + 1], views[k + 1] = blk, v
-                done[k].wait()
-                t = None
-                if views[k] is not None:           # TrackWithMotionModelWithLine matchers (src/Tracking.cc:1296,1308)
-                    t = track_fe[p].track(v, views[k])
-                with lock:
-                    if t is not None:
-                        stats["matches"] += t["nmatches"]; stats["line_matches"] += t.get("n_line_matches", 0)
-                    stats["kps"] += len(v.kps) + len(v.kps_r); stats["lines"] += len(v.kls) + len(v.kls_r)
-                    stats["d2h"] += (len(v.kps) + len(v.kps_r)) * 56 + len(v.kps) * 8 + (len(v.kls) + len(v.kls_r)) * 100 + len(v.kls) * 36
-                views[k] = None
-                done[k + 1].set()
+                views[k] = nat.view(blk, poses[i])
+                done[k].set()
         except Exception as e:       # noqa: BLE001
             errors.append(e)
             for d in done:
                 d.set()
 
-    ths = [threading.Thread(target=worker, args=(p,)) for p in range(P)]
+    def tracker():
+        try:
+            prev = None
+            for k in range(count):
+                done[k].wait()
+                if errors:
+                    return
+                v = views[k]
+                if prev is not None:               # src/Tracking.cc:1296 (SearchByProjection) and :1308 (line match)
+                    t = track_fe[0].track(v, prev)
+                    stats["matches"] += t["nmatches"]; stats["line_matches"] += t.get("n_line_matches", 0)
+                stats["kps"] += len(v.kps) + len(v.kps_r); stats["lines"] += len(v.kls) + len(v.kls_r)
+                stats["d2h"] += (len(v.kps) + len(v.kps_r)) * 56 + len(v.kps) * 8 + (len(v.kls) + len(v.kls_r)) * 100 + len(v.kls) * 36
+                prev = v
+                if k > 0:
+                    views[k - 1] = None
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+
+    ths = [threading.Thread(target=worker, args=(p,)) for p in range(P)] + [threading.Thread(target=tracker)]
     for t in ths:
         t.start()
     for t in ths:
