@@ -94,20 +94,26 @@ __global__ void __launch_bounds__(256) k_lsd_hist(const float* __restrict__ ang,
 
 // one block: bin offsets (descending bin order) and the wave plan (whole bins, cumulative targets doubling)
 struct LsdPlan { int n_seeds; int n_waves; int wave_start[64]; };
-__global__ void k_lsd_plan(const unsigned* __restrict__ hist, int n_bins, int first_wave, int wave_growth, unsigned* __restrict__ bin_start,
-                           unsigned* __restrict__ cursor, LsdPlan* __restrict__ plan) {
-    if (threadIdx.x != 0) return;
-    unsigned acc = 0;
-    int nw = 0;
-    long long target = first_wave;
-    plan->wave_start[0] = 0;
-    for (int b = n_bins - 1; b >= 0; --b) {
-        bin_start[b] = acc; cursor[b] = 0;
-        acc += hist[b];
-        if ((long long)acc - plan->wave_start[nw] >= target && nw < 61) { plan->wave_start[++nw] = (int)acc; target *= wave_growth; }
+__global__ void __launch_bounds__(1024) k_lsd_plan(const unsigned* __restrict__ hist, int n_bins, int first_wave, int wave_growth, unsigned* __restrict__ bin_start,
+                                                    unsigned* __restrict__ cursor, LsdPlan* __restrict__ plan) {
+    __shared__ unsigned sh[1024], st[1024];
+    for (int b = threadIdx.x; b < 1024; b += blockDim.x) sh[b] = b < n_bins ? hist[b] : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        int nw = 0;
+        long long target = first_wave;
+        plan->wave_start[0] = 0;
+        for (int b = n_bins - 1; b >= 0; --b) {
+            st[b] = acc;
+            acc += sh[b];
+            if ((long long)acc - plan->wave_start[nw] >= target && nw < 61) { plan->wave_start[++nw] = (int)acc; target *= wave_growth; }
+        }
+        if (plan->wave_start[nw] != (int)acc) plan->wave_start[++nw] = (int)acc;
+        plan->n_seeds = (int)acc; plan->n_waves = nw;
     }
-    if (plan->wave_start[nw] != (int)acc) plan->wave_start[++nw] = (int)acc;
-    plan->n_seeds = (int)acc; plan->n_waves = nw;
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) { bin_start[b] = st[b]; cursor[b] = 0; }
 }
 
 __global__ void __launch_bounds__(256) k_lsd_scatter(const float* __restrict__ ang, const short2_t* __restrict__ dabc, int S,
@@ -652,16 +658,71 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) k_lsd_phase(const GrowStateW
 
 // ---- region2rect ---------------------------------------------------------------------------
 struct RectRec { double x, y, theta; u64 prio; };
-__global__ void __launch_bounds__(128) k_lsd_rect_a(const LsdRegion* __restrict__ regs, const unsigned* __restrict__ nreg, unsigned cap,
+// Warp per region.  The reference's sums are sequential double additions in BFS order (not associative), so the additions
+// stay a single chain -- but everything that feeds them (pixel fetch, gradient weight sqrt/div, products) is computed by
+// the 32 lanes in parallel and staged in shared memory; lane 0 only walks the three add chains.
+__global__ void __launch_bounds__(256) k_lsd_rect_a(const LsdRegion* __restrict__ regs, const unsigned* __restrict__ nreg, unsigned cap,
                                                     const unsigned* __restrict__ final_pool, const short2_t* __restrict__ dabc, int W,
                                                     double prec, RectRec* __restrict__ out_host) {
+    __shared__ double sh[8][3][32];
     const unsigned n = min(*nreg, cap);
-    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const LsdRegion R = regs[r];
-    const RectA a = region_rect_a(final_pool + R.off, R.count, dabc, W, R.reg_angle, prec);
-    RectRec o; o.x = a.x; o.y = a.y; o.theta = a.theta; o.prio = R.prio;
-    out_host[r] = o;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (unsigned r = blockIdx.x * 8 + warp; r < n; r += gridDim.x * 8) {
+        const LsdRegion R = regs[r];
+        const unsigned* pix = final_pool + R.off;
+        // pass 1: centroid weighted by the gradient norm
+        double x = 0, y = 0, sum = 0;
+        for (int base = 0; base < R.count; base += 32) {
+            const int k = base + lane;
+            if (k < R.count) {
+                const int p = (int)pix[k];
+                const short2_t d = dabc[p];
+                const int gx = d.x + d.y, gy = d.x - d.y;
+                const double w = d_sqrt(d_div((double)(gx * gx + gy * gy), 4.0));
+                sh[warp][0][lane] = d_mul((double)(p % W), w);
+                sh[warp][1][lane] = d_mul((double)(p / W), w);
+                sh[warp][2][lane] = w;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const int m = min(32, R.count - base);
+                for (int j = 0; j < m; ++j) { x = d_add(x, sh[warp][0][j]); y = d_add(y, sh[warp][1][j]); sum = d_add(sum, sh[warp][2][j]); }
+            }
+            __syncwarp();
+        }
+        x = shfl_f64(d_div(x, sum), 0); y = shfl_f64(d_div(y, sum), 0);
+        // pass 2: inertia matrix
+        double Ixx = 0, Iyy = 0, Ixy = 0;
+        for (int base = 0; base < R.count; base += 32) {
+            const int k = base + lane;
+            if (k < R.count) {
+                const int p = (int)pix[k];
+                const short2_t d = dabc[p];
+                const int gx = d.x + d.y, gy = d.x - d.y;
+                const double w = d_sqrt(d_div((double)(gx * gx + gy * gy), 4.0));
+                const double dx = d_sub((double)(p % W), x), dy = d_sub((double)(p / W), y);
+                sh[warp][0][lane] = d_mul(d_mul(dy, dy), w);
+                sh[warp][1][lane] = d_mul(d_mul(dx, dx), w);
+                sh[warp][2][lane] = d_mul(d_mul(dx, dy), w);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const int m = min(32, R.count - base);
+                for (int j = 0; j < m; ++j) { Ixx = d_add(Ixx, sh[warp][0][j]); Iyy = d_add(Iyy, sh[warp][1][j]); Ixy = d_sub(Ixy, sh[warp][2][j]); }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const double dI = d_sub(Ixx, Iyy);
+            const double lambda = d_mul(0.5, d_sub(d_add(Ixx, Iyy), d_sqrt(d_add(d_mul(dI, dI), d_mul(d_mul(4.0, Ixy), Ixy)))));
+            double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)olf::lsd::fast_atan2_deg((float)d_sub(lambda, Ixx), (float)Ixy)
+                                                    : (double)olf::lsd::fast_atan2_deg((float)Ixy, (float)d_sub(lambda, Iyy));
+            theta = d_mul(theta, kDegToRads);
+            if (angle_diff(theta, R.reg_angle) > prec) theta = d_add(theta, M_PI);
+            RectRec o; o.x = x; o.y = y; o.theta = theta; o.prio = R.prio;
+            out_host[r] = o;
+        }
+    }
 }
 // warp per region: extreme projections on the (host-libm) direction -> segment end points (Vec4f)
 __global__ void __launch_bounds__(256) k_lsd_rect_b(const LsdRegion* __restrict__ regs, int n, const unsigned* __restrict__ final_pool, int W,
@@ -1074,7 +1135,7 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     }
     const int nb = h->P.lsd_n_bins;
     k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
-    k_lsd_plan<<<1, 32, 0, s>>>(h->hist.p, nb, h->first_wave, h->wave_growth, h->bin_start.p, h->cursor.p, h->plan.p);
+    k_lsd_plan<<<1, 1024, 0, s>>>(h->hist.p, nb, h->first_wave, h->wave_growth, h->bin_start.p, h->cursor.p, h->plan.p);
     k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p);
     GrowState G;
     G.A.W = W; G.A.H = H; G.A.ang = h->ang.p; G.A.dabc = h->dabc.p; G.A.tab_seed = h->tab_seed.p; G.A.tab_acc = h->tab_acc.p;
@@ -1112,7 +1173,7 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     }
     OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
     count_launches((h->blur_k ? 2 : 0) + 6);
-    k_lsd_rect_a<<<(h->reg_cap + 127) / 128, 128, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
+    k_lsd_rect_a<<<296, 256, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
     OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
@@ -1124,7 +1185,7 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
             for (int k = 0; k < h->phase_batch; ++k) k_lsd_phase<<<h->grow_blocks, GW_WARPS * 32, 0, s>>>(GW, h->phase.p);
             count_launches(h->phase_batch + 1);
             OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
-            k_lsd_rect_a<<<(h->reg_cap + 127) / 128, 128, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
+            k_lsd_rect_a<<<296, 256, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
             OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
             OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
             OLF_CUDA(stream_sync(s));

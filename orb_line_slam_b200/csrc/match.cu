@@ -295,24 +295,35 @@ __global__ void __launch_bounds__(256) k_stereo_points(const olf_keypoint* __res
     }
     if (lane == 0) { uRight[iL] = out_u; depth[iL] = out_d; sad[iL] = out_s; }
 }
-// median SAD outlier rejection (src/Frame.cc:861-875): one block; rank counting for the size/2-th order statistic
+// median SAD outlier rejection (src/Frame.cc:861-875): one block; the size/2-th order statistic of the SAD values
+// (all < 2^16: 121 px x 510) by a two-level radix select on shared-memory histograms
 __global__ void __launch_bounds__(1024) k_stereo_median(float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad, int N) {
-    __shared__ int s_cnt, s_median;
+    __shared__ unsigned hist[256];
+    __shared__ int s_cnt, s_hi, s_rank, s_median;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) { s_cnt = 0; s_median = -1; }
     __syncthreads();
     int local = 0;
-    for (int i = threadIdx.x; i < N; i += 1024) local += sad[i] >= 0;
-    atomicAdd(&s_cnt, local);
+    for (int i = threadIdx.x; i < N; i += 1024) { const int v = sad[i]; if (v >= 0) { ++local; atomicAdd(&hist[min(v, 65535) >> 8], 1u); } }
+    if (local) atomicAdd(&s_cnt, local);
     __syncthreads();
     const int cnt = s_cnt;
     if (cnt == 0) return;
-    const int k = cnt / 2;
-    for (int i = threadIdx.x; i < N; i += 1024) {
-        const int v = sad[i];
-        if (v < 0) continue;
-        int less = 0, leq = 0;
-        for (int j = 0; j < N; ++j) { const int u = sad[j]; if (u >= 0) { less += u < v; leq += u <= v; } }
-        if (less <= k && k < leq) s_median = v;
+    if (threadIdx.x == 0) {
+        int k = cnt / 2, b = 0;
+        while (k >= (int)hist[b]) { k -= (int)hist[b]; ++b; }
+        s_hi = b; s_rank = k;
+    }
+    __syncthreads();
+    const int hi = s_hi;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += 1024) { const int v = sad[i]; if (v >= 0 && (min(v, 65535) >> 8) == hi) atomicAdd(&hist[min(v, 65535) & 255], 1u); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int k = s_rank, b = 0;
+        while (k >= (int)hist[b]) { k -= (int)hist[b]; ++b; }
+        s_median = (hi << 8) | b;
     }
     __syncthreads();
     const float thDist = fmul(0x1.0cccccp+1f /* 1.5f*1.4f */, (float)s_median);

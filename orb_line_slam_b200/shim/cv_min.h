@@ -1,0 +1,62 @@
+// Minimal stand-in for the handful of OpenCV types that appear in the reference's front-end class surfaces
+// (cv::Mat, cv::KeyPoint, cv::Point2f, cv::InputArray/OutputArray, cv::line_descriptor::KeyLine).  Used ONLY when the
+// shim is built without OpenCV (this image has no OpenCV C++); define OLF_HAVE_OPENCV to compile the very same shim
+// sources against the real headers inside the reference tree.
+#pragma once
+#ifdef OLF_HAVE_OPENCV
+#include <opencv2/core/core.hpp>
+#include <line_descriptor_custom.hpp>
+#else
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_32F 5
+namespace cv {
+typedef unsigned char uchar;
+struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+struct KeyPoint {                      // cv::KeyPoint, same field names and defaults
+    Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1;
+};
+class Mat {
+public:
+    int rows = 0, cols = 0; size_t step = 0; uchar* data = nullptr;
+    Mat() {}
+    Mat(int r, int c, int type) { create(r, c, type); }
+    Mat(int r, int c, int type, void* ext, size_t step_) : rows(r), cols(c), step(step_), data((uchar*)ext), type_(type) {}
+    void create(int r, int c, int type) {
+        type_ = type; rows = r; cols = c; step = (size_t)c * elem();
+        buf_ = std::make_shared<std::vector<uchar>>((size_t)r * step);
+        data = buf_->data();
+    }
+    void release() { buf_.reset(); data = nullptr; rows = cols = 0; step = 0; }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    int type() const { return type_; }
+    uchar* ptr(int r = 0) { return data + (size_t)r * step; }
+    const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
+    template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
+    template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
+    template <typename T> T& at(int r, int c) { return ((T*)(data + (size_t)r * step))[c]; }
+    template <typename T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step))[c]; }
+    Mat row(int r) const { Mat m; m.rows = 1; m.cols = cols; m.step = step; m.data = data + (size_t)r * step; m.type_ = type_; m.buf_ = buf_; return m; }
+    Mat clone() const { Mat m(rows, cols, type_); for (int r = 0; r < rows; ++r) memcpy(m.ptr(r), ptr(r), (size_t)cols * elem()); return m; }
+    void copyTo(Mat& o) const { o = clone(); }
+private:
+    size_t elem() const { return type_ == CV_32F ? 4 : 1; }
+    int type_ = CV_8UC1;
+    std::shared_ptr<std::vector<uchar>> buf_;
+};
+typedef const Mat& InputArray;
+typedef Mat& OutputArray;
+namespace line_descriptor {
+struct KeyLine {                       // Thirdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp:105-145
+    float angle; int class_id; int octave; Point2f pt; float response; float size;
+    float startPointX, startPointY, endPointX, endPointY;
+    float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+    float lineLength; int numOfPixels;
+};
+}  // namespace line_descriptor
+}  // namespace cv
+#endif
