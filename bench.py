@@ -272,12 +272,12 @@ def main():
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 4 * 1280 * 720, "d2h_bytes_per_step": int(st_e2e["d2h"] / max(args.steps, 1)),
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "k_lsd_grow", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "k_lsd_phase", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)", "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel_ms": grow_ms,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "latency-bound sequential region growing; HBM fraction is honest but not the limiter (see DESIGN.md)"}}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             frames = args.cpu_frames
             cfps, dt = cpu_reference(frames, [(a, b) for a, b in host_pinned[:N_BASE_FRAMES]], poses[:N_BASE_FRAMES], warm=1)
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": 1, "kind": "port",

@@ -87,17 +87,23 @@ static inline void resize_linear(const Image8& src, Image8& dst) {   // dst.w/h 
     std::vector<LinCoef> cx, cy;
     linear_coeffs(src.w, dst.w, cx);
     linear_coeffs(src.h, dst.h, cy);
-    std::vector<int> r0(dst.w), r1(dst.w);
+    std::vector<int> rows[2] = {std::vector<int>(dst.w), std::vector<int>(dst.w)};
+    int have[2] = {-1, -1};
+    auto hrow = [&](int sy) -> const int* {              // horizontal pass of source row sy, cached (2 rows live)
+        for (int k = 0; k < 2; ++k) if (have[k] == sy) return rows[k].data();
+        const int k = (have[0] < have[1]) ? 0 : 1;       // evict the older (smaller) row
+        const uint8_t* s = src.row(sy);
+        int* o = rows[k].data();
+        for (int x = 0; x < dst.w; ++x) { const int x0 = cx[x].s, x1 = std::min(x0 + 1, src.w - 1); o[x] = s[x0] * cx[x].c0 + s[x1] * cx[x].c1; }
+        have[k] = sy;
+        return o;
+    };
     for (int y = 0; y < dst.h; ++y) {
-        int y0 = cy[y].s, y1 = std::min(y0 + 1, src.h - 1);
-        const uint8_t* s0 = src.row(y0);
-        const uint8_t* s1 = src.row(y1);
-        for (int x = 0; x < dst.w; ++x) {
-            int x0 = cx[x].s, x1 = std::min(x0 + 1, src.w - 1);
-            r0[x] = s0[x0] * cx[x].c0 + s0[x1] * cx[x].c1;
-            r1[x] = s1[x0] * cx[x].c0 + s1[x1] * cx[x].c1;
-        }
-        int b0 = cy[y].c0, b1 = cy[y].c1;
+        const int y0 = cy[y].s, y1 = std::min(y0 + 1, src.h - 1);
+        const int* r0 = hrow(y0);
+        const int* r1 = hrow(y1);
+        r0 = hrow(y0);                                    // (y1's fill may have evicted nothing of y0: 2 slots, distinct rows)
+        const int b0 = cy[y].c0, b1 = cy[y].c1;
         uint8_t* o = dst.row(y);
         for (int x = 0; x < dst.w; ++x)
             o[x] = (uint8_t)((((b0 * (r0[x] >> 4)) >> 16) + ((b1 * (r1[x] >> 4)) >> 16) + 2) >> 2);
@@ -161,19 +167,22 @@ static inline std::vector<int> gauss_kernel_q8(int n, double sigma) {
 static inline void gaussian_blur_q8(const Image8& src, const std::vector<int>& q, Image8& dst) {
     const int n = (int)q.size(), r = n / 2, w = src.w, h = src.h;
     std::vector<uint16_t> tmp((size_t)w * h);
-    for (int y = 0; y < h; ++y) {
+    std::vector<uint8_t> prow((size_t)w + 2 * r);
+    std::vector<uint32_t> acc(w);
+    for (int y = 0; y < h; ++y) {                       // horizontal pass, 8.8 fixed point
         const uint8_t* s = src.row(y);
-        uint16_t* t = tmp.data() + (size_t)y * w;
-        for (int x = 0; x < w; ++x) {
-            uint32_t a = 0;
-            if (x >= r && x < w - r) { for (int k = 0; k < n; ++k) a += (uint32_t)q[k] * s[x + k - r]; }
-            else { for (int k = 0; k < n; ++k) a += (uint32_t)q[k] * s[reflect101(x + k - r, w)]; }
-            t[x] = (uint16_t)a;
+        for (int x = -r; x < w + r; ++x) prow[x + r] = s[reflect101(x, w)];
+        std::fill(acc.begin(), acc.end(), 0u);
+        for (int k = 0; k < n; ++k) {
+            const uint32_t qk = (uint32_t)q[k];
+            const uint8_t* pk = prow.data() + k;
+            for (int x = 0; x < w; ++x) acc[x] += qk * pk[x];
         }
+        uint16_t* t = tmp.data() + (size_t)y * w;
+        for (int x = 0; x < w; ++x) t[x] = (uint16_t)acc[x];
     }
     dst = Image8(w, h);
-    std::vector<uint32_t> acc(w);
-    for (int y = 0; y < h; ++y) {
+    for (int y = 0; y < h; ++y) {                       // vertical pass, 16.16 fixed point
         std::fill(acc.begin(), acc.end(), 0u);
         for (int k = 0; k < n; ++k) {
             const uint16_t* t = tmp.data() + (size_t)reflect101(y + k - r, h) * w;
@@ -226,24 +235,27 @@ static inline int fast_score_px(const uint8_t* p, int stride) {
 // which allows the usual early rejection (any 9-arc contains one pixel of every opposite pair).
 static inline void fast_score_map(const uint8_t* img, int w, int h, int stride, std::vector<uint8_t>& score, int th = 1) {
     score.assign((size_t)w * h, 0);
-    int off[16];
-    for (int k = 0; k < 16; ++k) off[k] = FAST_DY[k] * stride + FAST_DX[k];
+    std::vector<uint8_t> cand(w, 0);
+    const unsigned band = (unsigned)(2 * th);
     for (int y = 3; y < h - 3; ++y) {
-        const uint8_t* row = img + (size_t)y * stride;
+        const uint8_t* r0 = img + (size_t)y * stride;
+        const uint8_t *u3 = r0 - 3 * stride, *d3 = r0 + 3 * stride, *u2 = r0 - 2 * stride, *d2 = r0 + 2 * stride;
+        // pass 1 (auto-vectorised): a 9-arc contains one pixel of every opposite pair, so a pair inside the band rejects
+        for (int x = 3; x < w - 3; ++x) {
+            const int v = r0[x] - th;
+            const bool p0 = (unsigned)(d3[x] - v) <= band, p8 = (unsigned)(u3[x] - v) <= band;
+            const bool p4 = (unsigned)(r0[x + 3] - v) <= band, p12 = (unsigned)(r0[x - 3] - v) <= band;
+            const bool p2 = (unsigned)(d2[x + 2] - v) <= band, p10 = (unsigned)(u2[x - 2] - v) <= band;
+            const bool p6 = (unsigned)(u2[x + 2] - v) <= band, p14 = (unsigned)(d2[x - 2] - v) <= band;
+            cand[x] = !((p0 & p8) | (p4 & p12) | (p2 & p10) | (p6 & p14));
+        }
         uint8_t* srow = score.data() + (size_t)y * w;
         for (int x = 3; x < w - 3; ++x) {
-            const uint8_t* p = row + x;
+            if (!cand[x]) continue;
+            const uint8_t* p = r0 + x;
             const int v = p[0], lo = v - th, hi = v + th;
-            int a = p[off[0]], b = p[off[8]];
-            if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
-            a = p[off[4]]; b = p[off[12]];
-            if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
-            a = p[off[2]]; b = p[off[10]];
-            if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
-            a = p[off[6]]; b = p[off[14]];
-            if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
             unsigned mpos = 0, mneg = 0;
-            for (int k = 0; k < 16; ++k) { const int q = p[off[k]]; mpos |= (unsigned)(q < lo) << k; mneg |= (unsigned)(q > hi) << k; }
+            for (int k = 0; k < 16; ++k) { const int q = p[FAST_DY[k] * stride + FAST_DX[k]]; mpos |= (unsigned)(q < lo) << k; mneg |= (unsigned)(q > hi) << k; }
             auto run9 = [](unsigned m) { unsigned u = m | (m << 16); unsigned r = u & (u >> 1); r &= r >> 2; r &= r >> 4; r &= u >> 8; return r != 0; };
             if (!run9(mpos) && !run9(mneg)) continue;
             const int s = fast_score_px(p, stride);
