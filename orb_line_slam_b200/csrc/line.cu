@@ -11,12 +11,10 @@
 #include "img_kernels.cuh"
 #include "lsd_core.h"
 #include "line.h"
-#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <numeric>
 
-namespace cg = cooperative_groups;
 
 namespace olf {
 using namespace lsd;
@@ -39,12 +37,25 @@ __global__ void k_resize_exact(const uint8_t* __restrict__ src, int sw, int sh, 
     dst[(size_t)y * dpitch + x] = (uint8_t)((acc + (1u << 15)) >> 16);
 }
 
+// Everything the grow kernel needs to know about a pixel sits in ONE 32-byte sector: both claim words, the level-line
+// angle, the (cos, sin) the reference accumulates and the priority bin.  A neighbour test costs one sector instead of four
+// scattered ones, which is what keeps many frames in flight from thrashing L2 / HBM with random 32-B accesses.
+struct __align__(32) PxRec { u64 claim[2]; float ang; float cx; float cy; unsigned binrev; };
+struct __align__(16) PxLo { float ang; float cx; float cy; unsigned binrev; };
+__device__ __forceinline__ u64 px_claim(const PxRec* px, int q, int parity) { return __ldcg(&px[q].claim[parity]); }
+__device__ __forceinline__ void px_load(const PxRec* px, int q, u64& c0, u64& c1, PxLo& lo) {
+    const ulonglong2 c = __ldcg(reinterpret_cast<const ulonglong2*>(&px[q]));
+    const float4 f = __ldcg(reinterpret_cast<const float4*>(&px[q]) + 1);
+    c0 = c.x; c1 = c.y; lo.ang = f.x; lo.cx = f.y; lo.cy = f.z; lo.binrev = __float_as_uint(f.w);
+}
+#define GW_HASH_BITS 8
+#define GW_HASH (1 << GW_HASH_BITS)
+
 // ---- ll_angle: gradient, level-line angle, max gradient ---------------------------------
 // n2_thresh = smallest gx^2+gy^2 whose norm sqrt(n2/4.0) exceeds rho (computed exactly on the host).
 __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, int W, int H, int pitch, int n2_thresh,
                                                   float* __restrict__ ang, short2_t* __restrict__ dabc,
-                                                  const float2_t* __restrict__ tab_acc, float2_t* __restrict__ cs,
-                                                  u64* __restrict__ claim0, u64* __restrict__ claim1, int* __restrict__ n2max) {
+                                                  const float2_t* __restrict__ tab_acc, PxRec* __restrict__ px, int* __restrict__ n2max) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     int n2 = 0;
@@ -63,7 +74,9 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
         }
         float2_t c; c.x = 0.f; c.y = 0.f;
         if (a >= 0.f) c = tab_acc[tab_index(d)];
-        ang[q] = a; dabc[q] = d; cs[q] = c; claim0[q] = kClaimNone; claim1[q] = kClaimNone;
+        ang[q] = a; dabc[q] = d;
+        PxRec r; r.claim[0] = kClaimNone; r.claim[1] = kClaimNone; r.ang = a; r.cx = c.x; r.cy = c.y; r.binrev = 0;
+        px[q] = r;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n2 = max(n2, __shfl_xor_sync(0xffffffffu, n2, o));
@@ -118,18 +131,20 @@ __global__ void __launch_bounds__(1024) k_lsd_plan(const unsigned* __restrict__ 
 
 __global__ void __launch_bounds__(256) k_lsd_scatter(const float* __restrict__ ang, const short2_t* __restrict__ dabc, int S,
                                                      const int* __restrict__ n2max, int n_bins, const unsigned* __restrict__ bin_start,
-                                                     unsigned* __restrict__ cursor, int* __restrict__ seed_pix, u64* __restrict__ seed_prio) {
+                                                     unsigned* __restrict__ cursor, int* __restrict__ seed_pix, u64* __restrict__ seed_prio,
+                                                     PxRec* __restrict__ px) {
     const double coef = lsd_bin_coef(*n2max, n_bins);
     for (int q = blockIdx.x * 256 + threadIdx.x; q < S; q += gridDim.x * 256)
         if (ang[q] >= 0.f) {
             const int b = lsd_bin(dabc[q], coef);
+            px[q].binrev = (unsigned)(n_bins - 1 - b);
             const unsigned pos = bin_start[b] + atomicAdd(&cursor[b], 1u);
             seed_pix[pos] = q;
             seed_prio[pos] = make_prio(n_bins - 1 - b, q);
         }
 }
 
-// ---- region growing: persistent cooperative kernel, one thread per seed per round (see lsd_core.h) ----------
+// ---- region growing state shared by the phase kernel (semantics: grow_seed() in lsd_core.h) ------------------
 struct LsdRegion { u64 prio; unsigned off; int count; double reg_angle; };
 struct GrowState {
     GrowArgs A;
@@ -144,59 +159,6 @@ struct GrowState {
     int* status;                // [0] error flag, [1] rounds used, [2] waves
 };
 
-__global__ void __launch_bounds__(256) k_lsd_grow(const GrowState G) {
-    cg::grid_group grid = cg::this_grid();
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const int n_waves = G.plan->n_waves;
-    unsigned round = 1;
-    for (int wv = 0; wv < n_waves; ++wv) {
-        const int lo = G.plan->wave_start[wv], hi = G.plan->wave_start[wv + 1];
-        for (int i = lo + tid; i < hi; i += nth) { G.cnt[0][i] = 0; G.cnt[1][i] = 0; }
-        for (;;) {
-            if (tid == 0) *G.A.pool_ctr[round & 1] = 0;
-            grid.sync();
-            bool any_change = false;
-            for (int i = lo + tid; i < hi; i += nth) {
-                const GrowResult r = grow_seed(G.A, round, G.seed_pix[i], G.seed_prio[i], G.head[(round - 1) & 1][i], G.cnt[(round - 1) & 1][i]);
-                G.head[round & 1][i] = r.head; G.cnt[round & 1][i] = r.count; G.regang[i] = r.reg_angle;
-                if (r.overflow) G.status[0] = OLF_ERR_CAPACITY;
-                any_change |= !r.same_as_prev;
-            }
-            if (__syncthreads_or(any_change) && threadIdx.x == 0) G.changed[round] = 1;
-            __threadfence();
-            grid.sync();
-            const bool changed = ((volatile unsigned*)G.changed)[round] != 0;
-            if (!changed || round + 2 >= G.max_rounds || ((volatile int*)G.status)[0] != 0) break;
-            ++round;
-        }
-        // finalise the wave: stamp the regions for good, keep the pixel lists of accepted regions
-        for (int i = lo + tid; i < hi; i += nth) {
-            const int c = G.cnt[round & 1][i];
-            if (c == 0) continue;
-            const u64 prio = G.seed_prio[i];
-            const bool accept = c >= G.min_reg_size;
-            unsigned off = 0;
-            if (accept) off = atomicAdd(G.final_ctr, (unsigned)c);
-            ListReader rd; rd.init(G.A.pool[round & 1], G.head[round & 1][i]);
-            for (int k = 0; k < c; ++k) {
-                const unsigned p = rd.next();
-                G.A.claim[0][p] = prio; G.A.claim[1][p] = prio;
-                if (accept) G.final_pool[off + k] = p;
-            }
-            if (accept) {
-                const unsigned r = atomicAdd(G.nreg, 1u);
-                if (r < G.reg_cap) { LsdRegion R; R.prio = prio; R.off = off; R.count = c; R.reg_angle = G.regang[i]; G.regs[r] = R; }
-                else G.status[0] = OLF_ERR_CAPACITY;
-            }
-        }
-        ++round;
-        __threadfence();
-        grid.sync();
-        if (((volatile int*)G.status)[0] != 0) break;
-    }
-    if (tid == 0) { G.status[1] = (int)round; G.status[2] = n_waves; }
-}
-
 // ---- region growing, warp-cooperative: one WARP per seed per round ----------------------------------------------
 // Same operator as grow_seed() in lsd_core.h (which stays the executable specification, emulated on the host by
 // tests/emul), restructured so that nothing on the sequential critical path of a region is a dependent global load:
@@ -209,17 +171,16 @@ __global__ void __launch_bounds__(256) k_lsd_grow(const GrowState G) {
 //   * claims are atomicMin by lane 0; their return values are awaited once per step, which makes the warp's own claims
 //     visible to the next step's (L2) loads -- no duplicate can enter a list.
 #define GW_WARPS 8
-#define GW_HASH_BITS 8
-#define GW_HASH (1 << GW_HASH_BITS)
 struct GrowStateW {
     GrowState G;
-    const float2_t* cs;         // per pixel (cos, sin) as accumulated by the reference: tab_acc[(DA,BC)]
+    PxRec* px;                  // packed per-pixel record (claims + angle + (cos, sin) + bin)
     unsigned* work_ctr;         // [2*max_rounds + 64] zero-initialised work counters (one per round / finalise pass)
     // per seed and round parity: the aligned candidates that were refused because a NON-final higher-priority claim held
     // them (one chunk at most; count 255 = too many, always re-grow).  Together with the pixel list they are the complete
     // set of external facts a growth depended on, which is what lets an unchanged region be verified instead of re-grown.
     unsigned* blk_chunk[2]; int* blk_cnt[2];
     int fast_align; float c_hi2, c_lo2;   // lazy alignment test: cos^2(prec -/+ 0.1 deg)
+    int defer;                            // first round of a wave: seeds with a live higher-priority aligned neighbour wait
     int* dbg;                   // optional per-round trace (see OLF_LSD_TRACE)
 };
 
@@ -247,8 +208,7 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
     const int cur = round & 1, prv = (round - 1) & 1;
     const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
     const u64 mine = (sf_cur << 40) | prio;
-    u64* claim_cur = A.claim[cur];
-    const u64* claim_prev = A.claim[prv];
+    PxRec* px = S.px;
     unsigned* pool = A.pool[cur];
     const unsigned* ppool = A.pool[prv];
     const unsigned prev_head = __ldcg(&G.head[prv][i]);
@@ -257,11 +217,11 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
     int dead = 0;
     unsigned first_chunk = 0;
     if (lane == 0) {
-        const u64 ep = __ldcg(&claim_prev[seed]);
+        const u64 ep = px_claim(px, seed, prv);
         u64 sf = ep >> 40;
         dead = (sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio);
         if (!dead) {
-            const u64 old = atomicMin(&claim_cur[seed], mine);
+            const u64 old = atomicMin(&px[seed].claim[cur], mine);
             sf = old >> 40;
             dead = (sf == 0) || (sf == sf_cur && (old & kPrioMask) < prio);
         }
@@ -282,7 +242,7 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
                 const unsigned v = __ldcg(&ppool[(size_t)chunk * kChunk + lane]);
                 bool bad = false;
                 if (lane < kChunk - 1 && k + lane < prev_cnt) {
-                    const u64 ep = __ldcg(&claim_prev[v]);
+                    const u64 ep = px_claim(px, (int)v, prv);
                     bad = ((ep >> 40) == sf_prev) && ((ep & kPrioMask) < prio);
                 }
                 ok = !__any_sync(0xffffffffu, bad);
@@ -293,7 +253,7 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
             const unsigned v = __ldcg(&ppool[(size_t)__ldcg(&S.blk_chunk[prv][i]) * kChunk + lane]);
             bool bad = false;
             if (lane < bc) {
-                const u64 ep = __ldcg(&claim_prev[v]);
+                const u64 ep = px_claim(px, (int)v, prv);
                 const u64 sf = ep >> 40;
                 bad = !((sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio));      // no longer held -> must re-grow
             }
@@ -303,7 +263,7 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
             unsigned chunk = prev_head;
             for (int k = 0; k < prev_cnt; k += kChunk - 1) {
                 const unsigned v = __ldcg(&ppool[(size_t)chunk * kChunk + lane]);
-                if (lane < kChunk - 1 && k + lane < prev_cnt && v != (unsigned)seed) atomicMin(&claim_cur[v], mine);
+                if (lane < kChunk - 1 && k + lane < prev_cnt && v != (unsigned)seed) atomicMin(&px[v].claim[cur], mine);
                 chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
             }
             if (S.dbg && lane == 0) atomicAdd(&S.dbg[round * TRACE_REC + 4], 1);
@@ -413,15 +373,14 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
         const int p = e == 0 ? ent[0] : (e == 1 ? ent[1] : ent[2]);
         Pf f; f.q = -1 - lane; f.aq = -1.f; f.ep = kClaimNone; f.ec = kClaimNone; f.cx = 0.f; f.cy = 0.f;
         if (lane < 27 && e < nb) {
-            const int py = p / A.W, px = p - py * A.W;
-            const int xx = px + (nidx % 3) - 1, yy = py + (nidx / 3) - 1;
+            const int ey = p / A.W, ex = p - ey * A.W;
+            const int xx = ex + (nidx % 3) - 1, yy = ey + (nidx / 3) - 1;
             if (xx >= 0 && xx < A.W && yy >= 0 && yy < A.H) {
                 f.q = yy * A.W + xx;
-                f.aq = __ldg(&A.ang[f.q]);
-                f.ep = __ldcg(&claim_prev[f.q]);
-                f.ec = __ldcg(&claim_cur[f.q]);
-                const float2_t c = S.cs[f.q];
-                f.cx = c.x; f.cy = c.y;
+                u64 c0, c1; PxLo lo;
+                px_load(px, f.q, c0, c1, lo);
+                f.ep = prv ? c1 : c0; f.ec = cur ? c1 : c0;
+                f.aq = lo.ang; f.cx = lo.cx; f.cy = lo.cy;
             }
         }
         i_issue += nb;
@@ -497,7 +456,7 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
             const float cx = __shfl_sync(0xffffffffu, cf.cx, c), cy = __shfl_sync(0xffffffffu, cf.cy, c);
             if (cf.q == qc) pot = false;                                                    // the same pixel seen from another entry
             const long long e2 = PCLK(); tS += e2 - e1;
-            if (lane == 0) { atomicMin(&claim_cur[qc], mine); hs_insert((unsigned)qc); }   // RED: no return value is consumed
+            if (lane == 0) { atomicMin(&px[qc].claim[cur], mine); hs_insert((unsigned)qc); }   // RED: no return value is consumed
             ++n_since_fence;
             const long long e3 = PCLK(); tL += e3 - e2;
             push((unsigned)qc);
@@ -555,14 +514,19 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
 // back-to-back launches walks through all phases without any host round trip; launches after `done` return at once.
 // Ordinary (non-cooperative) launches: no co-residency requirement, so the grow phases of the left/right eyes and of
 // several frames in flight interleave freely with every other kernel on the device.
-struct PhaseState { int wave; unsigned round; int mode; int done; unsigned pass; unsigned ticket; int launches; int pad; };
+struct PhaseState { int wave; unsigned round; int mode; int done; unsigned pass; unsigned ticket; int launches; unsigned wave_first_round; };
 
 __global__ void __launch_bounds__(GW_WARPS * 32, 3) k_lsd_phase(const GrowStateW S, PhaseState* __restrict__ st) {
     __shared__ unsigned hash_sets[GW_WARPS][GW_HASH];
     __shared__ bool s_last;
     const GrowState& G = S.G;
     const int wv = st->wave; const unsigned round = st->round; const int mode = st->mode; const unsigned pass = st->pass;
+    const bool first_round = round == st->wave_first_round;
     if (st->done) return;
+    if (wv >= G.plan->n_waves) {                                   // no seeds at all (flat image)
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->done = 1; G.status[1] = (int)round; G.status[2] = G.plan->n_waves; G.status[3] = 1; }
+        return;
+    }
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     const int lo = G.plan->wave_start[wv], hi = G.plan->wave_start[wv + 1];
@@ -581,11 +545,33 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) k_lsd_phase(const GrowStateW
             base = __shfl_sync(0xffffffffu, base, 0);
             if (lo + (int)base >= hi) break;
             const int i = lo + (int)base + lane;
-            int seed = 0; u64 prio = 0; bool alive = false;
+            int seed = 0; u64 prio = 0; bool alive = false, deferred = false;
             if (i < hi && lane < bsz) {
                 seed = G.seed_pix[i]; prio = G.seed_prio[i];
-                alive = !blocked_vals(__ldcg(&G.A.claim[prv][seed]), __ldcg(&G.A.claim[cur][seed]), sf_prev, sf_cur, prio);
-                if (!alive) { if (__ldcg(&G.cnt[prv][i]) != 0) any_change = true; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; }
+                alive = !blocked_vals(px_claim(S.px, seed, prv), px_claim(S.px, seed, cur), sf_prev, sf_cur, prio);
+                if (alive && first_round && S.defer) {
+                    // Work saver (does not change the fixed point): in the first round of a wave a seed that has a live,
+                    // higher-priority, aligned 8-neighbour will almost surely be absorbed by that neighbour's region, so it
+                    // sits this round out; from the second round on every live seed grows as usual.
+                    const int W = G.A.W, H = G.A.H, py = seed / W, px = seed - py * W;
+                    const float a_s = __ldg(&G.A.ang[seed]);
+                    for (int dy = -1; dy <= 1 && alive; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int xx = px + dx, yy = py + dy;
+                            if ((dx | dy) == 0 || xx < 0 || yy < 0 || xx >= W || yy >= H) continue;
+                            const int q = yy * W + xx;
+                            u64 c0, c1; PxLo lo;
+                            px_load(S.px, q, c0, c1, lo);
+                            const float a_q = lo.ang;
+                            if (a_q < 0.f) continue;
+                            const u64 pq = make_prio((int)lo.binrev, q);
+                            if (pq >= prio) continue;
+                            if (((prv ? c1 : c0) >> 40) == 0) continue;                       // finalised long ago: cannot absorb us now
+                            float d = fabsf(a_s - a_q); if (d > 180.f) d = 360.f - d;
+                            if (d <= 20.f) { alive = false; deferred = true; break; }
+                        }
+                }
+                if (!alive) { if (deferred || __ldcg(&G.cnt[prv][i]) != 0) any_change = true; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; }
             }
             unsigned m = __ballot_sync(0xffffffffu, alive);
             while (m) {
@@ -622,7 +608,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) k_lsd_phase(const GrowStateW
                 for (int k = 0; k < c; k += kChunk - 1) {
                     const unsigned v = __ldcg(&pool[(size_t)chunk * kChunk + lane]);
                     if (lane < kChunk - 1 && k + lane < c) {
-                        G.A.claim[0][v] = prio; G.A.claim[1][v] = prio;
+                        S.px[v].claim[0] = prio; S.px[v].claim[1] = prio;
                         if (accept) G.final_pool[off + k + lane] = v;
                     }
                     chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
@@ -649,7 +635,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) k_lsd_phase(const GrowStateW
         const bool changed = __ldcg(&G.changed[round]) != 0;
         if (!changed || round + 2 >= G.max_rounds || err != 0) st->mode = 1; else st->round = round + 1;
     } else {
-        st->mode = 0; st->round = round + 1; st->wave = wv + 1;
+        st->mode = 0; st->round = round + 1; st->wave = wv + 1; st->wave_first_round = round + 1;
         *G.A.pool_ctr[0] = 0;                                       // one bump pool per wave (lists may be carried over rounds)
         if (wv + 1 >= G.plan->n_waves || err != 0) { st->done = 1; G.status[1] = (int)(round + 1); G.status[2] = G.plan->n_waves; G.status[3] = 1; }
     }
@@ -923,6 +909,7 @@ struct LineImpl {
     DevBuf<float2_t> tab_seed, tab_acc, cs;
     DevBuf<unsigned> work_ctr, blk_chunk0, blk_chunk1;
     DevBuf<PhaseState> phase;
+    DevBuf<PxRec> px;
     int phase_batch = 40;
     DevBuf<int> blk_cnt0, blk_cnt1;
     bool scalar_grow = false, trace = false;
@@ -1019,9 +1006,7 @@ LineImpl* line_create(const olf_line_params* p, int device) {
     if (const char* e = getenv("OLF_LSD_FIRST_WAVE")) h->first_wave = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_WAVE_GROWTH")) h->wave_growth = std::max(2, atoi(e));
     h->trace = getenv("OLF_LSD_TRACE") != nullptr;                // per-round trace of the grow kernel (tools/lsd_trace.py)
-    h->scalar_grow = getenv("OLF_LSD_SCALAR") != nullptr;         // A/B switch: thread-per-seed reference kernel
-    if (h->scalar_grow) ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_grow, 256, 0) == cudaSuccess && per_sm > 0;
-    else ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_phase, GW_WARPS * 32, 0) == cudaSuccess && per_sm > 0;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_phase, GW_WARPS * 32, 0) == cudaSuccess && per_sm > 0;
     ok = ok && h->phase.ensure(1) == OLF_OK;
     if (const char* e = getenv("OLF_LSD_PHASE_BATCH")) h->phase_batch = std::max(4, atoi(e));
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
@@ -1047,7 +1032,7 @@ void line_destroy(LineImpl* h) {
     h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool0.release(); h->pool1.release(); h->ctrs.release();
     h->changed.release(); h->final_pool.release(); h->regang.release(); h->plan.release(); h->regs.release();
     h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->work_ctr.release();
-    h->blk_chunk0.release(); h->blk_chunk1.release(); h->blk_cnt0.release(); h->blk_cnt1.release(); h->phase.release(); h->rect_host.release(); h->dir_host.release(); h->seg_host.release();
+    h->blk_chunk0.release(); h->blk_chunk1.release(); h->blk_cnt0.release(); h->blk_cnt1.release(); h->phase.release(); h->px.release(); h->rect_host.release(); h->dir_host.release(); h->seg_host.release();
     h->status_host.release(); h->nreg_host.release(); h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
 }
@@ -1075,13 +1060,13 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
     OLF_CUDA(cudaMemcpy(h->coef.p, cx.data(), cx.size() * sizeof(ExCoef), cudaMemcpyHostToDevice));
     h->pool_chunks = (unsigned)std::max<size_t>(S / 2, 1u << 16);       // 16 px of list space per image pixel per round
     h->reg_cap = (unsigned)(S / std::max(h->min_reg_size, 1) + 16);
-    if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || (rc = h->claim0.ensure(S)) || (rc = h->claim1.ensure(S)) ||
+    if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || 
         (rc = h->seed_prio.ensure(S)) || (rc = h->seed_pix.ensure(S)) || (rc = h->cnt0.ensure(S)) || (rc = h->cnt1.ensure(S)) ||
         (rc = h->head0.ensure(S)) || (rc = h->head1.ensure(S)) || (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) ||
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
         (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->changed.ensure(h->max_rounds)) || (rc = h->plan.ensure(1)) ||
         (rc = h->pool0.ensure((size_t)h->pool_chunks * kChunk)) || (rc = h->pool1.ensure((size_t)h->pool_chunks * kChunk)) ||
-        (rc = h->dbg.ensure((size_t)h->max_rounds * TRACE_REC)) || (rc = h->cs.ensure(S)) || (rc = h->work_ctr.ensure(2 * h->max_rounds + 64)) ||
+        (rc = h->dbg.ensure((size_t)h->max_rounds * TRACE_REC)) || (rc = h->px.ensure(S)) || (rc = h->work_ctr.ensure(2 * h->max_rounds + 64)) ||
         (rc = h->blk_chunk0.ensure(S)) || (rc = h->blk_chunk1.ensure(S)) || (rc = h->blk_cnt0.ensure(S)) || (rc = h->blk_cnt1.ensure(S)) ||
         (rc = h->regs.ensure(h->reg_cap)) || (rc = h->rect_host.ensure(h->reg_cap)) || (rc = h->dir_host.ensure(h->reg_cap)) ||
         (rc = h->seg_host.ensure(h->reg_cap)) || (rc = h->status_host.ensure(4)) || (rc = h->nreg_host.ensure(1))) return rc;
@@ -1131,22 +1116,22 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     OLF_CUDA(cudaMemsetAsync(h->work_ctr.p, 0, (2 * h->max_rounds + 64) * sizeof(unsigned), s));
     {
         dim3 g((W + 31) / 32, (H + 7) / 8);
-        k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->tab_acc.p, h->cs.p, h->claim0.p, h->claim1.p, h->n2max.p);
+        k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->tab_acc.p, h->px.p, h->n2max.p);
     }
     const int nb = h->P.lsd_n_bins;
     k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
     k_lsd_plan<<<1, 1024, 0, s>>>(h->hist.p, nb, h->first_wave, h->wave_growth, h->bin_start.p, h->cursor.p, h->plan.p);
-    k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p);
+    k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p, h->px.p);
     GrowState G;
     G.A.W = W; G.A.H = H; G.A.ang = h->ang.p; G.A.dabc = h->dabc.p; G.A.tab_seed = h->tab_seed.p; G.A.tab_acc = h->tab_acc.p;
-    G.A.claim[0] = h->claim0.p; G.A.claim[1] = h->claim1.p; G.A.pool[0] = h->pool0.p; G.A.pool[1] = h->pool1.p;
+    G.A.claim[0] = nullptr; G.A.claim[1] = nullptr; G.A.pool[0] = h->pool0.p; G.A.pool[1] = h->pool1.p;
     G.A.pool_ctr[0] = h->ctrs.p; G.A.pool_ctr[1] = h->ctrs.p + 1; G.A.pool_chunks = h->pool_chunks; G.A.prec = h->prec;
     G.seed_pix = h->seed_pix.p; G.seed_prio = h->seed_prio.p;
     G.head[0] = h->head0.p; G.head[1] = h->head1.p; G.cnt[0] = h->cnt0.p; G.cnt[1] = h->cnt1.p; G.regang = h->regang.p;
     G.plan = h->plan.p; G.changed = h->changed.p; G.max_rounds = h->max_rounds; G.min_reg_size = h->min_reg_size;
     G.final_pool = h->final_pool.p; G.final_ctr = h->ctrs.p + 2; G.regs = h->regs.p; G.nreg = h->ctrs.p + 3; G.reg_cap = h->reg_cap;
     G.status = h->status.p;
-    GrowStateW GW; GW.G = G; GW.cs = h->cs.p; GW.work_ctr = h->work_ctr.p;
+    GrowStateW GW; GW.G = G; GW.px = h->px.p; GW.work_ctr = h->work_ctr.p;
     GW.G.A.pool[1] = GW.G.A.pool[0]; GW.G.A.pool_ctr[1] = GW.G.A.pool_ctr[0];      // warp kernel: one bump pool per wave
     GW.blk_chunk[0] = h->blk_chunk0.p; GW.blk_chunk[1] = h->blk_chunk1.p; GW.blk_cnt[0] = h->blk_cnt0.p; GW.blk_cnt[1] = h->blk_cnt1.p;
     {
@@ -1155,15 +1140,12 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
         GW.c_hi2 = (float)(std::cos(h->prec - margin) * std::cos(h->prec - margin));
         GW.c_lo2 = (float)(std::cos(h->prec + margin) * std::cos(h->prec + margin));
     }
+    GW.defer = getenv("OLF_LSD_NO_DEFER") ? 0 : 1;
     GW.dbg = h->trace ? h->dbg.p : nullptr;
     if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
-    void* args[] = {(void*)&G};
-    void* args_w[] = {(void*)&GW};
     OLF_CUDA(cudaEventRecord(h->ev_grow0, s));
-    if (h->scalar_grow) OLF_CUDA(cudaLaunchCooperativeKernel((const void*)k_lsd_grow, dim3(h->grow_blocks), dim3(256), args, 0, s));
-    else {
-        (void)args_w;
-        PhaseState init; memset(&init, 0, sizeof(init)); init.round = 1;
+    {
+        PhaseState init; memset(&init, 0, sizeof(init)); init.round = 1; init.wave_first_round = 1;
         // seeds of later waves must start with "no previous list"
         OLF_CUDA(cudaMemsetAsync(h->cnt0.p, 0, (size_t)S * sizeof(int), s));
         OLF_CUDA(cudaMemsetAsync(h->cnt1.p, 0, (size_t)S * sizeof(int), s));
@@ -1178,7 +1160,7 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(stream_sync(s));
-    if (!h->scalar_grow) {
+    {
         // the fixed batch of phase launches normally covers all rounds; otherwise keep going (rare)
         for (int guard = 0; guard < 400; ++guard) {
             if (h->status_host.p[3] || h->status_host.p[0]) break;
