@@ -5,6 +5,7 @@
 #include "match.h"
 #include <mutex>
 #include <atomic>
+#include <time.h>
 
 namespace olf {
 static thread_local std::string g_err;
@@ -12,17 +13,26 @@ static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches_total() { return g_launches.load(); }
 cudaError_t stream_sync(cudaStream_t s) {
-    static const bool spin = [] { const char* e = getenv("OLF_SYNC"); return e && std::string(e) == "spin"; }();
-    if (spin) return cudaStreamSynchronize(s);
+    // OLF_SYNC=spin  : cudaStreamSynchronize (lowest latency, one busy host core per waiting thread)
+    // OLF_SYNC=block : blocking-sync event (thread sleeps until the driver's interrupt; wake-up jitter under load)
+    // default        : poll an event, yielding the core between polls (bounded latency, cores stay available to the other rigs)
+    static const int mode = [] { const char* e = getenv("OLF_SYNC"); return !e ? 0 : (std::string(e) == "spin" ? 1 : (std::string(e) == "block" ? 2 : 0)); }();
+    if (mode == 1) return cudaStreamSynchronize(s);
     static thread_local cudaEvent_t ev[16] = {nullptr};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 16) return cudaStreamSynchronize(s);
-    if (!ev[dev]) { e = cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    if (!ev[dev]) { e = cudaEventCreateWithFlags(&ev[dev], (mode == 2 ? cudaEventBlockingSync : 0) | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
     e = cudaEventRecord(ev[dev], s);
     if (e != cudaSuccess) return e;
-    return cudaEventSynchronize(ev[dev]);
+    if (mode == 2) return cudaEventSynchronize(ev[dev]);
+    for (int spins = 0;; ++spins) {
+        e = cudaEventQuery(ev[dev]);
+        if (e != cudaErrorNotReady) return e;
+        if (spins < 64) { for (int k = 0; k < 64; ++k) __builtin_ia32_pause(); }
+        else { struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr); }
+    }
 }
 void set_last_error(const std::string& s) { g_err = s; }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {

@@ -33,7 +33,9 @@ struct DevBuf {
     size_t n = 0;
     int ensure(size_t count) {
         if (count <= n) return OLF_OK;
-        if (p) cudaFree(p);
+        // cudaFree / cudaMalloc synchronise the whole device (they would stall every rig in flight): when an existing
+        // buffer has to grow, grow it geometrically so that steady state never reallocates
+        if (p) { count = count + count / 2 + 4096; cudaFree(p); }
         p = nullptr; n = 0;
         cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
@@ -50,7 +52,7 @@ struct PinBuf {
     size_t n = 0;
     int ensure(size_t count) {
         if (count <= n) return OLF_OK;
-        if (p) cudaFreeHost(p);
+        if (p) { count = count + count / 2 + 4096; cudaFreeHost(p); }
         p = nullptr; d = nullptr; n = 0;
         cudaError_t e = cudaHostAlloc((void**)&p, count * sizeof(T), cudaHostAllocMapped);
         if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);

@@ -54,8 +54,9 @@ struct Planner {
 };
 static int arena_ensure(MatchCtx* c, const Planner& pl) {
     int rc;
-    if ((rc = c->a.dev.ensure(pl.dev + 256))) return rc;
-    if ((rc = c->a.pin.ensure(pl.pin + 256))) return rc;
+    // generous first allocation: the arena sizes follow the per-frame feature counts, which wobble from frame to frame
+    if (c->a.dev.n < pl.dev + 256 && (rc = c->a.dev.ensure(std::max<size_t>(2 * (pl.dev + 256), (size_t)4 << 20)))) return rc;
+    if (c->a.pin.n < pl.pin + 256 && (rc = c->a.pin.ensure(std::max<size_t>(2 * (pl.pin + 256), (size_t)1 << 20)))) return rc;
     return OLF_OK;
 }
 template <typename T> static T* dptr(MatchCtx* c, size_t off) { return (T*)(c->a.dev.p + off); }
