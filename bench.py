@@ -200,7 +200,7 @@ def main():
     api = olf.api(local)
     cam = CAMERAS[WORKLOAD["camera"]]
     # concurrent stereo rigs per GPU: the LSD grow phases are latency-bound, so frames in flight are what fills the GPU
-    P = args.pipelines or max(2, min(5, (os.cpu_count() or 16) // (2 * max(1, world))))   # 5 rigs x 5 streams + tracker stay within 32 work queues
+    P = args.pipelines or max(4, min(16, (os.cpu_count() or 16) // max(1, world)))   # measured optimum: 16 rigs x 2 streams per GPU
     sc, seq, poses = make_sequence(N_DISTINCT)
     # weak scaling: every rank runs the same number of frames of its own slice of the sequence
     shift = rank * 11

@@ -12,27 +12,38 @@ static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches_total() { return g_launches.load(); }
-cudaError_t stream_sync(cudaStream_t s) {
-    // OLF_SYNC=spin  : cudaStreamSynchronize (lowest latency, one busy host core per waiting thread)
+static int sync_mode() {
+    // OLF_SYNC=spin  : busy-wait (lowest latency, one busy host core per waiting thread)
     // OLF_SYNC=block : blocking-sync event (thread sleeps until the driver's interrupt; wake-up jitter under load)
-    // default        : poll an event, yielding the core between polls (bounded latency, cores stay available to the other rigs)
+    // default        : poll the event, yielding the core between polls (bounded latency, cores stay available to other rigs)
     static const int mode = [] { const char* e = getenv("OLF_SYNC"); return !e ? 0 : (std::string(e) == "spin" ? 1 : (std::string(e) == "block" ? 2 : 0)); }();
-    if (mode == 1) return cudaStreamSynchronize(s);
+    return mode;
+}
+cudaError_t stream_record(cudaStream_t s, cudaEvent_t* out) {
     static thread_local cudaEvent_t ev[16] = {nullptr};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 16) return cudaStreamSynchronize(s);
-    if (!ev[dev]) { e = cudaEventCreateWithFlags(&ev[dev], (mode == 2 ? cudaEventBlockingSync : 0) | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
-    e = cudaEventRecord(ev[dev], s);
-    if (e != cudaSuccess) return e;
-    if (mode == 2) return cudaEventSynchronize(ev[dev]);
+    if (dev < 0 || dev >= 16) return cudaErrorInvalidDevice;
+    if (!ev[dev]) { e = cudaEventCreateWithFlags(&ev[dev], (sync_mode() == 2 ? cudaEventBlockingSync : 0) | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    *out = ev[dev];
+    return cudaEventRecord(ev[dev], s);
+}
+cudaError_t event_wait(cudaEvent_t ev) {
+    const int mode = sync_mode();
+    if (mode == 2) return cudaEventSynchronize(ev);
     for (int spins = 0;; ++spins) {
-        e = cudaEventQuery(ev[dev]);
+        const cudaError_t e = cudaEventQuery(ev);
         if (e != cudaErrorNotReady) return e;
-        if (spins < 64) { for (int k = 0; k < 64; ++k) __builtin_ia32_pause(); }
+        if (mode == 1 || spins < 64) { for (int k = 0; k < 64; ++k) __builtin_ia32_pause(); }
         else { struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr); }
     }
+}
+cudaError_t stream_sync(cudaStream_t s) {
+    cudaEvent_t ev;
+    const cudaError_t e = stream_record(s, &ev);
+    if (e != cudaSuccess) return e;
+    return event_wait(ev);
 }
 void set_last_error(const std::string& s) { g_err = s; }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {

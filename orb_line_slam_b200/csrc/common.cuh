@@ -14,7 +14,10 @@ void set_last_error(const std::string& s);
 void count_launches(int n);
 // Wait for a stream without burning a host core: blocking-sync event (thread sleeps) unless OLF_SYNC=spin.
 // Many pipelines x 4 extraction threads wait concurrently; spinning would oversubscribe the host CPUs.
-cudaError_t stream_sync(cudaStream_t s);            // bookkeeping for bench.py's gpu_launches (kernels launched by this library)
+cudaError_t stream_sync(cudaStream_t s);
+// the two halves of stream_sync: mark "everything enqueued so far" / wait for that mark
+cudaError_t stream_record(cudaStream_t s, cudaEvent_t* out);
+cudaError_t event_wait(cudaEvent_t ev);            // bookkeeping for bench.py's gpu_launches (kernels launched by this library)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define OLF_CUDA(call)                                                         \

@@ -70,9 +70,13 @@ FrontendImpl* frontend_create(const olf_frontend_params* p, int device) {
     FrontendImpl* h = new FrontendImpl();
     h->P = *p; h->device = device;
     frame_layout(p->cap_points, p->cap_lines, &h->off);
+    const bool share = getenv("OLF_RIG_STREAMS") == nullptr || atoi(getenv("OLF_RIG_STREAMS")) <= 2;
     for (int e = 0; e < 2; ++e) {
-        h->orb[e] = orb_create(p->nfeatures, p->scale_factor, p->nlevels, p->ini_th_fast, p->min_th_fast, device);
         if (p->has_lines) h->line[e] = line_create(&p->line, device);
+        // each eye's ORB work rides on that eye's line stream (2 streams per rig); without lines the two eyes share one
+        cudaStream_t ext = (p->has_lines && share) ? line_stream(h->line[e]) : nullptr;
+        if (!(p->has_lines && !h->line[e]))
+            h->orb[e] = orb_create(p->nfeatures, p->scale_factor, p->nlevels, p->ini_th_fast, p->min_th_fast, device, ext);
         if (!h->orb[e] || (p->has_lines && !h->line[e])) {
             for (int k = 0; k < 2; ++k) { orb_destroy(h->orb[k]); line_destroy(h->line[k]); }
             delete h; return nullptr;
@@ -84,7 +88,8 @@ FrontendImpl* frontend_create(const olf_frontend_params* p, int device) {
 void frontend_destroy(FrontendImpl* h) {
     if (!h) return;
     for (int i = 0; i < 4; ++i) delete h->workers[i];
-    for (int e = 0; e < 2; ++e) { orb_destroy(h->orb[e]); line_destroy(h->line[e]); }
+    for (int e = 0; e < 2; ++e) orb_destroy(h->orb[e]);    // before the line extractors whose streams they may borrow
+    for (int e = 0; e < 2; ++e) line_destroy(h->line[e]);
     delete h;
 }
 
@@ -101,15 +106,24 @@ int frontend_process(FrontendImpl* h, const uint8_t* img_l, const uint8_t* img_r
     uint8_t* ldesc[2] = {base + o.ldesc_l, base + o.ldesc_r};
     const uint8_t* img[2] = {img_l, img_r};
     int n[2] = {0, 0}, m[2] = {0, 0};
-    // ExtractORB(0|1), ExtractLine(0|1) on four threads (src/Frame.cc:164-171)
+    // ExtractORB(0|1), ExtractLine(0|1) on four threads (src/Frame.cc:164-171).  Per eye the two extractors share a stream:
+    // the line thread enqueues its long LSD chain only after the ORB thread has enqueued (and marked) its pre-quadtree
+    // kernels, so the ORB host work (quadtree) overlaps the LSD phases instead of queueing behind them.
+    struct Gate { std::mutex m; std::condition_variable cv; bool open = false; } gate[2];
+    std::function<void()> open_gate[2];
     for (int e = 0; e < 2; ++e) {
+        Gate* g = &gate[e];
+        open_gate[e] = [g]() { { std::lock_guard<std::mutex> l(g->m); g->open = true; } g->cv.notify_all(); };
+        const std::function<void()>* hook = &open_gate[e];
         h->workers[e]->submit([=, &n, &h]() {
-            const int rc = orb_extract(h->orb[e], img[e], w, hgt, stride, on_device != 0, kps[e], desc[e], h->P.cap_points, &n[e]);
+            const int rc = orb_extract(h->orb[e], img[e], w, hgt, stride, on_device != 0, kps[e], desc[e], h->P.cap_points, &n[e], hook);
+            (*hook)();                                     // idempotent: covers the early-return paths
             if (rc) h->err[e] = olf_last_error();
             return rc;
         });
         if (h->P.has_lines)
             h->workers[2 + e]->submit([=, &m, &h]() {
+                { std::unique_lock<std::mutex> l(g->m); g->cv.wait(l, [g] { return g->open; }); }
                 const int rc = line_extract(h->line[e], img[e], w, hgt, stride, on_device != 0, kls[e], ldesc[e], h->P.cap_lines, &m[e]);
                 if (rc) h->err[2 + e] = olf_last_error();
                 return rc;

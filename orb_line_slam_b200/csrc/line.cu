@@ -170,7 +170,7 @@ struct GrowState {
 //     moves to and from global memory as one coalesced 128-byte transaction;
 //   * claims are atomicMin by lane 0; their return values are awaited once per step, which makes the warp's own claims
 //     visible to the next step's (L2) loads -- no duplicate can enter a list.
-#define GW_WARPS 8
+#define GW_WARPS 4
 struct GrowStateW {
     GrowState G;
     PxRec* px;                  // packed per-pixel record (claims + angle + (cos, sin) + bin)
@@ -516,7 +516,7 @@ __device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int s
 // several frames in flight interleave freely with every other kernel on the device.
 struct PhaseState { int wave; unsigned round; int mode; int done; unsigned pass; unsigned ticket; int launches; unsigned wave_first_round; };
 
-__global__ void __launch_bounds__(GW_WARPS * 32, 3) k_lsd_phase(const GrowStateW S, PhaseState* __restrict__ st) {
+__global__ void __launch_bounds__(GW_WARPS * 32, 6) k_lsd_phase(const GrowStateW S, PhaseState* __restrict__ st) {
     __shared__ unsigned hash_sets[GW_WARPS][GW_HASH];
     __shared__ bool s_last;
     const GrowState& G = S.G;
@@ -1012,9 +1012,9 @@ LineImpl* line_create(const olf_line_params* p, int device) {
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
     {   // blocks per SM of the persistent grow kernel: the kernel is latency-bound (one warp walks the longest region), so a
         // small grid loses little and lets the left/right eyes and several frames in flight share the GPU
-        int bps = 2;
-        if (const char* e = getenv("OLF_LSD_BPS")) bps = std::max(1, atoi(e));
-        h->grow_blocks = sms * std::min(per_sm, bps);
+        // half a block (4 warps) per SM: measured optimum with 16 rigs in flight (larger grids only fight for block slots)
+        h->grow_blocks = std::max(1, sms / 2);
+        if (const char* e = getenv("OLF_LSD_BPS")) h->grow_blocks = sms * std::max(1, std::min(per_sm, atoi(e)));
         if (const char* e = getenv("OLF_LSD_BLOCKS")) h->grow_blocks = std::max(1, std::min(atoi(e), sms * per_sm));
     }
     return h;
@@ -1310,6 +1310,7 @@ int line_extract(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bo
 
 // [0] rounds, [1] waves, [2] accepted regions, [3] k_lsd_grow device time in microseconds (CUDA events on its stream)
 void line_last_stats(const LineImpl* h, int* out8) { for (int i = 0; i < 8; ++i) out8[i] = h->last_stats[i]; }
+cudaStream_t line_stream(const LineImpl* h) { return h ? h->stream : nullptr; }
 int line_trace(LineImpl* h, int* out, int max_rounds) {
     if (!h || !h->trace || !h->dbg.p) return OLF_ERR_ARG;
     const int n = std::min<int>(max_rounds, (int)h->max_rounds);

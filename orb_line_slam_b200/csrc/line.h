@@ -1,6 +1,7 @@
 // internal C++ interface of the line half (see line.cu)
 #pragma once
 #include <cstdint>
+#include <cuda_runtime.h>
 #include "../../include/olf_abi.h"
 namespace olf {
 struct LineImpl;
@@ -10,5 +11,6 @@ int line_lsd_detect(LineImpl* h, const uint8_t* img, int w, int hgt, int stride,
 int line_lbd_compute(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, const olf_keyline* kls, int n, uint8_t* desc);
 int line_extract(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, olf_keyline* kls, uint8_t* desc, int cap, int* n);
 int line_trace(LineImpl* h, int* out, int max_rounds);
+cudaStream_t line_stream(const LineImpl* h);
 void line_last_stats(const LineImpl* h, int* out8);   // [0] rounds, [1] waves, [2] accepted regions
 }

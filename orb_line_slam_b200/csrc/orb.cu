@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <list>
+#include <functional>
 
 namespace olf {
 
@@ -273,6 +274,7 @@ struct OrbImpl {
     std::vector<int> feats_per_level;
     int umax[16];
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;
     // size-dependent state
     int img_w = 0, img_h = 0;
     LevelTable T;
@@ -469,7 +471,7 @@ void quadtree(const QCand* c, int nc, int minX, int maxX, int minY, int maxY, in
 }
 }  // namespace
 
-OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device) {
+OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device, cudaStream_t ext_stream) {
     if (nlevels < 1 || nlevels > OLF_MAX_LEVELS || nfeatures < 0 || scale_factor <= 1.0f || min_th < 1 || ini_th < min_th) {
         set_last_error("olf_orb_create: bad arguments"); return nullptr;
     }
@@ -496,7 +498,8 @@ OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
     int v, v0, vmax = (int)floorf(HP * sqrtf(2.f) / 2 + 1), vmin = (int)ceilf(HP * sqrtf(2.f) / 2);
     for (v = 0; v <= vmax; ++v) h->umax[v] = (int)lrint(sqrt((double)HP * HP - v * v));
     for (v = HP, v0 = 0; v >= vmin; --v) { while (h->umax[v0] == h->umax[v0 + 1]) ++v0; h->umax[v] = v0; ++v0; }
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (ext_stream) { h->stream = ext_stream; h->owns_stream = false; }
+    if ((!ext_stream && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) ||
         cudaMemcpyToSymbol(c_umax, h->umax, sizeof(h->umax)) != cudaSuccess ||
         cudaMemcpyToSymbol(c_pattern, OLF_BRIEF_PATTERN, 1024) != cudaSuccess) {
         set_last_error(std::string("olf_orb_create: ") + cudaGetErrorString(cudaGetLastError()));
@@ -508,7 +511,7 @@ OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
 void orb_destroy(OrbImpl* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->stream && h->owns_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     h->pyr.release(); h->score.release(); h->blur.release(); h->coef.release(); h->cell_counts.release(); h->cell_thr.release();
     h->cell_off.release(); h->total.release(); h->ticket.release(); h->cand.release(); h->cand_host.release(); h->angle_host.release();
     h->total_host.release(); h->kept.release(); h->kept_host.release(); h->desc.release(); h->desc_host.release(); h->img_stage.release();
@@ -551,15 +554,21 @@ static int orb_enqueue_phase1(OrbImpl* h, const uint8_t* img, int w, int hgt, in
 }
 
 int orb_extract(OrbImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device,
-                olf_keypoint* kps, uint8_t* desc, int cap, int* n) {
+                olf_keypoint* kps, uint8_t* desc, int cap, int* n, const std::function<void()>* on_phase1_enqueued) {
     if (!h || !n) return OLF_ERR_ARG;
     *n = 0;
     if (!img || w <= 0 || hgt <= 0) return OLF_OK;           // _image.empty(): silent return (:1048)
     if (stride < w || !kps || !desc) { set_last_error("olf_orb_extract: bad arguments"); return OLF_ERR_ARG; }
     OLF_CUDA(cudaSetDevice(h->device));
     int rc = orb_enqueue_phase1(h, img, w, hgt, stride, on_device);
-    if (rc) return rc;
-    OLF_CUDA(stream_sync(h->stream));
+    if (rc) { if (on_phase1_enqueued) (*on_phase1_enqueued)(); return rc; }
+    {   // wait for phase 1 only: whatever another thread enqueues on a shared stream after this mark is not waited for
+        cudaEvent_t ev;
+        const cudaError_t e = stream_record(h->stream, &ev);
+        if (on_phase1_enqueued) (*on_phase1_enqueued)();
+        OLF_CUDA(e);
+        OLF_CUDA(event_wait(ev));
+    }
     const int ncand = *h->total_host.p;
     if (ncand > h->cand_cap) { set_last_error("FAST candidate buffer overflow"); return OLF_ERR_CAPACITY; }
     h->last_ncand = ncand;
