@@ -5,11 +5,12 @@ package is the thin host mirror used by the tests and the benchmark; it never fa
 loading fails loudly when the library has not been built, and every call fails when no CUDA device is present.
 """
 from __future__ import annotations
-import ctypes, functools, pathlib
+import ctypes, functools, os, pathlib
 from .abi import FrontEndApi, LineParams, LineMatchParams, Camera, SbpLastArgs, SbpMapArgs, KEYPOINT, KEYLINE  # noqa: F401
 
 _PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libolf.so"
+# OLF_LIB selects another build of the same library (e.g. the -DOLF_LSD_PROFILE build used by tools/lsd_trace.py)
+LIB_PATH = pathlib.Path(os.environ["OLF_LIB"]).resolve() if os.environ.get("OLF_LIB") else _PKG / "libolf.so"
 
 
 @functools.lru_cache(maxsize=1)

@@ -37,20 +37,6 @@ __global__ void k_resize_exact(const uint8_t* __restrict__ src, int sw, int sh, 
     dst[(size_t)y * dpitch + x] = (uint8_t)((acc + (1u << 15)) >> 16);
 }
 
-// Everything the grow kernel needs to know about a pixel sits in ONE 32-byte sector: both claim words, the level-line
-// angle, the (cos, sin) the reference accumulates and the priority bin.  A neighbour test costs one sector instead of four
-// scattered ones, which is what keeps many frames in flight from thrashing L2 / HBM with random 32-B accesses.
-struct __align__(32) PxRec { u64 claim[2]; float ang; float cx; float cy; unsigned binrev; };
-struct __align__(16) PxLo { float ang; float cx; float cy; unsigned binrev; };
-__device__ __forceinline__ u64 px_claim(const PxRec* px, int q, int parity) { return __ldcg(&px[q].claim[parity]); }
-__device__ __forceinline__ void px_load(const PxRec* px, int q, u64& c0, u64& c1, PxLo& lo) {
-    const ulonglong2 c = __ldcg(reinterpret_cast<const ulonglong2*>(&px[q]));
-    const float4 f = __ldcg(reinterpret_cast<const float4*>(&px[q]) + 1);
-    c0 = c.x; c1 = c.y; lo.ang = f.x; lo.cx = f.y; lo.cy = f.z; lo.binrev = __float_as_uint(f.w);
-}
-#define GW_HASH_BITS 8
-#define GW_HASH (1 << GW_HASH_BITS)
-
 // ---- ll_angle: gradient, level-line angle, max gradient ---------------------------------
 // n2_thresh = smallest gx^2+gy^2 whose norm sqrt(n2/4.0) exceeds rho (computed exactly on the host).
 __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, int W, int H, int pitch, int n2_thresh,
@@ -75,7 +61,8 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
         float2_t c; c.x = 0.f; c.y = 0.f;
         if (a >= 0.f) c = tab_acc[tab_index(d)];
         ang[q] = a; dabc[q] = d;
-        PxRec r; r.claim[0] = kClaimNone; r.claim[1] = kClaimNone; r.ang = a; r.cx = c.x; r.cy = c.y; r.binrev = 0;
+        // NOTDEF pixels are never accepted by isAligned(): they are born with a final claim (stamp 0), so the grow pass needs no angle test
+        PxRec r; r.claim[0] = a >= 0.f ? kClaimNone : 0ull; r.claim[1] = r.claim[0]; r.ang = a; r.cx = c.x; r.cy = c.y; r.binrev = 0;
         px[q] = r;
     }
 #pragma unroll
@@ -144,482 +131,371 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const float* __restrict__ a
         }
 }
 
-// ---- region growing state shared by the phase kernel (semantics: grow_seed() in lsd_core.h) ------------------
-struct LsdRegion { u64 prio; unsigned off; int count; double reg_angle; };
-struct GrowState {
-    GrowArgs A;
-    const int* seed_pix; const u64* seed_prio;
-    unsigned* head[2]; int* cnt[2]; double* regang;
+// ---- region growing: three passes per round, one thread per seed (semantics: lsd_core.h) ------------------------------
+// The wave / round state machine lives on the device: the host enqueues a fixed batch of (scan, verify, grow) triples,
+// the last block of every grow launch advances {wave, round, mode}, launches after `done` return at once.  Ordinary
+// (non-cooperative) launches: no co-residency requirement, so the passes of the left/right eyes and of several frames in
+// flight interleave freely with every other kernel on the device.
+#define TRACE_REC 8
+struct PhaseState {
+    int wave; unsigned round; int mode; int done;           // mode 0: round passes, 1: finalise the converged wave
+    int launches; unsigned wave_first_round;
+    unsigned wl0_cnt, wl1_cnt, wl2_cnt, wl2_pop, changed, ticket;
+};
+struct GrowDev {
+    GrowCtx C;
     const LsdPlan* plan;
-    unsigned* changed;          // [max_rounds] zero-initialised
+    int* wl0; int* wl1; int* wl2;   // candidates of the wave (not finalised at its start) / alive seeds of the round / seeds that must (re)grow
+    FinalOut F;
+    int* status;                 // [0] error flag, [1] rounds used, [2] waves, [3] done
     unsigned max_rounds;
-    int min_reg_size;
-    unsigned* final_pool; unsigned* final_ctr;
-    LsdRegion* regs; unsigned* nreg; unsigned reg_cap;
-    int* status;                // [0] error flag, [1] rounds used, [2] waves
+    int defer;                   // first round of a wave: seeds with a live higher-priority aligned neighbour wait
+    int* dbg;                    // optional per-round trace (OLF_LSD_TRACE)
 };
-
-// ---- region growing, warp-cooperative: one WARP per seed per round ----------------------------------------------
-// Same operator as grow_seed() in lsd_core.h (which stays the executable specification, emulated on the host by
-// tests/emul), restructured so that nothing on the sequential critical path of a region is a dependent global load:
-//   * up to 3 queue entries x 9 neighbours are examined per step; each of 27 lanes fetches its neighbour's angle, both
-//     claim words and (cos, sin) in parallel (one L2 latency per step instead of ~30);
-//   * the order-dependent accept decisions (running region angle) are then replayed in the reference's scan order on
-//     warp-uniform registers, visiting only lanes whose prefetched data make them potential accepts;
-//   * pixel lists live in 31-entry chunks: the chunk being written / read / compared sits in one register per lane and
-//     moves to and from global memory as one coalesced 128-byte transaction;
-//   * claims are atomicMin by lane 0; their return values are awaited once per step, which makes the warp's own claims
-//     visible to the next step's (L2) loads -- no duplicate can enter a list.
-#define GW_WARPS 4
-struct GrowStateW {
-    GrowState G;
-    PxRec* px;                  // packed per-pixel record (claims + angle + (cos, sin) + bin)
-    unsigned* work_ctr;         // [2*max_rounds + 64] zero-initialised work counters (one per round / finalise pass)
-    // per seed and round parity: the aligned candidates that were refused because a NON-final higher-priority claim held
-    // them (one chunk at most; count 255 = too many, always re-grow).  Together with the pixel list they are the complete
-    // set of external facts a growth depended on, which is what lets an unchanged region be verified instead of re-grown.
-    unsigned* blk_chunk[2]; int* blk_cnt[2];
-    int fast_align; float c_hi2, c_lo2;   // lazy alignment test: cos^2(prec -/+ 0.1 deg)
-    int defer;                            // first round of a wave: seeds with a live higher-priority aligned neighbour wait
-    int* dbg;                   // optional per-round trace (see OLF_LSD_TRACE)
-};
-
-__device__ __forceinline__ bool blocked_vals(u64 e_prev, u64 e_cur, u64 sf_prev, u64 sf_cur, u64 prio) {
-    u64 sf = e_prev >> 40;
-    if (sf == 0) return true;
-    if (sf == sf_prev && (e_prev & kPrioMask) < prio) return true;
-    sf = e_cur >> 40;
-    if (sf == 0) return true;
-    if (sf == sf_cur && (e_cur & kPrioMask) <= prio) return true;
-    return false;
-}
 __device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
     const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
     return ((u64)hi << 32) | lo;
 }
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __longlong_as_double((long long)shfl_u64((u64)__double_as_longlong(v), src)); }
-
-// returns true if the seed's outcome differs from the previous round
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define TRACE_REC 8
-__device__ bool grow_seed_warp(const GrowStateW& S, unsigned round, int i, int seed, u64 prio, int lane, volatile unsigned* hs) {
-    const GrowState& G = S.G;
-    const GrowArgs& A = G.A;
-    const int cur = round & 1, prv = (round - 1) & 1;
-    const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
-    const u64 mine = (sf_cur << 40) | prio;
-    PxRec* px = S.px;
-    unsigned* pool = A.pool[cur];
-    const unsigned* ppool = A.pool[prv];
-    const unsigned prev_head = __ldcg(&G.head[prv][i]);
-    const int prev_cnt = __ldcg(&G.cnt[prv][i]);
-    // claim the seed pixel (authoritative check through the atomic's return value)
-    int dead = 0;
-    unsigned first_chunk = 0;
-    if (lane == 0) {
-        const u64 ep = px_claim(px, seed, prv);
-        u64 sf = ep >> 40;
-        dead = (sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio);
-        if (!dead) {
-            const u64 old = atomicMin(&px[seed].claim[cur], mine);
-            sf = old >> 40;
-            dead = (sf == 0) || (sf == sf_cur && (old & kPrioMask) < prio);
-        }
-    }
-    dead = __shfl_sync(0xffffffffu, dead, 0);
-    if (dead) {
-        if (lane == 0) { G.cnt[cur][i] = 0; G.head[cur][i] = kNull; }
-        return prev_cnt != 0;
-    }
-    // ---- verify instead of re-grow: last round's run is still exact iff every pixel it accepted is still free of
-    // higher-priority claims and every aligned candidate it was refused (by a non-final claim) is still held.
-    if (prev_cnt > 0) {
-        const int bc = __ldcg(&S.blk_cnt[prv][i]);
-        bool ok = bc != 255;
-        if (ok) {
-            unsigned chunk = prev_head;
-            for (int k = 0; k < prev_cnt && ok; k += kChunk - 1) {
-                const unsigned v = __ldcg(&ppool[(size_t)chunk * kChunk + lane]);
-                bool bad = false;
-                if (lane < kChunk - 1 && k + lane < prev_cnt) {
-                    const u64 ep = px_claim(px, (int)v, prv);
-                    bad = ((ep >> 40) == sf_prev) && ((ep & kPrioMask) < prio);
-                }
-                ok = !__any_sync(0xffffffffu, bad);
-                chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
-            }
-        }
-        if (ok && bc > 0) {
-            const unsigned v = __ldcg(&ppool[(size_t)__ldcg(&S.blk_chunk[prv][i]) * kChunk + lane]);
-            bool bad = false;
-            if (lane < bc) {
-                const u64 ep = px_claim(px, (int)v, prv);
-                const u64 sf = ep >> 40;
-                bad = !((sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio));      // no longer held -> must re-grow
-            }
-            ok = !__any_sync(0xffffffffu, bad);
-        }
-        if (ok) {                                                   // carry the region over: re-stamp its claims for this round
-            unsigned chunk = prev_head;
-            for (int k = 0; k < prev_cnt; k += kChunk - 1) {
-                const unsigned v = __ldcg(&ppool[(size_t)chunk * kChunk + lane]);
-                if (lane < kChunk - 1 && k + lane < prev_cnt && v != (unsigned)seed) atomicMin(&px[v].claim[cur], mine);
-                chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
-            }
-            if (S.dbg && lane == 0) atomicAdd(&S.dbg[round * TRACE_REC + 4], 1);
-            if (lane == 0) {
-                G.head[cur][i] = prev_head; G.cnt[cur][i] = prev_cnt;
-                S.blk_chunk[cur][i] = __ldcg(&S.blk_chunk[prv][i]); S.blk_cnt[cur][i] = bc;
-            }
-            return false;
-        }
-    }
-    if (lane == 0) first_chunk = atomicAdd(A.pool_ctr[cur], 1u);
-    first_chunk = __shfl_sync(0xffffffffu, first_chunk, 0);
-    if (first_chunk >= A.pool_chunks) { if (lane == 0) { G.status[0] = OLF_ERR_CAPACITY; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; } return true; }
-    // writer / reader / comparer state (warp-uniform scalars + one payload register per lane)
-    const unsigned w_head = first_chunk;
-    unsigned w_chunk = first_chunk; int w_n = 0; unsigned w_val = 0;
-    unsigned r_chunk = first_chunk; int r_n = 0; unsigned r_val = 0;
-    unsigned pv_val = (prev_cnt > 0 && prev_head != kNull) ? __ldcg(&ppool[(size_t)prev_head * kChunk + lane]) : kNull;
-    int pv_n = 0;
-    bool same = prev_cnt > 0;
-    int count = 0;
-    bool overflow = false;
-    unsigned b_chunk = kNull; int b_n = 0;                           // refused-candidate record (lazily allocated chunk)
-    auto record_blocked = [&](unsigned pix) {
-        if (b_n == 255) return;
-        if (b_chunk == kNull) {
-            unsigned nc = 0;
-            if (lane == 0) nc = atomicAdd(A.pool_ctr[cur], 1u);
-            nc = __shfl_sync(0xffffffffu, nc, 0);
-            if (nc >= A.pool_chunks) { overflow = true; return; }
-            b_chunk = nc;
-        }
-        if (b_n >= kChunk - 1) { b_n = 255; return; }
-        if (lane == 0) pool[(size_t)b_chunk * kChunk + b_n] = pix;
-        ++b_n;
-    };
-    auto push = [&](unsigned pix) {
-        if (w_n == kChunk - 1) {                                   // flush the full chunk, chain a new one
-            unsigned nc = 0;
-            if (lane == 0) nc = atomicAdd(A.pool_ctr[cur], 1u);
-            nc = __shfl_sync(0xffffffffu, nc, 0);
-            if (nc >= A.pool_chunks) { overflow = true; return; }
-            const unsigned outv = (lane == kChunk - 1) ? nc : w_val;
-            pool[(size_t)w_chunk * kChunk + lane] = outv;
-            if (r_chunk == w_chunk) r_val = outv;                  // the reader keeps the chunk it is still consuming
-            w_chunk = nc; w_n = 0;
-        }
-        if (lane == w_n) w_val = pix;
-        ++w_n;
-        if (same) {                                                // lock-step comparison with last round's list
-            if (count >= prev_cnt) same = false;
-            else {
-                if (__shfl_sync(0xffffffffu, pv_val, pv_n) != pix) same = false;
-                if (++pv_n == kChunk - 1) {
-                    const unsigned nxt = __shfl_sync(0xffffffffu, pv_val, kChunk - 1);
-                    pv_val = (nxt != kNull) ? __ldcg(&ppool[(size_t)nxt * kChunk + lane]) : kNull;
-                    pv_n = 0;
-                }
-            }
-        }
-        ++count;
-    };
-    push((unsigned)seed);
-    double reg_angle = d_mul((double)__ldg(&A.ang[seed]), kDegToRads);
-    const float2_t t0 = A.tab_seed[tab_index(A.dabc[seed])];
-    float sumdx = t0.x, sumdy = t0.y;
-    float u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
-    bool dirty = false;                                              // reg_angle is stale w.r.t. (sumdx, sumdy)
-    // ---- software-pipelined BFS: while the accept decisions of step k are replayed, the neighbour data of step k+1 are
-    // already in flight.  Claims are fire-and-forget reductions (RED): nothing on the critical path waits for L2.  The warp's
-    // own accepts since the last fence live in a small shared-memory hash set `hs`; loads are issued only after a fence has
-    // made every older own claim visible, so "already mine" is always decidable from (loaded claim word) OR (hash set hit).
-    struct Pf { int q; float aq; u64 ep, ec; float cx, cy; };
-    int n_since_fence = 0;
-    int i_issue = 0;                                                 // queue entries whose neighbour loads have been issued
-    for (int k = lane; k < GW_HASH; k += 32) hs[k] = kNull;
-    __syncwarp();
-    auto hs_insert = [&](unsigned pix) {                             // lane 0 only
-        unsigned slot = (pix * 2654435761u) >> (32 - GW_HASH_BITS);
-        while (hs[slot] != kNull) slot = (slot + 1) & (GW_HASH - 1);
-        hs[slot] = pix;
-    };
-    auto hs_contains = [&](unsigned pix) -> bool {
-        unsigned slot = (pix * 2654435761u) >> (32 - GW_HASH_BITS);
-        for (;;) {
-            const unsigned v = hs[slot];
-            if (v == pix) return true;
-            if (v == kNull) return false;
-            slot = (slot + 1) & (GW_HASH - 1);
-        }
-    };
-    auto issue = [&](int nb) -> Pf {
-        int ent[3] = {-1, -1, -1};
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            if (e < nb) {
-                if (r_n == kChunk - 1) {                           // lazily step to the next chunk (the old one is flushed by now)
-                    r_chunk = __shfl_sync(0xffffffffu, r_val, kChunk - 1); r_n = 0;
-                    if (r_chunk != w_chunk) r_val = __ldcg(&pool[(size_t)r_chunk * kChunk + lane]);
-                }
-                ent[e] = (int)((r_chunk == w_chunk) ? __shfl_sync(0xffffffffu, w_val, r_n) : __shfl_sync(0xffffffffu, r_val, r_n));
-                ++r_n;
-            }
-        }
-        // lane -> (entry, neighbour) in the reference's scan order: yy outer, xx inner
-        const int e = lane / 9, nidx = lane - e * 9;
-        const int p = e == 0 ? ent[0] : (e == 1 ? ent[1] : ent[2]);
-        Pf f; f.q = -1 - lane; f.aq = -1.f; f.ep = kClaimNone; f.ec = kClaimNone; f.cx = 0.f; f.cy = 0.f;
-        if (lane < 27 && e < nb) {
-            const int ey = p / A.W, ex = p - ey * A.W;
-            const int xx = ex + (nidx % 3) - 1, yy = ey + (nidx / 3) - 1;
-            if (xx >= 0 && xx < A.W && yy >= 0 && yy < A.H) {
-                f.q = yy * A.W + xx;
-                u64 c0, c1; PxLo lo;
-                px_load(px, f.q, c0, c1, lo);
-                f.ep = prv ? c1 : c0; f.ec = cur ? c1 : c0;
-                f.aq = lo.ang; f.cx = lo.cx; f.cy = lo.cy;
-            }
-        }
-        i_issue += nb;
-        return f;
-    };
-    Pf cf = issue(1);                                                // step 0: the seed
-    bool have_cur = true;
-#ifdef OLF_LSD_PROFILE
-#define PCLK() clock64()
-#else
-#define PCLK() 0ll
-#endif
-    long long tA = 0, tB0 = 0, tB1 = 0, tC = 0, tE = 0, tS = 0, tL = 0, tP = 0; int n_steps = 0, n_pot = 0, n_pipe = 0, n_accepts = 0;
-    while (have_cur && !overflow) {
-        const long long c0 = PCLK();
-        // [A] issue the next step's loads if the queue already holds its entries (not across a pending fence)
-        const bool need_fence = n_since_fence > GW_HASH / 2 - 32;
-        Pf nf; bool have_next = false;
-        if (count - i_issue > 0 && !need_fence) {
-            nf = issue(min(3, count - i_issue));
-            have_next = true;
-        }
-        const long long c1 = PCLK();
-        // [B] replay the accept decisions of the current step in scan order.  Every lane evaluates isAligned() for its own
-        // candidate against the warp-uniform region state; the lowest aligned lane is the next pixel the reference would take;
-        // after an accept the state changes and the remaining (higher) lanes are re-evaluated.  Candidates that are not aligned
-        // at their turn never come back (lanes below the last decision are dropped), exactly as in the sequential scan.
-        bool pot = false, held = false;
-        if (cf.q >= 0 && cf.aq >= 0.f) {
-            const u64 sp = cf.ep >> 40, sc = cf.ec >> 40;
-            const bool fin = sp == 0 || sc == 0;                                            // finalised region: never comes back
-            const bool own = sc == sf_cur && (cf.ec & kPrioMask) == prio;                   // already in this region
-            held = (sp == sf_prev && (cf.ep & kPrioMask) < prio) || (sc == sf_cur && (cf.ec & kPrioMask) < prio);
-            pot = !fin && !own && !hs_contains((unsigned)cf.q);
-        }
-        const long long c2 = PCLK();
-        n_pot += __popc(__ballot_sync(0xffffffffu, pot)); ++n_steps; n_pipe += have_next;
-        const double a_rad = d_mul((double)cf.aq, kDegToRads);
-        unsigned live = 0xffffffffu;                                                        // lanes not yet passed by the scan
-        bool state_changed = true;
-        unsigned al = 0;
-        for (;;) {
-            const long long e0 = PCLK();
-            if (state_changed) {
-                // isAligned(reg_angle, a) with reg_angle = fastAtan2(sumdy, sumdx) evaluated lazily: the sign
-                // of cos(angular distance) - cos(prec -/+ 0.1 deg) decides all but the candidates within 0.1 deg of the threshold
-                int st = 0;
-                if (pot && ((live >> lane) & 1u)) {
-                    const float dot = f_add(f_mul(sumdx, cf.cx), f_mul(sumdy, cf.cy)), d2 = f_mul(dot, dot);
-                    if (S.fast_align && u2 > 1e-3f && dot > 0.f && d2 >= f_mul(S.c_hi2, u2)) st = 1;
-                    else if (S.fast_align && u2 > 1e-3f && (dot <= 0.f || d2 <= f_mul(S.c_lo2, u2))) st = 0;
-                    else st = 2;
-                }
-                if (__any_sync(0xffffffffu, st == 2)) {
-                    if (dirty) { reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads); dirty = false; }
-                    if (st == 2) {
-                        double n_theta = d_sub(reg_angle, a_rad);
-                        if (n_theta < 0) n_theta = -n_theta;
-                        if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
-                        st = (n_theta <= A.prec) ? 1 : 0;
-                    }
-                }
-                al = __ballot_sync(0xffffffffu, st == 1);
-                state_changed = false;
-            }
-            al &= live;
-            const long long e1 = PCLK(); tE += e1 - e0;
-            if (!al) break;
-            const int c = __ffs(al) - 1;
-            live = (c == 31) ? 0u : (0xffffffffu << (c + 1));                               // the scan has passed lanes <= c
-            const int qc = __shfl_sync(0xffffffffu, cf.q, c);
-            if (__shfl_sync(0xffffffffu, (int)held, c)) { record_blocked((unsigned)qc); if (overflow) break; continue; }   // aligned but held by a higher-priority seed
-            const float cx = __shfl_sync(0xffffffffu, cf.cx, c), cy = __shfl_sync(0xffffffffu, cf.cy, c);
-            if (cf.q == qc) pot = false;                                                    // the same pixel seen from another entry
-            const long long e2 = PCLK(); tS += e2 - e1;
-            if (lane == 0) { atomicMin(&px[qc].claim[cur], mine); hs_insert((unsigned)qc); }   // RED: no return value is consumed
-            ++n_since_fence;
-            const long long e3 = PCLK(); tL += e3 - e2;
-            push((unsigned)qc);
-            const long long e4 = PCLK(); tP += e4 - e3; ++n_accepts;
-            if (overflow) break;
-            sumdx = f_add(sumdx, cx);
-            sumdy = f_add(sumdy, cy);
-            u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
-            dirty = true;
-            state_changed = true;
-        }
-        __syncwarp();                                                             // hash-set inserts visible to all lanes
-        const long long c3 = PCLK();
-        // [C] rotate; if nothing was prefetched, fence when due (every own claim reaches L2, the hash set restarts) and issue now
-        if (have_next) cf = nf;
-        else if (count - i_issue > 0 && !overflow) {
-            if (need_fence) {
-                __threadfence();
-                for (int k = lane; k < GW_HASH; k += 32) hs[k] = kNull;
-                __syncwarp();
-                n_since_fence = 0;
-            }
-            cf = issue(min(3, count - i_issue));
-        }
-        else have_cur = false;
-        const long long c4 = PCLK();
-        tA += c1 - c0; tB0 += c2 - c1; tB1 += c3 - c2; tC += c4 - c3;
-    }
-#ifdef OLF_LSD_PROFILE
-    if (S.dbg && lane == 0 && count >= 900) {
-        int* d = S.dbg + 200 * TRACE_REC;
-        d[0] = count; d[1] = n_steps; d[2] = n_pot; d[3] = n_pipe; d[4] = (int)tA; d[5] = (int)tB0; d[6] = (int)tB1; d[7] = (int)tC;
-        d[8] = n_accepts; d[9] = (int)tE; d[10] = (int)tS; d[11] = (int)tL; d[12] = (int)tP;
-    }
-#endif
-    const unsigned pend = 0;
-    if (dirty) reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads);
-#ifdef OLF_LSD_PROFILE
-    if (S.dbg && lane == 0 && count >= 900) {
-        int* d = S.dbg + 200 * TRACE_REC;
-        d[0] = count; d[1] = n_steps; d[2] = n_pot; d[3] = n_pipe; d[4] = (int)tA; d[5] = (int)tB0; d[6] = (int)tB1; d[7] = (int)tC;
-        d[8] = n_accepts; d[9] = (int)tE; d[10] = (int)tS; d[11] = (int)tL; d[12] = (int)tP;
-    }
-#endif
-    if (overflow) { if (lane == 0) { G.status[0] = OLF_ERR_CAPACITY; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; } return true; }
-    // flush the partial chunk
-    if (lane < w_n || lane == kChunk - 1) pool[(size_t)w_chunk * kChunk + lane] = (lane == kChunk - 1) ? kNull : w_val;
-    if (lane == 0) { G.head[cur][i] = w_head; G.cnt[cur][i] = count; G.regang[i] = reg_angle; S.blk_chunk[cur][i] = b_chunk; S.blk_cnt[cur][i] = b_n; }
-    if (S.dbg && lane == 0) { atomicAdd(&S.dbg[round * TRACE_REC + 5], 1); atomicAdd(&S.dbg[round * TRACE_REC + 6], count); atomicMax(&S.dbg[round * TRACE_REC + 7], count); }
-    return !(same && count == prev_cnt) || (pend == 0xFFFFFFFFu);
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+// warp-aggregated append of the lanes with `take` to a work list
+__device__ __forceinline__ void wl_append(bool take, int value, int* __restrict__ list, unsigned* __restrict__ counter) {
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (!m) return;
+    unsigned base = 0;
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (take) list[base + __popc(m & lanemask_lt())] = value;
 }
 
-// One launch = one phase of the wave/round state machine (ROUND: every live seed of the wave verifies or re-grows;
-// FINALIZE: the converged wave is stamped for good).  The last block to finish advances the state, so a fixed batch of
-// back-to-back launches walks through all phases without any host round trip; launches after `done` return at once.
-// Ordinary (non-cooperative) launches: no co-residency requirement, so the grow phases of the left/right eyes and of
-// several frames in flight interleave freely with every other kernel on the device.
-struct PhaseState { int wave; unsigned round; int mode; int done; unsigned pass; unsigned ticket; int launches; unsigned wave_first_round; };
-
-__global__ void __launch_bounds__(GW_WARPS * 32, 6) k_lsd_phase(const GrowStateW S, PhaseState* __restrict__ st) {
-    __shared__ unsigned hash_sets[GW_WARPS][GW_HASH];
-    __shared__ bool s_last;
-    const GrowState& G = S.G;
-    const int wv = st->wave; const unsigned round = st->round; const int mode = st->mode; const unsigned pass = st->pass;
+// pass 1: every seed of the wave -- dead or alive (+ first-round deferral); alive seeds go to work list 1
+__global__ void __launch_bounds__(256) k_lsd_scan(const GrowDev D, PhaseState* __restrict__ st) {
+    if (st->done || st->mode != 0) return;
+    const int wv = st->wave;
+    if (wv >= D.plan->n_waves) return;
+    const unsigned round = st->round;
     const bool first_round = round == st->wave_first_round;
+    const int lo = D.plan->wave_start[wv], hi = D.plan->wave_start[wv + 1];
+    const int cur = round & 1, prv = cur ^ 1;
+    if (D.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+        D.dbg[round * TRACE_REC + 0] = wv; D.dbg[round * TRACE_REC + 1] = hi - lo; D.dbg[round * TRACE_REC + 2] = (int)(gtime() & 0x7fffffff);
+    }
+    bool chg = false;
+    // first round of a wave: all its seeds, those not yet swallowed by a finalised region become the wave's candidates;
+    // later rounds: the candidates only
+    const int first = first_round ? lo : 0, last = first_round ? hi : (int)st->wl0_cnt;
+    for (int base = first + blockIdx.x * blockDim.x; base < last; base += gridDim.x * blockDim.x) {
+        const int j = base + threadIdx.x;
+        bool alive = false, cand = false;
+        int i = 0;
+        if (j < last) {
+            i = first_round ? j : D.wl0[j];
+            const int seed = D.C.seed_pix[i]; const u64 prio = D.C.seed_prio[i];
+            cand = first_round && !seed_final(D.C, seed);
+            if (cand || !first_round) {
+                alive = seed_alive(D.C, round, seed, prio);
+                bool deferred = false;
+                if (alive && first_round && D.defer && seed_deferred(D.C, round, seed, prio)) { alive = false; deferred = true; }
+                if (!alive) {
+                    if (deferred || (!first_round && D.C.srec[prv][i].cnt != 0)) chg = true;
+                    SeedRec z; z.head = kNull; z.cnt = 0; z.bchunk = kNull; z.bcnt = 0;
+                    D.C.srec[cur][i] = z;
+                }
+            }
+        }
+        if (first_round) wl_append(cand, i, D.wl0, &st->wl0_cnt);
+        wl_append(alive, i, D.wl1, &st->wl1_cnt);
+    }
+    if (__syncthreads_or(chg) && threadIdx.x == 0) st->changed = 1;
+}
+
+// Warp-cooperative verify of ONE long list (the thread-per-seed loop of verify_seed() would be the round's critical path):
+// 31 pixels of a chunk per step.  The seed pixel has been claimed by verify_seed().  Returns true if the region is carried.
+__device__ bool verify_long_warp(const GrowCtx& C, unsigned round, int i, int lane) {
+    const int cur = round & 1, prv = cur ^ 1;
+    const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
+    const int seed = C.seed_pix[i]; const u64 prio = C.seed_prio[i];
+    const u64 mine = (sf_cur << 40) | prio;
+    const SeedRec pr = C.srec[prv][i];
+    bool ok = true;
+    unsigned chunk = pr.head;
+    for (int k = 0; k < pr.cnt && ok; k += kChunk - 1) {
+        const unsigned v = C.pool[(size_t)chunk * kChunk + lane];
+        bool bad = false;
+        if (lane < kChunk - 1 && k + lane < pr.cnt) {
+            const u64 ep = ld_claim(&C.px[v], prv);
+            bad = ((ep >> 40) == sf_prev) && ((ep & kPrioMask) < prio);
+        }
+        ok = !__any_sync(0xffffffffu, bad);
+        chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
+    }
+    chunk = pr.bchunk;
+    for (int k = 0; k < pr.bcnt && ok; k += kChunk - 1) {
+        const unsigned v = C.pool[(size_t)chunk * kChunk + lane];
+        bool bad = false;
+        if (lane < kChunk - 1 && k + lane < pr.bcnt) {
+            const u64 ep = ld_claim(&C.px[v], prv);
+            const u64 sf = ep >> 40;
+            bad = !((sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio));      // no longer held -> must re-grow
+        }
+        ok = !__any_sync(0xffffffffu, bad);
+        chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
+    }
+    if (!ok) return false;
+    chunk = pr.head;                                                // carry the region over: re-stamp its claims for this round
+    for (int k = 0; k < pr.cnt; k += kChunk - 1) {
+        const unsigned v = C.pool[(size_t)chunk * kChunk + lane];
+        if (lane < kChunk - 1 && k + lane < pr.cnt && v != (unsigned)seed) red_min64(&C.px[v].claim[cur], mine);
+        chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
+    }
+    if (lane == 0) C.srec[cur][i] = pr;
+    return true;
+}
+
+// pass 2: every alive seed claims its pixel, then is carried over (verified) or sent to work list 2;
+// in finalise mode: every alive seed of the converged wave is stamped for good
+#define VERIFY_LONG 48
+__global__ void __launch_bounds__(128) k_lsd_verify(const GrowDev D, PhaseState* __restrict__ st) {
     if (st->done) return;
-    if (wv >= G.plan->n_waves) {                                   // no seeds at all (flat image)
-        if (blockIdx.x == 0 && threadIdx.x == 0) { st->done = 1; G.status[1] = (int)round; G.status[2] = G.plan->n_waves; G.status[3] = 1; }
+    const int wv = st->wave;
+    if (wv >= D.plan->n_waves) return;
+    const unsigned round = st->round;
+    const int n = (int)st->wl1_cnt;
+    const int nth = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    if (st->mode == 0) {
+        const bool first_round = round == st->wave_first_round;
+        bool chg = false;
+        int carried = 0;
+        // entry k of the list -> warp k % nwarps, lane k / nwarps: the long lists (walked by a whole warp, one after the other)
+        // are spread over as many warps as possible
+        const int nwarps = nth >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        for (int it = 0; it * 32 * nwarps + gw < n; ++it) {
+            const int k = (it * 32 + lane) * nwarps + gw;
+            bool grow = false; int i = 0;
+            VerifyResult r = kSeedDead;
+            if (k < n) {
+                i = D.wl1[k];
+                r = verify_seed(D.C, round, i, !first_round, &chg, VERIFY_LONG);
+                grow = r == kSeedGrow; carried += r == kSeedCarried;
+            }
+            unsigned lm = __ballot_sync(0xffffffffu, r == kSeedLong);
+            while (lm) {
+                const int src = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const bool okc = verify_long_warp(D.C, round, __shfl_sync(0xffffffffu, i, src), lane);
+                if (lane == src) { grow = !okc; carried += okc; }
+            }
+            wl_append(grow, i, D.wl2, &st->wl2_cnt);
+        }
+        if (D.dbg && carried) atomicAdd(&D.dbg[round * TRACE_REC + 4], carried);
+        if (__syncthreads_or(chg) && threadIdx.x == 0) st->changed = 1;
+    } else {
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += nth)
+            if (!finalize_seed(D.C, round, D.wl1[k], D.F)) D.status[0] = OLF_ERR_CAPACITY;
+    }
+}
+
+// pass 3: the seeds of work list 2 grow, ONE THREAD PER SEED.  Same decisions as grow_begin / grow_step / grow_end in
+// lsd_core.h (the executable specification, emulated on the host by tests/emul).  A single GPU thread walks a region's
+// sequential critical path no faster than a warp does (the path is instruction latency, not memory), but 32 regions per
+// warp cost 32x fewer issue slots -- so the kernel is written for few, branch-free instructions per queue entry:
+//   * the eight neighbour records (one 32-byte sector each) are fetched together; "free" / "held" are two 64-bit compares
+//     per record against (stamp|prio) keys, evaluated for all eight before any decision (full ILP);
+//   * only the candidates that survive are visited, in the reference's scan order, by a compact loop that reads their
+//     (angle, cos, sin) from a per-thread shared-memory slot;
+//   * the recent part of the queue lives in a per-thread shared-memory ring; claims are fire-and-forget atomicMin and a
+//     thread's own claims are visible to its own later (strong) loads, so no side table is needed;
+//   * a thread whose region is complete takes the next seed of the list: the lanes of a warp stay busy.
+#ifndef GROW_THREADS
+#define GROW_THREADS 64
+#endif
+#define GROW_RING 16
+struct GrowSmem { float nb[8][3][GROW_THREADS]; unsigned ring[GROW_RING][GROW_THREADS]; };
+
+// The last block to finish advances the wave / round state machine.
+__global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const GrowDev D, PhaseState* __restrict__ st) {
+    __shared__ GrowSmem sm;
+    __shared__ bool s_last;
+    if (st->done) return;
+    const int wv = st->wave; const unsigned round = st->round; const int mode = st->mode;
+    if (wv >= D.plan->n_waves) {                                   // no seeds at all (flat image)
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->done = 1; D.status[1] = (int)round; D.status[2] = D.plan->n_waves; D.status[3] = 1; }
         return;
     }
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const int lo = G.plan->wave_start[wv], hi = G.plan->wave_start[wv + 1];
-    const int cur = round & 1, prv = (round - 1) & 1;
-    if (mode == 0) {
+    if (mode == 0 && st->wl2_cnt > 0) {
+        const GrowCtx& C = D.C;
+        const bool have_prev = round != st->wave_first_round;
+        const unsigned n = st->wl2_cnt;
+        const int t = threadIdx.x;
+        const int cur = round & 1, prv = cur ^ 1;
         const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
-        bool any_change = false;
-        if (S.dbg && tid == 0) { S.dbg[round * TRACE_REC + 0] = wv; S.dbg[round * TRACE_REC + 1] = hi - lo; S.dbg[round * TRACE_REC + 2] = (int)(gtime() & 0x7fffffff); }
-        // seeds are handed out in batches of `bsz` (one per lane for the cheap liveness test); small waves use small
-        // batches so that the live seeds of a batch do not queue up behind each other inside one warp
-        const int nwarps = (int)(nth >> 5);
-        const int bsz = max(1, min(32, (hi - lo) / (2 * nwarps)));
+        const int W = C.W, H = C.H;
+        const float inv_w = 1.0f / (float)W;
+        unsigned* const pool = C.pool;
+        bool chg = false, active = false;
+        // per-seed state
+        int i = 0; u64 prio = 0, mine = 0, mine_prev = 0;
+        unsigned w_head = 0, w_chunk = 0, r_chunk = 0, p_chunk = 0, b_head = kNull, b_chunk = kNull;
+        int w_off = 0, r_off = 0, p_off = 0, b_off = 0, count = 0, done = 0, prev_cnt = 0, bcnt = 0;
+        bool diff = false, overflow = false, dirty = false;
+        float sumdx = 0.f, sumdy = 0.f, u2 = 0.f; double reg_angle = 0.0;
+        auto push = [&](unsigned pix) {
+            if (w_off == kChunk - 1) {
+                const unsigned nc = atomicAdd(C.pool_ctr, 1u);
+                if (nc >= C.pool_chunks) { overflow = true; return; }
+                pool[(size_t)nc * kChunk + kChunk - 1] = kNull;
+                pool[(size_t)w_chunk * kChunk + kChunk - 1] = nc;
+                w_chunk = nc; w_off = 0;
+            }
+            pool[(size_t)w_chunk * kChunk + w_off++] = pix;
+            sm.ring[count & (GROW_RING - 1)][t] = pix;
+            if (count >= prev_cnt) diff = true;                                  // lock-step comparison with last round's list
+            else {
+                if (p_off == kChunk - 1) { p_chunk = pool[(size_t)p_chunk * kChunk + kChunk - 1]; p_off = 0; }
+                diff |= pool[(size_t)p_chunk * kChunk + p_off++] != pix;
+            }
+            ++count;
+        };
+        auto record_blocked = [&](unsigned pix) {
+            if (b_chunk == kNull || b_off == kChunk - 1) {
+                const unsigned nc = atomicAdd(C.pool_ctr, 1u);
+                if (nc >= C.pool_chunks) { overflow = true; return; }
+                pool[(size_t)nc * kChunk + kChunk - 1] = kNull;
+                if (b_chunk == kNull) b_head = nc; else pool[(size_t)b_chunk * kChunk + kChunk - 1] = nc;
+                b_chunk = nc; b_off = 0;
+            }
+            pool[(size_t)b_chunk * kChunk + b_off++] = pix;
+            ++bcnt;
+        };
         for (;;) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&S.work_ctr[pass], (unsigned)bsz);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (lo + (int)base >= hi) break;
-            const int i = lo + (int)base + lane;
-            int seed = 0; u64 prio = 0; bool alive = false, deferred = false;
-            if (i < hi && lane < bsz) {
-                seed = G.seed_pix[i]; prio = G.seed_prio[i];
-                alive = !blocked_vals(px_claim(S.px, seed, prv), px_claim(S.px, seed, cur), sf_prev, sf_cur, prio);
-                if (alive && first_round && S.defer) {
-                    // Work saver (does not change the fixed point): in the first round of a wave a seed that has a live,
-                    // higher-priority, aligned 8-neighbour will almost surely be absorbed by that neighbour's region, so it
-                    // sits this round out; from the second round on every live seed grows as usual.
-                    const int W = G.A.W, H = G.A.H, py = seed / W, px = seed - py * W;
-                    const float a_s = __ldg(&G.A.ang[seed]);
-                    for (int dy = -1; dy <= 1 && alive; ++dy)
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const int xx = px + dx, yy = py + dy;
-                            if ((dx | dy) == 0 || xx < 0 || yy < 0 || xx >= W || yy >= H) continue;
-                            const int q = yy * W + xx;
-                            u64 c0, c1; PxLo lo;
-                            px_load(S.px, q, c0, c1, lo);
-                            const float a_q = lo.ang;
-                            if (a_q < 0.f) continue;
-                            const u64 pq = make_prio((int)lo.binrev, q);
-                            if (pq >= prio) continue;
-                            if (((prv ? c1 : c0) >> 40) == 0) continue;                       // finalised long ago: cannot absorb us now
-                            float d = fabsf(a_s - a_q); if (d > 180.f) d = 360.f - d;
-                            if (d <= 20.f) { alive = false; deferred = true; break; }
+            if (!active) {
+                // ---- grow_begin: the seed pixel has been claimed for this round by the verify pass
+                const unsigned k = atomicAdd(&st->wl2_pop, 1u);
+                if (k >= n) break;
+                i = D.wl2[k];
+                const int seed = C.seed_pix[i];
+                prio = C.seed_prio[i];
+                mine = (sf_cur << 40) | prio; mine_prev = (sf_prev << 40) | prio;
+                SeedRec pr; pr.head = kNull; pr.cnt = 0; pr.bchunk = kNull; pr.bcnt = 0;
+                if (have_prev) pr = C.srec[prv][i];
+                prev_cnt = pr.cnt > 0 ? pr.cnt : 0;
+                diff = prev_cnt == 0; p_chunk = pr.head; p_off = 0;
+                count = 0; done = 0; b_head = kNull; b_chunk = kNull; b_off = 0; bcnt = 0; overflow = false;
+                const unsigned nc = atomicAdd(C.pool_ctr, 1u);
+                if (nc >= C.pool_chunks) overflow = true;
+                else {
+                    pool[(size_t)nc * kChunk + kChunk - 1] = kNull;
+                    w_head = w_chunk = r_chunk = nc; w_off = 0; r_off = 0;
+                    push((unsigned)seed);
+                    float a, cx, cy; unsigned b;
+                    ld_lo(&C.px[seed], a, cx, cy, b);
+                    reg_angle = d_mul((double)a, kDegToRads);
+                    const float2_t t0 = C.tab_seed[tab_index(C.dabc[seed])];
+                    sumdx = t0.x; sumdy = t0.y;
+                    u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
+                    dirty = false;
+                }
+                active = true;
+            }
+            if (!overflow) {
+                // ---- grow_step: expand one queue entry
+                if (r_off == kChunk - 1) { r_chunk = pool[(size_t)r_chunk * kChunk + kChunk - 1]; r_off = 0; }
+                const int p = (int)((count - done <= GROW_RING) ? sm.ring[done & (GROW_RING - 1)][t] : pool[(size_t)r_chunk * kChunk + r_off]);
+                ++r_off; ++done;
+                int py = __float2int_rd(__fmul_rn((float)p, inv_w));           // p < 2^24: exact after one correction step
+                int px = p - py * W;
+                if (px < 0) { --py; px += W; } else if (px >= W) { ++py; px -= W; }
+                // which of the 8 neighbours exist (bit k = k-th neighbour in scan order, centre skipped)
+                unsigned vm = 0x18u;
+                if (py > 0) vm |= 0x07u;
+                if (py < H - 1) vm |= 0xE0u;
+                if (px == 0) vm &= ~0x29u;
+                if (px == W - 1) vm &= ~0x94u;
+                const PxRec* const base = C.px + p;
+                // all sixteen loads are issued before anything consumes them (one memory round trip per queue entry)
+                u64 c0[8], c1[8]; float4 lo[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int nk = k < 4 ? k : k + 1;
+                    const PxRec* r = base + ((nk / 3) - 1) * W + ((nk % 3) - 1);
+                    c0[k] = 0; c1[k] = 0;
+                    if ((vm >> k) & 1u) ld_claims(r, c0[k], c1[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int nk = k < 4 ? k : k + 1;
+                    const PxRec* r = base + ((nk / 3) - 1) * W + ((nk % 3) - 1);
+                    lo[k] = make_float4(-1.f, 0.f, 0.f, 0.f);
+#ifdef OLF_EXP_WEAK
+                    if ((vm >> k) & 1u) lo[k] = __ldg(reinterpret_cast<const float4*>(r) + 1);
+#else
+                    if ((vm >> k) & 1u) lo[k] = __ldcg(reinterpret_cast<const float4*>(r) + 1);
+#endif
+                }
+                unsigned m_free = 0, m_held = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const u64 ep = cur ? c0[k] : c1[k], ec = cur ? c1[k] : c0[k];
+                    // free: neither final nor held by a higher-priority seed nor already mine (NOTDEF pixels are born final)
+                    const bool fre = (ep >= mine_prev) && (ec > mine);
+                    const bool fin = ((unsigned)(ep >> 40) == 0u) || ((unsigned)(ec >> 40) == 0u);
+                    const bool hld = !fre && !fin && (ec != mine);
+                    m_free |= (unsigned)fre << k;
+                    m_held |= (unsigned)hld << k;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { sm.nb[k][0][t] = lo[k].x; sm.nb[k][1][t] = lo[k].y; sm.nb[k][2][t] = lo[k].z; }
+                // the surviving candidates, in scan order; the region angle changes after every accepted pixel
+                unsigned m = m_free | m_held;
+                while (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float cxk = sm.nb[k][1][t], cyk = sm.nb[k][2][t];
+                    bool al;
+                    {   // isAligned(), lazily: see grow_aligned() in lsd_core.h
+                        const float dot = f_add(f_mul(sumdx, cxk), f_mul(sumdy, cyk)), d2 = f_mul(dot, dot);
+                        const bool fast = C.fast_align && u2 > 1e-3f;
+                        if (fast && dot > 0.f && d2 >= f_mul(C.c_hi2, u2)) al = true;
+                        else if (fast && (dot <= 0.f || d2 <= f_mul(C.c_lo2, u2))) al = false;
+                        else {
+                            if (dirty) { reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads); dirty = false; }
+                            double n_theta = d_sub(reg_angle, d_mul((double)sm.nb[k][0][t], kDegToRads));
+                            if (n_theta < 0) n_theta = -n_theta;
+                            if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
+                            al = n_theta <= C.prec;
                         }
-                }
-                if (!alive) { if (deferred || __ldcg(&G.cnt[prv][i]) != 0) any_change = true; G.cnt[cur][i] = 0; G.head[cur][i] = kNull; }
-            }
-            unsigned m = __ballot_sync(0xffffffffu, alive);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const int s_seed = __shfl_sync(0xffffffffu, seed, src);
-                const u64 s_prio = shfl_u64(prio, src);
-                if (grow_seed_warp(S, round, lo + (int)base + src, s_seed, s_prio, lane, hash_sets[threadIdx.x >> 5])) any_change = true;
-            }
-        }
-        if (__syncthreads_or(any_change) && threadIdx.x == 0) G.changed[round] = 1;
-    } else {
-        // finalise the wave (warp per live seed): stamp the regions for good, keep the lists of accepted regions
-        const unsigned* pool = G.A.pool[cur];
-        for (;;) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&S.work_ctr[pass], 32u);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (lo + (int)base >= hi) break;
-            const int i = lo + (int)base + lane;
-            const int c_l = (i < hi) ? __ldcg(&G.cnt[cur][i]) : 0;
-            unsigned m = __ballot_sync(0xffffffffu, c_l > 0);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const int si = lo + (int)base + src;
-                const int c = __shfl_sync(0xffffffffu, c_l, src);
-                const u64 prio = G.seed_prio[si];
-                const bool accept = c >= G.min_reg_size;
-                unsigned off = 0;
-                if (accept && lane == 0) off = atomicAdd(G.final_ctr, (unsigned)c);
-                off = __shfl_sync(0xffffffffu, off, 0);
-                unsigned chunk = __ldcg(&G.head[cur][si]);
-                for (int k = 0; k < c; k += kChunk - 1) {
-                    const unsigned v = __ldcg(&pool[(size_t)chunk * kChunk + lane]);
-                    if (lane < kChunk - 1 && k + lane < c) {
-                        S.px[v].claim[0] = prio; S.px[v].claim[1] = prio;
-                        if (accept) G.final_pool[off + k + lane] = v;
                     }
-                    chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
-                }
-                if (accept && lane == 0) {
-                    const unsigned r = atomicAdd(G.nreg, 1u);
-                    if (r < G.reg_cap) { LsdRegion R; R.prio = prio; R.off = off; R.count = c; R.reg_angle = __ldcg(&G.regang[si]); G.regs[r] = R; }
-                    else G.status[0] = OLF_ERR_CAPACITY;
+                    if (!al) continue;
+                    const int nk = k < 4 ? k : k + 1;
+                    const int q = p + ((nk / 3) - 1) * W + ((nk % 3) - 1);
+                    if ((m_held >> k) & 1u) { record_blocked((unsigned)q); if (overflow) break; continue; }   // aligned but held by a higher-priority seed
+                    red_min64(&C.px[q].claim[cur], mine);
+                    push((unsigned)q);
+                    if (overflow) break;
+                    sumdx = f_add(sumdx, cxk);
+                    sumdy = f_add(sumdy, cyk);
+                    u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
+                    dirty = true;
                 }
             }
+            if (overflow || done >= count) {
+                // ---- grow_end
+                SeedRec r;
+                if (overflow) { r.head = kNull; r.cnt = 0; r.bchunk = kNull; r.bcnt = 0; D.status[0] = OLF_ERR_CAPACITY; chg = true; }
+                else {
+                    if (dirty) reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads);
+                    r.head = w_head; r.cnt = count; r.bchunk = b_head; r.bcnt = bcnt;
+                    C.regang[i] = reg_angle;
+                    if (diff || count != prev_cnt) chg = true;
+                }
+                C.srec[cur][i] = r;
+                if (D.dbg) { atomicAdd(&D.dbg[round * TRACE_REC + 5], 1); atomicAdd(&D.dbg[round * TRACE_REC + 6], count); atomicMax(&D.dbg[round * TRACE_REC + 7], count); }
+                active = false;
+            }
         }
+        if (chg) st->changed = 1;
     }
     // last block to finish advances the state machine
     __threadfence();
@@ -628,16 +504,18 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 6) k_lsd_phase(const GrowStateW
     __syncthreads();
     if (!s_last || threadIdx.x != 0) return;
     __threadfence();
-    const int err = __ldcg(&G.status[0]);
-    st->ticket = 0; st->launches += 1; st->pass = pass + 1;
+    const int err = *(volatile int*)&D.status[0];
+    st->ticket = 0; st->launches += 1;
     if (mode == 0) {
-        if (S.dbg) S.dbg[round * TRACE_REC + 3] = (int)(gtime() & 0x7fffffff);
-        const bool changed = __ldcg(&G.changed[round]) != 0;
-        if (!changed || round + 2 >= G.max_rounds || err != 0) st->mode = 1; else st->round = round + 1;
+        if (D.dbg) D.dbg[round * TRACE_REC + 3] = (int)(gtime() & 0x7fffffff);
+        const bool changed = *(volatile unsigned*)&st->changed != 0;
+        if (!changed || round + 2 >= D.max_rounds || err != 0) st->mode = 1;      // work list 1 is kept for the finalise pass
+        else { st->round = round + 1; st->wl1_cnt = 0; }
+        st->wl2_cnt = 0; st->wl2_pop = 0; st->changed = 0;
     } else {
-        st->mode = 0; st->round = round + 1; st->wave = wv + 1; st->wave_first_round = round + 1;
-        *G.A.pool_ctr[0] = 0;                                       // one bump pool per wave (lists may be carried over rounds)
-        if (wv + 1 >= G.plan->n_waves || err != 0) { st->done = 1; G.status[1] = (int)(round + 1); G.status[2] = G.plan->n_waves; G.status[3] = 1; }
+        st->mode = 0; st->round = round + 1; st->wave = wv + 1; st->wave_first_round = round + 1; st->wl1_cnt = 0; st->wl0_cnt = 0;
+        *D.C.pool_ctr = 0;                                          // one bump pool per wave (lists are carried over rounds)
+        if (wv + 1 >= D.plan->n_waves || err != 0) { st->done = 1; D.status[1] = (int)(round + 1); D.status[2] = D.plan->n_waves; D.status[3] = 1; }
     }
     __threadfence();
 }
@@ -900,23 +778,22 @@ struct LineImpl {
     DevBuf<uint8_t> img, blurred, scaled, lbd_blur;
     DevBuf<ExCoef> coef; size_t coef_y_off = 0;
     DevBuf<float> ang; DevBuf<short2_t> dabc;
-    DevBuf<u64> claim0, claim1, seed_prio;
-    DevBuf<int> seed_pix, cnt0, cnt1, n2max, status;
-    DevBuf<unsigned> head0, head1, hist, bin_start, cursor, pool0, pool1, ctrs, changed, final_pool;
+    DevBuf<u64> seed_prio;
+    DevBuf<int> seed_pix, n2max, status, wl0, wl1, wl2;
+    DevBuf<unsigned> hist, bin_start, cursor, pool, ctrs, final_pool;
+    DevBuf<SeedRec> srec0, srec1;
     DevBuf<double> regang;
     DevBuf<LsdPlan> plan;
     DevBuf<LsdRegion> regs;
     DevBuf<float2_t> tab_seed, tab_acc, cs;
-    DevBuf<unsigned> work_ctr, blk_chunk0, blk_chunk1;
     DevBuf<PhaseState> phase;
     DevBuf<PxRec> px;
     int phase_batch = 40;
-    DevBuf<int> blk_cnt0, blk_cnt1;
-    bool scalar_grow = false, trace = false;
+    bool trace = false;
     int first_wave = 4096, wave_growth = 16;
     DevBuf<int> dbg;
     unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
-    int grow_blocks = 0;
+    int scan_blocks = 0, verify_blocks = 0, grow_blocks = 0;
     PinBuf<RectRec> rect_host; PinBuf<double2> dir_host; PinBuf<float4> seg_host; PinBuf<int> status_host; PinBuf<unsigned> nreg_host;
     // LBD
     DevBuf<short2_t> grad;
@@ -1006,17 +883,13 @@ LineImpl* line_create(const olf_line_params* p, int device) {
     if (const char* e = getenv("OLF_LSD_FIRST_WAVE")) h->first_wave = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_WAVE_GROWTH")) h->wave_growth = std::max(2, atoi(e));
     h->trace = getenv("OLF_LSD_TRACE") != nullptr;                // per-round trace of the grow kernel (tools/lsd_trace.py)
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_phase, GW_WARPS * 32, 0) == cudaSuccess && per_sm > 0;
     ok = ok && h->phase.ensure(1) == OLF_OK;
     if (const char* e = getenv("OLF_LSD_PHASE_BATCH")) h->phase_batch = std::max(4, atoi(e));
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
-    {   // blocks per SM of the persistent grow kernel: the kernel is latency-bound (one warp walks the longest region), so a
-        // small grid loses little and lets the left/right eyes and several frames in flight share the GPU
-        // half a block (4 warps) per SM: measured optimum with 16 rigs in flight (larger grids only fight for block slots)
-        h->grow_blocks = std::max(1, sms / 2);
-        if (const char* e = getenv("OLF_LSD_BPS")) h->grow_blocks = sms * std::max(1, std::min(per_sm, atoi(e)));
-        if (const char* e = getenv("OLF_LSD_BLOCKS")) h->grow_blocks = std::max(1, std::min(atoi(e), sms * per_sm));
-    }
+    // grids of the three region-growing passes (one thread per seed; see k_lsd_scan / k_lsd_verify / k_lsd_grow)
+    h->scan_blocks = 2 * sms; h->verify_blocks = sms; h->grow_blocks = sms;
+    if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks = std::max(1, atoi(e));
+    (void)per_sm;
     return h;
 }
 
@@ -1027,13 +900,12 @@ void line_destroy(LineImpl* h) {
     if (h->ev_grow0) cudaEventDestroy(h->ev_grow0);
     if (h->ev_grow1) cudaEventDestroy(h->ev_grow1);
     h->img_stage.release(); h->img.release(); h->blurred.release(); h->scaled.release(); h->lbd_blur.release(); h->coef.release();
-    h->ang.release(); h->dabc.release(); h->claim0.release(); h->claim1.release(); h->seed_prio.release(); h->seed_pix.release();
-    h->cnt0.release(); h->cnt1.release(); h->n2max.release(); h->status.release(); h->head0.release(); h->head1.release();
-    h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool0.release(); h->pool1.release(); h->ctrs.release();
-    h->changed.release(); h->final_pool.release(); h->regang.release(); h->plan.release(); h->regs.release();
-    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->work_ctr.release();
-    h->blk_chunk0.release(); h->blk_chunk1.release(); h->blk_cnt0.release(); h->blk_cnt1.release(); h->phase.release(); h->px.release(); h->rect_host.release(); h->dir_host.release(); h->seg_host.release();
-    h->status_host.release(); h->nreg_host.release(); h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
+    h->ang.release(); h->dabc.release(); h->seed_prio.release(); h->seed_pix.release(); h->n2max.release(); h->status.release();
+    h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
+    h->final_pool.release(); h->srec0.release(); h->srec1.release(); h->regang.release(); h->plan.release(); h->regs.release();
+    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release();
+    h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release();
+    h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
 }
 
@@ -1060,14 +932,13 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
     OLF_CUDA(cudaMemcpy(h->coef.p, cx.data(), cx.size() * sizeof(ExCoef), cudaMemcpyHostToDevice));
     h->pool_chunks = (unsigned)std::max<size_t>(S / 2, 1u << 16);       // 16 px of list space per image pixel per round
     h->reg_cap = (unsigned)(S / std::max(h->min_reg_size, 1) + 16);
-    if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || 
-        (rc = h->seed_prio.ensure(S)) || (rc = h->seed_pix.ensure(S)) || (rc = h->cnt0.ensure(S)) || (rc = h->cnt1.ensure(S)) ||
-        (rc = h->head0.ensure(S)) || (rc = h->head1.ensure(S)) || (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) ||
+    if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || (rc = h->seed_prio.ensure(S)) || (rc = h->seed_pix.ensure(S)) ||
+        (rc = h->srec0.ensure(S)) || (rc = h->srec1.ensure(S)) || (rc = h->wl0.ensure(S)) || (rc = h->wl1.ensure(S)) || (rc = h->wl2.ensure(S)) ||
+        (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) ||
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
-        (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->changed.ensure(h->max_rounds)) || (rc = h->plan.ensure(1)) ||
-        (rc = h->pool0.ensure((size_t)h->pool_chunks * kChunk)) || (rc = h->pool1.ensure((size_t)h->pool_chunks * kChunk)) ||
-        (rc = h->dbg.ensure((size_t)h->max_rounds * TRACE_REC)) || (rc = h->px.ensure(S)) || (rc = h->work_ctr.ensure(2 * h->max_rounds + 64)) ||
-        (rc = h->blk_chunk0.ensure(S)) || (rc = h->blk_chunk1.ensure(S)) || (rc = h->blk_cnt0.ensure(S)) || (rc = h->blk_cnt1.ensure(S)) ||
+        (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->plan.ensure(1)) ||
+        (rc = h->pool.ensure((size_t)h->pool_chunks * kChunk)) ||
+        (rc = h->dbg.ensure((size_t)h->max_rounds * TRACE_REC)) || (rc = h->px.ensure(S)) ||
         (rc = h->regs.ensure(h->reg_cap)) || (rc = h->rect_host.ensure(h->reg_cap)) || (rc = h->dir_host.ensure(h->reg_cap)) ||
         (rc = h->seg_host.ensure(h->reg_cap)) || (rc = h->status_host.ensure(4)) || (rc = h->nreg_host.ensure(1))) return rc;
     h->img_w = w; h->img_h = hgt;
@@ -1112,8 +983,6 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     OLF_CUDA(cudaMemsetAsync(h->hist.p, 0, 1024 * sizeof(unsigned), s));
     OLF_CUDA(cudaMemsetAsync(h->ctrs.p, 0, 4 * sizeof(unsigned), s));
     OLF_CUDA(cudaMemsetAsync(h->status.p, 0, 4 * sizeof(int), s));
-    OLF_CUDA(cudaMemsetAsync(h->changed.p, 0, h->max_rounds * sizeof(unsigned), s));
-    OLF_CUDA(cudaMemsetAsync(h->work_ctr.p, 0, (2 * h->max_rounds + 64) * sizeof(unsigned), s));
     {
         dim3 g((W + 31) / 32, (H + 7) / 8);
         k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->tab_acc.p, h->px.p, h->n2max.p);
@@ -1122,36 +991,37 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
     k_lsd_plan<<<1, 1024, 0, s>>>(h->hist.p, nb, h->first_wave, h->wave_growth, h->bin_start.p, h->cursor.p, h->plan.p);
     k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p, h->px.p);
-    GrowState G;
-    G.A.W = W; G.A.H = H; G.A.ang = h->ang.p; G.A.dabc = h->dabc.p; G.A.tab_seed = h->tab_seed.p; G.A.tab_acc = h->tab_acc.p;
-    G.A.claim[0] = nullptr; G.A.claim[1] = nullptr; G.A.pool[0] = h->pool0.p; G.A.pool[1] = h->pool1.p;
-    G.A.pool_ctr[0] = h->ctrs.p; G.A.pool_ctr[1] = h->ctrs.p + 1; G.A.pool_chunks = h->pool_chunks; G.A.prec = h->prec;
-    G.seed_pix = h->seed_pix.p; G.seed_prio = h->seed_prio.p;
-    G.head[0] = h->head0.p; G.head[1] = h->head1.p; G.cnt[0] = h->cnt0.p; G.cnt[1] = h->cnt1.p; G.regang = h->regang.p;
-    G.plan = h->plan.p; G.changed = h->changed.p; G.max_rounds = h->max_rounds; G.min_reg_size = h->min_reg_size;
-    G.final_pool = h->final_pool.p; G.final_ctr = h->ctrs.p + 2; G.regs = h->regs.p; G.nreg = h->ctrs.p + 3; G.reg_cap = h->reg_cap;
-    G.status = h->status.p;
-    GrowStateW GW; GW.G = G; GW.px = h->px.p; GW.work_ctr = h->work_ctr.p;
-    GW.G.A.pool[1] = GW.G.A.pool[0]; GW.G.A.pool_ctr[1] = GW.G.A.pool_ctr[0];      // warp kernel: one bump pool per wave
-    GW.blk_chunk[0] = h->blk_chunk0.p; GW.blk_chunk[1] = h->blk_chunk1.p; GW.blk_cnt[0] = h->blk_cnt0.p; GW.blk_cnt[1] = h->blk_cnt1.p;
+    GrowDev D;
+    D.C.W = W; D.C.H = H; D.C.px = h->px.p; D.C.dabc = h->dabc.p; D.C.tab_seed = h->tab_seed.p;
+    D.C.pool = h->pool.p; D.C.pool_ctr = h->ctrs.p; D.C.pool_chunks = h->pool_chunks;
+    D.C.srec[0] = h->srec0.p; D.C.srec[1] = h->srec1.p; D.C.regang = h->regang.p;
+    D.C.seed_pix = h->seed_pix.p; D.C.seed_prio = h->seed_prio.p; D.C.prec = h->prec;
     {
         const double margin = 0.1 * M_PI / 180.0;
-        GW.fast_align = (h->prec + margin < 80.0 * M_PI / 180.0) && !getenv("OLF_LSD_EXACT_ALIGN");
-        GW.c_hi2 = (float)(std::cos(h->prec - margin) * std::cos(h->prec - margin));
-        GW.c_lo2 = (float)(std::cos(h->prec + margin) * std::cos(h->prec + margin));
+        D.C.fast_align = (h->prec + margin < 80.0 * M_PI / 180.0) && !getenv("OLF_LSD_EXACT_ALIGN");
+        D.C.c_hi2 = (float)(std::cos(h->prec - margin) * std::cos(h->prec - margin));
+        D.C.c_lo2 = (float)(std::cos(h->prec + margin) * std::cos(h->prec + margin));
     }
-    GW.defer = getenv("OLF_LSD_NO_DEFER") ? 0 : 1;
-    GW.dbg = h->trace ? h->dbg.p : nullptr;
+    D.plan = h->plan.p; D.wl0 = h->wl0.p; D.wl1 = h->wl1.p; D.wl2 = h->wl2.p;
+    D.F.final_pool = h->final_pool.p; D.F.final_ctr = h->ctrs.p + 2; D.F.regs = h->regs.p; D.F.nreg = h->ctrs.p + 3;
+    D.F.reg_cap = h->reg_cap; D.F.min_reg_size = h->min_reg_size;
+    D.status = h->status.p; D.max_rounds = h->max_rounds;
+    D.defer = getenv("OLF_LSD_NO_DEFER") ? 0 : 1;
+    D.dbg = h->trace ? h->dbg.p : nullptr;
     if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
     OLF_CUDA(cudaEventRecord(h->ev_grow0, s));
+    auto enqueue_phases = [&](int n) {
+        for (int k = 0; k < n; ++k) {
+            k_lsd_scan<<<h->scan_blocks, 256, 0, s>>>(D, h->phase.p);
+            k_lsd_verify<<<h->verify_blocks, 128, 0, s>>>(D, h->phase.p);
+            k_lsd_grow<<<h->grow_blocks, GROW_THREADS, 0, s>>>(D, h->phase.p);
+        }
+        count_launches(3 * n);
+    };
     {
         PhaseState init; memset(&init, 0, sizeof(init)); init.round = 1; init.wave_first_round = 1;
-        // seeds of later waves must start with "no previous list"
-        OLF_CUDA(cudaMemsetAsync(h->cnt0.p, 0, (size_t)S * sizeof(int), s));
-        OLF_CUDA(cudaMemsetAsync(h->cnt1.p, 0, (size_t)S * sizeof(int), s));
         OLF_CUDA(cudaMemcpyAsync(h->phase.p, &init, sizeof(init), cudaMemcpyHostToDevice, s));
-        for (int k = 0; k < h->phase_batch; ++k) k_lsd_phase<<<h->grow_blocks, GW_WARPS * 32, 0, s>>>(GW, h->phase.p);
-        count_launches(h->phase_batch);
+        enqueue_phases(h->phase_batch);
     }
     OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
     count_launches((h->blur_k ? 2 : 0) + 6);
@@ -1164,8 +1034,8 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
         // the fixed batch of phase launches normally covers all rounds; otherwise keep going (rare)
         for (int guard = 0; guard < 400; ++guard) {
             if (h->status_host.p[3] || h->status_host.p[0]) break;
-            for (int k = 0; k < h->phase_batch; ++k) k_lsd_phase<<<h->grow_blocks, GW_WARPS * 32, 0, s>>>(GW, h->phase.p);
-            count_launches(h->phase_batch + 1);
+            enqueue_phases(h->phase_batch);
+            count_launches(1);
             OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
             k_lsd_rect_a<<<296, 256, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
             OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE.  Host emulation of the parallel LSD region-growing scheme of
-// orb_line_slam_b200/csrc/lsd_core.h: the SAME grow_seed()/region_rect_a() source is compiled for the CPU and the
-// rounds are replayed sequentially with a random seed order per round (emulating arbitrary GPU scheduling).
+// orb_line_slam_b200/csrc/lsd_core.h: the SAME scan / verify_seed() / grow_step() / finalize_seed() / region_rect_a()
+// source the kernels run is compiled for the CPU; every pass is replayed in a random order and the growths of a round
+// are stepped in a random interleaving (emulating arbitrary GPU scheduling and partial visibility of claims).
 // The result must equal the oracle's sequential LSD; the test also reports waves / rounds / work amplification.
 #include "../../orb_line_slam_b200/csrc/lsd_core.h"
 #include "../../oracle/cvprim.hpp"
@@ -10,8 +11,8 @@
 
 using namespace olf::lsd;
 
-extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_params* P, unsigned rng_seed, int first_wave,
-                               float* segs, int cap, int* nseg, long long* stats /*[6]: waves, rounds, grown_px, final_px, regions, max_rounds_in_wave*/) {
+extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_params* P, unsigned rng_seed, int first_wave, int defer, int exact_align,
+                               float* segs, int cap, int* nseg, long long* stats /*[7]: waves, rounds, grown_px, final_px, regions, max_rounds_in_wave, carried*/) {
     orc::Image8 im(w, h);
     memcpy(im.d.data(), img, (size_t)w * h);
     const double scale = P->lsd_scale;
@@ -70,70 +71,130 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
     const double logNT = 5 * (std::log10((double)W) + std::log10((double)H)) / 2 + std::log10(11.0);
     const int min_reg_size = (int)(unsigned)(-logNT / std::log10(p));
 
-    std::vector<u64> claim0(S, kClaimNone), claim1(S, kClaimNone);
-    const unsigned pool_chunks = 1u << 22;
-    std::vector<unsigned> pool0((size_t)pool_chunks * kChunk), pool1((size_t)pool_chunks * kChunk);
-    unsigned ctr0 = 0, ctr1 = 0;
-    GrowArgs A;
-    A.W = W; A.H = H; A.ang = ang.data(); A.dabc = dabc.data(); A.tab_seed = tab_seed.data(); A.tab_acc = tab_acc.data();
-    A.claim[0] = claim0.data(); A.claim[1] = claim1.data(); A.pool[0] = pool0.data(); A.pool[1] = pool1.data();
-    A.pool_ctr[0] = &ctr0; A.pool_ctr[1] = &ctr1; A.pool_chunks = pool_chunks; A.prec = prec;
-    std::vector<unsigned> head[2] = {std::vector<unsigned>(n, kNull), std::vector<unsigned>(n, kNull)};
-    std::vector<int> cnt[2] = {std::vector<int>(n, 0), std::vector<int>(n, 0)};
+    // per-pixel records exactly as k_lsd_grad / k_lsd_scatter build them
+    std::vector<PxRec> px(S);
+    for (int q = 0; q < S; ++q) {
+        PxRec r; r.claim[0] = kClaimNone; r.claim[1] = kClaimNone; r.ang = ang[q]; r.cx = 0.f; r.cy = 0.f; r.binrev = 0;
+        if (ang[q] >= 0.f) {
+            const float2_t c = tab_acc[tab_index(dabc[q])];
+            r.cx = c.x; r.cy = c.y;
+            r.binrev = (unsigned)(n_bins - 1 - (int)(std::sqrt(n2[q] / 4.0) * bin_coef));
+        }
+        px[q] = r;
+    }
+    const unsigned pool_chunks = 1u << 21;
+    std::vector<unsigned> pool((size_t)pool_chunks * kChunk);
+    unsigned pool_ctr = 0;
+    std::vector<SeedRec> srec[2] = {std::vector<SeedRec>(n), std::vector<SeedRec>(n)};
     std::vector<double> regang(n, 0.0);
-    struct Seg { u64 prio; float v[4]; };
-    std::vector<Seg> out;
-    long long waves = 0, rounds = 0, grown = 0, final_px = 0, regions = 0, max_rw = 0;
+    GrowCtx C;
+    C.W = W; C.H = H; C.px = px.data(); C.dabc = dabc.data(); C.tab_seed = tab_seed.data();
+    C.pool = pool.data(); C.pool_ctr = &pool_ctr; C.pool_chunks = pool_chunks;
+    C.srec[0] = srec[0].data(); C.srec[1] = srec[1].data(); C.regang = regang.data();
+    C.seed_pix = seeds.data(); C.seed_prio = prio.data(); C.prec = prec;
+    {
+        const double margin = 0.1 * M_PI / 180.0;
+        C.fast_align = (exact_align == 0) && (prec + margin < 80.0 * M_PI / 180.0);
+        C.c_hi2 = (float)(std::cos(prec - margin) * std::cos(prec - margin));
+        C.c_lo2 = (float)(std::cos(prec + margin) * std::cos(prec + margin));
+    }
+    std::vector<unsigned> final_pool(S); unsigned final_ctr = 0, nreg = 0;
+    std::vector<LsdRegion> regs(S / std::max(min_reg_size, 1) + 16);
+    FinalOut F; F.final_pool = final_pool.data(); F.final_ctr = &final_ctr; F.regs = regs.data(); F.nreg = &nreg;
+    F.reg_cap = (unsigned)regs.size(); F.min_reg_size = min_reg_size;
+    long long waves = 0, rounds = 0, grown = 0, final_px = 0, regions = 0, max_rw = 0, carried = 0;
     unsigned round = 1;
-    std::vector<int> order;
+    std::vector<int> order, wl0, wl1, wl2;
     for (size_t wv = 0; wv + 1 < wave_start.size(); ++wv) {
         const int lo = wave_start[wv], hi = wave_start[wv + 1];
         if (lo == hi) continue;
         ++waves;
-        for (int i = lo; i < hi; ++i) { cnt[0][i] = cnt[1][i] = 0; }
+        pool_ctr = 0;                                          // one bump pool per wave
         long long rw = 0;
+        bool first_round = true;
         for (;;) {
             ++rounds; ++rw;
-            *A.pool_ctr[round & 1] = 0;
-            order.resize(hi - lo); std::iota(order.begin(), order.end(), lo);
-            std::shuffle(order.begin(), order.end(), rng);
+            const int cur = round & 1, prv = cur ^ 1;
             bool changed = false;
+            // pass 1: scan (any order)
+            if (first_round) { order.resize(hi - lo); std::iota(order.begin(), order.end(), lo); }
+            else order = wl0;
+            std::shuffle(order.begin(), order.end(), rng);
+            if (first_round) wl0.clear();
+            wl1.clear(); wl2.clear();
             for (int i : order) {
-                GrowResult r = grow_seed(A, round, seeds[i], prio[i], head[(round - 1) & 1][i], cnt[(round - 1) & 1][i]);
-                if (r.overflow) return -3;
-                head[round & 1][i] = r.head; cnt[round & 1][i] = r.count; regang[i] = r.reg_angle;
-                if (!r.same_as_prev) changed = true;
-                grown += r.count;
+                if (first_round) {                              // seeds swallowed by finalised regions leave the wave for good
+                    if (seed_final(C, seeds[i])) continue;
+                    wl0.push_back(i);
+                }
+                bool alive = seed_alive(C, round, seeds[i], prio[i]);
+                bool deferred = false;
+                if (alive && first_round && defer && seed_deferred(C, round, seeds[i], prio[i])) { alive = false; deferred = true; }
+                if (alive) { wl1.push_back(i); continue; }
+                if (deferred || (!first_round && srec[prv][i].cnt != 0)) changed = true;
+                SeedRec z; z.head = kNull; z.cnt = 0; z.bchunk = kNull; z.bcnt = 0;
+                srec[cur][i] = z;
             }
+            // pass 2: verify (any order)
+            std::shuffle(wl1.begin(), wl1.end(), rng);
+            for (int i : wl1) {
+                const VerifyResult v = verify_seed(C, round, i, !first_round, &changed);
+                if (v == kSeedGrow) wl2.push_back(i);
+                else if (v == kSeedCarried) ++carried;
+            }
+            // pass 3: grow -- `lanes` growths in flight, stepped in random interleaving (arbitrary GPU scheduling)
+            {
+                std::vector<GrowSt> act;
+                size_t next = 0;
+                const size_t lanes = 1 + rng() % 48;
+                while (next < wl2.size() || !act.empty()) {
+                    while (act.size() < lanes && next < wl2.size()) {
+                        GrowSt st; grow_begin(C, round, wl2[next++], !first_round, st);
+                        if (st.overflow) return -3;
+                        act.push_back(st);
+                    }
+                    const size_t k = rng() % act.size();
+                    if (!grow_step(C, round, act[k])) {
+                        if (act[k].overflow) return -3;
+                        grown += act[k].count;
+                        if (grow_end(C, round, act[k])) changed = true;
+                        act[k] = act.back(); act.pop_back();
+                    }
+                }
+            }
+            first_round = false;
             if (!changed) break;
             ++round;
         }
         max_rw = std::max(max_rw, rw);
-        // finalise: stamp 0 in both claim arrays, emit accepted regions
-        std::vector<unsigned> pix;
-        for (int i = lo; i < hi; ++i) {
-            const int c = cnt[round & 1][i];
-            if (c == 0) continue;
-            ++regions; final_px += c;
-            pix.resize(c);
-            ListReader rd; rd.init(A.pool[round & 1], head[round & 1][i]);
-            for (int k = 0; k < c; ++k) { pix[k] = rd.next(); claim0[pix[k]] = prio[i]; claim1[pix[k]] = prio[i]; }
-            if (c < min_reg_size) continue;
-            RectA ra = region_rect_a(pix.data(), c, dabc.data(), W, regang[i], prec);
-            const double dx = std::cos(ra.theta), dy = std::sin(ra.theta);
-            double l_min = 0, l_max = 0;
-            for (int k = 0; k < c; ++k) { const double l = region_proj(pix[k], W, ra.x, ra.y, dx, dy); if (l > l_max) l_max = l; else if (l < l_min) l_min = l; }
-            double r[4] = {ra.x + l_min * dx, ra.y + l_min * dy, ra.x + l_max * dx, ra.y + l_max * dy};
-            Seg s; s.prio = prio[i];
-            for (int k = 0; k < 4; ++k) { r[k] += 0.5; if (scale != 1.0) r[k] /= scale; s.v[k] = (float)r[k]; }
-            out.push_back(s);
+        // finalise the converged wave (its alive list is wl1)
+        for (int i : wl1) {
+            const int c = srec[round & 1][i].cnt;
+            if (c > 0) { ++regions; final_px += c; }
+            if (!finalize_seed(C, round, i, F)) return -3;
         }
         ++round;
+    }
+    // rectangle fit of the accepted regions
+    struct Seg { u64 prio; float v[4]; };
+    std::vector<Seg> out;
+    for (unsigned r = 0; r < nreg; ++r) {
+        const LsdRegion& R = regs[r];
+        const unsigned* pix = final_pool.data() + R.off;
+        const int c = R.count;
+        RectA ra = region_rect_a(pix, c, dabc.data(), W, R.reg_angle, prec);
+        const double dx = std::cos(ra.theta), dy = std::sin(ra.theta);
+        double l_min = 0, l_max = 0;
+        for (int k = 0; k < c; ++k) { const double l = region_proj(pix[k], W, ra.x, ra.y, dx, dy); if (l > l_max) l_max = l; else if (l < l_min) l_min = l; }
+        double rr[4] = {ra.x + l_min * dx, ra.y + l_min * dy, ra.x + l_max * dx, ra.y + l_max * dy};
+        Seg sg; sg.prio = R.prio;
+        for (int k = 0; k < 4; ++k) { rr[k] += 0.5; if (scale != 1.0) rr[k] /= scale; sg.v[k] = (float)rr[k]; }
+        out.push_back(sg);
     }
     std::sort(out.begin(), out.end(), [](const Seg& a, const Seg& b) { return a.prio < b.prio; });
     *nseg = (int)out.size();
     if ((int)out.size() > cap) return -3;
     for (size_t i = 0; i < out.size(); ++i) memcpy(segs + 4 * i, out[i].v, 16);
-    stats[0] = waves; stats[1] = rounds; stats[2] = grown; stats[3] = final_px; stats[4] = regions; stats[5] = max_rw;
+    stats[0] = waves; stats[1] = rounds; stats[2] = grown; stats[3] = final_px; stats[4] = regions; stats[5] = max_rw; stats[6] = carried;
     return 0;
 }

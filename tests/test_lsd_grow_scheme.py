@@ -1,7 +1,8 @@
 """The parallel LSD region-growing scheme (fixed-point iteration over priority waves, orb_line_slam_b200/csrc/
-lsd_core.h) is validated WITHOUT a GPU: the same grow_seed()/region_rect_a() source is compiled for the host and the
-rounds are replayed with a random seed order per round (tests/emul/lsd_emul.cpp).  Result must equal the oracle's
-sequential LSD bit for bit, for any schedule."""
+lsd_core.h) is validated WITHOUT a GPU: the same scan / verify_seed / grow_step / finalize_seed / region_rect_a source
+the kernels run is compiled for the host; every pass is replayed in a random order and the growths of a round are stepped
+in a random interleaving (tests/emul/lsd_emul.cpp).  Result must equal the oracle's sequential LSD bit for bit, for any
+schedule, with and without the first-round deferral and the lazy alignment test."""
 import ctypes as C, pathlib, subprocess
 import numpy as np
 import pytest
@@ -31,9 +32,12 @@ def test_fixed_point_equals_sequential(emul, w, h, seed, first_wave, nbins):
     hd = o.line_create(P)
     ref = o.lsd_detect(hd, img)
     o.line_destroy(hd)
-    for sched in (1, 2):                                   # two different random schedules
-        segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 6)()
-        rc = emul.emul_lsd_detect(ptr(img), w, h, C.byref(P), C.c_uint(seed * 10 + sched), first_wave, ptr(segs), 65536, C.byref(n), st)
+    carried = 0
+    for sched, defer, exact in ((1, 1, 0), (2, 1, 0), (3, 0, 0), (4, 1, 1)):     # different random schedules / options
+        segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 7)()
+        rc = emul.emul_lsd_detect(ptr(img), w, h, C.byref(P), C.c_uint(seed * 10 + sched), first_wave, defer, exact, ptr(segs), 65536, C.byref(n), st)
         assert rc == 0 and n.value == len(ref)
         assert np.array_equal(segs[:n.value], ref)
         assert st[1] >= st[0]                              # at least one round per wave
+        carried += st[6]
+    assert carried > 0                                     # the verify-instead-of-regrow path was exercised

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Per-round trace of k_lsd_grow_w on one 1280x720 frame (run on the GPU box with OLF_LSD_TRACE=1)."""
+"""Per-round trace of the LSD region-growing passes on one 1280x720 frame (run on the GPU box; sets OLF_LSD_TRACE=1)."""
 import os, sys, ctypes as C, pathlib, time
 os.environ["OLF_LSD_TRACE"] = "1"
 ROOT = pathlib.Path(__file__).resolve().parents[1]
@@ -24,7 +24,9 @@ if "-q" not in sys.argv:
         if n == 0: continue
         print("%5d %4d %6d %7.1f %7d %7d %8d %6d" % (r, w, n, ((t1 - t0) & 0x7fffffff) / 1e3, car, reg, px, mx))
 
+
 d = tr[200]
-print("big region: px %d steps %d pot %d pipelined %d | cycles issue[A] %d  wait+filter[B0] %d  decide[B1] %d  rotate[C] %d" % tuple(d))
-d = tr[201]
-print("  accepts %d | cycles eval %d  shfl %d  lane0(atomic+hash) %d  push %d" % tuple(d[:5]))
+if d[0]:
+    print("big region (OLF_LSD_PROFILE build): px %d steps %d prefetched %d | cycles/16: issue[A] %d  wait+eval %d  decide[B] %d  rotate[C] %d" % tuple(d[:7]))
+    d = tr[201]
+    print("  accepts %d | cycles/16: eval %d  ffs+shfl %d  leader(atomic+hash) %d  push %d" % tuple(d[:5]))
