@@ -92,15 +92,19 @@ def run_steps(pipes, frontends, track_fe, seq_imgs, poses, first, count, on_devi
     def worker(p):
         try:
             nat = pipes[p]
-            for k in range(p, count, P):
-                i = (first + k) % len(seq_imgs)
-                blk = nat.new_block()
+            B = nat.max_frames
+            nb = (count + B - 1) // B                       # batches of B consecutive frames, dealt round-robin to the rigs
+            for b in range(p, nb, P):
+                ks = list(range(b * B, min(count, (b + 1) * B)))
+                idx = [(first + k) % len(seq_imgs) for k in ks]
+                blks = [nat.new_block() for _ in ks]
                 if on_device:
-                    nat.process(dev_imgs[i][0], dev_imgs[i][1], blk, on_device=True)
+                    nat.process_batch([dev_imgs[i][0] for i in idx], [dev_imgs[i][1] for i in idx], blks, on_device=True)
                 else:
-                    nat.process(seq_imgs[i][0], seq_imgs[i][1], blk, on_device=False)
-                views[k] = nat.view(blk, poses[i])
-                done[k].set()
+                    nat.process_batch([seq_imgs[i][0] for i in idx], [seq_imgs[i][1] for i in idx], blks, on_device=False)
+                for k, i, blk in zip(ks, idx, blks):
+                    views[k] = nat.view(blk, poses[i])
+                    done[k].set()
         except Exception as e:       # noqa: BLE001
             errors.append(e)
             for d in done:
@@ -223,6 +227,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pipelines", type=int, default=0, help="concurrent stereo rigs per GPU (0 = auto)")
+    ap.add_argument("--batch", type=int, default=4, help="independent stereo frames per olf_frontend_process_batch call (1..4)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm-s", type=float, default=6.0, help="seconds of untimed work before the warm-up steps")
@@ -272,7 +277,8 @@ def main():
     api = olf.api(local)
     cam = CAMERAS[WORKLOAD["camera"]]
     # concurrent stereo rigs per GPU: the LSD grow phases are latency-bound, so frames in flight are what fills the GPU
-    P = args.pipelines or max(4, min(16, (os.cpu_count() or 16) // max(1, world)))   # measured optimum: 16 rigs x 2 streams per GPU
+    # a device has 32 hardware work queues: 2 streams per rig + the tracker's + the call-by-call extractors' (idle) must fit
+    P = args.pipelines or max(2, min(13, (os.cpu_count() or 16) // max(1, world)))
     sc, seq, poses = make_sequence(N_DISTINCT)
     # weak scaling: every rank runs the same number of frames of its own slice of the sequence
     shift = rank * 11
@@ -280,9 +286,9 @@ def main():
     dev_imgs = [(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()) for L, R in seq]
     dev_ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in dev_imgs]
     host_pinned = [(torch.from_numpy(L).pin_memory().numpy(), torch.from_numpy(R).pin_memory().numpy()) for L, R in seq]
-    fes = [FrontEnd(api, cam, WORKLOAD["nfeatures"], WORKLOAD["nlines"], WORKLOAD["min_line_length"]) for _ in range(P)]
-    # the call-by-call FrontEnd objects only serve the tracking matchers; extraction goes through the native rigs
-    pipes = [fe.native(WORKLOAD["nfeatures"], WORKLOAD["nlines"]) for fe in fes]
+    # the call-by-call FrontEnd object only serves the tracking matchers; extraction goes through the native rigs
+    fes = [FrontEnd(api, cam, WORKLOAD["nfeatures"], WORKLOAD["nlines"], WORKLOAD["min_line_length"])]
+    pipes = [fes[0].native(WORKLOAD["nfeatures"], WORKLOAD["nlines"], max_frames=args.batch) for _ in range(P)]
     gather_buf = None
     if world > 1:
         nbytes = int(pipes[0].off.total)
@@ -325,10 +331,10 @@ def main():
     stats8 = (ctypes.c_int * 8)()
     lib.olf_frontend_line.restype = ctypes.c_void_p
     for nat in pipes:
-        for eye in range(2):
+        for eye in range(1):                           # slot 0 carries the timing of the rig's batched chain
             lh = lib.olf_frontend_line(nat.handle, eye)
             if lh and lib.olf_line_last_stats(ctypes.c_void_p(lh), stats8) == 0:
-                grow_us.append(stats8[3])
+                grow_us.append(stats8[3] / max(stats8[4], 1))       # device time of the batched chain / images in it
     if rank == 0:
         peaks = {}
         try:
@@ -344,17 +350,17 @@ def main():
         fps_e2e = world * args.steps / (ms_e2e / 1000.0)
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": dict(WORKLOAD, pipelines_per_gpu=P, l2="inputs larger than L2: 80 distinct stereo pairs = 147 MB cycled",
+                "config": dict(WORKLOAD, pipelines_per_gpu=P, frames_per_call=args.batch, l2="inputs larger than L2: 80 distinct stereo pairs = 147 MB cycled",
                                host_cores=os.cpu_count(), per_frame={k: v / max(args.steps, 1) for k, v in st.items()}),
                 "clocks": clocks,
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 4 * 1280 * 720, "d2h_bytes_per_step": int(st_e2e["d2h"] / max(args.steps, 1)),
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "k_lsd_phase", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "k_lsd_grow (+scan, verify)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)", "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel_ms": grow_ms,
                              "algorithmic_bytes_per_launch": alg_bytes,
-                             "note": "latency-bound sequential region growing; HBM fraction is honest but not the limiter (see DESIGN.md)"}}
+                             "note": "k_lsd_scan/verify/grow chain, device time per image of a batched chain; latency-bound sequential region growing: the HBM fraction is honest but not the limiter (see DESIGN.md)"}}
         if not args.no_cpu_baseline and world == 1:
             frames = args.cpu_frames
             cfps, dt = cpu_reference(frames, [(a, b) for a, b in host_pinned[:N_BASE_FRAMES]], poses[:N_BASE_FRAMES], warm=1)

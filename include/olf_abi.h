@@ -198,7 +198,7 @@ int olf_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur /*
 
 /* ---- whole stereo frame: Frame::Frame(stereo+lines) (src/Frame.cc:136-221) ----------------------------------- */
 /* One rig = 2 ORB extractors + 2 line extractors on one device; olf_frontend_process runs ExtractORB(L|R) and
- * ExtractLine(L|R) on 4 host threads (src/Frame.cc:164-171), then ComputeStereoMatches and
+ * ExtractLine(L|R) on its own host threads (src/Frame.cc:164-171), then ComputeStereoMatches and
  * ComputeStereoMatches_Lines, and fills ONE fixed-capacity POD block (the unit the multi-GPU driver gathers). */
 typedef struct olf_frontend_params {
     int   nfeatures; float scale_factor; int nlevels; int ini_th_fast; int min_th_fast;   /* ORBextractor ctor */
@@ -230,9 +230,17 @@ void olf_frontend_destroy(olf_frontend* h);
 /* images: host pointers (on_device = 0) or device pointers (on_device = 1); result: host block of layout.total bytes */
 int  olf_frontend_process(olf_frontend* h, const uint8_t* img_l, const uint8_t* img_r, int width, int height, int stride,
                           int on_device, void* result);
-/* the extractors of the rig (e.g. for olf_orb_get_level) */
-olf_orb*  olf_frontend_orb(olf_frontend* h, int eye);
-olf_line* olf_frontend_line(olf_frontend* h, int eye);
+/* Batch entry (SURVEY 8b `olf_frame_batch_extract`, the unit of work of the multi-GPU driver, BASELINE config "8-frame
+ * batch"): `nframes` INDEPENDENT stereo frames (1..max_frames <= 4) through Frame::Frame at once.  The line extraction of
+ * all 2*nframes images runs as ONE chain of kernel launches (the LSD passes are latency-bound: a batch costs the latency of
+ * one image), so a rig keeps 2*max_frames images in flight on two CUDA streams.  Results are identical to nframes calls of
+ * olf_frontend_process; results[f] is the block of frame f. */
+olf_frontend* olf_frontend_create_batch(const olf_frontend_params* p, int device, int max_frames);
+int  olf_frontend_process_batch(olf_frontend* h, const uint8_t* const* img_l, const uint8_t* const* img_r, int nframes,
+                                int width, int height, int stride, int on_device, void* const* results);
+/* the extractors of the rig, slot = 2 * frame_in_batch + eye (e.g. for olf_orb_get_level) */
+olf_orb*  olf_frontend_orb(olf_frontend* h, int slot);
+olf_line* olf_frontend_line(olf_frontend* h, int slot);
 /* last-call statistics: out[0..1] LSD rounds L/R, out[2..3] LSD waves L/R */
 int  olf_line_last_stats(const olf_line* h, int* out8);
 

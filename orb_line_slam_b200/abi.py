@@ -245,9 +245,9 @@ class FrontEndApi:
         self.check(self.fn("frame_layout")(C.c_int(cap_points), C.c_int(cap_lines), C.byref(o)), "frame_layout")
         return o
 
-    def frontend_create(self, params: "FrontendParams"):
-        f = self.fn("frontend_create"); f.restype = C.c_void_p
-        h = f(C.byref(params), *self._dev)
+    def frontend_create(self, params: "FrontendParams", max_frames: int = 1):
+        f = self.fn("frontend_create_batch"); f.restype = C.c_void_p
+        h = f(C.byref(params), *self._dev, C.c_int(max_frames))
         if not h:
             self.check(OLF_ERR_INTERNAL, "frontend_create")
         return C.c_void_p(h)
@@ -263,6 +263,18 @@ class FrontEndApi:
             pl, pr = ptr(img_l), ptr(img_r)
         rc = self.fn("frontend_process")(h, pl, pr, C.c_int(width), C.c_int(height), C.c_int(stride), C.c_int(int(on_device)), ptr(result))
         self.check(rc, "frontend_process")
+
+    def frontend_process_batch(self, h, imgs_l, imgs_r, width, height, stride, on_device, results):
+        """imgs_l / imgs_r: lists of numpy uint8 images (host) or of integer device addresses; results: list of result blocks."""
+        n = len(imgs_l)
+        P = C.c_void_p * n
+        if on_device:
+            pl, pr = P(*[int(a) for a in imgs_l]), P(*[int(a) for a in imgs_r])
+        else:
+            pl, pr = P(*[a.ctypes.data for a in imgs_l]), P(*[a.ctypes.data for a in imgs_r])
+        pres = P(*[r.ctypes.data for r in results])
+        rc = self.fn("frontend_process_batch")(h, pl, pr, C.c_int(n), C.c_int(width), C.c_int(height), C.c_int(stride), C.c_int(int(on_device)), pres)
+        self.check(rc, "frontend_process_batch")
 
     def search_by_projection_last(self, args: SbpLastArgs, keep):
         n_last, n_cur = args.n_last, args.n_cur

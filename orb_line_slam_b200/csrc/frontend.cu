@@ -1,6 +1,6 @@
 // Whole-frame driver: the B200 replacement for Frame::Frame(stereo+lines) (reference src/Frame.cc:136-221).
-// Four persistent host threads play the role of the reference's four std::threads (src/Frame.cc:164-171): each owns one
-// extractor (own CUDA stream), so the left/right ORB and line pipelines overlap on the device.
+// Three persistent host threads play the role of the reference's four std::threads (src/Frame.cc:164-171): ORB of the left
+// images, ORB of the right images, and ONE batched chain of launches for the line extraction of all images of the call.
 #include "common.cuh"
 #include "orb.h"
 #include "line.h"
@@ -37,11 +37,14 @@ private:
 struct FrontendImpl {
     olf_frontend_params P;
     int device;
-    OrbImpl* orb[2] = {nullptr, nullptr};
-    LineImpl* line[2] = {nullptr, nullptr};
-    Worker* workers[4] = {nullptr, nullptr, nullptr, nullptr};
+    int max_frames = 1;                  // frames per olf_frontend_process_batch call
+    // slot 2*f + eye.  TWO streams per rig: every ORB extractor rides on the first one's stream (the stereo matchers too),
+    // every line extractor is driven through the first one's stream by ONE batched chain of launches (line_extract_batch)
+    std::vector<OrbImpl*> orb;
+    std::vector<LineImpl*> line;
+    Worker* workers[3] = {nullptr, nullptr, nullptr};   // ORB left images, ORB right images, all line images
     olf_frame_offsets off;
-    std::string err[4];
+    std::string err[3];
 };
 
 static uint64_t a64(uint64_t v) { return (v + 63) / 64 * 64; }
@@ -65,96 +68,121 @@ int frame_layout(int cap_p, int cap_l, olf_frame_offsets* o) {
     return OLF_OK;
 }
 
-FrontendImpl* frontend_create(const olf_frontend_params* p, int device) {
-    if (!p || p->cap_points < p->nfeatures || p->cap_lines < 0) { set_last_error("olf_frontend_create: bad arguments"); return nullptr; }
+FrontendImpl* frontend_create(const olf_frontend_params* p, int device, int max_frames) {
+    if (!p || p->cap_points < p->nfeatures || p->cap_lines < 0 || max_frames < 1 || 2 * max_frames > 8) {
+        set_last_error("olf_frontend_create: bad arguments (1..4 frames per batch)"); return nullptr;
+    }
     FrontendImpl* h = new FrontendImpl();
-    h->P = *p; h->device = device;
+    h->P = *p; h->device = device; h->max_frames = max_frames;
     frame_layout(p->cap_points, p->cap_lines, &h->off);
-    const bool share = getenv("OLF_RIG_STREAMS") == nullptr || atoi(getenv("OLF_RIG_STREAMS")) <= 2;
-    for (int e = 0; e < 2; ++e) {
-        if (p->has_lines) h->line[e] = line_create(&p->line, device);
-        // each eye's ORB work rides on that eye's line stream (2 streams per rig); without lines the two eyes share one
-        cudaStream_t ext = (p->has_lines && share) ? line_stream(h->line[e]) : nullptr;
-        if (!(p->has_lines && !h->line[e]))
-            h->orb[e] = orb_create(p->nfeatures, p->scale_factor, p->nlevels, p->ini_th_fast, p->min_th_fast, device, ext);
-        if (!h->orb[e] || (p->has_lines && !h->line[e])) {
-            for (int k = 0; k < 2; ++k) { orb_destroy(h->orb[k]); line_destroy(h->line[k]); }
-            delete h; return nullptr;
+    bool ok = true;
+    for (int k = 0; k < 2 * max_frames && ok; ++k) {
+        if (p->has_lines) { h->line.push_back(line_create(&p->line, device, h->line.empty() ? nullptr : line_stream(h->line[0]))); ok = h->line.back() != nullptr; }
+        if (ok) {
+            h->orb.push_back(orb_create(p->nfeatures, p->scale_factor, p->nlevels, p->ini_th_fast, p->min_th_fast, device,
+                                        h->orb.empty() ? nullptr : orb_stream(h->orb[0])));
+            ok = h->orb.back() != nullptr;
         }
     }
-    for (int i = 0; i < 4; ++i) h->workers[i] = new Worker();
+    if (!ok) {
+        const std::string e = olf_last_error();
+        for (size_t k = h->orb.size(); k-- > 0;) orb_destroy(h->orb[k]);
+        for (size_t k = h->line.size(); k-- > 0;) line_destroy(h->line[k]);
+        delete h; set_last_error(e); return nullptr;
+    }
+    for (int i = 0; i < 3; ++i) h->workers[i] = new Worker();
     return h;
 }
 void frontend_destroy(FrontendImpl* h) {
     if (!h) return;
-    for (int i = 0; i < 4; ++i) delete h->workers[i];
-    for (int e = 0; e < 2; ++e) orb_destroy(h->orb[e]);    // before the line extractors whose streams they may borrow
-    for (int e = 0; e < 2; ++e) line_destroy(h->line[e]);
+    for (int i = 0; i < 3; ++i) delete h->workers[i];
+    for (size_t k = h->orb.size(); k-- > 0;) orb_destroy(h->orb[k]);     // the borrowers before the owner of the stream
+    for (size_t k = h->line.size(); k-- > 0;) line_destroy(h->line[k]);
     delete h;
 }
 
-int frontend_process(FrontendImpl* h, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride, int on_device, void* result) {
-    if (!h || !img_l || !img_r || !result || w <= 0 || hgt <= 0 || stride < w) { set_last_error("olf_frontend_process: bad arguments"); return OLF_ERR_ARG; }
-    uint8_t* base = (uint8_t*)result;
-    olf_frame_header* hd = (olf_frame_header*)base;
-    memset(hd, 0, sizeof(*hd));
-    hd->cap_points = h->P.cap_points; hd->cap_lines = h->P.cap_lines;
+// Frame::Frame(stereo+lines) (src/Frame.cc:136-221) for `nframes` independent stereo frames at once
+int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const uint8_t* const* img_r, int nframes, int w, int hgt, int stride,
+                           int on_device, void* const* results) {
+    if (!h || !img_l || !img_r || !results || nframes < 1 || nframes > h->max_frames || w <= 0 || hgt <= 0 || stride < w) {
+        set_last_error("olf_frontend_process: bad arguments"); return OLF_ERR_ARG;
+    }
+    for (int f = 0; f < nframes; ++f) if (!img_l[f] || !img_r[f] || !results[f]) { set_last_error("olf_frontend_process: bad arguments"); return OLF_ERR_ARG; }
     const olf_frame_offsets& o = h->off;
-    olf_keypoint* kps[2] = {(olf_keypoint*)(base + o.kps_l), (olf_keypoint*)(base + o.kps_r)};
-    uint8_t* desc[2] = {base + o.desc_l, base + o.desc_r};
-    olf_keyline* kls[2] = {(olf_keyline*)(base + o.kls_l), (olf_keyline*)(base + o.kls_r)};
-    uint8_t* ldesc[2] = {base + o.ldesc_l, base + o.ldesc_r};
-    const uint8_t* img[2] = {img_l, img_r};
-    int n[2] = {0, 0}, m[2] = {0, 0};
-    // ExtractORB(0|1), ExtractLine(0|1) on four threads (src/Frame.cc:164-171).  Per eye the two extractors share a stream:
-    // the line thread enqueues its long LSD chain only after the ORB thread has enqueued (and marked) its pre-quadtree
-    // kernels, so the ORB host work (quadtree) overlaps the LSD phases instead of queueing behind them.
-    struct Gate { std::mutex m; std::condition_variable cv; bool open = false; } gate[2];
-    std::function<void()> open_gate[2];
-    for (int e = 0; e < 2; ++e) {
-        Gate* g = &gate[e];
-        open_gate[e] = [g]() { { std::lock_guard<std::mutex> l(g->m); g->open = true; } g->cv.notify_all(); };
-        const std::function<void()>* hook = &open_gate[e];
-        h->workers[e]->submit([=, &n, &h]() {
-            const int rc = orb_extract(h->orb[e], img[e], w, hgt, stride, on_device != 0, kps[e], desc[e], h->P.cap_points, &n[e], hook);
-            (*hook)();                                     // idempotent: covers the early-return paths
-            if (rc) h->err[e] = olf_last_error();
+    const int nimg = 2 * nframes;
+    std::vector<int> n(nimg, 0), m(nimg, 0);
+    std::vector<const uint8_t*> img(nimg);
+    std::vector<olf_keypoint*> kps(nimg); std::vector<uint8_t*> desc(nimg), ldesc(nimg); std::vector<olf_keyline*> kls(nimg);
+    for (int f = 0; f < nframes; ++f) {
+        uint8_t* base = (uint8_t*)results[f];
+        olf_frame_header* hd = (olf_frame_header*)base;
+        memset(hd, 0, sizeof(*hd));
+        hd->cap_points = h->P.cap_points; hd->cap_lines = h->P.cap_lines;
+        img[2 * f] = img_l[f]; img[2 * f + 1] = img_r[f];
+        kps[2 * f] = (olf_keypoint*)(base + o.kps_l); kps[2 * f + 1] = (olf_keypoint*)(base + o.kps_r);
+        desc[2 * f] = base + o.desc_l; desc[2 * f + 1] = base + o.desc_r;
+        kls[2 * f] = (olf_keyline*)(base + o.kls_l); kls[2 * f + 1] = (olf_keyline*)(base + o.kls_r);
+        ldesc[2 * f] = base + o.ldesc_l; ldesc[2 * f + 1] = base + o.ldesc_r;
+    }
+    // ExtractORB(0|1) of every frame on two threads (left images, right images), ExtractLine(0|1) of every frame as one
+    // batched chain on a third (the reference's four threads, src/Frame.cc:164-171, regrouped by kind of work)
+    for (int e = 0; e < 2; ++e)
+        h->workers[e]->submit([=, &n, &kps, &desc, &img]() {
+            for (int f = 0; f < nframes; ++f) {
+                const int k = 2 * f + e;
+                const int rc = orb_extract(h->orb[k], img[k], w, hgt, stride, on_device != 0, kps[k], desc[k], h->P.cap_points, &n[k]);
+                if (rc) { h->err[e] = olf_last_error(); return rc; }
+            }
+            return (int)OLF_OK;
+        });
+    if (h->P.has_lines)
+        h->workers[2]->submit([=, &m, &kls, &ldesc, &img]() {
+            const int rc = line_extract_batch(h->line.data(), nimg, img.data(), w, hgt, stride, on_device != 0, kls.data(), ldesc.data(), h->P.cap_lines, m.data());
+            if (rc) h->err[2] = olf_last_error();
             return rc;
         });
-        if (h->P.has_lines)
-            h->workers[2 + e]->submit([=, &m, &h]() {
-                { std::unique_lock<std::mutex> l(g->m); g->cv.wait(l, [g] { return g->open; }); }
-                const int rc = line_extract(h->line[e], img[e], w, hgt, stride, on_device != 0, kls[e], ldesc[e], h->P.cap_lines, &m[e]);
-                if (rc) h->err[2 + e] = olf_last_error();
-                return rc;
-            });
-    }
     int rc = OLF_OK;
-    for (int i = 0; i < 4; ++i) {
-        if (i >= 2 && !h->P.has_lines) break;
+    for (int i = 0; i < 3; ++i) {
+        if (i == 2 && !h->P.has_lines) break;
         const int r = h->workers[i]->wait();
         if (r && !rc) { rc = r; set_last_error(h->err[i]); }
     }
-    hd->n_l = n[0]; hd->n_r = n[1]; hd->m_l = m[0]; hd->m_r = m[1];
-    if (!rc && n[0] > 0)       // if(mvKeys.empty()) return;  (src/Frame.cc:176)
-        rc = stereo_points(h->orb[0], h->orb[1], kps[0], desc[0], n[0], kps[1], desc[1], n[1], h->P.cam.bf, h->P.cam.fx,
-                           (float*)(base + o.u_right), (float*)(base + o.depth));
-    if (!rc && n[0] > 0 && h->P.has_lines)
-        rc = stereo_lines(kls[0], ldesc[0], m[0], kls[1], ldesc[1], m[1], w, hgt, &h->P.line_match,
-                          (int*)(base + o.lmatch), (float*)(base + o.ldisp), (double*)(base + o.lle), h->device);
-    hd->status = rc;
+    match_use_stream(orb_stream(h->orb[0]));
+    for (int f = 0; f < nframes; ++f) {
+        uint8_t* base = (uint8_t*)results[f];
+        olf_frame_header* hd = (olf_frame_header*)base;
+        const int kl = 2 * f, kr = 2 * f + 1;
+        hd->n_l = n[kl]; hd->n_r = n[kr]; hd->m_l = m[kl]; hd->m_r = m[kr];
+        if (!rc && n[kl] > 0)       // if(mvKeys.empty()) return;  (src/Frame.cc:176)
+            rc = stereo_points(h->orb[kl], h->orb[kr], kps[kl], desc[kl], n[kl], kps[kr], desc[kr], n[kr], h->P.cam.bf, h->P.cam.fx,
+                               (float*)(base + o.u_right), (float*)(base + o.depth));
+        if (!rc && n[kl] > 0 && h->P.has_lines)
+            rc = stereo_lines(kls[kl], ldesc[kl], m[kl], kls[kr], ldesc[kr], m[kr], w, hgt, &h->P.line_match,
+                              (int*)(base + o.lmatch), (float*)(base + o.ldisp), (double*)(base + o.lle), h->device);
+        hd->status = rc;
+    }
+    match_use_stream(nullptr);
     return rc;
+}
+int frontend_process(FrontendImpl* h, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride, int on_device, void* result) {
+    if (!img_l || !img_r || !result) { set_last_error("olf_frontend_process: bad arguments"); return OLF_ERR_ARG; }
+    return frontend_process_batch(h, &img_l, &img_r, 1, w, hgt, stride, on_device, &result);
 }
 
 }  // namespace olf
 using namespace olf;
 extern "C" {
 int olf_frame_layout(int cap_points, int cap_lines, olf_frame_offsets* out) { return frame_layout(cap_points, cap_lines, out); }
-olf_frontend* olf_frontend_create(const olf_frontend_params* p, int device) { return (olf_frontend*)frontend_create(p, device); }
+olf_frontend* olf_frontend_create(const olf_frontend_params* p, int device) { return (olf_frontend*)frontend_create(p, device, 1); }
+olf_frontend* olf_frontend_create_batch(const olf_frontend_params* p, int device, int max_frames) { return (olf_frontend*)frontend_create(p, device, max_frames); }
+int olf_frontend_process_batch(olf_frontend* h, const uint8_t* const* img_l, const uint8_t* const* img_r, int nframes, int width, int height, int stride,
+                               int on_device, void* const* results) {
+    return frontend_process_batch((FrontendImpl*)h, img_l, img_r, nframes, width, height, stride, on_device, results);
+}
 void olf_frontend_destroy(olf_frontend* h) { frontend_destroy((FrontendImpl*)h); }
 int olf_frontend_process(olf_frontend* h, const uint8_t* img_l, const uint8_t* img_r, int width, int height, int stride, int on_device, void* result) {
     return frontend_process((FrontendImpl*)h, img_l, img_r, width, height, stride, on_device, result);
 }
-olf_orb* olf_frontend_orb(olf_frontend* h, int eye) { return h && eye >= 0 && eye < 2 ? (olf_orb*)((FrontendImpl*)h)->orb[eye] : nullptr; }
-olf_line* olf_frontend_line(olf_frontend* h, int eye) { return h && eye >= 0 && eye < 2 ? (olf_line*)((FrontendImpl*)h)->line[eye] : nullptr; }
+olf_orb* olf_frontend_orb(olf_frontend* h, int eye) { return h && eye >= 0 && eye < (int)((FrontendImpl*)h)->orb.size() ? (olf_orb*)((FrontendImpl*)h)->orb[eye] : nullptr; }
+olf_line* olf_frontend_line(olf_frontend* h, int eye) { return h && eye >= 0 && eye < (int)((FrontendImpl*)h)->line.size() ? (olf_line*)((FrontendImpl*)h)->line[eye] : nullptr; }
 }

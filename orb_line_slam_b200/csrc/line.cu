@@ -152,6 +152,20 @@ struct GrowDev {
     int defer;                   // first round of a wave: seeds with a live higher-priority aligned neighbour wait
     int* dbg;                    // optional per-round trace (OLF_LSD_TRACE)
 };
+// One launch serves a BATCH of images (the two eyes of a stereo frame, several frames): blockIdx.y selects the image, every
+// image has its own state machine.  The passes are latency-bound with small grids, so a batch costs one chain of launches
+// on one stream instead of one chain per image -- that is what keeps many frames in flight within the 32 hardware queues.
+#define LSD_MAX_BATCH 8
+struct GrowBatch { GrowDev d[LSD_MAX_BATCH]; PhaseState* st[LSD_MAX_BATCH]; };
+__device__ __forceinline__ const GrowDev& batch_image(const GrowBatch& B, GrowDev* sh, PhaseState*& st) {
+    // block-uniform copy of this image's descriptor into shared memory (the by-value batch lives in parameter space)
+    const int* src = reinterpret_cast<const int*>(&B.d[blockIdx.y]);
+    int* dst = reinterpret_cast<int*>(sh);
+    for (int k = threadIdx.x; k < (int)(sizeof(GrowDev) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
+    st = B.st[blockIdx.y];
+    __syncthreads();
+    return *sh;
+}
 __device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
     const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
     return ((u64)hi << 32) | lo;
@@ -170,7 +184,10 @@ __device__ __forceinline__ void wl_append(bool take, int value, int* __restrict_
 }
 
 // pass 1: every seed of the wave -- dead or alive (+ first-round deferral); alive seeds go to work list 1
-__global__ void __launch_bounds__(256) k_lsd_scan(const GrowDev D, PhaseState* __restrict__ st) {
+__global__ void __launch_bounds__(256) k_lsd_scan(const __grid_constant__ GrowBatch B) {
+    __shared__ GrowDev s_dev;
+    PhaseState* st;
+    const GrowDev& D = batch_image(B, &s_dev, st);
     if (st->done || st->mode != 0) return;
     const int wv = st->wave;
     if (wv >= D.plan->n_waves) return;
@@ -256,7 +273,10 @@ __device__ bool verify_long_warp(const GrowCtx& C, unsigned round, int i, int la
 // pass 2: every alive seed claims its pixel, then is carried over (verified) or sent to work list 2;
 // in finalise mode: every alive seed of the converged wave is stamped for good
 #define VERIFY_LONG 48
-__global__ void __launch_bounds__(128) k_lsd_verify(const GrowDev D, PhaseState* __restrict__ st) {
+__global__ void __launch_bounds__(128) k_lsd_verify(const __grid_constant__ GrowBatch B) {
+    __shared__ GrowDev s_dev;
+    PhaseState* st;
+    const GrowDev& D = batch_image(B, &s_dev, st);
     if (st->done) return;
     const int wv = st->wave;
     if (wv >= D.plan->n_waves) return;
@@ -315,9 +335,12 @@ __global__ void __launch_bounds__(128) k_lsd_verify(const GrowDev D, PhaseState*
 struct GrowSmem { float nb[8][3][GROW_THREADS]; unsigned ring[GROW_RING][GROW_THREADS]; };
 
 // The last block to finish advances the wave / round state machine.
-__global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const GrowDev D, PhaseState* __restrict__ st) {
+__global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant__ GrowBatch B) {
     __shared__ GrowSmem sm;
+    __shared__ GrowDev s_dev;
     __shared__ bool s_last;
+    PhaseState* st;
+    const GrowDev& D = batch_image(B, &s_dev, st);
     if (st->done) return;
     const int wv = st->wave; const unsigned round = st->round; const int mode = st->mode;
     if (wv >= D.plan->n_waves) {                                   // no seeds at all (flat image)
@@ -414,39 +437,67 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const GrowDev D, Phas
                 if (px == 0) vm &= ~0x29u;
                 if (px == W - 1) vm &= ~0x94u;
                 const PxRec* const base = C.px + p;
-                // all sixteen loads are issued before anything consumes them (one memory round trip per queue entry)
+                // all sixteen loads are issued before anything consumes them (one memory round trip per queue entry): ONE asm
+                // block, so that the assembler cannot trade the memory-level parallelism for registers; neighbours outside
+                // the image read the entry's own record instead (always valid, and "already mine")
                 u64 c0[8], c1[8]; float4 lo[8];
+                const PxRec* ra[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int nk = k < 4 ? k : k + 1;
-                    const PxRec* r = base + ((nk / 3) - 1) * W + ((nk % 3) - 1);
-                    c0[k] = 0; c1[k] = 0;
-                    if ((vm >> k) & 1u) ld_claims(r, c0[k], c1[k]);
+                    ra[k] = ((vm >> k) & 1u) ? base + ((nk / 3) - 1) * W + ((nk % 3) - 1) : base;
                 }
+                asm volatile(
+                    "ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%16];\n\t"
+                    "ld.relaxed.gpu.global.v2.u64 {%2, %3}, [%17];\n\t"
+                    "ld.relaxed.gpu.global.v2.u64 {%4, %5}, [%18];\n\t"
+                    "ld.relaxed.gpu.global.v2.u64 {%6, %7}, [%19];\n\t"
+                    "ld.relaxed.gpu.global.v2.u64 {%8, %9}, [%20];\n\t"
+                    "ld.relaxed.gpu.global.v2.u64 {%10, %11}, [%21];\n\t"
+                    "ld.relaxed.gpu.global.v2.u64 {%12, %13}, [%22];\n\t"
+                    "ld.relaxed.gpu.global.v2.u64 {%14, %15}, [%23];"
+                    : "=l"(c0[0]), "=l"(c1[0]), "=l"(c0[1]), "=l"(c1[1]), "=l"(c0[2]), "=l"(c1[2]), "=l"(c0[3]), "=l"(c1[3]),
+                      "=l"(c0[4]), "=l"(c1[4]), "=l"(c0[5]), "=l"(c1[5]), "=l"(c0[6]), "=l"(c1[6]), "=l"(c0[7]), "=l"(c1[7])
+                    : "l"(ra[0]), "l"(ra[1]), "l"(ra[2]), "l"(ra[3]), "l"(ra[4]), "l"(ra[5]), "l"(ra[6]), "l"(ra[7])
+                    : "memory");
+                asm volatile(
+                    "ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%32+16];\n\t"
+                    "ld.global.cg.v4.f32 {%4, %5, %6, %7}, [%33+16];\n\t"
+                    "ld.global.cg.v4.f32 {%8, %9, %10, %11}, [%34+16];\n\t"
+                    "ld.global.cg.v4.f32 {%12, %13, %14, %15}, [%35+16];\n\t"
+                    "ld.global.cg.v4.f32 {%16, %17, %18, %19}, [%36+16];\n\t"
+                    "ld.global.cg.v4.f32 {%20, %21, %22, %23}, [%37+16];\n\t"
+                    "ld.global.cg.v4.f32 {%24, %25, %26, %27}, [%38+16];\n\t"
+                    "ld.global.cg.v4.f32 {%28, %29, %30, %31}, [%39+16];"
+                    : "=f"(lo[0].x), "=f"(lo[0].y), "=f"(lo[0].z), "=f"(lo[0].w), "=f"(lo[1].x), "=f"(lo[1].y), "=f"(lo[1].z), "=f"(lo[1].w),
+                      "=f"(lo[2].x), "=f"(lo[2].y), "=f"(lo[2].z), "=f"(lo[2].w), "=f"(lo[3].x), "=f"(lo[3].y), "=f"(lo[3].z), "=f"(lo[3].w),
+                      "=f"(lo[4].x), "=f"(lo[4].y), "=f"(lo[4].z), "=f"(lo[4].w), "=f"(lo[5].x), "=f"(lo[5].y), "=f"(lo[5].z), "=f"(lo[5].w),
+                      "=f"(lo[6].x), "=f"(lo[6].y), "=f"(lo[6].z), "=f"(lo[6].w), "=f"(lo[7].x), "=f"(lo[7].y), "=f"(lo[7].z), "=f"(lo[7].w)
+                    : "l"(ra[0]), "l"(ra[1]), "l"(ra[2]), "l"(ra[3]), "l"(ra[4]), "l"(ra[5]), "l"(ra[6]), "l"(ra[7])
+                    : "memory");
+                // Scheduling guard: the keys every flag is compared with depend on ALL sixteen loads, so no consumer can be
+                // scheduled between the loads (the assembler otherwise serialises them to save registers: 5 memory round
+                // trips per entry instead of 1).  The guard never fires: bits 63..56 of a claim are 0x00 or 0xFF, bits 31..10
+                // of a bin number are zero.
+                unsigned acc_a = 0, acc_b = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int nk = k < 4 ? k : k + 1;
-                    const PxRec* r = base + ((nk / 3) - 1) * W + ((nk % 3) - 1);
-                    lo[k] = make_float4(-1.f, 0.f, 0.f, 0.f);
-#ifdef OLF_EXP_WEAK
-                    if ((vm >> k) & 1u) lo[k] = __ldg(reinterpret_cast<const float4*>(r) + 1);
-#else
-                    if ((vm >> k) & 1u) lo[k] = __ldcg(reinterpret_cast<const float4*>(r) + 1);
-#endif
-                }
+                for (int k = 0; k < 8; ++k) { acc_a |= (unsigned)(c0[k] >> 32); acc_b |= __float_as_uint(lo[k].w); }
+                const bool never = ((acc_a >> 24) == 0x55u) || ((acc_b >> 16) == 0x55u);
+                const u64 mine_g = never ? 0ull : mine, mine_prev_g = never ? ~0ull : mine_prev;
                 unsigned m_free = 0, m_held = 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const u64 ep = cur ? c0[k] : c1[k], ec = cur ? c1[k] : c0[k];
                     // free: neither final nor held by a higher-priority seed nor already mine (NOTDEF pixels are born final)
-                    const bool fre = (ep >= mine_prev) && (ec > mine);
+                    const bool fre = (ep >= mine_prev_g) && (ec > mine_g);
                     const bool fin = ((unsigned)(ep >> 40) == 0u) || ((unsigned)(ec >> 40) == 0u);
-                    const bool hld = !fre && !fin && (ec != mine);
+                    const bool hld = !fre && !fin && (ec != mine_g);
                     m_free |= (unsigned)fre << k;
                     m_held |= (unsigned)hld << k;
                 }
+                m_free &= vm; m_held &= vm;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { sm.nb[k][0][t] = lo[k].x; sm.nb[k][1][t] = lo[k].y; sm.nb[k][2][t] = lo[k].z; }
+                for (int k = 0; k < 8; ++k) { sm.nb[k][0][t] = lo[k].x; sm.nb[k][1][t] = lo[k].y; sm.nb[k][2][t] = never ? 0.f : lo[k].z; }
                 // the surviving candidates, in scan order; the region angle changes after every accepted pixel
                 unsigned m = m_free | m_held;
                 while (m) {
@@ -769,7 +820,7 @@ static const unsigned char LBD_COMB[64] = {0,1, 0,2, 0,3, 0,4, 0,5, 0,6, 1,2, 1,
 struct LineImpl {
     int device = 0;
     olf_line_params P;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; bool owns_stream = true;
     // derived LSD constants
     double prec, rho; int n2_thresh; int blur_k; int blur_q[4];
     // size-dependent
@@ -794,6 +845,7 @@ struct LineImpl {
     DevBuf<int> dbg;
     unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
     int scan_blocks = 0, verify_blocks = 0, grow_blocks = 0;
+    PinBuf<PhaseState> phase_init;
     PinBuf<RectRec> rect_host; PinBuf<double2> dir_host; PinBuf<float4> seg_host; PinBuf<int> status_host; PinBuf<unsigned> nreg_host;
     // LBD
     DevBuf<short2_t> grad;
@@ -827,7 +879,7 @@ static void gauss_kernel_q8(int n, double sigma, int* q) {                      
     q[n / 2] = 256 - acc;
 }
 
-LineImpl* line_create(const olf_line_params* p, int device) {
+LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_stream) {
     if (!p || p->lsd_refine != 0 || p->lsd_n_bins < 1 || p->lsd_n_bins > 1024 || p->lsd_scale <= 0 || p->lsd_ang_th <= 0 || p->lsd_ang_th >= 180) {
         set_last_error("olf_line_create: unsupported parameters (refine must be 0, n_bins <= 1024)"); return nullptr;
     }
@@ -870,7 +922,11 @@ LineImpl* line_create(const olf_line_params* p, int device) {
         u = (nb * wb - 1) / 2; sigma = u; inv = -1 / (2 * sigma * sigma);
         for (int i = 0; i < nb * wb; i++) { const double dis = i - u; gG[i] = (float)std::exp(dis * dis * inv); }
     }
-    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    // ext_stream: a rig drives all its line extractors through one stream (line_extract_batch); streams are a scarce
+    // resource (32 hardware work queues per device), so the borrowers do not create their own
+    bool ok = true;
+    if (ext_stream) { h->stream = ext_stream; h->owns_stream = false; }
+    else ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_grow0) == cudaSuccess && cudaEventCreate(&h->ev_grow1) == cudaSuccess;
     ok = ok && h->tab_seed.ensure(ts.size()) == OLF_OK && h->tab_acc.ensure(ta.size()) == OLF_OK;
     ok = ok && cudaMemcpy(h->tab_seed.p, ts.data(), ts.size() * sizeof(float2_t), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -883,7 +939,7 @@ LineImpl* line_create(const olf_line_params* p, int device) {
     if (const char* e = getenv("OLF_LSD_FIRST_WAVE")) h->first_wave = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_WAVE_GROWTH")) h->wave_growth = std::max(2, atoi(e));
     h->trace = getenv("OLF_LSD_TRACE") != nullptr;                // per-round trace of the grow kernel (tools/lsd_trace.py)
-    ok = ok && h->phase.ensure(1) == OLF_OK;
+    ok = ok && h->phase.ensure(1) == OLF_OK && h->phase_init.ensure(1) == OLF_OK;
     if (const char* e = getenv("OLF_LSD_PHASE_BATCH")) h->phase_batch = std::max(4, atoi(e));
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
     // grids of the three region-growing passes (one thread per seed; see k_lsd_scan / k_lsd_verify / k_lsd_grow)
@@ -896,7 +952,7 @@ LineImpl* line_create(const olf_line_params* p, int device) {
 void line_destroy(LineImpl* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->stream && h->owns_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     if (h->ev_grow0) cudaEventDestroy(h->ev_grow0);
     if (h->ev_grow1) cudaEventDestroy(h->ev_grow1);
     h->img_stage.release(); h->img.release(); h->blurred.release(); h->scaled.release(); h->lbd_blur.release(); h->coef.release();
@@ -904,7 +960,7 @@ void line_destroy(LineImpl* h) {
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
     h->final_pool.release(); h->srec0.release(); h->srec1.release(); h->regang.release(); h->plan.release(); h->regs.release();
     h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release();
-    h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release();
+    h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release(); h->phase_init.release();
     h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
 }
@@ -953,20 +1009,19 @@ static LevelTable single_level(int w, int hgt, int pitch) {
     return T;
 }
 
-static int line_upload(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device) {
+static int line_upload(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, cudaStream_t s) {
     int rc = line_ensure_size(h, w, hgt);
     if (rc) return rc;
-    if (on_device) OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, img, stride, w, hgt, cudaMemcpyDeviceToDevice, h->stream));
+    if (on_device) OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, img, stride, w, hgt, cudaMemcpyDeviceToDevice, s));
     else {
         for (int y = 0; y < hgt; ++y) memcpy(h->img_stage.p + (size_t)y * w, img + (size_t)y * stride, w);
-        OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, h->img_stage.p, w, w, hgt, cudaMemcpyHostToDevice, h->stream));
+        OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, h->img_stage.p, w, w, hgt, cudaMemcpyHostToDevice, s));
     }
     return OLF_OK;
 }
 
-// LSD on the uploaded image; returns segments sorted in seed order (host vector)
-static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
-    cudaStream_t s = h->stream;
+// LSD on the uploaded image, stage 1: everything before region growing + this image's descriptor for the batched passes
+static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D) {
     const int w = h->img_w, hgt = h->img_h, W = h->W, H = h->H, S = h->S;
     const uint8_t* work = h->img.p; int wp = h->ipitch;
     if (h->blur_k) {
@@ -991,7 +1046,7 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
     k_lsd_plan<<<1, 1024, 0, s>>>(h->hist.p, nb, h->first_wave, h->wave_growth, h->bin_start.p, h->cursor.p, h->plan.p);
     k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p, h->px.p);
-    GrowDev D;
+    count_launches((h->blur_k ? 2 : 0) + 4);
     D.C.W = W; D.C.H = H; D.C.px = h->px.p; D.C.dabc = h->dabc.p; D.C.tab_seed = h->tab_seed.p;
     D.C.pool = h->pool.p; D.C.pool_ctr = h->ctrs.p; D.C.pool_chunks = h->pool_chunks;
     D.C.srec[0] = h->srec0.p; D.C.srec[1] = h->srec1.p; D.C.regang = h->regang.p;
@@ -1009,61 +1064,78 @@ static int lsd_run(LineImpl* h, std::vector<float4>& segs) {
     D.defer = getenv("OLF_LSD_NO_DEFER") ? 0 : 1;
     D.dbg = h->trace ? h->dbg.p : nullptr;
     if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
-    OLF_CUDA(cudaEventRecord(h->ev_grow0, s));
-    auto enqueue_phases = [&](int n) {
-        for (int k = 0; k < n; ++k) {
-            k_lsd_scan<<<h->scan_blocks, 256, 0, s>>>(D, h->phase.p);
-            k_lsd_verify<<<h->verify_blocks, 128, 0, s>>>(D, h->phase.p);
-            k_lsd_grow<<<h->grow_blocks, GROW_THREADS, 0, s>>>(D, h->phase.p);
-        }
-        count_launches(3 * n);
-    };
-    {
-        PhaseState init; memset(&init, 0, sizeof(init)); init.round = 1; init.wave_first_round = 1;
-        OLF_CUDA(cudaMemcpyAsync(h->phase.p, &init, sizeof(init), cudaMemcpyHostToDevice, s));
-        enqueue_phases(h->phase_batch);
-    }
-    OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
-    count_launches((h->blur_k ? 2 : 0) + 6);
-    k_lsd_rect_a<<<296, 256, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
+    h->phase_init.p[0] = PhaseState{}; h->phase_init.p[0].round = 1; h->phase_init.p[0].wave_first_round = 1;
+    OLF_CUDA(cudaMemcpyAsync(h->phase.p, h->phase_init.p, sizeof(PhaseState), cudaMemcpyHostToDevice, s));
+    OLF_CUDA(cudaGetLastError());
+    return OLF_OK;
+}
+// stage 3 (after the passes): first half of the rectangle fit + the counters the host needs
+static int lsd_enqueue_rect_a(LineImpl* h, cudaStream_t s) {
+    k_lsd_rect_a<<<296, 256, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, h->W, h->prec, h->rect_host.d);
+    count_launches(1);
     OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(stream_sync(s));
-    {
-        // the fixed batch of phase launches normally covers all rounds; otherwise keep going (rare)
-        for (int guard = 0; guard < 400; ++guard) {
-            if (h->status_host.p[3] || h->status_host.p[0]) break;
-            enqueue_phases(h->phase_batch);
-            count_launches(1);
-            OLF_CUDA(cudaEventRecord(h->ev_grow1, s));
-            k_lsd_rect_a<<<296, 256, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, W, h->prec, h->rect_host.d);
-            OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-            OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-            OLF_CUDA(stream_sync(s));
+    return OLF_OK;
+}
+
+// LSD of a batch of uploaded images on ONE stream; segments of image k (seed order) -> segs[k]
+static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector<float4>* segs) {
+    if (n < 1 || n > LSD_MAX_BATCH) { set_last_error("LSD batch size out of range"); return OLF_ERR_ARG; }
+    GrowBatch B; memset(&B, 0, sizeof(B));
+    int rc;
+    for (int k = 0; k < n; ++k) { if ((rc = lsd_enqueue_pre(hs[k], s, B.d[k]))) return rc; B.st[k] = hs[k]->phase.p; }
+    LineImpl* h0 = hs[0];
+    OLF_CUDA(cudaEventRecord(h0->ev_grow0, s));
+    auto enqueue_phases = [&](int count) {
+        for (int k = 0; k < count; ++k) {
+            k_lsd_scan<<<dim3(h0->scan_blocks, n), 256, 0, s>>>(B);
+            k_lsd_verify<<<dim3(h0->verify_blocks, n), 128, 0, s>>>(B);
+            k_lsd_grow<<<dim3(h0->grow_blocks, n), GROW_THREADS, 0, s>>>(B);
         }
+        count_launches(3 * count);
+    };
+    // the wave / round state machines run on the device; a fixed batch of launches normally covers all rounds of all
+    // images (launches after an image is done return at once), otherwise keep going (rare)
+    for (int guard = 0; guard < 400; ++guard) {
+        enqueue_phases(h0->phase_batch);
+        OLF_CUDA(cudaEventRecord(h0->ev_grow1, s));
+        for (int k = 0; k < n; ++k) if ((rc = lsd_enqueue_rect_a(hs[k], s))) return rc;
+        OLF_CUDA(stream_sync(s));
+        bool all = true;
+        for (int k = 0; k < n; ++k) all = all && (hs[k]->status_host.p[3] || hs[k]->status_host.p[0]);
+        if (all) break;
     }
-    h->last_stats[0] = h->status_host.p[1]; h->last_stats[1] = h->status_host.p[2];
-    { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev_grow0, h->ev_grow1) == cudaSuccess) h->last_stats[3] = (int)(ms * 1000.f); }
-    if (h->status_host.p[0] != 0) { set_last_error("LSD region growing: internal pool overflow"); return OLF_ERR_CAPACITY; }
-    if (h->status_host.p[1] + 2 >= (int)h->max_rounds) { set_last_error("LSD region growing did not converge"); return OLF_ERR_INTERNAL; }
-    const int n = (int)*h->nreg_host.p;
-    h->last_stats[2] = n;
-    segs.clear();
-    if (n == 0) return OLF_OK;
-    // libm cos/sin of the O(#regions) rectangle angles, then the projection pass on the device
-    for (int i = 0; i < n; ++i) { const double t = h->rect_host.p[i].theta; h->dir_host.p[i] = make_double2(std::cos(t), std::sin(t)); }
-    k_lsd_rect_b<<<(n + 7) / 8, 256, 0, s>>>(h->regs.p, n, h->final_pool.p, W, h->rect_host.d, h->dir_host.d, h->P.lsd_scale, h->seg_host.d);
-    count_launches(1);
+    float grow_ms = 0; cudaEventElapsedTime(&grow_ms, h0->ev_grow0, h0->ev_grow1);
+    for (int k = 0; k < n; ++k) {
+        LineImpl* h = hs[k];
+        h->last_stats[0] = h->status_host.p[1]; h->last_stats[1] = h->status_host.p[2];
+        h->last_stats[3] = (int)(grow_ms * 1000.f); h->last_stats[4] = n;
+        if (h->status_host.p[0] != 0) { set_last_error("LSD region growing: internal pool overflow"); return OLF_ERR_CAPACITY; }
+        if (!h->status_host.p[3] || h->status_host.p[1] + 2 >= (int)h->max_rounds) { set_last_error("LSD region growing did not converge"); return OLF_ERR_INTERNAL; }
+        const int nr = (int)*h->nreg_host.p;
+        h->last_stats[2] = nr;
+        segs[k].clear();
+        if (nr == 0) continue;
+        // libm cos/sin of the O(#regions) rectangle angles, then the projection pass on the device
+        for (int i = 0; i < nr; ++i) { const double t = h->rect_host.p[i].theta; h->dir_host.p[i] = make_double2(std::cos(t), std::sin(t)); }
+        k_lsd_rect_b<<<(nr + 7) / 8, 256, 0, s>>>(h->regs.p, nr, h->final_pool.p, h->W, h->rect_host.d, h->dir_host.d, h->P.lsd_scale, h->seg_host.d);
+        count_launches(1);
+    }
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(stream_sync(s));
-    // seed order = ascending priority key
-    std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    const RectRec* rr = h->rect_host.p;
-    std::sort(order.begin(), order.end(), [rr](int a, int b) { return rr[a].prio < rr[b].prio; });
-    segs.resize(n);
-    for (int i = 0; i < n; ++i) segs[i] = h->seg_host.p[order[i]];
+    for (int k = 0; k < n; ++k) {
+        LineImpl* h = hs[k];
+        const int nr = h->last_stats[2];
+        if (nr == 0) continue;
+        // seed order = ascending priority key
+        std::vector<int> order(nr);
+        std::iota(order.begin(), order.end(), 0);
+        const RectRec* rr = h->rect_host.p;
+        std::sort(order.begin(), order.end(), [rr](int a, int b) { return rr[a].prio < rr[b].prio; });
+        segs[k].resize(nr);
+        for (int i = 0; i < nr; ++i) segs[k][i] = h->seg_host.p[order[i]];
+    }
     return OLF_OK;
 }
 
@@ -1099,10 +1171,10 @@ static void make_keylines(const std::vector<float4>& segs, int w, int hgt, doubl
     }
 }
 
-// LBD of `n` keylines on the uploaded image: blur 5x5 sigma 1 + Sobel, row sums, fold + binarise
-static int lbd_run(LineImpl* h, const olf_keyline* kls, int n, uint8_t* desc) {
+// LBD of `n` keylines on the uploaded image: blur 5x5 sigma 1 + Sobel, row sums, fold + binarise (enqueue only; the
+// descriptors land in h->desc_host once the stream has been waited for)
+static int lbd_enqueue(LineImpl* h, const olf_keyline* kls, int n, cudaStream_t s) {
     if (n == 0) return OLF_OK;
-    cudaStream_t s = h->stream;
     const int w = h->img_w, hgt = h->img_h;
     int rc;
     if (n > h->lbd_cap) {
@@ -1126,18 +1198,16 @@ static int lbd_run(LineImpl* h, const olf_keyline* kls, int n, uint8_t* desc) {
     k_lbd_fold<<<(n + 63) / 64, 64, 0, s>>>(h->rowsum.p, n, h->desc_host.d);
     count_launches(4);
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(stream_sync(s));
-    memcpy(desc, h->desc_host.p, (size_t)n * 32);
     return OLF_OK;
 }
 
 int line_lsd_detect(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, float* segs, int cap, int* n) {
     if (!h || !img || !n || w <= 0 || hgt <= 0 || stride < w) { set_last_error("olf_lsd_detect: bad arguments"); return OLF_ERR_ARG; }
     OLF_CUDA(cudaSetDevice(h->device));
-    int rc = line_upload(h, img, w, hgt, stride, on_device);
+    int rc = line_upload(h, img, w, hgt, stride, on_device, h->stream);
     if (rc) return rc;
     std::vector<float4> sg;
-    if ((rc = lsd_run(h, sg))) return rc;
+    if ((rc = lsd_run_batch(&h, 1, h->stream, &sg))) return rc;
     *n = (int)sg.size();
     if (*n > cap) { set_last_error("olf_lsd_detect: segment capacity too small"); return OLF_ERR_CAPACITY; }
     if (*n) memcpy(segs, sg.data(), sg.size() * sizeof(float4));
@@ -1148,34 +1218,50 @@ int line_lbd_compute(LineImpl* h, const uint8_t* img, int w, int hgt, int stride
     if (!h || !img || w <= 0 || hgt <= 0 || stride < w || n < 0) { set_last_error("olf_lbd_compute: bad arguments"); return OLF_ERR_ARG; }
     if (n == 0) return OLF_OK;                           // "keypoint list is empty": descriptors untouched (:556-560)
     OLF_CUDA(cudaSetDevice(h->device));
-    int rc = line_upload(h, img, w, hgt, stride, false);
+    int rc = line_upload(h, img, w, hgt, stride, false, h->stream);
     if (rc) return rc;
-    return lbd_run(h, kls, n, desc);
+    if ((rc = lbd_enqueue(h, kls, n, h->stream))) return rc;
+    OLF_CUDA(stream_sync(h->stream));
+    memcpy(desc, h->desc_host.p, (size_t)n * 32);
+    return OLF_OK;
 }
 
-// Lineextractor::operator() (src/LineExtractor.cc:31-67)
-int line_extract(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, olf_keyline* kls, uint8_t* desc, int cap, int* n) {
-    if (!h || !img || !n || w <= 0 || hgt <= 0 || stride < w) { set_last_error("olf_line_extract: bad arguments"); return OLF_ERR_ARG; }
-    *n = 0;
-    OLF_CUDA(cudaSetDevice(h->device));
-    int rc = line_upload(h, img, w, hgt, stride, on_device);
-    if (rc) return rc;
-    std::vector<float4> sg;
-    if ((rc = lsd_run(h, sg))) return rc;
-    std::vector<olf_keyline> k;
-    make_keylines(sg, w, hgt, h->P.min_line_length * std::min(w, hgt), k);
-    const int nf = h->P.lsd_nfeatures;
-    if ((int)k.size() > nf && nf != 0) {
-        // canonical: stable sort by response
-        std::stable_sort(k.begin(), k.end(), [](const olf_keyline& a, const olf_keyline& b) { return a.response > b.response; });
-        k.resize(nf);
-        for (int i = 0; i < nf; i++) k[i].class_id = i;
+// Lineextractor::operator() (src/LineExtractor.cc:31-67) for a batch of images (one per handle) on the first handle's stream
+int line_extract_batch(LineImpl* const* hs, int nimg, const uint8_t* const* imgs, int w, int hgt, int stride, bool on_device,
+                       olf_keyline* const* kls, uint8_t* const* desc, int cap, int* n) {
+    if (!hs || nimg < 1 || nimg > LSD_MAX_BATCH || !imgs || !n || w <= 0 || hgt <= 0 || stride < w) { set_last_error("olf_line_extract: bad arguments"); return OLF_ERR_ARG; }
+    for (int k = 0; k < nimg; ++k) { if (!hs[k] || !imgs[k]) { set_last_error("olf_line_extract: bad arguments"); return OLF_ERR_ARG; } n[k] = 0; }
+    OLF_CUDA(cudaSetDevice(hs[0]->device));
+    cudaStream_t s = hs[0]->stream;
+    int rc;
+    for (int k = 0; k < nimg; ++k) if ((rc = line_upload(hs[k], imgs[k], w, hgt, stride, on_device, s))) return rc;
+    std::vector<float4> sg[LSD_MAX_BATCH];
+    if ((rc = lsd_run_batch(hs, nimg, s, sg))) return rc;
+    std::vector<olf_keyline> kl[LSD_MAX_BATCH];
+    for (int k = 0; k < nimg; ++k) {
+        LineImpl* h = hs[k];
+        std::vector<olf_keyline>& v = kl[k];
+        make_keylines(sg[k], w, hgt, h->P.min_line_length * std::min(w, hgt), v);
+        const int nf = h->P.lsd_nfeatures;
+        if ((int)v.size() > nf && nf != 0) {
+            // canonical: stable sort by response
+            std::stable_sort(v.begin(), v.end(), [](const olf_keyline& a, const olf_keyline& b) { return a.response > b.response; });
+            v.resize(nf);
+            for (int i = 0; i < nf; i++) v[i].class_id = i;
+        }
+        if ((int)v.size() > cap) { set_last_error("olf_line_extract: keyline capacity too small"); return OLF_ERR_CAPACITY; }
+        n[k] = (int)v.size();
+        if (v.empty()) continue;
+        memcpy(kls[k], v.data(), v.size() * sizeof(olf_keyline));
+        if ((rc = lbd_enqueue(h, v.data(), (int)v.size(), s))) return rc;
     }
-    if ((int)k.size() > cap) { set_last_error("olf_line_extract: keyline capacity too small"); return OLF_ERR_CAPACITY; }
-    *n = (int)k.size();
-    if (k.empty()) return OLF_OK;
-    memcpy(kls, k.data(), k.size() * sizeof(olf_keyline));
-    return lbd_run(h, k.data(), (int)k.size(), desc);
+    OLF_CUDA(stream_sync(s));
+    for (int k = 0; k < nimg; ++k) if (n[k]) memcpy(desc[k], hs[k]->desc_host.p, (size_t)n[k] * 32);
+    return OLF_OK;
+}
+int line_extract(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, olf_keyline* kls, uint8_t* desc, int cap, int* n) {
+    if (!h || !n) { set_last_error("olf_line_extract: bad arguments"); return OLF_ERR_ARG; }
+    return line_extract_batch(&h, 1, &img, w, hgt, stride, on_device, &kls, &desc, cap, n);
 }
 
 // [0] rounds, [1] waves, [2] accepted regions, [3] k_lsd_grow device time in microseconds (CUDA events on its stream)

@@ -27,10 +27,15 @@ struct Arena {
 };
 struct MatchCtx {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // the calling thread's own stream
+    cudaStream_t cur = nullptr;        // stream of this call: the thread's own, or the one a rig lent (match_use_stream)
     Arena a;
 };
 static thread_local MatchCtx g_ctx[16];
+static thread_local cudaStream_t g_lent_stream = nullptr;
+// A rig runs its stereo matchers on one of its own streams instead of one more stream per calling thread: every stream
+// beyond the 32 hardware work queues aliases another one and queues behind its (long) chains.
+void match_use_stream(cudaStream_t s) { g_lent_stream = s; }
 
 static int get_ctx(int device, MatchCtx** out) {
     int ndev = 0;
@@ -41,7 +46,11 @@ static int get_ctx(int device, MatchCtx** out) {
     }
     OLF_CUDA(cudaSetDevice(device));
     MatchCtx& c = g_ctx[device];
-    if (!c.stream) { OLF_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); c.device = device; }
+    if (g_lent_stream) c.cur = g_lent_stream;
+    else {
+        if (!c.stream) { OLF_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); c.device = device; }
+        c.cur = c.stream;
+    }
     c.a.reset();
     *out = &c;
     return OLF_OK;
@@ -148,7 +157,7 @@ int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0
     const size_t o_q = pl.d((size_t)n1 * 32), o_t = pl.d((size_t)std::max(n2, 1) * 32), o_part = pl.d((size_t)splits * n1 * sizeof(Knn2)), o_out = pl.d((size_t)4 * n1 * 4);
     const size_t p_q = pl.p((size_t)n1 * 32), p_t = pl.p((size_t)std::max(n2, 1) * 32), p_out = pl.p((size_t)4 * n1 * 4);
     if ((rc = arena_ensure(c, pl))) return rc;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->cur;
     memcpy(hptr<uint8_t>(c, p_q), d1, (size_t)n1 * 32);
     if (n2) memcpy(hptr<uint8_t>(c, p_t), d2, (size_t)n2 * 32);
     OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_q), hptr<uint8_t>(c, p_q), (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
@@ -178,7 +187,7 @@ int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr,
     const size_t o_a = pl.d((size_t)4 * n1 * 4), o_b = pl.d((size_t)4 * n2 * 4), o_m12 = pl.d((size_t)n1 * 4), o_m21 = pl.d((size_t)n2 * 4);
     const size_t p_q = pl.p((size_t)n1 * 32), p_t = pl.p((size_t)n2 * 32), p_m = pl.p((size_t)n1 * 4);
     if ((rc = arena_ensure(c, pl))) return rc;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->cur;
     memcpy(hptr<uint8_t>(c, p_q), d1, (size_t)n1 * 32); memcpy(hptr<uint8_t>(c, p_t), d2, (size_t)n2 * 32);
     OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_q), hptr<uint8_t>(c, p_q), (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
     OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_t), hptr<uint8_t>(c, p_t), (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
@@ -355,7 +364,7 @@ int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const u
     const size_t o_u = pl.d((size_t)N * 4), o_d = pl.d((size_t)N * 4), o_s = pl.d((size_t)N * 4);
     const size_t p_in = pl.p((size_t)(N + Nr) * (sizeof(olf_keypoint) + 32)), p_out = pl.p((size_t)2 * N * 4);
     if ((rc = arena_ensure(c, pl))) return rc;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->cur;
     uint8_t* hp = hptr<uint8_t>(c, p_in);
     uint8_t* h_kl = hp; uint8_t* h_dl = h_kl + (size_t)N * sizeof(olf_keypoint); uint8_t* h_kr = h_dl + (size_t)N * 32; uint8_t* h_dr = h_kr + (size_t)Nr * sizeof(olf_keypoint);
     memcpy(h_kl, kl, (size_t)N * sizeof(olf_keypoint)); memcpy(h_dl, dl, (size_t)N * 32);
@@ -528,7 +537,7 @@ int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_key
     const size_t o_cand = pl.d((size_t)n1 * n2 * 4), o_m12 = pl.d((size_t)n1 * 4), o_m21 = pl.d((size_t)n2 * 4), o_disp = pl.d((size_t)n1 * 8), o_le = pl.d((size_t)n1 * 24);
     const size_t p_in = pl.p((size_t)(n1 + n2) * (sizeof(olf_keyline) + 32)), p_m = pl.p((size_t)n1 * 4), p_disp = pl.p((size_t)n1 * 8), p_le = pl.p((size_t)n1 * 24);
     if ((rc = arena_ensure(c, pl))) return rc;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->cur;
     uint8_t* h_kl = hptr<uint8_t>(c, p_in); uint8_t* h_dl = h_kl + (size_t)n1 * sizeof(olf_keyline); uint8_t* h_kr = h_dl + (size_t)n1 * 32; uint8_t* h_dr = h_kr + (size_t)n2 * sizeof(olf_keyline);
     memcpy(h_kl, kl, (size_t)n1 * sizeof(olf_keyline)); memcpy(h_dl, dl, (size_t)n1 * 32); memcpy(h_kr, kr, (size_t)n2 * sizeof(olf_keyline)); memcpy(h_dr, dr, (size_t)n2 * 32);
     OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_kl), h_kl, (size_t)n1 * sizeof(olf_keyline), cudaMemcpyHostToDevice, s));
@@ -676,7 +685,7 @@ static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t
     const size_t o_lists = pl.d((size_t)nq * SBP_K * 8), o_cnt = pl.d((size_t)nq * 4), o_oa = pl.d((size_t)n_cur * 4), o_ob = pl.d((size_t)n_cur * 4), o_as = pl.d((size_t)nq * 4), o_r = pl.d(4);
     const size_t p_in = pl.p((size_t)nq * (sizeof(SbpQuery) + 33) + (size_t)n_cur * (sizeof(olf_keypoint) + 37) + 64), p_out = pl.p((size_t)nq * 8 + 16);
     if ((rc = arena_ensure(c, pl))) return rc;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->cur;
     uint8_t* hp = hptr<uint8_t>(c, p_in);
     size_t off = 0;
     auto up = [&](size_t dev_off, const void* src, size_t bytes) -> int {

@@ -1,9 +1,12 @@
 // internal C++ interface of the matching half (see match.cu)
 #pragma once
 #include <cstdint>
+#include <cuda_runtime.h>
 #include "../../include/olf_abi.h"
 namespace olf {
 struct OrbImpl;
+// the calling thread's next matcher calls run on `s` (nullptr: back to the thread's own stream)
+void match_use_stream(cudaStream_t s);
 int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0, int* dist0, int* idx1, int* dist1, int device);
 int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int mutual, int* m12, int* nmatches, int device);
 int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const uint8_t* dl, int N, const olf_keypoint* kr, const uint8_t* dr, int Nr,

@@ -508,6 +508,7 @@ OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
     return h;
 }
 
+cudaStream_t orb_stream(const OrbImpl* h) { return h ? h->stream : nullptr; }
 void orb_destroy(OrbImpl* h) {
     if (!h) return;
     cudaSetDevice(h->device);

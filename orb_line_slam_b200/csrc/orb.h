@@ -15,6 +15,7 @@ struct OrbDeviceView {          // device-resident pyramid of the last extract (
 // 2 streams per rig keep many rigs within the 32 hardware work queues); the owner must outlive this extractor
 OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device, cudaStream_t ext_stream = nullptr);
 void orb_destroy(OrbImpl* h);
+cudaStream_t orb_stream(const OrbImpl* h);
 // on_phase1_enqueued: called once the GPU phase before the quadtree is enqueued and marked (a rig uses it to let the line
 // extractor of the same eye enqueue its long LSD chain BEHIND the ORB kernels on their shared stream)
 int orb_extract(OrbImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, olf_keypoint* kps, uint8_t* desc, int cap, int* n,

@@ -69,12 +69,13 @@ class FrontEnd:
         return f
 
     # ---- native whole-frame path (olf_frontend_*; product library only) ----
-    def native(self, nfeatures=2000, nlines=500, cap_points=None, cap_lines=None):
-        """Create the native rig (4 host threads + 4 streams inside libolf.so) that fills one POD block per frame."""
+    def native(self, nfeatures=2000, nlines=500, cap_points=None, cap_lines=None, max_frames=1):
+        """Create the native rig (3 host threads + 2 streams inside libolf.so) that fills one POD block per frame;
+        max_frames > 1: olf_frontend_process_batch takes that many independent stereo frames per call."""
         cap_points = cap_points or (nfeatures + 256)
         cap_lines = cap_lines or max(nlines, 64) if nlines else 4096
         p = FrontendParams(nfeatures, 1.2, 8, 20, 7, int(self.has_lines), self.lp, self.lmp, self.cam, cap_points, cap_lines)
-        return NativeFrontEnd(self.api, p, self.w, self.h)
+        return NativeFrontEnd(self.api, p, self.w, self.h, max_frames)
 
     # ---- tracking matchers (src/Tracking.cc:1296-1308) ----
     def sbp_last_args(self, cur: StereoFrame, last: StereoFrame, th=7.0, mono=False, check_orientation=True, observed=None):
@@ -157,10 +158,10 @@ class FrontEnd:
 class NativeFrontEnd:
     """olf_frontend_*: Frame::Frame(stereo+lines) in one native call; results land in a fixed-capacity POD block."""
 
-    def __init__(self, api: FrontEndApi, params: FrontendParams, w, h):
-        self.api, self.params, self.w, self.h = api, params, w, h
+    def __init__(self, api: FrontEndApi, params: FrontendParams, w, h, max_frames=1):
+        self.api, self.params, self.w, self.h, self.max_frames = api, params, w, h, max_frames
         self.off = api.frame_layout(params.cap_points, params.cap_lines)
-        self.handle = api.frontend_create(params)
+        self.handle = api.frontend_create(params, max_frames)
 
     def close(self):
         self.api.frontend_destroy(self.handle)
@@ -171,6 +172,11 @@ class NativeFrontEnd:
     def process(self, img_l, img_r, block: np.ndarray, on_device=False, stride=None):
         self.api.frontend_process(self.handle, img_l, img_r, self.w, self.h, stride or self.w, on_device, block)
         return block
+
+    def process_batch(self, imgs_l, imgs_r, blocks, on_device=False, stride=None):
+        """olf_frontend_process_batch: len(imgs_l) <= max_frames independent stereo frames through one call."""
+        self.api.frontend_process_batch(self.handle, imgs_l, imgs_r, self.w, self.h, stride or self.w, on_device, blocks)
+        return blocks
 
     def view(self, block: np.ndarray, pose=None) -> StereoFrame:
         """Zero-copy numpy views into a result block."""

@@ -139,3 +139,26 @@ def test_native_frontend_block(frames):
         for name in ("kps", "desc", "kps_r", "desc_r", "u_right", "depth", "kls", "ldesc", "kls_r", "ldesc_r", "line_matches", "line_disp", "line_le"):
             assert np.array_equal(getattr(v, name), getattr(ref, name)), name
     nat.close()
+
+
+def test_native_frontend_batch(frames):
+    """olf_frontend_process_batch: 3 independent stereo frames through ONE call (the line extraction of the six images is one
+    batched chain of launches) == frame-by-frame == oracle; a second call with a shorter batch reuses the rig."""
+    sc = Scene("euroc", 3)
+    fg = frames["fg"]
+    nat = fg.native(1000, 200, max_frames=3)
+    pairs = [sc.stereo(f) for f in (0, 1, 0)]
+    blocks = [nat.new_block() for _ in pairs]
+    nat.process_batch([p[0] for p in pairs], [p[1] for p in pairs], blocks)
+    names = ("kps", "desc", "kps_r", "desc_r", "u_right", "depth", "kls", "ldesc", "kls_r", "ldesc_r", "line_matches", "line_disp", "line_le")
+    for blk, f in zip(blocks, (0, 1, 0)):
+        v, ref = nat.view(blk), frames["o"][f]
+        for name in names:
+            assert np.array_equal(getattr(v, name), getattr(ref, name)), (f, name)
+    nat.process_batch([pairs[1][0]], [pairs[1][1]], blocks[:1])
+    v, ref = nat.view(blocks[0]), frames["o"][1]
+    for name in names:
+        assert np.array_equal(getattr(v, name), getattr(ref, name)), name
+    with pytest.raises(Exception):
+        nat.process_batch([p[0] for p in pairs] * 2, [p[1] for p in pairs] * 2, blocks * 2)     # more frames than the rig holds
+    nat.close()
