@@ -80,7 +80,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def run_steps(pipes, frontends, track_fe, seq_imgs, poses, first, count, on_device, dev_imgs):
+def run_steps(pipes, frontends, track_fe, seq_imgs, poses, first, count, on_device, dev_imgs, n_trackers=1, do_track=True):
     """Process frames [first, first+count) on len(pipes) concurrent rigs (Frame::Frame each); one tracker thread consumes
     the finished frames in order and runs the frame-to-frame matchers of TrackWithMotionModelWithLine on (f, f-1)."""
     P = len(pipes)
@@ -110,26 +110,32 @@ def run_steps(pipes, frontends, track_fe, seq_imgs, poses, first, count, on_devi
             for d in done:
                 d.set()
 
-    def tracker():
+    lock = threading.Lock()
+
+    def tracker(tid):
+        # frame-to-frame matchers of TrackWithMotionModelWithLine on (f, f-1): src/Tracking.cc:1296 (SearchByProjection) and
+        # :1308 (line match); the pairs are independent, tracker thread `tid` takes frames tid, tid+T, ...
         try:
-            prev = None
-            for k in range(count):
+            loc = {"matches": 0, "line_matches": 0, "kps": 0, "lines": 0, "d2h": 0}
+            for k in range(tid, count, n_trackers):
                 done[k].wait()
+                if k > 0:
+                    done[k - 1].wait()
                 if errors:
                     return
                 v = views[k]
-                if prev is not None:               # src/Tracking.cc:1296 (SearchByProjection) and :1308 (line match)
-                    t = track_fe[0].track(v, prev)
-                    stats["matches"] += t["nmatches"]; stats["line_matches"] += t.get("n_line_matches", 0)
-                stats["kps"] += len(v.kps) + len(v.kps_r); stats["lines"] += len(v.kls) + len(v.kls_r)
-                stats["d2h"] += (len(v.kps) + len(v.kps_r)) * 56 + len(v.kps) * 8 + (len(v.kls) + len(v.kls_r)) * 100 + len(v.kls) * 36
-                prev = v
-                if k > 0:
-                    views[k - 1] = None
+                if k > 0 and do_track:
+                    t = track_fe[tid % len(track_fe)].track(v, views[k - 1])
+                    loc["matches"] += t["nmatches"]; loc["line_matches"] += t.get("n_line_matches", 0)
+                loc["kps"] += len(v.kps) + len(v.kps_r); loc["lines"] += len(v.kls) + len(v.kls_r)
+                loc["d2h"] += (len(v.kps) + len(v.kps_r)) * 56 + len(v.kps) * 8 + (len(v.kls) + len(v.kls_r)) * 100 + len(v.kls) * 36
+            with lock:
+                for key, val in loc.items():
+                    stats[key] += val
         except Exception as e:       # noqa: BLE001
             errors.append(e)
 
-    ths = [threading.Thread(target=worker, args=(p,)) for p in range(P)] + [threading.Thread(target=tracker)]
+    ths = [threading.Thread(target=worker, args=(p,)) for p in range(P)] + [threading.Thread(target=tracker, args=(i,)) for i in range(n_trackers)]
     for t in ths:
         t.start()
     for t in ths:
@@ -223,10 +229,12 @@ def cpu_reference_all_cores(frames, seq, poses, warm=1, cores=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=480)
-    ap.add_argument("--warmup", type=int, default=24)
+    ap.add_argument("--steps", type=int, default=1664)
+    ap.add_argument("--warmup", type=int, default=52)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pipelines", type=int, default=0, help="concurrent stereo rigs per GPU (0 = auto)")
+    ap.add_argument("--trackers", type=int, default=1, help="host threads running the frame-to-frame matchers")
+    ap.add_argument("--no-track", action="store_true", help="(diagnostic) skip the frame-to-frame matchers")
     ap.add_argument("--batch", type=int, default=4, help="independent stereo frames per olf_frontend_process_batch call (1..4)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -304,7 +312,7 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.olf_kernel_launch_count()
         ev0.record()
-        st = run_steps(pipes, pipes, fes, host_pinned, poses, first, count, on_device, dev_ptrs)
+        st = run_steps(pipes, pipes, fes, host_pinned, poses, first, count, on_device, dev_ptrs, args.trackers, not args.no_track)
         if dist is not None:
             # trivial NCCL gather of the fixed-capacity keypoint/descriptor block of the rank's last frame
             dist.all_gather_into_tensor(gather_buf[1], gather_buf[0])
@@ -319,12 +327,12 @@ def main():
     # mappings and the host threads settle (the first seconds show multi-100-ms stalls); then the W warm-up steps
     t_pre = time.perf_counter()
     while time.perf_counter() - t_pre < args.prewarm_s:
-        timed(max(args.warmup, 4 * P), 0, True)
-    timed(args.warmup, 0, True)                                   # warm-up (also sizes every internal buffer)
+        timed(max(args.warmup, 2 * P * args.batch), 0, True)       # every rig sees at least two batches (buffers sized, modules loaded)
+    timed(max(args.warmup, P * args.batch), 0, True)               # the W warm-up steps (rounded up to one batch per rig)
     sampler = ClockSampler(local) if rank == 0 else None
     ms, st, launches = timed(args.steps, args.warmup, True)       # HBM-resident inputs
     clocks = sampler.stop() if sampler else None
-    timed(min(args.warmup, 8), 0, False)
+    timed(max(min(args.warmup, 8), P * args.batch), 0, False)
     ms_e2e, st_e2e, _ = timed(args.steps, args.warmup, False)     # host buffers in, host results out
     # live timing of the dominant kernel (k_lsd_grow): CUDA events on its own stream inside the library
     grow_us = []

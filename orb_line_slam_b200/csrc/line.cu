@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const float* __restrict__ a
 // flight interleave freely with every other kernel on the device.
 #define TRACE_REC 8
 struct PhaseState {
-    int wave; unsigned round; int mode; int done;           // mode 0: round passes, 1: finalise the converged wave
+    int wave; unsigned round; int mode; int done;           // mode 0: round passes, 1: finalise the converged wave, 2: converged, waiting for the batch
     int launches; unsigned wave_first_round;
     unsigned wl0_cnt, wl1_cnt, wl2_cnt, wl2_pop, changed, ticket;
 };
@@ -156,7 +156,8 @@ struct GrowDev {
 // image has its own state machine.  The passes are latency-bound with small grids, so a batch costs one chain of launches
 // on one stream instead of one chain per image -- that is what keeps many frames in flight within the 32 hardware queues.
 #define LSD_MAX_BATCH 8
-struct GrowBatch { GrowDev d[LSD_MAX_BATCH]; PhaseState* st[LSD_MAX_BATCH]; };
+#define LSD_MAX_WAVES 64
+struct GrowBatch { GrowDev d[LSD_MAX_BATCH]; PhaseState* st[LSD_MAX_BATCH]; unsigned* conv; int n; };   // conv[w]: images of the batch that have converged in wave w
 __device__ __forceinline__ const GrowDev& batch_image(const GrowBatch& B, GrowDev* sh, PhaseState*& st) {
     // block-uniform copy of this image's descriptor into shared memory (the by-value batch lives in parameter space)
     const int* src = reinterpret_cast<const int*>(&B.d[blockIdx.y]);
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(128) k_lsd_verify(const __grid_constant__ Grow
         }
         if (D.dbg && carried) atomicAdd(&D.dbg[round * TRACE_REC + 4], carried);
         if (__syncthreads_or(chg) && threadIdx.x == 0) st->changed = 1;
-    } else {
+    } else if (st->mode == 1) {
         for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += nth)
             if (!finalize_seed(D.C, round, D.wl1[k], D.F)) D.status[0] = OLF_ERR_CAPACITY;
     }
@@ -344,7 +345,10 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
     if (st->done) return;
     const int wv = st->wave; const unsigned round = st->round; const int mode = st->mode;
     if (wv >= D.plan->n_waves) {                                   // no seeds at all (flat image)
-        if (blockIdx.x == 0 && threadIdx.x == 0) { st->done = 1; D.status[1] = (int)round; D.status[2] = D.plan->n_waves; D.status[3] = 1; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            st->done = 1; D.status[1] = (int)round; D.status[2] = D.plan->n_waves; D.status[3] = 1;
+            for (int w = wv; w < LSD_MAX_WAVES; ++w) atomicAdd(&B.conv[w], 1u);       // never holds the batch back
+        }
         return;
     }
     if (mode == 0 && st->wl2_cnt > 0) {
@@ -557,16 +561,27 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
     __threadfence();
     const int err = *(volatile int*)&D.status[0];
     st->ticket = 0; st->launches += 1;
+    // The images of a batch advance through their waves TOGETHER: an image that has converged waits (mode 2) until every image
+    // of the batch has, so the expensive first rounds of a wave -- whose critical path is the longest region -- coincide in
+    // the same launches instead of adding up along the chain.
+    const unsigned nb = (unsigned)B.n;
     if (mode == 0) {
         if (D.dbg) D.dbg[round * TRACE_REC + 3] = (int)(gtime() & 0x7fffffff);
         const bool changed = *(volatile unsigned*)&st->changed != 0;
-        if (!changed || round + 2 >= D.max_rounds || err != 0) st->mode = 1;      // work list 1 is kept for the finalise pass
-        else { st->round = round + 1; st->wl1_cnt = 0; }
+        if (!changed || round + 2 >= D.max_rounds || err != 0) {              // work list 1 is kept for the finalise pass
+            const unsigned c = wv < LSD_MAX_WAVES ? atomicAdd(&B.conv[wv], 1u) + 1u : nb;
+            st->mode = (c >= nb) ? 1 : 2;
+        } else { st->round = round + 1; st->wl1_cnt = 0; }
         st->wl2_cnt = 0; st->wl2_pop = 0; st->changed = 0;
+    } else if (mode == 2) {
+        if (*(volatile unsigned*)&B.conv[wv] >= nb) st->mode = 1;
     } else {
         st->mode = 0; st->round = round + 1; st->wave = wv + 1; st->wave_first_round = round + 1; st->wl1_cnt = 0; st->wl0_cnt = 0;
         *D.C.pool_ctr = 0;                                          // one bump pool per wave (lists are carried over rounds)
-        if (wv + 1 >= D.plan->n_waves || err != 0) { st->done = 1; D.status[1] = (int)(round + 1); D.status[2] = D.plan->n_waves; D.status[3] = 1; }
+        if (wv + 1 >= D.plan->n_waves || err != 0) {
+            st->done = 1; D.status[1] = (int)(round + 1); D.status[2] = D.plan->n_waves; D.status[3] = 1;
+            for (int w = wv + 1; w < LSD_MAX_WAVES; ++w) atomicAdd(&B.conv[w], 1u);   // this image has no further waves
+        }
     }
     __threadfence();
 }
@@ -833,18 +848,19 @@ struct LineImpl {
     DevBuf<int> seed_pix, n2max, status, wl0, wl1, wl2;
     DevBuf<unsigned> hist, bin_start, cursor, pool, ctrs, final_pool;
     DevBuf<SeedRec> srec0, srec1;
+    DevBuf<unsigned> conv;
     DevBuf<double> regang;
     DevBuf<LsdPlan> plan;
     DevBuf<LsdRegion> regs;
     DevBuf<float2_t> tab_seed, tab_acc, cs;
     DevBuf<PhaseState> phase;
     DevBuf<PxRec> px;
-    int phase_batch = 40;
+    int phase_batch = 48;
     bool trace = false;
     int first_wave = 4096, wave_growth = 16;
     DevBuf<int> dbg;
     unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
-    int scan_blocks = 0, verify_blocks = 0, grow_blocks = 0;
+    int scan_blocks = 0, verify_blocks = 0, grow_blocks_wide = 0, grow_blocks_narrow = 0;
     PinBuf<PhaseState> phase_init;
     PinBuf<RectRec> rect_host; PinBuf<double2> dir_host; PinBuf<float4> seg_host; PinBuf<int> status_host; PinBuf<unsigned> nreg_host;
     // LBD
@@ -943,8 +959,16 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     if (const char* e = getenv("OLF_LSD_PHASE_BATCH")) h->phase_batch = std::max(4, atoi(e));
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
     // grids of the three region-growing passes (one thread per seed; see k_lsd_scan / k_lsd_verify / k_lsd_grow)
-    h->scan_blocks = 2 * sms; h->verify_blocks = sms; h->grow_blocks = sms;
-    if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks = std::max(1, atoi(e));
+    // Grids per image and pass.  Most launches of the chain find little or nothing to do (tail rounds, images waiting for the
+    // batch) and every pass is latency-bound, so the grids are small.  The grow pass has two settings: a region's critical
+    // path is sequential, so MORE threads only shorten a round while fewer threads keep the lanes of a warp busy (a lane
+    // whose region is complete takes the next seed) -- measured 4.9 active lanes per warp instruction with one seed per
+    // thread.  A single frame (<= 2 images) gets the wide grid (latency), a batch the narrow one (throughput).
+    h->scan_blocks = 64; h->verify_blocks = 48;
+    h->grow_blocks_wide = std::max(1, sms * 64 / GROW_THREADS); h->grow_blocks_narrow = std::max(1, 40 * 64 / GROW_THREADS);
+    if (const char* e = getenv("OLF_LSD_SCAN_BLOCKS")) h->scan_blocks = std::max(1, atoi(e));
+    if (const char* e = getenv("OLF_LSD_VERIFY_BLOCKS")) h->verify_blocks = std::max(1, atoi(e));
+    if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks_wide = h->grow_blocks_narrow = std::max(1, atoi(e));
     (void)per_sm;
     return h;
 }
@@ -958,7 +982,7 @@ void line_destroy(LineImpl* h) {
     h->img_stage.release(); h->img.release(); h->blurred.release(); h->scaled.release(); h->lbd_blur.release(); h->coef.release();
     h->ang.release(); h->dabc.release(); h->seed_prio.release(); h->seed_pix.release(); h->n2max.release(); h->status.release();
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
-    h->final_pool.release(); h->srec0.release(); h->srec1.release(); h->regang.release(); h->plan.release(); h->regs.release();
+    h->final_pool.release(); h->conv.release(); h->srec0.release(); h->srec1.release(); h->regang.release(); h->plan.release(); h->regs.release();
     h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release();
     h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release(); h->phase_init.release();
     h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
@@ -989,7 +1013,7 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
     h->pool_chunks = (unsigned)std::max<size_t>(S / 2, 1u << 16);       // 16 px of list space per image pixel per round
     h->reg_cap = (unsigned)(S / std::max(h->min_reg_size, 1) + 16);
     if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || (rc = h->seed_prio.ensure(S)) || (rc = h->seed_pix.ensure(S)) ||
-        (rc = h->srec0.ensure(S)) || (rc = h->srec1.ensure(S)) || (rc = h->wl0.ensure(S)) || (rc = h->wl1.ensure(S)) || (rc = h->wl2.ensure(S)) ||
+        (rc = h->conv.ensure(LSD_MAX_WAVES)) || (rc = h->srec0.ensure(S)) || (rc = h->srec1.ensure(S)) || (rc = h->wl0.ensure(S)) || (rc = h->wl1.ensure(S)) || (rc = h->wl2.ensure(S)) ||
         (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) ||
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
         (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->plan.ensure(1)) ||
@@ -1086,12 +1110,14 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     int rc;
     for (int k = 0; k < n; ++k) { if ((rc = lsd_enqueue_pre(hs[k], s, B.d[k]))) return rc; B.st[k] = hs[k]->phase.p; }
     LineImpl* h0 = hs[0];
+    B.conv = h0->conv.p; B.n = n;
+    OLF_CUDA(cudaMemsetAsync(h0->conv.p, 0, LSD_MAX_WAVES * sizeof(unsigned), s));
     OLF_CUDA(cudaEventRecord(h0->ev_grow0, s));
     auto enqueue_phases = [&](int count) {
         for (int k = 0; k < count; ++k) {
             k_lsd_scan<<<dim3(h0->scan_blocks, n), 256, 0, s>>>(B);
             k_lsd_verify<<<dim3(h0->verify_blocks, n), 128, 0, s>>>(B);
-            k_lsd_grow<<<dim3(h0->grow_blocks, n), GROW_THREADS, 0, s>>>(B);
+            k_lsd_grow<<<dim3(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n), GROW_THREADS, 0, s>>>(B);
         }
         count_launches(3 * count);
     };
