@@ -366,9 +366,12 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "k_lsd_grow (+scan, verify)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)", "unit": "GB/s",
-                             "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel_ms": grow_ms,
+                             "frac": (achieved / peak) if achieved else None,
+                             # DRAM bytes per image of the chain (scan 150 + verify 159 + grow 36 MB, cold caches): ncu launch list,
+                             # profiles/r01b_launches_summary.csv
+                             "traffic": 344.4e6, "kernel_ms": grow_ms,
                              "algorithmic_bytes_per_launch": alg_bytes,
-                             "note": "k_lsd_scan/verify/grow chain, device time per image of a batched chain; latency-bound sequential region growing: the HBM fraction is honest but not the limiter (see DESIGN.md)"}}
+                             "note": "dominant chain = the LSD region-growing passes (k_lsd_scan / k_lsd_verify / k_lsd_grow, ~95% of a frame's GPU time): device time of one batched chain / images in it, CUDA events on its stream; 'launch' = one image's chain; latency-bound sequential region growing -- the HBM fraction is honest but not the limiter (DESIGN.md section 5)"}}
         if not args.no_cpu_baseline and world == 1:
             frames = args.cpu_frames
             cfps, dt = cpu_reference(frames, [(a, b) for a, b in host_pinned[:N_BASE_FRAMES]], poses[:N_BASE_FRAMES], warm=1)
