@@ -42,9 +42,9 @@ struct FrontendImpl {
     // every line extractor is driven through the first one's stream by ONE batched chain of launches (line_extract_batch)
     std::vector<OrbImpl*> orb;
     std::vector<LineImpl*> line;
-    Worker* workers[3] = {nullptr, nullptr, nullptr};   // ORB left images, ORB right images, all line images
+    Worker* workers[4] = {nullptr, nullptr, nullptr, nullptr};   // ORB left images, ORB right images, line images (4th: right eye of a single-frame rig)
     olf_frame_offsets off;
-    std::string err[3];
+    std::string err[4];
 };
 
 static uint64_t a64(uint64_t v) { return (v + 63) / 64 * 64; }
@@ -77,7 +77,9 @@ FrontendImpl* frontend_create(const olf_frontend_params* p, int device, int max_
     frame_layout(p->cap_points, p->cap_lines, &h->off);
     bool ok = true;
     for (int k = 0; k < 2 * max_frames && ok; ++k) {
-        if (p->has_lines) { h->line.push_back(line_create(&p->line, device, h->line.empty() ? nullptr : line_stream(h->line[0]))); ok = h->line.back() != nullptr; }
+        // a single-frame rig (latency matters) keeps one stream per eye and extracts the two eyes' lines side by side; a batch
+        // rig (throughput matters) drives every line extractor through ONE stream and one batched chain of launches
+        if (p->has_lines) { h->line.push_back(line_create(&p->line, device, (h->line.empty() || max_frames == 1) ? nullptr : line_stream(h->line[0]))); ok = h->line.back() != nullptr; }
         if (ok) {
             h->orb.push_back(orb_create(p->nfeatures, p->scale_factor, p->nlevels, p->ini_th_fast, p->min_th_fast, device,
                                         h->orb.empty() ? nullptr : orb_stream(h->orb[0])));
@@ -90,12 +92,12 @@ FrontendImpl* frontend_create(const olf_frontend_params* p, int device, int max_
         for (size_t k = h->line.size(); k-- > 0;) line_destroy(h->line[k]);
         delete h; set_last_error(e); return nullptr;
     }
-    for (int i = 0; i < 3; ++i) h->workers[i] = new Worker();
+    for (int i = 0; i < 4; ++i) h->workers[i] = new Worker();
     return h;
 }
 void frontend_destroy(FrontendImpl* h) {
     if (!h) return;
-    for (int i = 0; i < 3; ++i) delete h->workers[i];
+    for (int i = 0; i < 4; ++i) delete h->workers[i];
     for (size_t k = h->orb.size(); k-- > 0;) orb_destroy(h->orb[k]);     // the borrowers before the owner of the stream
     for (size_t k = h->line.size(); k-- > 0;) line_destroy(h->line[k]);
     delete h;
@@ -135,15 +137,24 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
             }
             return (int)OLF_OK;
         });
-    if (h->P.has_lines)
+    const bool side_by_side = h->P.has_lines && h->max_frames == 1;      // one frame: the two eyes on their own streams
+    if (side_by_side) {
+        for (int e = 0; e < 2; ++e)
+            h->workers[2 + e]->submit([=, &m, &kls, &ldesc, &img]() {
+                const int rc = line_extract(h->line[e], img[e], w, hgt, stride, on_device != 0, kls[e], ldesc[e], h->P.cap_lines, &m[e]);
+                if (rc) h->err[2 + e] = olf_last_error();
+                return rc;
+            });
+    } else if (h->P.has_lines)
         h->workers[2]->submit([=, &m, &kls, &ldesc, &img]() {
             const int rc = line_extract_batch(h->line.data(), nimg, img.data(), w, hgt, stride, on_device != 0, kls.data(), ldesc.data(), h->P.cap_lines, m.data());
             if (rc) h->err[2] = olf_last_error();
             return rc;
         });
     int rc = OLF_OK;
-    for (int i = 0; i < 3; ++i) {
-        if (i == 2 && !h->P.has_lines) break;
+    for (int i = 0; i < 4; ++i) {
+        if (i >= 2 && !h->P.has_lines) break;
+        if (i == 3 && !side_by_side) break;
         const int r = h->workers[i]->wait();
         if (r && !rc) { rc = r; set_last_error(h->err[i]); }
     }

@@ -860,7 +860,7 @@ struct LineImpl {
     int first_wave = 4096, wave_growth = 16;
     DevBuf<int> dbg;
     unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
-    int scan_blocks = 0, verify_blocks = 0, grow_blocks_wide = 0, grow_blocks_narrow = 0;
+    int scan_blocks = 0, verify_blocks = 0, scan_blocks_wide = 0, verify_blocks_wide = 0, grow_blocks_wide = 0, grow_blocks_narrow = 0;
     PinBuf<PhaseState> phase_init;
     PinBuf<RectRec> rect_host; PinBuf<double2> dir_host; PinBuf<float4> seg_host; PinBuf<int> status_host; PinBuf<unsigned> nreg_host;
     // LBD
@@ -960,14 +960,14 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
     // grids of the three region-growing passes (one thread per seed; see k_lsd_scan / k_lsd_verify / k_lsd_grow)
     // Grids per image and pass.  Most launches of the chain find little or nothing to do (tail rounds, images waiting for the
-    // batch) and every pass is latency-bound, so the grids are small.  The grow pass has two settings: a region's critical
+    // batch) and every pass is latency-bound, so the grids of a batch are small.  Two settings: a region's critical
     // path is sequential, so MORE threads only shorten a round while fewer threads keep the lanes of a warp busy (a lane
     // whose region is complete takes the next seed) -- measured 4.9 active lanes per warp instruction with one seed per
     // thread.  A single frame (<= 2 images) gets the wide grid (latency), a batch the narrow one (throughput).
-    h->scan_blocks = 64; h->verify_blocks = 48;
+    h->scan_blocks = 64; h->verify_blocks = 48; h->scan_blocks_wide = 2 * sms; h->verify_blocks_wide = sms;
     h->grow_blocks_wide = std::max(1, sms * 64 / GROW_THREADS); h->grow_blocks_narrow = std::max(1, 40 * 64 / GROW_THREADS);
-    if (const char* e = getenv("OLF_LSD_SCAN_BLOCKS")) h->scan_blocks = std::max(1, atoi(e));
-    if (const char* e = getenv("OLF_LSD_VERIFY_BLOCKS")) h->verify_blocks = std::max(1, atoi(e));
+    if (const char* e = getenv("OLF_LSD_SCAN_BLOCKS")) h->scan_blocks = h->scan_blocks_wide = std::max(1, atoi(e));
+    if (const char* e = getenv("OLF_LSD_VERIFY_BLOCKS")) h->verify_blocks = h->verify_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks_wide = h->grow_blocks_narrow = std::max(1, atoi(e));
     (void)per_sm;
     return h;
@@ -1115,8 +1115,8 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     OLF_CUDA(cudaEventRecord(h0->ev_grow0, s));
     auto enqueue_phases = [&](int count) {
         for (int k = 0; k < count; ++k) {
-            k_lsd_scan<<<dim3(h0->scan_blocks, n), 256, 0, s>>>(B);
-            k_lsd_verify<<<dim3(h0->verify_blocks, n), 128, 0, s>>>(B);
+            k_lsd_scan<<<dim3(n <= 2 ? h0->scan_blocks_wide : h0->scan_blocks, n), 256, 0, s>>>(B);
+            k_lsd_verify<<<dim3(n <= 2 ? h0->verify_blocks_wide : h0->verify_blocks, n), 128, 0, s>>>(B);
             k_lsd_grow<<<dim3(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n), GROW_THREADS, 0, s>>>(B);
         }
         count_launches(3 * count);
