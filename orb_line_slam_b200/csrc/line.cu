@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128) k_lsd_verify(const __grid_constant__ Grow
 #define GROW_THREADS 64
 #endif
 #define GROW_RING 16
-struct GrowSmem { float nb[8][3][GROW_THREADS]; unsigned ring[GROW_RING][GROW_THREADS]; };
+struct GrowSmem { float2 nb[8][GROW_THREADS]; unsigned ring[GROW_RING][GROW_THREADS]; };   // (cos, sin) of the 8 neighbours; recent queue
 
 // The last block to finish advances the wave / round state machine.
 __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant__ GrowBatch B) {
@@ -488,26 +488,30 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                 for (int k = 0; k < 8; ++k) { acc_a |= (unsigned)(c0[k] >> 32); acc_b |= __float_as_uint(lo[k].w); }
                 const bool never = ((acc_a >> 24) == 0x55u) || ((acc_b >> 16) == 0x55u);
                 const u64 mine_g = never ? 0ull : mine, mine_prev_g = never ? ~0ull : mine_prev;
+                // free: neither final nor held by a higher-priority seed nor already mine (NOTDEF pixels are born final);
+                // held: by a non-final higher-priority claim.  The round parity is uniform: one copy of the flags per parity.
                 unsigned m_free = 0, m_held = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const u64 ep = cur ? c0[k] : c1[k], ec = cur ? c1[k] : c0[k];
-                    // free: neither final nor held by a higher-priority seed nor already mine (NOTDEF pixels are born final)
-                    const bool fre = (ep >= mine_prev_g) && (ec > mine_g);
-                    const bool fin = ((unsigned)(ep >> 40) == 0u) || ((unsigned)(ec >> 40) == 0u);
-                    const bool hld = !fre && !fin && (ec != mine_g);
-                    m_free |= (unsigned)fre << k;
-                    m_held |= (unsigned)hld << k;
+#define OLF_FLAGS(EP, EC)                                                                                      \
+                _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                                \
+                    const u64 ep = EP[k], ec = EC[k];                                                          \
+                    const bool fre = (ep >= mine_prev_g) && (ec > mine_g);                                     \
+                    const bool fin = ((unsigned)(ep >> 32) < 256u) || ((unsigned)(ec >> 32) < 256u);           \
+                    const bool hld = !fre && !fin && (ec != mine_g);                                           \
+                    m_free |= (unsigned)fre << k;                                                              \
+                    m_held |= (unsigned)hld << k;                                                              \
                 }
+                if (cur) { OLF_FLAGS(c0, c1) } else { OLF_FLAGS(c1, c0) }
+#undef OLF_FLAGS
                 m_free &= vm; m_held &= vm;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { sm.nb[k][0][t] = lo[k].x; sm.nb[k][1][t] = lo[k].y; sm.nb[k][2][t] = never ? 0.f : lo[k].z; }
+                for (int k = 0; k < 8; ++k) sm.nb[k][t] = make_float2(lo[k].y, never ? 0.f : lo[k].z);
                 // the surviving candidates, in scan order; the region angle changes after every accepted pixel
                 unsigned m = m_free | m_held;
                 while (m) {
                     const int k = __ffs(m) - 1;
                     m &= m - 1;
-                    const float cxk = sm.nb[k][1][t], cyk = sm.nb[k][2][t];
+                    const float2 csk = sm.nb[k][t];
+                    const float cxk = csk.x, cyk = csk.y;
                     bool al;
                     {   // isAligned(), lazily: see grow_aligned() in lsd_core.h
                         const float dot = f_add(f_mul(sumdx, cxk), f_mul(sumdy, cyk)), d2 = f_mul(dot, dot);
@@ -516,7 +520,9 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                         else if (fast && (dot <= 0.f || d2 <= f_mul(C.c_lo2, u2))) al = false;
                         else {
                             if (dirty) { reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads); dirty = false; }
-                            double n_theta = d_sub(reg_angle, d_mul((double)sm.nb[k][0][t], kDegToRads));
+                            const int nke = k < 4 ? k : k + 1;                       // rare path: the candidate's angle comes from its record
+                            const float ang_k = __ldcg(&C.px[p + ((nke / 3) - 1) * W + ((nke % 3) - 1)].ang);
+                            double n_theta = d_sub(reg_angle, d_mul((double)ang_k, kDegToRads));
                             if (n_theta < 0) n_theta = -n_theta;
                             if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
                             al = n_theta <= C.prec;
