@@ -443,13 +443,13 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                 const PxRec* const base = C.px + p;
                 // all sixteen loads are issued before anything consumes them (one memory round trip per queue entry): ONE asm
                 // block, so that the assembler cannot trade the memory-level parallelism for registers; neighbours outside
-                // the image read the entry's own record instead (always valid, and "already mine")
+                // the image read the guard band or the neighbouring row (valid memory) and are masked out by `vm`
                 u64 c0[8], c1[8]; float4 lo[8];
-                const PxRec* ra[8];
+                const PxRec* ra[8];                                      // (the record array has a guard band of W+2 records at both ends)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int nk = k < 4 ? k : k + 1;
-                    ra[k] = ((vm >> k) & 1u) ? base + ((nk / 3) - 1) * W + ((nk % 3) - 1) : base;
+                    ra[k] = base + ((nk / 3) - 1) * W + ((nk % 3) - 1);
                 }
                 asm volatile(
                     "ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%16];\n\t"
@@ -1024,9 +1024,11 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
         (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->plan.ensure(1)) ||
         (rc = h->pool.ensure((size_t)h->pool_chunks * kChunk)) ||
-        (rc = h->dbg.ensure((size_t)h->max_rounds * TRACE_REC)) || (rc = h->px.ensure(S)) ||
+        (rc = h->dbg.ensure((size_t)h->max_rounds * TRACE_REC)) || (rc = h->px.ensure((size_t)S + 2 * (h->W + 2))) ||
         (rc = h->regs.ensure(h->reg_cap)) || (rc = h->rect_host.ensure(h->reg_cap)) || (rc = h->dir_host.ensure(h->reg_cap)) ||
         (rc = h->seg_host.ensure(h->reg_cap)) || (rc = h->status_host.ensure(4)) || (rc = h->nreg_host.ensure(1))) return rc;
+    // guard bands of the pixel records: zero = "final" claims, never a candidate (the grow pass may read, never use them)
+    OLF_CUDA(cudaMemset(h->px.p, 0, ((size_t)S + 2 * (h->W + 2)) * sizeof(PxRec)));
     h->img_w = w; h->img_h = hgt;
     return OLF_OK;
 }
@@ -1070,14 +1072,14 @@ static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D) {
     OLF_CUDA(cudaMemsetAsync(h->status.p, 0, 4 * sizeof(int), s));
     {
         dim3 g((W + 31) / 32, (H + 7) / 8);
-        k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->tab_acc.p, h->px.p, h->n2max.p);
+        k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->tab_acc.p, h->px.p + h->W + 2, h->n2max.p);
     }
     const int nb = h->P.lsd_n_bins;
     k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
     k_lsd_plan<<<1, 1024, 0, s>>>(h->hist.p, nb, h->first_wave, h->wave_growth, h->bin_start.p, h->cursor.p, h->plan.p);
-    k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p, h->px.p);
+    k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p, h->px.p + h->W + 2);
     count_launches((h->blur_k ? 2 : 0) + 4);
-    D.C.W = W; D.C.H = H; D.C.px = h->px.p; D.C.dabc = h->dabc.p; D.C.tab_seed = h->tab_seed.p;
+    D.C.W = W; D.C.H = H; D.C.px = h->px.p + W + 2; D.C.dabc = h->dabc.p; D.C.tab_seed = h->tab_seed.p;
     D.C.pool = h->pool.p; D.C.pool_ctr = h->ctrs.p; D.C.pool_chunks = h->pool_chunks;
     D.C.srec[0] = h->srec0.p; D.C.srec[1] = h->srec1.p; D.C.regang = h->regang.p;
     D.C.seed_pix = h->seed_pix.p; D.C.seed_prio = h->seed_prio.p; D.C.prec = h->prec;
