@@ -274,7 +274,7 @@ __device__ bool verify_long_warp(const GrowCtx& C, unsigned round, int i, int la
 // pass 2: every alive seed claims its pixel, then is carried over (verified) or sent to work list 2;
 // in finalise mode: every alive seed of the converged wave is stamped for good
 #define VERIFY_LONG 48
-__global__ void __launch_bounds__(128) k_lsd_verify(const __grid_constant__ GrowBatch B) {
+__global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ GrowBatch B) {
     __shared__ GrowDev s_dev;
     PhaseState* st;
     const GrowDev& D = batch_image(B, &s_dev, st);

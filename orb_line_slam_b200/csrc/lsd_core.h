@@ -224,6 +224,58 @@ struct ListReader {
     }
 };
 
+#if defined(__CUDACC__)
+#define OLF_UNROLL _Pragma("unroll")
+#else
+#define OLF_UNROLL
+#endif
+#if defined(__CUDA_ARCH__)
+struct Quad { unsigned v0, v1, v2, v3; };
+OLF_HD Quad ld_u32x4(const unsigned* p) { const uint4 q = *reinterpret_cast<const uint4*>(p); Quad r; r.v0 = q.x; r.v1 = q.y; r.v2 = q.z; r.v3 = q.w; return r; }
+#else
+struct Quad { unsigned v0, v1, v2, v3; };
+OLF_HD Quad ld_u32x4(const unsigned* p) { Quad r; r.v0 = p[0]; r.v1 = p[1]; r.v2 = p[2]; r.v3 = p[3]; return r; }
+#endif
+OLF_HD unsigned ld_u32(const unsigned* p) { return *p; }
+// Walk a chunked list FOUR entries per step: one 16-byte load of pixel indices (chunks are 128-byte aligned, entries
+// 28..30 share their quad with the link), then four independent claim loads -- two memory round trips per four pixels
+// instead of eight.  `what` 0: all pixels free of higher-priority claims of round-1?  1: all pixels still held?
+// 2: re-stamp for this round (always true).
+OLF_HD bool walk_bad(u64 ep, int what, u64 sf_prev, u64 prio) {
+    const u64 sf = ep >> 40;
+    const bool higher = sf == sf_prev && (ep & kPrioMask) < prio;
+    return what == 0 ? higher : !(sf == 0 || higher);
+}
+OLF_HD bool walk_list4(const GrowCtx& C, unsigned head, int cnt, int what, int prv, int cur, u64 sf_prev, u64 prio, u64 mine, unsigned skip) {
+    unsigned chunk = head;
+    for (int k = 0; k < cnt; k += kChunk - 1) {
+        const int nc = cnt - k < kChunk - 1 ? cnt - k : kChunk - 1;
+        const unsigned* base = &C.pool[(size_t)chunk * kChunk];
+        for (int j = 0; j < nc; j += 4) {
+            const Quad q = ld_u32x4(base + j);
+            const int m = nc - j;                                   // entries of this quad that belong to the list: min(m, 4)
+            if (what == 2) {
+                if (q.v0 != skip) red_min64(&C.px[q.v0].claim[cur], mine);
+                if (m > 1 && q.v1 != skip) red_min64(&C.px[q.v1].claim[cur], mine);
+                if (m > 2 && q.v2 != skip) red_min64(&C.px[q.v2].claim[cur], mine);
+                if (m > 3 && q.v3 != skip) red_min64(&C.px[q.v3].claim[cur], mine);
+            } else {
+                const u64 e0 = ld_claim(&C.px[q.v0], prv);
+                const u64 e1 = m > 1 ? ld_claim(&C.px[q.v1], prv) : 0;
+                const u64 e2 = m > 2 ? ld_claim(&C.px[q.v2], prv) : 0;
+                const u64 e3 = m > 3 ? ld_claim(&C.px[q.v3], prv) : 0;
+                bool bad = walk_bad(e0, what, sf_prev, prio);
+                bad |= m > 1 && walk_bad(e1, what, sf_prev, prio);
+                bad |= m > 2 && walk_bad(e2, what, sf_prev, prio);
+                bad |= m > 3 && walk_bad(e3, what, sf_prev, prio);
+                if (bad) return false;
+            }
+        }
+        if (k + nc < cnt) chunk = ld_u32(base + kChunk - 1);
+    }
+    return true;
+}
+
 // ---- pass 2: verify -----------------------------------------------------------------------------------------------
 enum VerifyResult { kSeedDead = 0, kSeedCarried = 1, kSeedGrow = 2, kSeedLong = 3 };
 // One alive seed (index i in the seed arrays).  `have_prev` = the seed may own a list from round-1 (false in the first
@@ -259,30 +311,11 @@ OLF_HD VerifyResult verify_seed(const GrowCtx& C, unsigned round, int i, bool ha
     if (pr.cnt <= 0) return kSeedGrow;
     if (pr.cnt + pr.bcnt > long_cnt) return kSeedLong;
     // every pixel accepted last round must still be free of higher-priority claims of that round
-    {
-        ListReader rd; rd.init(pr.head);
-        for (int k = 0; k < pr.cnt; ++k) {
-            const unsigned v = rd.next(C.pool);
-            const u64 ep = ld_claim(&C.px[v], prv);
-            if ((ep >> 40) == sf_prev && (ep & kPrioMask) < prio) return kSeedGrow;
-        }
-    }
+    if (!walk_list4(C, pr.head, pr.cnt, 0, prv, cur, sf_prev, prio, mine, kNull)) return kSeedGrow;
     // every aligned candidate refused last round (by a non-final claim) must still be held
-    ListReader rb; rb.init(pr.bchunk);
-    for (int k = 0; k < pr.bcnt; ++k) {
-        const unsigned v = rb.next(C.pool);
-        const u64 ep = ld_claim(&C.px[v], prv);
-        const u64 sf = ep >> 40;
-        if (!((sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio))) return kSeedGrow;
-    }
+    if (!walk_list4(C, pr.bchunk, pr.bcnt, 1, prv, cur, sf_prev, prio, mine, kNull)) return kSeedGrow;
     // carry the region over: re-stamp its claims for this round
-    {
-        ListReader rd; rd.init(pr.head);
-        for (int k = 0; k < pr.cnt; ++k) {
-            const unsigned v = rd.next(C.pool);
-            if (v != (unsigned)seed) red_min64(&C.px[v].claim[cur], mine);
-        }
-    }
+    walk_list4(C, pr.head, pr.cnt, 2, prv, cur, sf_prev, prio, mine, (unsigned)seed);
     C.srec[cur][i] = pr;
     return kSeedCarried;
 }
