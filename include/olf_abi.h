@@ -196,6 +196,47 @@ typedef struct olf_sbp_map_args {
 } olf_sbp_map_args;
 int olf_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur /*n_points*/, int* nmatches, int device);
 
+/* ---- next row: bag of words -- Frame::ComputeBoW (src/Frame.cc:585-597) and ORBmatcher::SearchByBoW -------- */
+/* DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h) flattened: node 0 is the
+ * root; the children of node i are children[child_begin[i] .. child_begin[i] + child_count[i]) in the order of
+ * m_nodes[i].children; a node without children is a leaf = a word.  The same structure serves the line vocabulary
+ * (LBD descriptors are 32 bytes too). */
+typedef struct olf_vocab_desc {
+    int k, L, n_nodes;
+    const uint8_t* node_desc;              /* n_nodes x 32  m_nodes[i].descriptor (root: unused)              */
+    const int*     child_begin;            /* n_nodes                                                         */
+    const int*     child_count;            /* n_nodes       0 = leaf                                          */
+    const int*     children;               /* concatenated child node ids                                     */
+    const int*     word_id;                /* n_nodes       m_nodes[i].word_id of a leaf                      */
+    const double*  weight;                 /* n_nodes       m_nodes[i].weight of a leaf (0 = stopped word)    */
+} olf_vocab_desc;
+typedef struct olf_vocab olf_vocab;
+olf_vocab* olf_vocab_create(const olf_vocab_desc* v, int device);      /* copies the tree to the device */
+void olf_vocab_destroy(olf_vocab* v);
+/* TemplatedVocabulary::transform(feature, word_id, weight, &nid, levelsup) (TemplatedVocabulary.h:1218-1260) for n
+ * descriptors: tree descent by Hamming distance (FORB::distance, first minimum wins), per feature its word, the word's
+ * weight and its ancestor `levelsup` levels above the leaves (levelsup >= L: the root, 0).  The O(n) assembly of
+ * BowVector / FeatureVector (std::map order, double sums in feature order, L1 normalisation -- transform(features, v, fv,
+ * levelsup) :1131-1194 with TF_IDF + L1_NORM) stays with the caller: olf_bow_assemble does it on the host. */
+int olf_bow_transform(olf_vocab* v, const uint8_t* desc, int n, int levelsup, int* word_id, double* weight, int* node_id);
+/* BowVector as (word ascending, value) and FeatureVector as CSR over node ids ascending; capacities >= n.
+ * n_words / n_nodes: entries written. */
+int olf_bow_assemble(const int* word_id, const double* weight, const int* node_id, int n,
+                     int* bow_word, double* bow_value, int* n_words,
+                     int* fv_node, int* fv_begin /* n_nodes + 1 */, int* fv_index /* n */, int* n_nodes);
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:161-290): for every vocabulary node the
+ * key frame and the frame share, each key-frame feature with a good map point takes the closest still-unmatched frame
+ * feature of that node (best <= TH_LOW, best < nn_ratio * second), then the rotation-histogram filter. */
+typedef struct olf_bow_match_args {
+    const uint8_t* kf_desc; const olf_keypoint* kf_kps_un; int n_kf;
+    const uint8_t* kf_has_point;           /* n_kf  pMP != NULL && !pMP->isBad()                                */
+    const int* kf_fv_node; const int* kf_fv_begin; const int* kf_fv_index; int kf_n_nodes;     /* pKF->mFeatVec */
+    const uint8_t* f_desc; const olf_keypoint* f_kps; int n_f;
+    const int* f_fv_node; const int* f_fv_begin; const int* f_fv_index; int f_n_nodes;         /* F.mFeatVec    */
+    float nn_ratio; int check_orientation;
+} olf_bow_match_args;
+int olf_search_by_bow(const olf_bow_match_args* a, int* match_f /* n_f: key-frame feature index or -1 */, int* nmatches, int device);
+
 /* ---- whole stereo frame: Frame::Frame(stereo+lines) (src/Frame.cc:136-221) ----------------------------------- */
 /* One rig = 2 ORB extractors + 2 line extractors on one device; olf_frontend_process runs ExtractORB(L|R) and
  * ExtractLine(L|R) on its own host threads (src/Frame.cc:164-171), then ComputeStereoMatches and

@@ -45,6 +45,14 @@ int orc_stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf
                      int img_w, int img_h, const olf_line_match_params* P, int* matches12, float* disp, double* le);
 int orc_search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches);
 int orc_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches);
+/* bag of words (oracle/bow.cpp) */
+typedef struct orc_vocab orc_vocab;
+orc_vocab* orc_vocab_create(const olf_vocab_desc* v);
+void orc_vocab_destroy(orc_vocab* v);
+int orc_bow_transform(orc_vocab* v, const uint8_t* desc, int n, int levelsup, int* word_id, double* weight, int* node_id);
+int orc_bow_assemble(const int* word_id, const double* weight, const int* node_id, int n, int* bow_word, double* bow_value, int* n_words,
+                     int* fv_node, int* fv_begin, int* fv_index, int* n_nodes);
+int orc_search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches);
 
 /* cv primitive wrappers for the cv2 pinning tests */
 void orc_resize_linear(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);

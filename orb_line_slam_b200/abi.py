@@ -65,6 +65,20 @@ class FrameOffsets(C.Structure):
                                           "kls_r", "ldesc_r", "lmatch", "ldisp", "lle", "total")]
 
 
+class VocabDesc(C.Structure):
+    """olf_vocab_desc: a DBoW2 vocabulary tree flattened (include/olf_abi.h)."""
+    _fields_ = [("k", C.c_int), ("L", C.c_int), ("n_nodes", C.c_int), ("node_desc", _P), ("child_begin", _P), ("child_count", _P),
+                ("children", _P), ("word_id", _P), ("weight", _P)]
+
+
+class BowMatchArgs(C.Structure):
+    _fields_ = [("kf_desc", _P), ("kf_kps_un", _P), ("n_kf", C.c_int), ("kf_has_point", _P),
+                ("kf_fv_node", _P), ("kf_fv_begin", _P), ("kf_fv_index", _P), ("kf_n_nodes", C.c_int),
+                ("f_desc", _P), ("f_kps", _P), ("n_f", C.c_int),
+                ("f_fv_node", _P), ("f_fv_begin", _P), ("f_fv_index", _P), ("f_n_nodes", C.c_int),
+                ("nn_ratio", C.c_float), ("check_orientation", C.c_int)]
+
+
 class SbpLastArgs(C.Structure):
     _fields_ = [("cur_kps", _P), ("cur_desc", _P), ("cur_u_right", _P), ("n_cur", C.c_int),
                 ("cam", Camera), ("scale_factors", _P), ("nlevels", C.c_int),
@@ -282,6 +296,53 @@ class FrontEndApi:
         rc = self.fn("search_by_projection_last")(C.byref(args), ptr(a), ptr(c), C.byref(n), *self._dev)
         self.check(rc, "search_by_projection_last")
         return a, c, n.value
+
+    # ---- bag of words ----
+    def vocab_create(self, tree: dict):
+        """tree: dict(k, L, node_desc (n,32) u8, child_begin, child_count, children, word_id (int32), weight (float64))."""
+        keep = {k: np.ascontiguousarray(tree[k], dt) for k, dt in (("node_desc", np.uint8), ("child_begin", np.int32), ("child_count", np.int32),
+                                                                   ("children", np.int32), ("word_id", np.int32), ("weight", np.float64))}
+        d = VocabDesc(int(tree["k"]), int(tree["L"]), len(keep["child_begin"]), ptr(keep["node_desc"]), ptr(keep["child_begin"]),
+                      ptr(keep["child_count"]), ptr(keep["children"]), ptr(keep["word_id"]), ptr(keep["weight"]))
+        f = self.fn("vocab_create"); f.restype = C.c_void_p
+        h = f(C.byref(d), *self._dev)
+        if not h:
+            self.check(OLF_ERR_INTERNAL, "vocab_create")
+        return C.c_void_p(h)
+
+    def vocab_destroy(self, h):
+        f = self.fn("vocab_destroy"); f.restype = None; f(h)
+
+    def bow_transform(self, vocab, desc, levelsup=4):
+        """Per feature: (word id, word weight, node id `levelsup` levels above the leaves)."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        w = np.zeros(n, np.int32); v = np.zeros(n, np.float64); nd = np.zeros(n, np.int32)
+        self.check(self.fn("bow_transform")(vocab, ptr(desc), C.c_int(n), C.c_int(levelsup), ptr(w), ptr(v), ptr(nd)), "bow_transform")
+        return w, v, nd
+
+    def bow_assemble(self, word_id, weight, node_id):
+        """BowVector (words ascending, L1-normalised values) and FeatureVector (CSR over node ids ascending)."""
+        n = len(word_id)
+        bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64); nw = C.c_int(0)
+        fn_ = np.zeros(max(n, 1), np.int32); fb = np.zeros(n + 1, np.int32); fi = np.zeros(max(n, 1), np.int32); nn = C.c_int(0)
+        rc = self.fn("bow_assemble")(ptr(np.ascontiguousarray(word_id, np.int32)), ptr(np.ascontiguousarray(weight, np.float64)),
+                                     ptr(np.ascontiguousarray(node_id, np.int32)), C.c_int(n), ptr(bw), ptr(bv), C.byref(nw), ptr(fn_), ptr(fb), ptr(fi), C.byref(nn))
+        self.check(rc, "bow_assemble")
+        return bw[:nw.value].copy(), bv[:nw.value].copy(), fn_[:nn.value].copy(), fb[:nn.value + 1].copy(), fi[:fb[nn.value]].copy()
+
+    def search_by_bow(self, kf_desc, kf_kps, kf_has_point, kf_fv, f_desc, f_kps, f_fv, nn_ratio=0.7, check_orientation=True):
+        """ORBmatcher::SearchByBoW(KeyFrame*, Frame&): kf_fv / f_fv = (node, begin, index) from bow_assemble; returns (match_f, n)."""
+        keep = [np.ascontiguousarray(kf_desc, np.uint8), np.ascontiguousarray(kf_kps), np.ascontiguousarray(kf_has_point, np.uint8),
+                np.ascontiguousarray(kf_fv[0], np.int32), np.ascontiguousarray(kf_fv[1], np.int32), np.ascontiguousarray(kf_fv[2], np.int32),
+                np.ascontiguousarray(f_desc, np.uint8), np.ascontiguousarray(f_kps),
+                np.ascontiguousarray(f_fv[0], np.int32), np.ascontiguousarray(f_fv[1], np.int32), np.ascontiguousarray(f_fv[2], np.int32)]
+        a = BowMatchArgs(ptr(keep[0]), ptr(keep[1]), len(keep[0]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(keep[5]), len(keep[3]),
+                         ptr(keep[6]), ptr(keep[7]), len(keep[6]), ptr(keep[8]), ptr(keep[9]), ptr(keep[10]), len(keep[8]),
+                         nn_ratio, int(check_orientation))
+        m = np.zeros(max(len(keep[6]), 1), np.int32); n = C.c_int(0)
+        self.check(self.fn("search_by_bow")(C.byref(a), ptr(m), C.byref(n), *self._dev), "search_by_bow")
+        return m[:len(keep[6])], n.value
 
     def search_by_projection_map(self, args: SbpMapArgs, keep):
         a = np.zeros(args.n_points, np.int32); n = C.c_int(0)

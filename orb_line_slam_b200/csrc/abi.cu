@@ -129,4 +129,14 @@ int olf_search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur,
 int olf_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches, int device) {
     return search_by_projection_map(a, assigned_cur, nmatches, device);
 }
+olf_vocab* olf_vocab_create(const olf_vocab_desc* v, int device) { return (olf_vocab*)vocab_create(v, device); }
+void olf_vocab_destroy(olf_vocab* v) { vocab_destroy((VocabImpl*)v); }
+int olf_bow_transform(olf_vocab* v, const uint8_t* desc, int n, int levelsup, int* word_id, double* weight, int* node_id) {
+    return bow_transform((VocabImpl*)v, desc, n, levelsup, word_id, weight, node_id);
+}
+int olf_bow_assemble(const int* word_id, const double* weight, const int* node_id, int n, int* bow_word, double* bow_value, int* n_words,
+                     int* fv_node, int* fv_begin, int* fv_index, int* n_nodes) {
+    return bow_assemble(word_id, weight, node_id, n, bow_word, bow_value, n_words, fv_node, fv_begin, fv_index, n_nodes);
+}
+int olf_search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches, int device) { return search_by_bow(a, match_f, nmatches, device); }
 }

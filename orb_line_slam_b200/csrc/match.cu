@@ -813,4 +813,239 @@ int search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* 
     return OLF_OK;
 }
 
+// ======================================================================================================
+// Bag of words: Frame::ComputeBoW (src/Frame.cc:585-597) -> TemplatedVocabulary::transform
+// (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1260), and ORBmatcher::SearchByBoW (src/ORBmatcher.cc:161-290)
+// ======================================================================================================
+struct VocabImpl {
+    int device = 0, k = 0, L = 0, n = 0;
+    DevBuf<uint4> desc; DevBuf<int> child_begin, child_count, children, word_id; DevBuf<double> weight;
+};
+VocabImpl* vocab_create(const olf_vocab_desc* v, int device) {
+    if (!v || v->n_nodes < 1 || !v->node_desc || !v->child_begin || !v->child_count || !v->children || !v->word_id || !v->weight || v->child_count[0] < 1) {
+        set_last_error("olf_vocab_create: bad arguments"); return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError(); set_last_error("olf_vocab_create: no such CUDA device (this library has no CPU path)"); return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return nullptr; }
+    int nch = 0;
+    for (int i = 0; i < v->n_nodes; ++i) {
+        if (v->child_count[i] < 0 || v->child_begin[i] < 0) { set_last_error("olf_vocab_create: bad tree"); return nullptr; }
+        nch = std::max(nch, v->child_begin[i] + v->child_count[i]);
+    }
+    for (int i = 0; i < nch; ++i) if (v->children[i] <= 0 || v->children[i] >= v->n_nodes) { set_last_error("olf_vocab_create: bad tree"); return nullptr; }
+    VocabImpl* h = new VocabImpl();
+    h->device = device; h->k = v->k; h->L = v->L; h->n = v->n_nodes;
+    const size_t n = (size_t)v->n_nodes;
+    bool ok = h->desc.ensure(2 * n) == OLF_OK && h->child_begin.ensure(n) == OLF_OK && h->child_count.ensure(n) == OLF_OK &&
+              h->children.ensure(std::max(nch, 1)) == OLF_OK && h->word_id.ensure(n) == OLF_OK && h->weight.ensure(n) == OLF_OK;
+    ok = ok && cudaMemcpy(h->desc.p, v->node_desc, n * 32, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->child_begin.p, v->child_begin, n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->child_count.p, v->child_count, n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->children.p, v->children, (size_t)nch * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->word_id.p, v->word_id, n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->weight.p, v->weight, n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) { set_last_error(std::string("olf_vocab_create: ") + cudaGetErrorString(cudaGetLastError())); vocab_destroy(h); return nullptr; }
+    return h;
+}
+void vocab_destroy(VocabImpl* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->desc.release(); h->child_begin.release(); h->child_count.release(); h->children.release(); h->word_id.release(); h->weight.release();
+    delete h;
+}
+// thread per descriptor: descend the tree, at every node the first child at minimal Hamming distance (strict <)
+__global__ void __launch_bounds__(128) k_bow_transform(const uint4* __restrict__ feat, int n, const uint4* __restrict__ ndesc,
+                                                       const int* __restrict__ child_begin, const int* __restrict__ child_count,
+                                                       const int* __restrict__ children, const int* __restrict__ word_id,
+                                                       const double* __restrict__ weight, int nid_level,
+                                                       int* __restrict__ out_word, double* __restrict__ out_weight, int* __restrict__ out_node) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const uint4 a = feat[2 * f], b = feat[2 * f + 1];
+    int nid = 0, final_id = 0, level = 0;
+    do {
+        ++level;
+        const int cb = child_begin[final_id], cc = child_count[final_id];
+        int best = INT_MAX, best_id = 0;
+        for (int c = 0; c < cc; ++c) {
+            const int id = children[cb + c];
+            const uint4 x = ndesc[2 * (size_t)id], y = ndesc[2 * (size_t)id + 1];
+            const int d = __popc(a.x ^ x.x) + __popc(a.y ^ x.y) + __popc(a.z ^ x.z) + __popc(a.w ^ x.w) +
+                          __popc(b.x ^ y.x) + __popc(b.y ^ y.y) + __popc(b.z ^ y.z) + __popc(b.w ^ y.w);
+            if (d < best) { best = d; best_id = id; }
+        }
+        final_id = best_id;
+        if (level == nid_level) nid = final_id;
+    } while (child_count[final_id] != 0);
+    out_word[f] = word_id[final_id]; out_weight[f] = weight[final_id]; out_node[f] = nid;
+}
+int bow_transform(VocabImpl* V, const uint8_t* desc, int n, int levelsup, int* word_id, double* weight, int* node_id) {
+    if (!V || n < 0 || (n && (!desc || !word_id || !weight || !node_id))) { set_last_error("olf_bow_transform: bad arguments"); return OLF_ERR_ARG; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(V->device, &c))) return rc;
+    if (n == 0) return OLF_OK;
+    Planner pl;
+    const size_t o_f = pl.d((size_t)n * 32), o_w = pl.d((size_t)n * 4), o_v = pl.d((size_t)n * 8), o_n = pl.d((size_t)n * 4);
+    const size_t p_f = pl.p((size_t)n * 32), p_w = pl.p((size_t)n * 4), p_v = pl.p((size_t)n * 8), p_n = pl.p((size_t)n * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->cur;
+    memcpy(hptr<uint8_t>(c, p_f), desc, (size_t)n * 32);
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_f), hptr<uint8_t>(c, p_f), (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    k_bow_transform<<<(n + 127) / 128, 128, 0, s>>>(dptr<uint4>(c, o_f), n, V->desc.p, V->child_begin.p, V->child_count.p, V->children.p, V->word_id.p,
+                                                    V->weight.p, V->L - levelsup, dptr<int>(c, o_w), dptr<double>(c, o_v), dptr<int>(c, o_n));
+    count_launches(1);
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_w), dptr<int>(c, o_w), (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(hptr<double>(c, p_v), dptr<double>(c, o_v), (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_n), dptr<int>(c, o_n), (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(stream_sync(s));
+    memcpy(word_id, hptr<int>(c, p_w), (size_t)n * 4); memcpy(weight, hptr<double>(c, p_v), (size_t)n * 8); memcpy(node_id, hptr<int>(c, p_n), (size_t)n * 4);
+    return OLF_OK;
+}
+// transform(features, v, fv, levelsup) with TF_IDF + L1_NORM (TemplatedVocabulary.h:1131-1194): the O(n) std::map bookkeeping,
+// host side by design (double sums in feature order, words / nodes ascending)
+int bow_assemble(const int* word_id, const double* weight, const int* node_id, int n, int* bow_word, double* bow_value, int* n_words,
+                 int* fv_node, int* fv_begin, int* fv_index, int* n_nodes) {
+    if (n < 0 || !n_words || !n_nodes || (n && (!word_id || !weight || !node_id || !bow_word || !bow_value || !fv_node || !fv_begin || !fv_index))) {
+        set_last_error("olf_bow_assemble: bad arguments"); return OLF_ERR_ARG;
+    }
+    std::vector<int> ord;                                          // features that are not stopped, in feature order
+    for (int i = 0; i < n; ++i) if (weight[i] > 0) ord.push_back(i);
+    std::vector<int> by_word(ord), by_node(ord);
+    std::stable_sort(by_word.begin(), by_word.end(), [&](int a, int b) { return (unsigned)word_id[a] < (unsigned)word_id[b]; });
+    std::stable_sort(by_node.begin(), by_node.end(), [&](int a, int b) { return (unsigned)node_id[a] < (unsigned)node_id[b]; });
+    int k = 0;
+    for (size_t i = 0; i < by_word.size();) {                      // BowVector::addWeight: v[word] += w in feature order
+        const int w = word_id[by_word[i]];
+        double acc = weight[by_word[i]];
+        size_t j = i + 1;
+        for (; j < by_word.size() && word_id[by_word[j]] == w; ++j) acc += weight[by_word[j]];
+        bow_word[k] = w; bow_value[k] = acc; ++k; i = j;
+    }
+    double norm = 0.0;                                             // BowVector::normalize(L1)
+    for (int i = 0; i < k; ++i) norm += std::fabs(bow_value[i]);
+    if (norm > 0.0) for (int i = 0; i < k; ++i) bow_value[i] /= norm;
+    *n_words = k;
+    int m = 0, pos = 0;
+    for (size_t i = 0; i < by_node.size();) {                      // FeatureVector::addFeature
+        const int nd = node_id[by_node[i]];
+        fv_node[m] = nd; fv_begin[m] = pos;
+        for (; i < by_node.size() && node_id[by_node[i]] == nd; ++i) fv_index[pos++] = by_node[i];
+        ++m;
+    }
+    if (fv_begin) fv_begin[m] = pos;
+    *n_nodes = m;
+    return OLF_OK;
+}
+
+// warp per vocabulary node shared by the key frame and the frame: the key-frame features of the node in order (the
+// "already matched" rule is loop-carried inside a node only: a frame feature belongs to one node), the frame features of
+// the node over the lanes, (best, first index, second best) by shuffle
+struct BowPair { int kf_b, kf_e, f_b, f_e; };
+__global__ void __launch_bounds__(128) k_bow_match(const BowPair* __restrict__ pairs, int n_pairs, const uint4* __restrict__ kf_desc,
+                                                   const uint8_t* __restrict__ kf_has, const int* __restrict__ kf_idx,
+                                                   const uint4* __restrict__ f_desc, const int* __restrict__ f_idx, float nn_ratio,
+                                                   int* match_f) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_pairs) return;
+    const BowPair P = pairs[w];
+    for (int p = P.kf_b; p < P.kf_e; ++p) {
+        const int ikf = kf_idx[p];
+        if (!kf_has[ikf]) continue;
+        const uint4 a = kf_desc[2 * ikf], b = kf_desc[2 * ikf + 1];
+        int d1 = 256, pos1 = INT_MAX, i1 = -1, d2 = 256;
+        for (int q = P.f_b + lane; q < P.f_e; q += 32) {
+            const int jf = f_idx[q];
+            if (*(volatile int*)&match_f[jf] >= 0) continue;
+            const uint4 x = f_desc[2 * jf], y = f_desc[2 * jf + 1];
+            const int d = __popc(a.x ^ x.x) + __popc(a.y ^ x.y) + __popc(a.z ^ x.z) + __popc(a.w ^ x.w) +
+                          __popc(b.x ^ y.x) + __popc(b.y ^ y.y) + __popc(b.z ^ y.z) + __popc(b.w ^ y.w);
+            if (d < d1) { d2 = d1; d1 = d; pos1 = q; i1 = jf; }
+            else if (d < d2) d2 = d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int e1 = __shfl_xor_sync(0xffffffffu, d1, o), ep = __shfl_xor_sync(0xffffffffu, pos1, o);
+            const int ei = __shfl_xor_sync(0xffffffffu, i1, o), e2 = __shfl_xor_sync(0xffffffffu, d2, o);
+            if (e1 < d1 || (e1 == d1 && ep < pos1)) { d2 = min(e2, d1); d1 = e1; pos1 = ep; i1 = ei; }
+            else d2 = min(d2, e1);
+        }
+        if (lane == 0 && i1 >= 0 && d1 <= OLF_TH_LOW && (float)d1 < fmul(nn_ratio, (float)d2)) match_f[i1] = ikf;
+        __syncwarp();
+    }
+}
+int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches_out, int device) {
+    if (!a || !match_f || !nmatches_out || a->n_kf < 0 || a->n_f < 0) { set_last_error("olf_search_by_bow: bad arguments"); return OLF_ERR_ARG; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    *nmatches_out = 0;
+    for (int i = 0; i < a->n_f; ++i) match_f[i] = -1;
+    // the nodes both feature vectors contain (merge of two ascending lists = the lower_bound walk of :185-279)
+    std::vector<BowPair> pairs;
+    for (int ik = 0, jf = 0; ik < a->kf_n_nodes && jf < a->f_n_nodes;) {
+        if (a->kf_fv_node[ik] == a->f_fv_node[jf]) { pairs.push_back({a->kf_fv_begin[ik], a->kf_fv_begin[ik + 1], a->f_fv_begin[jf], a->f_fv_begin[jf + 1]}); ++ik; ++jf; }
+        else if (a->kf_fv_node[ik] < a->f_fv_node[jf]) ++ik;
+        else ++jf;
+    }
+    if (pairs.empty() || a->n_f == 0 || a->n_kf == 0) return OLF_OK;
+    const int nkf_idx = a->kf_fv_begin[a->kf_n_nodes], nf_idx = a->f_fv_begin[a->f_n_nodes], np = (int)pairs.size();
+    Planner pl;
+    const size_t o_kd = pl.d((size_t)a->n_kf * 32), o_kh = pl.d((size_t)a->n_kf), o_ki = pl.d((size_t)nkf_idx * 4), o_fd = pl.d((size_t)a->n_f * 32),
+                 o_fi = pl.d((size_t)nf_idx * 4), o_p = pl.d((size_t)np * sizeof(BowPair)), o_m = pl.d((size_t)a->n_f * 4);
+    const size_t p_kd = pl.p((size_t)a->n_kf * 32), p_kh = pl.p((size_t)a->n_kf), p_ki = pl.p((size_t)nkf_idx * 4), p_fd = pl.p((size_t)a->n_f * 32),
+                 p_fi = pl.p((size_t)nf_idx * 4), p_p = pl.p((size_t)np * sizeof(BowPair)), p_m = pl.p((size_t)a->n_f * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->cur;
+    auto up = [&](size_t po, size_t dof, const void* src, size_t bytes) -> cudaError_t {
+        memcpy(hptr<uint8_t>(c, po), src, bytes);
+        return cudaMemcpyAsync(dptr<uint8_t>(c, dof), hptr<uint8_t>(c, po), bytes, cudaMemcpyHostToDevice, s);
+    };
+    OLF_CUDA(up(p_kd, o_kd, a->kf_desc, (size_t)a->n_kf * 32)); OLF_CUDA(up(p_kh, o_kh, a->kf_has_point, (size_t)a->n_kf));
+    OLF_CUDA(up(p_ki, o_ki, a->kf_fv_index, (size_t)nkf_idx * 4)); OLF_CUDA(up(p_fd, o_fd, a->f_desc, (size_t)a->n_f * 32));
+    OLF_CUDA(up(p_fi, o_fi, a->f_fv_index, (size_t)nf_idx * 4)); OLF_CUDA(up(p_p, o_p, pairs.data(), (size_t)np * sizeof(BowPair)));
+    OLF_CUDA(cudaMemsetAsync(dptr<int>(c, o_m), 0xFF, (size_t)a->n_f * 4, s));
+    k_bow_match<<<(np * 32 + 127) / 128, 128, 0, s>>>(dptr<BowPair>(c, o_p), np, dptr<uint4>(c, o_kd), dptr<uint8_t>(c, o_kh), dptr<int>(c, o_ki),
+                                                      dptr<uint4>(c, o_fd), dptr<int>(c, o_fi), a->nn_ratio, dptr<int>(c, o_m));
+    count_launches(1);
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_m), dptr<int>(c, o_m), (size_t)a->n_f * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(stream_sync(s));
+    memcpy(match_f, hptr<int>(c, p_m), (size_t)a->n_f * 4);
+    // rotation histogram (:248-258, 281-302): O(#matches) bookkeeping on the host, like the projection matchers
+    int nm = 0;
+    std::vector<int> rot[OLF_HISTO_LENGTH];
+    const float factor = 1.0f / OLF_HISTO_LENGTH;
+    for (int j = 0; j < a->n_f; ++j) {
+        if (match_f[j] < 0) continue;
+        ++nm;
+        if (a->check_orientation) {
+            float r = a->kf_kps_un[match_f[j]].angle - a->f_kps[j].angle;
+            if (r < 0.0) r += 360.0f;
+            int bin = (int)roundf(r * factor);
+            if (bin == OLF_HISTO_LENGTH) bin = 0;
+            rot[bin].push_back(j);
+        }
+    }
+    if (a->check_orientation) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;          // ComputeThreeMaxima (:1749-1790)
+        for (int i = 0; i < OLF_HISTO_LENGTH; i++) {
+            const int sz = (int)rot[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < OLF_HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rot[i]) { match_f[j] = -1; --nm; }
+        }
+    }
+    *nmatches_out = nm;
+    return OLF_OK;
+}
+
 }  // namespace olf

@@ -15,4 +15,11 @@ int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_key
                  const olf_line_match_params* P, int* matches12, float* disp, double* le, int device);
 int search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device);
 int search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches, int device);
+struct VocabImpl;
+VocabImpl* vocab_create(const olf_vocab_desc* v, int device);
+void vocab_destroy(VocabImpl* h);
+int bow_transform(VocabImpl* V, const uint8_t* desc, int n, int levelsup, int* word_id, double* weight, int* node_id);
+int bow_assemble(const int* word_id, const double* weight, const int* node_id, int n, int* bow_word, double* bow_value, int* n_words,
+                 int* fv_node, int* fv_begin, int* fv_index, int* n_nodes);
+int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches, int device);
 }
