@@ -23,13 +23,14 @@ def best(f, reps=20):
         t = time.perf_counter(); r = f(); b = min(b, time.perf_counter() - t)
     return b * 1e3, r
 
-for name, api in (("GPU", g), ("CPU oracle", o)):
+# levelsup 4 of the reference's L=6 tree = 100 nodes at level 2; with L=5 that granularity is levelsup 3 (levelsup 4: 10 nodes)
+for name, api, levelsup in (("GPU", g, 3), ("CPU oracle", o, 3), ("GPU", g, 4), ("CPU oracle", o, 4)):
     v = api.vocab_create(tree)
-    t_tr, t0 = best(lambda: api.bow_transform(v, d0, 4))
-    t1 = api.bow_transform(v, d1, 4)
+    t_tr, t0 = best(lambda: api.bow_transform(v, d0, levelsup))
+    t1 = api.bow_transform(v, d1, levelsup)
     t_as, a0 = best(lambda: api.bow_assemble(*t0))
     a1 = api.bow_assemble(*t1)
     t_m, (m, n) = best(lambda: api.search_by_bow(d0, k0, np.ones(len(d0), np.uint8), a0[2:], d1, k1, a1[2:], 0.7, True))
-    print("%-10s transform(%d desc, L=5): %.3f ms   assemble: %.3f ms   SearchByBoW: %.3f ms (%d matches, %d shared nodes)" %
-          (name, len(d0), t_tr, t_as, t_m, n, len(np.intersect1d(a0[2], a1[2]))))
+    print("%-10s levelsup %d  transform(%d desc, L=5): %.3f ms   assemble: %.3f ms   SearchByBoW: %.3f ms (%d matches, %d shared nodes)" %
+          (name, levelsup, len(d0), t_tr, t_as, t_m, n, len(np.intersect1d(a0[2], a1[2]))))
     api.vocab_destroy(v)
