@@ -9,7 +9,7 @@
 // (atan2, sort by response, top-N) -- all O(#segments), the per-pixel work never leaves the device.
 #include "common.cuh"
 #include "img_kernels.cuh"
-#include "lsd_core.h"
+#include "lsd_sticky.h"
 #include "line.h"
 #include <algorithm>
 #include <cmath>
@@ -131,25 +131,27 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const float* __restrict__ a
         }
 }
 
-// ---- region growing: three passes per round, one thread per seed (semantics: lsd_core.h) ------------------------------
+// ---- region growing: three passes per round, one thread per seed (semantics: lsd_sticky.h) ----------------------------
 // The wave / round state machine lives on the device: the host enqueues a fixed batch of (scan, verify, grow) triples,
 // the last block of every grow launch advances {wave, round, mode}, launches after `done` return at once.  Ordinary
-// (non-cooperative) launches: no co-residency requirement, so the passes of the left/right eyes and of several frames in
-// flight interleave freely with every other kernel on the device.
+// (non-cooperative) launches: no co-residency requirement, so the passes of several rigs in flight interleave freely with
+// every other kernel on the device.
 #define TRACE_REC 8
 struct PhaseState {
-    int wave; unsigned round; int mode; int done;           // mode 0: round passes, 1: finalise the converged wave, 2: converged, waiting for the batch
+    int wave; unsigned round; int mode; int done;           // mode 0: round passes, 2: converged, waiting for the batch, 3: full verification, 1: finalise
     int launches; unsigned wave_first_round;
     unsigned wl0_cnt, wl1_cnt, wl2_cnt, wl2_pop, changed, ticket;
+    unsigned recheck, force, pad0, pad1;                     // full verification failed / the next round verifies every region
 };
 struct GrowDev {
-    GrowCtx C;
+    Ctx3 C;
     const LsdPlan* plan;
-    int* wl0; int* wl1; int* wl2;   // candidates of the wave (not finalised at its start) / alive seeds of the round / seeds that must (re)grow
+    int* wl0; int* wl1; int* wl2;   // candidates of the wave (not finalised at its start) / seeds to verify (~i: died) / seeds that must grow
     FinalOut F;
     int* status;                 // [0] error flag, [1] rounds used, [2] waves, [3] done
     unsigned max_rounds;
     int defer;                   // first round of a wave: seeds with a live higher-priority aligned neighbour wait
+    int dirty_words;             // words of one dirty bitmap
     int* dbg;                    // optional per-round trace (OLF_LSD_TRACE)
 };
 // One launch serves a BATCH of images (the two eyes of a stereo frame, several frames): blockIdx.y selects the image, every
@@ -159,11 +161,14 @@ struct GrowDev {
 #define LSD_MAX_WAVES 64
 struct GrowBatch { GrowDev d[LSD_MAX_BATCH]; PhaseState* st[LSD_MAX_BATCH]; unsigned* conv; int n; };   // conv[w]: images of the batch that have converged in wave w
 __device__ __forceinline__ const GrowDev& batch_image(const GrowBatch& B, GrowDev* sh, PhaseState*& st) {
-    // block-uniform copy of this image's descriptor into shared memory (the by-value batch lives in parameter space)
+    // block-uniform copy of this image's descriptor into shared memory (the by-value batch lives in parameter space);
+    // the claim stamp of the image's current wave is filled in here
     const int* src = reinterpret_cast<const int*>(&B.d[blockIdx.y]);
     int* dst = reinterpret_cast<int*>(sh);
     for (int k = threadIdx.x; k < (int)(sizeof(GrowDev) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
     st = B.st[blockIdx.y];
+    __syncthreads();
+    if (threadIdx.x == 0) sh->C.stamp = (u64)(0xFFFFFFu - (unsigned)(st->wave + 1)) << 40;
     __syncthreads();
     return *sh;
 }
@@ -184,7 +189,8 @@ __device__ __forceinline__ void wl_append(bool take, int value, int* __restrict_
     if (take) list[base + __popc(m & lanemask_lt())] = value;
 }
 
-// pass 1: every seed of the wave -- dead or alive (+ first-round deferral); alive seeds go to work list 1
+// pass 1: every candidate of the wave -- dead or alive (+ first-round deferral); alive seeds and seeds that died owning a
+// region go to work list 1; the bitmap that collects THIS round's events is cleared
 __global__ void __launch_bounds__(256) k_lsd_scan(const __grid_constant__ GrowBatch B) {
     __shared__ GrowDev s_dev;
     PhaseState* st;
@@ -195,84 +201,67 @@ __global__ void __launch_bounds__(256) k_lsd_scan(const __grid_constant__ GrowBa
     const unsigned round = st->round;
     const bool first_round = round == st->wave_first_round;
     const int lo = D.plan->wave_start[wv], hi = D.plan->wave_start[wv + 1];
-    const int cur = round & 1, prv = cur ^ 1;
     if (D.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
         D.dbg[round * TRACE_REC + 0] = wv; D.dbg[round * TRACE_REC + 1] = hi - lo; D.dbg[round * TRACE_REC + 2] = (int)(gtime() & 0x7fffffff);
     }
+    if (blockIdx.x == 0) for (int k = threadIdx.x; k < D.dirty_words; k += blockDim.x) D.C.dirty[round & 1][k] = 0u;
     bool chg = false;
     // first round of a wave: all its seeds, those not yet swallowed by a finalised region become the wave's candidates;
     // later rounds: the candidates only
     const int first = first_round ? lo : 0, last = first_round ? hi : (int)st->wl0_cnt;
     for (int base = first + blockIdx.x * blockDim.x; base < last; base += gridDim.x * blockDim.x) {
         const int j = base + threadIdx.x;
-        bool alive = false, cand = false;
-        int i = 0;
+        bool cand = false, list = false;
+        int i = 0, entry = 0;
         if (j < last) {
             i = first_round ? j : D.wl0[j];
             const int seed = D.C.seed_pix[i]; const u64 prio = D.C.seed_prio[i];
-            cand = first_round && !seed_final(D.C, seed);
+            cand = first_round && !s3_final(D.C, seed);
+            if (cand) { SeedRec3 z; z.head = kNull; z.cnt = 0; z.bhead = kNull; z.bcnt = 0; z.x0 = z.y0 = z.x1 = z.y1 = 0; z.pad0 = z.pad1 = 0; D.C.srec[i] = z; }
             if (cand || !first_round) {
-                alive = seed_alive(D.C, round, seed, prio);
-                bool deferred = false;
-                if (alive && first_round && D.defer && seed_deferred(D.C, round, seed, prio)) { alive = false; deferred = true; }
-                if (!alive) {
-                    if (deferred || (!first_round && D.C.srec[prv][i].cnt != 0)) chg = true;
-                    SeedRec z; z.head = kNull; z.cnt = 0; z.bchunk = kNull; z.bcnt = 0;
-                    D.C.srec[cur][i] = z;
-                }
+                const bool alive = s3_alive(D.C, seed, prio);
+                if (alive && first_round && D.defer && s3_deferred(D.C, seed, prio)) chg = true;       // sits this round out
+                else if (alive) { list = true; entry = i; }
+                else if (!first_round && D.C.srec[i].cnt > 0) { list = true; entry = ~i; }               // died owning a region
             }
         }
         if (first_round) wl_append(cand, i, D.wl0, &st->wl0_cnt);
-        wl_append(alive, i, D.wl1, &st->wl1_cnt);
+        wl_append(list, entry, D.wl1, &st->wl1_cnt);
     }
     if (__syncthreads_or(chg) && threadIdx.x == 0) st->changed = 1;
 }
 
-// Warp-cooperative verify of ONE long list (the thread-per-seed loop of verify_seed() would be the round's critical path):
-// 31 pixels of a chunk per step.  The seed pixel has been claimed by verify_seed().  Returns true if the region is carried.
-__device__ bool verify_long_warp(const GrowCtx& C, unsigned round, int i, int lane) {
-    const int cur = round & 1, prv = cur ^ 1;
-    const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
-    const int seed = C.seed_pix[i]; const u64 prio = C.seed_prio[i];
-    const u64 mine = (sf_cur << 40) | prio;
-    const SeedRec pr = C.srec[prv][i];
+// Warp-cooperative check / release of ONE long list (31 entries of a chunk per step).
+// what 0: every pixel still mine?  1: every refused candidate still held (or final)?
+__device__ bool walk3_warp(const Ctx3& C, unsigned head, int cnt, int what, u64 mine, int lane) {
     bool ok = true;
-    unsigned chunk = pr.head;
-    for (int k = 0; k < pr.cnt && ok; k += kChunk - 1) {
+    unsigned chunk = head;
+    for (int k = 0; k < cnt && ok; k += kChunk - 1) {
         const unsigned v = C.pool[(size_t)chunk * kChunk + lane];
         bool bad = false;
-        if (lane < kChunk - 1 && k + lane < pr.cnt) {
-            const u64 ep = ld_claim(&C.px[v], prv);
-            bad = ((ep >> 40) == sf_prev) && ((ep & kPrioMask) < prio);
+        if (lane < kChunk - 1 && k + lane < cnt) {
+            const u64 c = ld_claim0(&C.px[v]);
+            bad = what == 0 ? c != mine : !(c < mine);
         }
         ok = !__any_sync(0xffffffffu, bad);
         chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
     }
-    chunk = pr.bchunk;
-    for (int k = 0; k < pr.bcnt && ok; k += kChunk - 1) {
+    return ok;
+}
+__device__ void release3_warp(const Ctx3& C, unsigned round, unsigned head, int cnt, u64 mine, unsigned keep, int lane) {
+    unsigned chunk = head;
+    for (int k = 0; k < cnt; k += kChunk - 1) {
         const unsigned v = C.pool[(size_t)chunk * kChunk + lane];
-        bool bad = false;
-        if (lane < kChunk - 1 && k + lane < pr.bcnt) {
-            const u64 ep = ld_claim(&C.px[v], prv);
-            const u64 sf = ep >> 40;
-            bad = !((sf == 0) || (sf == sf_prev && (ep & kPrioMask) < prio));      // no longer held -> must re-grow
-        }
-        ok = !__any_sync(0xffffffffu, bad);
+        if (lane < kChunk - 1 && k + lane < cnt && v != keep)
+            if (atomicCAS(&C.px[v].claim[0], mine, kClaimNone) == mine) mark_dirty(C, round, v);
         chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
     }
-    if (!ok) return false;
-    chunk = pr.head;                                                // carry the region over: re-stamp its claims for this round
-    for (int k = 0; k < pr.cnt; k += kChunk - 1) {
-        const unsigned v = C.pool[(size_t)chunk * kChunk + lane];
-        if (lane < kChunk - 1 && k + lane < pr.cnt && v != (unsigned)seed) red_min64(&C.px[v].claim[cur], mine);
-        chunk = __shfl_sync(0xffffffffu, v, kChunk - 1);
-    }
-    if (lane == 0) C.srec[cur][i] = pr;
-    return true;
 }
 
-// pass 2: every alive seed claims its pixel, then is carried over (verified) or sent to work list 2;
-// in finalise mode: every alive seed of the converged wave is stamped for good
+// pass 2: every listed seed: dead -> give its region back; alive without a region -> claim the seed pixel, go to work list 2;
+// alive with a region -> nothing at all unless a tile its bounding box touches was dirtied in the previous round, then the
+// lists are checked (long ones by a whole warp) and a region that no longer holds is released and re-grown.
+// In finalise mode: every alive seed of the converged wave is stamped for good.
 #define VERIFY_LONG 48
 __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ GrowBatch B) {
     __shared__ GrowDev s_dev;
@@ -285,49 +274,113 @@ __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ G
     const int n = (int)st->wl1_cnt;
     const int nth = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
+    const Ctx3& C = D.C;
     if (st->mode == 0) {
-        const bool first_round = round == st->wave_first_round;
         bool chg = false;
         int carried = 0;
+        const bool force = st->force != 0;
         // entry k of the list -> warp k % nwarps, lane k / nwarps: the long lists (walked by a whole warp, one after the other)
         // are spread over as many warps as possible
         const int nwarps = nth >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         for (int it = 0; it * 32 * nwarps + gw < n; ++it) {
             const int k = (it * 32 + lane) * nwarps + gw;
-            bool grow = false; int i = 0;
-            VerifyResult r = kSeedDead;
+            bool grow = false, is_long = false; int i = 0;
             if (k < n) {
-                i = D.wl1[k];
-                r = verify_seed(D.C, round, i, !first_round, &chg, VERIFY_LONG);
-                grow = r == kSeedGrow; carried += r == kSeedCarried;
+                const int e = D.wl1[k];
+                const bool alive = e >= 0;
+                i = alive ? e : ~e;
+                const SeedRec3 r = C.srec[i];
+                if (alive && r.cnt > 0 && r.cnt + r.bcnt > VERIFY_LONG) is_long = force || bbox_dirty(C, round, r);      // else: carried, O(1)
+                else if (!alive && r.cnt > VERIFY_LONG) is_long = true;
+                else {
+                    const Verify3 v = s3_verify(C, round, i, alive, &chg, force);
+                    grow = v == kV3Grow; carried += v == kV3Carried;
+                }
+                if (alive && r.cnt > 0 && r.cnt + r.bcnt > VERIFY_LONG && !is_long) ++carried;
             }
-            unsigned lm = __ballot_sync(0xffffffffu, r == kSeedLong);
+            unsigned lm = __ballot_sync(0xffffffffu, is_long);
             while (lm) {
                 const int src = __ffs(lm) - 1;
                 lm &= lm - 1;
-                const bool okc = verify_long_warp(D.C, round, __shfl_sync(0xffffffffu, i, src), lane);
-                if (lane == src) { grow = !okc; carried += okc; }
+                const int si = __shfl_sync(0xffffffffu, i, src);
+                const int se = __shfl_sync(0xffffffffu, k < n ? D.wl1[k] : 0, src);
+                const bool alive = se >= 0;
+                const int seed = C.seed_pix[si];
+                const u64 mine = key_of(C, C.seed_prio[si]);
+                const SeedRec3 r = C.srec[si];
+                bool ok = false;
+                if (alive) ok = walk3_warp(C, r.head, r.cnt, 0, mine, lane) && walk3_warp(C, r.bhead, r.bcnt, 1, mine, lane);
+                if (!ok) release3_warp(C, round, r.head, r.cnt, mine, alive ? (unsigned)seed : kNull, lane);
+                if (lane == src) {
+                    if (ok) ++carried;
+                    else {
+                        SeedRec3 z = r; z.cnt = 0; z.bcnt = 0; z.head = kNull; z.bhead = kNull; C.srec[si] = z;
+                        chg = true;
+                        if (alive) {                                      // still owns the seed pixel? (see s3_verify)
+                            bool dead = false;
+                            if (ld_claim0(&C.px[seed]) != mine) {
+                                const u64 old = atomicMin(&C.px[seed].claim[0], mine);
+                                dead = old < mine;
+                                if (!dead && old != mine && claim_valid(C, old)) mark_dirty(C, round, (unsigned)seed);
+                            }
+                            grow = !dead;
+                        }
+                    }
+                }
             }
             wl_append(grow, i, D.wl2, &st->wl2_cnt);
         }
         if (D.dbg && carried) atomicAdd(&D.dbg[round * TRACE_REC + 4], carried);
         if (__syncthreads_or(chg) && threadIdx.x == 0) st->changed = 1;
+    } else if (st->mode == 3) {
+        // full verification of the converged wave (the grow pass claims without looking at return values): every live region,
+        // whatever the dirty tiles say; nothing is released here -- a failure sends the image back to the rounds
+        bool bad = false;
+        const int nwarps = nth >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        for (int it = 0; it * 32 * nwarps + gw < n; ++it) {
+            const int k = (it * 32 + lane) * nwarps + gw;
+            bool is_long = false; int i = 0;
+            if (k < n && D.wl1[k] >= 0) {
+                i = D.wl1[k];
+                const SeedRec3 r = C.srec[i];
+                const u64 mine = key_of(C, C.seed_prio[i]);
+                if (r.cnt + r.bcnt > VERIFY_LONG) is_long = true;
+                else if (r.cnt > 0) {
+                    ListReader rd; rd.init(r.head);
+                    for (int j = 0; j < r.cnt; ++j) bad |= ld_claim0(&C.px[rd.next(C.pool)]) != mine;
+                    ListReader rb; rb.init(r.bhead);
+                    for (int j = 0; j < r.bcnt; ++j) bad |= !(ld_claim0(&C.px[rb.next(C.pool)]) < mine);
+                }
+            }
+            unsigned lm = __ballot_sync(0xffffffffu, is_long);
+            while (lm) {
+                const int src = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const int si = __shfl_sync(0xffffffffu, i, src);
+                const u64 mine = key_of(C, C.seed_prio[si]);
+                const SeedRec3 r = C.srec[si];
+                if (!(walk3_warp(C, r.head, r.cnt, 0, mine, lane) && walk3_warp(C, r.bhead, r.bcnt, 1, mine, lane))) bad = true;
+            }
+        }
+        if (__syncthreads_or(bad) && threadIdx.x == 0) st->recheck = 1;
     } else if (st->mode == 1) {
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += nth)
-            if (!finalize_seed(D.C, round, D.wl1[k], D.F)) D.status[0] = OLF_ERR_CAPACITY;
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += nth) {
+            const int e = D.wl1[k];
+            if (e >= 0 && !s3_finalize(C, e, D.F)) D.status[0] = OLF_ERR_CAPACITY;
+        }
     }
 }
 
-// pass 3: the seeds of work list 2 grow, ONE THREAD PER SEED.  Same decisions as grow_begin / grow_step / grow_end in
-// lsd_core.h (the executable specification, emulated on the host by tests/emul).  A single GPU thread walks a region's
-// sequential critical path no faster than a warp does (the path is instruction latency, not memory), but 32 regions per
-// warp cost 32x fewer issue slots -- so the kernel is written for few, branch-free instructions per queue entry:
-//   * the eight neighbour records (one 32-byte sector each) are fetched together; "free" / "held" are two 64-bit compares
-//     per record against (stamp|prio) keys, evaluated for all eight before any decision (full ILP);
+// pass 3: the seeds of work list 2 grow, ONE THREAD PER SEED.  Same decisions as s3_begin / s3_step / s3_end in lsd_sticky.h
+// (the executable specification, emulated on the host by tests/emul).  A single GPU thread walks a region's sequential
+// critical path no faster than a warp does (the path is instruction latency, not memory), but 32 regions per warp cost 32x
+// fewer issue slots -- so the kernel is written for few, branch-free instructions per queue entry:
+//   * the eight neighbour records (one 32-byte sector each) are fetched together; with ONE claim word per pixel "free" /
+//     "mine" / "held" are single 64-bit compares against the key (stamp|prio), evaluated for all eight before any decision;
 //   * only the candidates that survive are visited, in the reference's scan order, by a compact loop that reads their
-//     (angle, cos, sin) from a per-thread shared-memory slot;
-//   * the recent part of the queue lives in a per-thread shared-memory ring; claims are fire-and-forget atomicMin and a
-//     thread's own claims are visible to its own later (strong) loads, so no side table is needed;
+//     (cos, sin) from a per-thread shared-memory slot;
+//   * the recent part of the queue lives in a per-thread shared-memory ring; a thread's own claims are visible to its own
+//     later (strong) loads, so no side table is needed;
 //   * a thread whose region is complete takes the next seed of the list: the lanes of a warp stay busy.
 #ifndef GROW_THREADS
 #define GROW_THREADS 64
@@ -352,21 +405,19 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
         return;
     }
     if (mode == 0 && st->wl2_cnt > 0) {
-        const GrowCtx& C = D.C;
-        const bool have_prev = round != st->wave_first_round;
+        const Ctx3& C = D.C;
         const unsigned n = st->wl2_cnt;
         const int t = threadIdx.x;
-        const int cur = round & 1, prv = cur ^ 1;
-        const u64 sf_prev = stamp_field(round - 1), sf_cur = stamp_field(round);
         const int W = C.W, H = C.H;
         const float inv_w = 1.0f / (float)W;
         unsigned* const pool = C.pool;
-        bool chg = false, active = false;
+        bool active = false;
         // per-seed state
-        int i = 0; u64 prio = 0, mine = 0, mine_prev = 0;
-        unsigned w_head = 0, w_chunk = 0, r_chunk = 0, p_chunk = 0, b_head = kNull, b_chunk = kNull;
-        int w_off = 0, r_off = 0, p_off = 0, b_off = 0, count = 0, done = 0, prev_cnt = 0, bcnt = 0;
-        bool diff = false, overflow = false, dirty = false;
+        int i = 0; u64 mine = 0;
+        unsigned w_head = 0, w_chunk = 0, r_chunk = 0, b_head = kNull, b_chunk = kNull;
+        int w_off = 0, r_off = 0, b_off = 0, count = 0, done = 0, bcnt = 0;
+        int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
+        bool overflow = false, dirty = false;
         float sumdx = 0.f, sumdy = 0.f, u2 = 0.f; double reg_angle = 0.0;
         auto push = [&](unsigned pix) {
             if (w_off == kChunk - 1) {
@@ -378,11 +429,6 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
             }
             pool[(size_t)w_chunk * kChunk + w_off++] = pix;
             sm.ring[count & (GROW_RING - 1)][t] = pix;
-            if (count >= prev_cnt) diff = true;                                  // lock-step comparison with last round's list
-            else {
-                if (p_off == kChunk - 1) { p_chunk = pool[(size_t)p_chunk * kChunk + kChunk - 1]; p_off = 0; }
-                diff |= pool[(size_t)p_chunk * kChunk + p_off++] != pix;
-            }
             ++count;
         };
         auto record_blocked = [&](unsigned pix) {
@@ -398,18 +444,18 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
         };
         for (;;) {
             if (!active) {
-                // ---- grow_begin: the seed pixel has been claimed for this round by the verify pass
+                // ---- s3_begin: the seed pixel has been claimed by the verify pass
                 const unsigned k = atomicAdd(&st->wl2_pop, 1u);
                 if (k >= n) break;
                 i = D.wl2[k];
                 const int seed = C.seed_pix[i];
-                prio = C.seed_prio[i];
-                mine = (sf_cur << 40) | prio; mine_prev = (sf_prev << 40) | prio;
-                SeedRec pr; pr.head = kNull; pr.cnt = 0; pr.bchunk = kNull; pr.bcnt = 0;
-                if (have_prev) pr = C.srec[prv][i];
-                prev_cnt = pr.cnt > 0 ? pr.cnt : 0;
-                diff = prev_cnt == 0; p_chunk = pr.head; p_off = 0;
+                mine = key_of(C, C.seed_prio[i]);
                 count = 0; done = 0; b_head = kNull; b_chunk = kNull; b_off = 0; bcnt = 0; overflow = false;
+                {
+                    int sy = __float2int_rd(__fmul_rn((float)seed, inv_w)), sx = seed - sy * W;
+                    if (sx < 0) { --sy; sx += W; } else if (sx >= W) { ++sy; sx -= W; }
+                    bx0 = bx1 = sx; by0 = by1 = sy;
+                }
                 const unsigned nc = atomicAdd(C.pool_ctr, 1u);
                 if (nc >= C.pool_chunks) overflow = true;
                 else {
@@ -427,7 +473,7 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                 active = true;
             }
             if (!overflow) {
-                // ---- grow_step: expand one queue entry
+                // ---- s3_step: expand one queue entry
                 if (r_off == kChunk - 1) { r_chunk = pool[(size_t)r_chunk * kChunk + kChunk - 1]; r_off = 0; }
                 const int p = (int)((count - done <= GROW_RING) ? sm.ring[done & (GROW_RING - 1)][t] : pool[(size_t)r_chunk * kChunk + r_off]);
                 ++r_off; ++done;
@@ -442,9 +488,9 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                 if (px == W - 1) vm &= ~0x94u;
                 const PxRec* const base = C.px + p;
                 // all sixteen loads are issued before anything consumes them (one memory round trip per queue entry): ONE asm
-                // block, so that the assembler cannot trade the memory-level parallelism for registers; neighbours outside
-                // the image read the guard band or the neighbouring row (valid memory) and are masked out by `vm`
-                u64 c0[8], c1[8]; float4 lo[8];
+                // block per kind; neighbours outside the image read the guard band or the neighbouring row (valid memory) and
+                // are masked out by `vm`
+                u64 cl[8], cl_c; float4 lo[8];
                 const PxRec* ra[8];                                      // (the record array has a guard band of W+2 records at both ends)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -452,17 +498,17 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                     ra[k] = base + ((nk / 3) - 1) * W + ((nk % 3) - 1);
                 }
                 asm volatile(
-                    "ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%16];\n\t"
-                    "ld.relaxed.gpu.global.v2.u64 {%2, %3}, [%17];\n\t"
-                    "ld.relaxed.gpu.global.v2.u64 {%4, %5}, [%18];\n\t"
-                    "ld.relaxed.gpu.global.v2.u64 {%6, %7}, [%19];\n\t"
-                    "ld.relaxed.gpu.global.v2.u64 {%8, %9}, [%20];\n\t"
-                    "ld.relaxed.gpu.global.v2.u64 {%10, %11}, [%21];\n\t"
-                    "ld.relaxed.gpu.global.v2.u64 {%12, %13}, [%22];\n\t"
-                    "ld.relaxed.gpu.global.v2.u64 {%14, %15}, [%23];"
-                    : "=l"(c0[0]), "=l"(c1[0]), "=l"(c0[1]), "=l"(c1[1]), "=l"(c0[2]), "=l"(c1[2]), "=l"(c0[3]), "=l"(c1[3]),
-                      "=l"(c0[4]), "=l"(c1[4]), "=l"(c0[5]), "=l"(c1[5]), "=l"(c0[6]), "=l"(c1[6]), "=l"(c0[7]), "=l"(c1[7])
-                    : "l"(ra[0]), "l"(ra[1]), "l"(ra[2]), "l"(ra[3]), "l"(ra[4]), "l"(ra[5]), "l"(ra[6]), "l"(ra[7])
+                    "ld.relaxed.gpu.global.u64 %0, [%9];\n\t"
+                    "ld.relaxed.gpu.global.u64 %1, [%10];\n\t"
+                    "ld.relaxed.gpu.global.u64 %2, [%11];\n\t"
+                    "ld.relaxed.gpu.global.u64 %3, [%12];\n\t"
+                    "ld.relaxed.gpu.global.u64 %4, [%13];\n\t"
+                    "ld.relaxed.gpu.global.u64 %5, [%14];\n\t"
+                    "ld.relaxed.gpu.global.u64 %6, [%15];\n\t"
+                    "ld.relaxed.gpu.global.u64 %7, [%16];\n\t"
+                    "ld.relaxed.gpu.global.u64 %8, [%17];"
+                    : "=l"(cl[0]), "=l"(cl[1]), "=l"(cl[2]), "=l"(cl[3]), "=l"(cl[4]), "=l"(cl[5]), "=l"(cl[6]), "=l"(cl[7]), "=l"(cl_c)
+                    : "l"(ra[0]), "l"(ra[1]), "l"(ra[2]), "l"(ra[3]), "l"(ra[4]), "l"(ra[5]), "l"(ra[6]), "l"(ra[7]), "l"(base)
                     : "memory");
                 asm volatile(
                     "ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%32+16];\n\t"
@@ -479,29 +525,31 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                       "=f"(lo[6].x), "=f"(lo[6].y), "=f"(lo[6].z), "=f"(lo[6].w), "=f"(lo[7].x), "=f"(lo[7].y), "=f"(lo[7].z), "=f"(lo[7].w)
                     : "l"(ra[0]), "l"(ra[1]), "l"(ra[2]), "l"(ra[3]), "l"(ra[4]), "l"(ra[5]), "l"(ra[6]), "l"(ra[7])
                     : "memory");
-                // Scheduling guard: the keys every flag is compared with depend on ALL sixteen loads, so no consumer can be
-                // scheduled between the loads (the assembler otherwise serialises them to save registers: 5 memory round
-                // trips per entry instead of 1).  The guard never fires: bits 63..56 of a claim are 0x00 or 0xFF, bits 31..10
-                // of a bin number are zero.
+                // Scheduling guard: the key every flag is compared with depends on ALL sixteen loads, so no consumer can be
+                // scheduled between the loads (the assembler otherwise serialises them to save registers: several memory
+                // round trips per entry instead of 1).  The guard never fires: bits 63..56 of a claim are 0x00 or 0xFF, bits
+                // 31..10 of a bin number are zero.
                 unsigned acc_a = 0, acc_b = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { acc_a |= (unsigned)(c0[k] >> 32); acc_b |= __float_as_uint(lo[k].w); }
+                for (int k = 0; k < 8; ++k) { acc_a |= (unsigned)(cl[k] >> 32); acc_b |= __float_as_uint(lo[k].w); }
+                acc_a |= (unsigned)(cl_c >> 32);
                 const bool never = ((acc_a >> 24) == 0x55u) || ((acc_b >> 16) == 0x55u);
-                const u64 mine_g = never ? 0ull : mine, mine_prev_g = never ? ~0ull : mine_prev;
-                // free: neither final nor held by a higher-priority seed nor already mine (NOTDEF pixels are born final);
-                // held: by a non-final higher-priority claim.  The round parity is uniform: one copy of the flags per parity.
-                unsigned m_free = 0, m_held = 0;
-#define OLF_FLAGS(EP, EC)                                                                                      \
-                _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                                \
-                    const u64 ep = EP[k], ec = EC[k];                                                          \
-                    const bool fre = (ep >= mine_prev_g) && (ec > mine_g);                                     \
-                    const bool fin = ((unsigned)(ep >> 32) < 256u) || ((unsigned)(ec >> 32) < 256u);           \
-                    const bool hld = !fre && !fin && (ec != mine_g);                                           \
-                    m_free |= (unsigned)fre << k;                                                              \
-                    m_held |= (unsigned)hld << k;                                                              \
+                const u64 mine_g = never ? 0ull : mine;
+                // free: c > mine (nobody's, a stale claim of an earlier wave, or a lower-priority claim that is taken over);
+                // held: c < mine and not final (NOTDEF pixels are born final); mine: c == mine
+                // the entry itself was claimed a while ago without looking at the return value: did it go to a higher-priority seed?
+                if (cl_c != mine_g) mark_dirty_xy(C, round, px, py);
+                unsigned m_free = 0, m_held = 0, m_low = 0;
+                const unsigned stamp_hi = (unsigned)(C.stamp >> 40);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const bool fre = cl[k] > mine_g;
+                    const bool hld = cl[k] < mine_g && (unsigned)(cl[k] >> 32) >= 256u;
+                    const bool low = fre && (unsigned)(cl[k] >> 40) == stamp_hi;          // a lower-priority claim of this wave
+                    m_free |= (unsigned)fre << k;
+                    m_held |= (unsigned)hld << k;
+                    m_low |= (unsigned)low << k;
                 }
-                if (cur) { OLF_FLAGS(c0, c1) } else { OLF_FLAGS(c1, c0) }
-#undef OLF_FLAGS
                 m_free &= vm; m_held &= vm;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) sm.nb[k][t] = make_float2(lo[k].y, never ? 0.f : lo[k].z);
@@ -512,16 +560,18 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                     m &= m - 1;
                     const float2 csk = sm.nb[k][t];
                     const float cxk = csk.x, cyk = csk.y;
+                    const int nk = k < 4 ? k : k + 1;
+                    const int dx = (nk % 3) - 1, dy = (nk / 3) - 1;
+                    const int q = p + dy * W + dx;
                     bool al;
-                    {   // isAligned(), lazily: see grow_aligned() in lsd_core.h
+                    {   // isAligned(), lazily: see s3_aligned() in lsd_sticky.h
                         const float dot = f_add(f_mul(sumdx, cxk), f_mul(sumdy, cyk)), d2 = f_mul(dot, dot);
                         const bool fast = C.fast_align && u2 > 1e-3f;
                         if (fast && dot > 0.f && d2 >= f_mul(C.c_hi2, u2)) al = true;
                         else if (fast && (dot <= 0.f || d2 <= f_mul(C.c_lo2, u2))) al = false;
                         else {
                             if (dirty) { reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads); dirty = false; }
-                            const int nke = k < 4 ? k : k + 1;                       // rare path: the candidate's angle comes from its record
-                            const float ang_k = __ldcg(&C.px[p + ((nke / 3) - 1) * W + ((nke % 3) - 1)].ang);
+                            const float ang_k = __ldcg(&C.px[q].ang);               // rare path: the candidate's angle comes from its record
                             double n_theta = d_sub(reg_angle, d_mul((double)ang_k, kDegToRads));
                             if (n_theta < 0) n_theta = -n_theta;
                             if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
@@ -529,10 +579,11 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                         }
                     }
                     if (!al) continue;
-                    const int nk = k < 4 ? k : k + 1;
-                    const int q = p + ((nk / 3) - 1) * W + ((nk % 3) - 1);
+                    const int qx = px + dx, qy = py + dy;
+                    bx0 = min(bx0, qx); bx1 = max(bx1, qx); by0 = min(by0, qy); by1 = max(by1, qy);
                     if ((m_held >> k) & 1u) { record_blocked((unsigned)q); if (overflow) break; continue; }   // aligned but held by a higher-priority seed
-                    red_min64(&C.px[q].claim[cur], mine);
+                    if ((m_low >> k) & 1u) mark_dirty_xy(C, round, qx, qy);      // taken from a lower-priority region: it must re-verify
+                    red_min64(&C.px[q].claim[0], mine);                          // fire and forget
                     push((unsigned)q);
                     if (overflow) break;
                     sumdx = f_add(sumdx, cxk);
@@ -542,21 +593,20 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                 }
             }
             if (overflow || done >= count) {
-                // ---- grow_end
-                SeedRec r;
-                if (overflow) { r.head = kNull; r.cnt = 0; r.bchunk = kNull; r.bcnt = 0; D.status[0] = OLF_ERR_CAPACITY; chg = true; }
+                // ---- s3_end
+                SeedRec3 r; r.pad0 = r.pad1 = 0;
+                if (overflow) { r.head = kNull; r.cnt = 0; r.bhead = kNull; r.bcnt = 0; r.x0 = r.y0 = r.x1 = r.y1 = 0; D.status[0] = OLF_ERR_CAPACITY; }
                 else {
                     if (dirty) reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads);
-                    r.head = w_head; r.cnt = count; r.bchunk = b_head; r.bcnt = bcnt;
+                    r.head = w_head; r.cnt = count; r.bhead = b_head; r.bcnt = bcnt;
+                    r.x0 = (unsigned short)bx0; r.y0 = (unsigned short)by0; r.x1 = (unsigned short)bx1; r.y1 = (unsigned short)by1;
                     C.regang[i] = reg_angle;
-                    if (diff || count != prev_cnt) chg = true;
                 }
-                C.srec[cur][i] = r;
+                C.srec[i] = r;
                 if (D.dbg) { atomicAdd(&D.dbg[round * TRACE_REC + 5], 1); atomicAdd(&D.dbg[round * TRACE_REC + 6], count); atomicMax(&D.dbg[round * TRACE_REC + 7], count); }
                 active = false;
             }
         }
-        if (chg) st->changed = 1;
     }
     // last block to finish advances the state machine
     __threadfence();
@@ -574,16 +624,20 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
     if (mode == 0) {
         if (D.dbg) D.dbg[round * TRACE_REC + 3] = (int)(gtime() & 0x7fffffff);
         const bool changed = *(volatile unsigned*)&st->changed != 0;
-        if (!changed || round + 2 >= D.max_rounds || err != 0) {              // work list 1 is kept for the finalise pass
+        if (!changed || round + 2 >= D.max_rounds || err != 0) {              // work list 1 is kept for the next passes
             const unsigned c = wv < LSD_MAX_WAVES ? atomicAdd(&B.conv[wv], 1u) + 1u : nb;
-            st->mode = (c >= nb) ? 1 : 2;
+            st->mode = (c >= nb) ? 3 : 2;
         } else { st->round = round + 1; st->wl1_cnt = 0; }
-        st->wl2_cnt = 0; st->wl2_pop = 0; st->changed = 0;
+        st->wl2_cnt = 0; st->wl2_pop = 0; st->changed = 0; st->force = 0; st->recheck = 0;
     } else if (mode == 2) {
-        if (*(volatile unsigned*)&B.conv[wv] >= nb) st->mode = 1;
+        if (*(volatile unsigned*)&B.conv[wv] >= nb) st->mode = 3;
+    } else if (mode == 3) {
+        if (*(volatile unsigned*)&st->recheck != 0 && err == 0 && round + 2 < D.max_rounds) {
+            st->mode = 0; st->round = round + 1; st->wl1_cnt = 0; st->force = 1; st->recheck = 0;      // back to the rounds, everything dirty
+        } else st->mode = 1;
     } else {
         st->mode = 0; st->round = round + 1; st->wave = wv + 1; st->wave_first_round = round + 1; st->wl1_cnt = 0; st->wl0_cnt = 0;
-        *D.C.pool_ctr = 0;                                          // one bump pool per wave (lists are carried over rounds)
+        *D.C.pool_ctr = 0;                                          // one bump pool per wave (lists live until the wave is final)
         if (wv + 1 >= D.plan->n_waves || err != 0) {
             st->done = 1; D.status[1] = (int)(round + 1); D.status[2] = D.plan->n_waves; D.status[3] = 1;
             for (int w = wv + 1; w < LSD_MAX_WAVES; ++w) atomicAdd(&B.conv[w], 1u);   // this image has no further waves
@@ -853,15 +907,16 @@ struct LineImpl {
     DevBuf<u64> seed_prio;
     DevBuf<int> seed_pix, n2max, status, wl0, wl1, wl2;
     DevBuf<unsigned> hist, bin_start, cursor, pool, ctrs, final_pool;
-    DevBuf<SeedRec> srec0, srec1;
-    DevBuf<unsigned> conv;
+    DevBuf<SeedRec3> srec0;
+    DevBuf<unsigned> conv, dirty;
+    int tile_wpr = 0, dirty_words = 0;
     DevBuf<double> regang;
     DevBuf<LsdPlan> plan;
     DevBuf<LsdRegion> regs;
     DevBuf<float2_t> tab_seed, tab_acc, cs;
     DevBuf<PhaseState> phase;
     DevBuf<PxRec> px;
-    int phase_batch = 48;
+    int phase_batch = 52;
     bool trace = false;
     int first_wave = 4096, wave_growth = 16;
     DevBuf<int> dbg;
@@ -988,7 +1043,7 @@ void line_destroy(LineImpl* h) {
     h->img_stage.release(); h->img.release(); h->blurred.release(); h->scaled.release(); h->lbd_blur.release(); h->coef.release();
     h->ang.release(); h->dabc.release(); h->seed_prio.release(); h->seed_pix.release(); h->n2max.release(); h->status.release();
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
-    h->final_pool.release(); h->conv.release(); h->srec0.release(); h->srec1.release(); h->regang.release(); h->plan.release(); h->regs.release();
+    h->final_pool.release(); h->conv.release(); h->dirty.release(); h->srec0.release(); h->regang.release(); h->plan.release(); h->regs.release();
     h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release();
     h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release(); h->phase_init.release();
     h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
@@ -1016,10 +1071,12 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
     cx.insert(cx.end(), cy.begin(), cy.end());
     if ((rc = h->coef.ensure(cx.size()))) return rc;
     OLF_CUDA(cudaMemcpy(h->coef.p, cx.data(), cx.size() * sizeof(ExCoef), cudaMemcpyHostToDevice));
+    h->tile_wpr = (((h->W + 31) >> 5) + 31) / 32; h->dirty_words = h->tile_wpr * ((h->H + 31) >> 5);
+    if ((rc = h->dirty.ensure((size_t)2 * h->dirty_words))) return rc;
     h->pool_chunks = (unsigned)std::max<size_t>(S / 2, 1u << 16);       // 16 px of list space per image pixel per round
     h->reg_cap = (unsigned)(S / std::max(h->min_reg_size, 1) + 16);
     if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || (rc = h->seed_prio.ensure(S)) || (rc = h->seed_pix.ensure(S)) ||
-        (rc = h->conv.ensure(LSD_MAX_WAVES)) || (rc = h->srec0.ensure(S)) || (rc = h->srec1.ensure(S)) || (rc = h->wl0.ensure(S)) || (rc = h->wl1.ensure(S)) || (rc = h->wl2.ensure(S)) ||
+        (rc = h->conv.ensure(LSD_MAX_WAVES)) || (rc = h->srec0.ensure(S)) || (rc = h->wl0.ensure(S)) || (rc = h->wl1.ensure(S)) || (rc = h->wl2.ensure(S)) ||
         (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) ||
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
         (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->plan.ensure(1)) ||
@@ -1081,7 +1138,8 @@ static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D) {
     count_launches((h->blur_k ? 2 : 0) + 4);
     D.C.W = W; D.C.H = H; D.C.px = h->px.p + W + 2; D.C.dabc = h->dabc.p; D.C.tab_seed = h->tab_seed.p;
     D.C.pool = h->pool.p; D.C.pool_ctr = h->ctrs.p; D.C.pool_chunks = h->pool_chunks;
-    D.C.srec[0] = h->srec0.p; D.C.srec[1] = h->srec1.p; D.C.regang = h->regang.p;
+    D.C.srec = h->srec0.p; D.C.regang = h->regang.p;
+    D.C.dirty[0] = h->dirty.p; D.C.dirty[1] = h->dirty.p + h->dirty_words; D.C.tile_wpr = h->tile_wpr; D.C.stamp = 0; D.dirty_words = h->dirty_words;
     D.C.seed_pix = h->seed_pix.p; D.C.seed_prio = h->seed_prio.p; D.C.prec = h->prec;
     {
         const double margin = 0.1 * M_PI / 180.0;

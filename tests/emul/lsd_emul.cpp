@@ -1,9 +1,9 @@
-// TEST INFRASTRUCTURE.  Host emulation of the parallel LSD region-growing scheme of
+// TEST INFRASTRUCTURE.  Host emulation of the PERSISTENT-CLAIMS variant (orb_line_slam_b200/csrc/lsd_sticky.h) of
 // orb_line_slam_b200/csrc/lsd_core.h: the SAME scan / verify_seed() / grow_step() / finalize_seed() / region_rect_a()
 // source the kernels run is compiled for the CPU; every pass is replayed in a random order and the growths of a round
 // are stepped in a random interleaving (emulating arbitrary GPU scheduling and partial visibility of claims).
 // The result must equal the oracle's sequential LSD; the test also reports waves / rounds / work amplification.
-#include "../../orb_line_slam_b200/csrc/lsd_core.h"
+#include "../../orb_line_slam_b200/csrc/lsd_sticky.h"
 #include "../../oracle/cvprim.hpp"
 #include "../../include/olf_abi.h"
 #include <random>
@@ -71,10 +71,9 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
     const double logNT = 5 * (std::log10((double)W) + std::log10((double)H)) / 2 + std::log10(11.0);
     const int min_reg_size = (int)(unsigned)(-logNT / std::log10(p));
 
-    // per-pixel records exactly as k_lsd_grad / k_lsd_scatter build them
     std::vector<PxRec> px(S);
     for (int q = 0; q < S; ++q) {
-        PxRec r; r.claim[0] = kClaimNone; r.claim[1] = kClaimNone; r.ang = ang[q]; r.cx = 0.f; r.cy = 0.f; r.binrev = 0;
+        PxRec r; r.claim[0] = ang[q] >= 0.f ? kClaimNone : 0ull; r.claim[1] = r.claim[0]; r.ang = ang[q]; r.cx = 0.f; r.cy = 0.f; r.binrev = 0;
         if (ang[q] >= 0.f) {
             const float2_t c = tab_acc[tab_index(dabc[q])];
             r.cx = c.x; r.cy = c.y;
@@ -85,13 +84,15 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
     const unsigned pool_chunks = 1u << 21;
     std::vector<unsigned> pool((size_t)pool_chunks * kChunk);
     unsigned pool_ctr = 0;
-    std::vector<SeedRec> srec[2] = {std::vector<SeedRec>(n), std::vector<SeedRec>(n)};
+    std::vector<SeedRec3> srec(n);
     std::vector<double> regang(n, 0.0);
-    GrowCtx C;
+    const int tiles_x = (W + 31) >> 5, tiles_y = (H + 31) >> 5, wpr = (tiles_x + 31) / 32;
+    std::vector<unsigned> dirty0((size_t)tiles_y * wpr, 0), dirty1((size_t)tiles_y * wpr, 0);
+    Ctx3 C;
     C.W = W; C.H = H; C.px = px.data(); C.dabc = dabc.data(); C.tab_seed = tab_seed.data();
     C.pool = pool.data(); C.pool_ctr = &pool_ctr; C.pool_chunks = pool_chunks;
-    C.srec[0] = srec[0].data(); C.srec[1] = srec[1].data(); C.regang = regang.data();
-    C.seed_pix = seeds.data(); C.seed_prio = prio.data(); C.prec = prec;
+    C.srec = srec.data(); C.regang = regang.data(); C.seed_pix = seeds.data(); C.seed_prio = prio.data(); C.prec = prec;
+    C.dirty[0] = dirty0.data(); C.dirty[1] = dirty1.data(); C.tile_wpr = wpr;
     {
         const double margin = 0.1 * M_PI / 180.0;
         C.fast_align = (exact_align == 0) && (prec + margin < 80.0 * M_PI / 180.0);
@@ -102,76 +103,87 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
     std::vector<LsdRegion> regs(S / std::max(min_reg_size, 1) + 16);
     FinalOut F; F.final_pool = final_pool.data(); F.final_ctr = &final_ctr; F.regs = regs.data(); F.nreg = &nreg;
     F.reg_cap = (unsigned)regs.size(); F.min_reg_size = min_reg_size;
-    long long waves = 0, rounds = 0, grown = 0, final_px = 0, regions = 0, max_rw = 0, carried = 0;
+    long long waves = 0, rounds = 0, grown = 0, final_px = 0, regions = 0, max_rw = 0, carried = 0, walked = 0, live_px = 0;
     unsigned round = 1;
-    std::vector<int> order, wl0, wl1, wl2;
+    std::vector<int> order, wl0, wl2;
+    std::vector<std::pair<int, bool>> wl1;
     for (size_t wv = 0; wv + 1 < wave_start.size(); ++wv) {
         const int lo = wave_start[wv], hi = wave_start[wv + 1];
         if (lo == hi) continue;
         ++waves;
-        pool_ctr = 0;                                          // one bump pool per wave
+        pool_ctr = 0;
+        C.stamp = (u64)(0xFFFFFFu - (unsigned)(wv + 1)) << 40;
+        for (int i = lo; i < hi; ++i) { SeedRec3 z; z.head = kNull; z.cnt = 0; z.bhead = kNull; z.bcnt = 0; z.x0 = z.y0 = z.x1 = z.y1 = 0; z.pad0 = z.pad1 = 0; srec[i] = z; }
+        std::fill(dirty0.begin(), dirty0.end(), 0u); std::fill(dirty1.begin(), dirty1.end(), 0u);
         long long rw = 0;
         bool first_round = true;
         for (;;) {
             ++rounds; ++rw;
-            const int cur = round & 1, prv = cur ^ 1;
             bool changed = false;
-            // pass 1: scan (any order)
+            std::fill(C.dirty[round & 1], C.dirty[round & 1] + (size_t)tiles_y * wpr, 0u);     // events of THIS round
+            // pass 1: scan
             if (first_round) { order.resize(hi - lo); std::iota(order.begin(), order.end(), lo); }
             else order = wl0;
             std::shuffle(order.begin(), order.end(), rng);
             if (first_round) wl0.clear();
             wl1.clear(); wl2.clear();
             for (int i : order) {
-                if (first_round) {                              // seeds swallowed by finalised regions leave the wave for good
-                    if (seed_final(C, seeds[i])) continue;
+                if (first_round) {
+                    if (s3_final(C, seeds[i])) continue;
                     wl0.push_back(i);
                 }
-                bool alive = seed_alive(C, round, seeds[i], prio[i]);
-                bool deferred = false;
-                if (alive && first_round && defer && seed_deferred(C, round, seeds[i], prio[i])) { alive = false; deferred = true; }
-                if (alive) { wl1.push_back(i); continue; }
-                if (deferred || (!first_round && srec[prv][i].cnt != 0)) changed = true;
-                SeedRec z; z.head = kNull; z.cnt = 0; z.bchunk = kNull; z.bcnt = 0;
-                srec[cur][i] = z;
+                bool alive = s3_alive(C, seeds[i], prio[i]);
+                if (alive && first_round && defer && s3_deferred(C, seeds[i], prio[i])) { changed = true; continue; }    // sits this round out
+                if (alive || srec[i].cnt > 0) wl1.push_back({i, alive});
             }
-            // pass 2: verify (any order)
+            // pass 2: verify
             std::shuffle(wl1.begin(), wl1.end(), rng);
-            for (int i : wl1) {
-                const VerifyResult v = verify_seed(C, round, i, !first_round, &changed);
-                if (v == kSeedGrow) wl2.push_back(i);
-                else if (v == kSeedCarried) ++carried;
+            for (auto& e : wl1) {
+                if (e.second && srec[e.first].cnt > 0) { live_px += srec[e.first].cnt; if (bbox_dirty(C, round, srec[e.first])) walked += srec[e.first].cnt; }
+                const Verify3 v = s3_verify(C, round, e.first, e.second, &changed);
+                if (v == kV3Grow) wl2.push_back(e.first);
+                else if (v == kV3Carried) ++carried;
             }
-            // pass 3: grow -- `lanes` growths in flight, stepped in random interleaving (arbitrary GPU scheduling)
+            // pass 3: grow, randomly interleaved
             {
-                std::vector<GrowSt> act;
+                std::vector<GrowSt3> act;
                 size_t next = 0;
                 const size_t lanes = 1 + rng() % 48;
                 while (next < wl2.size() || !act.empty()) {
                     while (act.size() < lanes && next < wl2.size()) {
-                        GrowSt st; grow_begin(C, round, wl2[next++], !first_round, st);
+                        GrowSt3 st; s3_begin(C, wl2[next++], st);
                         if (st.overflow) return -3;
                         act.push_back(st);
                     }
                     const size_t k = rng() % act.size();
-                    if (!grow_step(C, round, act[k])) {
+                    if (!s3_step(C, round, act[k])) {
                         if (act[k].overflow) return -3;
                         grown += act[k].count;
-                        if (grow_end(C, round, act[k])) changed = true;
+                        s3_end(C, act[k]);
                         act[k] = act.back(); act.pop_back();
                     }
                 }
             }
             first_round = false;
-            if (!changed) break;
+            if (!changed) {
+                // before the wave is finalised every live region is verified regardless of dirty tiles
+                bool clean = true;
+                for (int i : wl0) {
+                    if (srec[i].cnt <= 0 || !s3_alive(C, seeds[i], prio[i])) { if (srec[i].cnt > 0) clean = false; continue; }
+                    bool chg2 = false;
+                    if (s3_verify(C, round, i, true, &chg2, true) != kV3Carried) { clean = false; wl2.push_back(i); }
+                }
+                if (clean) break;
+                return -5;                                      // cannot happen in a sequential emulation (steps are atomic)
+            }
             ++round;
+            if (rw > 4000) return -4;
         }
         max_rw = std::max(max_rw, rw);
-        // finalise the converged wave (its alive list is wl1)
-        for (int i : wl1) {
-            const int c = srec[round & 1][i].cnt;
+        for (int i : wl0) {
+            const int c = srec[i].cnt;
             if (c > 0) { ++regions; final_px += c; }
-            if (!finalize_seed(C, round, i, F)) return -3;
+            if (!s3_finalize(C, i, F)) return -3;
         }
         ++round;
     }
@@ -195,6 +207,6 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
     *nseg = (int)out.size();
     if ((int)out.size() > cap) return -3;
     for (size_t i = 0; i < out.size(); ++i) memcpy(segs + 4 * i, out[i].v, 16);
-    stats[0] = waves; stats[1] = rounds; stats[2] = grown; stats[3] = final_px; stats[4] = regions; stats[5] = max_rw; stats[6] = carried;
+    stats[0] = waves; stats[1] = rounds; stats[2] = grown; stats[3] = final_px; stats[4] = regions; stats[5] = max_rw; stats[6] = carried; stats[7] = walked; stats[8] = live_px;
     return 0;
 }

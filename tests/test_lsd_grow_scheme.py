@@ -1,8 +1,8 @@
-"""The parallel LSD region-growing scheme (fixed-point iteration over priority waves, orb_line_slam_b200/csrc/
-lsd_core.h) is validated WITHOUT a GPU: the same scan / verify_seed / grow_step / finalize_seed / region_rect_a source
-the kernels run is compiled for the host; every pass is replayed in a random order and the growths of a round are stepped
-in a random interleaving (tests/emul/lsd_emul.cpp).  Result must equal the oracle's sequential LSD bit for bit, for any
-schedule, with and without the first-round deferral and the lazy alignment test."""
+"""The parallel LSD region-growing scheme (fixed-point iteration over priority waves with persistent claims and dirty
+tiles, orb_line_slam_b200/csrc/lsd_sticky.h) is validated WITHOUT a GPU: the same s3_alive / s3_verify / s3_step /
+s3_finalize / region_rect_a source the kernels follow is compiled for the host; every pass is replayed in a random order
+and the growths of a round are stepped in a random interleaving (tests/emul/lsd_emul.cpp).  Result must equal the oracle's
+sequential LSD bit for bit, for any schedule, with and without the first-round deferral and the lazy alignment test."""
 import ctypes as C, pathlib, subprocess
 import numpy as np
 import pytest
@@ -17,14 +17,14 @@ ROOT = pathlib.Path(__file__).resolve().parents[1]
 def emul():
     so = ROOT / "tests" / "emul" / "_lsd_emul.so"
     src = ROOT / "tests" / "emul" / "lsd_emul.cpp"
-    core = ROOT / "orb_line_slam_b200" / "csrc" / "lsd_core.h"
-    if not so.exists() or so.stat().st_mtime < max(src.stat().st_mtime, core.stat().st_mtime):
+    deps = [src, ROOT / "orb_line_slam_b200" / "csrc" / "lsd_core.h", ROOT / "orb_line_slam_b200" / "csrc" / "lsd_sticky.h"]
+    if not so.exists() or so.stat().st_mtime < max(d.stat().st_mtime for d in deps):
         subprocess.run(["g++", "-O2", "-march=native", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(src)], check=True)
     return C.CDLL(str(so))
 
 
 @pytest.mark.parametrize("w,h,seed,first_wave,nbins", [(320, 240, 1, 2048, 1024), (320, 240, 2, 64, 1024), (200, 150, 3, 100000, 1024),
-                                                       (400, 300, 4, 512, 64), (97, 131, 5, 16, 16)])
+                                                       (400, 300, 4, 512, 64), (97, 131, 5, 16, 16), (640, 480, 6, 4096, 1024)])
 def test_fixed_point_equals_sequential(emul, w, h, seed, first_wave, nbins):
     o = oracle()
     P = LineParams(lsd_n_bins=nbins)
@@ -34,10 +34,11 @@ def test_fixed_point_equals_sequential(emul, w, h, seed, first_wave, nbins):
     o.line_destroy(hd)
     carried = 0
     for sched, defer, exact in ((1, 1, 0), (2, 1, 0), (3, 0, 0), (4, 1, 1)):     # different random schedules / options
-        segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 7)()
+        segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
         rc = emul.emul_lsd_detect(ptr(img), w, h, C.byref(P), C.c_uint(seed * 10 + sched), first_wave, defer, exact, ptr(segs), 65536, C.byref(n), st)
         assert rc == 0 and n.value == len(ref)
         assert np.array_equal(segs[:n.value], ref)
         assert st[1] >= st[0]                              # at least one round per wave
         carried += st[6]
+        assert st[7] < st[8]                               # regions away from any event were carried without being walked
     assert carried > 0                                     # the verify-instead-of-regrow path was exercised
