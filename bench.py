@@ -367,9 +367,10 @@ def main():
                 "roofline": {"kernel": "k_lsd_grow (+scan, verify)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)", "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None,
-                             # DRAM bytes per image of the chain (scan 150 + verify 159 + grow 36 MB, cold caches): ncu launch list,
-                             # profiles/r01c_launches_summary.csv
-                             "traffic": 345.6e6, "kernel_ms": grow_ms,
+                             # DRAM bytes per image of the chain, cold caches, from the ncu launch list of the single-frame path
+                             # (profiles/r01d_launches_summary.csv: scan 268 + verify 155 + grow 42 MB); the batched chain of the bench
+                             # plans smaller waves and moves less
+                             "traffic": 465.0e6, "kernel_ms": grow_ms,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "dominant chain = the LSD region-growing passes (k_lsd_scan / k_lsd_verify / k_lsd_grow, ~95% of a frame's GPU time): device time of one batched chain / images in it, CUDA events on its stream; 'launch' = one image's chain; latency-bound sequential region growing -- the HBM fraction is honest but not the limiter (DESIGN.md section 5)"}}
         if not args.no_cpu_baseline and world == 1:
