@@ -152,6 +152,7 @@ struct GrowDev {
     unsigned max_rounds;
     int defer;                   // first round of a wave: seeds with a live higher-priority aligned neighbour wait
     int dirty_words;             // words of one dirty bitmap
+    int test_recheck;            // (test hook, OLF_LSD_TEST_RECHECK) pretend the full verification of every wave fails once
     int* dbg;                    // optional per-round trace (OLF_LSD_TRACE)
 };
 // One launch serves a BATCH of images (the two eyes of a stereo frame, several frames): blockIdx.y selects the image, every
@@ -632,7 +633,9 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
     } else if (mode == 2) {
         if (*(volatile unsigned*)&B.conv[wv] >= nb) st->mode = 3;
     } else if (mode == 3) {
-        if (*(volatile unsigned*)&st->recheck != 0 && err == 0 && round + 2 < D.max_rounds) {
+        const bool pretend = D.test_recheck && st->pad0 != (unsigned)(wv + 1);      // once per wave
+        if (pretend) st->pad0 = (unsigned)(wv + 1);
+        if ((*(volatile unsigned*)&st->recheck != 0 || pretend) && err == 0 && round + 2 < D.max_rounds) {
             st->mode = 0; st->round = round + 1; st->wl1_cnt = 0; st->force = 1; st->recheck = 0;      // back to the rounds, everything dirty
         } else st->mode = 1;
     } else {
@@ -1155,6 +1158,7 @@ static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D, int batch_im
     D.F.reg_cap = h->reg_cap; D.F.min_reg_size = h->min_reg_size;
     D.status = h->status.p; D.max_rounds = h->max_rounds;
     D.defer = getenv("OLF_LSD_NO_DEFER") ? 0 : 1;
+    D.test_recheck = getenv("OLF_LSD_TEST_RECHECK") ? 1 : 0;
     D.dbg = h->trace ? h->dbg.p : nullptr;
     if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
     h->phase_init.p[0] = PhaseState{}; h->phase_init.p[0].round = 1; h->phase_init.p[0].wave_first_round = 1;

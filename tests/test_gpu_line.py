@@ -77,3 +77,20 @@ def test_lbd_compute_parity_on_given_keylines():
     assert np.array_equal(g.lbd_compute(hg, img, kl), d)
     assert g.lbd_compute(hg, img, kl[:0]).shape == (0, 32)
     o.line_destroy(ho); g.line_destroy(hg)
+
+
+def test_lsd_full_verification_failure_path(monkeypatch):
+    """Before a wave is finalised every live region is verified; a failure sends the image back to the rounds with every
+    tile dirty.  The race that can make it fail is too rare to wait for, so a test hook pretends it failed once per wave:
+    the extra forced round must change nothing."""
+    o, g = oracle(), olf.api(0)
+    P = LineParams()
+    img = random_image(640, 480, 21)
+    ho = o.line_create(P); ref = o.lsd_detect(ho, img); o.line_destroy(ho)
+    monkeypatch.setenv("OLF_LSD_TEST_RECHECK", "1")
+    monkeypatch.setenv("OLF_LSD_FIRST_WAVE", "512")          # several waves
+    hg = g.line_create(P)
+    for _ in range(2):
+        got = g.lsd_detect(hg, img)
+        assert len(got) == len(ref) and np.array_equal(got, ref)
+    g.line_destroy(hg)
