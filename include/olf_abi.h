@@ -282,7 +282,8 @@ int  olf_frontend_process_batch(olf_frontend* h, const uint8_t* const* img_l, co
 /* the extractors of the rig, slot = 2 * frame_in_batch + eye (e.g. for olf_orb_get_level) */
 olf_orb*  olf_frontend_orb(olf_frontend* h, int slot);
 olf_line* olf_frontend_line(olf_frontend* h, int slot);
-/* last-call statistics: out[0..1] LSD rounds L/R, out[2..3] LSD waves L/R */
+/* last-call statistics of a line extractor: out[0] LSD rounds, out[1] waves, out[2] accepted regions, out[3] device time of
+ * the region-growing chain in microseconds (CUDA events on its stream), out[4] images that shared the chain */
 int  olf_line_last_stats(const olf_line* h, int* out8);
 
 #ifdef __cplusplus
