@@ -42,3 +42,21 @@ def test_fixed_point_equals_sequential(emul, w, h, seed, first_wave, nbins):
         carried += st[6]
         assert st[7] < st[8]                               # regions away from any event were carried without being walked
     assert carried > 0                                     # the verify-instead-of-regrow path was exercised
+
+
+def test_fixed_point_equals_sequential_bench_image(emul):
+    """The 1280x720 image of the benchmark (LSD working size 1536x864, 299 k seeds), with the wave plans the library uses for
+    batches (4096 x2 here) and for single frames (one big first wave)."""
+    from orb_line_slam_b200.synth import Scene
+    o = oracle()
+    P = LineParams()
+    img = Scene("zed720", 0).render(0, 0)
+    hd = o.line_create(P)
+    ref = o.lsd_detect(hd, img)
+    o.line_destroy(hd)
+    for first_wave in (4096, 262144):
+        segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
+        rc = emul.emul_lsd_detect(ptr(img), 1280, 720, C.byref(P), C.c_uint(first_wave), first_wave, 1, 0, ptr(segs), 65536, C.byref(n), st)
+        assert rc == 0 and n.value == len(ref) == 2114
+        assert np.array_equal(segs[:n.value], ref)
+        assert st[7] < st[8] // 2                              # most live pixel-rounds are never walked
