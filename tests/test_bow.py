@@ -95,3 +95,17 @@ def test_bow_edge_cases():
         assert n == int((m >= 0).sum())
         api.vocab_destroy(v)
     # identical descriptors at distance 0 with a unique nearest neighbour match themselves
+
+
+def test_product_bow_assemble_host_logic_matches_oracle():
+    """olf_bow_assemble is host code inside libolf.so (the std::map bookkeeping of DBoW2's transform): no GPU needed."""
+    import orb_line_slam_b200 as olf
+    o, g = oracle(), olf.api(0)
+    rng = np.random.RandomState(11)
+    for n in (0, 1, 7, 500, 3000):
+        w = rng.randint(0, max(1, n // 3 + 1), n).astype(np.int32)
+        v = np.where(rng.rand(n) < 0.1, 0.0, rng.rand(n) * 5).astype(np.float64)          # some stopped words
+        nd = rng.randint(1, 40, n).astype(np.int32)
+        ro, rg = o.bow_assemble(w, v, nd), g.bow_assemble(w, v, nd)
+        for a, b in zip(ro, rg):
+            assert np.array_equal(a, b), n
