@@ -11,7 +11,10 @@
  * A handle owns its CUDA stream(s), device pyramids and scratch.  Distinct handles may be used
  * concurrently from different host threads; one handle is not re-entrant (same as the reference:
  * ORBextractor is stateful through mvImagePyramid, include/ORBextractor.h:92).
- * Image pointers are HOST pointers unless the function name ends in _dev.
+ * Image pointers are HOST pointers unless the function name ends in _dev; pinned (page-locked) host images are read by
+ * the device directly, pageable ones go through a pinned staging buffer inside the handle.
+ * Nothing CUDA lives in the caller's thread-local storage for the extractors (events belong to the handles): the
+ * reference's Frame::Frame spawns fresh std::threads every frame (src/Frame.cc:164-171).
  */
 #ifndef OLF_ABI_H
 #define OLF_ABI_H
@@ -117,6 +120,10 @@ int olf_orb_features_per_level(const olf_orb* h, int* out);
 /* debug/parity: FAST candidates of the last extract, before the quadtree (src/ORBextractor.cc:791-831):
  * per candidate {level, x, y, score} with x,y relative to the level image. */
 int olf_orb_last_candidates(olf_orb* h, int* lvl_x_y_score /*cap x 4*/, int cap, int* n);
+
+/* parity hook: the device evaluates the per-keypoint cosf / sinf of rBRIEF (src/ORBextractor.cc:113-115) with glibc's own
+ * algorithm (csrc/sincosf_exact.h); cos_sin[2*i], cos_sin[2*i+1] = cos, sin of the float with bit pattern first_bits + i*stride */
+int olf_trig_sweep(unsigned first_bits, unsigned stride, unsigned count, float* cos_sin, int device);
 
 /* ---- Lineextractor (include/LineExtractor.h:40-72; src/LineExtractor.cc:31-67) ---------------------------- */
 olf_line* olf_line_create(const olf_line_params* p, int device);

@@ -61,6 +61,8 @@ void orc_gaussian_blur(const uint8_t* src, int w, int h, int ksize, double sigma
 void orc_gauss_kernel_q8(int ksize, double sigma, int* out);
 void orc_sobel3(const uint8_t* src, int w, int h, int16_t* dx, int16_t* dy);
 float orc_fast_atan2(float y, float x);
+/* host libm cosf / sinf of n floats (what computeOrbDescriptor calls, src/ORBextractor.cc:113-115) */
+void orc_cosf_sinf(const float* x, long n, float* c, float* s);
 int orc_fast_detect(const uint8_t* img, int w, int h, int stride, int th, int nms, int* xys, int cap);
 void orc_fast_score_map(const uint8_t* img, int w, int h, int stride, uint8_t* score);
 #ifdef __cplusplus

@@ -372,3 +372,5 @@ extern "C" void orc_fast_score_map(const uint8_t* img, int w, int h, int stride,
     fast_score_map(img, w, h, stride, s);
     memcpy(score, s.data(), s.size());
 }
+
+extern "C" void orc_cosf_sinf(const float* x, long n, float* c, float* s) { for (long i = 0; i < n; ++i) { c[i] = cosf(x[i]); s[i] = sinf(x[i]); } }

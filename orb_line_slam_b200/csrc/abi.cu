@@ -19,19 +19,24 @@ static int sync_mode() {
     static const int mode = [] { const char* e = getenv("OLF_SYNC"); return !e ? 0 : (std::string(e) == "spin" ? 1 : (std::string(e) == "block" ? 2 : 0)); }();
     return mode;
 }
+// per-thread events of the stateless entry points (matchers); destroyed when the thread exits
+struct ThreadEvents {
+    cudaEvent_t ev[16] = {nullptr};
+    ~ThreadEvents() { for (int d = 0; d < 16; ++d) if (ev[d]) { cudaEventDestroy(ev[d]); cudaGetLastError(); } }
+};
 cudaError_t stream_record(cudaStream_t s, cudaEvent_t* out) {
-    static thread_local cudaEvent_t ev[16] = {nullptr};
+    static thread_local ThreadEvents te;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 16) return cudaErrorInvalidDevice;
-    if (!ev[dev]) { e = cudaEventCreateWithFlags(&ev[dev], (sync_mode() == 2 ? cudaEventBlockingSync : 0) | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
-    *out = ev[dev];
-    return cudaEventRecord(ev[dev], s);
+    if (!te.ev[dev]) { e = cudaEventCreateWithFlags(&te.ev[dev], (sync_mode() == 2 ? cudaEventBlockingSync : 0) | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    *out = te.ev[dev];
+    return cudaEventRecord(te.ev[dev], s);
 }
-cudaError_t event_wait(cudaEvent_t ev) {
+cudaError_t event_wait(cudaEvent_t ev, bool blocking) {
     const int mode = sync_mode();
-    if (mode == 2) return cudaEventSynchronize(ev);
+    if (mode == 2 || (blocking && mode != 1)) return cudaEventSynchronize(ev);
     for (int spins = 0;; ++spins) {
         const cudaError_t e = cudaEventQuery(ev);
         if (e != cudaErrorNotReady) return e;
@@ -68,6 +73,7 @@ void olf_orb_destroy(olf_orb* h) { orb_destroy((OrbImpl*)h); }
 int olf_orb_extract(olf_orb* h, const uint8_t* img, int width, int height, int stride, olf_keypoint* kps, uint8_t* desc, int cap, int* n) {
     return orb_extract((OrbImpl*)h, img, width, height, stride, false, kps, desc, cap, n);
 }
+int olf_trig_sweep(unsigned first_bits, unsigned stride, unsigned count, float* cos_sin, int device) { return orb_trig_sweep(first_bits, stride, count, cos_sin, device); }
 int olf_orb_extract_dev(olf_orb* h, const uint8_t* d_img, int width, int height, int stride, olf_keypoint* kps, uint8_t* desc, int cap, int* n) {
     return orb_extract((OrbImpl*)h, d_img, width, height, stride, true, kps, desc, cap, n);
 }

@@ -17,7 +17,22 @@ void count_launches(int n);
 cudaError_t stream_sync(cudaStream_t s);
 // the two halves of stream_sync: mark "everything enqueued so far" / wait for that mark
 cudaError_t stream_record(cudaStream_t s, cudaEvent_t* out);
-cudaError_t event_wait(cudaEvent_t ev);            // bookkeeping for bench.py's gpu_launches (kernels launched by this library)
+cudaError_t event_wait(cudaEvent_t ev, bool blocking = false);
+// A "wait for everything enqueued so far" event owned by a handle (not by the calling thread: the reference's Frame::Frame
+// spawns fresh std::threads every frame, src/Frame.cc:164-171, so nothing CUDA may live in thread-local storage of callers).
+// blocking: the waiting thread sleeps until the driver's interrupt (batch rigs: many waiting threads, few host cores);
+// otherwise it polls, yielding the core between polls (lowest latency for a single frame).
+struct SyncEvent {
+    cudaEvent_t ev = nullptr; bool blocking = false;
+    cudaError_t create(bool blocking_) {
+        blocking = blocking_;
+        return cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0));
+    }
+    void destroy() { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    cudaError_t record(cudaStream_t s) { return cudaEventRecord(ev, s); }
+    cudaError_t wait() { return event_wait(ev, blocking); }
+    cudaError_t sync(cudaStream_t s) { const cudaError_t e = record(s); return e != cudaSuccess ? e : wait(); }
+};
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define OLF_CUDA(call)                                                         \
@@ -38,11 +53,12 @@ struct DevBuf {
         if (count <= n) return OLF_OK;
         // cudaFree / cudaMalloc synchronise the whole device (they would stall every rig in flight): when an existing
         // buffer has to grow, grow it geometrically so that steady state never reallocates
-        if (p) { count = count + count / 2 + 4096; cudaFree(p); }
-        p = nullptr; n = 0;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
-        n = count;
+        if (p) count = count + count / 2 + 4096;
+        T* np = nullptr;
+        cudaError_t e = cudaMalloc((void**)&np, count * sizeof(T));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);      // the old buffer stays valid
+        if (p) cudaFree(p);
+        p = np; n = count;
         return OLF_OK;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }

@@ -1,6 +1,10 @@
 // Whole-frame driver: the B200 replacement for Frame::Frame(stereo+lines) (reference src/Frame.cc:136-221).
-// Three persistent host threads play the role of the reference's four std::threads (src/Frame.cc:164-171): ORB of the left
-// images, ORB of the right images, and ONE batched chain of launches for the line extraction of all images of the call.
+// The reference runs ExtractORB(L|R) and ExtractLine(L|R) on four std::threads (src/Frame.cc:164-171).  Here the CALLING
+// thread is the only host thread of a batch rig: the ORB extraction of every image of the call and the stereo point
+// matcher are one asynchronous chain on the rig's first stream (no host step inside: quadtree and trig run on the device),
+// the line extraction of all images is one batched chain on the second stream whose three host steps (libm trig of the
+// O(#regions) rectangles, KeyLine construction, top-N) run on the calling thread while the first stream works.
+// A single-frame rig (latency) keeps ONE helper thread so that the two eyes' LSD chains run side by side.
 #include "common.cuh"
 #include "orb.h"
 #include "line.h"
@@ -9,7 +13,6 @@
 #include <mutex>
 #include <condition_variable>
 #include <functional>
-#include <atomic>
 
 namespace olf {
 
@@ -38,13 +41,15 @@ struct FrontendImpl {
     olf_frontend_params P;
     int device;
     int max_frames = 1;                  // frames per olf_frontend_process_batch call
-    // slot 2*f + eye.  TWO streams per rig: every ORB extractor rides on the first one's stream (the stereo matchers too),
-    // every line extractor is driven through the first one's stream by ONE batched chain of launches (line_extract_batch)
+    // slot 2*f + eye.  TWO streams per rig: every ORB extractor (and the stereo point matcher) rides on the first ORB extractor's
+    // stream; the line extractors of a batch rig are driven through the first one's stream by ONE batched chain of launches
     std::vector<OrbImpl*> orb;
     std::vector<LineImpl*> line;
-    Worker* workers[4] = {nullptr, nullptr, nullptr, nullptr};   // ORB left images, ORB right images, line images (4th: right eye of a single-frame rig)
+    StereoWs sws[4];
+    SyncEvent ev_orb;
+    Worker* worker = nullptr;            // single-frame rig only: the right eye's line extraction
     olf_frame_offsets off;
-    std::string err[4];
+    std::string err;
 };
 
 static uint64_t a64(uint64_t v) { return (v + 63) / 64 * 64; }
@@ -68,6 +73,7 @@ int frame_layout(int cap_p, int cap_l, olf_frame_offsets* o) {
     return OLF_OK;
 }
 
+void frontend_destroy(FrontendImpl* h);
 FrontendImpl* frontend_create(const olf_frontend_params* p, int device, int max_frames) {
     if (!p || p->cap_points < p->nfeatures || p->cap_lines < 0 || max_frames < 1 || 2 * max_frames > 8) {
         set_last_error("olf_frontend_create: bad arguments (1..4 frames per batch)"); return nullptr;
@@ -75,29 +81,33 @@ FrontendImpl* frontend_create(const olf_frontend_params* p, int device, int max_
     FrontendImpl* h = new FrontendImpl();
     h->P = *p; h->device = device; h->max_frames = max_frames;
     frame_layout(p->cap_points, p->cap_lines, &h->off);
+    const bool batch = max_frames > 1;
     bool ok = true;
     for (int k = 0; k < 2 * max_frames && ok; ++k) {
         // a single-frame rig (latency matters) keeps one stream per eye and extracts the two eyes' lines side by side; a batch
         // rig (throughput matters) drives every line extractor through ONE stream and one batched chain of launches
-        if (p->has_lines) { h->line.push_back(line_create(&p->line, device, (h->line.empty() || max_frames == 1) ? nullptr : line_stream(h->line[0]))); ok = h->line.back() != nullptr; }
+        if (p->has_lines) { h->line.push_back(line_create(&p->line, device, (h->line.empty() || !batch) ? nullptr : line_stream(h->line[0]), batch)); ok = h->line.back() != nullptr; }
         if (ok) {
             h->orb.push_back(orb_create(p->nfeatures, p->scale_factor, p->nlevels, p->ini_th_fast, p->min_th_fast, device,
                                         h->orb.empty() ? nullptr : orb_stream(h->orb[0])));
             ok = h->orb.back() != nullptr;
         }
     }
+    ok = ok && h->ev_orb.create(batch) == cudaSuccess;
     if (!ok) {
         const std::string e = olf_last_error();
-        for (size_t k = h->orb.size(); k-- > 0;) orb_destroy(h->orb[k]);
-        for (size_t k = h->line.size(); k-- > 0;) line_destroy(h->line[k]);
-        delete h; set_last_error(e); return nullptr;
+        frontend_destroy(h); set_last_error(e); return nullptr;
     }
-    for (int i = 0; i < 4; ++i) h->workers[i] = new Worker();
+    if (!batch && p->has_lines) h->worker = new Worker();
     return h;
 }
 void frontend_destroy(FrontendImpl* h) {
     if (!h) return;
-    for (int i = 0; i < 4; ++i) delete h->workers[i];
+    delete h->worker;
+    cudaSetDevice(h->device);
+    if (!h->orb.empty()) cudaStreamSynchronize(orb_stream(h->orb[0]));
+    for (int f = 0; f < 4; ++f) stereo_ws_release(&h->sws[f]);
+    h->ev_orb.destroy();
     for (size_t k = h->orb.size(); k-- > 0;) orb_destroy(h->orb[k]);     // the borrowers before the owner of the stream
     for (size_t k = h->line.size(); k-- > 0;) line_destroy(h->line[k]);
     delete h;
@@ -111,7 +121,7 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
     }
     for (int f = 0; f < nframes; ++f) if (!img_l[f] || !img_r[f] || !results[f]) { set_last_error("olf_frontend_process: bad arguments"); return OLF_ERR_ARG; }
     const olf_frame_offsets& o = h->off;
-    const int nimg = 2 * nframes;
+    const int nimg = 2 * nframes, capP = h->P.cap_points;
     std::vector<int> n(nimg, 0), m(nimg, 0);
     std::vector<const uint8_t*> img(nimg);
     std::vector<olf_keypoint*> kps(nimg); std::vector<uint8_t*> desc(nimg), ldesc(nimg); std::vector<olf_keyline*> kls(nimg);
@@ -119,57 +129,56 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
         uint8_t* base = (uint8_t*)results[f];
         olf_frame_header* hd = (olf_frame_header*)base;
         memset(hd, 0, sizeof(*hd));
-        hd->cap_points = h->P.cap_points; hd->cap_lines = h->P.cap_lines;
+        hd->cap_points = capP; hd->cap_lines = h->P.cap_lines;
         img[2 * f] = img_l[f]; img[2 * f + 1] = img_r[f];
         kps[2 * f] = (olf_keypoint*)(base + o.kps_l); kps[2 * f + 1] = (olf_keypoint*)(base + o.kps_r);
         desc[2 * f] = base + o.desc_l; desc[2 * f + 1] = base + o.desc_r;
         kls[2 * f] = (olf_keyline*)(base + o.kls_l); kls[2 * f + 1] = (olf_keyline*)(base + o.kls_r);
         ldesc[2 * f] = base + o.ldesc_l; ldesc[2 * f + 1] = base + o.ldesc_r;
     }
-    // ExtractORB(0|1) of every frame on two threads (left images, right images), ExtractLine(0|1) of every frame as one
-    // batched chain on a third (the reference's four threads, src/Frame.cc:164-171, regrouped by kind of work)
-    for (int e = 0; e < 2; ++e)
-        h->workers[e]->submit([=, &n, &kps, &desc, &img]() {
-            for (int f = 0; f < nframes; ++f) {
-                const int k = 2 * f + e;
-                const int rc = orb_extract(h->orb[k], img[k], w, hgt, stride, on_device != 0, kps[k], desc[k], h->P.cap_points, &n[k]);
-                if (rc) { h->err[e] = olf_last_error(); return rc; }
-            }
-            return (int)OLF_OK;
-        });
-    const bool side_by_side = h->P.has_lines && h->max_frames == 1;      // one frame: the two eyes on their own streams
-    if (side_by_side) {
-        for (int e = 0; e < 2; ++e)
-            h->workers[2 + e]->submit([=, &m, &kls, &ldesc, &img]() {
-                const int rc = line_extract(h->line[e], img[e], w, hgt, stride, on_device != 0, kls[e], ldesc[e], h->P.cap_lines, &m[e]);
-                if (rc) h->err[2 + e] = olf_last_error();
-                return rc;
+    // ExtractORB(0|1) of every frame + ComputeStereoMatches: one asynchronous chain on the first stream
+    cudaStream_t so = orb_stream(h->orb[0]);
+    int rc = orb_enqueue(h->orb.data(), nimg, img.data(), w, hgt, stride, on_device != 0, capP, so);
+    for (int f = 0; f < nframes && !rc; ++f)
+        rc = stereo_points_enqueue(&h->sws[f], h->orb[2 * f], h->orb[2 * f + 1], h->P.cam.bf, h->P.cam.fx, capP, so);
+    if (!rc && h->ev_orb.record(so) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaEventRecord", __FILE__, __LINE__);
+    if (rc) { cudaStreamSynchronize(so); return rc; }
+    // ExtractLine(0|1) of every frame on the second stream while the first one works
+    int rc_l = OLF_OK;
+    if (h->P.has_lines) {
+        if (h->worker) {           // one frame: the two eyes side by side on their own streams
+            h->worker->submit([=, &m, &kls, &ldesc, &img]() {
+                const int r = line_extract(h->line[1], img[1], w, hgt, stride, on_device != 0, kls[1], ldesc[1], h->P.cap_lines, &m[1]);
+                if (r) h->err = olf_last_error();
+                return r;
             });
-    } else if (h->P.has_lines)
-        h->workers[2]->submit([=, &m, &kls, &ldesc, &img]() {
-            const int rc = line_extract_batch(h->line.data(), nimg, img.data(), w, hgt, stride, on_device != 0, kls.data(), ldesc.data(), h->P.cap_lines, m.data());
-            if (rc) h->err[2] = olf_last_error();
-            return rc;
-        });
-    int rc = OLF_OK;
-    for (int i = 0; i < 4; ++i) {
-        if (i >= 2 && !h->P.has_lines) break;
-        if (i == 3 && !side_by_side) break;
-        const int r = h->workers[i]->wait();
-        if (r && !rc) { rc = r; set_last_error(h->err[i]); }
+            rc_l = line_extract(h->line[0], img[0], w, hgt, stride, on_device != 0, kls[0], ldesc[0], h->P.cap_lines, &m[0]);
+            const int r1 = h->worker->wait();
+            if (!rc_l && r1) { rc_l = r1; set_last_error(h->err); }
+        } else
+            rc_l = line_extract_batch(h->line.data(), nimg, img.data(), w, hgt, stride, on_device != 0, kls.data(), ldesc.data(), h->P.cap_lines, m.data());
     }
-    match_use_stream(orb_stream(h->orb[0]));
+    const std::string err_l = rc_l ? olf_last_error() : "";
+    if (h->ev_orb.wait() != cudaSuccess) return cuda_fail(cudaGetLastError(), "ORB chain", __FILE__, __LINE__);
+    for (int k = 0; k < nimg && !rc; ++k) rc = orb_collect(h->orb[k], kps[k], desc[k], capP, &n[k]);
+    if (!rc && rc_l) { rc = rc_l; set_last_error(err_l); }
+    match_use_stream(h->P.has_lines ? line_stream(h->line[0]) : so);
     for (int f = 0; f < nframes; ++f) {
         uint8_t* base = (uint8_t*)results[f];
         olf_frame_header* hd = (olf_frame_header*)base;
         const int kl = 2 * f, kr = 2 * f + 1;
         hd->n_l = n[kl]; hd->n_r = n[kr]; hd->m_l = m[kl]; hd->m_r = m[kr];
-        if (!rc && n[kl] > 0)       // if(mvKeys.empty()) return;  (src/Frame.cc:176)
-            rc = stereo_points(h->orb[kl], h->orb[kr], kps[kl], desc[kl], n[kl], kps[kr], desc[kr], n[kr], h->P.cam.bf, h->P.cam.fx,
-                               (float*)(base + o.u_right), (float*)(base + o.depth));
+        if (!rc && n[kl] > 0) {     // if(mvKeys.empty()) return;  (src/Frame.cc:176)
+            memcpy(base + o.u_right, h->sws[f].out.p, (size_t)n[kl] * 4);
+            memcpy(base + o.depth, h->sws[f].out.p + h->sws[f].cap, (size_t)n[kl] * 4);
+        }
         if (!rc && n[kl] > 0 && h->P.has_lines)
             rc = stereo_lines(kls[kl], ldesc[kl], m[kl], kls[kr], ldesc[kr], m[kr], w, hgt, &h->P.line_match,
                               (int*)(base + o.lmatch), (float*)(base + o.ldisp), (double*)(base + o.lle), h->device);
+        else if (h->P.has_lines) {  // ComputeStereoMatches_Lines not reached: every line unmatched (mvDisparity_l = (-1,-1), mvle_l = 0)
+            int* lm = (int*)(base + o.lmatch); float* ld = (float*)(base + o.ldisp); double* le = (double*)(base + o.lle);
+            for (int i = 0; i < m[kl]; ++i) { lm[i] = -1; ld[2 * i] = ld[2 * i + 1] = -1.f; le[3 * i] = le[3 * i + 1] = le[3 * i + 2] = 0; }
+        }
         hd->status = rc;
     }
     match_use_stream(nullptr);

@@ -37,9 +37,15 @@ static __device__ __forceinline__ void locate_tile(const LevelTable& T, int b, i
 
 // ---- fixed-point separable Gaussian blur on 8U, all levels in one launch ---------------------
 // H pass 8.8 (u16), V pass 16.16, rounding (acc + 2^15) >> 16, BORDER_REFLECT_101 at the level edge.
+// A batch of images per launch (blockIdx.y): the rigs keep 2..8 images in flight and every kernel of this front end is
+// launch-bound on one 0.9-MB image, so one launch serves all images of a call.
+#define IMG_MAX_BATCH 8
+struct BlurBatch { const uint8_t* src[IMG_MAX_BATCH]; uint8_t* dst[IMG_MAX_BATCH]; };
 template <int K>
-static __global__ void __launch_bounds__(256) k_blur_q8(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+static __global__ void __launch_bounds__(256) k_blur_q8(const __grid_constant__ BlurBatch BB,
                                                  const __grid_constant__ LevelTable T, const int q0, const int q1, const int q2, const int q3) {
+    const uint8_t* __restrict__ src = BB.src[blockIdx.y];
+    uint8_t* __restrict__ dst = BB.dst[blockIdx.y];
     constexpr int R = K / 2;
     __shared__ uint8_t tile[TILE_H + 2 * R][TILE_W + 2 * R + 2];
     __shared__ uint16_t hbuf[TILE_H + 2 * R][TILE_W];

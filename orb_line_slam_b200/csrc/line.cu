@@ -932,6 +932,7 @@ struct LineImpl {
     PinBuf<LbdLine> lbd_lines; DevBuf<float4> rowsum; PinBuf<uint8_t> desc_host;
     int lbd_cap = 0;
     cudaEvent_t ev_grow0 = nullptr, ev_grow1 = nullptr;
+    SyncEvent sync;                      // owned by the handle: callers may be short-lived threads
     int last_stats[8] = {0};
 };
 
@@ -959,7 +960,7 @@ static void gauss_kernel_q8(int n, double sigma, int* q) {                      
     q[n / 2] = 256 - acc;
 }
 
-LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_stream) {
+LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_stream, bool blocking_sync) {
     if (!p || p->lsd_refine != 0 || p->lsd_n_bins < 1 || p->lsd_n_bins > 1024 || p->lsd_scale <= 0 || p->lsd_ang_th <= 0 || p->lsd_ang_th >= 180) {
         set_last_error("olf_line_create: unsupported parameters (refine must be 0, n_bins <= 1024)"); return nullptr;
     }
@@ -1007,14 +1008,13 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     bool ok = true;
     if (ext_stream) { h->stream = ext_stream; h->owns_stream = false; }
     else ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaEventCreate(&h->ev_grow0) == cudaSuccess && cudaEventCreate(&h->ev_grow1) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev_grow0) == cudaSuccess && cudaEventCreate(&h->ev_grow1) == cudaSuccess && h->sync.create(blocking_sync) == cudaSuccess;
     ok = ok && h->tab_seed.ensure(ts.size()) == OLF_OK && h->tab_acc.ensure(ta.size()) == OLF_OK;
     ok = ok && cudaMemcpy(h->tab_seed.p, ts.data(), ts.size() * sizeof(float2_t), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(h->tab_acc.p, ta.data(), ta.size() * sizeof(float2_t), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpyToSymbol(c_gaussG, gG, sizeof(gG)) == cudaSuccess && cudaMemcpyToSymbol(c_gaussL, gL, sizeof(gL)) == cudaSuccess;
     ok = ok && cudaMemcpyToSymbol(c_lbd_comb, LBD_COMB, sizeof(LBD_COMB)) == cudaSuccess;
-    int coop = 0, sms = 0, per_sm = 0;
-    ok = ok && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && coop;
+    int sms = 0;
     ok = ok && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
     if (const char* e = getenv("OLF_LSD_FIRST_WAVE")) h->first_wave = h->first_wave_latency = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_WAVE_GROWTH")) h->wave_growth = std::max(2, atoi(e));
@@ -1033,7 +1033,6 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     if (const char* e = getenv("OLF_LSD_SCAN_BLOCKS")) h->scan_blocks = h->scan_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_VERIFY_BLOCKS")) h->verify_blocks = h->verify_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks_wide = h->grow_blocks_narrow = std::max(1, atoi(e));
-    (void)per_sm;
     return h;
 }
 
@@ -1043,6 +1042,7 @@ void line_destroy(LineImpl* h) {
     if (h->stream && h->owns_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     if (h->ev_grow0) cudaEventDestroy(h->ev_grow0);
     if (h->ev_grow1) cudaEventDestroy(h->ev_grow1);
+    h->sync.destroy();
     h->img_stage.release(); h->img.release(); h->blurred.release(); h->scaled.release(); h->lbd_blur.release(); h->coef.release();
     h->ang.release(); h->dabc.release(); h->seed_prio.release(); h->seed_pix.release(); h->n2max.release(); h->status.release();
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
@@ -1106,8 +1106,14 @@ static int line_upload(LineImpl* h, const uint8_t* img, int w, int hgt, int stri
     if (rc) return rc;
     if (on_device) OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, img, stride, w, hgt, cudaMemcpyDeviceToDevice, s));
     else {
-        for (int y = 0; y < hgt; ++y) memcpy(h->img_stage.p + (size_t)y * w, img + (size_t)y * stride, w);
-        OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, h->img_stage.p, w, w, hgt, cudaMemcpyHostToDevice, s));
+        cudaPointerAttributes a;
+        const bool pinned = cudaPointerGetAttributes(&a, img) == cudaSuccess && a.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();
+        if (pinned) OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, img, stride, w, hgt, cudaMemcpyHostToDevice, s));
+        else {      // pageable caller memory goes through the handle's pinned staging buffer
+            for (int y = 0; y < hgt; ++y) memcpy(h->img_stage.p + (size_t)y * w, img + (size_t)y * stride, w);
+            OLF_CUDA(cudaMemcpy2DAsync(h->img.p, h->ipitch, h->img_stage.p, w, w, hgt, cudaMemcpyHostToDevice, s));
+        }
     }
     return OLF_OK;
 }
@@ -1119,9 +1125,10 @@ static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D, int batch_im
     if (h->blur_k) {
         const LevelTable T = single_level(w, hgt, h->ipitch);
         const int nt = T.tile_start[1];
-        if (h->blur_k == 7) k_blur_q8<7><<<nt, 256, 0, s>>>(h->img.p, h->blurred.p, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], h->blur_q[3]);
-        else if (h->blur_k == 5) k_blur_q8<5><<<nt, 256, 0, s>>>(h->img.p, h->blurred.p, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], 0);
-        else k_blur_q8<3><<<nt, 256, 0, s>>>(h->img.p, h->blurred.p, T, h->blur_q[0], h->blur_q[1], 0, 0);
+        BlurBatch bb; memset(&bb, 0, sizeof(bb)); bb.src[0] = h->img.p; bb.dst[0] = h->blurred.p;
+        if (h->blur_k == 7) k_blur_q8<7><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], h->blur_q[3]);
+        else if (h->blur_k == 5) k_blur_q8<5><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], 0);
+        else k_blur_q8<3><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], 0, 0);
         dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
         k_resize_exact<<<g, b, 0, s>>>(h->blurred.p, w, hgt, h->ipitch, h->scaled.p, W, H, h->wpitch, h->coef.p, h->coef.p + h->coef_y_off);
         work = h->scaled.p; wp = h->wpitch;
@@ -1200,7 +1207,7 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
         enqueue_phases(h0->phase_batch);
         OLF_CUDA(cudaEventRecord(h0->ev_grow1, s));
         for (int k = 0; k < n; ++k) if ((rc = lsd_enqueue_rect_a(hs[k], s))) return rc;
-        OLF_CUDA(stream_sync(s));
+        OLF_CUDA(h0->sync.sync(s));
         bool all = true;
         for (int k = 0; k < n; ++k) all = all && (hs[k]->status_host.p[3] || hs[k]->status_host.p[0]);
         if (all) break;
@@ -1222,7 +1229,7 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
         count_launches(1);
     }
     OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(stream_sync(s));
+    OLF_CUDA(h0->sync.sync(s));
     for (int k = 0; k < n; ++k) {
         LineImpl* h = hs[k];
         const int nr = h->last_stats[2];
@@ -1290,7 +1297,8 @@ static int lbd_enqueue(LineImpl* h, const olf_keyline* kls, int n, cudaStream_t 
         h->lbd_lines.p[i] = L;
     }
     const LevelTable T = single_level(w, hgt, h->ipitch);
-    k_blur_q8<5><<<T.tile_start[1], 256, 0, s>>>(h->img.p, h->lbd_blur.p, T, 14, 62, 104, 0);       // 5x5 sigma 1 (:358)
+    BlurBatch bb; memset(&bb, 0, sizeof(bb)); bb.src[0] = h->img.p; bb.dst[0] = h->lbd_blur.p;
+    k_blur_q8<5><<<T.tile_start[1], 256, 0, s>>>(bb, T, 14, 62, 104, 0);       // 5x5 sigma 1 (:358)
     dim3 g((w + 31) / 32, (hgt + 7) / 8);
     k_sobel3<<<g, 256, 0, s>>>(h->lbd_blur.p, w, hgt, h->ipitch, h->grad.p);
     k_lbd_rows<<<(n * 63 + 255) / 256, 256, 0, s>>>(h->lbd_lines.d, n, h->grad.p, w, hgt, h->rowsum.p);
@@ -1320,7 +1328,7 @@ int line_lbd_compute(LineImpl* h, const uint8_t* img, int w, int hgt, int stride
     int rc = line_upload(h, img, w, hgt, stride, false, h->stream);
     if (rc) return rc;
     if ((rc = lbd_enqueue(h, kls, n, h->stream))) return rc;
-    OLF_CUDA(stream_sync(h->stream));
+    OLF_CUDA(h->sync.sync(h->stream));
     memcpy(desc, h->desc_host.p, (size_t)n * 32);
     return OLF_OK;
 }
@@ -1354,7 +1362,7 @@ int line_extract_batch(LineImpl* const* hs, int nimg, const uint8_t* const* imgs
         memcpy(kls[k], v.data(), v.size() * sizeof(olf_keyline));
         if ((rc = lbd_enqueue(h, v.data(), (int)v.size(), s))) return rc;
     }
-    OLF_CUDA(stream_sync(s));
+    OLF_CUDA(hs[0]->sync.sync(s));
     for (int k = 0; k < nimg; ++k) if (n[k]) memcpy(desc[k], hs[k]->desc_host.p, (size_t)n[k] * 32);
     return OLF_OK;
 }

@@ -5,7 +5,8 @@
 #include "../../include/olf_abi.h"
 namespace olf {
 struct LineImpl;
-LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_stream = nullptr);
+// blocking_sync: waits sleep on the driver's interrupt instead of polling (batch rigs)
+LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_stream = nullptr, bool blocking_sync = false);
 void line_destroy(LineImpl* h);
 int line_lsd_detect(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, float* segs, int cap, int* n);
 int line_lbd_compute(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, const olf_keyline* kls, int n, uint8_t* desc);

@@ -30,6 +30,14 @@ struct MatchCtx {
     cudaStream_t stream = nullptr;     // the calling thread's own stream
     cudaStream_t cur = nullptr;        // stream of this call: the thread's own, or the one a rig lent (match_use_stream)
     Arena a;
+    // a thread that ends gives its stream and arenas back (callers may be short-lived threads)
+    ~MatchCtx() {
+        if (device < 0) return;
+        if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+        a.dev.release(); a.pin.release();
+        cudaGetLastError();
+    }
 };
 static thread_local MatchCtx g_ctx[16];
 static thread_local cudaStream_t g_lent_stream = nullptr;
@@ -48,9 +56,10 @@ static int get_ctx(int device, MatchCtx** out) {
     MatchCtx& c = g_ctx[device];
     if (g_lent_stream) c.cur = g_lent_stream;
     else {
-        if (!c.stream) { OLF_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); c.device = device; }
+        if (!c.stream) OLF_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         c.cur = c.stream;
     }
+    c.device = device;
     c.a.reset();
     *out = &c;
     return OLF_OK;
@@ -217,11 +226,15 @@ struct PyrView { const uint8_t* pyr; int w[OLF_MAX_LEVELS], h[OLF_MAX_LEVELS], p
 __device__ __forceinline__ int px_reflect(const PyrView& P, int l, int x, int y) {
     return P.pyr[P.off[l] + (size_t)reflect101(y, P.h[l]) * P.pitch[l] + reflect101(x, P.w[l])];
 }
-__global__ void __launch_bounds__(256) k_stereo_points(const olf_keypoint* __restrict__ kl, const uint32_t* __restrict__ dl, int N,
-                                                       const olf_keypoint* __restrict__ kr, const uint32_t* __restrict__ dr, int Nr,
+// Np / Nrp: when not null the keypoint counts are read from the device (the extractor's result is still in flight when
+// this kernel is enqueued); N / Nr are then the capacities.
+__global__ void __launch_bounds__(256) k_stereo_points(const olf_keypoint* __restrict__ kl, const uint32_t* __restrict__ dl, int N, const int* __restrict__ Np,
+                                                       const olf_keypoint* __restrict__ kr, const uint32_t* __restrict__ dr, int Nr, const int* __restrict__ Nrp,
                                                        const __grid_constant__ PyrView PL, const __grid_constant__ PyrView PR,
                                                        float mbf, float fx, float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sad) {
     const int iL = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (Np) N = min(N, *Np);
+    if (Nrp) Nr = min(Nr, *Nrp);
     if (iL >= N) return;
     const olf_keypoint kpL = kl[iL];
     const int levelL = kpL.octave;
@@ -307,8 +320,9 @@ __global__ void __launch_bounds__(256) k_stereo_points(const olf_keypoint* __res
 }
 // median SAD outlier rejection (src/Frame.cc:861-875): one block; the size/2-th order statistic of the SAD values
 // (all < 2^16: 121 px x 510) by a two-level radix select on shared-memory histograms
-__global__ void __launch_bounds__(1024) k_stereo_median(float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad, int N) {
+__global__ void __launch_bounds__(1024) k_stereo_median(float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad, int N, const int* __restrict__ Np) {
     __shared__ unsigned hist[256];
+    if (Np) N = min(N, *Np);
     __shared__ int s_cnt, s_hi, s_rank, s_median;
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) { s_cnt = 0; s_median = -1; }
@@ -376,9 +390,9 @@ int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const u
         OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_dr), h_dr, (size_t)Nr * 32, cudaMemcpyHostToDevice, s));
     }
     // the extractors' entry points synchronise their own streams before returning, so the pyramids are complete
-    k_stereo_points<<<(N + 7) / 8, 256, 0, s>>>(dptr<olf_keypoint>(c, o_kl), dptr<uint32_t>(c, o_dl), N, dptr<olf_keypoint>(c, o_kr), dptr<uint32_t>(c, o_dr), Nr,
+    k_stereo_points<<<(N + 7) / 8, 256, 0, s>>>(dptr<olf_keypoint>(c, o_kl), dptr<uint32_t>(c, o_dl), N, nullptr, dptr<olf_keypoint>(c, o_kr), dptr<uint32_t>(c, o_dr), Nr, nullptr,
                                                  make_view(vl), make_view(vr), bf, fx, dptr<float>(c, o_u), dptr<float>(c, o_d), dptr<int>(c, o_s));
-    k_stereo_median<<<1, 1024, 0, s>>>(dptr<float>(c, o_u), dptr<float>(c, o_d), dptr<int>(c, o_s), N);
+    k_stereo_median<<<1, 1024, 0, s>>>(dptr<float>(c, o_u), dptr<float>(c, o_d), dptr<int>(c, o_s), N, nullptr);
     count_launches(2);
     float* ho = hptr<float>(c, p_out);
     OLF_CUDA(cudaMemcpyAsync(ho, dptr<float>(c, o_u), (size_t)N * 4, cudaMemcpyDeviceToHost, s));
@@ -386,6 +400,34 @@ int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const u
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(stream_sync(s));
     memcpy(uRight, ho, (size_t)N * 4); memcpy(depth, ho + N, (size_t)N * 4);
+    return OLF_OK;
+}
+
+// Frame::ComputeStereoMatches on the extractors' DEVICE-RESIDENT results, enqueued behind them on stream s (nothing waits):
+// uRight / depth of up to `cap` left keypoints land in ws->out (pinned) as [uRight[cap] | depth[cap]].
+int stereo_ws_ensure(StereoWs* ws, int cap) {
+    int rc;
+    if (cap <= ws->cap) return OLF_OK;
+    if ((rc = ws->u.ensure(cap)) || (rc = ws->d.ensure(cap)) || (rc = ws->sad.ensure(cap)) || (rc = ws->out.ensure((size_t)2 * cap))) return rc;
+    ws->cap = cap;
+    return OLF_OK;
+}
+void stereo_ws_release(StereoWs* ws) { ws->u.release(); ws->d.release(); ws->sad.release(); ws->out.release(); ws->cap = 0; }
+int stereo_points_enqueue(StereoWs* ws, OrbImpl* left, OrbImpl* right, float bf, float fx, int cap, cudaStream_t s) {
+    const OrbDeviceView vl = orb_device_view(left), vr = orb_device_view(right);
+    if (vl.device != vr.device || !vl.pyr || !vr.pyr || vl.nlevels != vr.nlevels) { set_last_error("olf_stereo_points: extractors must have run on the same device"); return OLF_ERR_ARG; }
+    if (vr.cap >= (1 << 20)) { set_last_error("olf_stereo_points: too many right keypoints"); return OLF_ERR_CAPACITY; }
+    int rc;
+    const int N = std::min(cap, vl.cap);
+    if (N <= 0) return OLF_OK;
+    if ((rc = stereo_ws_ensure(ws, N))) return rc;
+    k_stereo_points<<<(N + 7) / 8, 256, 0, s>>>(vl.kps, (const uint32_t*)vl.desc, N, vl.n, vr.kps, (const uint32_t*)vr.desc, vr.cap, vr.n,
+                                                 make_view(vl), make_view(vr), bf, fx, ws->u.p, ws->d.p, ws->sad.p);
+    k_stereo_median<<<1, 1024, 0, s>>>(ws->u.p, ws->d.p, ws->sad.p, N, vl.n);
+    count_launches(2);
+    OLF_CUDA(cudaMemcpyAsync(ws->out.p, ws->u.p, (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(ws->out.p + ws->cap, ws->d.p, (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
     return OLF_OK;
 }
 

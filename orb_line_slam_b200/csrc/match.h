@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/olf_abi.h"
+#include "common.cuh"
 namespace olf {
 struct OrbImpl;
 // the calling thread's next matcher calls run on `s` (nullptr: back to the thread's own stream)
@@ -11,6 +12,12 @@ int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0
 int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int mutual, int* m12, int* nmatches, int device);
 int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const uint8_t* dl, int N, const olf_keypoint* kr, const uint8_t* dr, int Nr,
                   float bf, float fx, float* uRight, float* depth);
+// device-resident variant used by the whole-frame driver (see match.cu): per-frame workspace, results in `out` (pinned)
+// as [uRight[cap] | depth[cap]] once the stream has been waited for
+struct StereoWs { DevBuf<float> u, d; DevBuf<int> sad; PinBuf<float> out; int cap = 0; };
+int stereo_ws_ensure(StereoWs* ws, int cap);
+void stereo_ws_release(StereoWs* ws);
+int stereo_points_enqueue(StereoWs* ws, OrbImpl* left, OrbImpl* right, float bf, float fx, int cap, cudaStream_t s);
 int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_keyline* kr, const uint8_t* dr, int n2, int img_w, int img_h,
                  const olf_line_match_params* P, int* matches12, float* disp, double* le, int device);
 int search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device);

@@ -1,30 +1,54 @@
 // ORB half of the front end on sm_100a: image pyramid, FAST-9/16 score map, per-cell threshold fallback + NMS +
-// ordered compaction, intensity-centroid orientation, 7x7 fixed-point blur, 256-bit rBRIEF.
-// Replaces ORB_SLAM2::ORBextractor (reference src/ORBextractor.cc:412-472, 767-855, 1045-1134).
+// ordered compaction, quadtree distribution, intensity-centroid orientation, 7x7 fixed-point blur, 256-bit rBRIEF.
+// Replaces ORB_SLAM2::ORBextractor (reference src/ORBextractor.cc:412-472, 483-765, 767-855, 1045-1134).
 // Arithmetic follows cv2 4.13 semantics pinned in SURVEY.md Appendix A (the reference's OpenCV is un-vendored).
-// The quadtree (DistributeOctTree, :541-765) is order-defining sequential list surgery and runs on the host
-// between the two GPU phases; candidates and orientations reach it through mapped pinned memory (no extra copy).
+//
+// The whole extractor is ONE asynchronous chain of launches per call, for a BATCH of images (blockIdx.y = image): nothing
+// returns to the host between the upload and the finished keypoints + descriptors.  The quadtree (DistributeOctTree,
+// :541-765) is order-defining list surgery in the reference; here one CTA per (image, level) replays it with prefix sums:
+// the list after a pass is [children of the divided nodes, newest first] ++ [undivided nodes in their old order], which is
+// exactly what the reference's push_front / erase sequence produces.
 #include "common.cuh"
 #include "orb.h"
 #include "img_kernels.cuh"
+#include "sincosf_exact.h"
 #include "../../include/olf_brief_pattern.h"
 #include <algorithm>
 #include <cmath>
-#include <list>
-#include <functional>
 
 namespace olf {
 
-// ---- pyramid: cv::resize INTER_LINEAR 8UC1, one launch per level ---------------------------
+typedef unsigned long long u64;
+
+// ---- per-image device pointers, a batch of them by value ---------------------------------------------------------
+struct OrbDev {
+    uint8_t *pyr, *score, *blur;
+    int *cell_counts, *cell_thr, *cell_off, *total; unsigned* ticket;
+    int4* cand; int cand_cap;
+    int* cnode;                 // quadtree: node position of every candidate
+    int4* nodes;                // two node lists (A, B) of qt_total entries each: {x0|y0<<16, x1|y1<<16, count, seq}
+    int* qi;                    // 12 ints per node slot: child counts[4], child positions[4], rof, moved, proc, E
+    u64* qk;                    // 3 u64 per node slot: expand keys (two lists), best candidate per node
+    int* lvl_count;             // kept keypoints per level
+    int* keep;                  // kept candidate index (into cand) per level, list order
+    olf_keypoint* kps; uint8_t* desc; int* out;    // out[0] = n, out[1] = error flag
+    int out_cap;
+};
+struct OrbBatch { int n; OrbDev d[IMG_MAX_BATCH]; };
+struct QtTable { int N[OLF_MAX_LEVELS], node_off[OLF_MAX_LEVELS], node_cap[OLF_MAX_LEVELS]; int total_cap; float scale[OLF_MAX_LEVELS]; };
+
+// ---- pyramid: cv::resize INTER_LINEAR 8UC1, one launch per level (level l is made from level l-1) ------
 // coefficient tables (x: dst_w entries, y: dst_h entries) of {src index, c0, c1} are built on the host once per size.
 struct LinCoef { int s; short c0, c1; };
 
-__global__ void k_resize_linear(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
-                                uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
+__global__ void k_resize_linear(const __grid_constant__ OrbBatch B, unsigned soff, int sw, int sh, int spitch,
+                                unsigned doff, int dw, int dh, int dpitch,
                                 const LinCoef* __restrict__ cx, const LinCoef* __restrict__ cy) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
+    const uint8_t* __restrict__ src = B.d[blockIdx.z].pyr + soff;
+    uint8_t* __restrict__ dst = B.d[blockIdx.z].pyr + doff;
     const LinCoef a = cx[x], b = cy[y];
     const int x1 = min(a.s + 1, sw - 1), y1 = min(b.s + 1, sh - 1);
     const uint8_t* r0 = src + (size_t)b.s * spitch;
@@ -36,14 +60,13 @@ __global__ void k_resize_linear(const uint8_t* __restrict__ src, int sw, int sh,
 
 // ---- FAST-9/16 threshold-free score map, all levels in one launch --------------------------
 // score = max over the 16 cyclic 9-arcs of min(d) / min(-d), minus 1; stored 0 when < min_th (never consulted then).
-__global__ void __launch_bounds__(256) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
-                                                    const __grid_constant__ LevelTable T, int min_th) {
+__global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ OrbBatch B, const __grid_constant__ LevelTable T, int min_th) {
     __shared__ uint8_t tile[TILE_H + 6][TILE_W + 8];
     int level, tx, ty;
     locate_tile(T, blockIdx.x, level, tx, ty);
     const int w = T.w[level], h = T.h[level], pitch = T.pitch[level];
-    const uint8_t* img = pyr + T.off[level];
-    uint8_t* out = score + T.off[level];
+    const uint8_t* img = B.d[blockIdx.y].pyr + T.off[level];
+    uint8_t* out = B.d[blockIdx.y].score + T.off[level];
     const int x0 = tx * TILE_W, y0 = ty * TILE_H;
     for (int i = threadIdx.x; i < (TILE_H + 6) * (TILE_W + 6); i += 256) {
         const int r = i / (TILE_W + 6), c = i % (TILE_W + 6);
@@ -76,15 +99,15 @@ __global__ void __launch_bounds__(256) k_fast_score(const uint8_t* __restrict__ 
                 int mn4[16], mx4[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-                int A = -255, B = -255;
+                int A = -255, Bm = -255;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
                     const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
                     A = max(A, mn9);
-                    B = max(B, -mx9);
+                    Bm = max(Bm, -mx9);
                 }
-                s = max(A, B) - 1;
+                s = max(A, Bm) - 1;
                 if (s < min_th) s = 0;
             }
         }
@@ -133,11 +156,11 @@ __device__ __forceinline__ void locate_cell(const LevelTable& T, int c, int& lev
     ci = t / T.ncols[level];
 }
 
-// counts[cell] = number of keypoints, thr[cell] = threshold used; the last block to finish scans counts -> offsets.
-__global__ void __launch_bounds__(128) k_cell_count(const uint8_t* __restrict__ score, const __grid_constant__ LevelTable T,
-                                                    int ini_th, int* __restrict__ counts, int* __restrict__ thr,
-                                                    int* __restrict__ offsets, int* __restrict__ total,
-                                                    unsigned* __restrict__ ticket, int ncells) {
+// counts[cell] = number of keypoints, thr[cell] = threshold used; the last block of an image scans its counts -> offsets.
+__global__ void __launch_bounds__(128) k_cell_count(const __grid_constant__ OrbBatch B, const __grid_constant__ LevelTable T, int ini_th, int ncells) {
+    const OrbDev& D = B.d[blockIdx.y];
+    const uint8_t* __restrict__ score = D.score;
+    int* __restrict__ counts = D.cell_counts;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * 4 + warp;
     if (c < ncells) {
@@ -157,13 +180,13 @@ __global__ void __launch_bounds__(128) k_cell_count(const uint8_t* __restrict__ 
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { c_hi += __shfl_xor_sync(0xffffffffu, c_hi, o); c_lo += __shfl_xor_sync(0xffffffffu, c_lo, o); }
-        if (lane == 0) { counts[c] = c_hi ? c_hi : c_lo; thr[c] = c_hi ? ini_th : 1; }
+        if (lane == 0) { counts[c] = c_hi ? c_hi : c_lo; D.cell_thr[c] = c_hi ? ini_th : 1; }
     }
     // last-block-done exclusive scan
     __shared__ bool last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) last = (atomicAdd(D.ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!last) return;
     __threadfence();
@@ -177,18 +200,17 @@ __global__ void __launch_bounds__(128) k_cell_count(const uint8_t* __restrict__ 
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int i = 0; i < 128; ++i) { const int v = part[i]; part[i] = acc; acc += v; }
-        *total = acc;
-        *ticket = 0;
+        *D.total = acc;
+        *D.ticket = 0;
     }
     __syncthreads();
     int acc = part[threadIdx.x];
-    for (int i = b; i < e; ++i) { offsets[i] = acc; acc += ((volatile int*)counts)[i]; }
+    for (int i = b; i < e; ++i) { D.cell_off[i] = acc; acc += ((volatile int*)counts)[i]; }
 }
 
 // cand[k] = {level, x, y, score} in reference order: cells row-major, pixels row-major inside a cell.
-__global__ void __launch_bounds__(128) k_cell_write(const uint8_t* __restrict__ score, const __grid_constant__ LevelTable T,
-                                                    const int* __restrict__ thr, const int* __restrict__ offsets,
-                                                    int4* __restrict__ cand, int4* __restrict__ cand_host, int cap, int ncells) {
+__global__ void __launch_bounds__(128) k_cell_write(const __grid_constant__ OrbBatch B, const __grid_constant__ LevelTable T, int ncells) {
+    const OrbDev& D = B.d[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * 4 + warp;
     if (c >= ncells) return;
@@ -196,9 +218,9 @@ __global__ void __launch_bounds__(128) k_cell_write(const uint8_t* __restrict__ 
     locate_cell(T, c, level, ci, cj);
     const CellGeom g = cell_geom(T, level, ci, cj);
     if (!g.valid) return;
-    const uint8_t* sc = score + T.off[level];
-    const int pitch = T.pitch[level], th = thr[c];
-    int pos = offsets[c];
+    const uint8_t* sc = D.score + T.off[level];
+    const int pitch = T.pitch[level], th = D.cell_thr[c];
+    int pos = D.cell_off[c];
     for (int y = g.y_lo; y < g.y_hi; ++y)
         for (int xb = g.x_lo; xb < g.x_hi; xb += 32) {
             const int x = xb + lane;
@@ -208,59 +230,286 @@ __global__ void __launch_bounds__(128) k_cell_write(const uint8_t* __restrict__ 
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int k = pos + __popc(m & ((1u << lane) - 1));
-                if (k < cap) { const int4 v = make_int4(level, x, y, s); cand[k] = v; cand_host[k] = v; }
+                if (k < D.cand_cap) D.cand[k] = make_int4(level, x, y, s);
             }
             pos += __popc(m);
         }
 }
 
-// ---- IC_Angle (src/ORBextractor.cc:79-106): one warp per candidate, lanes = rows of the radius-15 disc -----
+// ---- DistributeOctTree (src/ORBextractor.cc:483-765): one CTA per (image, level) ---------------------------------------
+// Reference semantics restated as array operations.  A node list is an array in list order (index 0 = lNodes.front()).
+// One "division step" divides the nodes proc[0..R] (in that order): their non-empty children n1..n4 are pushed to the
+// front one after the other -- so the child created e-th ends up at position K-1-e -- and every other node keeps its
+// relative order behind them.  Phase 1 (:598-669) divides every node with more than one key, in list order; phase 2
+// (:677-741) divides the nodes created by the previous step in descending (size, creation sequence) order and stops
+// as soon as the list has N nodes.  (The reference sorts pairs (size, ExtractorNode*): ties follow allocation
+// addresses; the canonical choice is creation order)  A node's keys keep their original order in
+// every child (stable partition), so "the first key of maximal response" (:747-760) is the candidate of maximal score
+// with the smallest index: no per-node key list is needed, only the node position of every candidate.
+__device__ __forceinline__ int qt_quadrant(int x, int y, const int4 nd) {
+    const int x0 = nd.x & 0xffff, y0 = nd.x >> 16, x1 = nd.y & 0xffff, y1 = nd.y >> 16;
+    const int hx = (x1 - x0 + 1) >> 1, hy = (y1 - y0 + 1) >> 1;              // ceil(static_cast<float>(d) / 2) (:485-486)
+    return (x < x0 + hx ? 0 : 1) + (y < y0 + hy ? 0 : 2);                    // n1, n2, n3, n4 (:513-527)
+}
+__device__ __forceinline__ int4 qt_child(const int4 nd, int q, int cnt, int seq) {
+    const int x0 = nd.x & 0xffff, y0 = nd.x >> 16, x1 = nd.y & 0xffff, y1 = nd.y >> 16;
+    const int hx = (x1 - x0 + 1) >> 1, hy = (y1 - y0 + 1) >> 1;
+    const int cx0 = (q & 1) ? x0 + hx : x0, cx1 = (q & 1) ? x1 : x0 + hx;
+    const int cy0 = (q & 2) ? y0 + hy : y0, cy1 = (q & 2) ? y1 : y0 + hy;
+    return make_int4(cx0 | (cy0 << 16), cx1 | (cy1 << 16), cnt, seq);
+}
+// exclusive prefix sum over the 1024 threads of the block; *total = sum.  sh: 33 ints.
+__device__ __forceinline__ int block_scan_1024(int v, int* total, int* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();                                   // sh may still be read from a previous scan
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = sh[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        sh[lane] = wi - w;
+        if (lane == 31) sh[32] = wi;
+    }
+    __syncthreads();
+    *total = sh[32];
+    return sh[warp] + incl - v;
+}
+#define QT_KEY(cnt, seq, pos) (((u64)(unsigned)(cnt) << 40) | ((u64)(unsigned)(seq) << 16) | (u64)(unsigned)(pos))
+
+extern __shared__ u64 s_qt_sort[];
+__global__ void __launch_bounds__(1024) k_quadtree(const __grid_constant__ OrbBatch B, const __grid_constant__ LevelTable T,
+                                                   const __grid_constant__ QtTable Q, int sort_cap) {
+    __shared__ int s_scan[34];
+    __shared__ int s_L, s_K, s_R, s_nE, s_seq, s_phase, s_done, s_nP, s_ER, s_kR;
+    const OrbDev& D = B.d[blockIdx.y];
+    const int level = blockIdx.x, tid = threadIdx.x;
+    const int total_raw = *D.total;
+    const int total = min(total_raw, D.cand_cap);
+    if (total_raw > D.cand_cap && tid == 0) D.out[1] = OLF_ERR_CAPACITY;
+    const int ncells = T.cell_start[T.n];
+    const int cs = T.cell_start[level], ce = T.cell_start[level + 1];
+    const int b = cs < ncells ? min(D.cell_off[cs], total) : total, e = ce < ncells ? min(D.cell_off[ce], total) : total;
+    const int m = e - b, N = Q.N[level], C = Q.node_cap[level], O = Q.node_off[level];
+    if (m <= 0) { if (tid == 0) D.lvl_count[level] = 0; return; }
+    int4* A = D.nodes + O;
+    int4* Bn = D.nodes + Q.total_cap + O;
+    int* cc = D.qi + (size_t)12 * O; int* childpos = cc + 4 * C; int* rof = childpos + 4 * C; int* moved = rof + C; int* proc = moved + C; int* Epre = proc + C;
+    u64* expA = D.qk + (size_t)3 * O; u64* expB = expA + C; u64* best = expB + C;
+    int* cnode = D.cnode + b;
+    const int4* cand = D.cand + b;
+    // ---- initial nodes (:545-590)
+    const int Wd = T.w[level] - 32, Hd = T.h[level] - 32;                     // maxX - minX, maxY - minY
+    const int nIni = max((int)roundf(fdiv((float)Wd, (float)Hd)), 1);
+    const float hX = fdiv((float)Wd, (float)nIni);
+    for (int i = tid; i < nIni; i += 1024) cc[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < m; i += 1024) {
+        const int ni = min((int)fdiv((float)(cand[i].y - 16), hX), nIni - 1);
+        cnode[i] = ni;
+        atomicAdd(&cc[ni], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int L = 0;
+        for (int i = 0; i < nIni && i < C; ++i) {
+            if (cc[i] > 0) { moved[i] = L; A[L] = make_int4((int)fmul(hX, (float)i), (int)fmul(hX, (float)(i + 1)) | (Hd << 16), cc[i], i); ++L; }
+            else moved[i] = -1;
+        }
+        s_L = L; s_seq = nIni; s_phase = 1; s_done = 0; s_nE = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += 1024) cnode[i] = moved[cnode[i]];
+    __syncthreads();
+    // ---- division steps
+    for (int iter = 0; iter < 8192; ++iter) {
+        if (s_done) break;
+        const int L = s_L, phase = s_phase, nE = s_nE;
+        int nP;
+        // a. nodes to divide, in processing order
+        if (phase == 1) {
+            const int per = (L + 1023) / 1024, pb = min(tid * per, L), pe = min(pb + per, L);
+            int loc = 0;
+            for (int p = pb; p < pe; ++p) loc += A[p].z >= 2;
+            int run = block_scan_1024(loc, &nP, s_scan);
+            for (int p = pb; p < pe; ++p) if (A[p].z >= 2) proc[run++] = p;
+        } else {
+            nP = nE;
+            int n2 = 1; while (n2 < nE) n2 <<= 1;
+            if (n2 > sort_cap) { if (tid == 0) { D.out[1] = OLF_ERR_CAPACITY; s_done = 1; } __syncthreads(); break; }
+            for (int i = tid; i < n2; i += 1024) s_qt_sort[i] = i < nE ? expA[i] : 0ull;
+            __syncthreads();
+            for (int k = 2; k <= n2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < n2; i += 1024) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const u64 a = s_qt_sort[i], c2 = s_qt_sort[ixj];
+                            const bool up = (i & k) == 0;
+                            if ((a > c2) == up) { s_qt_sort[i] = c2; s_qt_sort[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            for (int r = tid; r < nE; r += 1024) proc[r] = (int)(s_qt_sort[n2 - 1 - r] & 0xffffu);      // descending (size, seq) (:686-687)
+        }
+        if (tid == 0) { s_nP = nP; s_R = nP - 1; }
+        __syncthreads();
+        if (nP == 0) break;                                               // nothing to divide: the list cannot change any more
+        // b. processing rank of every node, child counters
+        for (int p = tid; p < L; p += 1024) rof[p] = 0;
+        for (int j = tid; j < 4 * nP; j += 1024) cc[j] = 0;
+        __syncthreads();
+        for (int r = tid; r < nP; r += 1024) rof[proc[r]] = r + 1;
+        __syncthreads();
+        // c. children sizes (DivideNode :483-537)
+        for (int i = tid; i < m; i += 1024) {
+            const int p = cnode[i], r = rof[p];
+            if (r) atomicAdd(&cc[4 * (r - 1) + qt_quadrant(cand[i].y - 16, cand[i].z - 16, A[p])], 1);
+        }
+        __syncthreads();
+        // d. creation index of every child; phase 2: the step stops after the first division that reaches N nodes (:730-733)
+        {
+            const int per = (nP + 1023) / 1024, rb = min(tid * per, nP), re = min(rb + per, nP);
+            int loc = 0;
+            for (int r = rb; r < re; ++r) loc += (cc[4 * r] > 0) + (cc[4 * r + 1] > 0) + (cc[4 * r + 2] > 0) + (cc[4 * r + 3] > 0);
+            int tot;
+            int run = block_scan_1024(loc, &tot, s_scan);
+            for (int r = rb; r < re; ++r) {
+                const int k = (cc[4 * r] > 0) + (cc[4 * r + 1] > 0) + (cc[4 * r + 2] > 0) + (cc[4 * r + 3] > 0);
+                Epre[r] = run; run += k;
+                if (phase == 2 && L + run - (r + 1) >= N) atomicMin(&s_R, r);
+            }
+        }
+        __syncthreads();
+        const int R = s_R;
+        if (tid == 0) { s_ER = Epre[R]; s_kR = (cc[4 * R] > 0) + (cc[4 * R + 1] > 0) + (cc[4 * R + 2] > 0) + (cc[4 * R + 3] > 0); }
+        __syncthreads();
+        const int K = s_ER + s_kR;
+        // f. the nodes that are not divided keep their order behind the K new ones
+        {
+            const int per = (L + 1023) / 1024, pb = min(tid * per, L), pe = min(pb + per, L);
+            int loc = 0;
+            for (int p = pb; p < pe; ++p) loc += !(rof[p] && rof[p] - 1 <= R);
+            int tot;
+            int run = block_scan_1024(loc, &tot, s_scan);
+            for (int p = pb; p < pe; ++p) if (!(rof[p] && rof[p] - 1 <= R)) { moved[p] = K + run; Bn[K + run] = A[p]; ++run; }
+        }
+        // g. children, newest first; i. those with more than one key are the next step's candidates, in creation order
+        {
+            const int seq0 = s_seq;
+            const int per = (R + 1 + 1023) / 1024, rb = min(tid * per, R + 1), re = min(rb + per, R + 1);
+            int loc = 0;
+            for (int r = rb; r < re; ++r) loc += (cc[4 * r] > 1) + (cc[4 * r + 1] > 1) + (cc[4 * r + 2] > 1) + (cc[4 * r + 3] > 1);
+            int nEn;
+            int run = block_scan_1024(loc, &nEn, s_scan);
+            for (int r = rb; r < re; ++r) {
+                const int4 nd = A[proc[r]];
+                int ecur = Epre[r];
+                for (int q = 0; q < 4; ++q) {
+                    const int cnt = cc[4 * r + q];
+                    if (cnt <= 0) continue;
+                    const int pos = K - 1 - ecur;
+                    Bn[pos] = qt_child(nd, q, cnt, seq0 + ecur);
+                    childpos[4 * r + q] = pos;
+                    if (cnt > 1) expB[run++] = QT_KEY(cnt, seq0 + ecur, pos);
+                    ++ecur;
+                }
+            }
+            __syncthreads();
+            // h. candidates follow their nodes
+            for (int i = tid; i < m; i += 1024) {
+                const int p = cnode[i], r = rof[p];
+                cnode[i] = (r && r - 1 <= R) ? childpos[4 * (r - 1) + qt_quadrant(cand[i].y - 16, cand[i].z - 16, A[p])] : moved[p];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const int Ln = K + (L - (R + 1));
+                s_seq = seq0 + K; s_L = Ln; s_nE = nEn;
+                if (Ln >= N || Ln == L) s_done = 1;                                         // (:671-674, :736-737)
+                else if (phase == 1 && Ln + 3 * nEn > N) s_phase = 2;                       // (:675)
+            }
+        }
+        { int4* t = A; A = Bn; Bn = t; }
+        { u64* t = expA; expA = expB; expB = t; }
+        __syncthreads();
+    }
+    // ---- the best key of every node, in list order (:744-762)
+    const int L = s_L;
+    for (int p = tid; p < L; p += 1024) best[p] = 0ull;
+    __syncthreads();
+    for (int i = tid; i < m; i += 1024) atomicMax(&best[cnode[i]], ((u64)(unsigned)cand[i].w << 32) | (u64)(0xFFFFFFFFu - (unsigned)i));
+    __syncthreads();
+    for (int p = tid; p < L; p += 1024) D.keep[O + p] = b + (int)(0xFFFFFFFFu - (unsigned)(best[p] & 0xFFFFFFFFull));
+    if (tid == 0) D.lvl_count[level] = L;
+}
+
+// ---- orientation + descriptor of the kept keypoints: one warp per keypoint -------------------------------------------
+// IC_Angle (src/ORBextractor.cc:79-106): lanes = rows of the radius-15 disc, integer moments, cv::fastAtan2.
+// computeOrbDescriptor (:110-149): lane i -> descriptor byte i; a = cosf(angle*pi/180), b = sinf(..) evaluated with glibc's
+// own algorithm (sincosf_exact.h), single-rounded float products, cvRound.
 __constant__ int c_umax[16];
-__global__ void __launch_bounds__(256) k_ic_angle(const uint8_t* __restrict__ pyr, const __grid_constant__ LevelTable T,
-                                                  const int4* __restrict__ cand, const int* __restrict__ total, int cap,
-                                                  float* __restrict__ angle_host) {
+__constant__ signed char c_pattern[1024];
+__global__ void __launch_bounds__(256) k_orb_describe(const __grid_constant__ OrbBatch B, const __grid_constant__ LevelTable T, const __grid_constant__ QtTable Q) {
+    const OrbDev& D = B.d[blockIdx.y];
     const int lane = threadIdx.x & 31;
-    const int n = min(*total, cap);
+    int start[OLF_MAX_LEVELS + 1];
+    start[0] = 0;
+    for (int l = 0; l < T.n; ++l) start[l + 1] = start[l] + D.lvl_count[l];
+    const int n_all = start[T.n], n = min(n_all, D.out_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { D.out[0] = n_all; if (n_all > D.out_cap) D.out[1] = OLF_ERR_CAPACITY; }
     for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < n; k += gridDim.x * 8) {
-        const int4 c = cand[k];
-        const uint8_t* center = pyr + T.off[c.x] + (size_t)c.z * T.pitch[c.x] + c.y;
+        int level = 0;
+        while (k >= start[level + 1]) ++level;
+        const int4 c = D.cand[D.keep[Q.node_off[level] + (k - start[level])]];
+        const int pitch = T.pitch[level];
+        const size_t center_off = T.off[level] + (size_t)c.z * pitch + c.y;
         int m10 = 0, m01 = 0;
         if (lane < 31) {
+            const uint8_t* center = D.pyr + center_off;
             const int v = lane - 15;
             const int d = c_umax[v < 0 ? -v : v];
-            const uint8_t* row = center + v * T.pitch[c.x];
+            const uint8_t* row = center + v * pitch;
             int rs = 0;
             for (int u = -d; u <= d; ++u) { const int p = row[u]; m10 += u * p; rs += p; }
             m01 = v * rs;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
-        if (lane == 0) angle_host[k] = fast_atan2_deg((float)m01, (float)m10);
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        if (lane == 0) {
+            olf_keypoint kp;
+            kp.x = (float)c.y; kp.y = (float)c.z;
+            if (level != 0) { kp.x = fmul(kp.x, Q.scale[level]); kp.y = fmul(kp.y, Q.scale[level]); }      // (:1097-1103)
+            kp.size = (float)(int)fmul(31.f, Q.scale[level]);                                               // PATCH_SIZE*mvScaleFactor[level] (:839)
+            kp.angle = angle; kp.response = (float)c.w; kp.octave = level;
+            D.kps[k] = kp;
+        }
+        const float ang = fmul(angle, 0x1.1df46ap-6f);                     // (float)(CV_PI/180.f)
+        const float a = trig::cosf_exact(ang), bsn = trig::sinf_exact(ang);
+        const uint8_t* center = D.blur + center_off;
+        int val = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const signed char* p = c_pattern + (lane * 8 + t) * 4;
+            const float x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
+            const int r0 = __float2int_rn(fadd(fmul(x0, bsn), fmul(y0, a))), c0 = __float2int_rn(fsub(fmul(x0, a), fmul(y0, bsn)));
+            const int r1 = __float2int_rn(fadd(fmul(x1, bsn), fmul(y1, a))), c1 = __float2int_rn(fsub(fmul(x1, a), fmul(y1, bsn)));
+            const int t0 = center[r0 * pitch + c0], t1 = center[r1 * pitch + c1];
+            val |= (t0 < t1) << t;
+        }
+        D.desc[(size_t)k * 32 + lane] = (uint8_t)val;
     }
 }
-
-// ---- rBRIEF (src/ORBextractor.cc:110-149): one warp per keypoint, lane i -> descriptor byte i -------------
-struct KeptKp { int level, x, y; float a, b; };      // a = cosf(angle), b = sinf(angle) (host glibc)
-__constant__ signed char c_pattern[1024];
-__global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur, const __grid_constant__ LevelTable T,
-                                                const KeptKp* __restrict__ kps, int n, uint8_t* __restrict__ desc) {
-    const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (k >= n) return;
-    const KeptKp kp = kps[k];
-    const int pitch = T.pitch[kp.level];
-    const uint8_t* center = blur + T.off[kp.level] + (size_t)kp.y * pitch + kp.x;
-    int val = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const signed char* p = c_pattern + (lane * 8 + t) * 4;
-        const float x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
-        const int r0 = __float2int_rn(fadd(fmul(x0, kp.b), fmul(y0, kp.a))), c0 = __float2int_rn(fsub(fmul(x0, kp.a), fmul(y0, kp.b)));
-        const int r1 = __float2int_rn(fadd(fmul(x1, kp.b), fmul(y1, kp.a))), c1 = __float2int_rn(fsub(fmul(x1, kp.a), fmul(y1, kp.b)));
-        const int t0 = center[r0 * pitch + c0], t1 = center[r1 * pitch + c1];
-        val |= (t0 < t1) << t;
-    }
-    desc[(size_t)k * 32 + lane] = (uint8_t)val;
+// device trig sweep for the parity test: out[i] = {cosf_exact(x_i), sinf_exact(x_i)} for the floats with bit patterns first + i*stride
+__global__ void k_trig_sweep(unsigned first, unsigned stride, unsigned count, float2* __restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float x = __uint_as_float(first + i * stride);
+    out[i] = make_float2(trig::cosf_exact(x), trig::sinf_exact(x));
 }
 
 // ======================================================================================================
@@ -275,28 +524,29 @@ struct OrbImpl {
     int umax[16];
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
+    SyncEvent done;
     // size-dependent state
     int img_w = 0, img_h = 0;
     LevelTable T;
+    QtTable Q;
     size_t pyr_bytes = 0;
-    int ncells = 0, ntiles = 0;
+    int ncells = 0, ntiles = 0, sort_cap = 0;
     DevBuf<uint8_t> pyr, score, blur;
     DevBuf<LinCoef> coef;                    // per level: cx then cy
     std::vector<size_t> coef_off_x, coef_off_y;
-    DevBuf<int> cell_counts, cell_thr, cell_off, total;
+    DevBuf<int> cell_counts, cell_thr, cell_off, total, cnode, qi, lvl_count, keep, out;
     DevBuf<unsigned> ticket;
-    DevBuf<int4> cand;
-    PinBuf<int4> cand_host;
-    PinBuf<float> angle_host;
-    PinBuf<int> total_host;
-    int cand_cap = 0;
-    DevBuf<KeptKp> kept;
-    PinBuf<KeptKp> kept_host;
+    DevBuf<int4> cand, nodes;
+    DevBuf<u64> qk;
+    int cand_cap = 0, out_cap = 0;
+    DevBuf<olf_keypoint> kps;
     DevBuf<uint8_t> desc;
+    PinBuf<olf_keypoint> kps_host;
     PinBuf<uint8_t> desc_host;
-    PinBuf<uint8_t> img_stage;               // pinned staging for host images
-    int kept_cap = 0;
-    int last_ncand = 0;
+    PinBuf<int> out_host;
+    PinBuf<uint8_t> img_stage;               // pinned staging for pageable host images
+    int copy_cap = 0;                        // entries copied back by the last enqueue
+    int last_ncand = -1;
 };
 
 static void build_lin_coefs(int src, int dst, std::vector<LinCoef>& out) {
@@ -357,119 +607,31 @@ static int orb_ensure_size(OrbImpl* h, int w, int hgt) {
     if (!all.empty()) OLF_CUDA(cudaMemcpy(h->coef.p, all.data(), all.size() * sizeof(LinCoef), cudaMemcpyHostToDevice));
     const int nc = std::max(cells, 1);
     if ((rc = h->cell_counts.ensure(nc)) || (rc = h->cell_thr.ensure(nc)) || (rc = h->cell_off.ensure(nc)) ||
-        (rc = h->total.ensure(1)) || (rc = h->ticket.ensure(1)) || (rc = h->total_host.ensure(1))) return rc;
+        (rc = h->total.ensure(1)) || (rc = h->ticket.ensure(1)) || (rc = h->out.ensure(4)) || (rc = h->out_host.ensure(4)) || (rc = h->lvl_count.ensure(OLF_MAX_LEVELS))) return rc;
     OLF_CUDA(cudaMemset(h->ticket.p, 0, sizeof(unsigned)));
     // at most one NMS survivor per 2x2 block of the evaluated area
     h->cand_cap = (int)std::min<size_t>(off / 4 + 1024, (size_t)1 << 22);
-    if ((rc = h->cand.ensure(h->cand_cap)) || (rc = h->cand_host.ensure(h->cand_cap)) || (rc = h->angle_host.ensure(h->cand_cap))) return rc;
+    if ((rc = h->cand.ensure(h->cand_cap)) || (rc = h->cnode.ensure(h->cand_cap))) return rc;
+    // quadtree node slots: a phase-1 pass can leave up to 4 x (N - 1) nodes
+    QtTable& Q = h->Q;
+    memset(&Q, 0, sizeof(Q));
+    int qoff = 0, maxcap = 0;
+    for (int l = 0; l < h->nlevels; ++l) {
+        Q.N[l] = h->feats_per_level[l]; Q.node_cap[l] = 4 * h->feats_per_level[l] + 64; Q.node_off[l] = qoff; Q.scale[l] = h->scale[l];
+        qoff += Q.node_cap[l]; maxcap = std::max(maxcap, Q.node_cap[l]);
+    }
+    Q.total_cap = qoff;
+    if (maxcap >= 65536) { set_last_error("olf_orb: too many features per level for the device quadtree (< 16368 per level)"); return OLF_ERR_ARG; }
+    h->sort_cap = 1; while (h->sort_cap < maxcap) h->sort_cap <<= 1;
+    if (h->sort_cap * sizeof(u64) > 48 * 1024)
+        OLF_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sort_cap * sizeof(u64))));
+    h->out_cap = qoff;
+    if ((rc = h->nodes.ensure((size_t)2 * qoff)) || (rc = h->qi.ensure((size_t)12 * qoff)) || (rc = h->qk.ensure((size_t)3 * qoff)) || (rc = h->keep.ensure(qoff)) ||
+        (rc = h->kps.ensure(qoff)) || (rc = h->desc.ensure((size_t)qoff * 32)) || (rc = h->kps_host.ensure(qoff)) || (rc = h->desc_host.ensure((size_t)qoff * 32))) return rc;
     if ((rc = h->img_stage.ensure((size_t)w * hgt))) return rc;
     h->img_w = w; h->img_h = hgt;
     return OLF_OK;
 }
-
-// ---- quadtree distribution on the host (src/ORBextractor.cc:483-765), index based ----------------------------
-namespace {
-struct QNode {
-    int ULx, ULy, URx, URy, BLx, BLy, BRx, BRy;
-    std::vector<int> keys;
-    bool no_more = false;
-    long seq = 0;
-    std::list<QNode>::iterator lit;
-};
-struct QCand { float x, y; int score; };
-void q_divide(const QNode& n, const QCand* c, QNode& n1, QNode& n2, QNode& n3, QNode& n4) {
-    const int halfX = (int)ceilf((float)(n.URx - n.ULx) / 2), halfY = (int)ceilf((float)(n.BRy - n.ULy) / 2);
-    n1.ULx = n.ULx; n1.ULy = n.ULy; n1.URx = n.ULx + halfX; n1.URy = n.ULy; n1.BLx = n.ULx; n1.BLy = n.ULy + halfY; n1.BRx = n.ULx + halfX; n1.BRy = n.ULy + halfY;
-    n2.ULx = n1.URx; n2.ULy = n1.URy; n2.URx = n.URx; n2.URy = n.URy; n2.BLx = n1.BRx; n2.BLy = n1.BRy; n2.BRx = n.URx; n2.BRy = n.ULy + halfY;
-    n3.ULx = n1.BLx; n3.ULy = n1.BLy; n3.URx = n1.BRx; n3.URy = n1.BRy; n3.BLx = n.BLx; n3.BLy = n.BLy; n3.BRx = n1.BRx; n3.BRy = n.BLy;
-    n4.ULx = n3.URx; n4.ULy = n3.URy; n4.URx = n2.BRx; n4.URy = n2.BRy; n4.BLx = n3.BRx; n4.BLy = n3.BRy; n4.BRx = n.BRx; n4.BRy = n.BRy;
-    const size_t m = n.keys.size();
-    n1.keys.reserve(m); n2.keys.reserve(m / 2 + 1); n3.keys.reserve(m / 2 + 1); n4.keys.reserve(m / 2 + 1);
-    for (int idx : n.keys) {
-        const QCand& kp = c[idx];
-        if (kp.x < n1.URx) { if (kp.y < n1.BRy) n1.keys.push_back(idx); else n3.keys.push_back(idx); }
-        else if (kp.y < n1.BRy) n2.keys.push_back(idx);
-        else n4.keys.push_back(idx);
-    }
-    if (n1.keys.size() == 1) n1.no_more = true;
-    if (n2.keys.size() == 1) n2.no_more = true;
-    if (n3.keys.size() == 1) n3.no_more = true;
-    if (n4.keys.size() == 1) n4.no_more = true;
-}
-void quadtree(const QCand* c, int nc, int minX, int maxX, int minY, int maxY, int N, std::vector<int>& result) {
-    result.clear();
-    const int nIni = std::max((int)roundf((float)(maxX - minX) / (maxY - minY)), 1);
-    const float hX = (float)(maxX - minX) / nIni;
-    std::list<QNode> nodes;
-    std::vector<QNode*> ini(nIni);
-    long seq = 0;
-    for (int i = 0; i < nIni; i++) {
-        QNode ni;
-        ni.ULx = (int)(hX * (float)i); ni.ULy = 0; ni.URx = (int)(hX * (float)(i + 1)); ni.URy = 0;
-        ni.BLx = ni.ULx; ni.BLy = maxY - minY; ni.BRx = ni.URx; ni.BRy = maxY - minY;
-        ni.seq = seq++;
-        nodes.push_back(std::move(ni));
-        ini[i] = &nodes.back();
-    }
-    for (int i = 0; i < nc; i++) ini[std::min((int)(c[i].x / hX), nIni - 1)]->keys.push_back(i);
-    for (auto lit = nodes.begin(); lit != nodes.end();) {
-        if (lit->keys.size() == 1) { lit->no_more = true; ++lit; }
-        else if (lit->keys.empty()) lit = nodes.erase(lit);
-        else ++lit;
-    }
-    std::vector<std::pair<int, QNode*>> expand;
-    auto push_child = [&](QNode& n, int* n_to_expand) {
-        if (n.keys.empty()) return;
-        n.seq = seq++;
-        const bool many = n.keys.size() > 1;
-        const int sz = (int)n.keys.size();
-        nodes.push_front(std::move(n));
-        if (many) {
-            if (n_to_expand) ++*n_to_expand;
-            expand.emplace_back(sz, &nodes.front());
-            nodes.front().lit = nodes.begin();
-        }
-    };
-    bool finish = false;
-    while (!finish) {
-        int prev = (int)nodes.size(), n_to_expand = 0;
-        expand.clear();
-        for (auto lit = nodes.begin(); lit != nodes.end();) {
-            if (lit->no_more) { ++lit; continue; }
-            QNode n1, n2, n3, n4;
-            q_divide(*lit, c, n1, n2, n3, n4);
-            push_child(n1, &n_to_expand); push_child(n2, &n_to_expand); push_child(n3, &n_to_expand); push_child(n4, &n_to_expand);
-            lit = nodes.erase(lit);
-        }
-        if ((int)nodes.size() >= N || (int)nodes.size() == prev) finish = true;
-        else if ((int)nodes.size() + n_to_expand * 3 > N) {
-            while (!finish) {
-                prev = (int)nodes.size();
-                std::vector<std::pair<int, QNode*>> order = expand;
-                expand.clear();
-                // canonical tie-break: (size, creation sequence), SURVEY Appendix C.1
-                std::sort(order.begin(), order.end(), [](const std::pair<int, QNode*>& a, const std::pair<int, QNode*>& b) {
-                    return a.first != b.first ? a.first < b.first : a.second->seq < b.second->seq; });
-                for (int j = (int)order.size() - 1; j >= 0; j--) {
-                    QNode n1, n2, n3, n4;
-                    q_divide(*order[j].second, c, n1, n2, n3, n4);
-                    push_child(n1, nullptr); push_child(n2, nullptr); push_child(n3, nullptr); push_child(n4, nullptr);
-                    nodes.erase(order[j].second->lit);
-                    if ((int)nodes.size() >= N) break;
-                }
-                if ((int)nodes.size() >= N || (int)nodes.size() == prev) finish = true;
-            }
-        }
-    }
-    for (const QNode& n : nodes) {
-        int best = n.keys[0];
-        int max_resp = c[best].score;
-        for (size_t k = 1; k < n.keys.size(); k++)
-            if (c[n.keys[k]].score > max_resp) { best = n.keys[k]; max_resp = c[best].score; }
-        result.push_back(best);
-    }
-}
-}  // namespace
 
 OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device, cudaStream_t ext_stream) {
     if (nlevels < 1 || nlevels > OLF_MAX_LEVELS || nfeatures < 0 || scale_factor <= 1.0f || min_th < 1 || ini_th < min_th) {
@@ -500,6 +662,7 @@ OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
     for (v = HP, v0 = 0; v >= vmin; --v) { while (h->umax[v0] == h->umax[v0 + 1]) ++v0; h->umax[v] = v0; ++v0; }
     if (ext_stream) { h->stream = ext_stream; h->owns_stream = false; }
     if ((!ext_stream && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) ||
+        h->done.create(false) != cudaSuccess ||
         cudaMemcpyToSymbol(c_umax, h->umax, sizeof(h->umax)) != cudaSuccess ||
         cudaMemcpyToSymbol(c_pattern, OLF_BRIEF_PATTERN, 1024) != cudaSuccess) {
         set_last_error(std::string("olf_orb_create: ") + cudaGetErrorString(cudaGetLastError()));
@@ -513,115 +676,106 @@ void orb_destroy(OrbImpl* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream && h->owns_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->done.destroy();
     h->pyr.release(); h->score.release(); h->blur.release(); h->coef.release(); h->cell_counts.release(); h->cell_thr.release();
-    h->cell_off.release(); h->total.release(); h->ticket.release(); h->cand.release(); h->cand_host.release(); h->angle_host.release();
-    h->total_host.release(); h->kept.release(); h->kept_host.release(); h->desc.release(); h->desc_host.release(); h->img_stage.release();
+    h->cell_off.release(); h->total.release(); h->ticket.release(); h->cand.release(); h->cnode.release(); h->nodes.release(); h->qi.release();
+    h->qk.release(); h->lvl_count.release(); h->keep.release(); h->out.release(); h->kps.release(); h->desc.release();
+    h->kps_host.release(); h->desc_host.release(); h->out_host.release(); h->img_stage.release();
     delete h;
 }
 
-// phase 1: upload + pyramid + FAST + cells + orientation + blur, all enqueued on the handle's stream
-static int orb_enqueue_phase1(OrbImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device) {
-    int rc = orb_ensure_size(h, w, hgt);
-    if (rc) return rc;
-    const LevelTable& T = h->T;
-    cudaStream_t s = h->stream;
-    if (on_device) {
-        OLF_CUDA(cudaMemcpy2DAsync(h->pyr.p, T.pitch[0], img, stride, w, hgt, cudaMemcpyDeviceToDevice, s));
-    } else {
-        for (int y = 0; y < hgt; ++y) memcpy(h->img_stage.p + (size_t)y * w, img + (size_t)y * stride, w);
-        OLF_CUDA(cudaMemcpy2DAsync(h->pyr.p, T.pitch[0], h->img_stage.p, w, w, hgt, cudaMemcpyHostToDevice, s));
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// The whole extractor for n images (one handle each, same parameters and image size), asynchronously on stream s:
+// upload -> pyramid -> FAST score -> cells -> quadtree -> orientation + rBRIEF -> results to pinned staging.
+int orb_enqueue(OrbImpl* const* hs, int n, const uint8_t* const* imgs, int w, int hgt, int stride, bool on_device, int cap, cudaStream_t s) {
+    if (!hs || n < 1 || n > IMG_MAX_BATCH || !imgs || w <= 0 || hgt <= 0 || stride < w || cap < 0) { set_last_error("olf_orb_extract: bad arguments"); return OLF_ERR_ARG; }
+    OrbImpl* h0 = hs[0];
+    OLF_CUDA(cudaSetDevice(h0->device));
+    int rc;
+    OrbBatch B; memset(&B, 0, sizeof(B));
+    BlurBatch BB; memset(&BB, 0, sizeof(BB));
+    B.n = n;
+    for (int k = 0; k < n; ++k) {
+        OrbImpl* h = hs[k];
+        if (!h || !imgs[k] || h->nfeatures != h0->nfeatures || h->nlevels != h0->nlevels || h->scale_factor != h0->scale_factor ||
+            h->ini_th != h0->ini_th || h->min_th != h0->min_th || h->device != h0->device) { set_last_error("olf_orb_extract: the extractors of a batch must be configured alike"); return OLF_ERR_ARG; }
+        if ((rc = orb_ensure_size(h, w, hgt))) return rc;
+        const LevelTable& T = h->T;
+        if (on_device) OLF_CUDA(cudaMemcpy2DAsync(h->pyr.p, T.pitch[0], imgs[k], stride, w, hgt, cudaMemcpyDeviceToDevice, s));
+        else if (is_pinned_host(imgs[k])) OLF_CUDA(cudaMemcpy2DAsync(h->pyr.p, T.pitch[0], imgs[k], stride, w, hgt, cudaMemcpyHostToDevice, s));
+        else {
+            // pageable caller memory: stage through the handle's pinned buffer.  The previous use of the staging buffer must have
+            // been consumed by the device: every entry point waits for its chain before it returns.
+            for (int y = 0; y < hgt; ++y) memcpy(h->img_stage.p + (size_t)y * w, imgs[k] + (size_t)y * stride, w);
+            OLF_CUDA(cudaMemcpy2DAsync(h->pyr.p, T.pitch[0], h->img_stage.p, w, w, hgt, cudaMemcpyHostToDevice, s));
+        }
+        OrbDev& D = B.d[k];
+        D.pyr = h->pyr.p; D.score = h->score.p; D.blur = h->blur.p;
+        D.cell_counts = h->cell_counts.p; D.cell_thr = h->cell_thr.p; D.cell_off = h->cell_off.p; D.total = h->total.p; D.ticket = h->ticket.p;
+        D.cand = h->cand.p; D.cand_cap = h->cand_cap; D.cnode = h->cnode.p; D.nodes = h->nodes.p; D.qi = h->qi.p; D.qk = h->qk.p;
+        D.lvl_count = h->lvl_count.p; D.keep = h->keep.p; D.kps = h->kps.p; D.desc = h->desc.p; D.out = h->out.p; D.out_cap = h->out_cap;
+        BB.src[k] = h->pyr.p; BB.dst[k] = h->blur.p;
+        OLF_CUDA(cudaMemsetAsync(h->out.p, 0, 4 * sizeof(int), s));
+        if (h->ncells == 0) { OLF_CUDA(cudaMemsetAsync(h->total.p, 0, sizeof(int), s)); OLF_CUDA(cudaMemsetAsync(h->lvl_count.p, 0, OLF_MAX_LEVELS * sizeof(int), s)); }
+        h->last_ncand = -1;
     }
-    for (int l = 1; l < h->nlevels; ++l) {
-        dim3 b(32, 8), g((T.w[l] + 31) / 32, (T.h[l] + 7) / 8);
-        k_resize_linear<<<g, b, 0, s>>>(h->pyr.p + T.off[l - 1], T.w[l - 1], T.h[l - 1], T.pitch[l - 1],
-                                        h->pyr.p + T.off[l], T.w[l], T.h[l], T.pitch[l],
-                                        h->coef.p + h->coef_off_x[l], h->coef.p + h->coef_off_y[l]);
+    const LevelTable& T = h0->T;
+    for (int l = 1; l < h0->nlevels; ++l) {
+        dim3 b(32, 8), g((T.w[l] + 31) / 32, (T.h[l] + 7) / 8, n);
+        k_resize_linear<<<g, b, 0, s>>>(B, T.off[l - 1], T.w[l - 1], T.h[l - 1], T.pitch[l - 1], T.off[l], T.w[l], T.h[l], T.pitch[l],
+                                        h0->coef.p + h0->coef_off_x[l], h0->coef.p + h0->coef_off_y[l]);
     }
-    k_fast_score<<<h->ntiles, 256, 0, s>>>(h->pyr.p, h->score.p, T, h->min_th);
-    if (h->ncells > 0) {
-        const int nb = (h->ncells + 3) / 4;
-        k_cell_count<<<nb, 128, 0, s>>>(h->score.p, T, h->ini_th, h->cell_counts.p, h->cell_thr.p, h->cell_off.p, h->total.p, h->ticket.p, h->ncells);
-        k_cell_write<<<nb, 128, 0, s>>>(h->score.p, T, h->cell_thr.p, h->cell_off.p, h->cand.p, h->cand_host.d, h->cand_cap, h->ncells);
-        k_ic_angle<<<296, 256, 0, s>>>(h->pyr.p, T, h->cand.p, h->total.p, h->cand_cap, h->angle_host.d);
-    } else {
-        OLF_CUDA(cudaMemsetAsync(h->total.p, 0, sizeof(int), s));
-    }
-    OLF_CUDA(cudaMemcpyAsync(h->total_host.p, h->total.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    k_fast_score<<<dim3(h0->ntiles, n), 256, 0, s>>>(B, T, h0->min_th);
     // ORB blur: 7x7 sigma 2 -> [18,34,48,56,48,34,18] (:1088)
-    k_blur_q8<7><<<h->ntiles, 256, 0, s>>>(h->pyr.p, h->blur.p, T, 18, 34, 48, 56);
-    count_launches((h->nlevels - 1) + 2 + (h->ncells > 0 ? 3 : 0));
+    k_blur_q8<7><<<dim3(h0->ntiles, n), 256, 0, s>>>(BB, T, 18, 34, 48, 56);
+    int launches = (h0->nlevels - 1) + 2;
+    if (h0->ncells > 0) {
+        const int nb = (h0->ncells + 3) / 4;
+        k_cell_count<<<dim3(nb, n), 128, 0, s>>>(B, T, h0->ini_th, h0->ncells);
+        k_cell_write<<<dim3(nb, n), 128, 0, s>>>(B, T, h0->ncells);
+        k_quadtree<<<dim3(h0->nlevels, n), 1024, h0->sort_cap * sizeof(u64), s>>>(B, T, h0->Q, h0->sort_cap);
+        launches += 3;
+    }
+    k_orb_describe<<<dim3(64, n), 256, 0, s>>>(B, T, h0->Q);
+    count_launches(launches + 1);
+    for (int k = 0; k < n; ++k) {
+        OrbImpl* h = hs[k];
+        h->copy_cap = std::min(cap, h->out_cap);
+        OLF_CUDA(cudaMemcpyAsync(h->out_host.p, h->out.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (h->copy_cap > 0) {
+            OLF_CUDA(cudaMemcpyAsync(h->kps_host.p, h->kps.p, (size_t)h->copy_cap * sizeof(olf_keypoint), cudaMemcpyDeviceToHost, s));
+            OLF_CUDA(cudaMemcpyAsync(h->desc_host.p, h->desc.p, (size_t)h->copy_cap * 32, cudaMemcpyDeviceToHost, s));
+        }
+    }
     OLF_CUDA(cudaGetLastError());
     return OLF_OK;
 }
+// after the stream of orb_enqueue has been waited for: results of one image from its pinned staging
+int orb_collect(OrbImpl* h, olf_keypoint* kps, uint8_t* desc, int cap, int* n) {
+    if (!h || !n) return OLF_ERR_ARG;
+    *n = 0;
+    if (h->out_host.p[1] != 0) { set_last_error("olf_orb_extract: internal candidate / keypoint buffer overflow"); return OLF_ERR_CAPACITY; }
+    const int total = h->out_host.p[0];
+    if (total > cap || total > h->copy_cap) { set_last_error("olf_orb_extract: keypoint capacity too small"); return OLF_ERR_CAPACITY; }
+    *n = total;
+    if (total) { memcpy(kps, h->kps_host.p, (size_t)total * sizeof(olf_keypoint)); memcpy(desc, h->desc_host.p, (size_t)total * 32); }
+    return OLF_OK;
+}
 
-int orb_extract(OrbImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device,
-                olf_keypoint* kps, uint8_t* desc, int cap, int* n, const std::function<void()>* on_phase1_enqueued) {
+int orb_extract(OrbImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, olf_keypoint* kps, uint8_t* desc, int cap, int* n) {
     if (!h || !n) return OLF_ERR_ARG;
     *n = 0;
     if (!img || w <= 0 || hgt <= 0) return OLF_OK;           // _image.empty(): silent return (:1048)
     if (stride < w || !kps || !desc) { set_last_error("olf_orb_extract: bad arguments"); return OLF_ERR_ARG; }
-    OLF_CUDA(cudaSetDevice(h->device));
-    int rc = orb_enqueue_phase1(h, img, w, hgt, stride, on_device);
-    if (rc) { if (on_phase1_enqueued) (*on_phase1_enqueued)(); return rc; }
-    {   // wait for phase 1 only: whatever another thread enqueues on a shared stream after this mark is not waited for
-        cudaEvent_t ev;
-        const cudaError_t e = stream_record(h->stream, &ev);
-        if (on_phase1_enqueued) (*on_phase1_enqueued)();
-        OLF_CUDA(e);
-        OLF_CUDA(event_wait(ev));
-    }
-    const int ncand = *h->total_host.p;
-    if (ncand > h->cand_cap) { set_last_error("FAST candidate buffer overflow"); return OLF_ERR_CAPACITY; }
-    h->last_ncand = ncand;
-    const LevelTable& T = h->T;
-    // host: quadtree per level (cand is grouped by level because cells are enumerated level by level)
-    const int4* cand = h->cand_host.p;
-    const float* ang = h->angle_host.p;
-    std::vector<QCand> qc;
-    std::vector<int> keep;
-    std::vector<KeptKp> kept;
-    const float factorPI = (float)(M_PI / 180.f);
-    int total = 0, pos = 0;
-    for (int level = 0; level < h->nlevels; ++level) {
-        const int b = pos;
-        while (pos < ncand && cand[pos].x == level) ++pos;
-        const int m = pos - b;
-        if (m == 0) continue;
-        qc.resize(m);
-        for (int i = 0; i < m; ++i) qc[i] = {(float)(cand[b + i].y - 16), (float)(cand[b + i].z - 16), cand[b + i].w};
-        quadtree(qc.data(), m, 16, T.w[level] - 16, 16, T.h[level] - 16, h->feats_per_level[level], keep);
-        if (total + (int)keep.size() > cap) { set_last_error("olf_orb_extract: keypoint capacity too small"); return OLF_ERR_CAPACITY; }
-        const int scaledPatchSize = (int)(31 * h->scale[level]);
-        for (int idx : keep) {
-            const int4 c = cand[b + idx];
-            olf_keypoint& kp = kps[total++];
-            kp.angle = ang[b + idx];
-            kp.response = (float)c.w;
-            kp.octave = level;
-            kp.size = (float)scaledPatchSize;
-            kp.x = (float)c.y; kp.y = (float)c.z;
-            if (level != 0) { kp.x *= h->scale[level]; kp.y *= h->scale[level]; }
-            const float a = kp.angle * factorPI;
-            kept.push_back({level, c.y, c.z, cosf(a), sinf(a)});
-        }
-    }
-    *n = total;
-    if (total == 0) return OLF_OK;
-    // phase 2: rBRIEF on the blurred pyramid
-    if (total > h->kept_cap) {
-        const int ncap = std::max(total * 2, 4096);
-        if ((rc = h->kept.ensure(ncap)) || (rc = h->kept_host.ensure(ncap)) || (rc = h->desc.ensure((size_t)ncap * 32)) || (rc = h->desc_host.ensure((size_t)ncap * 32))) return rc;
-        h->kept_cap = ncap;
-    }
-    memcpy(h->kept_host.p, kept.data(), kept.size() * sizeof(KeptKp));
-    OLF_CUDA(cudaMemcpyAsync(h->kept.p, h->kept_host.p, kept.size() * sizeof(KeptKp), cudaMemcpyHostToDevice, h->stream));
-    k_rbrief<<<(total + 7) / 8, 256, 0, h->stream>>>(h->blur.p, T, h->kept.p, total, h->desc.p);
-    count_launches(1);
-    OLF_CUDA(cudaMemcpyAsync(h->desc_host.p, h->desc.p, (size_t)total * 32, cudaMemcpyDeviceToHost, h->stream));
-    OLF_CUDA(stream_sync(h->stream));
-    OLF_CUDA(cudaGetLastError());
-    memcpy(desc, h->desc_host.p, (size_t)total * 32);
-    return OLF_OK;
+    int rc = orb_enqueue(&h, 1, &img, w, hgt, stride, on_device, cap, h->stream);
+    if (rc) return rc;
+    OLF_CUDA(h->done.sync(h->stream));
+    return orb_collect(h, kps, desc, cap, n);
 }
 
 int orb_level_size(const OrbImpl* h, int level, int* w, int* hh) {
@@ -635,11 +789,15 @@ int orb_get_level(OrbImpl* h, int level, uint8_t* dst, int dst_stride) {
     OLF_CUDA(cudaMemcpy2D(dst, dst_stride, h->pyr.p + h->T.off[level], h->T.pitch[level], h->T.w[level], h->T.h[level], cudaMemcpyDeviceToHost));
     return OLF_OK;
 }
+// debug / parity: the FAST candidates of the last extract stay on the device; they are fetched on demand
 int orb_last_candidates(OrbImpl* h, int* out, int cap, int* n) {
-    if (!h || !n) return OLF_ERR_ARG;
-    *n = h->last_ncand;
-    if (h->last_ncand > cap) return OLF_ERR_CAPACITY;
-    memcpy(out, h->cand_host.p, (size_t)h->last_ncand * sizeof(int4));
+    if (!h || !n || h->img_w == 0) return OLF_ERR_ARG;
+    OLF_CUDA(cudaSetDevice(h->device));
+    int total = 0;
+    OLF_CUDA(cudaMemcpy(&total, h->total.p, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = total;
+    if (total > cap || total > h->cand_cap) return OLF_ERR_CAPACITY;
+    if (total) OLF_CUDA(cudaMemcpy(out, h->cand.p, (size_t)total * sizeof(int4), cudaMemcpyDeviceToHost));
     return OLF_OK;
 }
 const OrbDeviceView orb_device_view(const OrbImpl* h) {
@@ -647,11 +805,22 @@ const OrbDeviceView orb_device_view(const OrbImpl* h) {
     v.pyr = h->pyr.p; v.nlevels = h->nlevels;
     for (int l = 0; l < h->nlevels; ++l) { v.w[l] = h->T.w[l]; v.h[l] = h->T.h[l]; v.pitch[l] = h->T.pitch[l]; v.off[l] = h->T.off[l]; v.scale[l] = h->scale[l]; v.inv_scale[l] = h->inv_scale[l]; }
     v.device = h->device;
+    v.kps = h->kps.p; v.desc = h->desc.p; v.n = h->out.p; v.cap = h->out_cap;
     return v;
 }
 void orb_scale_tables(const OrbImpl* h, const float** s, const float** is, const float** s2, const float** is2, const int** fpl, int* nlevels) {
     if (s) *s = h->scale.data(); if (is) *is = h->inv_scale.data(); if (s2) *s2 = h->sigma2.data(); if (is2) *is2 = h->inv_sigma2.data();
     if (fpl) *fpl = h->feats_per_level.data(); if (nlevels) *nlevels = h->nlevels;
+}
+int orb_trig_sweep(unsigned first, unsigned stride, unsigned count, float* cos_sin_out, int device) {
+    OLF_CUDA(cudaSetDevice(device));
+    float2* d = nullptr;
+    OLF_CUDA(cudaMalloc((void**)&d, (size_t)count * sizeof(float2)));
+    k_trig_sweep<<<(count + 255) / 256, 256>>>(first, stride, count, d);
+    cudaError_t e = cudaMemcpy(cos_sin_out, d, (size_t)count * sizeof(float2), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    OLF_CUDA(e);
+    return OLF_OK;
 }
 
 }  // namespace olf

@@ -49,3 +49,22 @@ def test_orb_flat_image_and_reuse():
     k, d = g.orb_extract(h, random_image(400, 300, 9))
     assert len(k) > 0
     g.orb_destroy(h)
+
+
+def test_device_trig_equals_host_libm():
+    """rBRIEF's a = cosf(angle*pi/180), b = sinf(..) run on the device with glibc's algorithm (csrc/sincosf_exact.h); a strided
+    sweep over every float in [0, 2 pi] (the exhaustive proof of the same source is the CPU test test_trig_exact.py)."""
+    import ctypes as C
+    lib = olf.load_library()
+    hi = np.array([6.2832], np.float32).view(np.uint32)[0]
+    for first, stride in ((0, 61), (17, 127)):
+        count = int((hi - first) // stride)
+        out = np.zeros((count, 2), np.float32)
+        rc = lib.olf_trig_sweep(C.c_uint(first), C.c_uint(stride), C.c_uint(count), out.ctypes.data_as(C.c_void_p), C.c_int(0))
+        assert rc == 0
+        x = np.ascontiguousarray((first + np.arange(count, dtype=np.uint64) * stride).astype(np.uint32).view(np.float32))
+        c = np.zeros(count, np.float32); s = np.zeros(count, np.float32)
+        o = oracle().lib
+        o.orc_cosf_sinf(x.ctypes.data_as(C.c_void_p), C.c_long(count), c.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(out[:, 0], c), "device cosf != libm cosf"
+        assert np.array_equal(out[:, 1], s), "device sinf != libm sinf"
