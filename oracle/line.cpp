@@ -211,7 +211,9 @@ static void make_keylines(const std::vector<float>& segs, int w, int h, double m
         // cv::LineIterator(img, Point2f, Point2f).count, 8-connected; endpoints already inside the image
         int x1 = cv_round(e[0]), y1 = cv_round(e[1]), x2 = cv_round(e[2]), y2 = cv_round(e[3]);
         kl.numOfPixels = std::max(std::abs(x2 - x1), std::abs(y2 - y1)) + 1;
-        kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+        // atan2( float, float ) (LSDDetector_custom.cpp:298): precomp_custom.hpp -> bitarray_custom.hpp -> <math.h>, whose C++ wrapper puts
+        // the float overloads into the global namespace, so the reference calls atan2f (pinned by oracle/_ref, tests/test_oracle_vs_ref.py)
+        kl.angle = atan2f(kl.endPointY - kl.startPointY, kl.endPointX - kl.startPointX);
         kl.class_id = ++class_counter;
         kl.octave = 0;
         kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);
@@ -255,8 +257,9 @@ static void lbd_one(const olf_keyline& kl, const int16_t* pdx, const int16_t* pd
     const short halfWidth = (lengthOfLSP - 1) / 2;
     const float lineMiddlePointX = (float)(0.5 * (kl.sPointInOctaveX + kl.ePointInOctaveX));
     const float lineMiddlePointY = (float)(0.5 * (kl.sPointInOctaveY + kl.ePointInOctaveY));
-    dL[0] = (float)std::cos((double)kl.angle);
-    dL[1] = (float)std::sin((double)kl.angle);
+    // cos( float ) / sin( float ) (binary_descriptor_custom.cpp:1130-1131) resolve to cosf / sinf for the same reason as atan2f above
+    dL[0] = cosf(kl.angle);
+    dL[1] = sinf(kl.angle);
     dO[0] = -dL[1];
     dO[1] = dL[0];
     float sCorX0 = -dL[0] * halfWidth + dL[1] * halfHeight + lineMiddlePointX;

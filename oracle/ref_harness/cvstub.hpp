@@ -13,6 +13,7 @@
 #pragma once
 #include <algorithm>
 #include <cassert>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -171,9 +172,24 @@ public:
     }
     void create(Size s, int type) { create(s.height, s.width, type); }
     void release() { buf_.reset(); data = nullptr; rows = cols = 0; step = MatStep(0); }
-    static Mat zeros(int r, int c, int type) { Mat m(r, c, type); if (m.buf_) std::fill(m.buf_->begin(), m.buf_->end(), 0); return m; }
-    static Mat zeros(Size s, int type) { return zeros(s.height, s.width, type); }
-    static Mat eye(int r, int c, int type) { Mat m = zeros(r, c, type); for (int i = 0; i < std::min(r, c); ++i) { if (type == CV_32F) m.at<float>(i, i) = 1.f; else if (type == CV_64F) m.at<double>(i, i) = 1.0; else m.ptr(i)[i] = 1; } return m; }
+    // Mat::zeros is a MatExpr in OpenCV: assigned to a Mat of the same size and type it is evaluated IN PLACE (create() keeps the
+    // buffer), which src/ORBextractor.cc:1039 relies on (`descriptors = Mat::zeros(...)` on a row range of the output matrix)
+    struct Zeros { int r, c, type; operator Mat() const { Mat m(r, c, type); m.fill0(); return m; } };
+    static Zeros zeros(int r, int c, int type) { return Zeros{r, c, type}; }
+    static Zeros zeros(Size s, int type) { return Zeros{s.height, s.width, type}; }
+    Mat& operator=(const Zeros& z) { create(z.r, z.c, z.type); fill0(); return *this; }
+    Mat(const Zeros& z) { create(z.r, z.c, z.type); fill0(); }
+    void fill0() { for (int r = 0; r < rows; ++r) memset(ptr(r), 0, (size_t)cols * elemSize()); }
+    static Mat ones(int r, int c, int type) { Mat m(r, c, type); m.setTo(Scalar(1)); return m; }
+    void convertTo(Mat& o, int rtype) const {             // 8U -> 32F / same type (the SAD windows of Frame::ComputeStereoMatches)
+        Mat d(rows, cols, rtype);
+        for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) {
+            double v = depth() == CV_8U ? (double)ptr(r)[c] : depth() == CV_32F ? (double)at<float>(r, c) : at<double>(r, c);
+            if (rtype == CV_32F) d.at<float>(r, c) = (float)v; else if (rtype == CV_64F) d.at<double>(r, c) = v; else d.ptr(r)[c] = (uchar)v;
+        }
+        o = d;
+    }
+    static Mat eye(int r, int c, int type) { Mat m(r, c, type); m.fill0(); for (int i = 0; i < std::min(r, c); ++i) { if (type == CV_32F) m.at<float>(i, i) = 1.f; else if (type == CV_64F) m.at<double>(i, i) = 1.0; else m.ptr(i)[i] = 1; } return m; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     int type() const { return flags; }
     int depth() const { return flags & 7; }

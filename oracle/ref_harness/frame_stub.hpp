@@ -1,0 +1,69 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+// Stand-ins for the reference classes whose real headers need Eigen / g2o / DBoW2 / Pangolin (include/Frame.h,
+// MapPoint.h, MapLine.h, KeyFrame.h): exactly the members that the hot-path functions sliced out of src/Frame.cc and
+// src/ORBmatcher.cc read or write, with the reference's names and types (include/Frame.h:83-259, include/MapPoint.h).
+// The Makefile pre-defines the include guards of the real headers so that the reference's own ORBmatcher.h /
+// LineMatcher.h (which include them) see these instead.
+#pragma once
+#include "cvstub.hpp"
+#include "eigen_stub.hpp"
+#include <line_descriptor/descriptor_custom.hpp>
+#include "ORBextractor.h"
+#include <mutex>
+#include <utility>
+using namespace std;
+using namespace Eigen;
+
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+
+namespace ORB_SLAM2 {
+class Map; class KeyFrameDatabase; class Frame;
+class KeyFrame { public: std::vector<float> mvLevelSigma2; };
+class MapPoint {
+public:
+    // set by Frame::isInFrustum (src/Frame.cc:436-441)
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0; bool mbTrackInView = false; int mnTrackScaleLevel = 0; float mTrackViewCos = 0;
+    long unsigned int mnLastFrameSeen = 0;
+    bool isBad() { return bad_; }
+    int Observations() { return nobs_; }
+    cv::Mat GetDescriptor() { return desc_.clone(); }
+    cv::Mat GetWorldPos() { return pos_.clone(); }
+    bool bad_ = false; int nobs_ = 1; cv::Mat desc_, pos_;
+};
+class MapLine {
+public:
+    cv::Mat GetDescriptor() { return desc_.clone(); }
+    cv::Mat desc_;
+};
+class Frame {
+public:
+    void AssignFeaturesToGrid();
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const;
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    void ComputeStereoMatches();
+    void ComputeStereoMatches_Lines(bool initial = false);
+    double lineSegmentOverlapStereo(double spl_obs, double epl_obs, double spl_proj, double epl_proj);
+    void filterLineSegmentDisparity(Vector2d spl, Vector2d epl, Vector2d spr, Vector2d epr, double& disp_s, double& disp_e);
+
+    ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+    float fx = 0, fy = 0, cx = 0, cy = 0, invfx = 0, invfy = 0;
+    float mbf = 0, mb = 0, mThDepth = 0;
+    int N = 0, N_l = 0;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<cv::line_descriptor::KeyLine> mvKeys_Line, mvKeysRight_Line;
+    std::vector<float> mvuRight, mvDepth;
+    std::vector<pair<float, float>> mvDisparity_l;
+    std::vector<Vector3d> mvle_l;
+    cv::Mat mDescriptors, mDescriptorsRight, mDescriptors_Line, mDescriptorsRight_Line;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    cv::Mat mTcw;
+    int mnScaleLevels = 0; float mfScaleFactor = 0, mfLogScaleFactor = 0;
+    vector<float> mvScaleFactors, mvInvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+    float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
+    double inv_width = 0, inv_height = 0;
+};
+}  // namespace ORB_SLAM2

@@ -1,0 +1,245 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// refcli: the REFERENCE'S OWN hot-path code behind a tiny file protocol, so that tests/test_oracle_vs_ref.py can pin the
+// CPU oracle (oracle/*.cpp) to the reference itself.  What is compiled here, unmodified, from /root/reference:
+//   whole files : src/ORBextractor.cc, src/LineExtractor.cc, src/LineMatcher.cpp, src/gridStructure.cpp, src/LineIterator.cpp,
+//                 src/Config.cpp, Thirdparty/line_descriptor/src/LSDDetector_custom.cpp
+//   sliced (oracle/ref_harness/slice.py, verbatim function text): BinaryDescriptor ctor / computeSobel / computeImpl /
+//                 computeLBD / binaryConversion (ref_lbd.cpp); ORBmatcher::SearchByProjection (map points; last frame), RadiusByViewingCos,
+//                 ComputeThreeMaxima, DescriptorDistance; Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid /
+//                 ComputeStereoMatches / ComputeStereoMatches_Lines (+ helpers)
+// against the stand-in types of cvstub.hpp / frame_stub.hpp.  Un-vendored OpenCV arithmetic comes from oracle/cvprim.hpp and
+// oracle/line.cpp (pinned to cv2 4.13 by the golden vectors).
+//
+// Determinism: DistributeOctTree sorts (size, ExtractorNode*) pairs, i.e. breaks ties by allocation
+// address.  This executable replaces the global operator new with a bump allocator (addresses grow in allocation order,
+// nothing is reused), which turns that into "creation order" -- the canonical choice of the oracle and the product.
+//
+// usage: refcli <command> <in.bin> <out.bin>; files = int32 count, then per array: int32 dtype (0 u8,1 i32,2 f32,3 f64),
+// int32 ndim, int64 dims[ndim], raw data.
+#include "frame_stub.hpp"
+#include "ORBmatcher.h"
+#include "LineMatcher.h"
+#include "LineExtractor.h"
+#include "LineIterator.h"
+#include "gridStructure.h"
+#include "Config.h"
+#include <new>
+
+// ---- bump allocator ---------------------------------------------------------------------------------------------------
+static char* g_arena = nullptr; static size_t g_off = 0; static const size_t ARENA = (size_t)6 << 30;
+void* operator new(size_t n) {
+    if (!g_arena) { g_arena = (char*)malloc(ARENA); if (!g_arena) abort(); }
+    n = (n + 15) & ~(size_t)15;
+    if (g_off + n > ARENA) { fprintf(stderr, "refcli: arena exhausted\n"); abort(); }
+    void* p = g_arena + g_off; g_off += n; return p;
+}
+void* operator new[](size_t n) { return operator new(n); }
+void operator delete(void*) noexcept {}
+void operator delete[](void*) noexcept {}
+void operator delete(void*, size_t) noexcept {}
+void operator delete[](void*, size_t) noexcept {}
+
+// ---- sliced reference functions -----------------------------------------------------------------------------------------
+namespace ORB_SLAM2 {
+const int ORBmatcher::TH_HIGH = 100;       // src/ORBmatcher.cc:39-41
+const int ORBmatcher::TH_LOW = 50;
+const int ORBmatcher::HISTO_LENGTH = 30;
+ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+#include "orbmatcher.inc"
+#include "frame.inc"
+}
+
+// ---- array file protocol ------------------------------------------------------------------------------------------------
+struct Arr { int dtype = 0; std::vector<long long> dims; std::vector<char> data;
+    size_t count() const { size_t c = 1; for (auto d : dims) c *= (size_t)d; return c; }
+    template <typename T> T* as() { return (T*)data.data(); }
+    template <typename T> T at(size_t i) { return ((T*)data.data())[i]; } };
+static const int ESZ[4] = {1, 4, 4, 8};
+static std::vector<Arr> read_arrays(const char* path) {
+    FILE* f = fopen(path, "rb"); if (!f) { perror(path); exit(2); }
+    int n = 0; if (fread(&n, 4, 1, f) != 1) exit(2);
+    std::vector<Arr> v(n);
+    for (auto& a : v) {
+        int nd = 0; if (fread(&a.dtype, 4, 1, f) != 1 || fread(&nd, 4, 1, f) != 1) exit(2);
+        a.dims.resize(nd); if (nd && fread(a.dims.data(), 8, nd, f) != (size_t)nd) exit(2);
+        a.data.resize(a.count() * ESZ[a.dtype]); if (!a.data.empty() && fread(a.data.data(), 1, a.data.size(), f) != a.data.size()) exit(2);
+    }
+    fclose(f); return v;
+}
+static void write_arrays(const char* path, std::vector<Arr>& v) {
+    FILE* f = fopen(path, "wb"); int n = (int)v.size(); fwrite(&n, 4, 1, f);
+    for (auto& a : v) { int nd = (int)a.dims.size(); fwrite(&a.dtype, 4, 1, f); fwrite(&nd, 4, 1, f); fwrite(a.dims.data(), 8, nd, f); if (!a.data.empty()) fwrite(a.data.data(), 1, a.data.size(), f); }
+    fclose(f);
+}
+template <typename T> static Arr make(int dtype, std::vector<long long> dims, const T* src) {
+    Arr a; a.dtype = dtype; a.dims = dims; a.data.resize(a.count() * ESZ[dtype]); if (!a.data.empty()) memcpy(a.data.data(), src, a.data.size()); return a;
+}
+static cv::Mat mat_u8(Arr& a) { cv::Mat m((int)a.dims[0], (int)a.dims[1], CV_8UC1); for (int r = 0; r < m.rows; ++r) memcpy(m.ptr(r), a.as<uchar>() + (size_t)r * m.cols, m.cols); return m; }
+static cv::Mat mat_f32(const float* p, int r, int c) { cv::Mat m(r, c, CV_32F); for (int i = 0; i < r; ++i) memcpy(m.ptr(i), p + (size_t)i * c, (size_t)c * 4); return m; }
+using cv::line_descriptor::KeyLine;
+static std::vector<KeyLine> keylines_from(Arr& a) {           // rows of 17 floats/ints in olf_keyline order
+    std::vector<KeyLine> v(a.dims[0]);
+    for (size_t i = 0; i < v.size(); ++i) {
+        const float* f = a.as<float>() + i * 17; const int* q = (const int*)f; KeyLine& k = v[i];
+        k.angle = f[0]; k.class_id = q[1]; k.octave = q[2]; k.pt = cv::Point2f(f[3], f[4]); k.response = f[5]; k.size = f[6];
+        k.startPointX = f[7]; k.startPointY = f[8]; k.endPointX = f[9]; k.endPointY = f[10];
+        k.sPointInOctaveX = f[11]; k.sPointInOctaveY = f[12]; k.ePointInOctaveX = f[13]; k.ePointInOctaveY = f[14]; k.lineLength = f[15]; k.numOfPixels = q[16];
+    }
+    return v;
+}
+static Arr keylines_to(const std::vector<KeyLine>& v) {
+    std::vector<float> o(v.size() * 17);
+    for (size_t i = 0; i < v.size(); ++i) {
+        float* f = o.data() + i * 17; int* q = (int*)f; const KeyLine& k = v[i];
+        f[0] = k.angle; q[1] = k.class_id; q[2] = k.octave; f[3] = k.pt.x; f[4] = k.pt.y; f[5] = k.response; f[6] = k.size;
+        f[7] = k.startPointX; f[8] = k.startPointY; f[9] = k.endPointX; f[10] = k.endPointY;
+        f[11] = k.sPointInOctaveX; f[12] = k.sPointInOctaveY; f[13] = k.ePointInOctaveX; f[14] = k.ePointInOctaveY; f[15] = k.lineLength; q[16] = k.numOfPixels;
+    }
+    return make<float>(2, {(long long)v.size(), 17}, o.data());
+}
+static Arr keypoints_to(const std::vector<cv::KeyPoint>& v) {       // olf_keypoint rows: x, y, size, angle, response, octave(int)
+    std::vector<float> o(v.size() * 6);
+    for (size_t i = 0; i < v.size(); ++i) { float* f = o.data() + i * 6; f[0] = v[i].pt.x; f[1] = v[i].pt.y; f[2] = v[i].size; f[3] = v[i].angle; f[4] = v[i].response; ((int*)f)[5] = v[i].octave; }
+    return make<float>(2, {(long long)v.size(), 6}, o.data());
+}
+static std::vector<cv::KeyPoint> keypoints_from(Arr& a) {
+    std::vector<cv::KeyPoint> v(a.dims[0]);
+    for (size_t i = 0; i < v.size(); ++i) { const float* f = a.as<float>() + i * 6; v[i] = cv::KeyPoint(f[0], f[1], f[2], f[3], f[4], ((const int*)f)[5]); }
+    return v;
+}
+static Arr mat_to(const cv::Mat& m) {
+    std::vector<uchar> o((size_t)m.rows * m.cols * m.elemSize());
+    for (int r = 0; r < m.rows; ++r) memcpy(o.data() + (size_t)r * m.cols * m.elemSize(), m.ptr(r), (size_t)m.cols * m.elemSize());
+    return make<uchar>(m.depth() == CV_32F ? 2 : 0, {m.rows, m.cols}, o.data());
+}
+static void fill_frame_points(ORB_SLAM2::Frame& F, ORB_SLAM2::ORBextractor& ex, Arr& kps, Arr& desc, Arr& cam /* fx fy cx cy bf w h */) {
+    F.mvKeys = keypoints_from(kps); F.mvKeysUn = F.mvKeys; F.N = (int)F.mvKeys.size();
+    F.mDescriptors = cv::Mat((int)desc.dims[0], 32, CV_8UC1); for (int r = 0; r < F.mDescriptors.rows; ++r) memcpy(F.mDescriptors.ptr(r), desc.as<uchar>() + (size_t)r * 32, 32);
+    const float* c = cam.as<float>();
+    F.fx = c[0]; F.fy = c[1]; F.cx = c[2]; F.cy = c[3]; F.invfx = 1.0f / F.fx; F.invfy = 1.0f / F.fy; F.mbf = c[4]; F.mb = F.mbf / F.fx;     // src/Frame.cc:182-196
+    F.mnMinX = 0.0f; F.mnMaxX = c[5]; F.mnMinY = 0.0f; F.mnMaxY = c[6];                                                                     // ComputeImageBounds, rectified
+    F.mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(F.mnMaxX - F.mnMinX);
+    F.mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(F.mnMaxY - F.mnMinY);
+    F.mvScaleFactors = ex.GetScaleFactors(); F.mvInvScaleFactors = ex.GetInverseScaleFactors(); F.mnScaleLevels = ex.GetLevels();
+    F.mvpMapPoints.assign(F.N, static_cast<ORB_SLAM2::MapPoint*>(NULL)); F.mvbOutlier.assign(F.N, false);
+    F.AssignFeaturesToGrid();
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: refcli <command> <in.bin> <out.bin>\n"); return 2; }
+    const std::string cmd = argv[1];
+    std::vector<Arr> in = read_arrays(argv[2]), out;
+    using namespace ORB_SLAM2;
+    if (cmd == "orb") {                       // in: img, params i32[5] (nfeatures, nlevels, iniTh, minTh, _), scale f32[1] -> kps, desc, level sizes
+        cv::Mat img = mat_u8(in[0]); const int* p = in[1].as<int>();
+        ORBextractor ex(p[0], in[2].as<float>()[0], p[1], p[2], p[3]);
+        std::vector<cv::KeyPoint> kps; cv::Mat desc;
+        ex(img, cv::Mat(), kps, desc);
+        out.push_back(keypoints_to(kps)); out.push_back(mat_to(desc));
+    } else if (cmd == "line_extract") {       // in: img, iparams i32[3] (nfeatures, refine, n_bins), dparams f64[7] (min_len, scale, sigma, quant, ang, eps, dens)
+        cv::Mat img = mat_u8(in[0]); const int* ip = in[1].as<int>(); const double* dp = in[2].as<double>();
+        Lineextractor le(ip[0], dp[0], ip[1], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], ip[2]);
+        std::vector<KeyLine> kls; cv::Mat desc;
+        le(img, cv::Mat(), kls, desc);
+        out.push_back(keylines_to(kls)); out.push_back(mat_to(desc));
+    } else if (cmd == "lbd") {                // in: img, keylines -> binary descriptors, float descriptors (BinaryDescriptor::compute)
+        cv::Mat img = mat_u8(in[0]); std::vector<KeyLine> kls = keylines_from(in[1]);
+        cv::Ptr<cv::line_descriptor::BinaryDescriptor> lbd = cv::line_descriptor::BinaryDescriptor::createBinaryDescriptor();
+        cv::Mat d, df; lbd->compute(img, kls, d, false); lbd->compute(img, kls, df, true);
+        out.push_back(mat_to(d)); out.push_back(mat_to(df));
+    } else if (cmd == "line_iterator") {      // in: f64[n,4] -> per line: coords list (getLineCoords, src/LineIterator.cpp + gridStructure.cpp)
+        std::vector<int> flat, cnt;
+        for (long long i = 0; i < in[0].dims[0]; ++i) {
+            const double* l = in[0].as<double>() + i * 4; std::list<std::pair<int, int>> lc;
+            getLineCoords(l[0], l[1], l[2], l[3], lc);
+            cnt.push_back((int)lc.size()); for (auto& p : lc) { flat.push_back(p.first); flat.push_back(p.second); }
+        }
+        out.push_back(make<int>(1, {(long long)cnt.size()}, cnt.data())); out.push_back(make<int>(1, {(long long)flat.size() / 2, 2}, flat.data()));
+    } else if (cmd == "match_nnr" || cmd == "match") {   // in: desc1, desc2, f32[1] nnr -> matches12, count
+        cv::Mat d1 = mat_u8(in[0]), d2 = mat_u8(in[1]); std::vector<int> m12;
+        const int n = cmd == "match" ? match(d1, d2, in[2].as<float>()[0], m12) : matchNNR(d1, d2, in[2].as<float>()[0], m12);
+        out.push_back(make<int>(1, {(long long)m12.size()}, m12.data())); out.push_back(make<int>(1, {1}, &n));
+    } else if (cmd == "descriptor_distance") {           // in: desc a [n,32], desc b [n,32] -> ORBmatcher::DescriptorDistance, LineMatcher distance
+        cv::Mat a = mat_u8(in[0]), b = mat_u8(in[1]); std::vector<int> d1(a.rows), d2(a.rows);
+        for (int i = 0; i < a.rows; ++i) { d1[i] = ORBmatcher::DescriptorDistance(a.row(i), b.row(i)); d2[i] = distance(a.row(i), b.row(i)); }
+        out.push_back(make<int>(1, {(long long)a.rows}, d1.data())); out.push_back(make<int>(1, {(long long)a.rows}, d2.data()));
+    } else if (cmd == "stereo") {
+        // in: imgL, imgR, orb params i32[5], scale f32[1], cam f32[7], line iparams i32[3], line dparams f64[7], has_lines i32[1]
+        // -> Frame::Frame(stereo+lines) (src/Frame.cc:136-221): kpsL, descL, kpsR, descR, uRight, depth, klsL, ldescL, klsR, ldescR, disp[n,2], le[n,3]
+        cv::Mat imL = mat_u8(in[0]), imR = mat_u8(in[1]); const int* p = in[2].as<int>();
+        ORBextractor exL(p[0], in[3].as<float>()[0], p[1], p[2], p[3]), exR(p[0], in[3].as<float>()[0], p[1], p[2], p[3]);
+        Frame F; F.mpORBextractorLeft = &exL; F.mpORBextractorRight = &exR;
+        exL(imL, cv::Mat(), F.mvKeys, F.mDescriptors); exR(imR, cv::Mat(), F.mvKeysRight, F.mDescriptorsRight);
+        Arr kl = keypoints_to(F.mvKeys), dl = mat_to(F.mDescriptors);
+        fill_frame_points(F, exL, kl, dl, in[4]);
+        F.ComputeStereoMatches();
+        out.push_back(kl); out.push_back(dl); out.push_back(keypoints_to(F.mvKeysRight)); out.push_back(mat_to(F.mDescriptorsRight));
+        out.push_back(make<float>(2, {(long long)F.mvuRight.size()}, F.mvuRight.data())); out.push_back(make<float>(2, {(long long)F.mvDepth.size()}, F.mvDepth.data()));
+        if (in[7].as<int>()[0]) {
+            const int* ip = in[5].as<int>(); const double* dp = in[6].as<double>();
+            Lineextractor leL(ip[0], dp[0], ip[1], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], ip[2]), leR(ip[0], dp[0], ip[1], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], ip[2]);
+            leL(imL, cv::Mat(), F.mvKeys_Line, F.mDescriptors_Line); leR(imR, cv::Mat(), F.mvKeysRight_Line, F.mDescriptorsRight_Line);
+            F.inv_width = FRAME_GRID_COLS / static_cast<double>(imL.cols); F.inv_height = FRAME_GRID_ROWS / static_cast<double>(imR.rows);   // src/Frame.cc:148-149
+            F.ComputeStereoMatches_Lines();
+            out.push_back(keylines_to(F.mvKeys_Line)); out.push_back(mat_to(F.mDescriptors_Line)); out.push_back(keylines_to(F.mvKeysRight_Line)); out.push_back(mat_to(F.mDescriptorsRight_Line));
+            std::vector<float> disp; std::vector<double> le;
+            for (auto& d : F.mvDisparity_l) { disp.push_back(d.first); disp.push_back(d.second); }
+            for (auto& v : F.mvle_l) { le.push_back(v(0)); le.push_back(v(1)); le.push_back(v(2)); }
+            out.push_back(make<float>(2, {(long long)disp.size() / 2, 2}, disp.data())); out.push_back(make<double>(3, {(long long)le.size() / 3, 3}, le.data()));
+        }
+    } else if (cmd == "sbp_last") {
+        // in: cur kps, cur desc, cur uRight, last kps, last has_point u8, last observed u8, last world f32[n,3], last point desc, cam f32[7],
+        //     poses f32[24] (Rcw 9, tcw 3, Rlw 9, tlw 3), scale factors f32[L], th_mono_ori f32[3], orb i32[5]/scale for the extractor tables
+        // -> ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono, match12) (src/ORBmatcher.cc:1474-1618): cur_point i32[n_cur], nmatches
+        Arr &ck = in[0], &cd = in[1], &cu = in[2], &lk = in[3], &has = in[4], &obs = in[5], &wp = in[6], &ld = in[7], &cam = in[8], &pose = in[9];
+        const int* p = in[12].as<int>();
+        ORBextractor ex(p[0], in[13].as<float>()[0], p[1], p[2], p[3]);
+        Frame Cur, Last;
+        fill_frame_points(Cur, ex, ck, cd, cam); Cur.mvuRight.assign(cu.as<float>(), cu.as<float>() + cu.count());
+        Arr lde = make<uchar>(0, {(long long)lk.dims[0], 32}, ld.as<uchar>());
+        fill_frame_points(Last, ex, lk, lde, cam);
+        auto Tcw = [](const float* R, const float* t) { cv::Mat T = cv::Mat::eye(4, 4, CV_32F); for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T.at<float>(r, c) = R[3 * r + c]; T.at<float>(r, 3) = t[r]; } return T; };
+        const float* ps = pose.as<float>();
+        Cur.mTcw = Tcw(ps, ps + 9); Last.mTcw = Tcw(ps + 12, ps + 21);
+        std::vector<MapPoint> pts(Last.N);
+        for (int i = 0; i < Last.N; ++i) {
+            if (!has.as<uchar>()[i]) continue;
+            pts[i].nobs_ = obs.as<uchar>()[i] ? 1 : 0; pts[i].pos_ = mat_f32(wp.as<float>() + 3 * i, 3, 1);
+            pts[i].desc_ = cv::Mat(1, 32, CV_8UC1); memcpy(pts[i].desc_.ptr(), ld.as<uchar>() + (size_t)32 * i, 32);
+            Last.mvpMapPoints[i] = &pts[i];
+        }
+        const float* tmo = in[11].as<float>();
+        ORBmatcher matcher(0.9, tmo[2] != 0);
+        std::map<int, int> match12;
+        const int n = matcher.SearchByProjection(Cur, Last, tmo[0], tmo[1] != 0, match12);
+        std::vector<int> cur_point(Cur.N, -1);
+        for (int j = 0; j < Cur.N; ++j) if (Cur.mvpMapPoints[j]) cur_point[j] = (int)(Cur.mvpMapPoints[j] - pts.data());
+        out.push_back(make<int>(1, {(long long)Cur.N}, cur_point.data())); out.push_back(make<int>(1, {1}, &n));
+    } else if (cmd == "sbp_map") {
+        // in: cur kps, cur desc, cur uRight, occupied u8 (or empty), cam, proj f32[n,3] (x,y,xr), level i32[n], viewcos f32[n], observed u8[n], point desc, th_ratio f32[2], orb i32[5], scale
+        // -> ORBmatcher::SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:47-131): assigned_cur i32[n_points], nmatches
+        Arr &ck = in[0], &cd = in[1], &cu = in[2], &occ = in[3], &cam = in[4], &proj = in[5], &lvl = in[6], &vc = in[7], &obs = in[8], &pd = in[9];
+        const int* p = in[11].as<int>();
+        ORBextractor ex(p[0], in[12].as<float>()[0], p[1], p[2], p[3]);
+        Frame F; fill_frame_points(F, ex, ck, cd, cam); F.mvuRight.assign(cu.as<float>(), cu.as<float>() + cu.count());
+        MapPoint occupied_marker; occupied_marker.nobs_ = 1;
+        if (occ.count()) for (int j = 0; j < F.N; ++j) if (occ.as<uchar>()[j]) F.mvpMapPoints[j] = &occupied_marker;
+        const int np = (int)lvl.count();
+        std::vector<MapPoint> pts(np); std::vector<MapPoint*> vp(np);
+        for (int i = 0; i < np; ++i) {
+            MapPoint& m = pts[i]; m.mbTrackInView = true; m.mTrackProjX = proj.as<float>()[3 * i]; m.mTrackProjY = proj.as<float>()[3 * i + 1]; m.mTrackProjXR = proj.as<float>()[3 * i + 2];
+            m.mnTrackScaleLevel = lvl.as<int>()[i]; m.mTrackViewCos = vc.as<float>()[i]; m.nobs_ = obs.as<uchar>()[i] ? 1 : 0;
+            m.desc_ = cv::Mat(1, 32, CV_8UC1); memcpy(m.desc_.ptr(), pd.as<uchar>() + (size_t)32 * i, 32);
+            vp[i] = &m;
+        }
+        const float* tr = in[10].as<float>();
+        ORBmatcher matcher(tr[1], true);
+        const int n = matcher.SearchByProjection(F, vp, tr[0]);
+        std::vector<int> assigned(np, -1);
+        for (int j = 0; j < F.N; ++j) if (F.mvpMapPoints[j] && F.mvpMapPoints[j] != &occupied_marker) assigned[(int)(F.mvpMapPoints[j] - pts.data())] = j;
+        out.push_back(make<int>(1, {(long long)np}, assigned.data())); out.push_back(make<int>(1, {1}, &n));
+    } else { fprintf(stderr, "refcli: unknown command %s\n", cmd.c_str()); return 2; }
+    write_arrays(argv[3], out);
+    return 0;
+}

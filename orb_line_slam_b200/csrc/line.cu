@@ -1267,7 +1267,8 @@ static void make_keylines(const std::vector<float4>& segs, int w, int hgt, doubl
         kl.lineLength = (float)length;
         const int x1 = (int)lrintf(e[0]), y1 = (int)lrintf(e[1]), x2 = (int)lrintf(e[2]), y2 = (int)lrintf(e[3]);
         kl.numOfPixels = std::max(std::abs(x2 - x1), std::abs(y2 - y1)) + 1;        // cv::LineIterator(...).count, 8-connected
-        kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+        // the reference's unqualified atan2(float, float) is atan2f: its precompiled header includes <math.h> (LSDDetector_custom.cpp:298)
+        kl.angle = atan2f(kl.endPointY - kl.startPointY, kl.endPointX - kl.startPointX);
         kl.class_id = ++class_counter;
         kl.octave = 0;
         kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);
@@ -1292,7 +1293,7 @@ static int lbd_enqueue(LineImpl* h, const olf_keyline* kls, int n, cudaStream_t 
         const olf_keyline& k = kls[i];
         LbdLine L;
         L.sx = k.sPointInOctaveX; L.sy = k.sPointInOctaveY; L.ex = k.ePointInOctaveX; L.ey = k.ePointInOctaveY;
-        L.dL0 = (float)std::cos((double)k.angle); L.dL1 = (float)std::sin((double)k.angle);       // :1130-1131
+        L.dL0 = cosf(k.angle); L.dL1 = sinf(k.angle);       // cos( float ), sin( float ) = cosf, sinf in the reference's build (:1130-1131)
         L.num_px = k.numOfPixels;
         h->lbd_lines.p[i] = L;
     }
