@@ -338,7 +338,7 @@ def main():
     ap.add_argument("--pipelines", type=int, default=0, help="concurrent stereo rigs per GPU (0 = auto)")
     ap.add_argument("--trackers", type=int, default=2, help="host threads running the frame-to-frame matchers")
     ap.add_argument("--no-track", action="store_true", help="(diagnostic) skip the frame-to-frame matchers")
-    ap.add_argument("--batch", type=int, default=4, help="independent stereo frames per olf_frontend_process_batch call (1..4)")
+    ap.add_argument("--batch", type=int, default=4, help="independent stereo frames per olf_frontend_process_batch call (1..8)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded single-thread CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm-steps", type=int, default=60, help="untimed steps before the warm-up steps (fixed count: rank-invariant)")
@@ -400,7 +400,7 @@ def main():
     # One host thread per rig (plus the trackers): the same number of rigs at every N as long as the box has the cores.
     cores = os.cpu_count() or 16
     P = args.pipelines or max(2, min(13, (cores - 2) // max(1, world)))
-    B = max(1, min(4, args.batch))
+    B = max(1, min(8, args.batch))
     sc, seq, poses = make_sequence(N_DISTINCT, wl)
     # weak scaling: every rank runs the same number of frames of its own slice of the sequence
     shift = (rank * 11) % len(seq)

@@ -37,6 +37,7 @@ extern "C" {
 #define OLF_TH_LOW         50   /* ORBmatcher::TH_LOW  src/ORBmatcher.cc:40                            */
 #define OLF_HISTO_LENGTH   30   /* ORBmatcher::HISTO_LENGTH src/ORBmatcher.cc:41                       */
 #define OLF_MAX_LEVELS     16
+#define OLF_MAX_BATCH_FRAMES 8  /* stereo frames per olf_frontend_process_batch call */
 
 /* cv::KeyPoint fields the reference fills (src/ORBextractor.cc:839-848, 1097-1103); class_id stays -1. */
 typedef struct olf_keypoint {
@@ -146,6 +147,9 @@ int olf_lbd_compute(olf_line* h, const uint8_t* img, int width, int height, int 
  * two nearest train rows per query, ties -> lowest train index.  idx1/dist1 = -1/INT_MAX-like 256*2 when n2 < 2. */
 int olf_knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
                      int* idx0, int* dist0, int* idx1, int* dist1, int device);
+/* measurement hook (BASELINE.json configs[4], the descriptor-match micro-benchmark): kernel-only time of the knn2 kernels on
+ * device-resident random descriptors, and the chip's measured xor+popc+add ceiling in 32-bit word pairs per second */
+int olf_knn2_bench(int n1, int n2, int iters, int device, double* kernel_ms, double* popc_word_pairs_per_s);
 /* matchNNR (src/LineMatcher.cpp:42-62): matches12[n1], returns count through *nmatches. */
 int olf_match_nnr(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int* matches12, int* nmatches, int device);
 /* match(desc1,desc2,nnr,matches12) (src/LineMatcher.cpp:104-132): adds the mutual check when best_lr_matches. */
@@ -166,6 +170,15 @@ int olf_stereo_lines(const olf_keyline* kls_l, const uint8_t* desc_l, int n_l,
                      int* matches12 /*n_l, raw matchGrid output*/,
                      float* disp_s_e /*n_l x 2, mvDisparity_l*/, double* le /*n_l x 3, mvle_l*/, int device);
 
+/* ---- matchGrid(lines1, desc1, grid, desc2, directions2, w, matches_12) (include/LineMatcher.h:69, src/LineMatcher.cpp:220-299) for
+ * callers that build the GridStructure themselves (Frame::ComputeStereoMatches_Lines, src/Frame.cc:896-927, unchanged).
+ * grid: the cells of GridStructure (include/gridStructure.h:40-58) as CSR, cell (x, y) at index x*rows + y; lines1: n1 x 4 grid
+ * coordinates (start x, y, end x, y); dir2: n2 x 2 normalised directions; window: GridWindow {width.first, width.second,
+ * height.first, height.second}.  Candidates are walked in ascending index (canonical order of the hash set, Appendix C.2). */
+typedef struct olf_grid_csr { int rows, cols; const int* cell_begin; /* rows*cols + 1 */ const int* items; } olf_grid_csr;
+int olf_match_grid_lines(const int* lines1, const uint8_t* desc1, int n1, const olf_grid_csr* grid, const uint8_t* desc2, int n2,
+                         const double* dir2, const int* window, const olf_line_match_params* p, int* matches12, int* nmatches, int device);
+
 /* ---- ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono, match12) (src/ORBmatcher.cc:1474-1618) - */
 typedef struct olf_sbp_last_args {
     /* current frame (the one being filled) */
@@ -181,6 +194,7 @@ typedef struct olf_sbp_last_args {
     const float*   last_world_pos;       /* n_last x 3, pMP->GetWorldPos()                  */
     const uint8_t* last_point_desc;      /* n_last x 32, pMP->GetDescriptor()               */
     float th; int mono; int check_orientation;
+    const uint8_t* cur_occupied;         /* optional (may be NULL): CurrentFrame.mvpMapPoints[j] && Observations()>0 on entry (:1550-1552) */
 } olf_sbp_last_args;
 /* assigned_cur[i] (n_last) = index of the current keypoint map point i was written to (before the
  * rotation-consistency pass) or -1; cur_point[j] (n_cur) = final index into last-frame points held by
@@ -279,9 +293,9 @@ void olf_frontend_destroy(olf_frontend* h);
 int  olf_frontend_process(olf_frontend* h, const uint8_t* img_l, const uint8_t* img_r, int width, int height, int stride,
                           int on_device, void* result);
 /* Batch entry (SURVEY 8b `olf_frame_batch_extract`, the unit of work of the multi-GPU driver, BASELINE config "8-frame
- * batch"): `nframes` INDEPENDENT stereo frames (1..max_frames <= 4) through Frame::Frame at once.  The line extraction of
+ * batch"): `nframes` INDEPENDENT stereo frames (1..max_frames <= OLF_MAX_BATCH_FRAMES) through Frame::Frame at once.  The line extraction of
  * all 2*nframes images runs as ONE chain of kernel launches (the LSD passes are latency-bound: a batch costs the latency of
- * one image), so a rig keeps 2*max_frames images in flight on two CUDA streams.  Results are identical to nframes calls of
+ * one image), so a rig keeps 2*max_frames images in flight on ONE CUDA stream (the short ORB + stereo chain first, the line chain behind it).  Results are identical to nframes calls of
  * olf_frontend_process; results[f] is the block of frame f. */
 olf_frontend* olf_frontend_create_batch(const olf_frontend_params* p, int device, int max_frames);
 int  olf_frontend_process_batch(olf_frontend* h, const uint8_t* const* img_l, const uint8_t* const* img_r, int nframes,

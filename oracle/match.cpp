@@ -377,6 +377,7 @@ extern "C" int orc_search_by_projection_last(const olf_sbp_last_args* a, int* as
     const bool bBackward = -tlc[2] > mb && !a->mono;
     for (int j = 0; j < a->n_cur; ++j) cur_point[j] = -1;
     std::vector<uint8_t> blocked(a->n_cur, 0);             // CurrentFrame.mvpMapPoints[i2] && Observations()>0
+    if (a->cur_occupied) for (int j = 0; j < a->n_cur; ++j) blocked[j] = a->cur_occupied[j];
     std::vector<int> cand;
     for (int i = 0; i < a->n_last; i++) {
         assigned_cur[i] = -1;

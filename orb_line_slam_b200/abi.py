@@ -85,7 +85,7 @@ class SbpLastArgs(C.Structure):
                 ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Rlw", C.c_float * 9), ("tlw", C.c_float * 3),
                 ("last_kps", _P), ("n_last", C.c_int), ("last_has_point", _P), ("last_point_observed", _P),
                 ("last_world_pos", _P), ("last_point_desc", _P),
-                ("th", C.c_float), ("mono", C.c_int), ("check_orientation", C.c_int)]
+                ("th", C.c_float), ("mono", C.c_int), ("check_orientation", C.c_int), ("cur_occupied", _P)]
 
 
 class SbpMapArgs(C.Structure):

@@ -115,6 +115,7 @@ int olf_line_last_stats(const olf_line* h, int* out8) { if (!h || !out8) return 
 int olf_knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0, int* dist0, int* idx1, int* dist1, int device) {
     return knn2_hamming(d1, n1, d2, n2, idx0, dist0, idx1, dist1, device);
 }
+int olf_knn2_bench(int n1, int n2, int iters, int device, double* kernel_ms, double* popc_word_pairs_per_s) { return knn2_bench(n1, n2, iters, device, kernel_ms, popc_word_pairs_per_s); }
 int olf_match_nnr(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int* matches12, int* nmatches, int device) {
     return match_lines(d1, n1, d2, n2, nnr, 0, matches12, nmatches, device);
 }
@@ -128,6 +129,10 @@ int olf_stereo_points(olf_orb* left, olf_orb* right, const olf_keypoint* kps_l, 
 int olf_stereo_lines(const olf_keyline* kls_l, const uint8_t* desc_l, int n_l, const olf_keyline* kls_r, const uint8_t* desc_r, int n_r,
                      int img_width, int img_height, const olf_line_match_params* p, int* matches12, float* disp_s_e, double* le, int device) {
     return stereo_lines(kls_l, desc_l, n_l, kls_r, desc_r, n_r, img_width, img_height, p, matches12, disp_s_e, le, device);
+}
+int olf_match_grid_lines(const int* lines1, const uint8_t* desc1, int n1, const olf_grid_csr* grid, const uint8_t* desc2, int n2, const double* dir2,
+                         const int* window, const olf_line_match_params* p, int* matches12, int* nmatches, int device) {
+    return match_grid_lines(lines1, desc1, n1, grid, desc2, n2, dir2, window, p, matches12, nmatches, device);
 }
 int olf_search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device) {
     return search_by_projection_last(a, assigned_cur, cur_point, nmatches, device);

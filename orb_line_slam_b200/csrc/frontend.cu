@@ -45,7 +45,7 @@ struct FrontendImpl {
     // stream; the line extractors of a batch rig are driven through the first one's stream by ONE batched chain of launches
     std::vector<OrbImpl*> orb;
     std::vector<LineImpl*> line;
-    StereoWs sws[4];
+    StereoWs sws[OLF_MAX_BATCH_FRAMES];
     SyncEvent ev_orb;
     Worker* worker = nullptr;            // single-frame rig only: the right eye's line extraction
     olf_frame_offsets off;
@@ -75,13 +75,17 @@ int frame_layout(int cap_p, int cap_l, olf_frame_offsets* o) {
 
 void frontend_destroy(FrontendImpl* h);
 FrontendImpl* frontend_create(const olf_frontend_params* p, int device, int max_frames) {
-    if (!p || p->cap_points < p->nfeatures || p->cap_lines < 0 || max_frames < 1 || 2 * max_frames > 8) {
-        set_last_error("olf_frontend_create: bad arguments (1..4 frames per batch)"); return nullptr;
+    if (!p || p->cap_points < p->nfeatures || p->cap_lines < 0 || max_frames < 1 || max_frames > OLF_MAX_BATCH_FRAMES) {
+        set_last_error("olf_frontend_create: bad arguments (1..8 frames per batch)"); return nullptr;
     }
     FrontendImpl* h = new FrontendImpl();
     h->P = *p; h->device = device; h->max_frames = max_frames;
     frame_layout(p->cap_points, p->cap_lines, &h->off);
     const bool batch = max_frames > 1;
+    // A device has 32 hardware work queues and streams beyond that alias (a long LSD chain then blocks an unrelated rig), so
+    // streams are what limits the number of rigs in flight.  A batch rig therefore uses ONE stream by default: the short ORB +
+    // stereo chain of the call runs first, the batched line chain behind it (OLF_RIG_STREAMS=2: ORB on a stream of its own).
+    const bool one_stream = batch && p->has_lines && !(getenv("OLF_RIG_STREAMS") && atoi(getenv("OLF_RIG_STREAMS")) == 2);
     bool ok = true;
     for (int k = 0; k < 2 * max_frames && ok; ++k) {
         // a single-frame rig (latency matters) keeps one stream per eye and extracts the two eyes' lines side by side; a batch
@@ -89,7 +93,7 @@ FrontendImpl* frontend_create(const olf_frontend_params* p, int device, int max_
         if (p->has_lines) { h->line.push_back(line_create(&p->line, device, (h->line.empty() || !batch) ? nullptr : line_stream(h->line[0]), batch)); ok = h->line.back() != nullptr; }
         if (ok) {
             h->orb.push_back(orb_create(p->nfeatures, p->scale_factor, p->nlevels, p->ini_th_fast, p->min_th_fast, device,
-                                        h->orb.empty() ? nullptr : orb_stream(h->orb[0])));
+                                        one_stream ? line_stream(h->line[0]) : (h->orb.empty() ? nullptr : orb_stream(h->orb[0]))));
             ok = h->orb.back() != nullptr;
         }
     }
@@ -106,7 +110,7 @@ void frontend_destroy(FrontendImpl* h) {
     delete h->worker;
     cudaSetDevice(h->device);
     if (!h->orb.empty()) cudaStreamSynchronize(orb_stream(h->orb[0]));
-    for (int f = 0; f < 4; ++f) stereo_ws_release(&h->sws[f]);
+    for (int f = 0; f < OLF_MAX_BATCH_FRAMES; ++f) stereo_ws_release(&h->sws[f]);
     h->ev_orb.destroy();
     for (size_t k = h->orb.size(); k-- > 0;) orb_destroy(h->orb[k]);     // the borrowers before the owner of the stream
     for (size_t k = h->line.size(); k-- > 0;) line_destroy(h->line[k]);

@@ -39,7 +39,7 @@ static __device__ __forceinline__ void locate_tile(const LevelTable& T, int b, i
 // H pass 8.8 (u16), V pass 16.16, rounding (acc + 2^15) >> 16, BORDER_REFLECT_101 at the level edge.
 // A batch of images per launch (blockIdx.y): the rigs keep 2..8 images in flight and every kernel of this front end is
 // launch-bound on one 0.9-MB image, so one launch serves all images of a call.
-#define IMG_MAX_BATCH 8
+#define IMG_MAX_BATCH 16
 struct BlurBatch { const uint8_t* src[IMG_MAX_BATCH]; uint8_t* dst[IMG_MAX_BATCH]; };
 template <int K>
 static __global__ void __launch_bounds__(256) k_blur_q8(const __grid_constant__ BlurBatch BB,

@@ -142,6 +142,16 @@ struct PhaseState {
     int launches; unsigned wave_first_round;
     unsigned wl0_cnt, wl1_cnt, wl2_cnt, wl2_pop, changed, ticket;
     unsigned recheck, force, pad0, pad1;                     // full verification failed / the next round verifies every region
+    // grow pass in instalments: regions that used up a launch's step budget wait in cont[cont_par] for the next launch
+    unsigned cont_cnt[2], cont_par, growing;
+};
+// a paused region: everything k_lsd_grow keeps in registers for a seed (64 bytes)
+struct alignas(16) GrowCont {
+    int i; unsigned w_head, w_chunk, r_chunk, b_head, b_chunk;
+    unsigned offs;                                           // w_off | r_off << 8 | b_off << 16 | dirty << 24
+    int count, done, bcnt;
+    unsigned short bx0, by0, bx1, by1;
+    float sumdx, sumdy; double reg_angle;
 };
 struct GrowDev {
     Ctx3 C;
@@ -154,11 +164,13 @@ struct GrowDev {
     int dirty_words;             // words of one dirty bitmap
     int test_recheck;            // (test hook, OLF_LSD_TEST_RECHECK) pretend the full verification of every wave fails once
     int* dbg;                    // optional per-round trace (OLF_LSD_TRACE)
+    GrowCont* cont[2];           // paused regions, by launch parity (capacity: threads of one grow launch per image)
+    int budget;                  // queue entries a thread may expand per grow launch
 };
 // One launch serves a BATCH of images (the two eyes of a stereo frame, several frames): blockIdx.y selects the image, every
 // image has its own state machine.  The passes are latency-bound with small grids, so a batch costs one chain of launches
 // on one stream instead of one chain per image -- that is what keeps many frames in flight within the 32 hardware queues.
-#define LSD_MAX_BATCH 8
+#define LSD_MAX_BATCH 16
 #define LSD_MAX_WAVES 64
 struct GrowBatch { GrowDev d[LSD_MAX_BATCH]; PhaseState* st[LSD_MAX_BATCH]; unsigned* conv; int n; };   // conv[w]: images of the batch that have converged in wave w
 __device__ __forceinline__ const GrowDev& batch_image(const GrowBatch& B, GrowDev* sh, PhaseState*& st) {
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(256) k_lsd_scan(const __grid_constant__ GrowBa
     __shared__ GrowDev s_dev;
     PhaseState* st;
     const GrowDev& D = batch_image(B, &s_dev, st);
-    if (st->done || st->mode != 0) return;
+    if (st->done || st->mode != 0 || st->growing) return;
     const int wv = st->wave;
     if (wv >= D.plan->n_waves) return;
     const unsigned round = st->round;
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ G
     __shared__ GrowDev s_dev;
     PhaseState* st;
     const GrowDev& D = batch_image(B, &s_dev, st);
-    if (st->done) return;
+    if (st->done || st->growing) return;
     const int wv = st->wave;
     if (wv >= D.plan->n_waves) return;
     const unsigned round = st->round;
@@ -390,7 +402,10 @@ __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ G
 struct GrowSmem { float2 nb[8][GROW_THREADS]; unsigned ring[GROW_RING][GROW_THREADS]; };   // (cos, sin) of the 8 neighbours; recent queue
 
 // The last block to finish advances the wave / round state machine.
-__global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant__ GrowBatch B) {
+#ifndef GROW_MIN_BLOCKS
+#define GROW_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(const __grid_constant__ GrowBatch B) {
     __shared__ GrowSmem sm;
     __shared__ GrowDev s_dev;
     __shared__ bool s_last;
@@ -420,6 +435,28 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
         int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
         bool overflow = false, dirty = false;
         float sumdx = 0.f, sumdy = 0.f, u2 = 0.f; double reg_angle = 0.0;
+        // The pass runs in instalments: a thread expands at most `budget` queue entries per launch; a region that is not complete
+        // then is parked (GrowCont) and the NEXT launch resumes the parked regions densely packed, thread k <- region k.  The few
+        // long regions of a round therefore end up together in a few warps instead of keeping one lane busy in every warp
+        // (and its block resident) for milliseconds; the decisions of a region are the same, only who executes them changes.
+        const unsigned par = st->cont_par;
+        const unsigned n_in = st->cont_cnt[par];
+        const GrowCont* const c_in = D.cont[par];
+        GrowCont* const c_out = D.cont[par ^ 1];
+        const unsigned gt = blockIdx.x * GROW_THREADS + t;
+        int steps = 0, ring_base = 0;
+        const int budget = D.budget;
+        if (gt < n_in) {
+            const GrowCont c = c_in[gt];
+            i = c.i; mine = key_of(C, C.seed_prio[i]);
+            w_head = c.w_head; w_chunk = c.w_chunk; r_chunk = c.r_chunk; b_head = c.b_head; b_chunk = c.b_chunk;
+            w_off = (int)(c.offs & 0xffu); r_off = (int)((c.offs >> 8) & 0xffu); b_off = (int)((c.offs >> 16) & 0xffu); dirty = (c.offs >> 24) != 0;
+            count = c.count; done = c.done; bcnt = c.bcnt; bx0 = c.bx0; by0 = c.by0; bx1 = c.bx1; by1 = c.by1;
+            sumdx = c.sumdx; sumdy = c.sumdy; reg_angle = c.reg_angle;
+            u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
+            ring_base = count;                                   // the shared-memory ring only holds what this thread pushes from now on
+            active = true;
+        }
         auto push = [&](unsigned pix) {
             if (w_off == kChunk - 1) {
                 const unsigned nc = atomicAdd(C.pool_ctr, 1u);
@@ -445,9 +482,11 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
         };
         for (;;) {
             if (!active) {
+                if (steps >= budget) break;                           // the rest of the list waits for the next launch
                 // ---- s3_begin: the seed pixel has been claimed by the verify pass
                 const unsigned k = atomicAdd(&st->wl2_pop, 1u);
                 if (k >= n) break;
+                ring_base = 0;
                 i = D.wl2[k];
                 const int seed = C.seed_pix[i];
                 mine = key_of(C, C.seed_prio[i]);
@@ -476,8 +515,8 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
             if (!overflow) {
                 // ---- s3_step: expand one queue entry
                 if (r_off == kChunk - 1) { r_chunk = pool[(size_t)r_chunk * kChunk + kChunk - 1]; r_off = 0; }
-                const int p = (int)((count - done <= GROW_RING) ? sm.ring[done & (GROW_RING - 1)][t] : pool[(size_t)r_chunk * kChunk + r_off]);
-                ++r_off; ++done;
+                const int p = (int)((count - done <= GROW_RING && done >= ring_base) ? sm.ring[done & (GROW_RING - 1)][t] : pool[(size_t)r_chunk * kChunk + r_off]);
+                ++r_off; ++done; ++steps;
                 int py = __float2int_rd(__fmul_rn((float)p, inv_w));           // p < 2^24: exact after one correction step
                 int px = p - py * W;
                 if (px < 0) { --py; px += W; } else if (px >= W) { ++py; px -= W; }
@@ -606,6 +645,17 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
                 C.srec[i] = r;
                 if (D.dbg) { atomicAdd(&D.dbg[round * TRACE_REC + 5], 1); atomicAdd(&D.dbg[round * TRACE_REC + 6], count); atomicMax(&D.dbg[round * TRACE_REC + 7], count); }
                 active = false;
+            } else if (steps >= budget) {
+                // ---- out of budget in the middle of a region: park it
+                GrowCont c;
+                c.i = i; c.w_head = w_head; c.w_chunk = w_chunk; c.r_chunk = r_chunk; c.b_head = b_head; c.b_chunk = b_chunk;
+                c.offs = (unsigned)w_off | ((unsigned)r_off << 8) | ((unsigned)b_off << 16) | ((unsigned)dirty << 24);
+                c.count = count; c.done = done; c.bcnt = bcnt;
+                c.bx0 = (unsigned short)bx0; c.by0 = (unsigned short)by0; c.bx1 = (unsigned short)bx1; c.by1 = (unsigned short)by1;
+                c.sumdx = sumdx; c.sumdy = sumdy; c.reg_angle = reg_angle;
+                c_out[atomicAdd(&st->cont_cnt[par ^ 1], 1u)] = c;
+                active = false;
+                break;
             }
         }
     }
@@ -622,6 +672,15 @@ __global__ void __launch_bounds__(GROW_THREADS) k_lsd_grow(const __grid_constant
     // of the batch has, so the expensive first rounds of a wave -- whose critical path is the longest region -- coincide in
     // the same launches instead of adding up along the chain.
     const unsigned nb = (unsigned)B.n;
+    if (mode == 0 && st->wl2_cnt > 0) {
+        // parked regions or seeds nobody has taken yet: the grow pass of this round goes on in the next launch
+        const unsigned par = st->cont_par;
+        const unsigned parked = *(volatile unsigned*)&st->cont_cnt[par ^ 1];
+        const bool seeds_left = *(volatile unsigned*)&st->wl2_pop < st->wl2_cnt;
+        st->cont_cnt[par] = 0;
+        if (parked > 0 || seeds_left) { st->cont_par = par ^ 1; st->growing = 1; __threadfence(); return; }
+        st->growing = 0;
+    }
     if (mode == 0) {
         if (D.dbg) D.dbg[round * TRACE_REC + 3] = (int)(gtime() & 0x7fffffff);
         const bool changed = *(volatile unsigned*)&st->changed != 0;
@@ -919,6 +978,8 @@ struct LineImpl {
     DevBuf<float2_t> tab_seed, tab_acc, cs;
     DevBuf<PhaseState> phase;
     DevBuf<PxRec> px;
+    DevBuf<GrowCont> cont;
+    int grow_budget = 1 << 30;          // OLF_LSD_GROW_BUDGET: queue entries per thread and grow launch (default: no limit)
     int phase_batch = 52;
     bool trace = false;
     int first_wave = 4096, first_wave_latency = 262144, wave_growth = 16;
@@ -1033,6 +1094,9 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     if (const char* e = getenv("OLF_LSD_SCAN_BLOCKS")) h->scan_blocks = h->scan_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_VERIFY_BLOCKS")) h->verify_blocks = h->verify_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks_wide = h->grow_blocks_narrow = std::max(1, atoi(e));
+    if (const char* e = getenv("OLF_LSD_GROW_BUDGET")) h->grow_budget = std::max(1, atoi(e));
+    ok = h->cont.ensure((size_t)2 * std::max(h->grow_blocks_wide, h->grow_blocks_narrow) * GROW_THREADS) == OLF_OK;
+    if (!ok) { delete h; return nullptr; }
     return h;
 }
 
@@ -1047,7 +1111,7 @@ void line_destroy(LineImpl* h) {
     h->ang.release(); h->dabc.release(); h->seed_prio.release(); h->seed_pix.release(); h->n2max.release(); h->status.release();
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
     h->final_pool.release(); h->conv.release(); h->dirty.release(); h->srec0.release(); h->regang.release(); h->plan.release(); h->regs.release();
-    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release();
+    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release(); h->cont.release();
     h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release(); h->phase_init.release();
     h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
@@ -1167,6 +1231,7 @@ static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D, int batch_im
     D.defer = getenv("OLF_LSD_NO_DEFER") ? 0 : 1;
     D.test_recheck = getenv("OLF_LSD_TEST_RECHECK") ? 1 : 0;
     D.dbg = h->trace ? h->dbg.p : nullptr;
+    D.cont[0] = h->cont.p; D.cont[1] = h->cont.p + h->cont.n / 2; D.budget = h->grow_budget;
     if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
     h->phase_init.p[0] = PhaseState{}; h->phase_init.p[0].round = 1; h->phase_init.p[0].wave_first_round = 1;
     OLF_CUDA(cudaMemcpyAsync(h->phase.p, h->phase_init.p, sizeof(PhaseState), cudaMemcpyHostToDevice, s));

@@ -181,6 +181,59 @@ int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0
     return OLF_OK;
 }
 
+// ---- C5 micro-benchmark support (BASELINE.json configs[4]) -----------------------------------------------------------
+// Integer-pipe ceiling for the all-pairs Hamming kernel: independent xor + popc + add chains, the instruction mix of one
+// 32-bit word of a descriptor pair.  popc_ops = word-pairs per second the chip sustains when nothing else is in the way.
+__global__ void __launch_bounds__(256) k_popc_peak(unsigned* __restrict__ out, int iters) {
+    unsigned a0 = threadIdx.x * 2654435761u + blockIdx.x, a1 = a0 ^ 0x9e3779b9u, a2 = a0 + 0x7f4a7c15u, a3 = ~a0;
+    unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+    for (int i = 0; i < iters; ++i) {
+        const unsigned k = (unsigned)i * 0x01000193u;
+        s0 += __popc(a0 ^ k); s1 += __popc(a1 ^ k); s2 += __popc(a2 ^ k); s3 += __popc(a3 ^ k);
+        s4 += __popc(a0 ^ ~k); s5 += __popc(a1 ^ ~k); s6 += __popc(a2 ^ ~k); s7 += __popc(a3 ^ ~k);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
+}
+// kernel-only time of the knn2 pair (partial + merge) on device-resident random descriptors, and the measured popc ceiling
+int knn2_bench(int n1, int n2, int iters, int device, double* kernel_ms, double* popc_word_pairs_per_s) {
+    if (n1 < 1 || n2 < 2 || iters < 1 || !kernel_ms || !popc_word_pairs_per_s) return OLF_ERR_ARG;
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    int splits, per; knn_splits(n1, n2, &splits, &per);
+    Planner pl;
+    const size_t o_q = pl.d((size_t)n1 * 32), o_t = pl.d((size_t)n2 * 32), o_part = pl.d((size_t)splits * n1 * sizeof(Knn2)), o_out = pl.d((size_t)4 * n1 * 4);
+    const size_t o_pk = pl.d((size_t)148 * 8 * 256 * 4);
+    const size_t p_q = pl.p((size_t)std::max(n1, n2) * 32);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->cur;
+    uint32_t x = 12345u;
+    uint32_t* h = hptr<uint32_t>(c, p_q);
+    for (size_t i = 0; i < (size_t)std::max(n1, n2) * 8; ++i) { x = x * 1664525u + 1013904223u; h[i] = x ^ (x >> 13); }
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_q), h, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_t), h, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    cudaEvent_t e0, e1;
+    OLF_CUDA(cudaEventCreate(&e0)); OLF_CUDA(cudaEventCreate(&e1));
+    int* o = dptr<int>(c, o_out);
+    for (int w = 0; w < 3; ++w) launch_knn2(s, dptr<uint4>(c, o_q), n1, dptr<uint4>(c, o_t), n2, dptr<Knn2>(c, o_part), o, o + n1, o + 2 * n1, o + 3 * n1, splits, per);
+    OLF_CUDA(cudaEventRecord(e0, s));
+    for (int w = 0; w < iters; ++w) launch_knn2(s, dptr<uint4>(c, o_q), n1, dptr<uint4>(c, o_t), n2, dptr<Knn2>(c, o_part), o, o + n1, o + 2 * n1, o + 3 * n1, splits, per);
+    OLF_CUDA(cudaEventRecord(e1, s));
+    OLF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; OLF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *kernel_ms = ms / iters;
+    const int pk_iters = 20000, pk_blocks = 148 * 8;
+    k_popc_peak<<<pk_blocks, 256, 0, s>>>(dptr<unsigned>(c, o_pk), 100);
+    OLF_CUDA(cudaEventRecord(e0, s));
+    k_popc_peak<<<pk_blocks, 256, 0, s>>>(dptr<unsigned>(c, o_pk), pk_iters);
+    OLF_CUDA(cudaEventRecord(e1, s));
+    OLF_CUDA(cudaEventSynchronize(e1));
+    OLF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *popc_word_pairs_per_s = (double)pk_blocks * 256 * 8.0 * pk_iters / (ms * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    OLF_CUDA(cudaGetLastError());
+    return OLF_OK;
+}
+
 int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int mutual, int* m12, int* nmatches, int device) {
     if (n1 < 0 || n2 < 0 || (n1 && !d1) || (n2 && !d2) || !nmatches) { set_last_error("olf_match: bad arguments"); return OLF_ERR_ARG; }
     MatchCtx* c; int rc;
@@ -603,6 +656,92 @@ int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_key
     return OLF_OK;
 }
 
+// ---- matchGrid(lines) as a stand-alone entry (src/LineMatcher.cpp:220-299) for callers that build the GridStructure
+// themselves (the reference's Frame::ComputeStereoMatches_Lines, src/Frame.cc:896-927): grid cells -> per right line cell list,
+// the candidate test with a general GridWindow, then the same passes as olf_stereo_lines.
+__global__ void __launch_bounds__(256) k_lines_cand_grid(const int4* __restrict__ l1, const uint32_t* __restrict__ dl, int n1,
+                                                         const uint32_t* __restrict__ dr, int n2, const double2* __restrict__ dir2,
+                                                         const short2* __restrict__ cells, const int* __restrict__ ncells, int rows, int cols,
+                                                         int4 win /* width.first, width.second, height.first, height.second */, double sim_th, int* __restrict__ cand) {
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y;
+    if (i2 >= n2) return;
+    const int4 L = l1[i1];
+    // GridStructure::get (src/gridStructure.cpp:68-79): x in [max(0,x-w.first), min(cols, x+w.second+1)), same for y
+    const int ax0 = max(0, L.x - win.x), ax1 = min(cols, L.x + win.y + 1), ay0 = max(0, L.y - win.z), ay1 = min(rows, L.y + win.w + 1);
+    const int bx0 = max(0, L.z - win.x), bx1 = min(cols, L.z + win.y + 1), by0 = max(0, L.w - win.z), by1 = min(rows, L.w + win.w + 1);
+    bool in = false;
+    const int nc = ncells[i2];
+    for (int c = 0; c < nc && !in; ++c) {
+        const short2 p = cells[(size_t)i2 * LCELLS + c];
+        in = (p.x >= ax0 && p.x < ax1 && p.y >= ay0 && p.y < ay1) || (p.x >= bx0 && p.x < bx1 && p.y >= by0 && p.y < by1);
+    }
+    int d = -1;
+    if (in) {
+        double vx = (double)(L.z - L.x), vy = (double)(L.w - L.y);
+        const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+        vx = __ddiv_rn(vx, mag); vy = __ddiv_rn(vy, mag);
+        const double2 o = dir2[i2];
+        const double dot = __dadd_rn(__dmul_rn(vx, o.x), __dmul_rn(vy, o.y));
+        if (!(fabs(dot) < sim_th)) d = hamming256(dl + (size_t)i1 * 8, dr + (size_t)i2 * 8);
+    }
+    cand[(size_t)i1 * n2 + i2] = d;
+}
+__global__ void k_lines_mutual(int* __restrict__ m12, const int* __restrict__ m21, int n1, int mutual) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i1 >= n1) return;
+    const int i2 = m12[i1];
+    if (mutual && i2 >= 0 && m21[i2] != i1) m12[i1] = -1;
+}
+int match_grid_lines(const int* lines1, const uint8_t* desc1, int n1, const olf_grid_csr* grid, const uint8_t* desc2, int n2, const double* dir2,
+                     const int* window, const olf_line_match_params* P, int* matches12, int* nmatches, int device) {
+    if (!P || !grid || !window || !nmatches || n1 < 0 || n2 < 0 || grid->rows <= 0 || grid->cols <= 0 || !grid->cell_begin ||
+        (n1 && (!lines1 || !desc1 || !matches12)) || (n2 && (!desc2 || !dir2))) { set_last_error("olf_match_grid_lines: bad arguments"); return OLF_ERR_ARG; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    *nmatches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return OLF_OK;
+    Planner pl;
+    const size_t o_l1 = pl.d((size_t)n1 * 16), o_dl = pl.d((size_t)n1 * 32), o_dr = pl.d((size_t)n2 * 32), o_dir = pl.d((size_t)n2 * 16);
+    const size_t o_cells = pl.d((size_t)n2 * LCELLS * sizeof(short2)), o_nc = pl.d((size_t)n2 * 4), o_cand = pl.d((size_t)n1 * n2 * 4), o_m12 = pl.d((size_t)n1 * 4), o_m21 = pl.d((size_t)n2 * 4);
+    const size_t p_l1 = pl.p((size_t)n1 * 16), p_dl = pl.p((size_t)n1 * 32), p_dr = pl.p((size_t)n2 * 32), p_dir = pl.p((size_t)n2 * 16);
+    const size_t p_cells = pl.p((size_t)n2 * LCELLS * sizeof(short2)), p_nc = pl.p((size_t)n2 * 4), p_m = pl.p((size_t)n1 * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->cur;
+    memcpy(hptr<uint8_t>(c, p_l1), lines1, (size_t)n1 * 16); memcpy(hptr<uint8_t>(c, p_dl), desc1, (size_t)n1 * 32);
+    memcpy(hptr<uint8_t>(c, p_dr), desc2, (size_t)n2 * 32); memcpy(hptr<uint8_t>(c, p_dir), dir2, (size_t)n2 * 16);
+    // cell lists per right line from the grid (an index outside [0, n2) is never a candidate, :256)
+    short2* hc = hptr<short2>(c, p_cells); int* hn = hptr<int>(c, p_nc);
+    for (int i = 0; i < n2; ++i) hn[i] = 0;
+    for (int x = 0; x < grid->cols; ++x)
+        for (int y = 0; y < grid->rows; ++y) {
+            const int cell = x * grid->rows + y;
+            for (int k = grid->cell_begin[cell]; k < grid->cell_begin[cell + 1]; ++k) {
+                const int i2 = grid->items[k];
+                if (i2 < 0 || i2 >= n2) continue;
+                if (hn[i2] >= LCELLS) { set_last_error("olf_match_grid_lines: a line covers more than 128 grid cells"); return OLF_ERR_CAPACITY; }
+                hc[(size_t)i2 * LCELLS + hn[i2]++] = make_short2((short)x, (short)y);
+            }
+        }
+    auto up = [&](size_t od, size_t op, size_t bytes) { return cudaMemcpyAsync(dptr<uint8_t>(c, od), hptr<uint8_t>(c, op), bytes, cudaMemcpyHostToDevice, s); };
+    OLF_CUDA(up(o_l1, p_l1, (size_t)n1 * 16)); OLF_CUDA(up(o_dl, p_dl, (size_t)n1 * 32)); OLF_CUDA(up(o_dr, p_dr, (size_t)n2 * 32)); OLF_CUDA(up(o_dir, p_dir, (size_t)n2 * 16));
+    OLF_CUDA(up(o_cells, p_cells, (size_t)n2 * LCELLS * sizeof(short2))); OLF_CUDA(up(o_nc, p_nc, (size_t)n2 * 4));
+    k_lines_cand_grid<<<dim3((n2 + 255) / 256, n1), 256, 0, s>>>(dptr<int4>(c, o_l1), dptr<uint32_t>(c, o_dl), n1, dptr<uint32_t>(c, o_dr), n2, dptr<double2>(c, o_dir),
+                                                                 dptr<short2>(c, o_cells), dptr<int>(c, o_nc), grid->rows, grid->cols,
+                                                                 make_int4(window[0], window[1], window[2], window[3]), P->line_sim_th, dptr<int>(c, o_cand));
+    if (P->best_lr_matches) k_lines_pass<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_cand), n1, n2, dptr<int>(c, o_m21));
+    k_lines_best<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_cand), n1, n2, P->min_ratio_12_l, dptr<int>(c, o_m12));
+    k_lines_mutual<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_m12), dptr<int>(c, o_m21), n1, P->best_lr_matches);
+    count_launches(P->best_lr_matches ? 4 : 3);
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_m), dptr<int>(c, o_m12), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(stream_sync(s));
+    int cnt = 0;
+    for (int i = 0; i < n1; ++i) { matches12[i] = hptr<int>(c, p_m)[i]; cnt += matches12[i] >= 0; }
+    *nmatches = cnt;
+    return OLF_OK;
+}
+
 // ======================================================================================================
 // ORBmatcher::SearchByProjection: candidate lists (warp per query) + fixed-point resolution of the blocking rule
 // ======================================================================================================
@@ -797,7 +936,7 @@ int search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int
         else { Q.min_level = oct - 1; Q.max_level = oct + 1; }
         Q.valid = 1;
     }
-    if ((rc = sbp_common(c, q, a->last_point_desc, a->last_point_observed, nullptr, a->cur_kps, a->cur_desc, a->cur_u_right, a->n_cur, a->cam, 0, OLF_TH_HIGH, 0.f, assigned_cur))) return rc;
+    if ((rc = sbp_common(c, q, a->last_point_desc, a->last_point_observed, a->cur_occupied, a->cur_kps, a->cur_desc, a->cur_u_right, a->n_cur, a->cam, 0, OLF_TH_HIGH, 0.f, assigned_cur))) return rc;
     // bookkeeping of the reference on the resolved assignments (:1564-1615): last writer wins, rotation histogram pruning
     int nmatches = 0;
     std::vector<int> rot[OLF_HISTO_LENGTH];

@@ -9,6 +9,7 @@ struct OrbImpl;
 // the calling thread's next matcher calls run on `s` (nullptr: back to the thread's own stream)
 void match_use_stream(cudaStream_t s);
 int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0, int* dist0, int* idx1, int* dist1, int device);
+int knn2_bench(int n1, int n2, int iters, int device, double* kernel_ms, double* popc_word_pairs_per_s);
 int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int mutual, int* m12, int* nmatches, int device);
 int stereo_points(OrbImpl* left, OrbImpl* right, const olf_keypoint* kl, const uint8_t* dl, int N, const olf_keypoint* kr, const uint8_t* dr, int Nr,
                   float bf, float fx, float* uRight, float* depth);
@@ -20,6 +21,8 @@ void stereo_ws_release(StereoWs* ws);
 int stereo_points_enqueue(StereoWs* ws, OrbImpl* left, OrbImpl* right, float bf, float fx, int cap, cudaStream_t s);
 int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_keyline* kr, const uint8_t* dr, int n2, int img_w, int img_h,
                  const olf_line_match_params* P, int* matches12, float* disp, double* le, int device);
+int match_grid_lines(const int* lines1, const uint8_t* desc1, int n1, const olf_grid_csr* grid, const uint8_t* desc2, int n2, const double* dir2,
+                     const int* window, const olf_line_match_params* P, int* matches12, int* nmatches, int device);
 int search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device);
 int search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches, int device);
 struct VocabImpl;

@@ -1,11 +1,15 @@
 #include "LineMatcher.h"
 #include "ORBextractor.h"
+#include "Frame.h"
+#include <climits>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
 
 namespace ORB_SLAM2 {
 olf_line_match_params OlfConfig::line_match = {1, 0.9, 0.75, 10, 1.0, 0.1, 0.75, 0.7};
 int OlfConfig::device = 0;
+double OlfConfig::min_ratio_12_p = 0.75;         // Config::minRatio12P() (src/Config.cpp:56)
 
 static std::vector<uint8_t> pack(const cv::Mat& d) {
     std::vector<uint8_t> v((size_t)d.rows * 32);
@@ -27,6 +31,58 @@ int match(const cv::Mat& desc1, const cv::Mat& desc2, float nnr, std::vector<int
     if (olf_match_lines(a.data(), desc1.rows, b.data(), desc2.rows, nnr, OlfConfig::line_match.best_lr_matches, matches_12.data(), &n, OlfConfig::device) != OLF_OK)
         throw std::runtime_error(std::string("[match] ") + olf_last_error());
     return n;
+}
+int match(const std::vector<MapLine*>& mvpLocalMapLines, Frame& CurrentFrame, float nnr, std::vector<int>& matches_12) {
+    std::vector<uint8_t> a((size_t)mvpLocalMapLines.size() * 32);
+    for (size_t i = 0; i < mvpLocalMapLines.size(); ++i) { const cv::Mat d = mvpLocalMapLines[i]->GetDescriptor(); memcpy(a.data() + i * 32, d.ptr(0), 32); }
+    const std::vector<uint8_t> b = pack(CurrentFrame.mDescriptors_Line);
+    matches_12.assign(mvpLocalMapLines.size(), -1);
+    int n = 0;
+    if (olf_match_nnr(a.data(), (int)mvpLocalMapLines.size(), b.data(), CurrentFrame.mDescriptors_Line.rows, nnr, matches_12.data(), &n, OlfConfig::device) != OLF_OK)
+        throw std::runtime_error(std::string("[matchNNR] ") + olf_last_error());
+    return n;
+}
+int matchGrid(const std::vector<line_2d>& lines1, const cv::Mat& desc1, const GridStructure& grid, const cv::Mat& desc2,
+              const std::vector<std::pair<double, double>>& directions2, const GridWindow& w, std::vector<int>& matches_12) {
+    if ((int)lines1.size() != desc1.rows) throw std::runtime_error("[matchGrid] Each line needs a corresponding descriptor!");     // :224-225
+    matches_12.resize(desc1.rows, -1);
+    const int n1 = desc1.rows, n2 = desc2.rows;
+    std::vector<int> l1((size_t)n1 * 4), begin(1, 0), items;
+    for (int i = 0; i < n1; ++i) { l1[4 * i] = lines1[i].first.first; l1[4 * i + 1] = lines1[i].first.second; l1[4 * i + 2] = lines1[i].second.first; l1[4 * i + 3] = lines1[i].second.second; }
+    GridStructure& g = const_cast<GridStructure&>(grid);
+    for (int x = 0; x < grid.cols; ++x)
+        for (int y = 0; y < grid.rows; ++y) { const std::list<int>& c = g.at(x, y); items.insert(items.end(), c.begin(), c.end()); begin.push_back((int)items.size()); }
+    std::vector<double> dir((size_t)n2 * 2);
+    for (int i = 0; i < n2 && i < (int)directions2.size(); ++i) { dir[2 * i] = directions2[i].first; dir[2 * i + 1] = directions2[i].second; }
+    const olf_grid_csr csr = {grid.rows, grid.cols, begin.data(), items.data()};
+    const int win[4] = {w.width.first, w.width.second, w.height.first, w.height.second};
+    const std::vector<uint8_t> a = pack(desc1), b = pack(desc2);
+    int n = 0;
+    if (olf_match_grid_lines(l1.data(), a.data(), n1, &csr, b.data(), n2, dir.data(), win, &OlfConfig::line_match, matches_12.data(), &n, OlfConfig::device) != OLF_OK)
+        throw std::runtime_error(std::string("[matchGrid] ") + olf_last_error());
+    return n;
+}
+int matchGrid(const std::vector<point_2d>& points1, const cv::Mat& desc1, const GridStructure& grid, const cv::Mat& desc2, const GridWindow& w, std::vector<int>& matches_12) {
+    if ((int)points1.size() != desc1.rows) throw std::runtime_error("[matchGrid] Each point needs a corresponding descriptor!");
+    // host loop (the reference never calls this overload on the per-frame path); candidates in ascending index
+    const bool lr = OlfConfig::line_match.best_lr_matches != 0;
+    matches_12.resize(desc1.rows, -1);
+    std::vector<int> m21(lr ? desc2.rows : 0, -1), dist(lr ? desc2.rows : 0, INT_MAX);
+    int matches = 0;
+    for (int i1 = 0; i1 < desc1.rows; ++i1) {
+        std::unordered_set<int> cs; grid.get(points1[i1].first, points1[i1].second, w, cs);
+        std::vector<int> cand(cs.begin(), cs.end()); std::sort(cand.begin(), cand.end());
+        int bd = INT_MAX, bd2 = INT_MAX, bi = -1;
+        for (int i2 : cand) {
+            if (i2 < 0 || i2 >= desc2.rows) continue;
+            const int d = distance(desc1.row(i1), desc2.row(i2));
+            if (lr) { if (d < dist[i2]) { dist[i2] = d; m21[i2] = i1; } else continue; }
+            if (d < bd) { bd2 = bd; bd = d; bi = i2; } else if (d < bd2) bd2 = d;
+        }
+        if (bi >= 0 && bd < bd2 * OlfConfig::min_ratio_12_p) { matches_12[i1] = bi; matches++; }
+    }
+    if (lr) for (int i1 = 0; i1 < desc1.rows; ++i1) { int& i2 = matches_12[i1]; if (i2 >= 0 && m21[i2] != i1) { i2 = -1; matches--; } }
+    return matches;
 }
 int distance(const cv::Mat& a, const cv::Mat& b) {               // src/LineMatcher.cpp:134-150 (host: single pair)
     const uint32_t* pa = a.ptr<uint32_t>(); const uint32_t* pb = b.ptr<uint32_t>();

@@ -16,8 +16,9 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 }
 ORBextractor::~ORBextractor() { olf_orb_destroy(h_); }
 
-void ORBextractor::operator()(cv::InputArray image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors) {
-    if (image.empty()) return;                                   // src/ORBextractor.cc:1048
+void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray _descriptors) {
+    if (_image.empty()) return;                                  // src/ORBextractor.cc:1048
+    cv::Mat image = _image.getMat();                             // :1051
     assert(image.type() == CV_8UC1);                             // :1052
     const int cap = nfeatures + nfeatures / 4 + 512;             // the quadtree may return a few more than nfeatures
     std::vector<olf_keypoint> kps(cap);
@@ -26,8 +27,9 @@ void ORBextractor::operator()(cv::InputArray image, cv::InputArray /*mask*/, std
     const int rc = olf_orb_extract(h_, image.ptr(), image.cols, image.rows, (int)image.step, kps.data(), desc.data(), cap, &n);
     if (rc != OLF_OK) throw std::runtime_error(std::string("[ORBextractor] ") + olf_last_error());
     keypoints.clear(); keypoints.reserve(n);
-    if (n == 0) { descriptors.release(); return; }               // :1066-1067
-    descriptors.create(n, 32, CV_8U);                            // :1070
+    if (n == 0) { _descriptors.release(); return; }              // :1066-1067
+    _descriptors.create(n, 32, CV_8U);                           // :1070
+    cv::Mat descriptors = _descriptors.getMat();                 // :1071
     for (int i = 0; i < n; ++i) {
         cv::KeyPoint kp;
         kp.pt.x = kps[i].x; kp.pt.y = kps[i].y; kp.size = kps[i].size; kp.angle = kps[i].angle;

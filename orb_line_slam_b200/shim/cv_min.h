@@ -1,7 +1,10 @@
 // Minimal stand-in for the handful of OpenCV types that appear in the reference's front-end class surfaces
 // (cv::Mat, cv::KeyPoint, cv::Point2f, cv::InputArray/OutputArray, cv::line_descriptor::KeyLine).  Used ONLY when the
 // shim is built without OpenCV (this image has no OpenCV C++); define OLF_HAVE_OPENCV to compile the very same shim
-// sources against the real headers inside the reference tree.
+// sources against the real headers inside the reference tree.  InputArray / OutputArray are proxy classes with the real
+// ones' semantics (getMat(), create(), release(), empty()) so that the shim sources use exactly the calls that exist on
+// cv::_InputArray / cv::_OutputArray (the reference does `Mat image = _image.getMat()`, `_descriptors.create(n,32,CV_8U)`,
+// src/ORBextractor.cc:1051,1070).
 #pragma once
 #ifdef OLF_HAVE_OPENCV
 #include <opencv2/core/core.hpp>
@@ -27,6 +30,7 @@ public:
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(int r, int c, int type, void* ext, size_t step_) : rows(r), cols(c), step(step_), data((uchar*)ext), type_(type) {}
     void create(int r, int c, int type) {
+        if (data && buf_ && rows == r && cols == c && type_ == type) return;
         type_ = type; rows = r; cols = c; step = (size_t)c * elem();
         buf_ = std::make_shared<std::vector<uchar>>((size_t)r * step);
         data = buf_->data();
@@ -48,8 +52,26 @@ private:
     int type_ = CV_8UC1;
     std::shared_ptr<std::vector<uchar>> buf_;
 };
-typedef const Mat& InputArray;
-typedef Mat& OutputArray;
+class _InputArray {
+public:
+    _InputArray() {}
+    _InputArray(const Mat& m) : m_(&m) {}
+    Mat getMat(int = -1) const { return m_ ? *m_ : Mat(); }
+    bool empty() const { return !m_ || m_->empty(); }
+protected:
+    const Mat* m_ = nullptr;
+};
+class _OutputArray : public _InputArray {
+public:
+    _OutputArray() {}
+    _OutputArray(Mat& m) : _InputArray(m), w_(&m) {}
+    void create(int rows, int cols, int type) const { if (w_) w_->create(rows, cols, type); }
+    void release() const { if (w_) w_->release(); }
+private:
+    Mat* w_ = nullptr;
+};
+typedef const _InputArray& InputArray;
+typedef const _OutputArray& OutputArray;
 namespace line_descriptor {
 struct KeyLine {                       // Thirdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp:105-145
     float angle; int class_id; int octave; Point2f pt; float response; float size;

@@ -13,7 +13,7 @@ SHIM = ROOT / "orb_line_slam_b200" / "shim"
 
 def build_shim_test():
     exe = ROOT / "tests" / "shim" / "_test_shim"
-    srcs = [ROOT / "tests" / "shim" / "test_shim.cpp", SHIM / "ORBextractor.cc", SHIM / "LineExtractor.cc", SHIM / "LineMatcher.cc"]
+    srcs = [ROOT / "tests" / "shim" / "test_shim.cpp"] + [SHIM / f for f in ("ORBextractor.cc", "LineExtractor.cc", "LineMatcher.cc", "ORBmatcher_hot.cc", "FrameStereo.cc")]
     cmd = ["g++", "-std=c++17", "-O2", "-o", str(exe), *map(str, srcs), "-L" + str(ROOT / "orb_line_slam_b200"), "-lolf",
            "-Wl,-rpath," + str(ROOT / "orb_line_slam_b200")]
     subprocess.run(cmd, check=True)
@@ -31,21 +31,53 @@ def test_shim_compiles_and_links():
     assert build_shim_test().exists()
 
 
+def test_shim_compiles_against_opencv_shaped_headers():
+    """-DOLF_HAVE_OPENCV: the same shim sources against headers with the REAL proxy semantics of cv::_InputArray /
+    _OutputArray (no ptr()/cols on them, getMat()/create() only) and the reference's own KeyLine declaration -- the stand-in
+    tree oracle/_ref/inc + the reference's line_descriptor header (needs /root/reference, so this runs in the build container)."""
+    ref = pathlib.Path("/root/reference")
+    if not ref.exists():
+        pytest.skip("/root/reference not present")
+    subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref"], check=True, capture_output=True)
+    inc = ["-I" + str(ROOT / "oracle" / "_ref" / "inc"), "-I" + str(ROOT / "oracle" / "ref_harness"), "-I" + str(ref / "Thirdparty/line_descriptor/include"), "-I" + str(ROOT / "include")]
+    for f in ("ORBextractor.cc", "LineExtractor.cc", "LineMatcher.cc", "ORBmatcher_hot.cc", "FrameStereo.cc"):
+        subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-DOLF_HAVE_OPENCV", *inc, str(SHIM / f)], check=True)
+
+
 @pytest.mark.gpu
 def test_shim_equals_abi(tmp_path):
+    from orb_line_slam_b200.synth import pose_f32
     exe = build_shim_test()
     sc = Scene("euroc", 3)
-    L, R = sc.stereo(0)
-    (tmp_path / "l.raw").write_bytes(L.tobytes()); (tmp_path / "r.raw").write_bytes(R.tobytes())
-    out = subprocess.run([str(exe), "640", "480", str(tmp_path / "l.raw"), str(tmp_path / "r.raw")], capture_output=True, text=True, check=True).stdout
+    (L0, R0), (L1, R1) = sc.stereo(0), sc.stereo(1)
+    for n, im in (("l0", L0), ("r0", R0), ("l1", L1), ("r1", R1)):
+        (tmp_path / f"{n}.raw").write_bytes(im.tobytes())
+    fe = FrontEnd(olf.api(0), CAMERAS["euroc"], 1000, 200)
+    last = fe.process(L0, R0, pose_f32(0)); cur = fe.process(L1, R1, pose_f32(1))
+    args, keep = fe.sbp_last_args(cur, last, 7.0)
+    a_last, c_last, n_last = fe.api.search_by_projection_last(args, keep)
+    margs, mkeep = fe.sbp_map_args(cur, last, 1.0, 0.8)
+    a_map, n_map = fe.api.search_by_projection_map(margs, mkeep)
+    pose = np.concatenate([np.asarray(cur.Rcw, np.float32).ravel(), np.asarray(cur.tcw, np.float32), np.asarray(last.Rcw, np.float32).ravel(), np.asarray(last.tcw, np.float32)]).astype(np.float32)
+    (tmp_path / "pose.f32").write_bytes(pose.tobytes()); (tmp_path / "has.u8").write_bytes(keep["has"].tobytes()); (tmp_path / "world.f32").write_bytes(keep["world"].tobytes())
+    mp = np.stack([mkeep["px"], mkeep["py"], mkeep["pxr"], mkeep["lvl"].astype(np.float32), mkeep["vc"]], 1).astype(np.float32)
+    (tmp_path / "map.f32").write_bytes(np.ascontiguousarray(mp).tobytes()); (tmp_path / "mapdesc.u8").write_bytes(np.ascontiguousarray(mkeep["pdesc"]).tobytes())
+    out = subprocess.run([str(exe), "640", "480", str(tmp_path)], capture_output=True, text=True, check=True).stdout
     assert "EXCEPTION" not in out, out
     v = dict(re.findall(r"(\w+) (\d+)", out))
-    fe = FrontEnd(olf.api(0), CAMERAS["euroc"], 1000, 200)
-    f = fe.process(L, R)
-    m, nm = fe.api.match_lines(f.ldesc, f.ldesc_r, 0.9, True)
+    f = last
     assert int(v["nL"]) == len(f.kps) and int(v["nR"]) == len(f.kps_r) and int(v["mL"]) == len(f.kls) and int(v["mR"]) == len(f.kls_r)
     assert int(v["desc"]) == fnv(f.desc.tobytes()) and int(v["ldesc"]) == fnv(f.ldesc.tobytes())
     assert int(v["uright"]) == fnv(f.u_right.tobytes()) and int(v["disp"]) == fnv(np.ascontiguousarray(f.line_disp).tobytes())
-    assert re.search(r"match (\d+) (\d+)", out).groups() == (str(nm), str(fnv(m.tobytes())))
     assert "pyr7 179x134" in out and int(v["levels"]) == 8
+    two = lambda key: re.search(key + r" (-?\d+) (\d+)", out).groups()
+    # matchGrid through the host GridStructure == the raw matchGrid output of the fused stereo-line entry
+    assert two("matchgrid") == (str(int((f.line_matches >= 0).sum())), str(fnv(np.ascontiguousarray(f.line_matches).tobytes())))
+    assert two("sbplast") == (str(n_last), str(fnv(c_last.tobytes()))) and n_last > 20
+    assert two("sbpmap") == (str(n_map), str(fnv(a_map.tobytes()))) and n_map > 20
+    m, nm = fe.api.match_lines(last.ldesc, cur.ldesc, 0.9, True)
+    assert two("match") == (str(nm), str(fnv(m.tobytes())))
+    m2, nm2 = fe.api.match_nnr(last.ldesc, cur.ldesc, 0.9)
+    assert two("matchmaplines") == (str(nm2), str(fnv(m2.tobytes())))
+    assert "distance 0" in out
     fe.close()
