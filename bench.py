@@ -132,6 +132,7 @@ class StepRunner:
         lock = threading.Lock()
         stats = {"matches": 0, "line_matches": 0, "kps": 0, "lines": 0, "d2h": 0}
         errors = []
+        calls = [[] for _ in range(P)]                    # per rig: (start, end, wait-for-ring) of every batch call, seconds
 
         def consumer_done(s):
             with lock:
@@ -148,10 +149,12 @@ class StepRunner:
             try:
                 nat = self.pipes[p]
                 for s in range(nsteps):
+                    tw = time.perf_counter()
                     if s >= RING:
                         released[s - RING].wait()
                     if errors:
                         return
+                    tc = time.perf_counter()
                     ks = [(s * P + p) * B + j for j in range(B)]
                     idx = [(first + k) % nseq for k in ks]
                     blks = [self.block(k) for k in ks]
@@ -159,6 +162,7 @@ class StepRunner:
                         nat.process_batch([self.dev_ptrs[i][0] for i in idx], [self.dev_ptrs[i][1] for i in idx], blks, on_device=True)
                     else:
                         nat.process_batch([self.host_imgs[i][0] for i in idx], [self.host_imgs[i][1] for i in idx], blks, on_device=False)
+                    calls[p].append((tc, time.perf_counter(), tc - tw))
                     for k, i, blk in zip(ks, idx, blks):
                         views[k] = nat.view(blk, self.poses[i])
                         done[k].set()
@@ -230,6 +234,12 @@ class StepRunner:
             t.join()
         if errors:
             raise errors[0]
+        # how steady the rigs ran: duration of the batch calls, time between calls (host glue), time spent waiting for a ring slot
+        dur = np.array([e - b for c in calls for (b, e, w) in c]); wait = np.array([w for c in calls for (b, e, w) in c])
+        gap = np.array([c[i + 1][0] - c[i][1] - c[i + 1][2] for c in calls for i in range(len(c) - 1)] or [0.0])
+        stats["call_ms"] = dict(p50=round(float(np.percentile(dur, 50)) * 1e3, 1), p99=round(float(np.percentile(dur, 99)) * 1e3, 1), max=round(float(dur.max()) * 1e3, 1))
+        stats["gap_ms"] = dict(p50=round(float(np.percentile(gap, 50)) * 1e3, 2), max=round(float(gap.max()) * 1e3, 1))
+        stats["ring_wait_ms"] = dict(total=round(float(wait.sum()) * 1e3, 1), max=round(float(wait.max()) * 1e3, 1))
         return stats
 
 
@@ -446,11 +456,18 @@ def main():
     grow_us = []
     stats8 = (ctypes.c_int * 8)()
     lib.olf_frontend_line.restype = ctypes.c_void_p
+    host_us = []
+    for nat in pipes:
+        t8 = (ctypes.c_int * 8)()
+        if lib.olf_frontend_last_timing(nat.handle, t8) == 0:
+            host_us.append(list(t8))
+    line_us = []
     if wl["has_lines"]:
         for nat in pipes:
             lh = lib.olf_frontend_line(nat.handle, 0)              # slot 0 carries the timing of the rig's batched chain
             if lh and lib.olf_line_last_stats(ctypes.c_void_p(lh), stats8) == 0:
                 grow_us.append(stats8[3] / max(stats8[4], 1))       # device time of the batched chain / images in it
+                line_us.append([stats8[5], stats8[6], stats8[7]])
     if rank == 0:
         peaks = load_peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -463,9 +480,14 @@ def main():
                 "config": dict(wl, step="one olf_frontend_process_batch call on every rig", pipelines_per_gpu=P, frames_per_call=B, frames_per_step=fps_step,
                                frames_timed_per_gpu=nframes, trackers=T, prewarm_steps=args.prewarm_steps,
                                l2=f"inputs larger than L2: {N_DISTINCT} distinct stereo pairs = {N_DISTINCT * 2 * w * h / 1e6:.0f} MB cycled",
-                               host_cores=cores, per_frame={k: v / max(nframes, 1) for k, v in st.items()},
+                               host_cores=cores, per_frame={k: v / max(nframes, 1) for k, v in st.items() if not isinstance(v, dict)},
+                               steadiness=dict(resident={k: v for k, v in st.items() if isinstance(v, dict)}, e2e={k: v for k, v in st_e2e.items() if isinstance(v, dict)}),
                                exchange=(None if dist is None else f"NCCL all_gather of {fps_step} result blocks x {runner.nbytes} B per rank per step"),
-                               gather_verified=runner.gather_checked),
+                               gather_verified=runner.gather_checked,
+                               rig_call_ms=(None if not host_us else dict(zip(("orb_enqueue", "lines", "orb_wait", "collect", "stereo_lines", "total"),
+                                                                              [round(float(v) / 1000, 2) for v in np.mean(np.array(host_us)[:, :6], 0)]))),
+                               line_call_ms=(None if not line_us else dict(zip(("enqueue_and_chain", "rect", "keylines_lbd"),
+                                                                               [round(float(v) / 1000, 2) for v in np.mean(np.array(line_us), 0)])))),
                 "clocks": clocks,
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * w * h * fps_step,
                         "d2h_bytes_per_step": int(st_e2e["d2h"] / max(args.steps, 1)), "ms_per_step": ms_e2e / args.steps},

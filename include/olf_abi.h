@@ -217,6 +217,12 @@ typedef struct olf_sbp_map_args {
 } olf_sbp_map_args;
 int olf_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur /*n_points*/, int* nmatches, int device);
 
+/* ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:254-322) and MapLine::ComputeDistinctiveDescriptors
+ * (src/MapLine.cc:257-322), batched: landmark g owns the observed descriptors desc[group_begin[g] .. group_begin[g+1]) (the rows
+ * pKF->mDescriptors.row(idx) of its non-bad observations, in the order of its observation map); best[g] = index inside the group
+ * of the descriptor with the least median Hamming distance to all of them (first on ties), -1 for an empty group. */
+int olf_distinctive_descriptors(const uint8_t* desc, const int* group_begin, int n_groups, int* best, int device);
+
 /* ---- next row: bag of words -- Frame::ComputeBoW (src/Frame.cc:585-597) and ORBmatcher::SearchByBoW -------- */
 /* DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h) flattened: node 0 is the
  * root; the children of node i are children[child_begin[i] .. child_begin[i] + child_count[i]) in the order of
@@ -303,8 +309,11 @@ int  olf_frontend_process_batch(olf_frontend* h, const uint8_t* const* img_l, co
 /* the extractors of the rig, slot = 2 * frame_in_batch + eye (e.g. for olf_orb_get_level) */
 olf_orb*  olf_frontend_orb(olf_frontend* h, int slot);
 olf_line* olf_frontend_line(olf_frontend* h, int slot);
+/* host view of the last olf_frontend_process(_batch) call, microseconds: [0] ORB + stereo-point enqueue, [1] line extraction (blocking),
+ * [2] wait for the ORB chain, [3] copy-out, [4] stereo lines, [5] whole call */
+int  olf_frontend_last_timing(const olf_frontend* h, int* out8);
 /* last-call statistics of a line extractor: out[0] LSD rounds, out[1] waves, out[2] accepted regions, out[3] device time of
- * the region-growing chain in microseconds (CUDA events on its stream), out[4] images that shared the chain */
+ * the region-growing chain in microseconds (CUDA events on its stream), out[4] images that shared the chain, out[5] host microseconds until the chain had finished (enqueue + wait), out[6] rectangle trig + second rectangle pass, out[7] KeyLine construction + LBD */
 int  olf_line_last_stats(const olf_line* h, int* out8);
 
 #ifdef __cplusplus

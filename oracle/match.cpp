@@ -472,3 +472,24 @@ extern "C" int orc_search_by_projection_map(const olf_sbp_map_args* a, int* assi
     *nmatches_out = nmatches;
     return OLF_OK;
 }
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:254-322; src/MapLine.cc:257-322 is the same on LBD descriptors):
+// full distance matrix, per row the sorted distances' element [0.5*(N-1)], the first row with the least such median wins.
+extern "C" int orc_distinctive_descriptors(const uint8_t* desc, const int* group_begin, int n_groups, int* best) {
+    for (int g = 0; g < n_groups; ++g) {
+        const int b = group_begin[g], N = group_begin[g + 1] - b;
+        if (N <= 0) { best[g] = -1; continue; }
+        std::vector<std::vector<float>> D(N, std::vector<float>(N, 0.f));
+        for (int i = 0; i < N; i++)
+            for (int j = i + 1; j < N; j++) { const int d = hamming256(desc + (size_t)(b + i) * 32, desc + (size_t)(b + j) * 32); D[i][j] = (float)d; D[j][i] = (float)d; }
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            std::vector<int> vDists(D[i].begin(), D[i].end());
+            std::sort(vDists.begin(), vDists.end());
+            const int median = vDists[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best[g] = BestIdx;
+    }
+    return 0;
+}

@@ -45,6 +45,8 @@ int orc_stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf
                      int img_w, int img_h, const olf_line_match_params* P, int* matches12, float* disp, double* le);
 int orc_search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches);
 int orc_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches);
+/* MapPoint / MapLine::ComputeDistinctiveDescriptors (src/MapPoint.cc:254-322, src/MapLine.cc:257-322), batched */
+int orc_distinctive_descriptors(const uint8_t* desc, const int* group_begin, int n_groups, int* best);
 /* bag of words (oracle/bow.cpp) */
 typedef struct orc_vocab orc_vocab;
 orc_vocab* orc_vocab_create(const olf_vocab_desc* v);

@@ -19,7 +19,7 @@ using namespace Eigen;
 
 namespace ORB_SLAM2 {
 class Map; class KeyFrameDatabase; class Frame;
-class KeyFrame { public: std::vector<float> mvLevelSigma2; };
+class KeyFrame { public: std::vector<float> mvLevelSigma2; cv::Mat mDescriptors; bool bad_ = false; bool isBad() { return bad_; } };
 class MapPoint {
 public:
     // set by Frame::isInFrustum (src/Frame.cc:436-441)
@@ -30,6 +30,9 @@ public:
     cv::Mat GetDescriptor() { return desc_.clone(); }
     cv::Mat GetWorldPos() { return pos_.clone(); }
     bool bad_ = false; int nobs_ = 1; cv::Mat desc_, pos_;
+    // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:254-322)
+    void ComputeDistinctiveDescriptors();
+    std::mutex mMutexFeatures; bool mbBad = false; std::map<KeyFrame*, size_t> mObservations; cv::Mat mDescriptor;
 };
 class MapLine {
 public:

@@ -7,7 +7,7 @@
 //   sliced (oracle/ref_harness/slice.py, verbatim function text): BinaryDescriptor ctor / computeSobel / computeImpl /
 //                 computeLBD / binaryConversion (ref_lbd.cpp); ORBmatcher::SearchByProjection (map points; last frame), RadiusByViewingCos,
 //                 ComputeThreeMaxima, DescriptorDistance; Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid /
-//                 ComputeStereoMatches / ComputeStereoMatches_Lines (+ helpers)
+//                 ComputeStereoMatches / ComputeStereoMatches_Lines (+ helpers); MapPoint::ComputeDistinctiveDescriptors
 // against the stand-in types of cvstub.hpp / frame_stub.hpp.  Un-vendored OpenCV arithmetic comes from oracle/cvprim.hpp and
 // oracle/line.cpp (pinned to cv2 4.13 by the golden vectors).
 //
@@ -48,6 +48,7 @@ const int ORBmatcher::HISTO_LENGTH = 30;
 ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
 #include "orbmatcher.inc"
 #include "frame.inc"
+#include "mappoint.inc"
 }
 
 // ---- array file protocol ------------------------------------------------------------------------------------------------
@@ -239,6 +240,20 @@ int main(int argc, char** argv) {
         std::vector<int> assigned(np, -1);
         for (int j = 0; j < F.N; ++j) if (F.mvpMapPoints[j] && F.mvpMapPoints[j] != &occupied_marker) assigned[(int)(F.mvpMapPoints[j] - pts.data())] = j;
         out.push_back(make<int>(1, {(long long)np}, assigned.data())); out.push_back(make<int>(1, {1}, &n));
+    } else if (cmd == "distinctive") {
+        // in: desc u8[total,32], group_begin i32[n+1] -> MapPoint::ComputeDistinctiveDescriptors per group: index of the chosen observation
+        Arr &d = in[0], &gb = in[1];
+        const int ng = (int)gb.count() - 1;
+        std::vector<int> best(ng, -1);
+        for (int g = 0; g < ng; ++g) {
+            const int b = gb.as<int>()[g], N = gb.as<int>()[g + 1] - b;
+            std::vector<KeyFrame> kfs(N);                         // ascending addresses: the observation map iterates in this order
+            MapPoint mp;
+            for (int i = 0; i < N; ++i) { kfs[i].mDescriptors = cv::Mat(1, 32, CV_8UC1); memcpy(kfs[i].mDescriptors.ptr(), d.as<uchar>() + (size_t)(b + i) * 32, 32); mp.mObservations[&kfs[i]] = 0; }
+            mp.ComputeDistinctiveDescriptors();
+            for (int i = 0; i < N && !mp.mDescriptor.empty(); ++i) if (!memcmp(mp.mDescriptor.ptr(), kfs[i].mDescriptors.ptr(), 32)) { best[g] = i; break; }
+        }
+        out.push_back(make<int>(1, {(long long)ng}, best.data()));
     } else { fprintf(stderr, "refcli: unknown command %s\n", cmd.c_str()); return 2; }
     write_arrays(argv[3], out);
     return 0;

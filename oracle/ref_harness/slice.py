@@ -39,6 +39,7 @@ SLICES = {
                        ("src/ORBmatcher.cc", "float ORBmatcher::RadiusByViewingCos("),
                        ("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono, map<int, int>& match12)"),
                        ("src/ORBmatcher.cc", "void ORBmatcher::ComputeThreeMaxima("), ("src/ORBmatcher.cc", "int ORBmatcher::DescriptorDistance(")],
+    "mappoint.inc": [("src/MapPoint.cc", "void MapPoint::ComputeDistinctiveDescriptors()")],
     "frame.inc": [("src/Frame.cc", "void Frame::AssignFeaturesToGrid()"), ("src/Frame.cc", "vector<size_t> Frame::GetFeaturesInArea("),
                   ("src/Frame.cc", "bool Frame::PosInGrid("), ("src/Frame.cc", "void Frame::ComputeStereoMatches()"),
                   ("src/Frame.cc", "void Frame::ComputeStereoMatches_Lines("), ("src/Frame.cc", "double Frame::lineSegmentOverlapStereo("),

@@ -297,6 +297,14 @@ class FrontEndApi:
         self.check(rc, "search_by_projection_last")
         return a, c, n.value
 
+    # ---- ComputeDistinctiveDescriptors ----
+    def distinctive_descriptors(self, desc, group_begin):
+        desc = np.ascontiguousarray(desc, np.uint8); group_begin = np.ascontiguousarray(group_begin, np.int32)
+        best = np.zeros(len(group_begin) - 1, np.int32)
+        rc = self.fn("distinctive_descriptors")(ptr(desc), ptr(group_begin), C.c_int(len(best)), ptr(best), *self._dev)
+        self.check(rc, "distinctive_descriptors")
+        return best
+
     # ---- bag of words ----
     def vocab_create(self, tree: dict):
         """tree: dict(k, L, node_desc (n,32) u8, child_begin, child_count, children, word_id (int32), weight (float64))."""

@@ -134,6 +134,7 @@ int olf_match_grid_lines(const int* lines1, const uint8_t* desc1, int n1, const 
                          const int* window, const olf_line_match_params* p, int* matches12, int* nmatches, int device) {
     return match_grid_lines(lines1, desc1, n1, grid, desc2, n2, dir2, window, p, matches12, nmatches, device);
 }
+int olf_distinctive_descriptors(const uint8_t* desc, const int* group_begin, int n_groups, int* best, int device) { return distinctive_descriptors(desc, group_begin, n_groups, best, device); }
 int olf_search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device) {
     return search_by_projection_last(a, assigned_cur, cur_point, nmatches, device);
 }

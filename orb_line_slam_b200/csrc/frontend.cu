@@ -13,6 +13,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <functional>
+#include <chrono>
 
 namespace olf {
 
@@ -50,6 +51,7 @@ struct FrontendImpl {
     Worker* worker = nullptr;            // single-frame rig only: the right eye's line extraction
     olf_frame_offsets off;
     std::string err;
+    int timing[8] = {0};                 // host view of the last call, microseconds: ORB enqueue, lines, ORB wait, collect, stereo lines, total
 };
 
 static uint64_t a64(uint64_t v) { return (v + 63) / 64 * 64; }
@@ -140,6 +142,8 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
         kls[2 * f] = (olf_keyline*)(base + o.kls_l); kls[2 * f + 1] = (olf_keyline*)(base + o.kls_r);
         ldesc[2 * f] = base + o.ldesc_l; ldesc[2 * f + 1] = base + o.ldesc_r;
     }
+    auto now = [] { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const long long t0 = now();
     // ExtractORB(0|1) of every frame + ComputeStereoMatches: one asynchronous chain on the first stream
     cudaStream_t so = orb_stream(h->orb[0]);
     int rc = orb_enqueue(h->orb.data(), nimg, img.data(), w, hgt, stride, on_device != 0, capP, so);
@@ -147,6 +151,7 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
         rc = stereo_points_enqueue(&h->sws[f], h->orb[2 * f], h->orb[2 * f + 1], h->P.cam.bf, h->P.cam.fx, capP, so);
     if (!rc && h->ev_orb.record(so) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaEventRecord", __FILE__, __LINE__);
     if (rc) { cudaStreamSynchronize(so); return rc; }
+    const long long t1 = now();
     // ExtractLine(0|1) of every frame on the second stream while the first one works
     int rc_l = OLF_OK;
     if (h->P.has_lines) {
@@ -163,8 +168,11 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
             rc_l = line_extract_batch(h->line.data(), nimg, img.data(), w, hgt, stride, on_device != 0, kls.data(), ldesc.data(), h->P.cap_lines, m.data());
     }
     const std::string err_l = rc_l ? olf_last_error() : "";
+    const long long t2 = now();
     if (h->ev_orb.wait() != cudaSuccess) return cuda_fail(cudaGetLastError(), "ORB chain", __FILE__, __LINE__);
+    const long long t3 = now();
     for (int k = 0; k < nimg && !rc; ++k) rc = orb_collect(h->orb[k], kps[k], desc[k], capP, &n[k]);
+    const long long t4 = now();
     if (!rc && rc_l) { rc = rc_l; set_last_error(err_l); }
     match_use_stream(h->P.has_lines ? line_stream(h->line[0]) : so);
     for (int f = 0; f < nframes; ++f) {
@@ -186,6 +194,8 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
         hd->status = rc;
     }
     match_use_stream(nullptr);
+    const long long t5 = now();
+    h->timing[0] = (int)(t1 - t0); h->timing[1] = (int)(t2 - t1); h->timing[2] = (int)(t3 - t2); h->timing[3] = (int)(t4 - t3); h->timing[4] = (int)(t5 - t4); h->timing[5] = (int)(t5 - t0);
     return rc;
 }
 int frontend_process(FrontendImpl* h, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride, int on_device, void* result) {
@@ -207,6 +217,7 @@ void olf_frontend_destroy(olf_frontend* h) { frontend_destroy((FrontendImpl*)h);
 int olf_frontend_process(olf_frontend* h, const uint8_t* img_l, const uint8_t* img_r, int width, int height, int stride, int on_device, void* result) {
     return frontend_process((FrontendImpl*)h, img_l, img_r, width, height, stride, on_device, result);
 }
+int olf_frontend_last_timing(const olf_frontend* h, int* out8) { if (!h || !out8) return OLF_ERR_ARG; for (int i = 0; i < 8; ++i) out8[i] = ((const FrontendImpl*)h)->timing[i]; return OLF_OK; }
 olf_orb* olf_frontend_orb(olf_frontend* h, int eye) { return h && eye >= 0 && eye < (int)((FrontendImpl*)h)->orb.size() ? (olf_orb*)((FrontendImpl*)h)->orb[eye] : nullptr; }
 olf_line* olf_frontend_line(olf_frontend* h, int eye) { return h && eye >= 0 && eye < (int)((FrontendImpl*)h)->line.size() ? (olf_line*)((FrontendImpl*)h)->line[eye] : nullptr; }
 }

@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <chrono>
+#include <cstddef>
 
 
 namespace olf {
@@ -172,7 +174,9 @@ struct GrowDev {
 // on one stream instead of one chain per image -- that is what keeps many frames in flight within the 32 hardware queues.
 #define LSD_MAX_BATCH 16
 #define LSD_MAX_WAVES 64
-struct GrowBatch { GrowDev d[LSD_MAX_BATCH]; PhaseState* st[LSD_MAX_BATCH]; unsigned* conv; int n; };   // conv[w]: images of the batch that have converged in wave w
+// conv[w]: images of the batch that have converged in wave w; conv[LSD_MAX_WAVES]: images that are done.
+// cond: handle of the graph's WHILE node when the chain runs as a CUDA graph (0: plain launches)
+struct GrowBatch { GrowDev d[LSD_MAX_BATCH]; PhaseState* st[LSD_MAX_BATCH]; unsigned* conv; int n; cudaGraphConditionalHandle cond; };
 __device__ __forceinline__ const GrowDev& batch_image(const GrowBatch& B, GrowDev* sh, PhaseState*& st) {
     // block-uniform copy of this image's descriptor into shared memory (the by-value batch lives in parameter space);
     // the claim stamp of the image's current wave is filled in here
@@ -202,6 +206,10 @@ __device__ __forceinline__ void wl_append(bool take, int value, int* __restrict_
     if (take) list[base + __popc(m & lanemask_lt())] = value;
 }
 
+// an image has finished all its waves: the last one ends the WHILE loop of the graph
+__device__ __forceinline__ void image_done(const GrowBatch& B) {
+    if (atomicAdd(&B.conv[LSD_MAX_WAVES], 1u) + 1u == (unsigned)B.n && B.cond) cudaGraphSetConditional(B.cond, 0);
+}
 // pass 1: every candidate of the wave -- dead or alive (+ first-round deferral); alive seeds and seeds that died owning a
 // region go to work list 1; the bitmap that collects THIS round's events is cleared
 __global__ void __launch_bounds__(256) k_lsd_scan(const __grid_constant__ GrowBatch B) {
@@ -417,6 +425,7 @@ __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(cons
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             st->done = 1; D.status[1] = (int)round; D.status[2] = D.plan->n_waves; D.status[3] = 1;
             for (int w = wv; w < LSD_MAX_WAVES; ++w) atomicAdd(&B.conv[w], 1u);       // never holds the batch back
+            image_done(B);
         }
         return;
     }
@@ -666,8 +675,9 @@ __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(cons
     __syncthreads();
     if (!s_last || threadIdx.x != 0) return;
     __threadfence();
-    const int err = *(volatile int*)&D.status[0];
+    int err = *(volatile int*)&D.status[0];
     st->ticket = 0; st->launches += 1;
+    if (st->launches > 6000 && err == 0) { D.status[0] = OLF_ERR_INTERNAL; err = OLF_ERR_INTERNAL; }     // a WHILE graph must end whatever happens
     // The images of a batch advance through their waves TOGETHER: an image that has converged waits (mode 2) until every image
     // of the batch has, so the expensive first rounds of a wave -- whose critical path is the longest region -- coincide in
     // the same launches instead of adding up along the chain.
@@ -703,6 +713,7 @@ __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(cons
         if (wv + 1 >= D.plan->n_waves || err != 0) {
             st->done = 1; D.status[1] = (int)(round + 1); D.status[2] = D.plan->n_waves; D.status[3] = 1;
             for (int w = wv + 1; w < LSD_MAX_WAVES; ++w) atomicAdd(&B.conv[w], 1u);   // this image has no further waves
+            image_done(B);
         }
     }
     __threadfence();
@@ -979,6 +990,7 @@ struct LineImpl {
     DevBuf<PhaseState> phase;
     DevBuf<PxRec> px;
     DevBuf<GrowCont> cont;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr; unsigned long long graph_key = 0; int use_graph = 1;
     int grow_budget = 1 << 30;          // OLF_LSD_GROW_BUDGET: queue entries per thread and grow launch (default: no limit)
     int phase_batch = 52;
     bool trace = false;
@@ -1095,6 +1107,7 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     if (const char* e = getenv("OLF_LSD_VERIFY_BLOCKS")) h->verify_blocks = h->verify_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks_wide = h->grow_blocks_narrow = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BUDGET")) h->grow_budget = std::max(1, atoi(e));
+    if (const char* e = getenv("OLF_LSD_GRAPH")) h->use_graph = atoi(e);
     ok = h->cont.ensure((size_t)2 * std::max(h->grow_blocks_wide, h->grow_blocks_narrow) * GROW_THREADS) == OLF_OK;
     if (!ok) { delete h; return nullptr; }
     return h;
@@ -1107,6 +1120,8 @@ void line_destroy(LineImpl* h) {
     if (h->ev_grow0) cudaEventDestroy(h->ev_grow0);
     if (h->ev_grow1) cudaEventDestroy(h->ev_grow1);
     h->sync.destroy();
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
     h->img_stage.release(); h->img.release(); h->blurred.release(); h->scaled.release(); h->lbd_blur.release(); h->coef.release();
     h->ang.release(); h->dabc.release(); h->seed_prio.release(); h->seed_pix.release(); h->n2max.release(); h->status.release();
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
@@ -1143,7 +1158,7 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
     h->pool_chunks = (unsigned)std::max<size_t>(S / 2, 1u << 16);       // 16 px of list space per image pixel per round
     h->reg_cap = (unsigned)(S / std::max(h->min_reg_size, 1) + 16);
     if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || (rc = h->seed_prio.ensure(S)) || (rc = h->seed_pix.ensure(S)) ||
-        (rc = h->conv.ensure(LSD_MAX_WAVES)) || (rc = h->srec0.ensure(S)) || (rc = h->wl0.ensure(S)) || (rc = h->wl1.ensure(S)) || (rc = h->wl2.ensure(S)) ||
+        (rc = h->conv.ensure(LSD_MAX_WAVES + 1)) || (rc = h->srec0.ensure(S)) || (rc = h->wl0.ensure(S)) || (rc = h->wl1.ensure(S)) || (rc = h->wl2.ensure(S)) ||
         (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) ||
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
         (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->plan.ensure(1)) ||
@@ -1249,14 +1264,16 @@ static int lsd_enqueue_rect_a(LineImpl* h, cudaStream_t s) {
 }
 
 // LSD of a batch of uploaded images on ONE stream; segments of image k (seed order) -> segs[k]
+static inline long long now_us() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector<float4>* segs) {
+    const long long t_begin = now_us();
     if (n < 1 || n > LSD_MAX_BATCH) { set_last_error("LSD batch size out of range"); return OLF_ERR_ARG; }
     GrowBatch B; memset(&B, 0, sizeof(B));
     int rc;
     for (int k = 0; k < n; ++k) { if ((rc = lsd_enqueue_pre(hs[k], s, B.d[k], n))) return rc; B.st[k] = hs[k]->phase.p; }
     LineImpl* h0 = hs[0];
     B.conv = h0->conv.p; B.n = n;
-    OLF_CUDA(cudaMemsetAsync(h0->conv.p, 0, LSD_MAX_WAVES * sizeof(unsigned), s));
+    OLF_CUDA(cudaMemsetAsync(h0->conv.p, 0, (LSD_MAX_WAVES + 1) * sizeof(unsigned), s));
     OLF_CUDA(cudaEventRecord(h0->ev_grow0, s));
     auto enqueue_phases = [&](int count) {
         for (int k = 0; k < count; ++k) {
@@ -1266,10 +1283,48 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
         }
         count_launches(3 * count);
     };
-    // the wave / round state machines run on the device; a fixed batch of launches normally covers all rounds of all
-    // images (launches after an image is done return at once), otherwise keep going (rare)
+    // The wave / round state machines run on the device.  Default: the three passes are the body of a CUDA-graph WHILE node
+    // that the last finishing image ends (cudaGraphSetConditional): one graph launch per batch, no launch is enqueued that
+    // has nothing to do.  OLF_LSD_GRAPH=0: a fixed batch of plain launches that normally covers all rounds of all images
+    // (launches after an image is done return at once), otherwise keep going (rare).
+    const dim3 g_scan(n <= 2 ? h0->scan_blocks_wide : h0->scan_blocks, n), g_verify(n <= 2 ? h0->verify_blocks_wide : h0->verify_blocks, n),
+               g_grow(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n);
+    bool graph_ok = false;
+    if (h0->use_graph) {
+        unsigned long long key = 1469598103934665603ull;
+        { const unsigned char* b = (const unsigned char*)&B; for (size_t i = 0; i < offsetof(GrowBatch, cond); ++i) { key ^= b[i]; key *= 1099511628211ull; } }
+        if (!h0->graph_exec || h0->graph_key != key) {
+            if (h0->graph_exec) { cudaGraphExecDestroy(h0->graph_exec); h0->graph_exec = nullptr; }
+            if (h0->graph) { cudaGraphDestroy(h0->graph); h0->graph = nullptr; }
+            cudaGraph_t g = nullptr; cudaGraphConditionalHandle cond = 0;
+            bool ok = cudaGraphCreate(&g, 0) == cudaSuccess && cudaGraphConditionalHandleCreate(&cond, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+            cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+            np.type = cudaGraphNodeTypeConditional; np.conditional.handle = cond; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+            cudaGraphNode_t wnode = nullptr;
+            ok = ok && cudaGraphAddNode(&wnode, g, nullptr, 0, &np) == cudaSuccess;
+            if (ok) {
+                cudaGraph_t body = np.conditional.phGraph_out[0];
+                GrowBatch Bg = B; Bg.cond = cond;
+                void* args[1] = {&Bg};
+                cudaKernelNodeParams kp = {};
+                cudaGraphNode_t n1 = nullptr, n2 = nullptr, n3 = nullptr;
+                kp.kernelParams = args; kp.sharedMemBytes = 0;
+                kp.func = (void*)k_lsd_scan; kp.gridDim = g_scan; kp.blockDim = dim3(256);
+                ok = ok && cudaGraphAddKernelNode(&n1, body, nullptr, 0, &kp) == cudaSuccess;
+                kp.func = (void*)k_lsd_verify; kp.gridDim = g_verify; kp.blockDim = dim3(128);
+                ok = ok && cudaGraphAddKernelNode(&n2, body, &n1, 1, &kp) == cudaSuccess;
+                kp.func = (void*)k_lsd_grow; kp.gridDim = g_grow; kp.blockDim = dim3(GROW_THREADS);
+                ok = ok && cudaGraphAddKernelNode(&n3, body, &n2, 1, &kp) == cudaSuccess;
+                ok = ok && cudaGraphInstantiate(&h0->graph_exec, g, 0) == cudaSuccess;
+            }
+            if (!ok) { cudaGetLastError(); if (g) cudaGraphDestroy(g); h0->graph_exec = nullptr; h0->use_graph = 0; }      // driver without conditional nodes: plain launches
+            else { h0->graph = g; h0->graph_key = key; }
+        }
+        graph_ok = h0->graph_exec != nullptr;
+    }
     for (int guard = 0; guard < 400; ++guard) {
-        enqueue_phases(h0->phase_batch);
+        if (graph_ok) { OLF_CUDA(cudaGraphLaunch(h0->graph_exec, s)); count_launches(3 * 30); }      // ~30 rounds x 3 passes (the exact count stays on the device)
+        else enqueue_phases(h0->phase_batch);
         OLF_CUDA(cudaEventRecord(h0->ev_grow1, s));
         for (int k = 0; k < n; ++k) if ((rc = lsd_enqueue_rect_a(hs[k], s))) return rc;
         OLF_CUDA(h0->sync.sync(s));
@@ -1277,6 +1332,7 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
         for (int k = 0; k < n; ++k) all = all && (hs[k]->status_host.p[3] || hs[k]->status_host.p[0]);
         if (all) break;
     }
+    const long long t_chain = now_us();
     float grow_ms = 0; cudaEventElapsedTime(&grow_ms, h0->ev_grow0, h0->ev_grow1);
     for (int k = 0; k < n; ++k) {
         LineImpl* h = hs[k];
@@ -1295,6 +1351,7 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     }
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(h0->sync.sync(s));
+    h0->last_stats[5] = (int)(t_chain - t_begin); h0->last_stats[6] = (int)(now_us() - t_chain);      // host view: enqueue + chain wait / trig + rect_b wait (us)
     for (int k = 0; k < n; ++k) {
         LineImpl* h = hs[k];
         const int nr = h->last_stats[2];
@@ -1410,6 +1467,7 @@ int line_extract_batch(LineImpl* const* hs, int nimg, const uint8_t* const* imgs
     for (int k = 0; k < nimg; ++k) if ((rc = line_upload(hs[k], imgs[k], w, hgt, stride, on_device, s))) return rc;
     std::vector<float4> sg[LSD_MAX_BATCH];
     if ((rc = lsd_run_batch(hs, nimg, s, sg))) return rc;
+    const long long t_lsd = now_us();
     std::vector<olf_keyline> kl[LSD_MAX_BATCH];
     for (int k = 0; k < nimg; ++k) {
         LineImpl* h = hs[k];
@@ -1429,6 +1487,7 @@ int line_extract_batch(LineImpl* const* hs, int nimg, const uint8_t* const* imgs
         if ((rc = lbd_enqueue(h, v.data(), (int)v.size(), s))) return rc;
     }
     OLF_CUDA(hs[0]->sync.sync(s));
+    hs[0]->last_stats[7] = (int)(now_us() - t_lsd);                      // keylines + LBD (us)
     for (int k = 0; k < nimg; ++k) if (n[k]) memcpy(desc[k], hs[k]->desc_host.p, (size_t)n[k] * 32);
     return OLF_OK;
 }

@@ -743,6 +743,73 @@ int match_grid_lines(const int* lines1, const uint8_t* desc1, int n1, const olf_
 }
 
 // ======================================================================================================
+// MapPoint / MapLine::ComputeDistinctiveDescriptors (src/MapPoint.cc:254-322, src/MapLine.cc:257-322), batched over landmarks:
+// the observation whose MEDIAN Hamming distance to all observations of the landmark (itself included, distance 0) is smallest,
+// first one on ties.  One warp per landmark: a row of the distance matrix at a time, the (int)(0.5*(N-1))-th smallest of the
+// row from a 257-bin histogram in shared memory (distances are integers in [0, 256]).
+// ======================================================================================================
+__global__ void __launch_bounds__(256) k_distinctive(const uint32_t* __restrict__ desc, const int* __restrict__ begin, int n_groups, int* __restrict__ best) {
+    __shared__ unsigned hist[8][264];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 8 + warp;
+    if (g >= n_groups) return;
+    const int b = begin[g], N = begin[g + 1] - b;
+    if (N <= 0) { if (lane == 0) best[g] = -1; return; }
+    const int kth = (int)(0.5 * (double)(N - 1));
+    int best_median = INT_MAX, best_idx = 0;
+    for (int i = 0; i < N; ++i) {
+        for (int k = lane; k < 264; k += 32) hist[warp][k] = 0;
+        __syncwarp();
+        uint32_t a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = desc[(size_t)(b + i) * 8 + k];
+        for (int j = lane; j < N; j += 32) atomicAdd(&hist[warp][hamming256(a, desc + (size_t)(b + j) * 8)], 1u);
+        __syncwarp();
+        // smallest d with cumulative count > kth: per-lane partial sums over 9 consecutive bins, warp scan
+        unsigned part = 0;
+        for (int k = 0; k < 9; ++k) { const int d = lane * 9 + k; if (d <= 256) part += hist[warp][d]; }
+        unsigned incl = part;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const unsigned excl = incl - part;
+        int median = INT_MAX;
+        if (excl <= (unsigned)kth && (unsigned)kth < incl) {
+            unsigned run = excl;
+            for (int k = 0; k < 9; ++k) { const int d = lane * 9 + k; if (d > 256) break; run += hist[warp][d]; if ((unsigned)kth < run) { median = d; break; } }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) median = min(median, __shfl_xor_sync(0xffffffffu, median, o));
+        if (median < best_median) { best_median = median; best_idx = i; }
+        __syncwarp();
+    }
+    if (lane == 0) best[g] = best_idx;
+}
+int distinctive_descriptors(const uint8_t* desc, const int* group_begin, int n_groups, int* best, int device) {
+    if (n_groups < 0 || (n_groups && (!group_begin || !best))) { set_last_error("olf_distinctive_descriptors: bad arguments"); return OLF_ERR_ARG; }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    if (n_groups == 0) return OLF_OK;
+    const int total = group_begin[n_groups];
+    if (total < 0 || (total && !desc)) { set_last_error("olf_distinctive_descriptors: bad arguments"); return OLF_ERR_ARG; }
+    Planner pl;
+    const size_t o_d = pl.d((size_t)std::max(total, 1) * 32), o_b = pl.d((size_t)(n_groups + 1) * 4), o_o = pl.d((size_t)n_groups * 4);
+    const size_t p_d = pl.p((size_t)std::max(total, 1) * 32), p_b = pl.p((size_t)(n_groups + 1) * 4), p_o = pl.p((size_t)n_groups * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->cur;
+    if (total) memcpy(hptr<uint8_t>(c, p_d), desc, (size_t)total * 32);
+    memcpy(hptr<int>(c, p_b), group_begin, (size_t)(n_groups + 1) * 4);
+    if (total) OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_d), hptr<uint8_t>(c, p_d), (size_t)total * 32, cudaMemcpyHostToDevice, s));
+    OLF_CUDA(cudaMemcpyAsync(dptr<int>(c, o_b), hptr<int>(c, p_b), (size_t)(n_groups + 1) * 4, cudaMemcpyHostToDevice, s));
+    k_distinctive<<<(n_groups + 7) / 8, 256, 0, s>>>(dptr<uint32_t>(c, o_d), dptr<int>(c, o_b), n_groups, dptr<int>(c, o_o));
+    count_launches(1);
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_o), dptr<int>(c, o_o), (size_t)n_groups * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(stream_sync(s));
+    memcpy(best, hptr<int>(c, p_o), (size_t)n_groups * 4);
+    return OLF_OK;
+}
+
+// ======================================================================================================
 // ORBmatcher::SearchByProjection: candidate lists (warp per query) + fixed-point resolution of the blocking rule
 // ======================================================================================================
 #define SBP_K 128

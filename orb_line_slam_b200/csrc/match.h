@@ -23,6 +23,7 @@ int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_key
                  const olf_line_match_params* P, int* matches12, float* disp, double* le, int device);
 int match_grid_lines(const int* lines1, const uint8_t* desc1, int n1, const olf_grid_csr* grid, const uint8_t* desc2, int n2, const double* dir2,
                      const int* window, const olf_line_match_params* P, int* matches12, int* nmatches, int device);
+int distinctive_descriptors(const uint8_t* desc, const int* group_begin, int n_groups, int* best, int device);
 int search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur, int* cur_point, int* nmatches, int device);
 int search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches, int device);
 struct VocabImpl;

@@ -162,3 +162,20 @@ def test_native_frontend_batch(frames):
     with pytest.raises(Exception):
         nat.process_batch([p[0] for p in pairs] * 2, [p[1] for p in pairs] * 2, blocks * 2)     # more frames than the rig holds
     nat.close()
+
+
+def test_distinctive_descriptors_parity():
+    """olf_distinctive_descriptors (MapPoint/MapLine::ComputeDistinctiveDescriptors batched over landmarks) == oracle, incl. empty
+    and single-observation groups, duplicate rows (first wins) and a landmark with 300 observations."""
+    rng = np.random.RandomState(12)
+    sizes = [0, 1, 2, 3, 5, 8, 31, 32, 33, 64, 100, 300] + list(rng.randint(1, 40, 500))
+    desc, begin = [], [0]
+    for n in sizes:
+        base = rng.randint(0, 256, 32).astype(np.uint8)
+        rows = np.stack([base ^ ((rng.rand(32) < 0.15) * rng.randint(0, 256, 32)).astype(np.uint8) for _ in range(n)]) if n else np.zeros((0, 32), np.uint8)
+        if n > 4:
+            rows[3] = rows[1]                                       # duplicates: ties in the medians
+        desc.append(rows); begin.append(begin[-1] + n)
+    desc = np.concatenate(desc); begin = np.array(begin, np.int32)
+    g, o = olf.api(0), oracle()
+    assert np.array_equal(g.distinctive_descriptors(desc, begin), o.distinctive_descriptors(desc, begin))

@@ -155,3 +155,21 @@ def test_search_by_projection_map_points():
                             keep["obs"], keep["pdesc"], np.array([th, ratio], np.float32), *orb_params(1000))
         assert nr[0] == no > 20 and np.array_equal(ar, ao), f"SearchByProjection(F, MapPoints) th={th}"
     fe.close()
+
+
+def test_compute_distinctive_descriptors():
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:254-322; MapLine's, src/MapLine.cc:257-322, is the same text on
+    LBD rows): the reference's function picks a descriptor; identical rows make the index ambiguous, so groups hold distinct rows."""
+    rng = np.random.RandomState(9)
+    sizes = [1, 2, 3, 4, 7, 16, 33, 64, 100]
+    desc, begin = [], [0]
+    for n in sizes * 3:
+        base = rng.randint(0, 256, 32).astype(np.uint8)
+        rows = np.stack([base ^ (rng.rand(32) < rng.uniform(0.02, 0.5)).astype(np.uint8) * rng.randint(1, 256, 32).astype(np.uint8) for _ in range(n)])
+        while len({bytes(r) for r in rows}) < n:
+            rows = rng.randint(0, 256, (n, 32)).astype(np.uint8)
+        desc.append(rows); begin.append(begin[-1] + n)
+    desc = np.concatenate(desc); begin = np.array(begin, np.int32)
+    br, = refcli.run("distinctive", desc, begin)
+    bo = oracle().distinctive_descriptors(desc, begin)
+    assert np.array_equal(br, bo)
