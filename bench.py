@@ -115,6 +115,10 @@ class StepRunner:
             self.recv = torch.empty(self.world * self.fps_step * self.nbytes, dtype=torch.uint8, device="cuda")
             self.gstream = torch.cuda.Stream()
         self.gather_checked = None
+        # persistent host threads (one per rig, the trackers, the gatherer): the matchers keep per-thread scratch on the device,
+        # and creating it costs device allocations -- nothing of that kind may happen inside a timed region
+        from concurrent.futures import ThreadPoolExecutor
+        self.pool_w, self.pool_t, self.pool_g = ThreadPoolExecutor(self.P), ThreadPoolExecutor(self.T), ThreadPoolExecutor(1)
 
     def block(self, k):
         s, j = divmod(k, self.fps_step)
@@ -225,13 +229,12 @@ class StepRunner:
             except Exception as e:       # noqa: BLE001
                 fail(e)
 
-        ths = [threading.Thread(target=worker, args=(p,)) for p in range(P)] + [threading.Thread(target=tracker, args=(i,)) for i in range(T)]
+        # every pool has exactly as many threads as tasks, so all tasks run concurrently (they wait for each other)
+        futs = [self.pool_w.submit(worker, p) for p in range(P)] + [self.pool_t.submit(tracker, i) for i in range(T)]
         if self.dist is not None:
-            ths.append(threading.Thread(target=gatherer))
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
+            futs.append(self.pool_g.submit(gatherer))
+        for f in futs:
+            f.result()
         if errors:
             raise errors[0]
         # how steady the rigs ran: duration of the batch calls, time between calls (host glue), time spent waiting for a ring slot
@@ -404,6 +407,7 @@ def main():
     lib = olf.load_library()
     import ctypes
     lib.olf_kernel_launch_count.restype = ctypes.c_longlong
+    lib.olf_alloc_count.restype = ctypes.c_longlong
     api = olf.api(local)
     cam = CAMERAS[wl["camera"]]
     # concurrent stereo rigs per GPU: the LSD grow phases are latency-bound, so frames in flight are what fills the GPU.
@@ -433,7 +437,7 @@ def main():
     def timed(nsteps, first, on_device):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.olf_kernel_launch_count()
+        l0 = lib.olf_kernel_launch_count(); a0 = lib.olf_alloc_count()
         ev0.record()
         st = runner.run(nsteps, first, on_device)
         torch.cuda.synchronize()
@@ -441,6 +445,7 @@ def main():
         ms = ev0.elapsed_time(ev1)
         if dist is not None:
             t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        st["allocs"] = int(lib.olf_alloc_count() - a0)
         return ms, st, lib.olf_kernel_launch_count() - l0
 
     # untimed pre-warm, a FIXED number of steps on every rank (the collective sequence must be rank-invariant): a fresh box
@@ -480,8 +485,9 @@ def main():
                 "config": dict(wl, step="one olf_frontend_process_batch call on every rig", pipelines_per_gpu=P, frames_per_call=B, frames_per_step=fps_step,
                                frames_timed_per_gpu=nframes, trackers=T, prewarm_steps=args.prewarm_steps,
                                l2=f"inputs larger than L2: {N_DISTINCT} distinct stereo pairs = {N_DISTINCT * 2 * w * h / 1e6:.0f} MB cycled",
-                               host_cores=cores, per_frame={k: v / max(nframes, 1) for k, v in st.items() if not isinstance(v, dict)},
-                               steadiness=dict(resident={k: v for k, v in st.items() if isinstance(v, dict)}, e2e={k: v for k, v in st_e2e.items() if isinstance(v, dict)}),
+                               host_cores=cores, per_frame={k: v / max(nframes, 1) for k, v in st.items() if not isinstance(v, dict) and k != "allocs"},
+                               steadiness=dict(resident=dict({k: v for k, v in st.items() if isinstance(v, dict)}, allocs=st["allocs"]),
+                                               e2e=dict({k: v for k, v in st_e2e.items() if isinstance(v, dict)}, allocs=st_e2e["allocs"])),
                                exchange=(None if dist is None else f"NCCL all_gather of {fps_step} result blocks x {runner.nbytes} B per rank per step"),
                                gather_verified=runner.gather_checked,
                                rig_call_ms=(None if not host_us else dict(zip(("orb_enqueue", "lines", "orb_wait", "collect", "stereo_lines", "total"),

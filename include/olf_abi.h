@@ -102,6 +102,8 @@ const char* olf_last_error(void);
 int olf_device_count(void);
 /* kernels launched by this library since load (bench.py reports the delta as gpu_launches) */
 long long olf_kernel_launch_count(void);
+/* device / pinned allocations made by this library since load (each one synchronises the device; steady state makes none) */
+long long olf_alloc_count(void);
 
 /* ---- ORBextractor (include/ORBextractor.h:52-118; src/ORBextractor.cc:412-472, 1045-1134) ---------------- */
 olf_orb* olf_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device);

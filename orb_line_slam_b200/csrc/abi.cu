@@ -11,6 +11,8 @@ namespace olf {
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<long long> g_allocs{0};
+void count_allocs(int n) { g_allocs.fetch_add(n, std::memory_order_relaxed); }
 long long launches_total() { return g_launches.load(); }
 static int sync_mode() {
     // OLF_SYNC=spin  : busy-wait (lowest latency, one busy host core per waiting thread)
@@ -64,6 +66,7 @@ using namespace olf;
 extern "C" {
 const char* olf_last_error(void) { return g_err.c_str(); }
 long long olf_kernel_launch_count(void) { return launches_total(); }
+long long olf_alloc_count(void) { return g_allocs.load(); }
 int olf_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
 olf_orb* olf_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int device) {

@@ -12,6 +12,7 @@ namespace olf {
 
 void set_last_error(const std::string& s);
 void count_launches(int n);
+void count_allocs(int n);          // cudaMalloc / cudaHostAlloc / cudaFree calls (each one synchronises the device: none may happen in steady state)
 // Wait for a stream without burning a host core: blocking-sync event (thread sleeps) unless OLF_SYNC=spin.
 // Many pipelines x 4 extraction threads wait concurrently; spinning would oversubscribe the host CPUs.
 cudaError_t stream_sync(cudaStream_t s);
@@ -55,6 +56,7 @@ struct DevBuf {
         // buffer has to grow, grow it geometrically so that steady state never reallocates
         if (p) count = count + count / 2 + 4096;
         T* np = nullptr;
+        count_allocs(1);
         cudaError_t e = cudaMalloc((void**)&np, count * sizeof(T));
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);      // the old buffer stays valid
         if (p) cudaFree(p);
@@ -73,6 +75,7 @@ struct PinBuf {
         if (count <= n) return OLF_OK;
         if (p) { count = count + count / 2 + 4096; cudaFreeHost(p); }
         p = nullptr; d = nullptr; n = 0;
+        count_allocs(1);
         cudaError_t e = cudaHostAlloc((void**)&p, count * sizeof(T), cudaHostAllocMapped);
         if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
         e = cudaHostGetDevicePointer((void**)&d, p, 0);

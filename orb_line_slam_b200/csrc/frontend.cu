@@ -48,6 +48,7 @@ struct FrontendImpl {
     std::vector<LineImpl*> line;
     StereoWs sws[OLF_MAX_BATCH_FRAMES];
     SyncEvent ev_orb;
+    MatchCtx* mctx = nullptr;            // scratch of the stereo line matcher (owned by the rig, not by the calling thread)
     Worker* worker = nullptr;            // single-frame rig only: the right eye's line extraction
     olf_frame_offsets off;
     std::string err;
@@ -100,6 +101,7 @@ FrontendImpl* frontend_create(const olf_frontend_params* p, int device, int max_
         }
     }
     ok = ok && h->ev_orb.create(batch) == cudaSuccess;
+    if (ok) h->mctx = match_ctx_create(device);
     if (!ok) {
         const std::string e = olf_last_error();
         frontend_destroy(h); set_last_error(e); return nullptr;
@@ -114,6 +116,7 @@ void frontend_destroy(FrontendImpl* h) {
     if (!h->orb.empty()) cudaStreamSynchronize(orb_stream(h->orb[0]));
     for (int f = 0; f < OLF_MAX_BATCH_FRAMES; ++f) stereo_ws_release(&h->sws[f]);
     h->ev_orb.destroy();
+    if (h->mctx) match_ctx_destroy(h->mctx);
     for (size_t k = h->orb.size(); k-- > 0;) orb_destroy(h->orb[k]);     // the borrowers before the owner of the stream
     for (size_t k = h->line.size(); k-- > 0;) line_destroy(h->line[k]);
     delete h;
@@ -175,6 +178,7 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
     const long long t4 = now();
     if (!rc && rc_l) { rc = rc_l; set_last_error(err_l); }
     match_use_stream(h->P.has_lines ? line_stream(h->line[0]) : so);
+    match_use_ctx(h->mctx);
     for (int f = 0; f < nframes; ++f) {
         uint8_t* base = (uint8_t*)results[f];
         olf_frame_header* hd = (olf_frame_header*)base;
@@ -193,7 +197,7 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
         }
         hd->status = rc;
     }
-    match_use_stream(nullptr);
+    match_use_stream(nullptr); match_use_ctx(nullptr);
     const long long t5 = now();
     h->timing[0] = (int)(t1 - t0); h->timing[1] = (int)(t2 - t1); h->timing[2] = (int)(t3 - t2); h->timing[3] = (int)(t4 - t3); h->timing[4] = (int)(t5 - t4); h->timing[5] = (int)(t5 - t0);
     return rc;

@@ -41,6 +41,12 @@ struct MatchCtx {
 };
 static thread_local MatchCtx g_ctx[16];
 static thread_local cudaStream_t g_lent_stream = nullptr;
+static thread_local MatchCtx* g_lent_ctx = nullptr;
+// A rig owns its matcher scratch (arenas) instead of taking the calling thread's: callers may be short-lived threads, and
+// creating a context costs device allocations, which synchronise the whole device.
+MatchCtx* match_ctx_create(int device) { MatchCtx* c = new MatchCtx(); c->device = device; return c; }
+void match_ctx_destroy(MatchCtx* c) { delete c; }
+void match_use_ctx(MatchCtx* c) { g_lent_ctx = c; }
 // A rig runs its stereo matchers on one of its own streams instead of one more stream per calling thread: every stream
 // beyond the 32 hardware work queues aliases another one and queues behind its (long) chains.
 void match_use_stream(cudaStream_t s) { g_lent_stream = s; }
@@ -53,7 +59,7 @@ static int get_ctx(int device, MatchCtx** out) {
         return OLF_ERR_NO_DEVICE;
     }
     OLF_CUDA(cudaSetDevice(device));
-    MatchCtx& c = g_ctx[device];
+    MatchCtx& c = (g_lent_ctx && g_lent_ctx->device == device) ? *g_lent_ctx : g_ctx[device];
     if (g_lent_stream) c.cur = g_lent_stream;
     else {
         if (!c.stream) OLF_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));

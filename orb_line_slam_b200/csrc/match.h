@@ -8,6 +8,11 @@ namespace olf {
 struct OrbImpl;
 // the calling thread's next matcher calls run on `s` (nullptr: back to the thread's own stream)
 void match_use_stream(cudaStream_t s);
+// the calling thread's next matcher calls use this scratch context instead of the thread's own (nullptr: back to the thread's)
+struct MatchCtx;
+MatchCtx* match_ctx_create(int device);
+void match_ctx_destroy(MatchCtx* c);
+void match_use_ctx(MatchCtx* c);
 int knn2_hamming(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* idx0, int* dist0, int* idx1, int* dist1, int device);
 int knn2_bench(int n1, int n2, int iters, int device, double* kernel_ms, double* popc_word_pairs_per_s);
 int match_lines(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int mutual, int* m12, int* nmatches, int device);
