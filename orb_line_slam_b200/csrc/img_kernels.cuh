@@ -41,8 +41,10 @@ static __device__ __forceinline__ void locate_tile(const LevelTable& T, int b, i
 // A batch of images per launch (blockIdx.y): the rigs keep 2..8 images in flight and every kernel of this front end is
 // launch-bound on one 0.9-MB image, so one launch serves all images of a call.
 #define IMG_MAX_BATCH 16
-// maps[k]: device array of one CUtensorMap per level of image k (TMA variant)
-struct BlurBatch { const uint8_t* src[IMG_MAX_BATCH]; uint8_t* dst[IMG_MAX_BATCH]; const CUtensorMap* maps[IMG_MAX_BATCH]; };
+struct BlurBatch { const uint8_t* src[IMG_MAX_BATCH]; uint8_t* dst[IMG_MAX_BATCH]; };
+// TMA variant: the tensor maps travel as a __grid_constant__ kernel parameter (the one placement that needs no proxy fence and
+// that no stray device write can reach); m[image * T.n + level]
+template <int NM> struct alignas(64) TmaSet { CUtensorMap m[NM]; };
 template <int K>
 static __global__ void __launch_bounds__(256) k_blur_q8(const __grid_constant__ BlurBatch BB,
                                                  const __grid_constant__ LevelTable T, const int q0, const int q1, const int q2, const int q3) {
@@ -89,8 +91,8 @@ static __global__ void __launch_bounds__(256) k_blur_q8(const __grid_constant__ 
 // pixels are inside the same box).
 #define TMA_BOX_W 96
 #define TMA_PAD 16
-template <int K>
-static __global__ void __launch_bounds__(256) k_blur_q8_tma(const __grid_constant__ BlurBatch BB,
+template <int K, int NM>
+static __global__ void __launch_bounds__(256) k_blur_q8_tma(const __grid_constant__ BlurBatch BB, const __grid_constant__ TmaSet<NM> M,
                                                      const __grid_constant__ LevelTable T, const int q0, const int q1, const int q2, const int q3) {
     constexpr int R = K / 2;
     constexpr int ROWS = TILE_H + 2 * R;
@@ -107,7 +109,7 @@ static __global__ void __launch_bounds__(256) k_blur_q8_tma(const __grid_constan
     __syncthreads();
     if (threadIdx.x == 0) {
         tma::mbar_expect_tx(&bar, ROWS * TMA_BOX_W);
-        tma::load_2d(&tile[0][0], BB.maps[blockIdx.y] + level, x0 - TMA_PAD, y0 - R, &bar);
+        tma::load_2d(&tile[0][0], &M.m[blockIdx.y * T.n + level], x0 - TMA_PAD, y0 - R, &bar);
     }
     tma::mbar_wait(&bar, 0);
     // reflect-101 fix-up of the zero-filled cells (edge tiles only): columns first, then whole rows

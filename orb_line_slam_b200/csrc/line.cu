@@ -990,7 +990,7 @@ struct LineImpl {
     DevBuf<PhaseState> phase;
     DevBuf<PxRec> px;
     DevBuf<GrowCont> cont;
-    DevBuf<CUtensorMap> tmaps; bool has_tma = false;      // [0]: input image, 7x7 box (LSD pre-blur); [1]: input image, 5x5 box (LBD blur)
+    TmaSet<1> tmaps[2]; bool has_tma = false;      // [0]: input image, 7x7 box (LSD pre-blur); [1]: input image, 5x5 box (LBD blur)
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr; unsigned long long graph_key = 0; int use_graph = 1;
     int grow_budget = 1 << 30;          // OLF_LSD_GROW_BUDGET: queue entries per thread and grow launch (default: no limit)
     int phase_batch = 52;
@@ -1127,7 +1127,7 @@ void line_destroy(LineImpl* h) {
     h->ang.release(); h->dabc.release(); h->seed_prio.release(); h->seed_pix.release(); h->n2max.release(); h->status.release();
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
     h->final_pool.release(); h->conv.release(); h->dirty.release(); h->srec0.release(); h->regang.release(); h->plan.release(); h->regs.release();
-    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release(); h->cont.release(); h->tmaps.release();
+    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release(); h->cont.release();
     h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release(); h->phase_init.release();
     h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
@@ -1175,13 +1175,9 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
         (rc = h->dbg.ensure((size_t)h->max_rounds * TRACE_REC)) || (rc = h->px.ensure((size_t)S + 2 * (h->W + 2))) ||
         (rc = h->regs.ensure(h->reg_cap)) || (rc = h->rect_host.ensure(h->reg_cap)) || (rc = h->dir_host.ensure(h->reg_cap)) ||
         (rc = h->seg_host.ensure(h->reg_cap)) || (rc = h->status_host.ensure(4)) || (rc = h->nreg_host.ensure(1))) return rc;
-    if ((rc = h->tmaps.ensure(2))) return rc;
     {
-        CUtensorMap hm[2];
         const LevelTable T1 = single_level(w, hgt, h->ipitch);
-        CUtensorMap t7[OLF_MAX_LEVELS], t5[OLF_MAX_LEVELS];
-        h->has_tma = h->blur_k == 7 && build_level_maps(h->img.p, T1, 7, t7) && build_level_maps(h->img.p, T1, 5, t5);
-        if (h->has_tma) { hm[0] = t7[0]; hm[1] = t5[0]; OLF_CUDA(cudaMemcpy(h->tmaps.p, hm, sizeof(hm), cudaMemcpyHostToDevice)); }
+        h->has_tma = h->blur_k == 7 && build_level_maps(h->img.p, T1, 7, h->tmaps[0].m) && build_level_maps(h->img.p, T1, 5, h->tmaps[1].m);
     }
     // guard bands of the pixel records: zero = "final" claims, never a candidate (the grow pass may read, never use them)
     OLF_CUDA(cudaMemset(h->px.p, 0, ((size_t)S + 2 * (h->W + 2)) * sizeof(PxRec)));
@@ -1214,8 +1210,8 @@ static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D, int batch_im
     if (h->blur_k) {
         const LevelTable T = single_level(w, hgt, h->ipitch);
         const int nt = T.tile_start[1];
-        BlurBatch bb; memset(&bb, 0, sizeof(bb)); bb.src[0] = h->img.p; bb.dst[0] = h->blurred.p; bb.maps[0] = h->tmaps.p;
-        if (h->blur_k == 7 && h->has_tma) k_blur_q8_tma<7><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], h->blur_q[3]);
+        BlurBatch bb; memset(&bb, 0, sizeof(bb)); bb.src[0] = h->img.p; bb.dst[0] = h->blurred.p;
+        if (h->blur_k == 7 && h->has_tma) k_blur_q8_tma<7, 1><<<nt, 256, 0, s>>>(bb, h->tmaps[0], T, h->blur_q[0], h->blur_q[1], h->blur_q[2], h->blur_q[3]);
         else if (h->blur_k == 7) k_blur_q8<7><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], h->blur_q[3]);
         else if (h->blur_k == 5) k_blur_q8<5><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], 0);
         else k_blur_q8<3><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], 0, 0);
@@ -1431,8 +1427,8 @@ static int lbd_enqueue(LineImpl* h, const olf_keyline* kls, int n, cudaStream_t 
         h->lbd_lines.p[i] = L;
     }
     const LevelTable T = single_level(w, hgt, h->ipitch);
-    BlurBatch bb; memset(&bb, 0, sizeof(bb)); bb.src[0] = h->img.p; bb.dst[0] = h->lbd_blur.p; bb.maps[0] = h->tmaps.p + 1;
-    if (h->has_tma) k_blur_q8_tma<5><<<T.tile_start[1], 256, 0, s>>>(bb, T, 14, 62, 104, 0);       // 5x5 sigma 1 (:358)
+    BlurBatch bb; memset(&bb, 0, sizeof(bb)); bb.src[0] = h->img.p; bb.dst[0] = h->lbd_blur.p;
+    if (h->has_tma) k_blur_q8_tma<5, 1><<<T.tile_start[1], 256, 0, s>>>(bb, h->tmaps[1], T, 14, 62, 104, 0);       // 5x5 sigma 1 (:358)
     else k_blur_q8<5><<<T.tile_start[1], 256, 0, s>>>(bb, T, 14, 62, 104, 0);
     dim3 g((w + 31) / 32, (hgt + 7) / 8);
     k_sobel3<<<g, 256, 0, s>>>(h->lbd_blur.p, w, hgt, h->ipitch, h->grad.p);

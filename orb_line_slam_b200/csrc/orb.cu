@@ -12,6 +12,7 @@
 #include "orb.h"
 #include "img_kernels.cuh"
 #include "sincosf_exact.h"
+#define ORB_TMA_MAPS 64            // tensor maps per blur launch (8 images x 8 levels), 8 KB of kernel parameters
 #include "../../include/olf_brief_pattern.h"
 #include <algorithm>
 #include <cmath>
@@ -545,7 +546,7 @@ struct OrbImpl {
     PinBuf<uint8_t> desc_host;
     PinBuf<int> out_host;
     PinBuf<uint8_t> img_stage;               // pinned staging for pageable host images
-    DevBuf<CUtensorMap> tmaps; bool has_tma = false;      // one tensor map per pyramid level (TMA tile staging of the 7x7 blur)
+    CUtensorMap tmaps[OLF_MAX_LEVELS]; bool has_tma = false;      // one tensor map per pyramid level (TMA tile staging of the 7x7 blur), passed by value
     int copy_cap = 0;                        // entries copied back by the last enqueue
     int last_ncand = -1;
 };
@@ -629,12 +630,8 @@ static int orb_ensure_size(OrbImpl* h, int w, int hgt) {
     h->out_cap = qoff;
     if ((rc = h->nodes.ensure((size_t)2 * qoff)) || (rc = h->qi.ensure((size_t)12 * qoff)) || (rc = h->qk.ensure((size_t)3 * qoff)) || (rc = h->keep.ensure(qoff)) ||
         (rc = h->kps.ensure(qoff)) || (rc = h->desc.ensure((size_t)qoff * 32)) || (rc = h->kps_host.ensure(qoff)) || (rc = h->desc_host.ensure((size_t)qoff * 32))) return rc;
-    if ((rc = h->img_stage.ensure((size_t)w * hgt)) || (rc = h->tmaps.ensure(OLF_MAX_LEVELS))) return rc;
-    {
-        CUtensorMap hm[OLF_MAX_LEVELS];
-        h->has_tma = build_level_maps(h->pyr.p, T, 7, hm);
-        if (h->has_tma) OLF_CUDA(cudaMemcpy(h->tmaps.p, hm, sizeof(CUtensorMap) * h->nlevels, cudaMemcpyHostToDevice));
-    }
+    if ((rc = h->img_stage.ensure((size_t)w * hgt))) return rc;
+    h->has_tma = build_level_maps(h->pyr.p, T, 7, h->tmaps);
     h->img_w = w; h->img_h = hgt;
     return OLF_OK;
 }
@@ -686,7 +683,7 @@ void orb_destroy(OrbImpl* h) {
     h->pyr.release(); h->score.release(); h->blur.release(); h->coef.release(); h->cell_counts.release(); h->cell_thr.release();
     h->cell_off.release(); h->total.release(); h->ticket.release(); h->cand.release(); h->cnode.release(); h->nodes.release(); h->qi.release();
     h->qk.release(); h->lvl_count.release(); h->keep.release(); h->out.release(); h->kps.release(); h->desc.release();
-    h->kps_host.release(); h->desc_host.release(); h->out_host.release(); h->img_stage.release(); h->tmaps.release();
+    h->kps_host.release(); h->desc_host.release(); h->out_host.release(); h->img_stage.release();
     delete h;
 }
 
@@ -725,7 +722,7 @@ int orb_enqueue(OrbImpl* const* hs, int n, const uint8_t* const* imgs, int w, in
         D.cell_counts = h->cell_counts.p; D.cell_thr = h->cell_thr.p; D.cell_off = h->cell_off.p; D.total = h->total.p; D.ticket = h->ticket.p;
         D.cand = h->cand.p; D.cand_cap = h->cand_cap; D.cnode = h->cnode.p; D.nodes = h->nodes.p; D.qi = h->qi.p; D.qk = h->qk.p;
         D.lvl_count = h->lvl_count.p; D.keep = h->keep.p; D.kps = h->kps.p; D.desc = h->desc.p; D.out = h->out.p; D.out_cap = h->out_cap;
-        BB.src[k] = h->pyr.p; BB.dst[k] = h->blur.p; BB.maps[k] = h->tmaps.p;
+        BB.src[k] = h->pyr.p; BB.dst[k] = h->blur.p;
         OLF_CUDA(cudaMemsetAsync(h->out.p, 0, 4 * sizeof(int), s));
         if (h->ncells == 0) { OLF_CUDA(cudaMemsetAsync(h->total.p, 0, sizeof(int), s)); OLF_CUDA(cudaMemsetAsync(h->lvl_count.p, 0, OLF_MAX_LEVELS * sizeof(int), s)); }
         h->last_ncand = -1;
@@ -738,9 +735,13 @@ int orb_enqueue(OrbImpl* const* hs, int n, const uint8_t* const* imgs, int w, in
     }
     k_fast_score<<<dim3(h0->ntiles, n), 256, 0, s>>>(B, T, h0->min_th);
     // ORB blur: 7x7 sigma 2 -> [18,34,48,56,48,34,18] (:1088)
-    bool all_tma = true;
+    bool all_tma = n * T.n <= ORB_TMA_MAPS;
     for (int k = 0; k < n; ++k) all_tma = all_tma && hs[k]->has_tma;
-    if (all_tma) k_blur_q8_tma<7><<<dim3(h0->ntiles, n), 256, 0, s>>>(BB, T, 18, 34, 48, 56);
+    if (all_tma) {
+        static thread_local TmaSet<ORB_TMA_MAPS> M;
+        for (int k = 0; k < n; ++k) memcpy(&M.m[k * T.n], hs[k]->tmaps, sizeof(CUtensorMap) * T.n);
+        k_blur_q8_tma<7, ORB_TMA_MAPS><<<dim3(h0->ntiles, n), 256, 0, s>>>(BB, M, T, 18, 34, 48, 56);
+    }
     else k_blur_q8<7><<<dim3(h0->ntiles, n), 256, 0, s>>>(BB, T, 18, 34, 48, 56);
     int launches = (h0->nlevels - 1) + 2;
     if (h0->ncells > 0) {
