@@ -266,6 +266,59 @@ typedef struct olf_bow_match_args {
 } olf_bow_match_args;
 int olf_search_by_bow(const olf_bow_match_args* a, int* match_f /* n_f: key-frame feature index or -1 */, int* nmatches, int device);
 
+/* ---- the remaining ORBmatcher overloads (LocalMapping / LoopClosing / relocalisation) ------------------ */
+/* Grid-window search shared by Fuse(KF, MPs, th) (src/ORBmatcher.cc:827-977), Fuse(KF, Scw, MPs, th, replace) (:979-1102),
+ * SearchByProjection(KF, Scw, MPs, matched, th) (:292-405), both directions of SearchBySim3 (:1104-1328) and
+ * SearchByProjection(Frame, KF, found, th, ORBdist) (:1620-1747).  The caller runs the per-point prologue of the overload
+ * (projection with cv::Mat float arithmetic, depth / viewing-angle tests, MapPoint::PredictScale -- O(#points) host geometry)
+ * and hands over one query per surviving point; the library does what is data-parallel: KeyFrame::GetFeaturesInArea
+ * (src/KeyFrame.cc:747-786; src/Frame.cc:517-570 is the same window) over the 64 x 48 grid in the reference's cell-major
+ * order, the octave window, the optional chi-square reprojection gate of Fuse (:916-940), the Hamming distances, the FIRST
+ * minimum (`dist < bestDist`), and -- for the two overloads that write into the searched frame while they loop -- the rule
+ * that a keypoint taken by an earlier query is no longer a candidate (:360,:397; :1691,:1705).
+ * best_idx[i] = keypoint of query i, or -1 when the best admissible distance exceeds max_dist (or there is no candidate);
+ * best_dist[i] = its distance (256 when none). */
+typedef struct olf_window_search_args {
+    const olf_keypoint* kps; const uint8_t* desc; int n;      /* searched keypoints: mvKeysUn, mDescriptors                      */
+    olf_camera cam;                                            /* grid geometry mnMinX.., (bf unused)                             */
+    const float* u_right;                                      /* n, mvuRight: chi2_check only (may be NULL otherwise)            */
+    const float* inv_level_sigma2; int nlevels;                /* mvInvLevelSigma2: chi2_check only                               */
+    int n_queries;
+    const float* u; const float* v; const float* radius;       /* projection and th * mvScaleFactors[nPredictedLevel]             */
+    const float* ur;                                           /* u - bf * invz: chi2_check only                                  */
+    const int* min_level; const int* max_level;                /* octave window of the candidate loop                             */
+    const uint8_t* qdesc;                                      /* n_queries x 32, pMP->GetDescriptor()                            */
+    const uint8_t* blocked;                                    /* n (may be NULL): vpMatched[idx] / mvpMapPoints[i2] on entry     */
+    int sequential_blocking;                                   /* 1: an accepted keypoint blocks the queries after it             */
+    int chi2_check;                                            /* 1: Fuse(KF, MPs, th) reprojection gate (7.8 stereo / 5.99 mono) */
+    int max_dist;                                              /* TH_LOW, TH_HIGH or ORBdist                                      */
+} olf_window_search_args;
+int olf_window_search(const olf_window_search_args* a, int* best_idx, int* best_dist, int device);
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:659-825): for every
+ * vocabulary node both key frames share, each feature of KF1 without a map point takes the feature of KF2 (without a map
+ * point) at minimal Hamming distance <= TH_LOW that passes the epipole and CheckDistEpipolarLine tests (:142-159) -- the LAST
+ * one among equals (`dist > bestDist` rejects) -- then the rotation-histogram filter.  matches12[i1] = i2 or -1. */
+typedef struct olf_triangulation_args {
+    const olf_keypoint* kps1; const uint8_t* desc1; int n1;
+    const uint8_t* skip1;                  /* n1: GetMapPoint(idx1) != NULL                                        */
+    const float* u_right1;                 /* n1: mvuRight (stereo iff >= 0)                                       */
+    const int* fv1_node; const int* fv1_begin; const int* fv1_index; int fv1_n_nodes;
+    const olf_keypoint* kps2; const uint8_t* desc2; int n2;
+    const uint8_t* skip2; const float* u_right2;
+    const int* fv2_node; const int* fv2_begin; const int* fv2_index; int fv2_n_nodes;
+    const float* scale_factors2; const float* level_sigma2_2; int nlevels;     /* pKF2->mvScaleFactors, mvLevelSigma2 */
+    float F12[9];                          /* row major                                                            */
+    float ex, ey;                          /* epipole in the second image (:666-672, computed by the caller)       */
+    int only_stereo; int check_orientation;
+} olf_triangulation_args;
+int olf_search_for_triangulation(const olf_triangulation_args* a, int* matches12 /* n1 */, int* nmatches, int device);
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:524-657): as olf_search_by_bow, but both sides
+ * need a good map point, the acceptance is `best < TH_LOW` (strict) and the result is indexed by the first key frame.
+ * The argument block is the one of olf_search_by_bow (kf = pKF1, f = pKF2, f_kps = pKF2->mvKeysUn) plus has_point2. */
+int olf_search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2 /* n_f */, int* matches12 /* n_kf */, int* nmatches, int device);
+
 /* ---- whole stereo frame: Frame::Frame(stereo+lines) (src/Frame.cc:136-221) ----------------------------------- */
 /* One rig = 2 ORB extractors + 2 line extractors on one device; olf_frontend_process runs ExtractORB(L|R) and
  * ExtractLine(L|R) on its own host threads (src/Frame.cc:164-171), then ComputeStereoMatches and

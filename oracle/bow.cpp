@@ -150,3 +150,60 @@ extern "C" int orc_search_by_bow(const olf_bow_match_args* a, int* match_f, int*
     *nmatches_out = nmatches;
     return OLF_OK;
 }
+
+// SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12)  src/ORBmatcher.cc:524-657 (kf = pKF1, f = pKF2)
+extern "C" int orc_search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int* matches12, int* nmatches_out) {
+    if (!a || !has_point2 || !matches12 || !nmatches_out) return OLF_ERR_ARG;
+    for (int i = 0; i < a->n_kf; ++i) matches12[i] = -1;
+    std::vector<uint8_t> vbMatched2(std::max(a->n_f, 1), 0);
+    int nmatches = 0;
+    std::vector<int> rotHist[OLF_HISTO_LENGTH];
+    const float factor = 1.0f / OLF_HISTO_LENGTH;
+    int i1n = 0, i2n = 0;
+    while (i1n < a->kf_n_nodes && i2n < a->f_n_nodes) {
+        if (a->kf_fv_node[i1n] == a->f_fv_node[i2n]) {
+            for (int p = a->kf_fv_begin[i1n]; p < a->kf_fv_begin[i1n + 1]; ++p) {
+                const int idx1 = a->kf_fv_index[p];
+                if (!a->kf_has_point[idx1]) continue;
+                const uint8_t* d1 = a->kf_desc + (size_t)idx1 * 32;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int q = a->f_fv_begin[i2n]; q < a->f_fv_begin[i2n + 1]; ++q) {
+                    const int idx2 = a->f_fv_index[q];
+                    if (vbMatched2[idx2] || !has_point2[idx2]) continue;
+                    const int dist = hamming256(d1, a->f_desc + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < OLF_TH_LOW) {
+                    if ((float)bestDist1 < a->nn_ratio * (float)bestDist2) {
+                        matches12[idx1] = bestIdx2;
+                        vbMatched2[bestIdx2] = 1;
+                        if (a->check_orientation) {
+                            float rot = a->kf_kps_un[idx1].angle - a->f_kps[bestIdx2].angle;
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)roundf(rot * factor);
+                            if (bin == OLF_HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back(idx1);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            ++i1n; ++i2n;
+        } else if (a->kf_fv_node[i1n] < a->f_fv_node[i2n]) {
+            while (i1n < a->kf_n_nodes && a->kf_fv_node[i1n] < a->f_fv_node[i2n]) ++i1n;
+        } else {
+            while (i2n < a->f_n_nodes && a->f_fv_node[i2n] < a->kf_fv_node[i1n]) ++i2n;
+        }
+    }
+    if (a->check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima_bow(rotHist, OLF_HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < OLF_HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    *nmatches_out = nmatches;
+    return OLF_OK;
+}

@@ -493,3 +493,120 @@ extern "C" int orc_distinctive_descriptors(const uint8_t* desc, const int* group
     }
     return 0;
 }
+
+// ---- the remaining ORBmatcher overloads ----------------------------------------------------------------
+// The candidate loop shared by Fuse (src/ORBmatcher.cc:894-974, 1053-1098), SearchByProjection(KF, Scw, ..) (:344-400), SearchBySim3
+// (:1193-1226, :1273-1306) and SearchByProjection(Frame, KF, found, th, ORBdist) (:1680-1721): KeyFrame::GetFeaturesInArea
+// (src/KeyFrame.cc:747-786) in cell-major order, octave window, optional chi-square gate, first minimum, optional blocking.
+extern "C" int orc_window_search(const olf_window_search_args* a, int* best_idx, int* best_dist) {
+    if (!a || !best_idx || !best_dist) return OLF_ERR_ARG;
+    FrameGrid g;
+    build_grid(a->kps, a->n, a->cam, g);
+    std::vector<uint8_t> blocked(std::max(a->n, 1), 0);
+    if (a->blocked) for (int j = 0; j < a->n; ++j) blocked[j] = a->blocked[j];
+    std::vector<int> cand;
+    for (int i = 0; i < a->n_queries; ++i) {
+        best_idx[i] = -1; best_dist[i] = 256;
+        const float u = a->u[i], v = a->v[i];
+        features_in_area(g, a->kps, u, v, a->radius[i], -1, -1, cand);            // the KeyFrame overload has no level arguments (:747)
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            if (blocked[idx]) continue;
+            const olf_keypoint& kp = a->kps[idx];
+            if (kp.octave < a->min_level[i] || kp.octave > a->max_level[i]) continue;
+            if (a->chi2_check) {                                                 // :916-940
+                const float ex = u - kp.x, ey = v - kp.y;
+                if (a->u_right[idx] >= 0) {
+                    const float er = a->ur[i] - a->u_right[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * a->inv_level_sigma2[kp.octave] > 7.8) continue;
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * a->inv_level_sigma2[kp.octave] > 5.99) continue;
+                }
+            }
+            const int dist = hamming256(a->qdesc + (size_t)i * 32, a->desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestIdx >= 0 && bestDist <= a->max_dist) {
+            best_idx[i] = bestIdx; best_dist[i] = bestDist;
+            if (a->sequential_blocking) blocked[bestIdx] = 1;
+        }
+    }
+    return OLF_OK;
+}
+
+// ORBmatcher::CheckDistEpipolarLine (src/ORBmatcher.cc:142-159)
+static bool check_dist_epipolar_line(const olf_keypoint& kp1, const olf_keypoint& kp2, const float* F12, const float* level_sigma2) {
+    const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+    const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+    const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * level_sigma2[kp2.octave];
+}
+
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:659-825).  vbMatched2 is never set in the reference (:679 is its only
+// write), so a feature of KF2 can serve several features of KF1.
+extern "C" int orc_search_for_triangulation(const olf_triangulation_args* a, int* matches12, int* nmatches_out) {
+    if (!a || !matches12 || !nmatches_out) return OLF_ERR_ARG;
+    int nmatches = 0;
+    for (int i = 0; i < a->n1; ++i) matches12[i] = -1;
+    std::vector<int> rotHist[OLF_HISTO_LENGTH];
+    const float factor = 1.0f / OLF_HISTO_LENGTH;
+    int i1n = 0, i2n = 0;
+    while (i1n < a->fv1_n_nodes && i2n < a->fv2_n_nodes) {
+        if (a->fv1_node[i1n] == a->fv2_node[i2n]) {
+            for (int p = a->fv1_begin[i1n]; p < a->fv1_begin[i1n + 1]; ++p) {
+                const int idx1 = a->fv1_index[p];
+                if (a->skip1[idx1]) continue;
+                const bool bStereo1 = a->u_right1[idx1] >= 0;
+                if (a->only_stereo && !bStereo1) continue;
+                const olf_keypoint& kp1 = a->kps1[idx1];
+                int bestDist = OLF_TH_LOW, bestIdx2 = -1;
+                for (int q = a->fv2_begin[i2n]; q < a->fv2_begin[i2n + 1]; ++q) {
+                    const int idx2 = a->fv2_index[q];
+                    if (a->skip2[idx2]) continue;
+                    const bool bStereo2 = a->u_right2[idx2] >= 0;
+                    if (a->only_stereo && !bStereo2) continue;
+                    const int dist = hamming256(a->desc1 + (size_t)idx1 * 32, a->desc2 + (size_t)idx2 * 32);
+                    if (dist > OLF_TH_LOW || dist > bestDist) continue;
+                    const olf_keypoint& kp2 = a->kps2[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = a->ex - kp2.x, distey = a->ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * a->scale_factors2[kp2.octave]) continue;
+                    }
+                    if (check_dist_epipolar_line(kp1, kp2, a->F12, a->level_sigma2_2)) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (a->check_orientation) {
+                        float rot = kp1.angle - a->kps2[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)roundf(rot * factor);
+                        if (bin == OLF_HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                }
+            }
+            ++i1n; ++i2n;
+        } else if (a->fv1_node[i1n] < a->fv2_node[i2n]) {
+            while (i1n < a->fv1_n_nodes && a->fv1_node[i1n] < a->fv2_node[i2n]) ++i1n;      // lower_bound (:785)
+        } else {
+            while (i2n < a->fv2_n_nodes && a->fv2_node[i2n] < a->fv1_node[i1n]) ++i2n;
+        }
+    }
+    if (a->check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, OLF_HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < OLF_HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    *nmatches_out = nmatches;
+    return OLF_OK;
+}

@@ -47,6 +47,10 @@ int orc_search_by_projection_last(const olf_sbp_last_args* a, int* assigned_cur,
 int orc_search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* nmatches);
 /* MapPoint / MapLine::ComputeDistinctiveDescriptors (src/MapPoint.cc:254-322, src/MapLine.cc:257-322), batched */
 int orc_distinctive_descriptors(const uint8_t* desc, const int* group_begin, int n_groups, int* best);
+/* the remaining ORBmatcher overloads (src/ORBmatcher.cc:292-405, 659-1328, 1620-1747) */
+int orc_window_search(const olf_window_search_args* a, int* best_idx, int* best_dist);
+int orc_search_for_triangulation(const olf_triangulation_args* a, int* matches12, int* nmatches);
+int orc_search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int* matches12, int* nmatches);
 /* bag of words (oracle/bow.cpp) */
 typedef struct orc_vocab orc_vocab;
 orc_vocab* orc_vocab_create(const olf_vocab_desc* v);

@@ -275,9 +275,11 @@ template <typename F> inline Mat mat_zip(const Mat& a, const Mat& b, F f) {
 inline Mat operator+(const Mat& a, const Mat& b) { return mat_zip(a, b, [](auto x, auto y) { return x + y; }); }
 inline Mat operator-(const Mat& a, const Mat& b) { return mat_zip(a, b, [](auto x, auto y) { return x - y; }); }
 inline Mat operator-(const Mat& a) { Mat m(a.rows, a.cols, a.type()); for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) { if (a.depth() == CV_32F) m.at<float>(r, c) = -a.at<float>(r, c); else m.at<double>(r, c) = -a.at<double>(r, c); } return m; }
-inline Mat operator*(const Mat& a, double s) { Mat m(a.rows, a.cols, a.type()); for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) { if (a.depth() == CV_32F) m.at<float>(r, c) = (float)(a.at<float>(r, c) * s); else m.at<double>(r, c) = a.at<double>(r, c) * s; } return m; }
+// MatExpr scaling (Mat * double, Mat / double): OpenCV evaluates it as a.convertTo(dst, -1, alpha) whose CV_32F kernel (cvtScale32f) multiplies
+// by the alpha ROUNDED TO FLOAT, one float product per element; a / s is a * (1. / s) (MatExpr operator/ in matop.cpp)
+inline Mat operator*(const Mat& a, double s) { Mat m(a.rows, a.cols, a.type()); const float sf = (float)s; for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) { if (a.depth() == CV_32F) m.at<float>(r, c) = a.at<float>(r, c) * sf; else m.at<double>(r, c) = a.at<double>(r, c) * s; } return m; }
 inline Mat operator*(double s, const Mat& a) { return a * s; }
-inline Mat operator/(const Mat& a, double s) { Mat m(a.rows, a.cols, a.type()); for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) { if (a.depth() == CV_32F) m.at<float>(r, c) = (float)(a.at<float>(r, c) / s); else m.at<double>(r, c) = a.at<double>(r, c) / s; } return m; }
+inline Mat operator/(const Mat& a, double s) { return a * (1. / s); }
 // cv::norm(Mat) L2 of a small float vector: double accumulation, sqrt (OpenCV's normL2_32f accumulates in double)
 inline double norm(const Mat& a) { double s = 0; for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) { const double v = a.depth() == CV_32F ? (double)a.at<float>(r, c) : a.at<double>(r, c); s += v * v; } return std::sqrt(s); }
 // cv::norm(a, b, NORM_L1) on 8-bit windows (Frame.cc:820): integer sum of absolute differences

@@ -9,7 +9,9 @@
 #include "eigen_stub.hpp"
 #include <line_descriptor/descriptor_custom.hpp>
 #include "ORBextractor.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
 #include <mutex>
+#include <set>
 #include <utility>
 using namespace std;
 using namespace Eigen;
@@ -18,10 +20,44 @@ using namespace Eigen;
 #define FRAME_GRID_COLS 64
 
 namespace ORB_SLAM2 {
-class Map; class KeyFrameDatabase; class Frame;
-class KeyFrame { public: std::vector<float> mvLevelSigma2; cv::Mat mDescriptors; bool bad_ = false; bool isBad() { return bad_; } };
+class Map; class KeyFrameDatabase; class Frame; class MapPoint;
+// include/KeyFrame.h: the members the ORBmatcher overloads of LocalMapping / LoopClosing / relocalisation touch (same names and types;
+// GetFeaturesInArea and IsInImage are the reference's own text, sliced from src/KeyFrame.cc)
+class KeyFrame {
+public:
+    std::vector<float> mvLevelSigma2, mvInvLevelSigma2, mvScaleFactors; cv::Mat mDescriptors; bool bad_ = false; bool isBad() { return bad_; }
+    cv::Mat GetRotation() { return Rcw_.clone(); }
+    cv::Mat GetTranslation() { return tcw_.clone(); }
+    cv::Mat GetCameraCenter() { return Ow_.clone(); }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> s; for (MapPoint* p : mvpMapPoints) if (p) s.insert(p); return s; }
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
+    bool IsInImage(const float& x, const float& y) const;
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0;
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeysUn; std::vector<float> mvuRight;
+    DBoW2::FeatureVector mFeatVec;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;     // const int in the reference
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0, mfLogScaleFactor = 0; int mnScaleLevels = 0;
+    std::vector<std::vector<std::vector<size_t>>> mGrid;
+    std::vector<MapPoint*> mvpMapPoints;
+    cv::Mat Rcw_, tcw_, Ow_;
+};
 class MapPoint {
 public:
+    // LocalMapping / LoopClosing side (include/MapPoint.h); PredictScale and Get*DistanceInvariance are sliced from src/MapPoint.cc
+    cv::Mat GetNormal() { return normal_.clone(); }
+    float GetMinDistanceInvariance();
+    float GetMaxDistanceInvariance();
+    int PredictScale(const float& currentDist, KeyFrame* pKF);
+    int PredictScale(const float& currentDist, Frame* pF);
+    bool IsInKeyFrame(KeyFrame* pKF) { return in_kf_ == pKF; }
+    int GetIndexInKeyFrame(KeyFrame* pKF) { return in_kf_ == pKF ? kf_idx_ : -1; }
+    void AddObservation(KeyFrame* pKF, size_t idx) { fused_ = (int)idx; (void)pKF; }
+    void Replace(MapPoint* pMP) { if (fused_ < 0) fused_ = pMP->fused_; else if (pMP->fused_ < 0) pMP->fused_ = fused_; }      // records where the pair met
+    std::mutex mMutexPos; float mfMinDistance = 0, mfMaxDistance = 0; cv::Mat normal_; KeyFrame* in_kf_ = nullptr; int kf_idx_ = -1, fused_ = -1;
     // set by Frame::isInFrustum (src/Frame.cc:436-441)
     float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0; bool mbTrackInView = false; int mnTrackScaleLevel = 0; float mTrackViewCos = 0;
     long unsigned int mnLastFrameSeen = 0;

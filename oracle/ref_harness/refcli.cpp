@@ -49,6 +49,7 @@ ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbChe
 #include "orbmatcher.inc"
 #include "frame.inc"
 #include "mappoint.inc"
+#include "keyframe.inc"
 }
 
 // ---- array file protocol ------------------------------------------------------------------------------------------------
@@ -125,6 +126,43 @@ static void fill_frame_points(ORB_SLAM2::Frame& F, ORB_SLAM2::ORBextractor& ex, 
     F.mvScaleFactors = ex.GetScaleFactors(); F.mvInvScaleFactors = ex.GetInverseScaleFactors(); F.mnScaleLevels = ex.GetLevels();
     F.mvpMapPoints.assign(F.N, static_cast<ORB_SLAM2::MapPoint*>(NULL)); F.mvbOutlier.assign(F.N, false);
     F.AssignFeaturesToGrid();
+}
+
+// ---- key frames and map points for Fuse / SearchBySim3 / SearchByProjection(KF|reloc) / SearchForTriangulation / SearchByBoW(KF,KF)
+// cam = fx fy cx cy bf w h; pose = Rcw[9] tcw[3] Ow[3] (may be null: identity); the grid is the Frame's (KeyFrame copies F.mGrid, src/KeyFrame.cc:49-54)
+static void fill_keyframe(ORB_SLAM2::KeyFrame& K, ORB_SLAM2::ORBextractor& ex, Arr& kps, Arr& desc, Arr* uright, Arr& cam, const float* pose) {
+    using namespace ORB_SLAM2;
+    Frame F; fill_frame_points(F, ex, kps, desc, cam);
+    K.mvKeysUn = F.mvKeysUn; K.N = F.N; K.mDescriptors = F.mDescriptors.clone();
+    K.mvuRight.assign(K.N, -1.f); if (uright && uright->count()) K.mvuRight.assign(uright->as<float>(), uright->as<float>() + uright->count());
+    K.fx = F.fx; K.fy = F.fy; K.cx = F.cx; K.cy = F.cy; K.mbf = F.mbf;
+    K.mnMinX = (int)F.mnMinX; K.mnMinY = (int)F.mnMinY; K.mnMaxX = (int)F.mnMaxX; K.mnMaxY = (int)F.mnMaxY;
+    K.mfGridElementWidthInv = F.mfGridElementWidthInv; K.mfGridElementHeightInv = F.mfGridElementHeightInv;
+    K.mGrid.resize(K.mnGridCols);
+    for (int i = 0; i < K.mnGridCols; ++i) { K.mGrid[i].resize(K.mnGridRows); for (int j = 0; j < K.mnGridRows; ++j) K.mGrid[i][j] = F.mGrid[i][j]; }
+    K.mvScaleFactors = ex.GetScaleFactors(); K.mvLevelSigma2 = ex.GetScaleSigmaSquares(); K.mvInvLevelSigma2 = ex.GetInverseScaleSigmaSquares();
+    K.mnScaleLevels = ex.GetLevels(); K.mfLogScaleFactor = log(ex.GetScaleFactor());            // src/Frame.cc:149: log(float) under `using namespace std`
+    K.mvpMapPoints.assign(K.N, static_cast<MapPoint*>(NULL));
+    if (pose) { K.Rcw_ = mat_f32(pose, 3, 3); K.tcw_ = mat_f32(pose + 9, 3, 1); K.Ow_ = mat_f32(pose + 12, 3, 1); }
+}
+// map points: pos f32[n,3], normal f32[n,3] (or empty), maxd f32[n], mind f32[n], desc u8[n,32], obs i32[n] (or empty)
+static void fill_points(std::vector<ORB_SLAM2::MapPoint>& pts, Arr& pos, Arr* normal, Arr& maxd, Arr& mind, Arr& desc, Arr* obs) {
+    const int n = (int)maxd.count();
+    pts = std::vector<ORB_SLAM2::MapPoint>(n);
+    for (int i = 0; i < n; ++i) {
+        ORB_SLAM2::MapPoint& m = pts[i];
+        m.pos_ = mat_f32(pos.as<float>() + 3 * i, 3, 1);
+        if (normal && normal->count()) m.normal_ = mat_f32(normal->as<float>() + 3 * i, 3, 1);
+        m.mfMaxDistance = maxd.as<float>()[i]; m.mfMinDistance = mind.as<float>()[i];
+        m.desc_ = cv::Mat(1, 32, CV_8UC1); memcpy(m.desc_.ptr(), desc.as<uchar>() + (size_t)32 * i, 32);
+        m.nobs_ = obs && obs->count() ? obs->as<int>()[i] : 1;
+    }
+}
+static void fill_featvec(DBoW2::FeatureVector& fv, Arr& node, Arr& begin, Arr& index) {
+    for (size_t a = 0; a < node.count(); ++a) {
+        std::vector<unsigned int>& v = fv[(DBoW2::NodeId)node.as<int>()[a]];
+        for (int p = begin.as<int>()[a]; p < begin.as<int>()[a + 1]; ++p) v.push_back((unsigned)index.as<int>()[p]);
+    }
 }
 
 int main(int argc, char** argv) {
@@ -254,6 +292,102 @@ int main(int argc, char** argv) {
             for (int i = 0; i < N && !mp.mDescriptor.empty(); ++i) if (!memcmp(mp.mDescriptor.ptr(), kfs[i].mDescriptors.ptr(), 32)) { best[g] = i; break; }
         }
         out.push_back(make<int>(1, {(long long)ng}, best.data()));
+    } else if (cmd == "fuse" || cmd == "fuse_sim3" || cmd == "sbp_kf") {
+        // in: kf kps, desc, uRight, cam f32[7], pose (fuse: Rcw tcw Ow f32[15]; others: Scw f32[16]), pos, normal, maxd, mind, pdesc, obs i32[n],
+        //     blocked u8[n_kf] (sbp_kf: vpMatched entries on entry; else empty), th f32[1], orb i32[5], scale f32[1]
+        // -> per point: the key-frame feature it met (-1: none), return value
+        Arr &ck = in[0], &cd = in[1], &cu = in[2], &cam = in[3], &pose = in[4];
+        const int* p = in[13].as<int>();
+        ORBextractor ex(p[0], in[14].as<float>()[0], p[1], p[2], p[3]);
+        KeyFrame KF; fill_keyframe(KF, ex, ck, cd, &cu, cam, cmd == "fuse" ? pose.as<float>() : nullptr);
+        std::vector<MapPoint> pts; fill_points(pts, in[5], &in[6], in[7], in[8], in[9], &in[10]);
+        const int np = (int)pts.size();
+        std::vector<MapPoint*> vp(np); for (int i = 0; i < np; ++i) vp[i] = &pts[i];
+        const float th = in[12].as<float>()[0];
+        ORBmatcher matcher(0.8, true);
+        std::vector<int> res(np, -1); int n = 0;
+        if (cmd == "fuse") {
+            n = matcher.Fuse(&KF, vp, th);
+            for (int i = 0; i < np; ++i) res[i] = pts[i].fused_;
+        } else if (cmd == "fuse_sim3") {
+            std::vector<MapPoint*> repl(np, static_cast<MapPoint*>(NULL));
+            n = matcher.Fuse(&KF, mat_f32(pose.as<float>(), 4, 4), vp, th, repl);
+            for (int i = 0; i < np; ++i) res[i] = repl[i] ? repl[i]->fused_ : pts[i].fused_;
+        } else {
+            MapPoint marker;
+            std::vector<MapPoint*> matched(KF.N, static_cast<MapPoint*>(NULL));
+            for (int j = 0; j < KF.N && in[11].count(); ++j) if (in[11].as<uchar>()[j]) matched[j] = &marker;
+            n = matcher.SearchByProjection(&KF, mat_f32(pose.as<float>(), 4, 4), vp, matched, (int)th);
+            for (int j = 0; j < KF.N; ++j) if (matched[j] && matched[j] != &marker) res[(int)(matched[j] - pts.data())] = j;
+        }
+        out.push_back(make<int>(1, {(long long)np}, res.data())); out.push_back(make<int>(1, {1}, &n));
+    } else if (cmd == "sim3") {
+        // in: kps1, desc1, pose1 f32[15], has1 u8[N1], pos1, maxd1, mind1, pdesc1, kps2, desc2, pose2 f32[15], has2 u8[N2], pos2, maxd2, mind2, pdesc2,
+        //     cam f32[7], sim f32[13] (s12, R12[9], t12[3]), th f32[1], orb i32[5], scale f32[1] -> matches12 i32[N1] (index into KF2), nFound
+        const int* p = in[19].as<int>();
+        ORBextractor ex(p[0], in[20].as<float>()[0], p[1], p[2], p[3]);
+        KeyFrame K1, K2; fill_keyframe(K1, ex, in[0], in[1], nullptr, in[16], in[2].as<float>()); fill_keyframe(K2, ex, in[8], in[9], nullptr, in[16], in[10].as<float>());
+        std::vector<MapPoint> p1, p2; fill_points(p1, in[4], nullptr, in[5], in[6], in[7], nullptr); fill_points(p2, in[12], nullptr, in[13], in[14], in[15], nullptr);
+        for (int i = 0; i < K1.N; ++i) if (in[3].as<uchar>()[i]) K1.mvpMapPoints[i] = &p1[i];
+        for (int i = 0; i < K2.N; ++i) if (in[11].as<uchar>()[i]) K2.mvpMapPoints[i] = &p2[i];
+        const float* sm = in[17].as<float>();
+        std::vector<MapPoint*> m12(K1.N, static_cast<MapPoint*>(NULL));
+        ORBmatcher matcher(0.75, true);
+        const float s12 = sm[0];
+        const int n = matcher.SearchBySim3(&K1, &K2, m12, s12, mat_f32(sm + 1, 3, 3), mat_f32(sm + 10, 3, 1), in[18].as<float>()[0]);
+        std::vector<int> res(K1.N, -1);
+        for (int i = 0; i < K1.N; ++i) if (m12[i]) res[i] = (int)(m12[i] - p2.data());
+        out.push_back(make<int>(1, {(long long)K1.N}, res.data())); out.push_back(make<int>(1, {1}, &n));
+    } else if (cmd == "reloc") {
+        // in: cur kps, desc, cam f32[7], Tcw (R, t) f32[12], occupied u8[n_cur], kf kps, has u8[n_kf], pos, maxd, mind, pdesc, th_dist f32[2], orb, scale
+        // -> SearchByProjection(CurrentFrame, pKF, sAlreadyFound = {}, th, ORBdist) with mbCheckOrientation = false: cur_point i32[n_cur], n
+        const int* p = in[12].as<int>();
+        ORBextractor ex(p[0], in[13].as<float>()[0], p[1], p[2], p[3]);
+        Frame Cur; fill_frame_points(Cur, ex, in[0], in[1], in[2]);
+        Cur.mfScaleFactor = ex.GetScaleFactor(); Cur.mfLogScaleFactor = log(Cur.mfScaleFactor);
+        const float* ps = in[3].as<float>();
+        Cur.mTcw = cv::Mat::eye(4, 4, CV_32F); for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Cur.mTcw.at<float>(r, c) = ps[3 * r + c]; Cur.mTcw.at<float>(r, 3) = ps[9 + r]; }
+        MapPoint marker;
+        for (int j = 0; j < Cur.N; ++j) if (in[4].as<uchar>()[j]) Cur.mvpMapPoints[j] = &marker;
+        Arr kdesc = make<uchar>(0, {(long long)in[5].dims[0], 32}, in[10].as<uchar>());
+        KeyFrame KF; fill_keyframe(KF, ex, in[5], kdesc, nullptr, in[2], nullptr);
+        std::vector<MapPoint> pts; fill_points(pts, in[7], nullptr, in[8], in[9], in[10], nullptr);
+        for (int i = 0; i < KF.N; ++i) if (in[6].as<uchar>()[i]) KF.mvpMapPoints[i] = &pts[i];
+        ORBmatcher matcher(0.9, false);
+        std::set<MapPoint*> found;
+        const int n = matcher.SearchByProjection(Cur, &KF, found, in[11].as<float>()[0], (int)in[11].as<float>()[1]);
+        std::vector<int> res(Cur.N, -1);
+        for (int j = 0; j < Cur.N; ++j) if (Cur.mvpMapPoints[j] && Cur.mvpMapPoints[j] != &marker) res[j] = (int)(Cur.mvpMapPoints[j] - pts.data());
+        out.push_back(make<int>(1, {(long long)Cur.N}, res.data())); out.push_back(make<int>(1, {1}, &n));
+    } else if (cmd == "triangulation" || cmd == "bow_kf") {
+        // in: kps1, desc1, skip1 u8, uRight1, node1, begin1, index1, kps2, desc2, skip2, uRight2, node2, begin2, index2, cam f32[7],
+        //     geo f32[24] (Cw[3], R2w[9], t2w[3], F12[9]), flags f32[3] (only_stereo, check_orientation, nn_ratio), orb, scale
+        // -> matches12 i32[n1], return value.  skip = "has a map point" for triangulation, = "has NO good map point" for bow_kf
+        const int* p = in[17].as<int>();
+        ORBextractor ex(p[0], in[18].as<float>()[0], p[1], p[2], p[3]);
+        const float* geo = in[15].as<float>(); const float* fl = in[16].as<float>();
+        float pose1[15] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, geo[0], geo[1], geo[2]}, pose2[15];
+        memcpy(pose2, geo + 3, 12 * sizeof(float)); pose2[12] = pose2[13] = pose2[14] = 0;
+        KeyFrame K1, K2; fill_keyframe(K1, ex, in[0], in[1], &in[3], in[14], pose1); fill_keyframe(K2, ex, in[7], in[8], &in[10], in[14], pose2);
+        fill_featvec(K1.mFeatVec, in[4], in[5], in[6]); fill_featvec(K2.mFeatVec, in[11], in[12], in[13]);
+        MapPoint marker;                                   // a good map point
+        std::vector<int> res(K1.N, -1); int n = 0;
+        ORBmatcher matcher(fl[2], fl[1] != 0);
+        if (cmd == "triangulation") {
+            for (int i = 0; i < K1.N; ++i) if (in[2].as<uchar>()[i]) K1.mvpMapPoints[i] = &marker;
+            for (int i = 0; i < K2.N; ++i) if (in[9].as<uchar>()[i]) K2.mvpMapPoints[i] = &marker;
+            std::vector<std::pair<size_t, size_t>> pairs;
+            n = matcher.SearchForTriangulation(&K1, &K2, mat_f32(geo + 15, 3, 3), pairs, fl[0] != 0);
+            for (auto& pr : pairs) res[pr.first] = (int)pr.second;
+        } else {
+            std::vector<MapPoint> m2(K2.N);
+            for (int i = 0; i < K1.N; ++i) if (!in[2].as<uchar>()[i]) K1.mvpMapPoints[i] = &marker;
+            for (int i = 0; i < K2.N; ++i) if (!in[9].as<uchar>()[i]) K2.mvpMapPoints[i] = &m2[i];
+            std::vector<MapPoint*> m12;
+            n = matcher.SearchByBoW(&K1, &K2, m12);
+            for (int i = 0; i < K1.N; ++i) if (m12[i]) res[i] = (int)(m12[i] - m2.data());
+        }
+        out.push_back(make<int>(1, {(long long)K1.N}, res.data())); out.push_back(make<int>(1, {1}, &n));
     } else { fprintf(stderr, "refcli: unknown command %s\n", cmd.c_str()); return 2; }
     write_arrays(argv[3], out);
     return 0;

@@ -38,8 +38,21 @@ SLICES = {
     "orbmatcher.inc": [("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)"),
                        ("src/ORBmatcher.cc", "float ORBmatcher::RadiusByViewingCos("),
                        ("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono, map<int, int>& match12)"),
-                       ("src/ORBmatcher.cc", "void ORBmatcher::ComputeThreeMaxima("), ("src/ORBmatcher.cc", "int ORBmatcher::DescriptorDistance(")],
-    "mappoint.inc": [("src/MapPoint.cc", "void MapPoint::ComputeDistinctiveDescriptors()")],
+                       ("src/ORBmatcher.cc", "void ORBmatcher::ComputeThreeMaxima("), ("src/ORBmatcher.cc", "int ORBmatcher::DescriptorDistance("),
+                       # SURVEY 8f rank 2
+                       ("src/ORBmatcher.cc", "bool ORBmatcher::CheckDistEpipolarLine("),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw,"),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2,"),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchForTriangulation("),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th)"),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw,"),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchBySim3("),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF,")],
+    "mappoint.inc": [("src/MapPoint.cc", "void MapPoint::ComputeDistinctiveDescriptors()"),
+                     ("src/MapPoint.cc", "float MapPoint::GetMinDistanceInvariance()"), ("src/MapPoint.cc", "float MapPoint::GetMaxDistanceInvariance()"),
+                     ("src/MapPoint.cc", "int MapPoint::PredictScale(const float &currentDist, KeyFrame* pKF)"),
+                     ("src/MapPoint.cc", "int MapPoint::PredictScale(const float &currentDist, Frame* pF)")],
+    "keyframe.inc": [("src/KeyFrame.cc", "vector<size_t> KeyFrame::GetFeaturesInArea("), ("src/KeyFrame.cc", "bool KeyFrame::IsInImage(")],
     "frame.inc": [("src/Frame.cc", "void Frame::AssignFeaturesToGrid()"), ("src/Frame.cc", "vector<size_t> Frame::GetFeaturesInArea("),
                   ("src/Frame.cc", "bool Frame::PosInGrid("), ("src/Frame.cc", "void Frame::ComputeStereoMatches()"),
                   ("src/Frame.cc", "void Frame::ComputeStereoMatches_Lines("), ("src/Frame.cc", "double Frame::lineSegmentOverlapStereo("),

@@ -95,6 +95,23 @@ class SbpMapArgs(C.Structure):
                 ("view_cos", _P), ("point_observed", _P), ("point_desc", _P), ("th", C.c_float), ("nn_ratio", C.c_float)]
 
 
+class WindowSearchArgs(C.Structure):
+    """olf_window_search_args (include/olf_abi.h): the grid-window search shared by Fuse / SearchBySim3 / SearchByProjection(KF|reloc)."""
+    _fields_ = [("kps", _P), ("desc", _P), ("n", C.c_int), ("cam", Camera), ("u_right", _P), ("inv_level_sigma2", _P), ("nlevels", C.c_int),
+                ("n_queries", C.c_int), ("u", _P), ("v", _P), ("radius", _P), ("ur", _P), ("min_level", _P), ("max_level", _P), ("qdesc", _P),
+                ("blocked", _P), ("sequential_blocking", C.c_int), ("chi2_check", C.c_int), ("max_dist", C.c_int)]
+
+
+class TriangulationArgs(C.Structure):
+    """olf_triangulation_args (include/olf_abi.h): ORBmatcher::SearchForTriangulation."""
+    _fields_ = [("kps1", _P), ("desc1", _P), ("n1", C.c_int), ("skip1", _P), ("u_right1", _P),
+                ("fv1_node", _P), ("fv1_begin", _P), ("fv1_index", _P), ("fv1_n_nodes", C.c_int),
+                ("kps2", _P), ("desc2", _P), ("n2", C.c_int), ("skip2", _P), ("u_right2", _P),
+                ("fv2_node", _P), ("fv2_begin", _P), ("fv2_index", _P), ("fv2_n_nodes", C.c_int),
+                ("scale_factors2", _P), ("level_sigma2_2", _P), ("nlevels", C.c_int),
+                ("F12", C.c_float * 9), ("ex", C.c_float), ("ey", C.c_float), ("only_stereo", C.c_int), ("check_orientation", C.c_int)]
+
+
 def ptr(a):
     """void* of a contiguous numpy array (or None)."""
     if a is None:
@@ -351,6 +368,53 @@ class FrontEndApi:
         m = np.zeros(max(len(keep[6]), 1), np.int32); n = C.c_int(0)
         self.check(self.fn("search_by_bow")(C.byref(a), ptr(m), C.byref(n), *self._dev), "search_by_bow")
         return m[:len(keep[6])], n.value
+
+    # ---- the remaining ORBmatcher overloads ----
+    def search_by_bow_kf(self, d1, kps1, has1, fv1, d2, kps2, has2, fv2, nn_ratio=0.75, check_orientation=True):
+        """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*): returns (matches12 over KF1 features, n)."""
+        keep = [np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(kps1), np.ascontiguousarray(has1, np.uint8),
+                np.ascontiguousarray(fv1[0], np.int32), np.ascontiguousarray(fv1[1], np.int32), np.ascontiguousarray(fv1[2], np.int32),
+                np.ascontiguousarray(d2, np.uint8), np.ascontiguousarray(kps2),
+                np.ascontiguousarray(fv2[0], np.int32), np.ascontiguousarray(fv2[1], np.int32), np.ascontiguousarray(fv2[2], np.int32),
+                np.ascontiguousarray(has2, np.uint8)]
+        a = BowMatchArgs(ptr(keep[0]), ptr(keep[1]), len(keep[0]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(keep[5]), len(keep[3]),
+                         ptr(keep[6]), ptr(keep[7]), len(keep[6]), ptr(keep[8]), ptr(keep[9]), ptr(keep[10]), len(keep[8]),
+                         nn_ratio, int(check_orientation))
+        m = np.zeros(max(len(keep[0]), 1), np.int32); n = C.c_int(0)
+        self.check(self.fn("search_by_bow_kf")(C.byref(a), ptr(keep[11]), ptr(m), C.byref(n), *self._dev), "search_by_bow_kf")
+        return m[:len(keep[0])], n.value
+
+    def window_search(self, kps, desc, cam: Camera, u, v, radius, min_level, max_level, qdesc, max_dist, blocked=None, sequential=False,
+                      chi2=None):
+        """olf_window_search; chi2 = (u_right, inv_level_sigma2, ur) switches the Fuse reprojection gate on.  Returns (best_idx, best_dist)."""
+        f32 = lambda x: np.ascontiguousarray(x, np.float32)
+        keep = [np.ascontiguousarray(kps), np.ascontiguousarray(desc, np.uint8), f32(u), f32(v), f32(radius),
+                np.ascontiguousarray(min_level, np.int32), np.ascontiguousarray(max_level, np.int32), np.ascontiguousarray(qdesc, np.uint8),
+                None if blocked is None else np.ascontiguousarray(blocked, np.uint8)]
+        ck = [None, None, None] if chi2 is None else [f32(chi2[0]), f32(chi2[1]), f32(chi2[2])]
+        nq = len(keep[2])
+        a = WindowSearchArgs(ptr(keep[0]), ptr(keep[1]), len(keep[0]), cam, ptr(ck[0]), ptr(ck[1]), 0 if chi2 is None else len(ck[1]),
+                             nq, ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(ck[2]), ptr(keep[5]), ptr(keep[6]), ptr(keep[7]),
+                             ptr(keep[8]), int(sequential), int(chi2 is not None), int(max_dist))
+        bi = np.zeros(max(nq, 1), np.int32); bd = np.zeros(max(nq, 1), np.int32)
+        self.check(self.fn("window_search")(C.byref(a), ptr(bi), ptr(bd), *self._dev), "window_search")
+        return bi[:nq], bd[:nq]
+
+    def search_for_triangulation(self, kf1: dict, kf2: dict, F12, ex, ey, only_stereo=False, check_orientation=False):
+        """kf = dict(kps, desc, skip, u_right, fv=(node, begin, index)); kf2 also scale_factors, level_sigma2.  Returns (matches12, n)."""
+        f32 = lambda x: np.ascontiguousarray(x, np.float32)
+        i32 = lambda x: np.ascontiguousarray(x, np.int32)
+        k = [np.ascontiguousarray(kf1["kps"]), np.ascontiguousarray(kf1["desc"], np.uint8), np.ascontiguousarray(kf1["skip"], np.uint8), f32(kf1["u_right"]),
+             i32(kf1["fv"][0]), i32(kf1["fv"][1]), i32(kf1["fv"][2]),
+             np.ascontiguousarray(kf2["kps"]), np.ascontiguousarray(kf2["desc"], np.uint8), np.ascontiguousarray(kf2["skip"], np.uint8), f32(kf2["u_right"]),
+             i32(kf2["fv"][0]), i32(kf2["fv"][1]), i32(kf2["fv"][2]), f32(kf2["scale_factors"]), f32(kf2["level_sigma2"])]
+        a = TriangulationArgs(ptr(k[0]), ptr(k[1]), len(k[0]), ptr(k[2]), ptr(k[3]), ptr(k[4]), ptr(k[5]), ptr(k[6]), len(k[4]),
+                              ptr(k[7]), ptr(k[8]), len(k[7]), ptr(k[9]), ptr(k[10]), ptr(k[11]), ptr(k[12]), ptr(k[13]), len(k[11]),
+                              ptr(k[14]), ptr(k[15]), len(k[14]), (C.c_float * 9)(*[float(x) for x in np.asarray(F12, np.float32).ravel()]),
+                              float(np.float32(ex)), float(np.float32(ey)), int(only_stereo), int(check_orientation))
+        m = np.zeros(max(len(k[0]), 1), np.int32); n = C.c_int(0)
+        self.check(self.fn("search_for_triangulation")(C.byref(a), ptr(m), C.byref(n), *self._dev), "search_for_triangulation")
+        return m[:len(k[0])], n.value
 
     def search_by_projection_map(self, args: SbpMapArgs, keep):
         a = np.zeros(args.n_points, np.int32); n = C.c_int(0)

@@ -154,4 +154,7 @@ int olf_bow_assemble(const int* word_id, const double* weight, const int* node_i
     return bow_assemble(word_id, weight, node_id, n, bow_word, bow_value, n_words, fv_node, fv_begin, fv_index, n_nodes);
 }
 int olf_search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches, int device) { return search_by_bow(a, match_f, nmatches, device); }
+int olf_search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int* matches12, int* nmatches, int device) { return search_by_bow_kf(a, has_point2, matches12, nmatches, device); }
+int olf_window_search(const olf_window_search_args* a, int* best_idx, int* best_dist, int device) { return window_search(a, best_idx, best_dist, device); }
+int olf_search_for_triangulation(const olf_triangulation_args* a, int* matches12, int* nmatches, int device) { return search_for_triangulation(a, matches12, nmatches, device); }
 }

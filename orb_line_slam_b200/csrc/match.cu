@@ -829,7 +829,10 @@ typedef unsigned long long u64;
 // lexicographic key (dist, ix, iy, j).  Lists are written sorted by that key.
 __global__ void __launch_bounds__(256) k_sbp_candidates(const SbpQuery* __restrict__ q, const uint32_t* __restrict__ qdesc, int nq,
                                                         const olf_keypoint* __restrict__ kps, const uint32_t* __restrict__ desc, const float* __restrict__ uRight, int n_cur,
-                                                        GridParams G, int max_dist, u64* __restrict__ lists, int* __restrict__ counts) {
+                                                        GridParams G, int max_dist, int gate, const float* __restrict__ inv_sigma2,
+                                                        u64* __restrict__ lists, int* __restrict__ counts) {
+    // gate 1: |ur - uRight[j]| <= radius for stereo keypoints (SearchByProjection last frame / local map, :1556-1561, :93-98)
+    // gate 2: chi-square reprojection gate of Fuse(KF, MPs, th) (:916-940); gate 0: none (KeyFrame window searches)
     __shared__ u64 sh[8][SBP_K];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + w;
@@ -856,7 +859,14 @@ __global__ void __launch_bounds__(256) k_sbp_candidates(const SbpQuery* __restri
                        posX >= nMinCellX && posX <= nMaxCellX && posY >= nMinCellY && posY <= nMaxCellY;
                 if (take && check_levels) { if (kp.octave < Q.min_level) take = false; if (Q.max_level >= 0 && kp.octave > Q.max_level) take = false; }
                 if (take) take = fabsf(fsub(kp.x, Q.u)) < Q.radius && fabsf(fsub(kp.y, Q.v)) < Q.radius;
-                if (take) { const float ur = uRight[j]; if (ur > 0 && fabsf(fsub(Q.ur, ur)) > Q.radius) take = false; }
+                if (take && gate == 1) { const float ur = uRight[j]; if (ur > 0 && fabsf(fsub(Q.ur, ur)) > Q.radius) take = false; }
+                if (take && gate == 2) {
+                    const float ex = fsub(Q.u, kp.x), ey = fsub(Q.v, kp.y), kpr = uRight[j];
+                    float e2 = fadd(fmul(ex, ex), fmul(ey, ey));
+                    double lim = 5.99;
+                    if (kpr >= 0) { const float er = fsub(Q.ur, kpr); e2 = fadd(e2, fmul(er, er)); lim = 7.8; }
+                    if ((double)fmul(e2, inv_sigma2[kp.octave]) > lim) take = false;
+                }
                 if (take) {
                     const int d = hamming256(a, desc + (size_t)j * 8);
                     if (d > max_dist) take = false;
@@ -929,7 +939,7 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(const u64* __restrict__ li
 
 static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t* qdesc, const uint8_t* observed, const uint8_t* occupied,
                       const olf_keypoint* cur_kps, const uint8_t* cur_desc, const float* cur_u_right, int n_cur, const olf_camera& cam,
-                      int mode, int max_dist, float nn_ratio, int* assign_out) {
+                      int mode, int max_dist, float nn_ratio, int* assign_out, int gate = 1, const float* inv_sigma2 = nullptr, int nlevels = 0, int* dist_out = nullptr) {
     const int nq = (int)q.size();
     int rc;
     if (n_cur >= (1 << 24)) { set_last_error("olf_search_by_projection: too many keypoints"); return OLF_ERR_CAPACITY; }
@@ -937,7 +947,8 @@ static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t
     const size_t o_q = pl.d((size_t)nq * sizeof(SbpQuery)), o_qd = pl.d((size_t)nq * 32), o_obs = pl.d(nq), o_occ = pl.d(std::max(n_cur, 1));
     const size_t o_k = pl.d((size_t)n_cur * sizeof(olf_keypoint)), o_d = pl.d((size_t)n_cur * 32), o_u = pl.d((size_t)n_cur * 4);
     const size_t o_lists = pl.d((size_t)nq * SBP_K * 8), o_cnt = pl.d((size_t)nq * 4), o_oa = pl.d((size_t)n_cur * 4), o_ob = pl.d((size_t)n_cur * 4), o_as = pl.d((size_t)nq * 4), o_r = pl.d(4);
-    const size_t p_in = pl.p((size_t)nq * (sizeof(SbpQuery) + 33) + (size_t)n_cur * (sizeof(olf_keypoint) + 37) + 64), p_out = pl.p((size_t)nq * 8 + 16);
+    const size_t o_sig = pl.d((size_t)OLF_MAX_LEVELS * 4);
+    const size_t p_in = pl.p((size_t)nq * (sizeof(SbpQuery) + 33) + (size_t)n_cur * (sizeof(olf_keypoint) + 37) + 64 + OLF_MAX_LEVELS * 4), p_out = pl.p((size_t)nq * 8 + 16 + (size_t)nq * SBP_K * 8);
     if ((rc = arena_ensure(c, pl))) return rc;
     cudaStream_t s = c->cur;
     uint8_t* hp = hptr<uint8_t>(c, p_in);
@@ -951,23 +962,31 @@ static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t
         return OLF_OK;
     };
     if ((rc = up(o_q, q.data(), (size_t)nq * sizeof(SbpQuery))) || (rc = up(o_qd, qdesc, (size_t)nq * 32)) || (rc = up(o_obs, observed, nq)) ||
-        (rc = up(o_k, cur_kps, (size_t)n_cur * sizeof(olf_keypoint))) || (rc = up(o_d, cur_desc, (size_t)n_cur * 32)) || (rc = up(o_u, cur_u_right, (size_t)n_cur * 4))) return rc;
+        (rc = up(o_k, cur_kps, (size_t)n_cur * sizeof(olf_keypoint))) || (rc = up(o_d, cur_desc, (size_t)n_cur * 32))) return rc;
+    if (cur_u_right && (rc = up(o_u, cur_u_right, (size_t)n_cur * 4))) return rc;
+    if (gate == 2 && (rc = up(o_sig, inv_sigma2, (size_t)std::min(nlevels, OLF_MAX_LEVELS) * 4))) return rc;
     if (occupied && (rc = up(o_occ, occupied, n_cur))) return rc;
     GridParams G; G.min_x = cam.min_x; G.min_y = cam.min_y;
     G.inv_w = (float)OLF_GRID_COLS / (cam.max_x - cam.min_x); G.inv_h = (float)OLF_GRID_ROWS / (cam.max_y - cam.min_y);       // src/Frame.cc:185-186
     k_sbp_candidates<<<(nq + 7) / 8, 256, 0, s>>>(dptr<SbpQuery>(c, o_q), dptr<uint32_t>(c, o_qd), nq, dptr<olf_keypoint>(c, o_k), dptr<uint32_t>(c, o_d), dptr<float>(c, o_u), n_cur,
-                                                  G, max_dist, dptr<u64>(c, o_lists), dptr<int>(c, o_cnt));
+                                                  G, max_dist, gate, dptr<float>(c, o_sig), dptr<u64>(c, o_lists), dptr<int>(c, o_cnt));
     k_sbp_resolve<<<1, 1024, 0, s>>>(dptr<u64>(c, o_lists), dptr<int>(c, o_cnt), nq, n_cur, dptr<uint8_t>(c, o_obs), occupied ? dptr<uint8_t>(c, o_occ) : nullptr,
                                      dptr<olf_keypoint>(c, o_k), mode, nn_ratio, dptr<int>(c, o_oa), dptr<int>(c, o_ob), dptr<int>(c, o_as), dptr<int>(c, o_r));
     count_launches(2);
     int* ho = hptr<int>(c, p_out);
     OLF_CUDA(cudaMemcpyAsync(ho, dptr<int>(c, o_as), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(ho + nq, dptr<int>(c, o_cnt), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    u64* hl = (u64*)(ho + 2 * nq + 4);
+    if (dist_out) OLF_CUDA(cudaMemcpyAsync(hl, dptr<u64>(c, o_lists), (size_t)nq * SBP_K * 8, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(stream_sync(s));
     for (int i = 0; i < nq; ++i) {
         if (ho[nq + i] > SBP_K) { set_last_error("olf_search_by_projection: more than 128 candidates in one search window"); return OLF_ERR_CAPACITY; }
         assign_out[i] = ho[i];
+        if (dist_out) {          // distance of the chosen candidate: its key in the query's list
+            dist_out[i] = 256;
+            for (int e = 0; e < ho[nq + i] && ho[i] >= 0; ++e) if ((int)(hl[(size_t)i * SBP_K + e] & 0xFFFFFF) == ho[i]) { dist_out[i] = (int)(hl[(size_t)i * SBP_K + e] >> 40); break; }
+        }
     }
     return OLF_OK;
 }
@@ -1064,6 +1083,171 @@ int search_by_projection_map(const olf_sbp_map_args* a, int* assigned_cur, int* 
     int n = 0;
     for (int i = 0; i < a->n_points; ++i) n += assigned_cur[i] >= 0;
     *nmatches_out = n;
+    return OLF_OK;
+}
+
+// ======================================================================================================
+// grid-window search of Fuse / SearchByProjection(KF, Scw) / SearchBySim3 / SearchByProjection(Frame, KF)
+// (src/ORBmatcher.cc:292-405, 827-1328, 1620-1747) on the candidate / resolve kernels above
+// ======================================================================================================
+int window_search(const olf_window_search_args* a, int* best_idx, int* best_dist, int device) {
+    if (!a || !best_idx || !best_dist || a->n < 0 || a->n_queries < 0 || (a->n_queries > 0 && (!a->u || !a->v || !a->radius || !a->min_level || !a->max_level || !a->qdesc)) ||
+        (a->chi2_check && (!a->u_right || !a->inv_level_sigma2 || !a->ur || a->nlevels < 1 || a->nlevels > OLF_MAX_LEVELS)) || a->max_dist < 0) {
+        set_last_error("olf_window_search: bad arguments"); return OLF_ERR_ARG;
+    }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    for (int i = 0; i < a->n_queries; ++i) { best_idx[i] = -1; best_dist[i] = 256; }
+    if (a->n == 0 || a->n_queries == 0) return OLF_OK;
+    if (!a->kps || !a->desc) { set_last_error("olf_window_search: bad arguments"); return OLF_ERR_ARG; }
+    std::vector<SbpQuery> q(a->n_queries);
+    std::vector<uint8_t> observed(a->n_queries, a->sequential_blocking ? 1 : 0);
+    for (int i = 0; i < a->n_queries; ++i) {
+        SbpQuery& Q = q[i];
+        Q.u = a->u[i]; Q.v = a->v[i]; Q.radius = a->radius[i]; Q.ur = a->ur ? a->ur[i] : 0.f;
+        // an octave window [min, max]; max < 0 would switch the level test off in the kernel (Frame::GetFeaturesInArea semantics), so an
+        // empty window is expressed as an invalid query
+        Q.min_level = a->min_level[i]; Q.max_level = a->max_level[i]; Q.valid = a->max_level[i] >= 0 && a->max_level[i] >= a->min_level[i];
+    }
+    return sbp_common(c, q, a->qdesc, observed.data(), a->blocked, a->kps, a->desc, a->u_right, a->n, a->cam, 0, std::min(a->max_dist, 256), 0.f, best_idx,
+                      a->chi2_check ? 2 : 0, a->inv_level_sigma2, a->nlevels, best_dist);
+}
+
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:659-825): a warp per feature of KF1 (the features are independent: the
+// reference never sets vbMatched2), the features of KF2 in the same vocabulary node over the lanes; minimum distance, the LAST
+// position among equals (`dist > bestDist` rejects, so an equal later candidate replaces)
+struct TriItem { int idx1, b2, e2; };
+__global__ void __launch_bounds__(128) k_triangulate(const TriItem* __restrict__ items, int n_items, const olf_keypoint* __restrict__ kps1, const uint4* __restrict__ desc1,
+                                                     const float* __restrict__ ur1, const olf_keypoint* __restrict__ kps2, const uint4* __restrict__ desc2,
+                                                     const uint8_t* __restrict__ skip2, const float* __restrict__ ur2, const int* __restrict__ idx2s,
+                                                     const float* __restrict__ sf2, const float* __restrict__ sig2, const float* __restrict__ F, float ex, float ey,
+                                                     int only_stereo, int* __restrict__ m12) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_items) return;
+    const TriItem it = items[w];
+    const olf_keypoint kp1 = kps1[it.idx1];
+    const bool stereo1 = ur1[it.idx1] >= 0;
+    const uint4 a = desc1[2 * it.idx1], b = desc1[2 * it.idx1 + 1];
+    // epipolar line of kp1 in the second image (:145-147)
+    const float la = fadd(fadd(fmul(kp1.x, F[0]), fmul(kp1.y, F[3])), F[6]);
+    const float lb = fadd(fadd(fmul(kp1.x, F[1]), fmul(kp1.y, F[4])), F[7]);
+    const float lc = fadd(fadd(fmul(kp1.x, F[2]), fmul(kp1.y, F[5])), F[8]);
+    const float den = fadd(fmul(la, la), fmul(lb, lb));
+    int best = INT_MAX, pos = -1, bi = -1;
+    for (int q = it.b2 + lane; q < it.e2; q += 32) {
+        const int j = idx2s[q];
+        if (skip2[j]) continue;
+        const bool stereo2 = ur2[j] >= 0;
+        if (only_stereo && !stereo2) continue;
+        const uint4 x = desc2[2 * j], y = desc2[2 * j + 1];
+        const int d = __popc(a.x ^ x.x) + __popc(a.y ^ x.y) + __popc(a.z ^ x.z) + __popc(a.w ^ x.w) +
+                      __popc(b.x ^ y.x) + __popc(b.y ^ y.y) + __popc(b.z ^ y.z) + __popc(b.w ^ y.w);
+        if (d > OLF_TH_LOW) continue;
+        const olf_keypoint kp2 = kps2[j];
+        if (!stereo1 && !stereo2) {
+            const float dx = fsub(ex, kp2.x), dy = fsub(ey, kp2.y);
+            if (fadd(fmul(dx, dx), fmul(dy, dy)) < fmul(100.f, sf2[kp2.octave])) continue;
+        }
+        if (den == 0) continue;
+        const float num = fadd(fadd(fmul(la, kp2.x), fmul(lb, kp2.y)), lc);
+        const float dsqr = fdiv(fmul(num, num), den);
+        if (!((double)dsqr < __dmul_rn(3.84, (double)sig2[kp2.octave]))) continue;
+        if (d < best || (d == best && q > pos)) { best = d; pos = q; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int eb = __shfl_xor_sync(0xffffffffu, best, o), ep = __shfl_xor_sync(0xffffffffu, pos, o), ei = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (eb < best || (eb == best && ep > pos)) { best = eb; pos = ep; bi = ei; }
+    }
+    if (lane == 0) m12[it.idx1] = bi;
+}
+
+static void rotation_filter(const std::vector<std::pair<int, float>>& rots, std::vector<int>& reject) {     // (entry, angle difference) -> entries of the pruned bins
+    std::vector<int> rot[OLF_HISTO_LENGTH];
+    const float factor = 1.0f / OLF_HISTO_LENGTH;
+    for (const auto& e : rots) {
+        float r = e.second;
+        if (r < 0.0) r += 360.0f;
+        int bin = (int)roundf(r * factor);
+        if (bin == OLF_HISTO_LENGTH) bin = 0;
+        rot[bin].push_back(e.first);
+    }
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;          // ComputeThreeMaxima (:1749-1790)
+    for (int i = 0; i < OLF_HISTO_LENGTH; i++) {
+        const int sz = (int)rot[i].size();
+        if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+        else if (sz > max3) { max3 = sz; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) ind3 = -1;
+    for (int i = 0; i < OLF_HISTO_LENGTH; i++)
+        if (i != ind1 && i != ind2 && i != ind3) for (int e : rot[i]) reject.push_back(e);
+}
+
+int search_for_triangulation(const olf_triangulation_args* a, int* matches12, int* nmatches_out, int device) {
+    if (!a || !matches12 || !nmatches_out || a->n1 < 0 || a->n2 < 0 || a->fv1_n_nodes < 0 || a->fv2_n_nodes < 0 || a->nlevels < 1 || a->nlevels > OLF_MAX_LEVELS) {
+        set_last_error("olf_search_for_triangulation: bad arguments"); return OLF_ERR_ARG;
+    }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    *nmatches_out = 0;
+    for (int i = 0; i < a->n1; ++i) matches12[i] = -1;
+    if (a->n1 == 0 || a->n2 == 0 || a->fv1_n_nodes == 0 || a->fv2_n_nodes == 0) return OLF_OK;
+    std::vector<TriItem> items;
+    for (int i = 0, j = 0; i < a->fv1_n_nodes && j < a->fv2_n_nodes;) {
+        if (a->fv1_node[i] == a->fv2_node[j]) {
+            for (int p = a->fv1_begin[i]; p < a->fv1_begin[i + 1]; ++p) {
+                const int idx1 = a->fv1_index[p];
+                if (a->skip1[idx1] || (a->only_stereo && !(a->u_right1[idx1] >= 0))) continue;
+                items.push_back({idx1, a->fv2_begin[j], a->fv2_begin[j + 1]});
+            }
+            ++i; ++j;
+        } else if (a->fv1_node[i] < a->fv2_node[j]) ++i;
+        else ++j;
+    }
+    if (items.empty()) return OLF_OK;
+    const int ni = (int)items.size(), n2i = a->fv2_begin[a->fv2_n_nodes];
+    Planner pl;
+    const size_t o_it = pl.d((size_t)ni * sizeof(TriItem)), o_k1 = pl.d((size_t)a->n1 * sizeof(olf_keypoint)), o_d1 = pl.d((size_t)a->n1 * 32), o_u1 = pl.d((size_t)a->n1 * 4),
+                 o_k2 = pl.d((size_t)a->n2 * sizeof(olf_keypoint)), o_d2 = pl.d((size_t)a->n2 * 32), o_s2 = pl.d((size_t)a->n2), o_u2 = pl.d((size_t)a->n2 * 4),
+                 o_i2 = pl.d((size_t)n2i * 4), o_sf = pl.d(OLF_MAX_LEVELS * 4), o_sg = pl.d(OLF_MAX_LEVELS * 4), o_F = pl.d(64), o_m = pl.d((size_t)a->n1 * 4);
+    const size_t in_bytes = (size_t)ni * sizeof(TriItem) + (size_t)a->n1 * (sizeof(olf_keypoint) + 36) + (size_t)a->n2 * (sizeof(olf_keypoint) + 37) + (size_t)n2i * 4 + 2 * OLF_MAX_LEVELS * 4 + 64;
+    const size_t p_in = pl.p(in_bytes + 256), p_m = pl.p((size_t)a->n1 * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->cur;
+    uint8_t* hp = hptr<uint8_t>(c, p_in);
+    size_t off = 0;
+    auto up = [&](size_t dev_off, const void* src, size_t bytes) -> int {
+        if (!bytes) return OLF_OK;
+        memcpy(hp + off, src, bytes);
+        cudaError_t e = cudaMemcpyAsync(c->a.dev.p + dev_off, hp + off, bytes, cudaMemcpyHostToDevice, s);
+        off += (bytes + 15) & ~(size_t)15;
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+        return OLF_OK;
+    };
+    if ((rc = up(o_it, items.data(), (size_t)ni * sizeof(TriItem))) || (rc = up(o_k1, a->kps1, (size_t)a->n1 * sizeof(olf_keypoint))) || (rc = up(o_d1, a->desc1, (size_t)a->n1 * 32)) ||
+        (rc = up(o_u1, a->u_right1, (size_t)a->n1 * 4)) || (rc = up(o_k2, a->kps2, (size_t)a->n2 * sizeof(olf_keypoint))) || (rc = up(o_d2, a->desc2, (size_t)a->n2 * 32)) ||
+        (rc = up(o_s2, a->skip2, (size_t)a->n2)) || (rc = up(o_u2, a->u_right2, (size_t)a->n2 * 4)) || (rc = up(o_i2, a->fv2_index, (size_t)n2i * 4)) ||
+        (rc = up(o_sf, a->scale_factors2, (size_t)a->nlevels * 4)) || (rc = up(o_sg, a->level_sigma2_2, (size_t)a->nlevels * 4)) || (rc = up(o_F, a->F12, 36))) return rc;
+    OLF_CUDA(cudaMemsetAsync(dptr<int>(c, o_m), 0xFF, (size_t)a->n1 * 4, s));
+    k_triangulate<<<(ni * 32 + 127) / 128, 128, 0, s>>>(dptr<TriItem>(c, o_it), ni, dptr<olf_keypoint>(c, o_k1), dptr<uint4>(c, o_d1), dptr<float>(c, o_u1),
+                                                        dptr<olf_keypoint>(c, o_k2), dptr<uint4>(c, o_d2), dptr<uint8_t>(c, o_s2), dptr<float>(c, o_u2), dptr<int>(c, o_i2),
+                                                        dptr<float>(c, o_sf), dptr<float>(c, o_sg), dptr<float>(c, o_F), a->ex, a->ey, a->only_stereo, dptr<int>(c, o_m));
+    count_launches(1);
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_m), dptr<int>(c, o_m), (size_t)a->n1 * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(stream_sync(s));
+    memcpy(matches12, hptr<int>(c, p_m), (size_t)a->n1 * 4);
+    int nm = 0;
+    std::vector<std::pair<int, float>> rots;
+    for (int i = 0; i < a->n1; ++i) if (matches12[i] >= 0) { ++nm; rots.push_back({i, a->kps1[i].angle - a->kps2[matches12[i]].angle}); }
+    if (a->check_orientation) {
+        std::vector<int> reject;
+        rotation_filter(rots, reject);
+        for (int i : reject) { matches12[i] = -1; --nm; }
+    }
+    *nmatches_out = nm;
     return OLF_OK;
 }
 
@@ -1201,8 +1385,10 @@ int bow_assemble(const int* word_id, const double* weight, const int* node_id, i
 struct BowPair { int kf_b, kf_e, f_b, f_e; };
 __global__ void __launch_bounds__(128) k_bow_match(const BowPair* __restrict__ pairs, int n_pairs, const uint4* __restrict__ kf_desc,
                                                    const uint8_t* __restrict__ kf_has, const int* __restrict__ kf_idx,
-                                                   const uint4* __restrict__ f_desc, const int* __restrict__ f_idx, float nn_ratio,
-                                                   int* match_f) {
+                                                   const uint4* __restrict__ f_desc, const int* __restrict__ f_idx, const uint8_t* __restrict__ f_has, int accept_below,
+                                                   float nn_ratio, int* match_f) {
+    // f_has / accept_below: SearchByBoW(KF, KF) needs a good map point on the second side too and accepts best < TH_LOW
+    // (src/ORBmatcher.cc:580-585, 606); SearchByBoW(KF, Frame) accepts best <= TH_LOW (:234): accept_below = TH_LOW + 1
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_pairs) return;
     const BowPair P = pairs[w];
@@ -1214,6 +1400,7 @@ __global__ void __launch_bounds__(128) k_bow_match(const BowPair* __restrict__ p
         for (int q = P.f_b + lane; q < P.f_e; q += 32) {
             const int jf = f_idx[q];
             if (*(volatile int*)&match_f[jf] >= 0) continue;
+            if (f_has && !f_has[jf]) continue;
             const uint4 x = f_desc[2 * jf], y = f_desc[2 * jf + 1];
             const int d = __popc(a.x ^ x.x) + __popc(a.y ^ x.y) + __popc(a.z ^ x.z) + __popc(a.w ^ x.w) +
                           __popc(b.x ^ y.x) + __popc(b.y ^ y.y) + __popc(b.z ^ y.z) + __popc(b.w ^ y.w);
@@ -1227,11 +1414,11 @@ __global__ void __launch_bounds__(128) k_bow_match(const BowPair* __restrict__ p
             if (e1 < d1 || (e1 == d1 && ep < pos1)) { d2 = min(e2, d1); d1 = e1; pos1 = ep; i1 = ei; }
             else d2 = min(d2, e1);
         }
-        if (lane == 0 && i1 >= 0 && d1 <= OLF_TH_LOW && (float)d1 < fmul(nn_ratio, (float)d2)) match_f[i1] = ikf;
+        if (lane == 0 && i1 >= 0 && d1 < accept_below && (float)d1 < fmul(nn_ratio, (float)d2)) match_f[i1] = ikf;
         __syncwarp();
     }
 }
-int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches_out, int device) {
+static int bow_match_common(const olf_bow_match_args* a, const uint8_t* f_has, int accept_below, int* match_f, int* nmatches_out, int device) {
     if (!a || !match_f || !nmatches_out || a->n_kf < 0 || a->n_f < 0) { set_last_error("olf_search_by_bow: bad arguments"); return OLF_ERR_ARG; }
     MatchCtx* c; int rc;
     if ((rc = get_ctx(device, &c))) return rc;
@@ -1248,9 +1435,9 @@ int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches_out, 
     const int nkf_idx = a->kf_fv_begin[a->kf_n_nodes], nf_idx = a->f_fv_begin[a->f_n_nodes], np = (int)pairs.size();
     Planner pl;
     const size_t o_kd = pl.d((size_t)a->n_kf * 32), o_kh = pl.d((size_t)a->n_kf), o_ki = pl.d((size_t)nkf_idx * 4), o_fd = pl.d((size_t)a->n_f * 32),
-                 o_fi = pl.d((size_t)nf_idx * 4), o_p = pl.d((size_t)np * sizeof(BowPair)), o_m = pl.d((size_t)a->n_f * 4);
+                 o_fi = pl.d((size_t)nf_idx * 4), o_p = pl.d((size_t)np * sizeof(BowPair)), o_m = pl.d((size_t)a->n_f * 4), o_fh = pl.d((size_t)a->n_f);
     const size_t p_kd = pl.p((size_t)a->n_kf * 32), p_kh = pl.p((size_t)a->n_kf), p_ki = pl.p((size_t)nkf_idx * 4), p_fd = pl.p((size_t)a->n_f * 32),
-                 p_fi = pl.p((size_t)nf_idx * 4), p_p = pl.p((size_t)np * sizeof(BowPair)), p_m = pl.p((size_t)a->n_f * 4);
+                 p_fi = pl.p((size_t)nf_idx * 4), p_p = pl.p((size_t)np * sizeof(BowPair)), p_m = pl.p((size_t)a->n_f * 4), p_fh = pl.p((size_t)a->n_f);
     if ((rc = arena_ensure(c, pl))) return rc;
     cudaStream_t s = c->cur;
     auto up = [&](size_t po, size_t dof, const void* src, size_t bytes) -> cudaError_t {
@@ -1260,9 +1447,11 @@ int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches_out, 
     OLF_CUDA(up(p_kd, o_kd, a->kf_desc, (size_t)a->n_kf * 32)); OLF_CUDA(up(p_kh, o_kh, a->kf_has_point, (size_t)a->n_kf));
     OLF_CUDA(up(p_ki, o_ki, a->kf_fv_index, (size_t)nkf_idx * 4)); OLF_CUDA(up(p_fd, o_fd, a->f_desc, (size_t)a->n_f * 32));
     OLF_CUDA(up(p_fi, o_fi, a->f_fv_index, (size_t)nf_idx * 4)); OLF_CUDA(up(p_p, o_p, pairs.data(), (size_t)np * sizeof(BowPair)));
+    if (f_has) OLF_CUDA(up(p_fh, o_fh, f_has, (size_t)a->n_f));
     OLF_CUDA(cudaMemsetAsync(dptr<int>(c, o_m), 0xFF, (size_t)a->n_f * 4, s));
     k_bow_match<<<(np * 32 + 127) / 128, 128, 0, s>>>(dptr<BowPair>(c, o_p), np, dptr<uint4>(c, o_kd), dptr<uint8_t>(c, o_kh), dptr<int>(c, o_ki),
-                                                      dptr<uint4>(c, o_fd), dptr<int>(c, o_fi), a->nn_ratio, dptr<int>(c, o_m));
+                                                      dptr<uint4>(c, o_fd), dptr<int>(c, o_fi), f_has ? dptr<uint8_t>(c, o_fh) : nullptr, accept_below,
+                                                      a->nn_ratio, dptr<int>(c, o_m));
     count_launches(1);
     OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_m), dptr<int>(c, o_m), (size_t)a->n_f * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
@@ -1299,6 +1488,18 @@ int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches_out, 
         }
     }
     *nmatches_out = nm;
+    return OLF_OK;
+}
+int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches_out, int device) { return bow_match_common(a, nullptr, OLF_TH_LOW + 1, match_f, nmatches_out, device); }
+// SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:524-657): a feature of KF2 is matched at most once, so the
+// per-KF2 result inverts into the reference's per-KF1 vector
+int search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int* matches12, int* nmatches_out, int device) {
+    if (!a || !has_point2 || !matches12 || !nmatches_out || a->n_kf < 0 || a->n_f < 0) { set_last_error("olf_search_by_bow_kf: bad arguments"); return OLF_ERR_ARG; }
+    std::vector<int> match_f(std::max(a->n_f, 1), -1);
+    for (int i = 0; i < a->n_kf; ++i) matches12[i] = -1;
+    const int rc = bow_match_common(a, has_point2, OLF_TH_LOW, match_f.data(), nmatches_out, device);
+    if (rc) return rc;
+    for (int j = 0; j < a->n_f; ++j) if (match_f[j] >= 0) matches12[match_f[j]] = j;
     return OLF_OK;
 }
 

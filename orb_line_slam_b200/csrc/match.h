@@ -38,4 +38,7 @@ int bow_transform(VocabImpl* V, const uint8_t* desc, int n, int levelsup, int* w
 int bow_assemble(const int* word_id, const double* weight, const int* node_id, int n, int* bow_word, double* bow_value, int* n_words,
                  int* fv_node, int* fv_begin, int* fv_index, int* n_nodes);
 int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches, int device);
+int search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int* matches12, int* nmatches, int device);
+int window_search(const olf_window_search_args* a, int* best_idx, int* best_dist, int device);
+int search_for_triangulation(const olf_triangulation_args* a, int* matches12, int* nmatches, int device);
 }
