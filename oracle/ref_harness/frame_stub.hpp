@@ -97,6 +97,7 @@ public:
     cv::Mat mDescriptors, mDescriptorsRight, mDescriptors_Line, mDescriptorsRight_Line;
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
+    DBoW2::FeatureVector mFeatVec;
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     cv::Mat mTcw;

@@ -2,7 +2,7 @@
 // Replaces those two member function bodies of src/Frame.cc: the stereo point matcher reads the
 // pyramids where the extractors left them -- on the device -- instead of ORBextractor::mvImagePyramid, and the line matcher
 // runs grid construction, matchGrid and the geometric filters as one call.
-#include "Frame.h"
+#include "olf_ref_classes.h"
 #include "ORBextractor.h"
 #include "LineMatcher.h"
 #include <cstring>

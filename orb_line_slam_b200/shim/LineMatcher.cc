@@ -1,6 +1,6 @@
 #include "LineMatcher.h"
 #include "ORBextractor.h"
-#include "Frame.h"
+#include "olf_ref_classes.h"
 #include <climits>
 #include <stdexcept>
 #include <string>

@@ -6,7 +6,11 @@
 #include <vector>
 #include <utility>
 #include "cv_min.h"
-#include "gridStructure.h"
+#ifdef OLF_IN_REFERENCE_TREE
+#include "gridStructure.h"          // the reference's own (include/gridStructure.h)
+#else
+#include "standin/gridStructure.h"
+#endif
 #include "../../include/olf_abi.h"
 
 namespace ORB_SLAM2 {

@@ -1,6 +1,5 @@
 // The hot overloads of ORB_SLAM2::ORBmatcher on the B200 (replaces src/ORBmatcher.cc:47-131, 161-290, 1330-1472, 1474-1618).
-#include "ORBmatcher.h"
-#include "Frame.h"
+#include "olf_ref_classes.h"
 #include "../../include/olf_abi.h"
 #include <cstring>
 #include <stdexcept>
@@ -19,6 +18,17 @@ int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {        
     int dist = 0;
     for (int i = 0; i < 8; i++) dist += __builtin_popcount(pa[i] ^ pb[i]);
     return dist;
+}
+void ORBmatcher::ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3) {      // :1749-1790 (stays in src/ORBmatcher.cc in the reference tree)
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) ind3 = -1;
 }
 #define OLF_MATCHER_DEVICE ORBmatcher::device
 #else

@@ -10,6 +10,7 @@
 #include <opencv2/core/core.hpp>
 #include <line_descriptor_custom.hpp>
 #else
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -44,6 +45,13 @@ public:
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     template <typename T> T& at(int r, int c) { return ((T*)(data + (size_t)r * step))[c]; }
     template <typename T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step))[c]; }
+    template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }                  // vector access, as cv::Mat::at(int)
+    template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    Mat rowRange(int a, int b) const { Mat m = row(a); m.rows = b - a; return m; }
+    Mat colRange(int a, int b) const { Mat m = *this; m.cols = b - a; m.data = data + (size_t)a * elem(); return m; }
+    Mat col(int c) const { return colRange(c, c + 1); }
+    Mat t() const { Mat m(cols, rows, type_); for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) m.at<float>(c, r) = at<float>(r, c); return m; }
+    double dot(const Mat& o) const { double s = 0; for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) s += (double)at<float>(r, c) * o.at<float>(r, c); return s; }
     Mat row(int r) const { Mat m; m.rows = 1; m.cols = cols; m.step = step; m.data = data + (size_t)r * step; m.type_ = type_; m.buf_ = buf_; return m; }
     Mat clone() const { Mat m(rows, cols, type_); for (int r = 0; r < rows; ++r) memcpy(m.ptr(r), ptr(r), (size_t)cols * elem()); return m; }
     void copyTo(Mat& o) const { o = clone(); }
@@ -52,6 +60,21 @@ private:
     int type_ = CV_8UC1;
     std::shared_ptr<std::vector<uchar>> buf_;
 };
+// The CV_32F matrix algebra the ORBmatcher overloads use on 3x3 / 3x1 / 4x4 matrices, with OpenCV's arithmetic: small float gemm = row . column
+// accumulated left to right in float (pinned by tests/golden: cv2.gemm), MatExpr scaling multiplies by the scalar rounded to float (cvtScale32f),
+// a / s = a * (1. / s), cv::norm and Mat::dot accumulate in double.
+inline Mat operator*(const Mat& a, const Mat& b) {
+    Mat m(a.rows, b.cols, CV_32F);
+    for (int r = 0; r < a.rows; ++r) for (int c = 0; c < b.cols; ++c) { float s = a.at<float>(r, 0) * b.at<float>(0, c); for (int k = 1; k < a.cols; ++k) s = s + a.at<float>(r, k) * b.at<float>(k, c); m.at<float>(r, c) = s; }
+    return m;
+}
+inline Mat operator+(const Mat& a, const Mat& b) { Mat m(a.rows, a.cols, CV_32F); for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) m.at<float>(r, c) = a.at<float>(r, c) + b.at<float>(r, c); return m; }
+inline Mat operator-(const Mat& a, const Mat& b) { Mat m(a.rows, a.cols, CV_32F); for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) m.at<float>(r, c) = a.at<float>(r, c) - b.at<float>(r, c); return m; }
+inline Mat operator-(const Mat& a) { Mat m(a.rows, a.cols, CV_32F); for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) m.at<float>(r, c) = -a.at<float>(r, c); return m; }
+inline Mat operator*(const Mat& a, double s) { Mat m(a.rows, a.cols, CV_32F); const float sf = (float)s; for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) m.at<float>(r, c) = a.at<float>(r, c) * sf; return m; }
+inline Mat operator*(double s, const Mat& a) { return a * s; }
+inline Mat operator/(const Mat& a, double s) { return a * (1. / s); }
+inline double norm(const Mat& a) { double s = 0; for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) { const double v = a.at<float>(r, c); s += v * v; } return std::sqrt(s); }
 class _InputArray {
 public:
     _InputArray() {}

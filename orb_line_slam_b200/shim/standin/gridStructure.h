@@ -3,9 +3,6 @@
 // reference's own gridStructure.cpp / LineIterator.cpp (OpenCV-free, 160 lines) stay as they are; this header is the
 // stand-in for builds outside it.  Storage is one flat vector of cells; the API is the reference's.
 #pragma once
-#ifdef OLF_IN_REFERENCE_TREE
-#include "gridStructure.h"
-#else
 #include <list>
 #include <stdexcept>
 #include <unordered_set>
@@ -52,4 +49,3 @@ inline void getLineCoords(double x1, double y1, double x2, double y2, std::list<
     }
 }
 }  // namespace ORB_SLAM2
-#endif

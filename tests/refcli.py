@@ -18,6 +18,11 @@ def available() -> bool:
 
 
 def run(cmd: str, *arrays):
+    return run_exe(EXE, cmd, *arrays)
+
+
+def run_exe(exe, cmd: str, *arrays):
+    """The array-file protocol with any executable that speaks it (oracle/_ref/refcli, tests/shim/_test_shim_kf)."""
     with tempfile.TemporaryDirectory() as d:
         fin, fout = pathlib.Path(d) / "in.bin", pathlib.Path(d) / "out.bin"
         with open(fin, "wb") as f:
@@ -25,9 +30,9 @@ def run(cmd: str, *arrays):
             for a in arrays:
                 a = np.ascontiguousarray(a)
                 f.write(struct.pack("<ii", _DT[a.dtype], a.ndim)); f.write(struct.pack(f"<{a.ndim}q", *a.shape)); f.write(a.tobytes())
-        r = subprocess.run([str(EXE), cmd, str(fin), str(fout)], capture_output=True, text=True)
+        r = subprocess.run([str(exe), cmd, str(fin), str(fout)], capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f"refcli {cmd} failed ({r.returncode}): {r.stderr[-2000:]}")
+            raise RuntimeError(f"{pathlib.Path(exe).name} {cmd} failed ({r.returncode}): {r.stderr[-2000:]}")
         raw = fout.read_bytes()
     n, = struct.unpack_from("<i", raw, 0); off = 4; out = []
     for _ in range(n):

@@ -7,8 +7,7 @@
 #include "../../orb_line_slam_b200/shim/ORBextractor.h"
 #include "../../orb_line_slam_b200/shim/LineExtractor.h"
 #include "../../orb_line_slam_b200/shim/LineMatcher.h"
-#include "../../orb_line_slam_b200/shim/ORBmatcher.h"
-#include "../../orb_line_slam_b200/shim/Frame.h"
+#include "../../orb_line_slam_b200/shim/olf_ref_classes.h"
 #include <cstdio>
 #include <cstdlib>
 #include <string>

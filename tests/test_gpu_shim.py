@@ -11,9 +11,12 @@ ROOT = pathlib.Path(__file__).resolve().parents[1]
 SHIM = ROOT / "orb_line_slam_b200" / "shim"
 
 
+SHIM_SOURCES = ("ORBextractor.cc", "LineExtractor.cc", "LineMatcher.cc", "ORBmatcher_hot.cc", "ORBmatcher_kf.cc", "FrameStereo.cc")
+
+
 def build_shim_test():
     exe = ROOT / "tests" / "shim" / "_test_shim"
-    srcs = [ROOT / "tests" / "shim" / "test_shim.cpp"] + [SHIM / f for f in ("ORBextractor.cc", "LineExtractor.cc", "LineMatcher.cc", "ORBmatcher_hot.cc", "FrameStereo.cc")]
+    srcs = [ROOT / "tests" / "shim" / "test_shim.cpp"] + [SHIM / f for f in SHIM_SOURCES]
     cmd = ["g++", "-std=c++17", "-O2", "-o", str(exe), *map(str, srcs), "-L" + str(ROOT / "orb_line_slam_b200"), "-lolf",
            "-Wl,-rpath," + str(ROOT / "orb_line_slam_b200")]
     subprocess.run(cmd, check=True)
@@ -40,8 +43,25 @@ def test_shim_compiles_against_opencv_shaped_headers():
         pytest.skip("/root/reference not present")
     subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref"], check=True, capture_output=True)
     inc = ["-I" + str(ROOT / "oracle" / "_ref" / "inc"), "-I" + str(ROOT / "oracle" / "ref_harness"), "-I" + str(ref / "Thirdparty/line_descriptor/include"), "-I" + str(ROOT / "include")]
-    for f in ("ORBextractor.cc", "LineExtractor.cc", "LineMatcher.cc", "ORBmatcher_hot.cc", "FrameStereo.cc"):
+    for f in SHIM_SOURCES:
         subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-DOLF_HAVE_OPENCV", *inc, str(SHIM / f)], check=True)
+
+
+def test_shim_compiles_in_reference_tree_mode():
+    """-DOLF_IN_REFERENCE_TREE: the shim sources against the REFERENCE'S OWN include/ORBmatcher.h, LineMatcher-side headers and
+    gridStructure.h (the member definitions must match the reference's declarations: signatures, constness, default arguments), with
+    the reference's Frame / KeyFrame / MapPoint / MapLine replaced by the harness stand-ins that carry the reference's member names
+    (oracle/ref_harness/frame_stub.hpp; the real ones need Eigen / DBoW2 / g2o).  This is the configuration INTEGRATION.md describes."""
+    ref = pathlib.Path("/root/reference")
+    if not ref.exists():
+        pytest.skip("/root/reference not present")
+    subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref"], check=True, capture_output=True)
+    flags = ["-std=c++14", "-fsyntax-only", "-w", "-DOLF_IN_REFERENCE_TREE", "-DOLF_HAVE_OPENCV", "-I" + str(SHIM), "-I" + str(ROOT / "include"),
+             "-I" + str(ROOT / "oracle" / "_ref" / "inc"), "-I" + str(ROOT / "oracle" / "ref_harness"), "-I" + str(ref / "include"),
+             "-I" + str(ref / "Thirdparty/line_descriptor/include"), "-I" + str(ref), "-DFRAME_H", "-DMAPPOINT_H", "-DMAPLINE_H", "-DKEYFRAME_H", "-DMAP_H",
+             "-DORBVOCABULARY_H", "-DKEYFRAMEDATABASE_H", "-include", str(ROOT / "oracle" / "ref_harness" / "frame_stub.hpp")]
+    for f in SHIM_SOURCES:
+        subprocess.run(["g++", *flags, str(SHIM / f)], check=True)
 
 
 @pytest.mark.gpu
@@ -81,3 +101,39 @@ def test_shim_equals_abi(tmp_path):
     assert two("matchmaplines") == (str(nm2), str(fnv(m2.tobytes())))
     assert "distance 0" in out
     fe.close()
+
+
+# ---- the LocalMapping / LoopClosing / relocalisation overloads (shim/ORBmatcher_kf.cc) through the shim classes on the GPU: the same cases
+# that tests/test_oracle_vs_ref.py runs through the reference's own function text
+def build_shim_kf_test():
+    exe = ROOT / "tests" / "shim" / "_test_shim_kf"
+    srcs = [ROOT / "tests" / "shim" / "test_shim_kf.cpp"] + [SHIM / f for f in ("ORBmatcher_kf.cc", "ORBmatcher_hot.cc", "ORBextractor.cc")]
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), *map(str, srcs), "-L" + str(ROOT / "orb_line_slam_b200"), "-lolf",
+                    "-Wl,-rpath," + str(ROOT / "orb_line_slam_b200")], check=True)
+    return exe
+
+
+def shim_kf_runner():
+    import functools, refcli
+    exe = build_shim_kf_test()
+    return functools.partial(refcli.run_exe, exe)
+
+
+def test_shim_kf_compiles_and_links():
+    olf.load_library()
+    assert build_shim_kf_test().exists()
+
+
+@pytest.mark.gpu
+def test_shim_kf_overloads_equal_prologue_plus_oracle():
+    import kf_cases as KC
+    run = shim_kf_runner()
+    for mode, th in KC.FUSE_CASES:
+        KC.check_fuse(run, mode, th)
+    KC.check_sim3(run)
+    for th, dist in KC.RELOC_CASES:
+        KC.check_reloc(run, th, dist)
+    for only_stereo, ori in KC.TRI_CASES:
+        KC.check_triangulation(run, only_stereo, ori)
+    for ratio, ori in KC.BOW_CASES:
+        KC.check_bow_kf(run, ratio, ori)
