@@ -168,7 +168,36 @@ struct GrowDev {
     int* dbg;                    // optional per-round trace (OLF_LSD_TRACE)
     GrowCont* cont[2];           // paused regions, by launch parity (capacity: threads of one grow launch per image)
     int budget;                  // queue entries a thread may expand per grow launch
+    // Event-driven bookkeeping (what the passes read every round is 9 bytes per candidate instead of ~100):
+    unsigned char* sstate;       // per seed: 1 = alive at the last evaluation.  A seed's state can only change where an event dirtied
+                                 // the tile of its pixel (takeover / release), or in the verify pass (which writes a death back)
+    unsigned* tbox;              // per seed: the tile-coordinate bounding box of its region packed 4 x 8 bits (tx0 | ty0 << 8 | tx1 << 16 | ty1 << 24),
+                                 // kNull = no region, kTboxWide = look at the seed record (an image wider than 255 tiles)
+    int event_scan;              // 0: evaluate every candidate every round (OLF_LSD_FULL_SCAN, the previous behaviour)
 };
+constexpr unsigned kTboxWide = 0xFFFFFFFEu;
+__device__ __forceinline__ unsigned tbox_pack(int x0, int y0, int x1, int y1) {
+    const int tx0 = x0 >> kTileShift, ty0 = y0 >> kTileShift, tx1 = x1 >> kTileShift, ty1 = y1 >> kTileShift;
+    if ((tx1 | ty1) > 254) return kTboxWide;
+    return (unsigned)tx0 | ((unsigned)ty0 << 8) | ((unsigned)tx1 << 16) | ((unsigned)ty1 << 24);
+}
+// the same test as bbox_dirty() (lsd_sticky.h) on the packed tile box
+__device__ __forceinline__ bool tbox_dirty(const Ctx3& C, unsigned round, unsigned tb) {
+    const unsigned* d = C.dirty[(round - 1) & 1];
+    const int tx0 = tb & 255, ty0 = (tb >> 8) & 255, tx1 = (tb >> 16) & 255, ty1 = tb >> 24;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int w = tx0 >> 5; w <= tx1 >> 5; ++w) {
+            const int lo = tx0 > w * 32 ? tx0 - w * 32 : 0, hi = tx1 < w * 32 + 31 ? tx1 - w * 32 : 31;
+            const unsigned mask = (hi == 31 ? 0xFFFFFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            if (d[ty * C.tile_wpr + w] & mask) return true;
+        }
+    return false;
+}
+__device__ __forceinline__ bool pixel_tile_dirty(const Ctx3& C, unsigned round, int pix) {
+    const int y = pix / C.W, x = pix - y * C.W;
+    const int tx = x >> kTileShift, ty = y >> kTileShift;
+    return (C.dirty[(round - 1) & 1][ty * C.tile_wpr + (tx >> 5)] >> (tx & 31)) & 1u;
+}
 // One launch serves a BATCH of images (the two eyes of a stereo frame, several frames): blockIdx.y selects the image, every
 // image has its own state machine.  The passes are latency-bound with small grids, so a batch costs one chain of launches
 // on one stream instead of one chain per image -- that is what keeps many frames in flight within the 32 hardware queues.
@@ -228,22 +257,30 @@ __global__ void __launch_bounds__(256) k_lsd_scan(const __grid_constant__ GrowBa
     if (blockIdx.x == 0) for (int k = threadIdx.x; k < D.dirty_words; k += blockDim.x) D.C.dirty[round & 1][k] = 0u;
     bool chg = false;
     // first round of a wave: all its seeds, those not yet swallowed by a finalised region become the wave's candidates;
-    // later rounds: the candidates only
+    // later rounds: the candidates only.  From the second round on a candidate is re-evaluated only where the previous round's
+    // events dirtied the tile of its pixel (or after a failed full verification: everything); otherwise its recorded state stands.
     const int first = first_round ? lo : 0, last = first_round ? hi : (int)st->wl0_cnt;
+    const bool everything = first_round || st->force != 0 || !D.event_scan;
     for (int base = first + blockIdx.x * blockDim.x; base < last; base += gridDim.x * blockDim.x) {
         const int j = base + threadIdx.x;
         bool cand = false, list = false;
         int i = 0, entry = 0;
         if (j < last) {
             i = first_round ? j : D.wl0[j];
-            const int seed = D.C.seed_pix[i]; const u64 prio = D.C.seed_prio[i];
-            cand = first_round && !s3_final(D.C, seed);
-            if (cand) { SeedRec3 z; z.head = kNull; z.cnt = 0; z.bhead = kNull; z.bcnt = 0; z.x0 = z.y0 = z.x1 = z.y1 = 0; z.pad0 = z.pad1 = 0; D.C.srec[i] = z; }
+            const int seed = D.C.seed_pix[i];
+            if (first_round) {
+                cand = !s3_final(D.C, seed);
+                if (cand) { SeedRec3 z; z.head = kNull; z.cnt = 0; z.bhead = kNull; z.bcnt = 0; z.x0 = z.y0 = z.x1 = z.y1 = 0; z.pad0 = z.pad1 = 0; D.C.srec[i] = z; D.tbox[i] = kNull; }
+            }
             if (cand || !first_round) {
-                const bool alive = s3_alive(D.C, seed, prio);
-                if (alive && first_round && D.defer && s3_deferred(D.C, seed, prio)) chg = true;       // sits this round out
+                bool alive;
+                if (everything || pixel_tile_dirty(D.C, round, seed)) {
+                    alive = s3_alive(D.C, seed, D.C.seed_prio[i]);
+                    D.sstate[i] = alive ? 1 : 0;
+                    if (!alive && !first_round && D.C.srec[i].cnt > 0) { list = true; entry = ~i; }                 // died owning a region
+                } else alive = D.sstate[i] != 0;
+                if (alive && first_round && D.defer && s3_deferred(D.C, seed, D.C.seed_prio[i])) chg = true;       // sits this round out
                 else if (alive) { list = true; entry = i; }
-                else if (!first_round && D.C.srec[i].cnt > 0) { list = true; entry = ~i; }               // died owning a region
             }
         }
         if (first_round) wl_append(cand, i, D.wl0, &st->wl0_cnt);
@@ -310,14 +347,21 @@ __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ G
                 const int e = D.wl1[k];
                 const bool alive = e >= 0;
                 i = alive ? e : ~e;
-                const SeedRec3 r = C.srec[i];
-                if (alive && r.cnt > 0 && r.cnt + r.bcnt > VERIFY_LONG) is_long = force || bbox_dirty(C, round, r);      // else: carried, O(1)
-                else if (!alive && r.cnt > VERIFY_LONG) is_long = true;
+                // the common case first, on 4 bytes: a live region whose tile box no event touched is carried as it is
+                const unsigned tb = D.tbox[i];
+                if (alive && !force && tb < kTboxWide && !tbox_dirty(C, round, tb)) ++carried;
                 else {
-                    const Verify3 v = s3_verify(C, round, i, alive, &chg, force);
-                    grow = v == kV3Grow; carried += v == kV3Carried;
+                    const SeedRec3 r = C.srec[i];
+                    if (alive && r.cnt > 0 && r.cnt + r.bcnt > VERIFY_LONG) is_long = force || bbox_dirty(C, round, r);      // else: carried, O(1)
+                    else if (!alive && r.cnt > VERIFY_LONG) is_long = true;
+                    else {
+                        const Verify3 v = s3_verify(C, round, i, alive, &chg, force);
+                        grow = v == kV3Grow; carried += v == kV3Carried;
+                        if (v != kV3Carried) D.tbox[i] = kNull;                      // the region is gone (released, or never was)
+                        if (alive && v == kV3Dead) D.sstate[i] = 0;                   // lost the seed pixel meanwhile: the scan's record follows
+                    }
+                    if (alive && r.cnt > 0 && r.cnt + r.bcnt > VERIFY_LONG && !is_long) ++carried;
                 }
-                if (alive && r.cnt > 0 && r.cnt + r.bcnt > VERIFY_LONG && !is_long) ++carried;
             }
             unsigned lm = __ballot_sync(0xffffffffu, is_long);
             while (lm) {
@@ -335,7 +379,7 @@ __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ G
                 if (lane == src) {
                     if (ok) ++carried;
                     else {
-                        SeedRec3 z = r; z.cnt = 0; z.bcnt = 0; z.head = kNull; z.bhead = kNull; C.srec[si] = z;
+                        SeedRec3 z = r; z.cnt = 0; z.bcnt = 0; z.head = kNull; z.bhead = kNull; C.srec[si] = z; D.tbox[si] = kNull;
                         chg = true;
                         if (alive) {                                      // still owns the seed pixel? (see s3_verify)
                             bool dead = false;
@@ -345,6 +389,7 @@ __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ G
                                 if (!dead && old != mine && claim_valid(C, old)) mark_dirty(C, round, (unsigned)seed);
                             }
                             grow = !dead;
+                            if (dead) D.sstate[si] = 0;
                         }
                     }
                 }
@@ -405,6 +450,13 @@ __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ G
 //   * a thread whose region is complete takes the next seed of the list: the lanes of a warp stay busy.
 #ifndef GROW_THREADS
 #define GROW_THREADS 64
+#endif
+// The static half of a pixel record (angle, cos, sin, bin: written before the chain starts, never during it) is read through L1: a pixel is
+// a neighbour of up to eight queue entries that the same thread expands one after the other, so most of these loads hit and the L2 sees
+// nine instead of seventeen requests per queue entry (with 20 chains in flight the L2 request rate is what the chains share).  The claim
+// half of the same sector changes under atomics and is always read with a strong load that bypasses L1.
+#ifndef OLF_LO_LD
+#define OLF_LO_LD "ld.global.ca.v4.f32"
 #endif
 #define GROW_RING 16
 struct GrowSmem { float2 nb[8][GROW_THREADS]; unsigned ring[GROW_RING][GROW_THREADS]; };   // (cos, sin) of the 8 neighbours; recent queue
@@ -560,14 +612,14 @@ __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(cons
                     : "l"(ra[0]), "l"(ra[1]), "l"(ra[2]), "l"(ra[3]), "l"(ra[4]), "l"(ra[5]), "l"(ra[6]), "l"(ra[7]), "l"(base)
                     : "memory");
                 asm volatile(
-                    "ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%32+16];\n\t"
-                    "ld.global.cg.v4.f32 {%4, %5, %6, %7}, [%33+16];\n\t"
-                    "ld.global.cg.v4.f32 {%8, %9, %10, %11}, [%34+16];\n\t"
-                    "ld.global.cg.v4.f32 {%12, %13, %14, %15}, [%35+16];\n\t"
-                    "ld.global.cg.v4.f32 {%16, %17, %18, %19}, [%36+16];\n\t"
-                    "ld.global.cg.v4.f32 {%20, %21, %22, %23}, [%37+16];\n\t"
-                    "ld.global.cg.v4.f32 {%24, %25, %26, %27}, [%38+16];\n\t"
-                    "ld.global.cg.v4.f32 {%28, %29, %30, %31}, [%39+16];"
+                    OLF_LO_LD " {%0, %1, %2, %3}, [%32+16];\n\t"
+                    OLF_LO_LD " {%4, %5, %6, %7}, [%33+16];\n\t"
+                    OLF_LO_LD " {%8, %9, %10, %11}, [%34+16];\n\t"
+                    OLF_LO_LD " {%12, %13, %14, %15}, [%35+16];\n\t"
+                    OLF_LO_LD " {%16, %17, %18, %19}, [%36+16];\n\t"
+                    OLF_LO_LD " {%20, %21, %22, %23}, [%37+16];\n\t"
+                    OLF_LO_LD " {%24, %25, %26, %27}, [%38+16];\n\t"
+                    OLF_LO_LD " {%28, %29, %30, %31}, [%39+16];"
                     : "=f"(lo[0].x), "=f"(lo[0].y), "=f"(lo[0].z), "=f"(lo[0].w), "=f"(lo[1].x), "=f"(lo[1].y), "=f"(lo[1].z), "=f"(lo[1].w),
                       "=f"(lo[2].x), "=f"(lo[2].y), "=f"(lo[2].z), "=f"(lo[2].w), "=f"(lo[3].x), "=f"(lo[3].y), "=f"(lo[3].z), "=f"(lo[3].w),
                       "=f"(lo[4].x), "=f"(lo[4].y), "=f"(lo[4].z), "=f"(lo[4].w), "=f"(lo[5].x), "=f"(lo[5].y), "=f"(lo[5].z), "=f"(lo[5].w),
@@ -589,16 +641,28 @@ __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(cons
                 // the entry itself was claimed a while ago without looking at the return value: did it go to a higher-priority seed?
                 if (cl_c != mine_g) mark_dirty_xy(C, round, px, py);
                 unsigned m_free = 0, m_held = 0, m_low = 0;
-                const unsigned stamp_hi = (unsigned)(C.stamp >> 40);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const bool fre = cl[k] > mine_g;
-                    const bool hld = cl[k] < mine_g && (unsigned)(cl[k] >> 32) >= 256u;
-                    const bool low = fre && (unsigned)(cl[k] >> 40) == stamp_hi;          // a lower-priority claim of this wave
-                    m_free |= (unsigned)fre << k;
-                    m_held |= (unsigned)hld << k;
-                    m_low |= (unsigned)low << k;
-                }
+                // on the 32-bit halves (the stamp is the top 24 bits of the high word): x < 256 <=> same stamp <=> a claim of this wave
+                const unsigned mh = (unsigned)(mine_g >> 32), ml = (unsigned)mine_g;
+                // ten instructions per neighbour, written out (the compiler's version of the same tests took sixteen):
+                //   x = h ^ mh;  fre = c > mine;  low = fre && x < 256;  hld = !fre && (x | (l ^ ml)) != 0 && h >= 256   (not mine, not final)
+#define OLF_NB_FLAGS(K)                                                                                                         \
+                asm("{\n\t.reg .pred pf, pl, ph;\n\t.reg .b32 x, y;\n\t"                                                        \
+                    "xor.b32 x, %3, %5;\n\t"                                                                                    \
+                    "setp.gt.u64 pf, %7, %8;\n\t"                                                                               \
+                    "setp.lt.and.u32 pl, x, 256, pf;\n\t"                                                                       \
+                    "xor.b32 y, %4, %6;\n\t"                                                                                    \
+                    "or.b32 y, y, x;\n\t"                                                                                       \
+                    "setp.ne.and.u32 ph, y, 0, !pf;\n\t"                                                                        \
+                    "setp.ge.and.u32 ph, %3, 256, ph;\n\t"                                                                      \
+                    "@pf or.b32 %0, %0, " #K ";\n\t"                                                                            \
+                    "@ph or.b32 %1, %1, " #K ";\n\t"                                                                            \
+                    "@pl or.b32 %2, %2, " #K ";\n\t}"                                                                           \
+                    : "+r"(m_free), "+r"(m_held), "+r"(m_low)                                                                   \
+                    : "r"((unsigned)(cl[K2IDX(K)] >> 32)), "r"((unsigned)cl[K2IDX(K)]), "r"(mh), "r"(ml), "l"(cl[K2IDX(K)]), "l"(mine_g))
+#define K2IDX(K) ((K) == 1 ? 0 : (K) == 2 ? 1 : (K) == 4 ? 2 : (K) == 8 ? 3 : (K) == 16 ? 4 : (K) == 32 ? 5 : (K) == 64 ? 6 : 7)
+                OLF_NB_FLAGS(1); OLF_NB_FLAGS(2); OLF_NB_FLAGS(4); OLF_NB_FLAGS(8); OLF_NB_FLAGS(16); OLF_NB_FLAGS(32); OLF_NB_FLAGS(64); OLF_NB_FLAGS(128);
+#undef OLF_NB_FLAGS
+#undef K2IDX
                 m_free &= vm; m_held &= vm;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) sm.nb[k][t] = make_float2(lo[k].y, never ? 0.f : lo[k].z);
@@ -652,6 +716,7 @@ __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(cons
                     C.regang[i] = reg_angle;
                 }
                 C.srec[i] = r;
+                D.tbox[i] = overflow ? kNull : tbox_pack(bx0, by0, bx1, by1);
                 if (D.dbg) { atomicAdd(&D.dbg[round * TRACE_REC + 5], 1); atomicAdd(&D.dbg[round * TRACE_REC + 6], count); atomicMax(&D.dbg[round * TRACE_REC + 7], count); }
                 active = false;
             } else if (steps >= budget) {
@@ -990,6 +1055,7 @@ struct LineImpl {
     DevBuf<PhaseState> phase;
     DevBuf<PxRec> px;
     DevBuf<GrowCont> cont;
+    DevBuf<unsigned char> sstate; DevBuf<unsigned> tbox;
     TmaSet<1> tmaps[2]; bool has_tma = false;      // [0]: input image, 7x7 box (LSD pre-blur); [1]: input image, 5x5 box (LBD blur)
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr; unsigned long long graph_key = 0; int use_graph = 1;
     int grow_budget = 1 << 30;          // OLF_LSD_GROW_BUDGET: queue entries per thread and grow launch (default: no limit)
@@ -1127,7 +1193,7 @@ void line_destroy(LineImpl* h) {
     h->ang.release(); h->dabc.release(); h->seed_prio.release(); h->seed_pix.release(); h->n2max.release(); h->status.release();
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
     h->final_pool.release(); h->conv.release(); h->dirty.release(); h->srec0.release(); h->regang.release(); h->plan.release(); h->regs.release();
-    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release(); h->cont.release();
+    h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release(); h->cont.release(); h->sstate.release(); h->tbox.release();
     h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release(); h->phase_init.release();
     h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
@@ -1168,7 +1234,7 @@ static int line_ensure_size(LineImpl* h, int w, int hgt) {
     h->reg_cap = (unsigned)(S / std::max(h->min_reg_size, 1) + 16);
     if ((rc = h->ang.ensure(S)) || (rc = h->dabc.ensure(S)) || (rc = h->seed_prio.ensure(S)) || (rc = h->seed_pix.ensure(S)) ||
         (rc = h->conv.ensure(LSD_MAX_WAVES + 1)) || (rc = h->srec0.ensure(S)) || (rc = h->wl0.ensure(S)) || (rc = h->wl1.ensure(S)) || (rc = h->wl2.ensure(S)) ||
-        (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) ||
+        (rc = h->regang.ensure(S)) || (rc = h->final_pool.ensure(S)) || (rc = h->sstate.ensure(S)) || (rc = h->tbox.ensure(S)) ||
         (rc = h->n2max.ensure(1)) || (rc = h->status.ensure(4)) || (rc = h->hist.ensure(1024)) || (rc = h->bin_start.ensure(1024)) ||
         (rc = h->cursor.ensure(1024)) || (rc = h->ctrs.ensure(4)) || (rc = h->plan.ensure(1)) ||
         (rc = h->pool.ensure((size_t)h->pool_chunks * kChunk)) ||
@@ -1254,6 +1320,7 @@ static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D, int batch_im
     D.test_recheck = getenv("OLF_LSD_TEST_RECHECK") ? 1 : 0;
     D.dbg = h->trace ? h->dbg.p : nullptr;
     D.cont[0] = h->cont.p; D.cont[1] = h->cont.p + h->cont.n / 2; D.budget = h->grow_budget;
+    D.sstate = h->sstate.p; D.tbox = h->tbox.p; D.event_scan = getenv("OLF_LSD_FULL_SCAN") ? 0 : 1;
     if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
     h->phase_init.p[0] = PhaseState{}; h->phase_init.p[0].round = 1; h->phase_init.p[0].wave_first_round = 1;
     OLF_CUDA(cudaMemcpyAsync(h->phase.p, h->phase_init.p, sizeof(PhaseState), cudaMemcpyHostToDevice, s));
