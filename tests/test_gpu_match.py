@@ -121,6 +121,12 @@ def test_track_720p(frames):
     assert to["nmatches"] == tg["nmatches"] and to["nmatches"] > 100
     for k in ("assigned", "cur_point", "line_matches"):
         assert np.array_equal(to[k], tg[k]), k
+    # SearchByProjection(F, vpMapPoints, th) at 1280x720 (src/ORBmatcher.cc:47-131; Tracking::SearchLocalPoints uses th = 1, 3, 5)
+    for th in (1.0, 3.0, 5.0):
+        ao, ko = fo.sbp_map_args(po[1], po[0], th, 0.8)
+        ag, kg = fg.sbp_map_args(pg[1], pg[0], th, 0.8)
+        ro, rg = fo.api.search_by_projection_map(ao, ko), fg.api.search_by_projection_map(ag, kg)
+        assert ro[1] == rg[1] > 100 and np.array_equal(ro[0], rg[0]), th
     fo.close(); fg.close()
 
 

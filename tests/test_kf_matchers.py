@@ -259,3 +259,60 @@ def test_gpu_search_by_bow_kf(seed, n, ratio, ori):
     gm, gn = olf.api(0).search_by_bow_kf(*args)
     om, on = oracle().search_by_bow_kf(*args)
     assert np.array_equal(gm, om) and gn == on and gn > n // 20
+
+
+def _empty_like(kf):
+    e = dict(kf)
+    e["kps"] = kf["kps"][:0]; e["desc"] = kf["desc"][:0]; e["skip"] = kf["skip"][:0]; e["u_right"] = kf["u_right"][:0]
+    e["fv"] = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    return e
+
+
+def _edge_cases(api):
+    """Empty key frames, disjoint vocabulary nodes, every feature skipped: what the reference's loops simply fall through."""
+    kf1, kf2, F12, ex, ey = K.make_stereo_pair_keyframes(5, n=300)
+    out = []
+    out.append(api.search_for_triangulation(_empty_like(kf1), kf2, F12, ex, ey))
+    out.append(api.search_for_triangulation(kf1, _empty_like(kf2), F12, ex, ey))
+    disjoint = dict(kf2); disjoint["fv"] = (kf2["fv"][0] + 1000, kf2["fv"][1], kf2["fv"][2])     # no node in common
+    out.append(api.search_for_triangulation(kf1, disjoint, F12, ex, ey))
+    allskip = dict(kf1); allskip["skip"] = np.ones_like(kf1["skip"])
+    out.append(api.search_for_triangulation(allskip, kf2, F12, ex, ey, False, True))
+    zeroF = np.zeros(9, np.float32)                                                               # den == 0: CheckDistEpipolarLine returns false
+    out.append(api.search_for_triangulation(kf1, kf2, zeroF, ex, ey))
+    has1, has2 = 1 - kf1["skip"], 1 - kf2["skip"]
+    out.append(api.search_by_bow_kf(kf1["desc"], kf1["kps"], has1, kf1["fv"], kf2["desc"], kf2["kps"], np.zeros_like(has2), kf2["fv"]))
+    out.append(api.search_by_bow_kf(kf1["desc"], kf1["kps"], has1, kf1["fv"], kf2["desc"], kf2["kps"], has2, disjoint["fv"]))
+    e1 = _empty_like(kf1)
+    out.append(api.search_by_bow_kf(e1["desc"], e1["kps"], e1["skip"], e1["fv"], kf2["desc"], kf2["kps"], has2, kf2["fv"]))
+    return out
+
+
+def test_oracle_edge_cases():
+    for m, n in _edge_cases(oracle()):
+        assert n == 0 and (m == -1).all()
+
+
+@pytest.mark.gpu
+def test_gpu_edge_cases():
+    import orb_line_slam_b200 as olf
+    api = olf.api(0)
+    for (gm, gn), (om, on) in zip(_edge_cases(api), _edge_cases(oracle())):
+        assert gn == on == 0 and np.array_equal(gm, om)
+    kf = K.make_keyframe(7, n=50)
+    q = K.random_queries(kf, 20, 2)
+    q["u"][:5] = [-500, 5000, 10, 10, 1279.5]; q["v"][:5] = [10, 10, -900, 9000, 719.5]
+    args = (kf["kps"], kf["desc"], kf["cam"], q["u"], q["v"], q["radius"], q["min_level"], q["max_level"], q["qdesc"], 256)
+    gi, gd = api.window_search(*args); oi, od = oracle().window_search(*args)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    q0 = K.random_queries(kf, 0, 1)
+    gi, gd = api.window_search(kf["kps"], kf["desc"], kf["cam"], q0["u"], q0["v"], q0["radius"], q0["min_level"], q0["max_level"], q0["qdesc"], 50)
+    assert len(gi) == 0
+    gi, gd = api.window_search(kf["kps"][:0], kf["desc"][:0], kf["cam"], q["u"], q["v"], q["radius"], q["min_level"], q["max_level"], q["qdesc"], 256)
+    assert (gi == -1).all() and (gd == 256).all()
+    # a window with more than 128 admissible candidates is reported, not truncated
+    dense = K.make_keyframe(8, n=4000, w=320, h=240)
+    dense["cam"] = K.Camera(300.0, 300.0, 160.0, 120.0, 40.0, 0.0, 320.0, 0.0, 240.0)
+    with pytest.raises(RuntimeError, match="128 candidates"):
+        api.window_search(dense["kps"], dense["desc"], dense["cam"], np.array([160.0], np.float32), np.array([120.0], np.float32), np.array([100.0], np.float32),
+                          np.array([0], np.int32), np.array([7], np.int32), dense["desc"][:1], 256)
