@@ -452,6 +452,12 @@ def main():
     # untimed pre-warm, a FIXED number of steps on every rank (the collective sequence must be rank-invariant): a fresh box
     # needs a few seconds of GPU work before clocks, lazily loaded modules, pinned-page mappings and host threads settle
     timed(max(2, args.prewarm_steps), 0, True)
+    if os.environ.get("OLF_BENCH_BURN"):
+        # diagnostic (tools/burn.cu): a persistent kernel takes a known share of every scheduler's issue slots during the timed regions
+        chains, secs = os.environ["OLF_BENCH_BURN"].split(",")
+        burn = ctypes.CDLL(str(ROOT / "tools" / "libburn.so"))
+        burn.burn_start.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double]
+        assert burn.burn_start(local, int(chains), float(secs)) == 0
     timed(args.warmup, 0, True)                                      # the W warm-up steps
     sampler = ClockSampler(local) if rank == 0 else None
     ms, st, launches = timed(args.steps, args.warmup * fps_step, True)       # HBM-resident inputs
@@ -523,6 +529,9 @@ def main():
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": 1, "kind": "port",
                                     "sample": f"{frames} consecutive frames of the same sequence through oracle/ (single thread, {dt:.1f} s)"}
         print(json.dumps(line), flush=True)
+    if os.environ.get("OLF_BENCH_BURN"):
+        burn.burn_wait.restype = ctypes.c_ulonglong
+        print("burn: outer iterations of one warp (x 256 inner iterations)", burn.burn_wait(), file=sys.stderr, flush=True)
     for nat in pipes:
         nat.close()
     for fe in fes:
