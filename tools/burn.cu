@@ -36,12 +36,34 @@ __global__ void __launch_bounds__(1024) k_burn_mem(unsigned long long dur_ns, co
     out[blockIdx.x * blockDim.x + threadIdx.x] = idx;
     if (threadIdx.x == 0 && blockIdx.x == 0) *iters_out = it;
 }
+// mode 3: a host thread keeps launching grids of `ctas` trivial CTAs (each writes one word and exits): load on the CTA dispatcher / launch path only
+__global__ void __launch_bounds__(64) k_burn_cta(unsigned* out) { if (threadIdx.x == 0) out[blockIdx.x & 1023] = blockIdx.x; }
+#include <thread>
+#include <atomic>
+#include <chrono>
+static std::thread g_thr; static std::atomic<unsigned long long> g_launches{0};
 static unsigned* g_buf = nullptr;
 static cudaStream_t g_s = nullptr; static unsigned* g_out = nullptr; static unsigned long long* g_it = nullptr;
 extern "C" int burn_start(int device, int chains, double seconds) {
     if (cudaSetDevice(device) != cudaSuccess) return -1;
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (!g_s) { cudaStreamCreateWithFlags(&g_s, cudaStreamNonBlocking); cudaMalloc(&g_out, (size_t)sms * 128 * 4); cudaMallocHost(&g_it, 8); }
+    if (chains >= 1000) {         // CTA-dispatch mode: chains = CTAs per launch
+        const int ctas = chains;
+        if (g_thr.joinable()) g_thr.join();
+        g_launches = 0;
+        g_thr = std::thread([device, ctas, seconds] {
+            cudaSetDevice(device);
+            const auto t_end = std::chrono::steady_clock::now() + std::chrono::duration<double>(seconds);
+            unsigned long long n = 0;
+            while (std::chrono::steady_clock::now() < t_end) {
+                for (int k = 0; k < 8; ++k) k_burn_cta<<<ctas, 64, 0, g_s>>>(g_out);
+                cudaStreamSynchronize(g_s); n += 8;
+            }
+            g_launches = n;
+        });
+        return 0;
+    }
     if (chains >= 100) {          // memory mode: chains - 100 = warps per SM
         const int warps = chains - 100;
         const size_t sectors = (size_t)1 << 26;           // 2 GB of 32-byte sectors
@@ -51,4 +73,4 @@ extern "C" int burn_start(int device, int chains, double seconds) {
     k_burn<<<sms, 128, 0, g_s>>>((unsigned long long)(seconds * 1e9), chains, g_out, g_it);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-extern "C" unsigned long long burn_wait() { cudaStreamSynchronize(g_s); return *g_it; }
+extern "C" unsigned long long burn_wait() { if (g_thr.joinable()) { g_thr.join(); return g_launches.load(); } cudaStreamSynchronize(g_s); return *g_it; }
