@@ -53,14 +53,6 @@ cudaError_t stream_sync(cudaStream_t s) {
     return event_wait(ev);
 }
 void set_last_error(const std::string& s) { g_err = s; }
-void apply_carveout(int device) {
-    static std::atomic<unsigned> done{0};
-    if (device < 0 || device >= 32 || (done.fetch_or(1u << device) >> device) & 1u) return;
-    int percent = 50;
-    if (const char* e = getenv("OLF_CARVEOUT")) percent = atoi(e);
-    if (percent < 0) return;
-    orb_set_carveout(percent); line_set_carveout(percent); match_set_carveout(percent);
-}
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     char buf[512];
     snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);

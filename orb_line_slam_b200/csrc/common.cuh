@@ -35,10 +35,6 @@ struct SyncEvent {
     cudaError_t sync(cudaStream_t s) { const cudaError_t e = record(s); return e != cudaSuccess ? e : wait(); }
 };
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
-void orb_set_carveout(int percent); void line_set_carveout(int percent); void match_set_carveout(int percent);
-// applied once per device at the first handle / context creation (OLF_CARVEOUT=percent of shared memory, -1 = leave the driver's per-kernel choice)
-void apply_carveout(int device);
-
 #define OLF_CUDA(call)                                                         \
     do {                                                                       \
         cudaError_t e__ = (call);                                              \

@@ -1110,7 +1110,6 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
         set_last_error("olf_line_create: no such CUDA device (this library has no CPU path)"); return nullptr;
     }
     if (cudaSetDevice(device) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return nullptr; }
-    apply_carveout(device);
     LineImpl* h = new LineImpl();
     h->device = device; h->P = *p;
     h->prec = M_PI * p->lsd_ang_th / 180.0;
@@ -1603,27 +1602,4 @@ int line_trace(LineImpl* h, int* out, int max_rounds) {
 }
 
 
-// One shared-memory carve-out for every kernel of the library: an SM whose resident CTAs were launched under another L1 / shared-memory split has to
-// drain before a CTA with a different preferred split can start, and with long-lived region-growing CTAs on every SM that drain takes milliseconds.
-void line_set_carveout(int percent) {
-    cudaFuncSetAttribute(k_blur_q8<3>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_blur_q8<5>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_blur_q8<7>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_blur_q8_tma<5, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_blur_q8_tma<7, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lbd_fold, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lbd_rows, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_grad, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_hist, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_plan, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_rect_a, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_rect_b, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_resize_exact, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_sobel3, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_scan, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_verify, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaGetLastError();
-}
 }  // namespace olf

@@ -59,7 +59,6 @@ static int get_ctx(int device, MatchCtx** out) {
         return OLF_ERR_NO_DEVICE;
     }
     OLF_CUDA(cudaSetDevice(device));
-    apply_carveout(device);
     MatchCtx& c = (g_lent_ctx && g_lent_ctx->device == device) ? *g_lent_ctx : g_ctx[device];
     if (g_lent_stream) c.cur = g_lent_stream;
     else {
@@ -1505,29 +1504,4 @@ int search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int
 }
 
 
-// One shared-memory carve-out for every kernel of the library: an SM whose resident CTAs were launched under another L1 / shared-memory split has to
-// drain before a CTA with a different preferred split can start, and with long-lived region-growing CTAs on every SM that drain takes milliseconds.
-void match_set_carveout(int percent) {
-    cudaFuncSetAttribute(k_bow_match, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_bow_transform, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_distinctive, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_knn2_merge, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_knn2_partial, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lines_best, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lines_cand, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lines_cand_grid, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lines_geom, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lines_mutual, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lines_pass, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_lines_raster, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_mutual, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_nnr_accept, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_popc_peak, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_sbp_candidates, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_sbp_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_stereo_median, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_stereo_points, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_triangulate, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaGetLastError();
-}
 }  // namespace olf

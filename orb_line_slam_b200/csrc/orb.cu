@@ -645,7 +645,6 @@ OrbImpl* orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
         set_last_error("olf_orb_create: no such CUDA device (this library has no CPU path)"); return nullptr;
     }
     if (cudaSetDevice(device) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return nullptr; }
-    apply_carveout(device);
     OrbImpl* h = new OrbImpl();
     h->device = device; h->nfeatures = nfeatures; h->nlevels = nlevels; h->ini_th = ini_th; h->min_th = min_th; h->scale_factor = scale_factor;
     // ORBextractor ctor (:417-448)
@@ -835,18 +834,4 @@ int orb_trig_sweep(unsigned first, unsigned stride, unsigned count, float* cos_s
 }
 
 
-// One shared-memory carve-out for every kernel of the library: an SM whose resident CTAs were launched under another L1 / shared-memory split has to
-// drain before a CTA with a different preferred split can start, and with long-lived region-growing CTAs on every SM that drain takes milliseconds.
-void orb_set_carveout(int percent) {
-    cudaFuncSetAttribute(k_blur_q8<7>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_blur_q8_tma<7, ORB_TMA_MAPS>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_cell_count, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_cell_write, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_fast_score, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_orb_describe, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_quadtree, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_resize_linear, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaFuncSetAttribute(k_trig_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    cudaGetLastError();
-}
 }  // namespace olf
