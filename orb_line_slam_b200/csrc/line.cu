@@ -451,10 +451,9 @@ __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ G
 #ifndef GROW_THREADS
 #define GROW_THREADS 64
 #endif
-// The static half of a pixel record (angle, cos, sin, bin: written before the chain starts, never during it) is read through L1: a pixel is
-// a neighbour of up to eight queue entries that the same thread expands one after the other, so most of these loads hit and the L2 sees
-// nine instead of seventeen requests per queue entry (with 20 chains in flight the L2 request rate is what the chains share).  The claim
-// half of the same sector changes under atomics and is always read with a strong load that bypasses L1.
+// The static half of a pixel record (angle, cos, sin, bin: written before the chain starts, never during it) may be read through L1; the claim
+// half of the same sector changes under atomics and is always read with a strong load that bypasses L1.  (Measured: .cg / .ca / .nc make no
+// difference to the frame rate and the L1 hit rate of this kernel stays at 6 % -- profiles/r02_notes.md.)
 #ifndef OLF_LO_LD
 #define OLF_LO_LD "ld.global.ca.v4.f32"
 #endif
