@@ -319,6 +319,15 @@ int olf_search_for_triangulation(const olf_triangulation_args* a, int* matches12
  * The argument block is the one of olf_search_by_bow (kf = pKF1, f = pKF2, f_kps = pKF2->mvKeysUn) plus has_point2. */
 int olf_search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2 /* n_f */, int* matches12 /* n_kf */, int* nmatches, int device);
 
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:407-522; monocular map initialisation):
+ * every level-0 keypoint of F1 searches the window of `window_size` pixels around prev_matched[i1] among the level-0 keypoints of F2; a
+ * keypoint of F2 can be taken over by a later, closer keypoint of F1 (vMatchedDistance / vnMatches21), then the ratio test and the rotation
+ * histogram.  The window x Hamming candidate lists come from the device; the order-dependent take-over runs on the host in keypoint order.
+ * matches12[n1]; prev_matched (n1 x 2, x y) is updated in place for the surviving matches (:516-518). */
+int olf_search_for_initialization(const olf_keypoint* kps1, const uint8_t* desc1, int n1, const olf_keypoint* kps2, const uint8_t* desc2, int n2,
+                                  const olf_camera* cam, float* prev_matched, int window_size, float nn_ratio, int check_orientation,
+                                  int* matches12, int* nmatches, int device);
+
 /* ---- whole stereo frame: Frame::Frame(stereo+lines) (src/Frame.cc:136-221) ----------------------------------- */
 /* One rig = 2 ORB extractors + 2 line extractors on one device; olf_frontend_process runs ExtractORB(L|R) and
  * ExtractLine(L|R) on its own host threads (src/Frame.cc:164-171), then ComputeStereoMatches and

@@ -610,3 +610,56 @@ extern "C" int orc_search_for_triangulation(const olf_triangulation_args* a, int
     *nmatches_out = nmatches;
     return OLF_OK;
 }
+
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522)
+extern "C" int orc_search_for_initialization(const olf_keypoint* kps1, const uint8_t* desc1, int n1, const olf_keypoint* kps2, const uint8_t* desc2, int n2,
+                                             const olf_camera* cam, float* prev_matched, int window_size, float nn_ratio, int check_orientation,
+                                             int* vnMatches12, int* nmatches_out) {
+    if (!cam || !vnMatches12 || !nmatches_out) return OLF_ERR_ARG;
+    FrameGrid g;
+    build_grid(kps2, n2, *cam, g);
+    int nmatches = 0;
+    for (int i = 0; i < n1; ++i) vnMatches12[i] = -1;
+    std::vector<int> rotHist[OLF_HISTO_LENGTH];
+    const float factor = 1.0f / OLF_HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(std::max(n2, 1), INT_MAX), vnMatches21(std::max(n2, 1), -1), cand;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = kps1[i1].octave;
+        if (level1 > 0) continue;
+        features_in_area(g, kps2, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window_size, level1, level1, cand);
+        if (cand.empty()) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : cand) {
+            const int dist = hamming256(desc1 + (size_t)i1 * 32, desc2 + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= OLF_TH_LOW) {
+            if (bestDist < (float)bestDist2 * nn_ratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2; vnMatches21[bestIdx2] = i1; vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_orientation) {
+                    float rot = kps1[i1].angle - kps2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == OLF_HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, OLF_HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < OLF_HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (vnMatches12[i1] >= 0) { prev_matched[2 * i1] = kps2[vnMatches12[i1]].x; prev_matched[2 * i1 + 1] = kps2[vnMatches12[i1]].y; }
+    *nmatches_out = nmatches;
+    return OLF_OK;
+}

@@ -50,6 +50,8 @@ int orc_distinctive_descriptors(const uint8_t* desc, const int* group_begin, int
 /* the remaining ORBmatcher overloads (src/ORBmatcher.cc:292-405, 659-1328, 1620-1747) */
 int orc_window_search(const olf_window_search_args* a, int* best_idx, int* best_dist);
 int orc_search_for_triangulation(const olf_triangulation_args* a, int* matches12, int* nmatches);
+int orc_search_for_initialization(const olf_keypoint* kps1, const uint8_t* desc1, int n1, const olf_keypoint* kps2, const uint8_t* desc2, int n2,
+                                  const olf_camera* cam, float* prev_matched, int window_size, float nn_ratio, int check_orientation, int* matches12, int* nmatches);
 int orc_search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int* matches12, int* nmatches);
 /* bag of words (oracle/bow.cpp) */
 typedef struct orc_vocab orc_vocab;

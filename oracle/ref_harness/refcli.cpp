@@ -359,6 +359,21 @@ int main(int argc, char** argv) {
         std::vector<int> res(Cur.N, -1);
         for (int j = 0; j < Cur.N; ++j) if (Cur.mvpMapPoints[j] && Cur.mvpMapPoints[j] != &marker) res[j] = (int)(Cur.mvpMapPoints[j] - pts.data());
         out.push_back(make<int>(1, {(long long)Cur.N}, res.data())); out.push_back(make<int>(1, {1}, &n));
+    } else if (cmd == "init") {
+        // in: kps1, desc1, kps2, desc2, cam f32[7], prev f32[n1,2], par f32[3] (window, nn_ratio, check_orientation), orb i32[5], scale
+        // -> ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522): matches12 i32[n1], n, prev f32[n1,2]
+        const int* p = in[7].as<int>();
+        ORBextractor ex(p[0], in[8].as<float>()[0], p[1], p[2], p[3]);
+        Frame F1, F2; fill_frame_points(F1, ex, in[0], in[1], in[4]); fill_frame_points(F2, ex, in[2], in[3], in[4]);
+        std::vector<cv::Point2f> prev(F1.N);
+        for (int i = 0; i < F1.N; ++i) prev[i] = cv::Point2f(in[5].as<float>()[2 * i], in[5].as<float>()[2 * i + 1]);
+        const float* par = in[6].as<float>();
+        ORBmatcher matcher(par[1], par[2] != 0);
+        std::vector<int> m12;
+        const int n = matcher.SearchForInitialization(F1, F2, prev, m12, (int)par[0]);
+        std::vector<float> pv(2 * (size_t)F1.N);
+        for (int i = 0; i < F1.N; ++i) { pv[2 * i] = prev[i].x; pv[2 * i + 1] = prev[i].y; }
+        out.push_back(make<int>(1, {(long long)F1.N}, m12.data())); out.push_back(make<int>(1, {1}, &n)); out.push_back(make<float>(2, {(long long)F1.N, 2}, pv.data()));
     } else if (cmd == "triangulation" || cmd == "bow_kf") {
         // in: kps1, desc1, skip1 u8, uRight1, node1, begin1, index1, kps2, desc2, skip2, uRight2, node2, begin2, index2, cam f32[7],
         //     geo f32[24] (Cw[3], R2w[9], t2w[3], F12[9]), flags f32[3] (only_stereo, check_orientation, nn_ratio), orb, scale

@@ -47,7 +47,8 @@ SLICES = {
                        ("src/ORBmatcher.cc", "int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th)"),
                        ("src/ORBmatcher.cc", "int ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw,"),
                        ("src/ORBmatcher.cc", "int ORBmatcher::SearchBySim3("),
-                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF,")],
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF,"),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchForInitialization(")],
     "mappoint.inc": [("src/MapPoint.cc", "void MapPoint::ComputeDistinctiveDescriptors()"),
                      ("src/MapPoint.cc", "float MapPoint::GetMinDistanceInvariance()"), ("src/MapPoint.cc", "float MapPoint::GetMaxDistanceInvariance()"),
                      ("src/MapPoint.cc", "int MapPoint::PredictScale(const float &currentDist, KeyFrame* pKF)"),

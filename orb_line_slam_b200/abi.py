@@ -416,6 +416,17 @@ class FrontEndApi:
         self.check(self.fn("search_for_triangulation")(C.byref(a), ptr(m), C.byref(n), *self._dev), "search_for_triangulation")
         return m[:len(k[0])], n.value
 
+    def search_for_initialization(self, kps1, desc1, kps2, desc2, cam: Camera, prev_matched, window_size=100, nn_ratio=0.9, check_orientation=True):
+        """ORBmatcher::SearchForInitialization: returns (matches12, n, updated prev_matched [n1, 2])."""
+        k1, d1, k2, d2 = np.ascontiguousarray(kps1), np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(kps2), np.ascontiguousarray(desc2, np.uint8)
+        pm = np.array(prev_matched, np.float32, copy=True).reshape(-1, 2) if len(k1) else np.zeros((0, 2), np.float32)
+        pm = np.ascontiguousarray(pm)
+        m = np.zeros(max(len(k1), 1), np.int32); n = C.c_int(0)
+        rc = self.fn("search_for_initialization")(ptr(k1), ptr(d1), C.c_int(len(k1)), ptr(k2), ptr(d2), C.c_int(len(k2)), C.byref(cam), ptr(pm) if len(k1) else None,
+                                                  C.c_int(int(window_size)), C.c_float(nn_ratio), C.c_int(int(check_orientation)), ptr(m), C.byref(n), *self._dev)
+        self.check(rc, "search_for_initialization")
+        return m[:len(k1)], n.value, pm
+
     def search_by_projection_map(self, args: SbpMapArgs, keep):
         a = np.zeros(args.n_points, np.int32); n = C.c_int(0)
         rc = self.fn("search_by_projection_map")(C.byref(args), ptr(a), C.byref(n), *self._dev)

@@ -156,5 +156,9 @@ int olf_bow_assemble(const int* word_id, const double* weight, const int* node_i
 int olf_search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches, int device) { return search_by_bow(a, match_f, nmatches, device); }
 int olf_search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int* matches12, int* nmatches, int device) { return search_by_bow_kf(a, has_point2, matches12, nmatches, device); }
 int olf_window_search(const olf_window_search_args* a, int* best_idx, int* best_dist, int device) { return window_search(a, best_idx, best_dist, device); }
+int olf_search_for_initialization(const olf_keypoint* kps1, const uint8_t* desc1, int n1, const olf_keypoint* kps2, const uint8_t* desc2, int n2, const olf_camera* cam,
+                                  float* prev_matched, int window_size, float nn_ratio, int check_orientation, int* matches12, int* nmatches, int device) {
+    return search_for_initialization(kps1, desc1, n1, kps2, desc2, n2, cam, prev_matched, window_size, nn_ratio, check_orientation, matches12, nmatches, device);
+}
 int olf_search_for_triangulation(const olf_triangulation_args* a, int* matches12, int* nmatches, int device) { return search_for_triangulation(a, matches12, nmatches, device); }
 }

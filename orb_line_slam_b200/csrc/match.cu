@@ -896,7 +896,8 @@ __global__ void __launch_bounds__(256) k_sbp_candidates(const SbpQuery* __restri
 __global__ void __launch_bounds__(1024) k_sbp_resolve(const u64* __restrict__ lists, const int* __restrict__ counts, int nq, int n_cur,
                                                       const uint8_t* __restrict__ observed, const uint8_t* __restrict__ occupied,
                                                       const olf_keypoint* __restrict__ kps, int mode, float nn_ratio,
-                                                      int* __restrict__ owner_a, int* __restrict__ owner_b, int* __restrict__ assign, int* __restrict__ rounds_out) {
+                                                      int* __restrict__ owner_a, int* __restrict__ owner_b, int* __restrict__ assign, int* __restrict__ rounds_out,
+                                                      int* __restrict__ adist = nullptr) {
     __shared__ int s_changed;
     int* own_prev = owner_a; int* own_new = owner_b;
     for (int j = threadIdx.x; j < n_cur; j += 1024) { own_prev[j] = (occupied && occupied[j]) ? -1 : INT_MAX; }
@@ -909,9 +910,9 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(const u64* __restrict__ li
         __syncthreads();
         for (int i = threadIdx.x; i < nq; i += 1024) {
             const int cnt = min(counts[i], SBP_K);
-            int sel = -1;
+            int sel = -1, seld = 256;
             if (mode == 0) {
-                for (int e = 0; e < cnt; ++e) { const int j = (int)(lists[(size_t)i * SBP_K + e] & 0xFFFFFF); if (!(own_prev[j] < i)) { sel = j; break; } }
+                for (int e = 0; e < cnt; ++e) { const u64 key = lists[(size_t)i * SBP_K + e]; const int j = (int)(key & 0xFFFFFF); if (!(own_prev[j] < i)) { sel = j; seld = (int)(key >> 40); break; } }
             } else {
                 int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1, found = 0;
                 for (int e = 0; e < cnt && found < 2; ++e) {
@@ -925,6 +926,7 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(const u64* __restrict__ li
                 if (bestIdx >= 0 && bestDist <= OLF_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > fmul(nn_ratio, (float)bestDist2))) sel = bestIdx;
             }
             if (sel != assign[i]) { assign[i] = sel; s_changed = 1; }
+            if (adist) adist[i] = seld;                    // mode 0 only: the Hamming distance of the chosen candidate
             if (sel >= 0 && observed[i]) atomicMin(&own_new[sel], i);
         }
         __syncthreads();
@@ -947,8 +949,8 @@ static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t
     const size_t o_q = pl.d((size_t)nq * sizeof(SbpQuery)), o_qd = pl.d((size_t)nq * 32), o_obs = pl.d(nq), o_occ = pl.d(std::max(n_cur, 1));
     const size_t o_k = pl.d((size_t)n_cur * sizeof(olf_keypoint)), o_d = pl.d((size_t)n_cur * 32), o_u = pl.d((size_t)n_cur * 4);
     const size_t o_lists = pl.d((size_t)nq * SBP_K * 8), o_cnt = pl.d((size_t)nq * 4), o_oa = pl.d((size_t)n_cur * 4), o_ob = pl.d((size_t)n_cur * 4), o_as = pl.d((size_t)nq * 4), o_r = pl.d(4);
-    const size_t o_sig = pl.d((size_t)OLF_MAX_LEVELS * 4);
-    const size_t p_in = pl.p((size_t)nq * (sizeof(SbpQuery) + 33) + (size_t)n_cur * (sizeof(olf_keypoint) + 37) + 64 + OLF_MAX_LEVELS * 4), p_out = pl.p((size_t)nq * 8 + 16 + (size_t)nq * SBP_K * 8);
+    const size_t o_sig = pl.d((size_t)OLF_MAX_LEVELS * 4), o_ad = pl.d((size_t)nq * 4);
+    const size_t p_in = pl.p((size_t)nq * (sizeof(SbpQuery) + 33) + (size_t)n_cur * (sizeof(olf_keypoint) + 37) + 64 + OLF_MAX_LEVELS * 4), p_out = pl.p((size_t)nq * 12 + 16);
     if ((rc = arena_ensure(c, pl))) return rc;
     cudaStream_t s = c->cur;
     uint8_t* hp = hptr<uint8_t>(c, p_in);
@@ -971,22 +973,19 @@ static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t
     k_sbp_candidates<<<(nq + 7) / 8, 256, 0, s>>>(dptr<SbpQuery>(c, o_q), dptr<uint32_t>(c, o_qd), nq, dptr<olf_keypoint>(c, o_k), dptr<uint32_t>(c, o_d), dptr<float>(c, o_u), n_cur,
                                                   G, max_dist, gate, dptr<float>(c, o_sig), dptr<u64>(c, o_lists), dptr<int>(c, o_cnt));
     k_sbp_resolve<<<1, 1024, 0, s>>>(dptr<u64>(c, o_lists), dptr<int>(c, o_cnt), nq, n_cur, dptr<uint8_t>(c, o_obs), occupied ? dptr<uint8_t>(c, o_occ) : nullptr,
-                                     dptr<olf_keypoint>(c, o_k), mode, nn_ratio, dptr<int>(c, o_oa), dptr<int>(c, o_ob), dptr<int>(c, o_as), dptr<int>(c, o_r));
+                                     dptr<olf_keypoint>(c, o_k), mode, nn_ratio, dptr<int>(c, o_oa), dptr<int>(c, o_ob), dptr<int>(c, o_as), dptr<int>(c, o_r),
+                                     dist_out ? dptr<int>(c, o_ad) : nullptr);
     count_launches(2);
     int* ho = hptr<int>(c, p_out);
     OLF_CUDA(cudaMemcpyAsync(ho, dptr<int>(c, o_as), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaMemcpyAsync(ho + nq, dptr<int>(c, o_cnt), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
-    u64* hl = (u64*)(ho + 2 * nq + 4);
-    if (dist_out) OLF_CUDA(cudaMemcpyAsync(hl, dptr<u64>(c, o_lists), (size_t)nq * SBP_K * 8, cudaMemcpyDeviceToHost, s));
+    if (dist_out) OLF_CUDA(cudaMemcpyAsync(ho + 2 * nq, dptr<int>(c, o_ad), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(stream_sync(s));
     for (int i = 0; i < nq; ++i) {
         if (ho[nq + i] > SBP_K) { set_last_error("olf_search_by_projection: more than 128 candidates in one search window"); return OLF_ERR_CAPACITY; }
         assign_out[i] = ho[i];
-        if (dist_out) {          // distance of the chosen candidate: its key in the query's list
-            dist_out[i] = 256;
-            for (int e = 0; e < ho[nq + i] && ho[i] >= 0; ++e) if ((int)(hl[(size_t)i * SBP_K + e] & 0xFFFFFF) == ho[i]) { dist_out[i] = (int)(hl[(size_t)i * SBP_K + e] >> 40); break; }
-        }
+        if (dist_out) dist_out[i] = ho[i] >= 0 ? ho[2 * nq + i] : 256;
     }
     return OLF_OK;
 }
@@ -1111,6 +1110,84 @@ int window_search(const olf_window_search_args* a, int* best_idx, int* best_dist
     }
     return sbp_common(c, q, a->qdesc, observed.data(), a->blocked, a->kps, a->desc, a->u_right, a->n, a->cam, 0, std::min(a->max_dist, 256), 0.f, best_idx,
                       a->chi2_check ? 2 : 0, a->inv_level_sigma2, a->nlevels, best_dist);
+}
+
+static void rotation_filter(const std::vector<std::pair<int, float>>& rots, std::vector<int>& reject);
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522): the device builds, per level-0 keypoint of F1, the list of level-0 keypoints of
+// F2 in its window sorted by (distance, cell, index) -- the reference's preference order; the take-over rule (vMatchedDistance / vnMatches21) depends
+// on the order of the keypoints of F1 and runs on the host over those lists
+int search_for_initialization(const olf_keypoint* kps1, const uint8_t* desc1, int n1, const olf_keypoint* kps2, const uint8_t* desc2, int n2,
+                              const olf_camera* cam, float* prev_matched, int window_size, float nn_ratio, int check_orientation,
+                              int* m12, int* nmatches_out, int device) {
+    if (!cam || !m12 || !nmatches_out || n1 < 0 || n2 < 0 || (n1 && (!kps1 || !desc1 || !prev_matched)) || (n2 && (!kps2 || !desc2)) || window_size < 0) {
+        set_last_error("olf_search_for_initialization: bad arguments"); return OLF_ERR_ARG;
+    }
+    MatchCtx* c; int rc;
+    if ((rc = get_ctx(device, &c))) return rc;
+    *nmatches_out = 0;
+    for (int i = 0; i < n1; ++i) m12[i] = -1;
+    if (n1 == 0 || n2 == 0) return OLF_OK;
+    if (n2 >= (1 << 24)) { set_last_error("olf_search_for_initialization: too many keypoints"); return OLF_ERR_CAPACITY; }
+    std::vector<SbpQuery> q(n1);
+    for (int i = 0; i < n1; ++i) {
+        SbpQuery& Q = q[i];
+        Q.u = prev_matched[2 * i]; Q.v = prev_matched[2 * i + 1]; Q.radius = (float)window_size; Q.ur = 0.f;
+        Q.min_level = 0; Q.max_level = 0; Q.valid = kps1[i].octave <= 0;                     // `if (level1 > 0) continue`, GetFeaturesInArea(.., level1, level1)
+    }
+    Planner pl;
+    const size_t o_q = pl.d((size_t)n1 * sizeof(SbpQuery)), o_qd = pl.d((size_t)n1 * 32), o_k = pl.d((size_t)n2 * sizeof(olf_keypoint)), o_d = pl.d((size_t)n2 * 32),
+                 o_lists = pl.d((size_t)n1 * SBP_K * 8), o_cnt = pl.d((size_t)n1 * 4);
+    const size_t p_in = pl.p((size_t)n1 * (sizeof(SbpQuery) + 32) + (size_t)n2 * (sizeof(olf_keypoint) + 32) + 64), p_l = pl.p((size_t)n1 * SBP_K * 8), p_c = pl.p((size_t)n1 * 4);
+    if ((rc = arena_ensure(c, pl))) return rc;
+    cudaStream_t s = c->cur;
+    uint8_t* hp = hptr<uint8_t>(c, p_in);
+    size_t off = 0;
+    auto up = [&](size_t dev_off, const void* src, size_t bytes) -> int {
+        memcpy(hp + off, src, bytes);
+        cudaError_t e = cudaMemcpyAsync(c->a.dev.p + dev_off, hp + off, bytes, cudaMemcpyHostToDevice, s);
+        off += (bytes + 15) & ~(size_t)15;
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+        return OLF_OK;
+    };
+    if ((rc = up(o_q, q.data(), (size_t)n1 * sizeof(SbpQuery))) || (rc = up(o_qd, desc1, (size_t)n1 * 32)) || (rc = up(o_k, kps2, (size_t)n2 * sizeof(olf_keypoint))) ||
+        (rc = up(o_d, desc2, (size_t)n2 * 32))) return rc;
+    GridParams G; G.min_x = cam->min_x; G.min_y = cam->min_y;
+    G.inv_w = (float)OLF_GRID_COLS / (cam->max_x - cam->min_x); G.inv_h = (float)OLF_GRID_ROWS / (cam->max_y - cam->min_y);
+    k_sbp_candidates<<<(n1 + 7) / 8, 256, 0, s>>>(dptr<SbpQuery>(c, o_q), dptr<uint32_t>(c, o_qd), n1, dptr<olf_keypoint>(c, o_k), dptr<uint32_t>(c, o_d), nullptr, n2,
+                                                  G, 256, 0, nullptr, dptr<u64>(c, o_lists), dptr<int>(c, o_cnt));
+    count_launches(1);
+    OLF_CUDA(cudaMemcpyAsync(hptr<u64>(c, p_l), dptr<u64>(c, o_lists), (size_t)n1 * SBP_K * 8, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_c), dptr<int>(c, o_cnt), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    OLF_CUDA(cudaGetLastError());
+    OLF_CUDA(stream_sync(s));
+    const u64* lists = hptr<u64>(c, p_l); const int* cnt = hptr<int>(c, p_c);
+    std::vector<int> vMatchedDistance(n2, INT_MAX), vnMatches21(n2, -1);
+    std::vector<std::pair<int, float>> rots;
+    int nmatches = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        if (cnt[i1] > SBP_K) { set_last_error("olf_search_for_initialization: more than 128 candidates in one search window"); return OLF_ERR_CAPACITY; }
+        // first and second admissible entry of the sorted list = bestDist / bestIdx2 and bestDist2 of the reference's loop (:443-458)
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int e = 0; e < cnt[i1]; ++e) {
+            const int i2 = (int)(lists[(size_t)i1 * SBP_K + e] & 0xFFFFFF), dist = (int)(lists[(size_t)i1 * SBP_K + e] >> 40);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (bestIdx2 < 0) { bestDist = dist; bestIdx2 = i2; } else { bestDist2 = dist; break; }
+        }
+        if (bestIdx2 >= 0 && bestDist <= OLF_TH_LOW && (float)bestDist < (float)bestDist2 * nn_ratio) {
+            if (vnMatches21[bestIdx2] >= 0) { m12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+            m12[i1] = bestIdx2; vnMatches21[bestIdx2] = i1; vMatchedDistance[bestIdx2] = bestDist;
+            nmatches++;
+            rots.push_back({i1, kps1[i1].angle - kps2[bestIdx2].angle});
+        }
+    }
+    if (check_orientation) {
+        std::vector<int> reject;
+        rotation_filter(rots, reject);
+        for (int i1 : reject) if (m12[i1] >= 0) { m12[i1] = -1; nmatches--; }
+    }
+    for (int i1 = 0; i1 < n1; ++i1) if (m12[i1] >= 0) { prev_matched[2 * i1] = kps2[m12[i1]].x; prev_matched[2 * i1 + 1] = kps2[m12[i1]].y; }
+    *nmatches_out = nmatches;
+    return OLF_OK;
 }
 
 // ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:659-825): a warp per feature of KF1 (the features are independent: the

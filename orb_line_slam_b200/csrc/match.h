@@ -40,5 +40,7 @@ int bow_assemble(const int* word_id, const double* weight, const int* node_id, i
 int search_by_bow(const olf_bow_match_args* a, int* match_f, int* nmatches, int device);
 int search_by_bow_kf(const olf_bow_match_args* a, const uint8_t* has_point2, int* matches12, int* nmatches, int device);
 int window_search(const olf_window_search_args* a, int* best_idx, int* best_dist, int device);
+int search_for_initialization(const olf_keypoint* kps1, const uint8_t* desc1, int n1, const olf_keypoint* kps2, const uint8_t* desc2, int n2, const olf_camera* cam,
+                              float* prev_matched, int window_size, float nn_ratio, int check_orientation, int* m12, int* nmatches, int device);
 int search_for_triangulation(const olf_triangulation_args* a, int* matches12, int* nmatches, int device);
 }

@@ -1,5 +1,5 @@
-// The LocalMapping / LoopClosing / relocalisation overloads of ORB_SLAM2::ORBmatcher on the B200 (replaces src/ORBmatcher.cc:292-405,
-// 524-1328, 1620-1747).  Every overload keeps its O(#points) host prologue -- cv::Mat projection, depth / viewing-angle tests,
+// The LocalMapping / LoopClosing / relocalisation / initialisation overloads of ORB_SLAM2::ORBmatcher on the B200 (replaces
+// src/ORBmatcher.cc:292-1328, 1620-1747).  Every overload keeps its O(#points) host prologue -- cv::Mat projection, depth / viewing-angle tests,
 // MapPoint::PredictScale: the very calls the reference makes, so OpenCV's arithmetic is the reference's by construction -- and hands
 // the data-parallel part (grid window x octave window x Hamming distance, first minimum, blocking) to the sm_100a library:
 // olf_window_search, olf_search_for_triangulation, olf_search_by_bow_kf (include/olf_abi.h).  The epilogues (AddObservation /
@@ -307,6 +307,21 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     vMatchedPairs.clear();
     vMatchedPairs.reserve(nmatches);
     for (int i = 0; i < T1.n; i++) if (vMatches12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)vMatches12[i]));
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:407-522 (monocular map initialisation)
+int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize) {
+    const Target T1(F1.mvKeysUn, F1.mDescriptors, F1.fx, F1.fy, F1.cx, F1.cy, F1.mbf, F1.mnMinX, F1.mnMaxX, F1.mnMinY, F1.mnMaxY);
+    const Target T2(F2.mvKeysUn, F2.mDescriptors, F2.fx, F2.fy, F2.cx, F2.cy, F2.mbf, F2.mnMinX, F2.mnMaxX, F2.mnMinY, F2.mnMaxY);
+    std::vector<float> prev(2 * vbPrevMatched.size() + 2);
+    for (size_t i = 0; i < vbPrevMatched.size(); ++i) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    vnMatches12 = std::vector<int>(F1.mvKeysUn.size(), -1);
+    std::vector<int> m12(T1.n + 1, -1); int nmatches = 0;
+    if (olf_search_for_initialization(T1.kps.data(), T1.desc.data(), T1.n, T2.kps.data(), T2.desc.data(), T2.n, &T2.cam, prev.data(), windowSize, mfNNratio,
+                                      mbCheckOrientation, m12.data(), &nmatches, OLF_MATCHER_DEVICE) != OLF_OK)
+        throw std::runtime_error(std::string("[SearchForInitialization] ") + olf_last_error());
+    for (int i = 0; i < T1.n; ++i) { vnMatches12[i] = m12[i]; if (m12[i] >= 0) vbPrevMatched[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]); }
     return nmatches;
 }
 

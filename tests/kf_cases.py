@@ -159,3 +159,15 @@ def check_bow_kf(run, ratio, ori):
                             np.array([0, ori, ratio], np.float32), *orb_params(1000))
     m, n = oracle().search_by_bow_kf(kf1["desc"], kf1["kps"], 1 - kf1["skip"], kf1["fv"], kf2["desc"], kf2["kps"], 1 - kf2["skip"], kf2["fv"], ratio, bool(ori))
     assert np.array_equal(res_r, m) and n_r[0] == n > 60
+
+
+INIT_CASES = [(1, 100, 0.9, 1), (2, 40, 0.9, 0), (3, 100, 0.7, 1)]
+
+
+def check_init(run, seed, window, ratio, ori):
+    """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522)."""
+    from test_kf_matchers import init_case
+    k1, d1, k2, d2, cam, prev = init_case(seed, n=900)
+    m_r, n_r, p_r = run("init", keypoints_as_rows(k1), d1, keypoints_as_rows(k2), d2, _camv(cam), prev, np.array([window, ratio, ori], np.float32), *orb_params(1000))
+    m, n, pm = oracle().search_for_initialization(k1, d1, k2, d2, cam, prev, window, ratio, bool(ori))
+    assert np.array_equal(m_r, m) and n_r[0] == n > 50 and np.array_equal(p_r.view(np.uint32), pm.view(np.uint32))

@@ -143,6 +143,24 @@ int main(int argc, char** argv) {
             std::vector<int> res(Cur.N, -1);
             for (int j = 0; j < Cur.N; ++j) if (Cur.mvpMapPoints[j] && Cur.mvpMapPoints[j] != &marker) res[j] = (int)(Cur.mvpMapPoints[j] - pts.data());
             out.push_back(ints(res)); out.push_back(ints({n}));
+        } else if (cmd == "init") {
+            Frame F1, F2;
+            auto fill = [&](Frame& F, Arr& kps, Arr& desc) {
+                F.mvKeysUn = keypoints_from(kps); F.mvKeys = F.mvKeysUn; F.N = (int)F.mvKeysUn.size(); F.mDescriptors = desc_from(desc.as<uchar>(), F.N);
+                const float* c = in[4].as<float>();
+                F.fx = c[0]; F.fy = c[1]; F.cx = c[2]; F.cy = c[3]; F.mbf = c[4]; F.mnMinX = 0; F.mnMaxX = c[5]; F.mnMinY = 0; F.mnMaxY = c[6];
+            };
+            fill(F1, in[0], in[1]); fill(F2, in[2], in[3]);
+            std::vector<cv::Point2f> prev(F1.N);
+            for (int i = 0; i < F1.N; ++i) prev[i] = cv::Point2f(in[5].as<float>()[2 * i], in[5].as<float>()[2 * i + 1]);
+            const float* par = in[6].as<float>();
+            ORBmatcher matcher(par[1], par[2] != 0);
+            std::vector<int> m12;
+            const int n = matcher.SearchForInitialization(F1, F2, prev, m12, (int)par[0]);
+            std::vector<float> pv(2 * (size_t)F1.N + 2);
+            for (int i = 0; i < F1.N; ++i) { pv[2 * i] = prev[i].x; pv[2 * i + 1] = prev[i].y; }
+            out.push_back(ints(m12)); out.push_back(ints({n}));
+            Arr a; a.dtype = 2; a.dims = {(long long)F1.N, 2}; a.data.resize((size_t)F1.N * 8); if (F1.N) memcpy(a.data.data(), pv.data(), a.data.size()); out.push_back(a);
         } else if (cmd == "triangulation" || cmd == "bow_kf") {
             const Scales S = scales(in[17].as<int>()[1], in[18].as<float>()[0]);
             const float* geo = in[15].as<float>(); const float* fl = in[16].as<float>();

@@ -137,3 +137,5 @@ def test_shim_kf_overloads_equal_prologue_plus_oracle():
         KC.check_triangulation(run, only_stereo, ori)
     for ratio, ori in KC.BOW_CASES:
         KC.check_bow_kf(run, ratio, ori)
+    for seed, window, ratio, ori in KC.INIT_CASES:
+        KC.check_init(run, seed, window, ratio, ori)

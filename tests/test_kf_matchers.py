@@ -316,3 +316,103 @@ def test_gpu_edge_cases():
     with pytest.raises(RuntimeError, match="128 candidates"):
         api.window_search(dense["kps"], dense["desc"], dense["cam"], np.array([160.0], np.float32), np.array([120.0], np.float32), np.array([100.0], np.float32),
                           np.array([0], np.int32), np.array([7], np.int32), dense["desc"][:1], 256)
+
+
+# ---- ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522) ---------------------------------------------------------
+def init_case(seed, n=1500, shift=(6.0, -3.0)):
+    """Two monocular frames: F2 = F1's keypoints moved by a small flow + noise, descriptors of a small pool (take-overs and ties are frequent)."""
+    kf = K.make_keyframe(seed, n=n, pool=200)
+    rng = np.random.RandomState(seed + 1)
+    k1 = kf["kps"].copy(); k1["octave"] = np.where(rng.rand(n) < 0.6, 0, k1["octave"])
+    k2 = k1.copy()
+    k2["x"] = np.clip(k1["x"] + shift[0] + rng.randn(n) * 3, 0, 1279).astype(np.float32); k2["y"] = np.clip(k1["y"] + shift[1] + rng.randn(n) * 3, 0, 719).astype(np.float32)
+    k2["angle"] = ((k1["angle"] + rng.randn(n) * 4) % 360).astype(np.float32)
+    d2 = kf["desc"].copy()
+    for i in range(n):
+        for b in rng.randint(0, 256, rng.randint(0, 25)):
+            d2[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    perm = rng.permutation(n)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)                 # vbPrevMatched starts as F1's keypoints (src/Tracking.cc:731-733)
+    return k1, kf["desc"], k2[perm], d2[perm], kf["cam"], prev
+
+
+def init_numpy(k1, d1, k2, d2, cam, prev, window, ratio, ori):
+    n1, n2 = len(k1), len(k2)
+    m12 = np.full(n1, -1, np.int32); m21 = np.full(n2, -1, np.int64); md = np.full(n2, 2 ** 31 - 1, np.int64)
+    kf2 = dict(kps=k2, desc=d2, cam=cam)
+    hist = [[] for _ in range(30)]; nm = 0
+    inv_w = f32(f32(64) / f32(cam.max_x - cam.min_x)); inv_h = f32(f32(48) / f32(cam.max_y - cam.min_y))
+    px = np.floor((k2["x"] - f32(cam.min_x)) * inv_w + f32(0.5)).astype(int); py = np.floor((k2["y"] - f32(cam.min_y)) * inv_h + f32(0.5)).astype(int)
+    for i1 in range(n1):
+        if k1["octave"][i1] > 0:
+            continue
+        u, v, r = prev[i1, 0], prev[i1, 1], f32(window)
+        c0 = max(0, int(np.floor(f32(f32(f32(u - f32(cam.min_x)) - r) * inv_w)))); c1 = min(63, int(np.ceil(f32(f32(f32(u - f32(cam.min_x)) + r) * inv_w))))
+        r0 = max(0, int(np.floor(f32(f32(f32(v - f32(cam.min_y)) - r) * inv_h)))); r1 = min(47, int(np.ceil(f32(f32(f32(v - f32(cam.min_y)) + r) * inv_h))))
+        if c0 >= 64 or c1 < 0 or r0 >= 48 or r1 < 0:
+            continue
+        m = (px >= c0) & (px <= c1) & (py >= r0) & (py <= r1) & (px < 64) & (py < 48) & (k2["octave"] == 0)
+        m &= (np.abs(k2["x"] - u) < r) & (np.abs(k2["y"] - v) < r)
+        idx = np.nonzero(m)[0]
+        if len(idx) == 0:
+            continue
+        d = popcount_rows(d2[idx], d1[i1][None, :])
+        ok = md[idx] > d
+        idx, d = idx[ok], d[ok]
+        if len(idx) == 0:
+            continue
+        order = np.lexsort((idx, py[idx], px[idx], d))
+        best, bd = idx[order[0]], int(d[order[0]]); bd2 = int(d[order[1]]) if len(order) > 1 else 2 ** 31 - 1
+        if bd <= 50 and f32(bd) < f32(f32(bd2) * f32(ratio)):
+            if m21[best] >= 0:
+                m12[m21[best]] = -1; nm -= 1
+            m12[i1] = best; m21[best] = i1; md[best] = bd; nm += 1
+            rot = f32(k1["angle"][i1] - k2["angle"][best])
+            if rot < 0:
+                rot = f32(rot + f32(360))
+            b = int(np.floor(float(f32(rot * f32(f32(1.0) / f32(30)))) + 0.5))
+            hist[0 if b == 30 else b].append(i1)
+    if ori:
+        sizes = [len(h) for h in hist]; mx = [0, 0, 0]; ind = [-1, -1, -1]
+        for i, s_ in enumerate(sizes):
+            if s_ > mx[0]:
+                mx = [s_, mx[0], mx[1]]; ind = [i, ind[0], ind[1]]
+            elif s_ > mx[1]:
+                mx = [mx[0], s_, mx[1]]; ind = [ind[0], i, ind[1]]
+            elif s_ > mx[2]:
+                mx[2] = s_; ind[2] = i
+        if mx[1] < f32(0.1) * f32(mx[0]):
+            ind[1] = ind[2] = -1
+        elif mx[2] < f32(0.1) * f32(mx[0]):
+            ind[2] = -1
+        for i, h in enumerate(hist):
+            if i not in ind:
+                for e in h:
+                    if m12[e] >= 0:
+                        m12[e] = -1; nm -= 1
+    out = prev.copy()
+    for i1 in np.nonzero(m12 >= 0)[0]:
+        out[i1] = (k2["x"][m12[i1]], k2["y"][m12[i1]])
+    return m12, nm, out
+
+
+@pytest.mark.parametrize("seed,window,ratio,ori", [(1, 100, 0.9, True), (2, 40, 0.9, False), (3, 100, 0.7, True)])
+def test_oracle_search_for_initialization_matches_numpy(seed, window, ratio, ori):
+    k1, d1, k2, d2, cam, prev = init_case(seed, n=500)
+    m, n, pm = oracle().search_for_initialization(k1, d1, k2, d2, cam, prev, window, ratio, ori)
+    m2, n2, pm2 = init_numpy(k1, d1, k2, d2, cam, prev, window, ratio, ori)
+    assert np.array_equal(m, m2) and n == n2 and np.array_equal(pm, pm2) and n > 30
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,window,ratio,ori", [(1, 2000, 100, 0.9, True), (2, 2000, 30, 0.9, False), (3, 1000, 100, 0.7, True), (4, 60, 100, 0.9, True)])
+def test_gpu_search_for_initialization(seed, n, window, ratio, ori):
+    import orb_line_slam_b200 as olf
+    k1, d1, k2, d2, cam, prev = init_case(seed, n=n)
+    gm, gn, gp = olf.api(0).search_for_initialization(k1, d1, k2, d2, cam, prev, window, ratio, ori)
+    om, on, op = oracle().search_for_initialization(k1, d1, k2, d2, cam, prev, window, ratio, ori)
+    assert np.array_equal(gm, om) and gn == on and np.array_equal(gp, op) and gn > n // 30
+    e = olf.api(0).search_for_initialization(k1[:0], d1[:0], k2, d2, cam, prev[:0], window, ratio, ori)
+    assert len(e[0]) == 0 and e[1] == 0
+    gm, gn, gp = olf.api(0).search_for_initialization(k1, d1, k2[:0], d2[:0], cam, prev, window, ratio, ori)
+    assert gn == 0 and (gm == -1).all() and np.array_equal(gp, prev)

@@ -203,3 +203,8 @@ def test_search_for_triangulation(only_stereo, ori):
 @pytest.mark.parametrize("ratio,ori", KC.BOW_CASES)
 def test_search_by_bow_keyframes(ratio, ori):
     KC.check_bow_kf(refcli.run, ratio, ori)
+
+
+@pytest.mark.parametrize("seed,window,ratio,ori", KC.INIT_CASES)
+def test_search_for_initialization(seed, window, ratio, ori):
+    KC.check_init(refcli.run, seed, window, ratio, ori)
