@@ -23,9 +23,24 @@ using namespace lsd;
 
 // ---- cv::resize INTER_LINEAR_EXACT 8UC1 -------------------------------------------------------
 struct ExCoef { int s; int c0, c1; };
-__global__ void k_resize_exact(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
-                               uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
+// Everything before region growing runs ONE launch per stage for all images of a call (blockIdx.z / .y = image): the images of a rig have the
+// same size and parameters, and every one of these stages is launch-bound on a single 0.9-MB image.
+#define LSD_PRE_MAX 16
+struct LsdPlan;
+struct PhaseState;
+struct PreBatch {
+    int n;
+    const uint8_t* work_src[LSD_PRE_MAX]; uint8_t* scaled[LSD_PRE_MAX];          // resize: blurred (or raw) image -> scaled image
+    const uint8_t* grad_src[LSD_PRE_MAX];                                        // gradient input (scaled image, or the raw one at scale 1)
+    float* ang[LSD_PRE_MAX]; short2_t* dabc[LSD_PRE_MAX]; PxRec* px[LSD_PRE_MAX];
+    int* n2max[LSD_PRE_MAX]; unsigned* hist[LSD_PRE_MAX]; unsigned* bin_start[LSD_PRE_MAX]; unsigned* cursor[LSD_PRE_MAX];
+    int* seed_pix[LSD_PRE_MAX]; u64* seed_prio[LSD_PRE_MAX]; LsdPlan* plan[LSD_PRE_MAX];
+    unsigned* ctrs[LSD_PRE_MAX]; int* status[LSD_PRE_MAX]; PhaseState* phase[LSD_PRE_MAX];
+};
+__global__ void k_resize_exact(const __grid_constant__ PreBatch PB, int sw, int sh, int spitch, int dw, int dh, int dpitch,
                                const ExCoef* __restrict__ cx, const ExCoef* __restrict__ cy) {
+    const uint8_t* __restrict__ src = PB.work_src[blockIdx.z];
+    uint8_t* __restrict__ dst = PB.scaled[blockIdx.z];
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
@@ -41,9 +56,11 @@ __global__ void k_resize_exact(const uint8_t* __restrict__ src, int sw, int sh, 
 
 // ---- ll_angle: gradient, level-line angle, max gradient ---------------------------------
 // n2_thresh = smallest gx^2+gy^2 whose norm sqrt(n2/4.0) exceeds rho (computed exactly on the host).
-__global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, int W, int H, int pitch, int n2_thresh,
-                                                  float* __restrict__ ang, short2_t* __restrict__ dabc,
-                                                  const float2_t* __restrict__ tab_acc, PxRec* __restrict__ px, int* __restrict__ n2max) {
+__global__ void __launch_bounds__(256) k_lsd_grad(const __grid_constant__ PreBatch PB, int W, int H, int pitch, int n2_thresh,
+                                                  const float2_t* __restrict__ tab_acc) {
+    const uint8_t* __restrict__ img = PB.grad_src[blockIdx.z];
+    float* __restrict__ ang = PB.ang[blockIdx.z]; short2_t* __restrict__ dabc = PB.dabc[blockIdx.z];
+    PxRec* __restrict__ px = PB.px[blockIdx.z]; int* __restrict__ n2max = PB.n2max[blockIdx.z];
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     int n2 = 0;
@@ -82,8 +99,9 @@ __device__ __forceinline__ double lsd_bin_coef(int n2max, int n_bins) {
 }
 
 // histogram of gradient bins over defined pixels
-__global__ void __launch_bounds__(256) k_lsd_hist(const float* __restrict__ ang, const short2_t* __restrict__ dabc, int S,
-                                                  const int* __restrict__ n2max, int n_bins, unsigned* __restrict__ hist) {
+__global__ void __launch_bounds__(256) k_lsd_hist(const __grid_constant__ PreBatch PB, int S, int n_bins) {
+    const float* __restrict__ ang = PB.ang[blockIdx.y]; const short2_t* __restrict__ dabc = PB.dabc[blockIdx.y];
+    const int* __restrict__ n2max = PB.n2max[blockIdx.y]; unsigned* __restrict__ hist = PB.hist[blockIdx.y];
     extern __shared__ unsigned sh[];
     for (int i = threadIdx.x; i < n_bins; i += 256) sh[i] = 0;
     __syncthreads();
@@ -96,8 +114,9 @@ __global__ void __launch_bounds__(256) k_lsd_hist(const float* __restrict__ ang,
 
 // one block: bin offsets (descending bin order) and the wave plan (whole bins, cumulative targets doubling)
 struct LsdPlan { int n_seeds; int n_waves; int wave_start[64]; };
-__global__ void __launch_bounds__(1024) k_lsd_plan(const unsigned* __restrict__ hist, int n_bins, int first_wave, int wave_growth, unsigned* __restrict__ bin_start,
-                                                    unsigned* __restrict__ cursor, LsdPlan* __restrict__ plan) {
+__global__ void __launch_bounds__(1024) k_lsd_plan(const __grid_constant__ PreBatch PB, int n_bins, int first_wave, int wave_growth) {
+    const unsigned* __restrict__ hist = PB.hist[blockIdx.x]; unsigned* __restrict__ bin_start = PB.bin_start[blockIdx.x];
+    unsigned* __restrict__ cursor = PB.cursor[blockIdx.x]; LsdPlan* __restrict__ plan = PB.plan[blockIdx.x];
     __shared__ unsigned sh[1024], st[1024];
     for (int b = threadIdx.x; b < 1024; b += blockDim.x) sh[b] = b < n_bins ? hist[b] : 0;
     __syncthreads();
@@ -118,10 +137,11 @@ __global__ void __launch_bounds__(1024) k_lsd_plan(const unsigned* __restrict__ 
     for (int b = threadIdx.x; b < n_bins; b += blockDim.x) { bin_start[b] = st[b]; cursor[b] = 0; }
 }
 
-__global__ void __launch_bounds__(256) k_lsd_scatter(const float* __restrict__ ang, const short2_t* __restrict__ dabc, int S,
-                                                     const int* __restrict__ n2max, int n_bins, const unsigned* __restrict__ bin_start,
-                                                     unsigned* __restrict__ cursor, int* __restrict__ seed_pix, u64* __restrict__ seed_prio,
-                                                     PxRec* __restrict__ px) {
+__global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ PreBatch PB, int S, int n_bins) {
+    const float* __restrict__ ang = PB.ang[blockIdx.y]; const short2_t* __restrict__ dabc = PB.dabc[blockIdx.y];
+    const int* __restrict__ n2max = PB.n2max[blockIdx.y]; const unsigned* __restrict__ bin_start = PB.bin_start[blockIdx.y];
+    unsigned* __restrict__ cursor = PB.cursor[blockIdx.y]; int* __restrict__ seed_pix = PB.seed_pix[blockIdx.y];
+    u64* __restrict__ seed_prio = PB.seed_prio[blockIdx.y]; PxRec* __restrict__ px = PB.px[blockIdx.y];
     const double coef = lsd_bin_coef(*n2max, n_bins);
     for (int q = blockIdx.x * 256 + threadIdx.x; q < S; q += gridDim.x * 256)
         if (ang[q] >= 0.f) {
@@ -239,6 +259,18 @@ __device__ __forceinline__ void wl_append(bool take, int value, int* __restrict_
 __device__ __forceinline__ void image_done(const GrowBatch& B) {
     if (atomicAdd(&B.conv[LSD_MAX_WAVES], 1u) + 1u == (unsigned)B.n && B.cond) cudaGraphSetConditional(B.cond, 0);
 }
+// start of a call: counters, histogram, status and the state machine of every image of the batch (one launch instead of five stream operations per image)
+__global__ void __launch_bounds__(256) k_lsd_reset(const __grid_constant__ PreBatch PB) {
+    const int k = blockIdx.x;
+    for (int i = threadIdx.x; i < 1024; i += 256) PB.hist[k][i] = 0u;
+    if (threadIdx.x < 4) { PB.ctrs[k][threadIdx.x] = 0u; PB.status[k][threadIdx.x] = 0; }
+    if (threadIdx.x == 0) {
+        *PB.n2max[k] = 0;
+        PhaseState z; memset(&z, 0, sizeof(z)); z.round = 1; z.wave_first_round = 1;
+        *PB.phase[k] = z;
+    }
+}
+
 // pass 1: every candidate of the wave -- dead or alive (+ first-round deferral); alive seeds and seeds that died owning a
 // region go to work list 1; the bitmap that collects THIS round's events is cleared
 __global__ void __launch_bounds__(256) k_lsd_scan(const __grid_constant__ GrowBatch B) {
@@ -1270,38 +1302,61 @@ static int line_upload(LineImpl* h, const uint8_t* img, int w, int hgt, int stri
     return OLF_OK;
 }
 
-// LSD on the uploaded image, stage 1: everything before region growing + this image's descriptor for the batched passes
-static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D, int batch_images) {
-    const int w = h->img_w, hgt = h->img_h, W = h->W, H = h->H, S = h->S;
-    const uint8_t* work = h->img.p; int wp = h->ipitch;
-    if (h->blur_k) {
-        const LevelTable T = single_level(w, hgt, h->ipitch);
+// (the per-image part that stays on the host: this image's descriptor for the batched passes follows in lsd_fill_dev)
+// LSD on the uploaded images, stage 1: everything before region growing, ONE launch per stage for all images of the call
+static int lsd_enqueue_pre_batch(LineImpl* const* hs, int n, cudaStream_t s) {
+    LineImpl* h0 = hs[0];
+    const int w = h0->img_w, hgt = h0->img_h, W = h0->W, H = h0->H, S = h0->S;
+    for (int k = 1; k < n; ++k)
+        if (hs[k]->img_w != w || hs[k]->img_h != hgt || hs[k]->blur_k != h0->blur_k || hs[k]->P.lsd_n_bins != h0->P.lsd_n_bins || hs[k]->n2_thresh != h0->n2_thresh ||
+            hs[k]->P.lsd_scale != h0->P.lsd_scale || hs[k]->has_tma != h0->has_tma) { set_last_error("line batch: extractors of one batch must share size and parameters"); return OLF_ERR_ARG; }
+    PreBatch PB; memset(&PB, 0, sizeof(PB)); PB.n = n;
+    for (int k = 0; k < n; ++k) {
+        LineImpl* h = hs[k];
+        PB.work_src[k] = h->blur_k ? h->blurred.p : h->img.p; PB.scaled[k] = h->scaled.p;
+        PB.grad_src[k] = h->blur_k ? h->scaled.p : h->img.p;
+        PB.ang[k] = h->ang.p; PB.dabc[k] = h->dabc.p; PB.px[k] = h->px.p + h->W + 2; PB.n2max[k] = h->n2max.p; PB.hist[k] = h->hist.p;
+        PB.bin_start[k] = h->bin_start.p; PB.cursor[k] = h->cursor.p; PB.seed_pix[k] = h->seed_pix.p; PB.seed_prio[k] = h->seed_prio.p; PB.plan[k] = h->plan.p;
+        PB.ctrs[k] = h->ctrs.p; PB.status[k] = h->status.p; PB.phase[k] = h->phase.p;
+        if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
+    }
+    k_lsd_reset<<<n, 256, 0, s>>>(PB);
+    int wp = h0->ipitch;
+    if (h0->blur_k) {
+        const LevelTable T = single_level(w, hgt, h0->ipitch);
         const int nt = T.tile_start[1];
-        BlurBatch bb; memset(&bb, 0, sizeof(bb)); bb.src[0] = h->img.p; bb.dst[0] = h->blurred.p;
-        if (h->blur_k == 7 && h->has_tma) k_blur_q8_tma<7, 1><<<nt, 256, 0, s>>>(bb, h->tmaps[0], T, h->blur_q[0], h->blur_q[1], h->blur_q[2], h->blur_q[3]);
-        else if (h->blur_k == 7) k_blur_q8<7><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], h->blur_q[3]);
-        else if (h->blur_k == 5) k_blur_q8<5><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], h->blur_q[2], 0);
-        else k_blur_q8<3><<<nt, 256, 0, s>>>(bb, T, h->blur_q[0], h->blur_q[1], 0, 0);
-        dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-        k_resize_exact<<<g, b, 0, s>>>(h->blurred.p, w, hgt, h->ipitch, h->scaled.p, W, H, h->wpitch, h->coef.p, h->coef.p + h->coef_y_off);
-        work = h->scaled.p; wp = h->wpitch;
+        BlurBatch bb; memset(&bb, 0, sizeof(bb));
+        for (int k = 0; k < n; ++k) { bb.src[k] = hs[k]->img.p; bb.dst[k] = hs[k]->blurred.p; }
+        if (h0->blur_k == 7 && h0->has_tma) {
+            static thread_local TmaSet<LSD_PRE_MAX> M;
+            for (int k = 0; k < n; ++k) M.m[k] = hs[k]->tmaps[0].m[0];
+            k_blur_q8_tma<7, LSD_PRE_MAX><<<dim3(nt, n), 256, 0, s>>>(bb, M, T, h0->blur_q[0], h0->blur_q[1], h0->blur_q[2], h0->blur_q[3]);
+        }
+        else if (h0->blur_k == 7) k_blur_q8<7><<<dim3(nt, n), 256, 0, s>>>(bb, T, h0->blur_q[0], h0->blur_q[1], h0->blur_q[2], h0->blur_q[3]);
+        else if (h0->blur_k == 5) k_blur_q8<5><<<dim3(nt, n), 256, 0, s>>>(bb, T, h0->blur_q[0], h0->blur_q[1], h0->blur_q[2], 0);
+        else k_blur_q8<3><<<dim3(nt, n), 256, 0, s>>>(bb, T, h0->blur_q[0], h0->blur_q[1], 0, 0);
+        dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8, n);
+        k_resize_exact<<<g, b, 0, s>>>(PB, w, hgt, h0->ipitch, W, H, h0->wpitch, h0->coef.p, h0->coef.p + h0->coef_y_off);
+        wp = h0->wpitch;
     }
-    OLF_CUDA(cudaMemsetAsync(h->n2max.p, 0, sizeof(int), s));
-    OLF_CUDA(cudaMemsetAsync(h->hist.p, 0, 1024 * sizeof(unsigned), s));
-    OLF_CUDA(cudaMemsetAsync(h->ctrs.p, 0, 4 * sizeof(unsigned), s));
-    OLF_CUDA(cudaMemsetAsync(h->status.p, 0, 4 * sizeof(int), s));
     {
-        dim3 g((W + 31) / 32, (H + 7) / 8);
-        k_lsd_grad<<<g, 256, 0, s>>>(work, W, H, wp, h->n2_thresh, h->ang.p, h->dabc.p, h->tab_acc.p, h->px.p + h->W + 2, h->n2max.p);
+        dim3 g((W + 31) / 32, (H + 7) / 8, n);
+        k_lsd_grad<<<g, 256, 0, s>>>(PB, W, H, wp, h0->n2_thresh, h0->tab_acc.p);
     }
-    const int nb = h->P.lsd_n_bins;
-    k_lsd_hist<<<296, 256, nb * sizeof(unsigned), s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->hist.p);
+    const int nb = h0->P.lsd_n_bins;
+    k_lsd_hist<<<dim3(296, n), 256, nb * sizeof(unsigned), s>>>(PB, S, nb);
     // Wave plan: with persistent claims a round costs little, so a BIG first wave (few waves, few first rounds whose critical
     // path is the longest region) gives the lowest latency (5.7 instead of 10.5 ms per image) at the price of ~40 % more
     // speculative growth; a batch, which is throughput-bound, keeps the small first wave.
-    k_lsd_plan<<<1, 1024, 0, s>>>(h->hist.p, nb, batch_images <= 2 ? h->first_wave_latency : h->first_wave, h->wave_growth, h->bin_start.p, h->cursor.p, h->plan.p);
-    k_lsd_scatter<<<296, 256, 0, s>>>(h->ang.p, h->dabc.p, S, h->n2max.p, nb, h->bin_start.p, h->cursor.p, h->seed_pix.p, h->seed_prio.p, h->px.p + h->W + 2);
-    count_launches((h->blur_k ? 2 : 0) + 4);
+    k_lsd_plan<<<n, 1024, 0, s>>>(PB, nb, n <= 2 ? h0->first_wave_latency : h0->first_wave, h0->wave_growth);
+    k_lsd_scatter<<<dim3(296, n), 256, 0, s>>>(PB, S, nb);
+    count_launches((h0->blur_k ? 2 : 0) + 5);
+    OLF_CUDA(cudaGetLastError());
+    return OLF_OK;
+}
+// this image's descriptor for the batched passes (host side only)
+static int lsd_fill_dev(LineImpl* h, GrowDev& D) {
+    const int W = h->W, H = h->H;
     D.C.W = W; D.C.H = H; D.C.px = h->px.p + W + 2; D.C.dabc = h->dabc.p; D.C.tab_seed = h->tab_seed.p;
     D.C.pool = h->pool.p; D.C.pool_ctr = h->ctrs.p; D.C.pool_chunks = h->pool_chunks;
     D.C.srec = h->srec0.p; D.C.regang = h->regang.p;
@@ -1322,10 +1377,6 @@ static int lsd_enqueue_pre(LineImpl* h, cudaStream_t s, GrowDev& D, int batch_im
     D.dbg = h->trace ? h->dbg.p : nullptr;
     D.cont[0] = h->cont.p; D.cont[1] = h->cont.p + h->cont.n / 2; D.budget = h->grow_budget;
     D.sstate = h->sstate.p; D.tbox = h->tbox.p; D.event_scan = getenv("OLF_LSD_FULL_SCAN") ? 0 : 1;
-    if (h->trace) OLF_CUDA(cudaMemsetAsync(h->dbg.p, 0, (size_t)h->max_rounds * TRACE_REC * sizeof(int), s));
-    h->phase_init.p[0] = PhaseState{}; h->phase_init.p[0].round = 1; h->phase_init.p[0].wave_first_round = 1;
-    OLF_CUDA(cudaMemcpyAsync(h->phase.p, h->phase_init.p, sizeof(PhaseState), cudaMemcpyHostToDevice, s));
-    OLF_CUDA(cudaGetLastError());
     return OLF_OK;
 }
 // stage 3 (after the passes): first half of the rectangle fit + the counters the host needs
@@ -1345,7 +1396,8 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     if (n < 1 || n > LSD_MAX_BATCH) { set_last_error("LSD batch size out of range"); return OLF_ERR_ARG; }
     GrowBatch B; memset(&B, 0, sizeof(B));
     int rc;
-    for (int k = 0; k < n; ++k) { if ((rc = lsd_enqueue_pre(hs[k], s, B.d[k], n))) return rc; B.st[k] = hs[k]->phase.p; }
+    if ((rc = lsd_enqueue_pre_batch(hs, n, s))) return rc;
+    for (int k = 0; k < n; ++k) { if ((rc = lsd_fill_dev(hs[k], B.d[k]))) return rc; B.st[k] = hs[k]->phase.p; }
     LineImpl* h0 = hs[0];
     B.conv = h0->conv.p; B.n = n;
     OLF_CUDA(cudaMemsetAsync(h0->conv.p, 0, (LSD_MAX_WAVES + 1) * sizeof(unsigned), s));
