@@ -820,11 +820,23 @@ struct RectRec { double x, y, theta; u64 prio; };
 // Warp per region.  The reference's sums are sequential double additions in BFS order (not associative), so the additions
 // stay a single chain -- but everything that feeds them (pixel fetch, gradient weight sqrt/div, products) is computed by
 // the 32 lanes in parallel and staged in shared memory; lane 0 only walks the three add chains.
-__global__ void __launch_bounds__(256) k_lsd_rect_a(const LsdRegion* __restrict__ regs, const unsigned* __restrict__ nreg, unsigned cap,
-                                                    const unsigned* __restrict__ final_pool, const short2_t* __restrict__ dabc, int W,
-                                                    double prec, RectRec* __restrict__ out_host) {
+// per-image pointers of the rectangle passes and of the LBD passes (blockIdx.y = image)
+struct LbdLine;
+struct PostBatch {
+    const LsdRegion* regs[LSD_PRE_MAX]; const unsigned* nreg[LSD_PRE_MAX]; const unsigned* final_pool[LSD_PRE_MAX]; const short2_t* dabc[LSD_PRE_MAX];
+    RectRec* rect_host[LSD_PRE_MAX]; const double2* dir_host[LSD_PRE_MAX]; float4* seg_host[LSD_PRE_MAX];
+    const int* status[LSD_PRE_MAX]; int* status_host[LSD_PRE_MAX]; unsigned* nreg_host[LSD_PRE_MAX];
+    int nr[LSD_PRE_MAX];                                  // rect_b / LBD: regions (lines) of the image
+    const uint8_t* lbd_blur[LSD_PRE_MAX]; short2_t* grad[LSD_PRE_MAX]; const LbdLine* lines[LSD_PRE_MAX]; float4* rowsum[LSD_PRE_MAX]; uint8_t* desc_host[LSD_PRE_MAX];
+};
+__global__ void __launch_bounds__(256) k_lsd_rect_a(const __grid_constant__ PostBatch PB, unsigned cap, int W, double prec) {
+    const LsdRegion* __restrict__ regs = PB.regs[blockIdx.y]; const unsigned* __restrict__ nreg = PB.nreg[blockIdx.y];
+    const unsigned* __restrict__ final_pool = PB.final_pool[blockIdx.y]; const short2_t* __restrict__ dabc = PB.dabc[blockIdx.y];
+    RectRec* __restrict__ out_host = PB.rect_host[blockIdx.y];
     __shared__ double sh[8][3][32];
     const unsigned n = min(*nreg, cap);
+    // what the host looks at after the chain, written straight to mapped host memory (no copies to enqueue per image)
+    if (blockIdx.x == 0 && threadIdx.x < 4) { PB.status_host[blockIdx.y][threadIdx.x] = PB.status[blockIdx.y][threadIdx.x]; if (threadIdx.x == 0) *PB.nreg_host[blockIdx.y] = *nreg; }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (unsigned r = blockIdx.x * 8 + warp; r < n; r += gridDim.x * 8) {
         const LsdRegion R = regs[r];
@@ -884,9 +896,11 @@ __global__ void __launch_bounds__(256) k_lsd_rect_a(const LsdRegion* __restrict_
     }
 }
 // warp per region: extreme projections on the (host-libm) direction -> segment end points (Vec4f)
-__global__ void __launch_bounds__(256) k_lsd_rect_b(const LsdRegion* __restrict__ regs, int n, const unsigned* __restrict__ final_pool, int W,
-                                                    const RectRec* __restrict__ rect, const double2* __restrict__ dir, double scale,
-                                                    float4* __restrict__ seg_host) {
+__global__ void __launch_bounds__(256) k_lsd_rect_b(const __grid_constant__ PostBatch PB, int W, double scale) {
+    const LsdRegion* __restrict__ regs = PB.regs[blockIdx.y]; const unsigned* __restrict__ final_pool = PB.final_pool[blockIdx.y];
+    const RectRec* __restrict__ rect = PB.rect_host[blockIdx.y]; const double2* __restrict__ dir = PB.dir_host[blockIdx.y];
+    float4* __restrict__ seg_host = PB.seg_host[blockIdx.y];
+    const int n = PB.nr[blockIdx.y];
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (r >= n) return;
     const LsdRegion R = regs[r];
@@ -912,7 +926,8 @@ __global__ void __launch_bounds__(256) k_lsd_rect_b(const LsdRegion* __restrict_
 
 // ---- LBD (binary_descriptor_custom.cpp:350-412, 1026-1372) ---------------------------------------------------------
 // cv::Sobel 8U->16S ksize 3, BORDER_REFLECT_101; dx and dy packed as short2 per pixel
-__global__ void __launch_bounds__(256) k_sobel3(const uint8_t* __restrict__ img, int w, int h, int pitch, short2_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_sobel3(const __grid_constant__ PostBatch PB, int w, int h, int pitch) {
+    const uint8_t* __restrict__ img = PB.lbd_blur[blockIdx.z]; short2_t* __restrict__ out = PB.grad[blockIdx.z];
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= w || y >= h) return;
     const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
@@ -930,8 +945,10 @@ __constant__ float c_gaussG[63];
 __constant__ float c_gaussL[21];
 
 // thread per (line, row of the line support region): the reference's sequential float sums along the row (:1146-1186)
-__global__ void __launch_bounds__(256) k_lbd_rows(const LbdLine* __restrict__ lines, int n, const short2_t* __restrict__ grad,
-                                                  int imw, int imh, float4* __restrict__ rowsum) {
+__global__ void __launch_bounds__(256) k_lbd_rows(const __grid_constant__ PostBatch PB, int imw, int imh) {
+    const LbdLine* __restrict__ lines = PB.lines[blockIdx.y]; const short2_t* __restrict__ grad = PB.grad[blockIdx.y];
+    float4* __restrict__ rowsum = PB.rowsum[blockIdx.y];
+    const int n = PB.nr[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * 63) return;
     const int li = t / 63, hID = t % 63;
@@ -964,7 +981,9 @@ __global__ void __launch_bounds__(256) k_lbd_rows(const LbdLine* __restrict__ li
 
 __constant__ unsigned char c_lbd_comb[64];
 // thread per line: fold the 63 rows into 9 bands in reference order, mean/std, normalise, clamp, binarise (:1188-1341, :401-412)
-__global__ void __launch_bounds__(64) k_lbd_fold(const float4* __restrict__ rowsum, int n, uint8_t* __restrict__ desc_host) {
+__global__ void __launch_bounds__(64) k_lbd_fold(const __grid_constant__ PostBatch PB) {
+    const float4* __restrict__ rowsum = PB.rowsum[blockIdx.y]; uint8_t* __restrict__ desc_host = PB.desc_host[blockIdx.y];
+    const int n = PB.nr[blockIdx.y];
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n) return;
     float band[8][9];
@@ -1380,11 +1399,21 @@ static int lsd_fill_dev(LineImpl* h, GrowDev& D) {
     return OLF_OK;
 }
 // stage 3 (after the passes): first half of the rectangle fit + the counters the host needs
-static int lsd_enqueue_rect_a(LineImpl* h, cudaStream_t s) {
-    k_lsd_rect_a<<<296, 256, 0, s>>>(h->regs.p, h->ctrs.p + 3, h->reg_cap, h->final_pool.p, h->dabc.p, h->W, h->prec, h->rect_host.d);
+static void post_fill(PostBatch& PB, LineImpl* const* hs, int n) {
+    memset(&PB, 0, sizeof(PB));
+    for (int k = 0; k < n; ++k) {
+        LineImpl* h = hs[k];
+        PB.regs[k] = h->regs.p; PB.nreg[k] = h->ctrs.p + 3; PB.final_pool[k] = h->final_pool.p; PB.dabc[k] = h->dabc.p;
+        PB.rect_host[k] = h->rect_host.d; PB.dir_host[k] = h->dir_host.d; PB.seg_host[k] = h->seg_host.d;
+        PB.status[k] = h->status.p; PB.status_host[k] = h->status_host.d; PB.nreg_host[k] = h->nreg_host.d;
+        PB.lbd_blur[k] = h->lbd_blur.p; PB.grad[k] = h->grad.p; PB.lines[k] = h->lbd_lines.d; PB.rowsum[k] = h->rowsum.p; PB.desc_host[k] = h->desc_host.d;
+    }
+}
+// stage 3 (after the passes): first half of the rectangle fit + the counters the host needs, all images of the batch in one launch
+static int lsd_enqueue_rect_a(LineImpl* const* hs, int n, cudaStream_t s) {
+    PostBatch PB; post_fill(PB, hs, n);
+    k_lsd_rect_a<<<dim3(296, n), 256, 0, s>>>(PB, hs[0]->reg_cap, hs[0]->W, hs[0]->prec);
     count_launches(1);
-    OLF_CUDA(cudaMemcpyAsync(h->nreg_host.p, h->ctrs.p + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    OLF_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     OLF_CUDA(cudaGetLastError());
     return OLF_OK;
 }
@@ -1471,7 +1500,7 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
         if (graph_ok) { OLF_CUDA(cudaGraphLaunch(h0->graph_exec, s)); count_launches(3 * 30); }      // ~30 rounds x 3 passes (the exact count stays on the device)
         else enqueue_phases(h0->phase_batch);
         OLF_CUDA(cudaEventRecord(h0->ev_grow1, s));
-        for (int k = 0; k < n; ++k) if ((rc = lsd_enqueue_rect_a(hs[k], s))) return rc;
+        if ((rc = lsd_enqueue_rect_a(hs, n, s))) return rc;
         OLF_CUDA(h0->sync.sync(s));
         bool all = true;
         for (int k = 0; k < n; ++k) all = all && (hs[k]->status_host.p[3] || hs[k]->status_host.p[0]);
@@ -1489,10 +1518,14 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
         h->last_stats[2] = nr;
         segs[k].clear();
         if (nr == 0) continue;
-        // libm cos/sin of the O(#regions) rectangle angles, then the projection pass on the device
+        // libm cos/sin of the O(#regions) rectangle angles; the projection pass of all images follows in one launch
         for (int i = 0; i < nr; ++i) { const double t = h->rect_host.p[i].theta; h->dir_host.p[i] = make_double2(std::cos(t), std::sin(t)); }
-        k_lsd_rect_b<<<(nr + 7) / 8, 256, 0, s>>>(h->regs.p, nr, h->final_pool.p, h->W, h->rect_host.d, h->dir_host.d, h->P.lsd_scale, h->seg_host.d);
-        count_launches(1);
+    }
+    {
+        PostBatch PB; post_fill(PB, hs, n);
+        int max_nr = 0;
+        for (int k = 0; k < n; ++k) { PB.nr[k] = hs[k]->last_stats[2]; max_nr = std::max(max_nr, PB.nr[k]); }
+        if (max_nr > 0) { k_lsd_rect_b<<<dim3((max_nr + 7) / 8, n), 256, 0, s>>>(PB, h0->W, h0->P.lsd_scale); count_launches(1); }
     }
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(h0->sync.sync(s));
@@ -1547,34 +1580,63 @@ static void make_keylines(const std::vector<float4>& segs, int w, int hgt, doubl
 
 // LBD of `n` keylines on the uploaded image: blur 5x5 sigma 1 + Sobel, row sums, fold + binarise (enqueue only; the
 // descriptors land in h->desc_host once the stream has been waited for)
-static int lbd_enqueue(LineImpl* h, const olf_keyline* kls, int n, cudaStream_t s) {
-    if (n == 0) return OLF_OK;
-    const int w = h->img_w, hgt = h->img_h;
-    int rc;
-    if (n > h->lbd_cap) {
-        const int cap = std::max(2 * n, 1024);
-        if ((rc = h->lbd_lines.ensure(cap)) || (rc = h->rowsum.ensure((size_t)cap * 63)) || (rc = h->desc_host.ensure((size_t)cap * 32))) return rc;
-        h->lbd_cap = cap;
-    }
-    for (int i = 0; i < n; ++i) {
-        const olf_keyline& k = kls[i];
-        LbdLine L;
-        L.sx = k.sPointInOctaveX; L.sy = k.sPointInOctaveY; L.ex = k.ePointInOctaveX; L.ey = k.ePointInOctaveY;
-        L.dL0 = cosf(k.angle); L.dL1 = sinf(k.angle);       // cos( float ), sin( float ) = cosf, sinf in the reference's build (:1130-1131)
-        L.num_px = k.numOfPixels;
-        h->lbd_lines.p[i] = L;
-    }
-    const LevelTable T = single_level(w, hgt, h->ipitch);
-    BlurBatch bb; memset(&bb, 0, sizeof(bb)); bb.src[0] = h->img.p; bb.dst[0] = h->lbd_blur.p;
-    if (h->has_tma) k_blur_q8_tma<5, 1><<<T.tile_start[1], 256, 0, s>>>(bb, h->tmaps[1], T, 14, 62, 104, 0);       // 5x5 sigma 1 (:358)
-    else k_blur_q8<5><<<T.tile_start[1], 256, 0, s>>>(bb, T, 14, 62, 104, 0);
-    dim3 g((w + 31) / 32, (hgt + 7) / 8);
-    k_sobel3<<<g, 256, 0, s>>>(h->lbd_blur.p, w, hgt, h->ipitch, h->grad.p);
-    k_lbd_rows<<<(n * 63 + 255) / 256, 256, 0, s>>>(h->lbd_lines.d, n, h->grad.p, w, hgt, h->rowsum.p);
-    k_lbd_fold<<<(n + 63) / 64, 64, 0, s>>>(h->rowsum.p, n, h->desc_host.d);
-    count_launches(4);
+// LBD, image half (blur 5x5 + Sobel; binary_descriptor_custom.cpp:350-412): independent of the keylines, so a batch runs it with the LSD pre-phase,
+// off the critical path after the region growing; one launch per stage for all images
+static int lbd_prepare_batch(LineImpl* const* hs, int n, cudaStream_t s) {
+    LineImpl* h0 = hs[0];
+    const int w = h0->img_w, hgt = h0->img_h;
+    const LevelTable T = single_level(w, hgt, h0->ipitch);
+    BlurBatch bb; memset(&bb, 0, sizeof(bb));
+    bool tma = true;
+    for (int k = 0; k < n; ++k) { bb.src[k] = hs[k]->img.p; bb.dst[k] = hs[k]->lbd_blur.p; tma = tma && hs[k]->has_tma; }
+    if (tma) {
+        static thread_local TmaSet<LSD_PRE_MAX> M;
+        for (int k = 0; k < n; ++k) M.m[k] = hs[k]->tmaps[1].m[0];
+        k_blur_q8_tma<5, LSD_PRE_MAX><<<dim3(T.tile_start[1], n), 256, 0, s>>>(bb, M, T, 14, 62, 104, 0);       // 5x5 sigma 1 (:358)
+    } else k_blur_q8<5><<<dim3(T.tile_start[1], n), 256, 0, s>>>(bb, T, 14, 62, 104, 0);
+    PostBatch PB; post_fill(PB, hs, n);
+    dim3 g((w + 31) / 32, (hgt + 7) / 8, n);
+    k_sobel3<<<g, 256, 0, s>>>(PB, w, hgt, h0->ipitch);
+    count_launches(2);
     OLF_CUDA(cudaGetLastError());
     return OLF_OK;
+}
+// LBD, line half (computeLBD, binary_descriptor_custom.cpp:1026-1372): the keylines of every image of the batch in two launches
+static int lbd_describe_batch(LineImpl* const* hs, int n, const std::vector<olf_keyline>* kls, cudaStream_t s) {
+    int rc, max_n = 0;
+    for (int k = 0; k < n; ++k) {
+        LineImpl* h = hs[k];
+        const int nl = (int)kls[k].size();
+        max_n = std::max(max_n, nl);
+        if (nl > h->lbd_cap) {
+            const int cap = std::max(2 * nl, 1024);
+            if ((rc = h->lbd_lines.ensure(cap)) || (rc = h->rowsum.ensure((size_t)cap * 63)) || (rc = h->desc_host.ensure((size_t)cap * 32))) return rc;
+            h->lbd_cap = cap;
+        }
+        for (int i = 0; i < nl; ++i) {
+            const olf_keyline& kk = kls[k][i];
+            LbdLine L;
+            L.sx = kk.sPointInOctaveX; L.sy = kk.sPointInOctaveY; L.ex = kk.ePointInOctaveX; L.ey = kk.ePointInOctaveY;
+            L.dL0 = cosf(kk.angle); L.dL1 = sinf(kk.angle);       // cos( float ), sin( float ) = cosf, sinf in the reference's build (:1130-1131)
+            L.num_px = kk.numOfPixels;
+            h->lbd_lines.p[i] = L;
+        }
+    }
+    if (max_n == 0) return OLF_OK;
+    PostBatch PB; post_fill(PB, hs, n);                          // after the ensure() calls: the buffers may have moved
+    for (int k = 0; k < n; ++k) PB.nr[k] = (int)kls[k].size();
+    k_lbd_rows<<<dim3((max_n * 63 + 255) / 256, n), 256, 0, s>>>(PB, hs[0]->img_w, hs[0]->img_h);
+    k_lbd_fold<<<dim3((max_n + 63) / 64, n), 64, 0, s>>>(PB);
+    count_launches(2);
+    OLF_CUDA(cudaGetLastError());
+    return OLF_OK;
+}
+static int lbd_enqueue(LineImpl* h, const olf_keyline* kls, int n, cudaStream_t s) {
+    if (n == 0) return OLF_OK;
+    int rc;
+    if ((rc = lbd_prepare_batch(&h, 1, s))) return rc;
+    std::vector<olf_keyline> v(kls, kls + n);
+    return lbd_describe_batch(&h, 1, &v, s);
 }
 
 int line_lsd_detect(LineImpl* h, const uint8_t* img, int w, int hgt, int stride, bool on_device, float* segs, int cap, int* n) {
@@ -1612,6 +1674,7 @@ int line_extract_batch(LineImpl* const* hs, int nimg, const uint8_t* const* imgs
     int rc;
     for (int k = 0; k < nimg; ++k) if ((rc = line_upload(hs[k], imgs[k], w, hgt, stride, on_device, s))) return rc;
     std::vector<float4> sg[LSD_MAX_BATCH];
+    if ((rc = lbd_prepare_batch(hs, nimg, s))) return rc;           // ahead of the LSD chain: needs the uploaded images only
     if ((rc = lsd_run_batch(hs, nimg, s, sg))) return rc;
     const long long t_lsd = now_us();
     std::vector<olf_keyline> kl[LSD_MAX_BATCH];
@@ -1630,8 +1693,8 @@ int line_extract_batch(LineImpl* const* hs, int nimg, const uint8_t* const* imgs
         n[k] = (int)v.size();
         if (v.empty()) continue;
         memcpy(kls[k], v.data(), v.size() * sizeof(olf_keyline));
-        if ((rc = lbd_enqueue(h, v.data(), (int)v.size(), s))) return rc;
     }
+    if ((rc = lbd_describe_batch(hs, nimg, kl, s))) return rc;
     OLF_CUDA(hs[0]->sync.sync(s));
     hs[0]->last_stats[7] = (int)(now_us() - t_lsd);                      // keylines + LBD (us)
     for (int k = 0; k < nimg; ++k) if (n[k]) memcpy(desc[k], hs[k]->desc_host.p, (size_t)n[k] * 32);
