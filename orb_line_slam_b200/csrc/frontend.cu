@@ -179,6 +179,10 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
     if (!rc && rc_l) { rc = rc_l; set_last_error(err_l); }
     match_use_stream(h->P.has_lines ? line_stream(h->line[0]) : so);
     match_use_ctx(h->mctx);
+    // stereo association of the lines: the frames of the call are enqueued together and waited for once
+    const olf_keyline* b_kl[OLF_MAX_BATCH_FRAMES]; const uint8_t* b_dl[OLF_MAX_BATCH_FRAMES]; const olf_keyline* b_kr[OLF_MAX_BATCH_FRAMES]; const uint8_t* b_dr[OLF_MAX_BATCH_FRAMES];
+    int b_n1[OLF_MAX_BATCH_FRAMES], b_n2[OLF_MAX_BATCH_FRAMES], nb = 0;
+    int* b_m[OLF_MAX_BATCH_FRAMES]; float* b_d[OLF_MAX_BATCH_FRAMES]; double* b_le[OLF_MAX_BATCH_FRAMES];
     for (int f = 0; f < nframes; ++f) {
         uint8_t* base = (uint8_t*)results[f];
         olf_frame_header* hd = (olf_frame_header*)base;
@@ -188,15 +192,16 @@ int frontend_process_batch(FrontendImpl* h, const uint8_t* const* img_l, const u
             memcpy(base + o.u_right, h->sws[f].out.p, (size_t)n[kl] * 4);
             memcpy(base + o.depth, h->sws[f].out.p + h->sws[f].cap, (size_t)n[kl] * 4);
         }
-        if (!rc && n[kl] > 0 && h->P.has_lines)
-            rc = stereo_lines(kls[kl], ldesc[kl], m[kl], kls[kr], ldesc[kr], m[kr], w, hgt, &h->P.line_match,
-                              (int*)(base + o.lmatch), (float*)(base + o.ldisp), (double*)(base + o.lle), h->device);
-        else if (h->P.has_lines) {  // ComputeStereoMatches_Lines not reached: every line unmatched (mvDisparity_l = (-1,-1), mvle_l = 0)
+        if (!rc && n[kl] > 0 && h->P.has_lines) {
+            b_kl[nb] = kls[kl]; b_dl[nb] = ldesc[kl]; b_n1[nb] = m[kl]; b_kr[nb] = kls[kr]; b_dr[nb] = ldesc[kr]; b_n2[nb] = m[kr];
+            b_m[nb] = (int*)(base + o.lmatch); b_d[nb] = (float*)(base + o.ldisp); b_le[nb] = (double*)(base + o.lle); ++nb;
+        } else if (h->P.has_lines) {  // ComputeStereoMatches_Lines not reached: every line unmatched (mvDisparity_l = (-1,-1), mvle_l = 0)
             int* lm = (int*)(base + o.lmatch); float* ld = (float*)(base + o.ldisp); double* le = (double*)(base + o.lle);
             for (int i = 0; i < m[kl]; ++i) { lm[i] = -1; ld[2 * i] = ld[2 * i + 1] = -1.f; le[3 * i] = le[3 * i + 1] = le[3 * i + 2] = 0; }
         }
-        hd->status = rc;
     }
+    if (!rc && nb > 0) rc = stereo_lines_batch(nb, b_kl, b_dl, b_n1, b_kr, b_dr, b_n2, w, hgt, &h->P.line_match, b_m, b_d, b_le, h->device);
+    for (int f = 0; f < nframes; ++f) ((olf_frame_header*)results[f])->status = rc;
     match_use_stream(nullptr); match_use_ctx(nullptr);
     const long long t5 = now();
     h->timing[0] = (int)(t1 - t0); h->timing[1] = (int)(t2 - t1); h->timing[2] = (int)(t3 - t2); h->timing[3] = (int)(t4 - t3); h->timing[4] = (int)(t5 - t4); h->timing[5] = (int)(t5 - t0);

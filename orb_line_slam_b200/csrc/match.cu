@@ -622,44 +622,71 @@ __global__ void k_lines_geom(const olf_keyline* __restrict__ kl, const olf_keyli
     }
 }
 
-int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_keyline* kr, const uint8_t* dr, int n2, int img_w, int img_h,
-                 const olf_line_match_params* P, int* matches12, float* disp, double* le, int device) {
-    if (!P || n1 < 0 || n2 < 0 || img_w <= 0 || img_h <= 0 || (n1 && (!kl || !dl || !matches12 || !disp || !le)) || (n2 && (!kr || !dr))) {
-        set_last_error("olf_stereo_lines: bad arguments"); return OLF_ERR_ARG;
+// Frame::ComputeStereoMatches_Lines for `nf` independent stereo frames: the five kernels of every frame are enqueued back to back on the context's
+// stream and waited for ONCE (a rig call has four frames; a wait costs a host wake-up, and under load that is the expensive part of this phase)
+int stereo_lines_batch(int nf, const olf_keyline* const* kl, const uint8_t* const* dl, const int* n1s, const olf_keyline* const* kr, const uint8_t* const* dr, const int* n2s,
+                       int img_w, int img_h, const olf_line_match_params* P, int* const* matches12, float* const* disp, double* const* le, int device) {
+    if (!P || nf < 1 || nf > 16 || img_w <= 0 || img_h <= 0) { set_last_error("olf_stereo_lines: bad arguments"); return OLF_ERR_ARG; }
+    for (int f = 0; f < nf; ++f) {
+        const int n1 = n1s[f], n2 = n2s[f];
+        if (n1 < 0 || n2 < 0 || (n1 && (!kl[f] || !dl[f] || !matches12[f] || !disp[f] || !le[f])) || (n2 && (!kr[f] || !dr[f]))) { set_last_error("olf_stereo_lines: bad arguments"); return OLF_ERR_ARG; }
     }
     MatchCtx* c; int rc;
     if ((rc = get_ctx(device, &c))) return rc;
-    for (int i = 0; i < n1; ++i) { matches12[i] = -1; disp[2 * i] = disp[2 * i + 1] = -1.f; le[3 * i] = le[3 * i + 1] = le[3 * i + 2] = 0; }
-    if (n1 == 0 || n2 == 0) return OLF_OK;
     const double inv_w = OLF_GRID_COLS / (double)img_w, inv_h = OLF_GRID_ROWS / (double)img_h;
+    struct Off { size_t kl, dl, kr, dr, dir, cells, nc, cand, m12, m21, disp, le, p_in, p_m, p_disp, p_le; bool live; } off[16];
     Planner pl;
-    const size_t o_kl = pl.d((size_t)n1 * sizeof(olf_keyline)), o_dl = pl.d((size_t)n1 * 32), o_kr = pl.d((size_t)n2 * sizeof(olf_keyline)), o_dr = pl.d((size_t)n2 * 32);
-    const size_t o_dir = pl.d((size_t)n2 * sizeof(double2)), o_cells = pl.d((size_t)n2 * LCELLS * sizeof(short2)), o_nc = pl.d((size_t)n2 * 4);
-    const size_t o_cand = pl.d((size_t)n1 * n2 * 4), o_m12 = pl.d((size_t)n1 * 4), o_m21 = pl.d((size_t)n2 * 4), o_disp = pl.d((size_t)n1 * 8), o_le = pl.d((size_t)n1 * 24);
-    const size_t p_in = pl.p((size_t)(n1 + n2) * (sizeof(olf_keyline) + 32)), p_m = pl.p((size_t)n1 * 4), p_disp = pl.p((size_t)n1 * 8), p_le = pl.p((size_t)n1 * 24);
+    bool any = false;
+    for (int f = 0; f < nf; ++f) {
+        const int n1 = n1s[f], n2 = n2s[f];
+        for (int i = 0; i < n1; ++i) { matches12[f][i] = -1; disp[f][2 * i] = disp[f][2 * i + 1] = -1.f; le[f][3 * i] = le[f][3 * i + 1] = le[f][3 * i + 2] = 0; }
+        Off& o = off[f];
+        o.live = n1 > 0 && n2 > 0;
+        if (!o.live) continue;
+        any = true;
+        o.kl = pl.d((size_t)n1 * sizeof(olf_keyline)); o.dl = pl.d((size_t)n1 * 32); o.kr = pl.d((size_t)n2 * sizeof(olf_keyline)); o.dr = pl.d((size_t)n2 * 32);
+        o.dir = pl.d((size_t)n2 * sizeof(double2)); o.cells = pl.d((size_t)n2 * LCELLS * sizeof(short2)); o.nc = pl.d((size_t)n2 * 4);
+        o.cand = pl.d((size_t)n1 * n2 * 4); o.m12 = pl.d((size_t)n1 * 4); o.m21 = pl.d((size_t)n2 * 4); o.disp = pl.d((size_t)n1 * 8); o.le = pl.d((size_t)n1 * 24);
+        o.p_in = pl.p((size_t)(n1 + n2) * (sizeof(olf_keyline) + 32)); o.p_m = pl.p((size_t)n1 * 4); o.p_disp = pl.p((size_t)n1 * 8); o.p_le = pl.p((size_t)n1 * 24);
+    }
+    if (!any) return OLF_OK;
     if ((rc = arena_ensure(c, pl))) return rc;
     cudaStream_t s = c->cur;
-    uint8_t* h_kl = hptr<uint8_t>(c, p_in); uint8_t* h_dl = h_kl + (size_t)n1 * sizeof(olf_keyline); uint8_t* h_kr = h_dl + (size_t)n1 * 32; uint8_t* h_dr = h_kr + (size_t)n2 * sizeof(olf_keyline);
-    memcpy(h_kl, kl, (size_t)n1 * sizeof(olf_keyline)); memcpy(h_dl, dl, (size_t)n1 * 32); memcpy(h_kr, kr, (size_t)n2 * sizeof(olf_keyline)); memcpy(h_dr, dr, (size_t)n2 * 32);
-    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_kl), h_kl, (size_t)n1 * sizeof(olf_keyline), cudaMemcpyHostToDevice, s));
-    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_dl), h_dl, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
-    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_kr), h_kr, (size_t)n2 * sizeof(olf_keyline), cudaMemcpyHostToDevice, s));
-    OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o_dr), h_dr, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
-    k_lines_raster<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<olf_keyline>(c, o_kr), n2, inv_w, inv_h, dptr<double2>(c, o_dir), dptr<short2>(c, o_cells), dptr<int>(c, o_nc));
-    k_lines_cand<<<dim3((n2 + 255) / 256, n1), 256, 0, s>>>(dptr<olf_keyline>(c, o_kl), dptr<uint32_t>(c, o_dl), n1, dptr<uint32_t>(c, o_dr), n2, inv_w, inv_h,
-                                                            dptr<double2>(c, o_dir), dptr<short2>(c, o_cells), dptr<int>(c, o_nc), P->matching_s_ws, P->line_sim_th, dptr<int>(c, o_cand));
-    count_launches(P->best_lr_matches ? 5 : 4);
-    if (P->best_lr_matches) k_lines_pass<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_cand), n1, n2, dptr<int>(c, o_m21));
-    k_lines_best<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o_cand), n1, n2, P->min_ratio_12_l, dptr<int>(c, o_m12));
-    k_lines_geom<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<olf_keyline>(c, o_kl), dptr<olf_keyline>(c, o_kr), n1, dptr<int>(c, o_m12), dptr<int>(c, o_m21), P->best_lr_matches, *P,
-                                                  dptr<float>(c, o_disp), dptr<double>(c, o_le));
-    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_m), dptr<int>(c, o_m12), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-    OLF_CUDA(cudaMemcpyAsync(hptr<float>(c, p_disp), dptr<float>(c, o_disp), (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
-    OLF_CUDA(cudaMemcpyAsync(hptr<double>(c, p_le), dptr<double>(c, o_le), (size_t)n1 * 24, cudaMemcpyDeviceToHost, s));
+    for (int f = 0; f < nf; ++f) {
+        const Off& o = off[f];
+        if (!o.live) continue;
+        const int n1 = n1s[f], n2 = n2s[f];
+        uint8_t* h_kl = hptr<uint8_t>(c, o.p_in); uint8_t* h_dl = h_kl + (size_t)n1 * sizeof(olf_keyline); uint8_t* h_kr = h_dl + (size_t)n1 * 32; uint8_t* h_dr = h_kr + (size_t)n2 * sizeof(olf_keyline);
+        memcpy(h_kl, kl[f], (size_t)n1 * sizeof(olf_keyline)); memcpy(h_dl, dl[f], (size_t)n1 * 32); memcpy(h_kr, kr[f], (size_t)n2 * sizeof(olf_keyline)); memcpy(h_dr, dr[f], (size_t)n2 * 32);
+        OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o.kl), h_kl, (size_t)n1 * sizeof(olf_keyline), cudaMemcpyHostToDevice, s));
+        OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o.dl), h_dl, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+        OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o.kr), h_kr, (size_t)n2 * sizeof(olf_keyline), cudaMemcpyHostToDevice, s));
+        OLF_CUDA(cudaMemcpyAsync(dptr<uint8_t>(c, o.dr), h_dr, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+        k_lines_raster<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<olf_keyline>(c, o.kr), n2, inv_w, inv_h, dptr<double2>(c, o.dir), dptr<short2>(c, o.cells), dptr<int>(c, o.nc));
+        k_lines_cand<<<dim3((n2 + 255) / 256, n1), 256, 0, s>>>(dptr<olf_keyline>(c, o.kl), dptr<uint32_t>(c, o.dl), n1, dptr<uint32_t>(c, o.dr), n2, inv_w, inv_h,
+                                                                dptr<double2>(c, o.dir), dptr<short2>(c, o.cells), dptr<int>(c, o.nc), P->matching_s_ws, P->line_sim_th, dptr<int>(c, o.cand));
+        count_launches(P->best_lr_matches ? 5 : 4);
+        if (P->best_lr_matches) k_lines_pass<<<(n2 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o.cand), n1, n2, dptr<int>(c, o.m21));
+        k_lines_best<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<int>(c, o.cand), n1, n2, P->min_ratio_12_l, dptr<int>(c, o.m12));
+        k_lines_geom<<<(n1 + 127) / 128, 128, 0, s>>>(dptr<olf_keyline>(c, o.kl), dptr<olf_keyline>(c, o.kr), n1, dptr<int>(c, o.m12), dptr<int>(c, o.m21), P->best_lr_matches, *P,
+                                                      dptr<float>(c, o.disp), dptr<double>(c, o.le));
+        OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, o.p_m), dptr<int>(c, o.m12), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+        OLF_CUDA(cudaMemcpyAsync(hptr<float>(c, o.p_disp), dptr<float>(c, o.disp), (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
+        OLF_CUDA(cudaMemcpyAsync(hptr<double>(c, o.p_le), dptr<double>(c, o.le), (size_t)n1 * 24, cudaMemcpyDeviceToHost, s));
+    }
     OLF_CUDA(cudaGetLastError());
     OLF_CUDA(stream_sync(s));
-    memcpy(matches12, hptr<int>(c, p_m), (size_t)n1 * 4); memcpy(disp, hptr<float>(c, p_disp), (size_t)n1 * 8); memcpy(le, hptr<double>(c, p_le), (size_t)n1 * 24);
+    for (int f = 0; f < nf; ++f) {
+        const Off& o = off[f];
+        if (!o.live) continue;
+        const int n1 = n1s[f];
+        memcpy(matches12[f], hptr<int>(c, o.p_m), (size_t)n1 * 4); memcpy(disp[f], hptr<float>(c, o.p_disp), (size_t)n1 * 8); memcpy(le[f], hptr<double>(c, o.p_le), (size_t)n1 * 24);
+    }
     return OLF_OK;
+}
+int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_keyline* kr, const uint8_t* dr, int n2, int img_w, int img_h,
+                 const olf_line_match_params* P, int* matches12, float* disp, double* le, int device) {
+    return stereo_lines_batch(1, &kl, &dl, &n1, &kr, &dr, &n2, img_w, img_h, P, &matches12, &disp, &le, device);
 }
 
 // ---- matchGrid(lines) as a stand-alone entry (src/LineMatcher.cpp:220-299) for callers that build the GridStructure

@@ -24,6 +24,8 @@ struct StereoWs { DevBuf<float> u, d; DevBuf<int> sad; PinBuf<float> out; int ca
 int stereo_ws_ensure(StereoWs* ws, int cap);
 void stereo_ws_release(StereoWs* ws);
 int stereo_points_enqueue(StereoWs* ws, OrbImpl* left, OrbImpl* right, float bf, float fx, int cap, cudaStream_t s);
+int stereo_lines_batch(int nf, const olf_keyline* const* kl, const uint8_t* const* dl, const int* n1s, const olf_keyline* const* kr, const uint8_t* const* dr, const int* n2s,
+                       int img_w, int img_h, const olf_line_match_params* P, int* const* matches12, float* const* disp, double* const* le, int device);
 int stereo_lines(const olf_keyline* kl, const uint8_t* dl, int n1, const olf_keyline* kr, const uint8_t* dr, int n2, int img_w, int img_h,
                  const olf_line_match_params* P, int* matches12, float* disp, double* le, int device);
 int match_grid_lines(const int* lines1, const uint8_t* desc1, int n1, const olf_grid_csr* grid, const uint8_t* desc2, int n2, const double* dir2,
