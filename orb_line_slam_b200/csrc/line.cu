@@ -1108,7 +1108,6 @@ struct LineImpl {
     DevBuf<unsigned char> sstate; DevBuf<unsigned> tbox;
     TmaSet<1> tmaps[2]; bool has_tma = false;      // [0]: input image, 7x7 box (LSD pre-blur); [1]: input image, 5x5 box (LBD blur)
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr; unsigned long long graph_key = 0; int use_graph = 1;
-    int pass_priority = 1;              // OLF_LSD_PASS_PRIORITY=0: the pass kernels at the default launch priority
     int grow_budget = 1 << 30;          // OLF_LSD_GROW_BUDGET: queue entries per thread and grow launch (default: no limit)
     int phase_batch = 52;
     bool trace = false;
@@ -1116,7 +1115,6 @@ struct LineImpl {
     DevBuf<int> dbg;
     unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
     int scan_blocks = 0, verify_blocks = 0, scan_blocks_wide = 0, verify_blocks_wide = 0, grow_blocks_wide = 0, grow_blocks_narrow = 0;
-    PinBuf<PhaseState> phase_init;
     PinBuf<RectRec> rect_host; PinBuf<double2> dir_host; PinBuf<float4> seg_host; PinBuf<int> status_host; PinBuf<unsigned> nreg_host;
     // LBD
     DevBuf<short2_t> grad;
@@ -1210,7 +1208,7 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     if (const char* e = getenv("OLF_LSD_FIRST_WAVE")) h->first_wave = h->first_wave_latency = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_WAVE_GROWTH")) h->wave_growth = std::max(2, atoi(e));
     h->trace = getenv("OLF_LSD_TRACE") != nullptr;                // per-round trace of the grow kernel (tools/lsd_trace.py)
-    ok = ok && h->phase.ensure(1) == OLF_OK && h->phase_init.ensure(1) == OLF_OK;
+    ok = ok && h->phase.ensure(1) == OLF_OK;
     if (const char* e = getenv("OLF_LSD_PHASE_BATCH")) h->phase_batch = std::max(4, atoi(e));
     if (!ok) { set_last_error(std::string("olf_line_create: ") + cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
     // grids of the three region-growing passes (one thread per seed; see k_lsd_scan / k_lsd_verify / k_lsd_grow)
@@ -1225,7 +1223,6 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     if (const char* e = getenv("OLF_LSD_VERIFY_BLOCKS")) h->verify_blocks = h->verify_blocks_wide = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks_wide = h->grow_blocks_narrow = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BUDGET")) h->grow_budget = std::max(1, atoi(e));
-    if (const char* e = getenv("OLF_LSD_PASS_PRIORITY")) h->pass_priority = atoi(e);
     if (const char* e = getenv("OLF_LSD_GRAPH")) h->use_graph = atoi(e);
     ok = h->cont.ensure((size_t)2 * std::max(h->grow_blocks_wide, h->grow_blocks_narrow) * GROW_THREADS) == OLF_OK;
     if (!ok) { delete h; return nullptr; }
@@ -1246,7 +1243,7 @@ void line_destroy(LineImpl* h) {
     h->wl0.release(); h->wl1.release(); h->wl2.release(); h->hist.release(); h->bin_start.release(); h->cursor.release(); h->pool.release(); h->ctrs.release();
     h->final_pool.release(); h->conv.release(); h->dirty.release(); h->srec0.release(); h->regang.release(); h->plan.release(); h->regs.release();
     h->tab_seed.release(); h->tab_acc.release(); h->cs.release(); h->phase.release(); h->px.release(); h->dbg.release(); h->cont.release(); h->sstate.release(); h->tbox.release();
-    h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release(); h->phase_init.release();
+    h->rect_host.release(); h->dir_host.release(); h->seg_host.release(); h->status_host.release(); h->nreg_host.release();
     h->grad.release(); h->lbd_lines.release(); h->rowsum.release(); h->desc_host.release();
     delete h;
 }
@@ -1431,24 +1428,11 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     B.conv = h0->conv.p; B.n = n;
     OLF_CUDA(cudaMemsetAsync(h0->conv.p, 0, (LSD_MAX_WAVES + 1) * sizeof(unsigned), s));
     OLF_CUDA(cudaEventRecord(h0->ev_grow0, s));
-    // The pass kernels are tiny in most rounds and sit on the chain's critical path (~90 dependent launches per chain), while the streaming kernels
-    // of the other rigs (FAST score, blurs, gradients: tens of thousands of CTAs per launch) keep the CTA dispatcher busy for hundreds of
-    // microseconds at a time: measured under 19 other rigs, a pass kernel with a few microseconds of work took 100-480 us from launch to end.
-    // So the passes carry the highest launch priority (cudaLaunchAttributePriority): their CTAs are dispatched ahead of pending lower-priority CTAs.
-    int prio_least = 0, prio_greatest = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    const int pass_prio = h0->pass_priority ? prio_greatest : 0;
-    auto launch_pass = [&](void (*kern)(GrowBatch), dim3 grid, dim3 block) {
-        cudaLaunchConfig_t cfg = {}; cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
-        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributePriority; at[0].val.priority = pass_prio;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, kern, B);
-    };
     auto enqueue_phases = [&](int count) {
         for (int k = 0; k < count; ++k) {
-            launch_pass(k_lsd_scan, dim3(n <= 2 ? h0->scan_blocks_wide : h0->scan_blocks, n), dim3(256));
-            launch_pass(k_lsd_verify, dim3(n <= 2 ? h0->verify_blocks_wide : h0->verify_blocks, n), dim3(128));
-            launch_pass(k_lsd_grow, dim3(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n), dim3(GROW_THREADS));
+            k_lsd_scan<<<dim3(n <= 2 ? h0->scan_blocks_wide : h0->scan_blocks, n), 256, 0, s>>>(B);
+            k_lsd_verify<<<dim3(n <= 2 ? h0->verify_blocks_wide : h0->verify_blocks, n), 128, 0, s>>>(B);
+            k_lsd_grow<<<dim3(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n), GROW_THREADS, 0, s>>>(B);
         }
         count_launches(3 * count);
     };
@@ -1462,7 +1446,6 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     if (h0->use_graph) {
         unsigned long long key = 1469598103934665603ull;
         { const unsigned char* b = (const unsigned char*)&B; for (size_t i = 0; i < offsetof(GrowBatch, cond); ++i) { key ^= b[i]; key *= 1099511628211ull; } }
-        key ^= (unsigned long long)(unsigned)pass_prio; key *= 1099511628211ull;
         if (!h0->graph_exec || h0->graph_key != key) {
             if (h0->graph_exec) { cudaGraphExecDestroy(h0->graph_exec); h0->graph_exec = nullptr; }
             if (h0->graph) { cudaGraphDestroy(h0->graph); h0->graph = nullptr; }
@@ -1485,10 +1468,6 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
                 ok = ok && cudaGraphAddKernelNode(&n2, body, &n1, 1, &kp) == cudaSuccess;
                 kp.func = (void*)k_lsd_grow; kp.gridDim = g_grow; kp.blockDim = dim3(GROW_THREADS);
                 ok = ok && cudaGraphAddKernelNode(&n3, body, &n2, 1, &kp) == cudaSuccess;
-                if (ok && pass_prio != 0) {
-                    cudaKernelNodeAttrValue pv; memset(&pv, 0, sizeof(pv)); pv.priority = pass_prio;
-                    for (cudaGraphNode_t nd : {n1, n2, n3}) ok = ok && cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributePriority, &pv) == cudaSuccess;
-                }
                 ok = ok && cudaGraphInstantiate(&h0->graph_exec, g, 0) == cudaSuccess;
             }
             if (!ok) { cudaGetLastError(); if (g) cudaGraphDestroy(g); h0->graph_exec = nullptr; h0->use_graph = 0; }      // driver without conditional nodes: plain launches
