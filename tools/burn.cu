@@ -42,6 +42,25 @@ __global__ void __launch_bounds__(64) k_burn_cta(unsigned* out) { if (threadIdx.
 #include <atomic>
 #include <chrono>
 static std::thread g_thr; static std::atomic<unsigned long long> g_launches{0};
+// mode 4: as mode 2, but with the operations the region-growing passes use on their claim words: strong (relaxed, gpu-scope) 64-bit loads and a
+// fire-and-forget 64-bit atomic min every fourth access, at random 32-byte sectors
+__global__ void __launch_bounds__(1024) k_burn_strong(unsigned long long dur_ns, unsigned long long* __restrict__ buf, unsigned mask, unsigned* out, unsigned long long* iters_out) {
+    unsigned long long it = 0, t_end_ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end_ns)); t_end_ns += dur_ns;
+    unsigned idx = (threadIdx.x * 2654435761u + blockIdx.x * 40503u) & mask;
+    for (;;) {
+#pragma unroll 1
+        for (int k = 0; k < 64; ++k) {
+            unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(buf + (size_t)idx * 4) : "memory");
+            if ((k & 3) == 3) atomicMin(buf + (size_t)idx * 4, 0xFFFFFFFFFFFFFFFFull - k);
+            idx = (idx * 1664525u + 1013904223u + (unsigned)v) & mask;
+        }
+        ++it;
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (t > t_end_ns) break;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = idx;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *iters_out = it;
+}
 static unsigned* g_buf = nullptr;
 static cudaStream_t g_s = nullptr; static unsigned* g_out = nullptr; static unsigned long long* g_it = nullptr;
 extern "C" int burn_start(int device, int chains, double seconds) {
@@ -63,6 +82,13 @@ extern "C" int burn_start(int device, int chains, double seconds) {
             g_launches = n;
         });
         return 0;
+    }
+    if (chains >= 200 && chains < 1000) {          // strong loads + atomics: chains - 200 = warps per SM
+        const int warps = chains - 200;
+        const size_t sectors = (size_t)1 << 26;
+        if (!g_buf) { cudaMalloc(&g_buf, sectors * 32); cudaMemset(g_buf, 0xFF, sectors * 32); cudaFree(g_out); cudaMalloc(&g_out, (size_t)sms * 1024 * 4); }
+        k_burn_strong<<<sms, 32 * warps, 0, g_s>>>((unsigned long long)(seconds * 1e9), (unsigned long long*)g_buf, (unsigned)(sectors - 1), g_out, g_it);
+        return cudaGetLastError() == cudaSuccess ? 0 : -2;
     }
     if (chains >= 100) {          // memory mode: chains - 100 = warps per SM
         const int warps = chains - 100;
