@@ -73,3 +73,30 @@ def test_product_does_not_import_oracle():
             t = f.read_text()
             assert "oracle/" not in t.replace("oracle/ ", "") or f.name in ("lsd_core.h",), f
             assert "import orc" not in t and "liborc" not in t, f
+
+
+def test_key_frame_matchers_without_a_device_or_with_bad_arguments(lib):
+    """SURVEY 8f rank 2 entry points: bad arguments are rejected before anything touches CUDA; with good arguments and no CUDA device they
+    report OLF_ERR_NO_DEVICE (never a CPU fallback).  On a GPU box the second half is covered by tests/test_kf_matchers.py."""
+    import kf_search as K
+    from orb_line_slam_b200.abi import WindowSearchArgs, TriangulationArgs, OLF_ERR_ARG, OLF_ERR_NO_DEVICE
+    bi = np.zeros(4, np.int32); bd = np.zeros(4, np.int32); n = C.c_int(0)
+    assert lib.olf_window_search(None, ptr(bi), ptr(bd), 0) == OLF_ERR_ARG
+    a = WindowSearchArgs(); a.n = 0; a.n_queries = -1
+    assert lib.olf_window_search(C.byref(a), ptr(bi), ptr(bd), 0) == OLF_ERR_ARG
+    a.n_queries = 4; a.max_dist = 50                                       # query arrays missing
+    assert lib.olf_window_search(C.byref(a), ptr(bi), ptr(bd), 0) == OLF_ERR_ARG
+    assert lib.olf_search_for_triangulation(None, ptr(bi), C.byref(n), 0) == OLF_ERR_ARG
+    t = TriangulationArgs(); t.nlevels = 0
+    assert lib.olf_search_for_triangulation(C.byref(t), ptr(bi), C.byref(n), 0) == OLF_ERR_ARG
+    assert lib.olf_search_by_bow_kf(None, None, ptr(bi), C.byref(n), 0) == OLF_ERR_ARG
+    assert lib.olf_search_for_initialization(None, None, 0, None, None, 0, None, None, 10, C.c_float(0.9), 1, ptr(bi), C.byref(n), 0) == OLF_ERR_ARG
+    if olf.device_count() == 0:
+        kf = K.make_keyframe(1, n=20)
+        q = K.random_queries(kf, 4, 2)
+        g = olf.api(0)
+        with pytest.raises(RuntimeError, match="code -4"):
+            g.window_search(kf["kps"], kf["desc"], kf["cam"], q["u"], q["v"], q["radius"], q["min_level"], q["max_level"], q["qdesc"], 50)
+        prev = np.stack([kf["kps"]["x"], kf["kps"]["y"]], 1)
+        with pytest.raises(RuntimeError, match="code -4"):
+            g.search_for_initialization(kf["kps"], kf["desc"], kf["kps"], kf["desc"], kf["cam"], prev)
