@@ -11,8 +11,25 @@
 
 using namespace olf::lsd;
 
-extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_params* P, unsigned rng_seed, int first_wave, int defer, int exact_align,
-                               float* segs, int cap, int* nseg, long long* stats /*[7]: waves, rounds, grown_px, final_px, regions, max_rounds_in_wave, carried*/) {
+// event_scan (the bookkeeping of k_lsd_scan / k_lsd_verify in line.cu): per seed a state byte (alive at the last evaluation) and a packed tile box of its
+// region; from the second round of a wave a candidate is re-evaluated only where the previous round dirtied the tile of its pixel, the verify pass looks at
+// the 4-byte tile box before the seed record and writes a death it discovers back into the state byte.  stats[9] = candidates NOT re-evaluated.
+static unsigned emul_tbox_pack(const SeedRec3& r) {
+    const int tx0 = r.x0 >> kTileShift, ty0 = r.y0 >> kTileShift, tx1 = r.x1 >> kTileShift, ty1 = r.y1 >> kTileShift;
+    if ((tx1 | ty1) > 254) return 0xFFFFFFFEu;
+    return (unsigned)tx0 | ((unsigned)ty0 << 8) | ((unsigned)tx1 << 16) | ((unsigned)ty1 << 24);
+}
+static bool emul_tbox_dirty(const Ctx3& C, unsigned round, unsigned tb) {
+    SeedRec3 r; r.x0 = (unsigned short)((tb & 255) << kTileShift); r.y0 = (unsigned short)(((tb >> 8) & 255) << kTileShift);
+    r.x1 = (unsigned short)(((tb >> 16) & 255) << kTileShift); r.y1 = (unsigned short)((tb >> 24) << kTileShift);
+    return bbox_dirty(C, round, r);
+}
+static bool emul_pixel_tile_dirty(const Ctx3& C, unsigned round, int pix) {
+    const int y = pix / C.W, x = pix - y * C.W, tx = x >> kTileShift, ty = y >> kTileShift;
+    return (C.dirty[(round - 1) & 1][ty * C.tile_wpr + (tx >> 5)] >> (tx & 31)) & 1u;
+}
+extern "C" int emul_lsd_detect2(const uint8_t* img, int w, int h, const olf_line_params* P, unsigned rng_seed, int first_wave, int defer, int exact_align, int event_scan,
+                                float* segs, int cap, int* nseg, long long* stats /*[10]: waves, rounds, grown_px, final_px, regions, max_rounds_in_wave, carried, walked, live, skipped*/) {
     orc::Image8 im(w, h);
     memcpy(im.d.data(), img, (size_t)w * h);
     const double scale = P->lsd_scale;
@@ -107,6 +124,8 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
     unsigned round = 1;
     std::vector<int> order, wl0, wl2;
     std::vector<std::pair<int, bool>> wl1;
+    std::vector<unsigned char> sstate(n, 0); std::vector<unsigned> tbox(n, kNull);
+    long long skipped = 0;
     for (size_t wv = 0; wv + 1 < wave_start.size(); ++wv) {
         const int lo = wave_start[wv], hi = wave_start[wv + 1];
         if (lo == hi) continue;
@@ -131,16 +150,28 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
                 if (first_round) {
                     if (s3_final(C, seeds[i])) continue;
                     wl0.push_back(i);
+                    tbox[i] = kNull;
                 }
-                bool alive = s3_alive(C, seeds[i], prio[i]);
+                bool alive;
+                if (!event_scan) {
+                    alive = s3_alive(C, seeds[i], prio[i]);
+                    if (!alive && srec[i].cnt > 0) wl1.push_back({i, false});
+                } else if (first_round || emul_pixel_tile_dirty(C, round, seeds[i])) {
+                    alive = s3_alive(C, seeds[i], prio[i]);
+                    sstate[i] = alive ? 1 : 0;
+                    if (!alive && !first_round && srec[i].cnt > 0) wl1.push_back({i, false});       // died owning a region
+                } else { alive = sstate[i] != 0; ++skipped; }
                 if (alive && first_round && defer && s3_deferred(C, seeds[i], prio[i])) { changed = true; continue; }    // sits this round out
-                if (alive || srec[i].cnt > 0) wl1.push_back({i, alive});
+                if (alive) wl1.push_back({i, true});
             }
             // pass 2: verify
             std::shuffle(wl1.begin(), wl1.end(), rng);
             for (auto& e : wl1) {
                 if (e.second && srec[e.first].cnt > 0) { live_px += srec[e.first].cnt; if (bbox_dirty(C, round, srec[e.first])) walked += srec[e.first].cnt; }
+                if (event_scan && e.second && tbox[e.first] < 0xFFFFFFFEu && !emul_tbox_dirty(C, round, tbox[e.first])) { ++carried; continue; }     // 4 bytes instead of the record
                 const Verify3 v = s3_verify(C, round, e.first, e.second, &changed);
+                if (v != kV3Carried) tbox[e.first] = kNull;
+                if (e.second && v == kV3Dead) sstate[e.first] = 0;
                 if (v == kV3Grow) wl2.push_back(e.first);
                 else if (v == kV3Carried) ++carried;
             }
@@ -160,6 +191,7 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
                         if (act[k].overflow) return -3;
                         grown += act[k].count;
                         s3_end(C, act[k]);
+                        tbox[act[k].i] = emul_tbox_pack(srec[act[k].i]);
                         act[k] = act.back(); act.pop_back();
                     }
                 }
@@ -207,6 +239,10 @@ extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_
     *nseg = (int)out.size();
     if ((int)out.size() > cap) return -3;
     for (size_t i = 0; i < out.size(); ++i) memcpy(segs + 4 * i, out[i].v, 16);
-    stats[0] = waves; stats[1] = rounds; stats[2] = grown; stats[3] = final_px; stats[4] = regions; stats[5] = max_rw; stats[6] = carried; stats[7] = walked; stats[8] = live_px;
+    stats[0] = waves; stats[1] = rounds; stats[2] = grown; stats[3] = final_px; stats[4] = regions; stats[5] = max_rw; stats[6] = carried; stats[7] = walked; stats[8] = live_px; stats[9] = skipped;
     return 0;
+}
+extern "C" int emul_lsd_detect(const uint8_t* img, int w, int h, const olf_line_params* P, unsigned rng_seed, int first_wave, int defer, int exact_align,
+                               float* segs, int cap, int* nseg, long long* stats) {
+    return emul_lsd_detect2(img, w, h, P, rng_seed, first_wave, defer, exact_align, 0, segs, cap, nseg, stats);
 }

@@ -33,15 +33,18 @@ def test_fixed_point_equals_sequential(emul, w, h, seed, first_wave, nbins):
     ref = o.lsd_detect(hd, img)
     o.line_destroy(hd)
     carried = 0
-    for sched, defer, exact in ((1, 1, 0), (2, 1, 0), (3, 0, 0), (4, 1, 1)):     # different random schedules / options
+    skipped = 0
+    # different random schedules / options; event = the event-driven scan + tile-box verify bookkeeping of the kernels (state byte per seed, deaths written back)
+    for sched, defer, exact, event in ((1, 1, 0, 0), (2, 1, 0, 1), (3, 0, 0, 1), (4, 1, 1, 1), (5, 0, 1, 0), (6, 1, 0, 1)):
         segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
-        rc = emul.emul_lsd_detect(ptr(img), w, h, C.byref(P), C.c_uint(seed * 10 + sched), first_wave, defer, exact, ptr(segs), 65536, C.byref(n), st)
+        rc = emul.emul_lsd_detect2(ptr(img), w, h, C.byref(P), C.c_uint(seed * 10 + sched), first_wave, defer, exact, event, ptr(segs), 65536, C.byref(n), st)
         assert rc == 0 and n.value == len(ref)
         assert np.array_equal(segs[:n.value], ref)
         assert st[1] >= st[0]                              # at least one round per wave
-        carried += st[6]
+        carried += st[6]; skipped += st[9]
         assert st[7] < st[8]                               # regions away from any event were carried without being walked
     assert carried > 0                                     # the verify-instead-of-regrow path was exercised
+    assert skipped > 0                                     # candidates outside the dirty tiles were not re-evaluated
 
 
 def test_fixed_point_equals_sequential_bench_image(emul):
@@ -56,7 +59,8 @@ def test_fixed_point_equals_sequential_bench_image(emul):
     o.line_destroy(hd)
     for first_wave in (4096, 262144):
         segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
-        rc = emul.emul_lsd_detect(ptr(img), 1280, 720, C.byref(P), C.c_uint(first_wave), first_wave, 1, 0, ptr(segs), 65536, C.byref(n), st)
+        rc = emul.emul_lsd_detect2(ptr(img), 1280, 720, C.byref(P), C.c_uint(first_wave), first_wave, 1, 0, 1, ptr(segs), 65536, C.byref(n), st)
         assert rc == 0 and n.value == len(ref) == 2114
         assert np.array_equal(segs[:n.value], ref)
         assert st[7] < st[8] // 2                              # most live pixel-rounds are never walked
+        assert st[9] > 0                                       # event-driven scan: candidates skipped

@@ -25,7 +25,7 @@ for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 150):
     hd = o.line_create(P); ref = o.lsd_detect(hd, img); o.line_destroy(hd)
     for sched in range(3):
         segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
-        rc = em.emul_lsd_detect(ptr(img), w, h, C.byref(P), C.c_uint(it * 17 + sched), fw, int(rng.randint(2)), int(rng.randint(2)), ptr(segs), 65536, C.byref(n), st)
+        rc = em.emul_lsd_detect2(ptr(img), w, h, C.byref(P), C.c_uint(it * 17 + sched), fw, int(rng.randint(2)), int(rng.randint(2)), int(sched != 0), ptr(segs), 65536, C.byref(n), st)
         runs += 1
         if not (rc == 0 and n.value == len(ref) and np.array_equal(segs[:n.value], ref)):
             bad += 1
