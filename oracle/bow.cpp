@@ -4,8 +4,11 @@
 //   DBoW2::FeatureVector::addFeature        Thirdparty/DBoW2/DBoW2/FeatureVector.cpp
 //   FORB::distance                          Thirdparty/DBoW2/DBoW2/FORB.cpp:81-101
 //   ORBmatcher::SearchByBoW(KeyFrame*,Frame&,...)  src/ORBmatcher.cc:161-290, ComputeThreeMaxima :1749-1790
-// Parity: the reference ships no tests or vectors for this row ("parity unpinned by the reference"); the restatement
-// follows the cited lines, std::map semantics included (words / nodes ascending, double sums in feature order).
+// Parity: PINNED.  The reference ships no tests or vectors for this row, so oracle/_ref compiles DBoW2 itself (TemplatedVocabulary<FORB>,
+// BowVector, FeatureVector, FORB, ScoringObject -- vendored under Thirdparty/DBoW2) and both SearchByBoW overloads; a synthetic tree is
+// written in the ORBvoc.txt format, loaded with the reference's loadFromTextFile and transformed there: BowVector doubles, FeatureVector
+// and match arrays must equal this file's bit for bit (tests/test_oracle_vs_ref.py).  std::map semantics included (words / nodes
+// ascending, double sums in feature order).
 #include "oracle.h"
 #include "cvprim.hpp"
 #include <map>

@@ -1,9 +1,10 @@
 /* ORACLE -- TEST INFRASTRUCTURE ONLY.  Not part of the product path.
  * C interface of the CPU restatement of the reference hot path (see oracle/README.md).
  * Mirrors include/olf_abi.h with the prefix orc_ so the parity tests can call both sides alike.
- * Parity pinning: OpenCV halves pinned against cv2 4.13.0 by tests/test_oracle_vs_cv2.py and tests/golden/;
- * vendored halves (rBRIEF, quadtree, LBD, matchers) restate the cited reference lines -- the reference
- * ships no tests or golden vectors for them, so those parts are "parity unpinned".
+ * Parity pinning: PINNED.  OpenCV halves against cv2 4.13.0 (tests/test_oracle_vs_cv2.py, tests/golden/); the vendored halves
+ * (ORBextractor incl. quadtree and rBRIEF, LSD KeyLines, LBD, every matcher, stereo association) against the reference's own
+ * sources compiled in oracle/_ref (make -C oracle ref; tests/test_oracle_vs_ref.py) -- the reference ships no tests or golden
+ * vectors of its own.
  */
 #ifndef ORC_ORACLE_H
 #define ORC_ORACLE_H

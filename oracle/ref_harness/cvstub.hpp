@@ -19,12 +19,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <limits>
 #include <list>
 #include <map>
 #include <memory>
 #include <set>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <unordered_set>
@@ -419,6 +421,8 @@ public:
     std::string string() const { return std::string(); }
     FileNode operator[](const char*) const { return FileNode(); }
     FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
 };
 class FileStorage {
 public:
@@ -431,6 +435,7 @@ public:
     FileNode operator[](const std::string&) const { return FileNode(); }
 };
 template <typename T> inline void operator>>(const FileNode&, T&) {}
+template <typename T> inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }  // never opened: writes go nowhere
 
 class Algorithm { public: virtual ~Algorithm() {} };
 }  // namespace cv

@@ -24,6 +24,8 @@
 #include "LineIterator.h"
 #include "gridStructure.h"
 #include "Config.h"
+#include "Thirdparty/DBoW2/DBoW2/FORB.h"
+#include "Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h"
 #include <new>
 
 // ---- bump allocator ---------------------------------------------------------------------------------------------------
@@ -251,7 +253,9 @@ int main(int argc, char** argv) {
         const float* tmo = in[11].as<float>();
         ORBmatcher matcher(0.9, tmo[2] != 0);
         std::map<int, int> match12;
-        const int n = matcher.SearchByProjection(Cur, Last, tmo[0], tmo[1] != 0, match12);
+        // th_mono_ori[3] != 0 selects the overload without match12 (src/ORBmatcher.cc:1330-1472)
+        const int n = in[11].count() > 3 && tmo[3] != 0 ? matcher.SearchByProjection(Cur, Last, tmo[0], tmo[1] != 0)
+                                                        : matcher.SearchByProjection(Cur, Last, tmo[0], tmo[1] != 0, match12);
         std::vector<int> cur_point(Cur.N, -1);
         for (int j = 0; j < Cur.N; ++j) if (Cur.mvpMapPoints[j]) cur_point[j] = (int)(Cur.mvpMapPoints[j] - pts.data());
         out.push_back(make<int>(1, {(long long)Cur.N}, cur_point.data())); out.push_back(make<int>(1, {1}, &n));
@@ -403,6 +407,43 @@ int main(int argc, char** argv) {
             for (int i = 0; i < K1.N; ++i) if (m12[i]) res[i] = (int)(m12[i] - m2.data());
         }
         out.push_back(make<int>(1, {(long long)K1.N}, res.data())); out.push_back(make<int>(1, {1}, &n));
+    } else if (cmd == "bow_transform") {
+        // in: vocabulary in the ORBvoc.txt text format u8[len], desc u8[n,32], levelsup i32[1]
+        // -> DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::loadFromTextFile + transform(features, BowVector, FeatureVector, levelsup)
+        //    (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1131-1194, 1330-1407; the typedef of include/ORBVocabulary.h:31, the call of src/Frame.cc:548-556):
+        //    bow word i32[nw], bow value f64[nw], fv node i32[nn], fv begin i32[nn+1], fv index i32[m]
+        const std::string path = std::string(argv[3]) + ".voc";
+        { FILE* f = fopen(path.c_str(), "wb"); fwrite(in[0].as<uchar>(), 1, in[0].count(), f); fclose(f); }
+        DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> voc;
+        if (!voc.loadFromTextFile(path)) { fprintf(stderr, "refcli: loadFromTextFile failed\n"); return 3; }
+        remove(path.c_str());
+        std::vector<cv::Mat> feats(in[1].dims[0]);
+        for (size_t j = 0; j < feats.size(); ++j) { feats[j] = cv::Mat(1, 32, CV_8UC1); memcpy(feats[j].ptr(), in[1].as<uchar>() + 32 * j, 32); }
+        DBoW2::BowVector bv; DBoW2::FeatureVector fv;
+        voc.transform(feats, bv, fv, in[2].as<int>()[0]);
+        std::vector<int> bw, fn, fb(1, 0), fi; std::vector<double> bval;
+        for (auto& e : bv) { bw.push_back((int)e.first); bval.push_back(e.second); }
+        for (auto& e : fv) { fn.push_back((int)e.first); for (unsigned x : e.second) fi.push_back((int)x); fb.push_back((int)fi.size()); }
+        out.push_back(make<int>(1, {(long long)bw.size()}, bw.data())); out.push_back(make<double>(3, {(long long)bval.size()}, bval.data()));
+        out.push_back(make<int>(1, {(long long)fn.size()}, fn.data())); out.push_back(make<int>(1, {(long long)fb.size()}, fb.data()));
+        out.push_back(make<int>(1, {(long long)fi.size()}, fi.data()));
+    } else if (cmd == "bow_kff") {
+        // in: kf kps, desc, has u8, node, begin, index, frame kps, desc, node, begin, index, flags f32[2] (nn_ratio, check_orientation), cam f32[7], orb, scale
+        // -> SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (src/ORBmatcher.cc:161-290): key-frame index per frame feature i32[nF], return value
+        const int* p = in[13].as<int>();
+        ORBextractor ex(p[0], in[14].as<float>()[0], p[1], p[2], p[3]);
+        const float* fl = in[11].as<float>();
+        KeyFrame K; fill_keyframe(K, ex, in[0], in[1], nullptr, in[12], nullptr);
+        Frame F; fill_frame_points(F, ex, in[6], in[7], in[12]);
+        fill_featvec(K.mFeatVec, in[3], in[4], in[5]); fill_featvec(F.mFeatVec, in[8], in[9], in[10]);
+        std::vector<MapPoint> pts(K.N);
+        for (int i = 0; i < K.N; ++i) if (in[2].as<uchar>()[i]) K.mvpMapPoints[i] = &pts[i];
+        ORBmatcher matcher(fl[0], fl[1] != 0);
+        std::vector<MapPoint*> mf;
+        int n = matcher.SearchByBoW(&K, F, mf);
+        std::vector<int> res(F.N, -1);
+        for (int j = 0; j < F.N; ++j) if (mf[j]) res[j] = (int)(mf[j] - pts.data());
+        out.push_back(make<int>(1, {(long long)F.N}, res.data())); out.push_back(make<int>(1, {1}, &n));
     } else { fprintf(stderr, "refcli: unknown command %s\n", cmd.c_str()); return 2; }
     write_arrays(argv[3], out);
     return 0;

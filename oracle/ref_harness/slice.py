@@ -43,6 +43,8 @@ SLICES = {
                        ("src/ORBmatcher.cc", "bool ORBmatcher::CheckDistEpipolarLine("),
                        ("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw,"),
                        ("src/ORBmatcher.cc", "int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2,"),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F,"),
+                       ("src/ORBmatcher.cc", "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)"),
                        ("src/ORBmatcher.cc", "int ORBmatcher::SearchForTriangulation("),
                        ("src/ORBmatcher.cc", "int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th)"),
                        ("src/ORBmatcher.cc", "int ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw,"),

@@ -58,3 +58,31 @@ def transform_numpy(tree, desc, levelsup):
                 break
         out_w.append(tree["word_id"][node]); out_v.append(tree["weight"][node]); out_n.append(nid)
     return np.array(out_w, np.int32), np.array(out_v, np.float64), np.array(out_n, np.int32)
+
+
+def as_text_file(tree):
+    """The vocabulary in the reference's ORBvoc.txt format (TemplatedVocabulary::loadFromTextFile,
+    Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1337-1407): header `k L scoring weighting` (0 0 = L1_NORM, TF_IDF), then one line per
+    non-root node in id order: `parent is_leaf d0 .. d31 weight`.  The loader numbers nodes by line and words by leaf order and lists
+    children in line order, so the tree handed to the oracle is `loader_view(tree)`.
+    No trailing newline: the loader's `while(!f.eof())` would parse the empty last line into one more node whose parent, leaf flag
+    and descriptor are never assigned (indeterminate in the reference, FORB.cpp:120-135) -- nothing a parity test can hold on to."""
+    n = len(tree["child_begin"])
+    parent = np.zeros(n, np.int64)
+    for i in range(n):
+        for c in tree["children"][tree["child_begin"][i]:tree["child_begin"][i] + tree["child_count"][i]]:
+            parent[c] = i
+    lines = [f"{tree['k']} {tree['L']} 0 0"]
+    for i in range(1, n):
+        leaf = int(tree["child_count"][i] == 0)
+        lines.append(f"{parent[i]} {leaf} " + " ".join(str(int(x)) for x in tree["node_desc"][i]) + f" {float(tree['weight'][i])!r}")
+    return np.frombuffer("\n".join(lines).encode(), np.uint8).copy()
+
+
+def loader_view(tree):
+    """What loadFromTextFile builds from as_text_file(tree): the same nodes with every child list in ascending id order."""
+    t = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in tree.items()}
+    for i in range(len(t["child_begin"])):
+        b, c = t["child_begin"][i], t["child_count"][i]
+        t["children"][b:b + c] = np.sort(t["children"][b:b + c])
+    return t

@@ -161,6 +161,17 @@ def check_bow_kf(run, ratio, ori):
     assert np.array_equal(res_r, m) and n_r[0] == n > 60
 
 
+def check_bow_frame(run, ratio, ori):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:161-290): key frame 1 against view 2 taken as a Frame."""
+    kf1, kf2, _, _, _ = KS.make_stereo_pair_keyframes(67, n=900, pool_noise=30)
+    cam = KS.Camera(670.44, 670.44, 640.0, 360.0, 80.45, 0.0, 1280.0, 0.0, 720.0)
+    has = (1 - kf1["skip"]).astype(np.uint8)
+    res_r, n_r = run("bow_kff", keypoints_as_rows(kf1["kps"]), kf1["desc"], has, *kf1["fv"], keypoints_as_rows(kf2["kps"]), kf2["desc"], *kf2["fv"],
+                     np.array([ratio, ori], np.float32), _camv(cam), *orb_params(1000))
+    m, n = oracle().search_by_bow(kf1["desc"], kf1["kps"], has, kf1["fv"], kf2["desc"], kf2["kps"], kf2["fv"], ratio, bool(ori))
+    assert np.array_equal(res_r, m) and n_r[0] == n > 60
+
+
 INIT_CASES = [(1, 100, 0.9, 1), (2, 40, 0.9, 0), (3, 100, 0.7, 1)]
 
 

@@ -133,12 +133,13 @@ def test_search_by_projection_last_frame():
     fe, cur, last = _tracking_pair()
     w, h, fx, fy, cx, cy, bf = CAMERAS["euroc"]
     camv = np.array([fx, fy, cx, cy, bf, w, h], np.float32)
-    for th, mono, ori in ((7.0, 0, 1), (15.0, 0, 1), (7.0, 1, 0)):
+    # last column: 1 = the overload without match12 (src/ORBmatcher.cc:1330), which must give the same assignment
+    for th, mono, ori, plain in ((7.0, 0, 1, 0), (15.0, 0, 1, 0), (7.0, 1, 0, 0), (7.0, 0, 1, 1), (15.0, 1, 0, 1)):
         args, keep = fe.sbp_last_args(cur, last, th, bool(mono), bool(ori))
         ao, co, no = fe.api.search_by_projection_last(args, keep)
         pose = np.concatenate([np.asarray(cur.Rcw, np.float32).ravel(), np.asarray(cur.tcw, np.float32), np.asarray(last.Rcw, np.float32).ravel(), np.asarray(last.tcw, np.float32)])
         cr, nr = refcli.run("sbp_last", refcli.keypoints_as_rows(cur.kps), cur.desc, cur.u_right, refcli.keypoints_as_rows(last.kps), keep["has"], keep["obs"],
-                            keep["world"], keep["ldesc"], camv, pose.astype(np.float32), keep["sf"], np.array([th, mono, ori], np.float32), *orb_params(1000))
+                            keep["world"], keep["ldesc"], camv, pose.astype(np.float32), keep["sf"], np.array([th, mono, ori, plain], np.float32), *orb_params(1000))
         assert nr[0] == no > 20 and np.array_equal(cr, co), f"SearchByProjection(cur,last) th={th} mono={mono}"
     fe.close()
 
@@ -203,6 +204,28 @@ def test_search_for_triangulation(only_stereo, ori):
 @pytest.mark.parametrize("ratio,ori", KC.BOW_CASES)
 def test_search_by_bow_keyframes(ratio, ori):
     KC.check_bow_kf(refcli.run, ratio, ori)
+
+
+@pytest.mark.parametrize("k,L,levelsup", [(10, 3, 2), (10, 4, 4), (6, 3, 0), (10, 3, 1), (4, 2, 4), (10, 3, 3)])
+def test_bow_transform_against_dbow2(k, L, levelsup):
+    """Frame::ComputeBoW (src/Frame.cc:548-556) -> DBoW2 transform: the reference's own TemplatedVocabulary<FORB> loads the synthetic tree
+    from the ORBvoc text format and transforms real ORB descriptors; BowVector doubles and FeatureVector must equal the oracle's."""
+    from bow_util import make_vocabulary, as_text_file, loader_view
+    o = oracle()
+    sc = Scene("euroc", 5)
+    h = o.orb_create(1200); _, desc = o.orb_extract(h, sc.stereo(0)[0]); o.orb_destroy(h)
+    tree = make_vocabulary(k, L, seed=k + L, seed_desc=desc)
+    bw_r, bv_r, fn_r, fb_r, fi_r = refcli.run("bow_transform", as_text_file(tree), desc, np.array([levelsup], np.int32))
+    v = o.vocab_create(loader_view(tree))
+    bw, bv, fn, fb, fi = o.bow_assemble(*o.bow_transform(v, desc, levelsup))
+    o.vocab_destroy(v)
+    assert len(bw) > min(30, k ** L // 2) and np.array_equal(bw, bw_r) and np.array_equal(bv.view(np.uint64), bv_r.view(np.uint64))
+    assert np.array_equal(fn, fn_r) and np.array_equal(fb, fb_r) and np.array_equal(fi, fi_r)
+
+
+@pytest.mark.parametrize("ratio,ori", KC.BOW_CASES)
+def test_search_by_bow_keyframe_against_frame(ratio, ori):
+    KC.check_bow_frame(refcli.run, ratio, ori)
 
 
 @pytest.mark.parametrize("seed,window,ratio,ori", KC.INIT_CASES)
