@@ -857,14 +857,20 @@ typedef unsigned long long u64;
 __global__ void __launch_bounds__(256) k_sbp_candidates(const SbpQuery* __restrict__ q, const uint32_t* __restrict__ qdesc, int nq,
                                                         const olf_keypoint* __restrict__ kps, const uint32_t* __restrict__ desc, const float* __restrict__ uRight, int n_cur,
                                                         GridParams G, int max_dist, int gate, const float* __restrict__ inv_sigma2,
-                                                        u64* __restrict__ lists, int* __restrict__ counts) {
+                                                        u64* __restrict__ lists, int* __restrict__ counts,
+                                                        const unsigned* __restrict__ off = nullptr, u64* __restrict__ stage_g = nullptr) {
     // gate 1: |ur - uRight[j]| <= radius for stereo keypoints (SearchByProjection last frame / local map, :1556-1561, :93-98)
     // gate 2: chi-square reprojection gate of Fuse(KF, MPs, th) (:916-940); gate 0: none (KeyFrame window searches)
+    // Lists: SBP_K slots per query, staged in shared memory (off == nullptr); a window that holds more makes the host run the
+    // pass again with exact per-query capacities (CSR offsets `off` from the counts of the first pass, staging in global memory)
     __shared__ u64 sh[8][SBP_K];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + w;
     if (i >= nq) return;
     const SbpQuery Q = q[i];
+    u64* const stage = off ? stage_g + off[i] : sh[w];
+    u64* const out = off ? lists + off[i] : lists + (size_t)i * SBP_K;
+    const int cap = off ? (int)(off[i + 1] - off[i]) : SBP_K;
     int n = 0;
     if (Q.valid) {
         const int nMinCellX = max(0, (int)floorf(fmul(fsub(fsub(Q.u, G.min_x), Q.radius), G.inv_w)));
@@ -901,20 +907,20 @@ __global__ void __launch_bounds__(256) k_sbp_candidates(const SbpQuery* __restri
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, take);
-            if (take) { const int p = n + __popc(m & ((1u << lane) - 1)); if (p < SBP_K) sh[w][p] = key; }
+            if (take) { const int p = n + __popc(m & ((1u << lane) - 1)); if (p < cap) stage[p] = key; }
             n += __popc(m);
         }
     }
     __syncwarp();
-    const int stored = min(n, SBP_K);
+    const int stored = min(n, cap);
     // rank sort (keys are distinct: they embed j)
     for (int e = lane; e < stored; e += 32) {
-        const u64 key = sh[w][e];
+        const u64 key = stage[e];
         int rank = 0;
-        for (int f = 0; f < stored; ++f) rank += sh[w][f] < key;
-        lists[(size_t)i * SBP_K + rank] = key;
+        for (int f = 0; f < stored; ++f) rank += stage[f] < key;
+        out[rank] = key;
     }
-    if (lane == 0) counts[i] = n;          // n > SBP_K flags an overflow to the host
+    if (lane == 0) counts[i] = n;          // n > SBP_K in the first pass: the host runs the exact-capacity pass
 }
 
 // One block.  Iterates  assign[i] = first candidate of i not owned by an earlier observed point  to its fixed point.
@@ -924,7 +930,7 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(const u64* __restrict__ li
                                                       const uint8_t* __restrict__ observed, const uint8_t* __restrict__ occupied,
                                                       const olf_keypoint* __restrict__ kps, int mode, float nn_ratio,
                                                       int* __restrict__ owner_a, int* __restrict__ owner_b, int* __restrict__ assign, int* __restrict__ rounds_out,
-                                                      int* __restrict__ adist = nullptr) {
+                                                      int* __restrict__ adist = nullptr, const unsigned* __restrict__ off = nullptr) {
     __shared__ int s_changed;
     int* own_prev = owner_a; int* own_new = owner_b;
     for (int j = threadIdx.x; j < n_cur; j += 1024) { own_prev[j] = (occupied && occupied[j]) ? -1 : INT_MAX; }
@@ -936,14 +942,15 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(const u64* __restrict__ li
         for (int j = threadIdx.x; j < n_cur; j += 1024) own_new[j] = (occupied && occupied[j]) ? -1 : INT_MAX;
         __syncthreads();
         for (int i = threadIdx.x; i < nq; i += 1024) {
-            const int cnt = min(counts[i], SBP_K);
+            const int cnt = off ? counts[i] : min(counts[i], SBP_K);
+            const u64* const L = off ? lists + off[i] : lists + (size_t)i * SBP_K;
             int sel = -1, seld = 256;
             if (mode == 0) {
-                for (int e = 0; e < cnt; ++e) { const u64 key = lists[(size_t)i * SBP_K + e]; const int j = (int)(key & 0xFFFFFF); if (!(own_prev[j] < i)) { sel = j; seld = (int)(key >> 40); break; } }
+                for (int e = 0; e < cnt; ++e) { const u64 key = L[e]; const int j = (int)(key & 0xFFFFFF); if (!(own_prev[j] < i)) { sel = j; seld = (int)(key >> 40); break; } }
             } else {
                 int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1, found = 0;
                 for (int e = 0; e < cnt && found < 2; ++e) {
-                    const u64 key = lists[(size_t)i * SBP_K + e];
+                    const u64 key = L[e];
                     const int j = (int)(key & 0xFFFFFF), d = (int)(key >> 40);
                     if (own_prev[j] < i) continue;
                     if (found == 0) { if (d < bestDist) { bestDist = d; bestLevel = kps[j].octave; bestIdx = j; } }
@@ -966,55 +973,86 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(const u64* __restrict__ li
     if (threadIdx.x == 0) *rounds_out = rounds;
 }
 
+// A window that holds more than SBP_K candidates (dense texture, SearchForInitialization's 100-pixel window) sends the call through the pass
+// again with exact per-window capacities: CSR offsets from the counts of the first pass.  The lists of all windows together are bounded
+// (16 bytes per candidate on the device); beyond that the call fails loudly.
+#define SBP_CSR_MAX ((size_t)32 << 20)
+static int csr_from_counts(const int* cnt, int nq, std::vector<unsigned>& off, const char* who) {
+    off.assign((size_t)nq + 1, 0u);
+    size_t total = 0;
+    for (int i = 0; i < nq; ++i) {
+        off[i] = (unsigned)total; total += (size_t)std::max(cnt[i], 0);
+        if (total > SBP_CSR_MAX) { set_last_error(std::string(who) + ": the search windows hold more than 2^25 candidates together"); return OLF_ERR_CAPACITY; }
+    }
+    off[nq] = (unsigned)total;
+    return OLF_OK;
+}
+
 static int sbp_common(MatchCtx* c, const std::vector<SbpQuery>& q, const uint8_t* qdesc, const uint8_t* observed, const uint8_t* occupied,
                       const olf_keypoint* cur_kps, const uint8_t* cur_desc, const float* cur_u_right, int n_cur, const olf_camera& cam,
                       int mode, int max_dist, float nn_ratio, int* assign_out, int gate = 1, const float* inv_sigma2 = nullptr, int nlevels = 0, int* dist_out = nullptr) {
     const int nq = (int)q.size();
     int rc;
     if (n_cur >= (1 << 24)) { set_last_error("olf_search_by_projection: too many keypoints"); return OLF_ERR_CAPACITY; }
-    Planner pl;
-    const size_t o_q = pl.d((size_t)nq * sizeof(SbpQuery)), o_qd = pl.d((size_t)nq * 32), o_obs = pl.d(nq), o_occ = pl.d(std::max(n_cur, 1));
-    const size_t o_k = pl.d((size_t)n_cur * sizeof(olf_keypoint)), o_d = pl.d((size_t)n_cur * 32), o_u = pl.d((size_t)n_cur * 4);
-    const size_t o_lists = pl.d((size_t)nq * SBP_K * 8), o_cnt = pl.d((size_t)nq * 4), o_oa = pl.d((size_t)n_cur * 4), o_ob = pl.d((size_t)n_cur * 4), o_as = pl.d((size_t)nq * 4), o_r = pl.d(4);
-    const size_t o_sig = pl.d((size_t)OLF_MAX_LEVELS * 4), o_ad = pl.d((size_t)nq * 4);
-    const size_t p_in = pl.p((size_t)nq * (sizeof(SbpQuery) + 33) + (size_t)n_cur * (sizeof(olf_keypoint) + 37) + 64 + OLF_MAX_LEVELS * 4), p_out = pl.p((size_t)nq * 12 + 16);
-    if ((rc = arena_ensure(c, pl))) return rc;
-    cudaStream_t s = c->cur;
-    uint8_t* hp = hptr<uint8_t>(c, p_in);
-    size_t off = 0;
-    auto up = [&](size_t dev_off, const void* src, size_t bytes) -> int {
-        if (!bytes) return OLF_OK;
-        memcpy(hp + off, src, bytes);
-        cudaError_t e = cudaMemcpyAsync(c->a.dev.p + dev_off, hp + off, bytes, cudaMemcpyHostToDevice, s);
-        off += bytes;
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+    std::vector<unsigned> csr;                                  // empty: first pass, SBP_K slots per window
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool wide = !csr.empty();
+        const size_t slots = wide ? (size_t)csr.back() : (size_t)nq * SBP_K;
+        Planner pl;
+        const size_t o_q = pl.d((size_t)nq * sizeof(SbpQuery)), o_qd = pl.d((size_t)nq * 32), o_obs = pl.d(nq), o_occ = pl.d(std::max(n_cur, 1));
+        const size_t o_k = pl.d((size_t)n_cur * sizeof(olf_keypoint)), o_d = pl.d((size_t)n_cur * 32), o_u = pl.d((size_t)n_cur * 4);
+        const size_t o_lists = pl.d(slots * 8), o_cnt = pl.d((size_t)nq * 4), o_oa = pl.d((size_t)n_cur * 4), o_ob = pl.d((size_t)n_cur * 4), o_as = pl.d((size_t)nq * 4), o_r = pl.d(4);
+        const size_t o_sig = pl.d((size_t)OLF_MAX_LEVELS * 4), o_ad = pl.d((size_t)nq * 4);
+        const size_t o_stage = pl.d(wide ? slots * 8 : 0), o_off = pl.d(wide ? ((size_t)nq + 1) * 4 : 0);
+        const size_t p_in = pl.p((size_t)nq * (sizeof(SbpQuery) + 33) + (size_t)n_cur * (sizeof(olf_keypoint) + 37) + 64 + OLF_MAX_LEVELS * 4 + (wide ? ((size_t)nq + 1) * 4 : 0)),
+                     p_out = pl.p((size_t)nq * 12 + 16);
+        if ((rc = arena_ensure(c, pl))) return rc;
+        cudaStream_t s = c->cur;
+        uint8_t* hp = hptr<uint8_t>(c, p_in);
+        size_t off = 0;
+        auto up = [&](size_t dev_off, const void* src, size_t bytes) -> int {
+            if (!bytes) return OLF_OK;
+            memcpy(hp + off, src, bytes);
+            cudaError_t e = cudaMemcpyAsync(c->a.dev.p + dev_off, hp + off, bytes, cudaMemcpyHostToDevice, s);
+            off += bytes;
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+            return OLF_OK;
+        };
+        if (wide && (rc = up(o_off, csr.data(), csr.size() * 4))) return rc;
+        if ((rc = up(o_q, q.data(), (size_t)nq * sizeof(SbpQuery))) || (rc = up(o_qd, qdesc, (size_t)nq * 32)) || (rc = up(o_obs, observed, nq)) ||
+            (rc = up(o_k, cur_kps, (size_t)n_cur * sizeof(olf_keypoint))) || (rc = up(o_d, cur_desc, (size_t)n_cur * 32))) return rc;
+        if (cur_u_right && (rc = up(o_u, cur_u_right, (size_t)n_cur * 4))) return rc;
+        if (gate == 2 && (rc = up(o_sig, inv_sigma2, (size_t)std::min(nlevels, OLF_MAX_LEVELS) * 4))) return rc;
+        if (occupied && (rc = up(o_occ, occupied, n_cur))) return rc;
+        GridParams G; G.min_x = cam.min_x; G.min_y = cam.min_y;
+        G.inv_w = (float)OLF_GRID_COLS / (cam.max_x - cam.min_x); G.inv_h = (float)OLF_GRID_ROWS / (cam.max_y - cam.min_y);       // src/Frame.cc:185-186
+        const unsigned* d_off = wide ? dptr<unsigned>(c, o_off) : nullptr;
+        k_sbp_candidates<<<(nq + 7) / 8, 256, 0, s>>>(dptr<SbpQuery>(c, o_q), dptr<uint32_t>(c, o_qd), nq, dptr<olf_keypoint>(c, o_k), dptr<uint32_t>(c, o_d), dptr<float>(c, o_u), n_cur,
+                                                      G, max_dist, gate, dptr<float>(c, o_sig), dptr<u64>(c, o_lists), dptr<int>(c, o_cnt), d_off, wide ? dptr<u64>(c, o_stage) : nullptr);
+        k_sbp_resolve<<<1, 1024, 0, s>>>(dptr<u64>(c, o_lists), dptr<int>(c, o_cnt), nq, n_cur, dptr<uint8_t>(c, o_obs), occupied ? dptr<uint8_t>(c, o_occ) : nullptr,
+                                         dptr<olf_keypoint>(c, o_k), mode, nn_ratio, dptr<int>(c, o_oa), dptr<int>(c, o_ob), dptr<int>(c, o_as), dptr<int>(c, o_r),
+                                         dist_out ? dptr<int>(c, o_ad) : nullptr, d_off);
+        count_launches(2);
+        int* ho = hptr<int>(c, p_out);
+        OLF_CUDA(cudaMemcpyAsync(ho, dptr<int>(c, o_as), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        OLF_CUDA(cudaMemcpyAsync(ho + nq, dptr<int>(c, o_cnt), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        if (dist_out) OLF_CUDA(cudaMemcpyAsync(ho + 2 * nq, dptr<int>(c, o_ad), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        OLF_CUDA(cudaGetLastError());
+        OLF_CUDA(stream_sync(s));
+        bool overflow = false;
+        for (int i = 0; i < nq && !wide; ++i) overflow |= ho[nq + i] > SBP_K;
+        if (overflow) {
+            if ((rc = csr_from_counts(ho + nq, nq, csr, "olf_search_by_projection"))) return rc;
+            continue;
+        }
+        for (int i = 0; i < nq; ++i) {
+            if (wide && ho[nq + i] != (int)(csr[i + 1] - csr[i])) { set_last_error("olf_search_by_projection: candidate counts changed between the passes"); return OLF_ERR_INTERNAL; }
+            assign_out[i] = ho[i];
+            if (dist_out) dist_out[i] = ho[i] >= 0 ? ho[2 * nq + i] : 256;
+        }
         return OLF_OK;
-    };
-    if ((rc = up(o_q, q.data(), (size_t)nq * sizeof(SbpQuery))) || (rc = up(o_qd, qdesc, (size_t)nq * 32)) || (rc = up(o_obs, observed, nq)) ||
-        (rc = up(o_k, cur_kps, (size_t)n_cur * sizeof(olf_keypoint))) || (rc = up(o_d, cur_desc, (size_t)n_cur * 32))) return rc;
-    if (cur_u_right && (rc = up(o_u, cur_u_right, (size_t)n_cur * 4))) return rc;
-    if (gate == 2 && (rc = up(o_sig, inv_sigma2, (size_t)std::min(nlevels, OLF_MAX_LEVELS) * 4))) return rc;
-    if (occupied && (rc = up(o_occ, occupied, n_cur))) return rc;
-    GridParams G; G.min_x = cam.min_x; G.min_y = cam.min_y;
-    G.inv_w = (float)OLF_GRID_COLS / (cam.max_x - cam.min_x); G.inv_h = (float)OLF_GRID_ROWS / (cam.max_y - cam.min_y);       // src/Frame.cc:185-186
-    k_sbp_candidates<<<(nq + 7) / 8, 256, 0, s>>>(dptr<SbpQuery>(c, o_q), dptr<uint32_t>(c, o_qd), nq, dptr<olf_keypoint>(c, o_k), dptr<uint32_t>(c, o_d), dptr<float>(c, o_u), n_cur,
-                                                  G, max_dist, gate, dptr<float>(c, o_sig), dptr<u64>(c, o_lists), dptr<int>(c, o_cnt));
-    k_sbp_resolve<<<1, 1024, 0, s>>>(dptr<u64>(c, o_lists), dptr<int>(c, o_cnt), nq, n_cur, dptr<uint8_t>(c, o_obs), occupied ? dptr<uint8_t>(c, o_occ) : nullptr,
-                                     dptr<olf_keypoint>(c, o_k), mode, nn_ratio, dptr<int>(c, o_oa), dptr<int>(c, o_ob), dptr<int>(c, o_as), dptr<int>(c, o_r),
-                                     dist_out ? dptr<int>(c, o_ad) : nullptr);
-    count_launches(2);
-    int* ho = hptr<int>(c, p_out);
-    OLF_CUDA(cudaMemcpyAsync(ho, dptr<int>(c, o_as), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
-    OLF_CUDA(cudaMemcpyAsync(ho + nq, dptr<int>(c, o_cnt), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
-    if (dist_out) OLF_CUDA(cudaMemcpyAsync(ho + 2 * nq, dptr<int>(c, o_ad), (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
-    OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(stream_sync(s));
-    for (int i = 0; i < nq; ++i) {
-        if (ho[nq + i] > SBP_K) { set_last_error("olf_search_by_projection: more than 128 candidates in one search window"); return OLF_ERR_CAPACITY; }
-        assign_out[i] = ho[i];
-        if (dist_out) dist_out[i] = ho[i] >= 0 ? ho[2 * nq + i] : 256;
     }
-    return OLF_OK;
+    set_last_error("olf_search_by_projection: internal error"); return OLF_ERR_INTERNAL;
 }
 
 static void mat3_mul_vec(const float* R, const float* v, float* o) { for (int r = 0; r < 3; ++r) o[r] = R[3 * r] * v[0] + R[3 * r + 1] * v[1] + R[3 * r + 2] * v[2]; }
@@ -1161,42 +1199,59 @@ int search_for_initialization(const olf_keypoint* kps1, const uint8_t* desc1, in
         Q.u = prev_matched[2 * i]; Q.v = prev_matched[2 * i + 1]; Q.radius = (float)window_size; Q.ur = 0.f;
         Q.min_level = 0; Q.max_level = 0; Q.valid = kps1[i].octave <= 0;                     // `if (level1 > 0) continue`, GetFeaturesInArea(.., level1, level1)
     }
-    Planner pl;
-    const size_t o_q = pl.d((size_t)n1 * sizeof(SbpQuery)), o_qd = pl.d((size_t)n1 * 32), o_k = pl.d((size_t)n2 * sizeof(olf_keypoint)), o_d = pl.d((size_t)n2 * 32),
-                 o_lists = pl.d((size_t)n1 * SBP_K * 8), o_cnt = pl.d((size_t)n1 * 4);
-    const size_t p_in = pl.p((size_t)n1 * (sizeof(SbpQuery) + 32) + (size_t)n2 * (sizeof(olf_keypoint) + 32) + 64), p_l = pl.p((size_t)n1 * SBP_K * 8), p_c = pl.p((size_t)n1 * 4);
-    if ((rc = arena_ensure(c, pl))) return rc;
-    cudaStream_t s = c->cur;
-    uint8_t* hp = hptr<uint8_t>(c, p_in);
-    size_t off = 0;
-    auto up = [&](size_t dev_off, const void* src, size_t bytes) -> int {
-        memcpy(hp + off, src, bytes);
-        cudaError_t e = cudaMemcpyAsync(c->a.dev.p + dev_off, hp + off, bytes, cudaMemcpyHostToDevice, s);
-        off += (bytes + 15) & ~(size_t)15;
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
-        return OLF_OK;
-    };
-    if ((rc = up(o_q, q.data(), (size_t)n1 * sizeof(SbpQuery))) || (rc = up(o_qd, desc1, (size_t)n1 * 32)) || (rc = up(o_k, kps2, (size_t)n2 * sizeof(olf_keypoint))) ||
-        (rc = up(o_d, desc2, (size_t)n2 * 32))) return rc;
-    GridParams G; G.min_x = cam->min_x; G.min_y = cam->min_y;
-    G.inv_w = (float)OLF_GRID_COLS / (cam->max_x - cam->min_x); G.inv_h = (float)OLF_GRID_ROWS / (cam->max_y - cam->min_y);
-    k_sbp_candidates<<<(n1 + 7) / 8, 256, 0, s>>>(dptr<SbpQuery>(c, o_q), dptr<uint32_t>(c, o_qd), n1, dptr<olf_keypoint>(c, o_k), dptr<uint32_t>(c, o_d), nullptr, n2,
-                                                  G, 256, 0, nullptr, dptr<u64>(c, o_lists), dptr<int>(c, o_cnt));
-    count_launches(1);
-    OLF_CUDA(cudaMemcpyAsync(hptr<u64>(c, p_l), dptr<u64>(c, o_lists), (size_t)n1 * SBP_K * 8, cudaMemcpyDeviceToHost, s));
-    OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_c), dptr<int>(c, o_cnt), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-    OLF_CUDA(cudaGetLastError());
-    OLF_CUDA(stream_sync(s));
-    const u64* lists = hptr<u64>(c, p_l); const int* cnt = hptr<int>(c, p_c);
+    std::vector<unsigned> csr;                                  // empty: first pass, SBP_K slots per window (see sbp_common)
+    const u64* lists = nullptr; const int* cnt = nullptr;
+    for (int pass = 0; pass < 2 && !lists; ++pass) {
+        const bool wide = !csr.empty();
+        const size_t slots = wide ? (size_t)csr.back() : (size_t)n1 * SBP_K;
+        Planner pl;
+        const size_t o_q = pl.d((size_t)n1 * sizeof(SbpQuery)), o_qd = pl.d((size_t)n1 * 32), o_k = pl.d((size_t)n2 * sizeof(olf_keypoint)), o_d = pl.d((size_t)n2 * 32),
+                     o_lists = pl.d(slots * 8), o_cnt = pl.d((size_t)n1 * 4), o_stage = pl.d(wide ? slots * 8 : 0), o_off = pl.d(wide ? ((size_t)n1 + 1) * 4 : 0);
+        const size_t p_in = pl.p((size_t)n1 * (sizeof(SbpQuery) + 32) + (size_t)n2 * (sizeof(olf_keypoint) + 32) + 96 + (wide ? ((size_t)n1 + 1) * 4 : 0)),
+                     p_l = pl.p(slots * 8), p_c = pl.p((size_t)n1 * 4);
+        if ((rc = arena_ensure(c, pl))) return rc;
+        cudaStream_t s = c->cur;
+        uint8_t* hp = hptr<uint8_t>(c, p_in);
+        size_t off = 0;
+        auto up = [&](size_t dev_off, const void* src, size_t bytes) -> int {
+            memcpy(hp + off, src, bytes);
+            cudaError_t e = cudaMemcpyAsync(c->a.dev.p + dev_off, hp + off, bytes, cudaMemcpyHostToDevice, s);
+            off += (bytes + 15) & ~(size_t)15;
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+            return OLF_OK;
+        };
+        if ((rc = up(o_q, q.data(), (size_t)n1 * sizeof(SbpQuery))) || (rc = up(o_qd, desc1, (size_t)n1 * 32)) || (rc = up(o_k, kps2, (size_t)n2 * sizeof(olf_keypoint))) ||
+            (rc = up(o_d, desc2, (size_t)n2 * 32)) || (wide && (rc = up(o_off, csr.data(), csr.size() * 4)))) return rc;
+        GridParams G; G.min_x = cam->min_x; G.min_y = cam->min_y;
+        G.inv_w = (float)OLF_GRID_COLS / (cam->max_x - cam->min_x); G.inv_h = (float)OLF_GRID_ROWS / (cam->max_y - cam->min_y);
+        k_sbp_candidates<<<(n1 + 7) / 8, 256, 0, s>>>(dptr<SbpQuery>(c, o_q), dptr<uint32_t>(c, o_qd), n1, dptr<olf_keypoint>(c, o_k), dptr<uint32_t>(c, o_d), nullptr, n2,
+                                                      G, 256, 0, nullptr, dptr<u64>(c, o_lists), dptr<int>(c, o_cnt),
+                                                      wide ? dptr<unsigned>(c, o_off) : nullptr, wide ? dptr<u64>(c, o_stage) : nullptr);
+        count_launches(1);
+        if (slots) OLF_CUDA(cudaMemcpyAsync(hptr<u64>(c, p_l), dptr<u64>(c, o_lists), slots * 8, cudaMemcpyDeviceToHost, s));
+        OLF_CUDA(cudaMemcpyAsync(hptr<int>(c, p_c), dptr<int>(c, o_cnt), (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+        OLF_CUDA(cudaGetLastError());
+        OLF_CUDA(stream_sync(s));
+        const int* hc = hptr<int>(c, p_c);
+        bool overflow = false;
+        for (int i1 = 0; i1 < n1 && !wide; ++i1) overflow |= hc[i1] > SBP_K;
+        if (overflow) {
+            if ((rc = csr_from_counts(hc, n1, csr, "olf_search_for_initialization"))) return rc;
+            continue;
+        }
+        if (!wide) { csr.resize((size_t)n1 + 1); for (int i1 = 0; i1 <= n1; ++i1) csr[i1] = (unsigned)i1 * SBP_K; }
+        lists = hptr<u64>(c, p_l); cnt = hc;
+    }
+    if (!lists) { set_last_error("olf_search_for_initialization: internal error"); return OLF_ERR_INTERNAL; }
     std::vector<int> vMatchedDistance(n2, INT_MAX), vnMatches21(n2, -1);
     std::vector<std::pair<int, float>> rots;
     int nmatches = 0;
     for (int i1 = 0; i1 < n1; ++i1) {
-        if (cnt[i1] > SBP_K) { set_last_error("olf_search_for_initialization: more than 128 candidates in one search window"); return OLF_ERR_CAPACITY; }
         // first and second admissible entry of the sorted list = bestDist / bestIdx2 and bestDist2 of the reference's loop (:443-458)
         int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
         for (int e = 0; e < cnt[i1]; ++e) {
-            const int i2 = (int)(lists[(size_t)i1 * SBP_K + e] & 0xFFFFFF), dist = (int)(lists[(size_t)i1 * SBP_K + e] >> 40);
+            const u64 key = lists[(size_t)csr[i1] + e];
+            const int i2 = (int)(key & 0xFFFFFF), dist = (int)(key >> 40);
             if (vMatchedDistance[i2] <= dist) continue;
             if (bestIdx2 < 0) { bestDist = dist; bestIdx2 = i2; } else { bestDist2 = dist; break; }
         }

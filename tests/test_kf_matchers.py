@@ -219,6 +219,34 @@ def test_gpu_window_search(case, seed, n, nq):
     assert (gi >= 0).sum() > nq // 10
 
 
+def dense_keyframe(seed, n):
+    """Every keypoint inside a 260 x 200 patch, two octaves, two descriptor families: a 100-pixel window holds hundreds of candidates within
+    max_dist -- far beyond the 128 slots of the first device pass (the reference's vectors have no such limit)."""
+    kf = K.make_keyframe(seed, n=n, pool=2)
+    rng = np.random.RandomState(seed + 7)
+    kf["kps"]["x"] = (500 + rng.rand(n) * 260).astype(np.float32); kf["kps"]["y"] = (300 + rng.rand(n) * 200).astype(np.float32)
+    kf["kps"]["octave"] = rng.randint(0, 2, n)
+    kf["u_right"] = np.where(kf["u_right"] >= 0, kf["kps"]["x"] - (5 + 40 * rng.rand(n)).astype(np.float32), np.float32(-1)).astype(np.float32)
+    return kf
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_gpu_window_search_dense_windows(case):
+    import orb_line_slam_b200 as olf
+    kf = dense_keyframe(11, 1500)
+    q = K.random_queries(kf, 700, 111, max_radius=120.0, pool=2)
+    q["min_level"][:] = 0; q["max_level"][:] = 1
+    q["radius"][::7] = 4.0                                                        # and a few ordinary windows among them
+    inside = (np.abs(kf["kps"]["x"][None, :] - q["u"][:40, None]) < q["radius"][:40, None]) & (np.abs(kf["kps"]["y"][None, :] - q["v"][:40, None]) < q["radius"][:40, None])
+    near = np.stack([popcount_rows(kf["desc"], q["qdesc"][i][None, :]) <= case["max_dist"] for i in range(40)])
+    assert (inside & near).sum(1).max() > 300                                     # the case does overflow the first pass
+    _, _, inv_sig, _ = K.scale_tables()
+    (gi, gd), _, _ = run_window(olf.api(0), kf, q, case, inv_sig)
+    (oi, od), _, _ = run_window(oracle(), kf, q, case, inv_sig)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od) and (gi >= 0).sum() > 100
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,th,max_dist", [("fuse", 3.0, 50), ("fuse_sim3", 4.0, 50), ("sbp_kf", 10.0, 50), ("reloc", 10.0, 100), ("reloc", 3.0, 64)])
 def test_gpu_projection_overloads(mode, th, max_dist):
@@ -310,12 +338,13 @@ def test_gpu_edge_cases():
     assert len(gi) == 0
     gi, gd = api.window_search(kf["kps"][:0], kf["desc"][:0], kf["cam"], q["u"], q["v"], q["radius"], q["min_level"], q["max_level"], q["qdesc"], 256)
     assert (gi == -1).all() and (gd == 256).all()
-    # a window with more than 128 admissible candidates is reported, not truncated
+    # a window with more than 128 admissible candidates (here: thousands) is neither truncated nor refused
     dense = K.make_keyframe(8, n=4000, w=320, h=240)
     dense["cam"] = K.Camera(300.0, 300.0, 160.0, 120.0, 40.0, 0.0, 320.0, 0.0, 240.0)
-    with pytest.raises(RuntimeError, match="128 candidates"):
-        api.window_search(dense["kps"], dense["desc"], dense["cam"], np.array([160.0], np.float32), np.array([120.0], np.float32), np.array([100.0], np.float32),
-                          np.array([0], np.int32), np.array([7], np.int32), dense["desc"][:1], 256)
+    args = (dense["kps"], dense["desc"], dense["cam"], np.array([160.0], np.float32), np.array([120.0], np.float32), np.array([100.0], np.float32),
+            np.array([0], np.int32), np.array([7], np.int32), dense["desc"][:1], 256)
+    gi, gd = api.window_search(*args); oi, od = oracle().window_search(*args)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od) and gd[0] == 0
 
 
 # ---- ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:407-522) ---------------------------------------------------------
@@ -416,3 +445,20 @@ def test_gpu_search_for_initialization(seed, n, window, ratio, ori):
     assert len(e[0]) == 0 and e[1] == 0
     gm, gn, gp = olf.api(0).search_for_initialization(k1, d1, k2[:0], d2[:0], cam, prev, window, ratio, ori)
     assert gn == 0 and (gm == -1).all() and np.array_equal(gp, prev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,ratio,ori", [(5, 0.9, True), (6, 0.8, False)])
+def test_gpu_search_for_initialization_dense_windows(seed, ratio, ori):
+    """4000 keypoints squeezed into a quarter of the image: the 100-pixel window of SearchForInitialization (src/ORBmatcher.cc:407) holds many
+    hundreds of level-0 keypoints, the lists go through the exact-capacity second pass."""
+    import orb_line_slam_b200 as olf
+    k1, d1, k2, d2, cam, prev = init_case(seed, n=4000)
+    for k in (k1, k2):
+        k["x"] = (400 + k["x"] * 0.25).astype(np.float32); k["y"] = (250 + k["y"] * 0.3).astype(np.float32)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    lvl0 = k2[k2["octave"] == 0]
+    assert ((np.abs(lvl0["x"] - prev[0, 0]) < 100) & (np.abs(lvl0["y"] - prev[0, 1]) < 100)).sum() > 300
+    gm, gn, gp = olf.api(0).search_for_initialization(k1, d1, k2, d2, cam, prev, 100, ratio, ori)
+    om, on, op = oracle().search_for_initialization(k1, d1, k2, d2, cam, prev, 100, ratio, ori)
+    assert np.array_equal(gm, om) and gn == on and np.array_equal(gp, op) and gn > 20
