@@ -496,6 +496,11 @@ struct GrowSmem { float2 nb[8][GROW_THREADS]; unsigned ring[GROW_RING][GROW_THRE
 #ifndef GROW_MIN_BLOCKS
 #define GROW_MIN_BLOCKS 1
 #endif
+// PIPE: software-pipelined walk -- the sixteen loads of the NEXT queue entry travel while the candidates of the current one are decided.
+// Same decisions (a region's own claims made meanwhile are patched into the loaded flags); measured on a B200: one chain alone 8 % shorter
+// (24.97 -> 23.13 ms for 8 images), no difference at 20 rigs (1041 vs 1037 frames/s) -- so a single frame (latency) runs the pipelined
+// instance, a batch (throughput) the plain one with its smaller register footprint (114 vs 135).
+template <bool PIPE>
 __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(const __grid_constant__ GrowBatch B) {
     __shared__ GrowSmem sm;
     __shared__ GrowDev s_dev;
@@ -572,6 +577,223 @@ __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(cons
             pool[(size_t)b_chunk * kChunk + b_off++] = pix;
             ++bcnt;
         };
+        if constexpr (PIPE) {
+        // software-pipelined walk; the plain one (one memory round trip per entry ON the critical path) is the else branch
+        bool have_cur = false;
+        int p_c = 0, px_c = 0, py_c = 0, p_n = 0, px_n = 0, py_n = 0;
+        unsigned mask_n = 0, m_free = 0, m_held = 0, m_low = 0;
+        u64 cl[8], cl_c = 0; float4 lo[8];
+        for (;;) {
+            if (!active) {
+                if (steps >= budget) break;                           // the rest of the list waits for the next launch
+                // ---- s3_begin: the seed pixel has been claimed by the verify pass
+                const unsigned k = atomicAdd(&st->wl2_pop, 1u);
+                if (k >= n) break;
+                ring_base = 0;
+                i = D.wl2[k];
+                const int seed = C.seed_pix[i];
+                mine = key_of(C, C.seed_prio[i]);
+                count = 0; done = 0; b_head = kNull; b_chunk = kNull; b_off = 0; bcnt = 0; overflow = false;
+                {
+                    int sy = __float2int_rd(__fmul_rn((float)seed, inv_w)), sx = seed - sy * W;
+                    if (sx < 0) { --sy; sx += W; } else if (sx >= W) { ++sy; sx -= W; }
+                    bx0 = bx1 = sx; by0 = by1 = sy;
+                }
+                const unsigned nc = atomicAdd(C.pool_ctr, 1u);
+                if (nc >= C.pool_chunks) overflow = true;
+                else {
+                    pool[(size_t)nc * kChunk + kChunk - 1] = kNull;
+                    w_head = w_chunk = r_chunk = nc; w_off = 0; r_off = 0;
+                    push((unsigned)seed);
+                    float a, cx, cy; unsigned b;
+                    ld_lo(&C.px[seed], a, cx, cy, b);
+                    reg_angle = d_mul((double)a, kDegToRads);
+                    const float2_t t0 = C.tab_seed[tab_index(C.dabc[seed])];
+                    sumdx = t0.x; sumdy = t0.y;
+                    u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
+                    dirty = false;
+                }
+                have_cur = false;
+                active = true;
+            }
+            // (1) the next queue entry, if the queue holds one: pop it and issue its sixteen loads; they travel while the candidates of the
+            //     current entry are decided below.  What this thread claims meanwhile is missing from the loaded claim words: mask_n collects it
+            bool have_next = false;
+            if (!overflow && done < count && steps < budget) {
+                if (r_off == kChunk - 1) { r_chunk = pool[(size_t)r_chunk * kChunk + kChunk - 1]; r_off = 0; }
+                p_n = (int)((count - done <= GROW_RING && done >= ring_base) ? sm.ring[done & (GROW_RING - 1)][t] : pool[(size_t)r_chunk * kChunk + r_off]);
+                ++r_off; ++done; ++steps;
+                py_n = __float2int_rd(__fmul_rn((float)p_n, inv_w));            // p < 2^24: exact after one correction step
+                px_n = p_n - py_n * W;
+                if (px_n < 0) { --py_n; px_n += W; } else if (px_n >= W) { ++py_n; px_n -= W; }
+                mask_n = 0; have_next = true;                               // (all bookkeeping BEFORE the loads: nothing may touch a register between them and the candidates)
+                const PxRec* const base = C.px + p_n;
+                // all sixteen loads are issued before anything consumes them (one memory round trip per queue entry): ONE asm
+                // block per kind; neighbours outside the image read the guard band or the neighbouring row (valid memory) and
+                // are masked out by `vm`
+                const PxRec* ra[8];                                      // (the record array has a guard band of W+2 records at both ends)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int nk = k < 4 ? k : k + 1;
+                    ra[k] = base + ((nk / 3) - 1) * W + ((nk % 3) - 1);
+                }
+                asm volatile(
+                    "ld.relaxed.gpu.global.u64 %0, [%9];\n\t"
+                    "ld.relaxed.gpu.global.u64 %1, [%10];\n\t"
+                    "ld.relaxed.gpu.global.u64 %2, [%11];\n\t"
+                    "ld.relaxed.gpu.global.u64 %3, [%12];\n\t"
+                    "ld.relaxed.gpu.global.u64 %4, [%13];\n\t"
+                    "ld.relaxed.gpu.global.u64 %5, [%14];\n\t"
+                    "ld.relaxed.gpu.global.u64 %6, [%15];\n\t"
+                    "ld.relaxed.gpu.global.u64 %7, [%16];\n\t"
+                    "ld.relaxed.gpu.global.u64 %8, [%17];"
+                    : "=l"(cl[0]), "=l"(cl[1]), "=l"(cl[2]), "=l"(cl[3]), "=l"(cl[4]), "=l"(cl[5]), "=l"(cl[6]), "=l"(cl[7]), "=l"(cl_c)
+                    : "l"(ra[0]), "l"(ra[1]), "l"(ra[2]), "l"(ra[3]), "l"(ra[4]), "l"(ra[5]), "l"(ra[6]), "l"(ra[7]), "l"(base)
+                    : "memory");
+                asm volatile(
+                    OLF_LO_LD " {%0, %1, %2, %3}, [%32+16];\n\t"
+                    OLF_LO_LD " {%4, %5, %6, %7}, [%33+16];\n\t"
+                    OLF_LO_LD " {%8, %9, %10, %11}, [%34+16];\n\t"
+                    OLF_LO_LD " {%12, %13, %14, %15}, [%35+16];\n\t"
+                    OLF_LO_LD " {%16, %17, %18, %19}, [%36+16];\n\t"
+                    OLF_LO_LD " {%20, %21, %22, %23}, [%37+16];\n\t"
+                    OLF_LO_LD " {%24, %25, %26, %27}, [%38+16];\n\t"
+                    OLF_LO_LD " {%28, %29, %30, %31}, [%39+16];"
+                    : "=f"(lo[0].x), "=f"(lo[0].y), "=f"(lo[0].z), "=f"(lo[0].w), "=f"(lo[1].x), "=f"(lo[1].y), "=f"(lo[1].z), "=f"(lo[1].w),
+                      "=f"(lo[2].x), "=f"(lo[2].y), "=f"(lo[2].z), "=f"(lo[2].w), "=f"(lo[3].x), "=f"(lo[3].y), "=f"(lo[3].z), "=f"(lo[3].w),
+                      "=f"(lo[4].x), "=f"(lo[4].y), "=f"(lo[4].z), "=f"(lo[4].w), "=f"(lo[5].x), "=f"(lo[5].y), "=f"(lo[5].z), "=f"(lo[5].w),
+                      "=f"(lo[6].x), "=f"(lo[6].y), "=f"(lo[6].z), "=f"(lo[6].w), "=f"(lo[7].x), "=f"(lo[7].y), "=f"(lo[7].z), "=f"(lo[7].w)
+                    : "l"(ra[0]), "l"(ra[1]), "l"(ra[2]), "l"(ra[3]), "l"(ra[4]), "l"(ra[5]), "l"(ra[6]), "l"(ra[7])
+                    : "memory");
+            }
+            // (2) the candidates of the current entry (its flags were set up at the end of the previous turn)
+            if (have_cur && !overflow) {
+                // the surviving candidates, in scan order; the region angle changes after every accepted pixel
+                unsigned m = m_free | m_held;
+                const int p = p_c, px = px_c, py = py_c;
+                while (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float2 csk = sm.nb[k][t];
+                    const float cxk = csk.x, cyk = csk.y;
+                    const int nk = k < 4 ? k : k + 1;
+                    const int dx = (nk % 3) - 1, dy = (nk / 3) - 1;
+                    const int q = p + dy * W + dx;
+                    bool al;
+                    {   // isAligned(), lazily: see s3_aligned() in lsd_sticky.h
+                        const float dot = f_add(f_mul(sumdx, cxk), f_mul(sumdy, cyk)), d2 = f_mul(dot, dot);
+                        const bool fast = C.fast_align && u2 > 1e-3f;
+                        if (fast && dot > 0.f && d2 >= f_mul(C.c_hi2, u2)) al = true;
+                        else if (fast && (dot <= 0.f || d2 <= f_mul(C.c_lo2, u2))) al = false;
+                        else {
+                            if (dirty) { reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads); dirty = false; }
+                            const float ang_k = __ldcg(&C.px[q].ang);               // rare path: the candidate's angle comes from its record
+                            double n_theta = d_sub(reg_angle, d_mul((double)ang_k, kDegToRads));
+                            if (n_theta < 0) n_theta = -n_theta;
+                            if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
+                            al = n_theta <= C.prec;
+                        }
+                    }
+                    if (!al) continue;
+                    const int qx = px + dx, qy = py + dy;
+                    bx0 = min(bx0, qx); bx1 = max(bx1, qx); by0 = min(by0, qy); by1 = max(by1, qy);
+                    if ((m_held >> k) & 1u) { record_blocked((unsigned)q); if (overflow) break; continue; }   // aligned but held by a higher-priority seed
+                    if ((m_low >> k) & 1u) mark_dirty_xy(C, round, qx, qy);      // taken from a lower-priority region: it must re-verify
+                    red_min64(&C.px[q].claim[0], mine);                          // fire and forget
+                    push((unsigned)q);
+                    if (overflow) break;
+                    if (have_next) {                                             // is q one of the eight neighbours of the entry whose claim words are in flight?
+                        const int ex = qx - px_n, ey = qy - py_n;
+                        if (ex >= -1 && ex <= 1 && ey >= -1 && ey <= 1 && (ex | ey) != 0) { const int nq = (ey + 1) * 3 + ex + 1; mask_n |= 1u << (nq < 4 ? nq : nq - 1); }
+                    }
+                    sumdx = f_add(sumdx, cxk);
+                    sumdy = f_add(sumdy, cyk);
+                    u2 = f_add(f_mul(sumdx, sumdx), f_mul(sumdy, sumdy));
+                    dirty = true;
+                }
+            }
+            have_cur = false;
+            // (3) the loads have arrived: flags of the next entry, which becomes the current one
+            if (have_next && !overflow) {
+                // Scheduling guard: the key every flag is compared with depends on ALL sixteen loads, so no consumer can be
+                // scheduled between the loads (the assembler otherwise serialises them to save registers: several memory
+                // round trips per entry instead of 1).  The guard never fires: bits 63..56 of a claim are 0x00 or 0xFF, bits
+                // 31..10 of a bin number are zero.
+                // (The angle word of each record is part of the guard although nothing else reads it here: a destination register that is
+                // dead would be reused right after the loads, and writing it waits for the load -- before the candidates, not after.  Eight
+                // angles whose top byte is 0xFF do not exist: they are degrees in [0, 360) or NOTDEF = -1024.)
+                unsigned acc_a = 0, acc_b = 0, acc_c = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { acc_a |= (unsigned)(cl[k] >> 32); acc_b |= __float_as_uint(lo[k].w); acc_c &= __float_as_uint(lo[k].x); }
+                acc_a |= (unsigned)(cl_c >> 32);
+                const bool never = ((acc_a >> 24) == 0x55u) || ((acc_b >> 16) == 0x55u) || ((acc_c >> 24) == 0xFFu);
+                const u64 mine_g = never ? 0ull : mine;
+                // free: c > mine (nobody's, a stale claim of an earlier wave, or a lower-priority claim that is taken over);
+                // held: c < mine and not final (NOTDEF pixels are born final); mine: c == mine
+                // the entry itself was claimed a while ago without looking at the return value: did it go to a higher-priority seed?
+                if (cl_c != mine_g) mark_dirty_xy(C, round, px_n, py_n);
+                m_free = 0; m_held = 0; m_low = 0;
+                // on the 32-bit halves (the stamp is the top 24 bits of the high word): x < 256 <=> same stamp <=> a claim of this wave
+                const unsigned mh = (unsigned)(mine_g >> 32), ml = (unsigned)mine_g;
+                // ten instructions per neighbour, written out (the compiler's version of the same tests took sixteen):
+                //   x = h ^ mh;  fre = c > mine;  low = fre && x < 256;  hld = !fre && (x | (l ^ ml)) != 0 && h >= 256   (not mine, not final)
+#define OLF_NB_FLAGS(K)                                                                                                         \
+                asm("{\n\t.reg .pred pf, pl, ph;\n\t.reg .b32 x, y;\n\t"                                                        \
+                    "xor.b32 x, %3, %5;\n\t"                                                                                    \
+                    "setp.gt.u64 pf, %7, %8;\n\t"                                                                               \
+                    "setp.lt.and.u32 pl, x, 256, pf;\n\t"                                                                       \
+                    "xor.b32 y, %4, %6;\n\t"                                                                                    \
+                    "or.b32 y, y, x;\n\t"                                                                                       \
+                    "setp.ne.and.u32 ph, y, 0, !pf;\n\t"                                                                        \
+                    "setp.ge.and.u32 ph, %3, 256, ph;\n\t"                                                                      \
+                    "@pf or.b32 %0, %0, " #K ";\n\t"                                                                            \
+                    "@ph or.b32 %1, %1, " #K ";\n\t"                                                                            \
+                    "@pl or.b32 %2, %2, " #K ";\n\t}"                                                                           \
+                    : "+r"(m_free), "+r"(m_held), "+r"(m_low)                                                                   \
+                    : "r"((unsigned)(cl[K2IDX(K)] >> 32)), "r"((unsigned)cl[K2IDX(K)]), "r"(mh), "r"(ml), "l"(cl[K2IDX(K)]), "l"(mine_g))
+#define K2IDX(K) ((K) == 1 ? 0 : (K) == 2 ? 1 : (K) == 4 ? 2 : (K) == 8 ? 3 : (K) == 16 ? 4 : (K) == 32 ? 5 : (K) == 64 ? 6 : 7)
+                OLF_NB_FLAGS(1); OLF_NB_FLAGS(2); OLF_NB_FLAGS(4); OLF_NB_FLAGS(8); OLF_NB_FLAGS(16); OLF_NB_FLAGS(32); OLF_NB_FLAGS(64); OLF_NB_FLAGS(128);
+#undef OLF_NB_FLAGS
+#undef K2IDX
+                // which of the 8 neighbours exist (bit k = k-th neighbour in scan order, centre skipped)
+                unsigned vm_n = 0x18u;
+                if (py_n > 0) vm_n |= 0x07u;
+                if (py_n < H - 1) vm_n |= 0xE0u;
+                if (px_n == 0) vm_n &= ~0x29u;
+                if (px_n == W - 1) vm_n &= ~0x94u;
+                m_free &= vm_n & ~mask_n; m_held &= vm_n & ~mask_n; m_low &= ~mask_n;       // what was claimed since the loads left is this thread's
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sm.nb[k][t] = make_float2(lo[k].y, never ? 0.f : lo[k].z);
+                p_c = p_n; px_c = px_n; py_c = py_n; have_cur = true;
+            }
+            if (overflow || (!have_cur && done >= count)) {
+                // ---- s3_end
+                SeedRec3 r; r.pad0 = r.pad1 = 0;
+                if (overflow) { r.head = kNull; r.cnt = 0; r.bhead = kNull; r.bcnt = 0; r.x0 = r.y0 = r.x1 = r.y1 = 0; D.status[0] = OLF_ERR_CAPACITY; }
+                else {
+                    if (dirty) reg_angle = d_mul((double)olf::lsd::fast_atan2_deg(sumdy, sumdx), kDegToRads);
+                    r.head = w_head; r.cnt = count; r.bhead = b_head; r.bcnt = bcnt;
+                    r.x0 = (unsigned short)bx0; r.y0 = (unsigned short)by0; r.x1 = (unsigned short)bx1; r.y1 = (unsigned short)by1;
+                    C.regang[i] = reg_angle;
+                }
+                C.srec[i] = r;
+                D.tbox[i] = overflow ? kNull : tbox_pack(bx0, by0, bx1, by1);
+                if (D.dbg) { atomicAdd(&D.dbg[round * TRACE_REC + 5], 1); atomicAdd(&D.dbg[round * TRACE_REC + 6], count); atomicMax(&D.dbg[round * TRACE_REC + 7], count); }
+                active = false;
+            } else if (!have_cur && steps >= budget) {
+                // ---- out of budget in the middle of a region: park it
+                GrowCont c;
+                c.i = i; c.w_head = w_head; c.w_chunk = w_chunk; c.r_chunk = r_chunk; c.b_head = b_head; c.b_chunk = b_chunk;
+                c.offs = (unsigned)w_off | ((unsigned)r_off << 8) | ((unsigned)b_off << 16) | ((unsigned)dirty << 24);
+                c.count = count; c.done = done; c.bcnt = bcnt;
+                c.bx0 = (unsigned short)bx0; c.by0 = (unsigned short)by0; c.bx1 = (unsigned short)bx1; c.by1 = (unsigned short)by1;
+                c.sumdx = sumdx; c.sumdy = sumdy; c.reg_angle = reg_angle;
+                c_out[atomicAdd(&st->cont_cnt[par ^ 1], 1u)] = c;
+                active = false;
+                break;
+            }
+        }
+        } else {
         for (;;) {
             if (!active) {
                 if (steps >= budget) break;                           // the rest of the list waits for the next launch
@@ -762,6 +984,7 @@ __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(cons
                 active = false;
                 break;
             }
+        }
         }
     }
     // last block to finish advances the state machine
@@ -1112,6 +1335,7 @@ struct LineImpl {
     int phase_batch = 52;
     bool trace = false;
     int first_wave = 4096, first_wave_latency = 262144, wave_growth = 16;
+    int pipeline = -1;                                           // grow kernel: -1 = pipelined walk for single frames only, 0 / 1 forced
     DevBuf<int> dbg;
     unsigned pool_chunks = 0, reg_cap = 0, max_rounds = 4096;
     int scan_blocks = 0, verify_blocks = 0, scan_blocks_wide = 0, verify_blocks_wide = 0, grow_blocks_wide = 0, grow_blocks_narrow = 0;
@@ -1224,6 +1448,7 @@ LineImpl* line_create(const olf_line_params* p, int device, cudaStream_t ext_str
     if (const char* e = getenv("OLF_LSD_GROW_BLOCKS")) h->grow_blocks_wide = h->grow_blocks_narrow = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GROW_BUDGET")) h->grow_budget = std::max(1, atoi(e));
     if (const char* e = getenv("OLF_LSD_GRAPH")) h->use_graph = atoi(e);
+    if (const char* e = getenv("OLF_LSD_PIPELINE")) h->pipeline = atoi(e) != 0;      // 0 / 1 forces the plain / pipelined grow kernel (default: by batch size)
     ok = h->cont.ensure((size_t)2 * std::max(h->grow_blocks_wide, h->grow_blocks_narrow) * GROW_THREADS) == OLF_OK;
     if (!ok) { delete h; return nullptr; }
     return h;
@@ -1428,11 +1653,13 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     B.conv = h0->conv.p; B.n = n;
     OLF_CUDA(cudaMemsetAsync(h0->conv.p, 0, (LSD_MAX_WAVES + 1) * sizeof(unsigned), s));
     OLF_CUDA(cudaEventRecord(h0->ev_grow0, s));
+    const bool pipelined = h0->pipeline < 0 ? n <= 2 : h0->pipeline != 0;           // single frame: latency; batch: throughput (see k_lsd_grow)
     auto enqueue_phases = [&](int count) {
         for (int k = 0; k < count; ++k) {
             k_lsd_scan<<<dim3(n <= 2 ? h0->scan_blocks_wide : h0->scan_blocks, n), 256, 0, s>>>(B);
             k_lsd_verify<<<dim3(n <= 2 ? h0->verify_blocks_wide : h0->verify_blocks, n), 128, 0, s>>>(B);
-            k_lsd_grow<<<dim3(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n), GROW_THREADS, 0, s>>>(B);
+            const dim3 gg(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n);
+            if (pipelined) k_lsd_grow<true><<<gg, GROW_THREADS, 0, s>>>(B); else k_lsd_grow<false><<<gg, GROW_THREADS, 0, s>>>(B);
         }
         count_launches(3 * count);
     };
@@ -1466,7 +1693,7 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
                 ok = ok && cudaGraphAddKernelNode(&n1, body, nullptr, 0, &kp) == cudaSuccess;
                 kp.func = (void*)k_lsd_verify; kp.gridDim = g_verify; kp.blockDim = dim3(128);
                 ok = ok && cudaGraphAddKernelNode(&n2, body, &n1, 1, &kp) == cudaSuccess;
-                kp.func = (void*)k_lsd_grow; kp.gridDim = g_grow; kp.blockDim = dim3(GROW_THREADS);
+                kp.func = pipelined ? (void*)k_lsd_grow<true> : (void*)k_lsd_grow<false>; kp.gridDim = g_grow; kp.blockDim = dim3(GROW_THREADS);
                 ok = ok && cudaGraphAddKernelNode(&n3, body, &n2, 1, &kp) == cudaSuccess;
                 ok = ok && cudaGraphInstantiate(&h0->graph_exec, g, 0) == cudaSuccess;
             }

@@ -94,3 +94,17 @@ def test_lsd_full_verification_failure_path(monkeypatch):
         got = g.lsd_detect(hg, img)
         assert len(got) == len(ref) and np.array_equal(got, ref)
     g.line_destroy(hg)
+
+
+@pytest.mark.parametrize("pipeline", ["0", "1"])
+@pytest.mark.parametrize("first_wave,budget", [("512", None), ("262144", None), ("4096", "96")])
+def test_lsd_both_grow_kernels(monkeypatch, pipeline, first_wave, budget):
+    """The region-growing pass has two instances (k_lsd_grow<false>: plain walk, batches; <true>: software-pipelined walk, single
+    frames).  Each is forced here on single images, with several wave plans and with a step budget (regions parked and resumed)."""
+    monkeypatch.setenv("OLF_LSD_PIPELINE", pipeline)
+    monkeypatch.setenv("OLF_LSD_FIRST_WAVE", first_wave)
+    if budget:
+        monkeypatch.setenv("OLF_LSD_GROW_BUDGET", budget)
+    for w, h, seed in [(640, 480, 31), (333, 217, 32), (1280, 720, 33)]:
+        so, sg = _segs(random_image(w, h, seed), LineParams())
+        assert so.shape == sg.shape and len(so) > 0 and np.array_equal(so, sg)
