@@ -183,12 +183,41 @@ OLF_HD bool s3_aligned(const Ctx3& C, GrowSt3& s, float aq, float cx, float cy) 
     if (n_theta > k3_2Pi) { n_theta = d_sub(n_theta, k2Pi); if (n_theta < 0) n_theta = -n_theta; }
     return n_theta <= C.prec;
 }
-OLF_HD bool s3_step(const Ctx3& C, unsigned round, GrowSt3& s) {
+// The claim words of a queue entry's 3 x 3 neighbourhood as a thread saw them EARLIER (k_lsd_grow<true> issues the loads of the next entry
+// before it decides the candidates of the current one): c[4] is the entry itself.  What the thread itself claimed after the sample was taken
+// must be patched in (s3_view_patch) -- a stale view of everybody else's claims is what the passes tolerate anyway.
+struct View3 { int p; bool valid; u64 c[9]; };
+// sample the view of the entry `ahead` positions behind the next one to be expanded (0 = the next one); false if the queue does not hold it yet
+OLF_HD bool s3_peek(const Ctx3& C, const GrowSt3& s, int ahead, View3& v) {
+    v.valid = false;
+    if (s.done + ahead >= s.count) return false;
+    ListReader r = s.rd;
+    unsigned p = 0;
+    for (int k = 0; k <= ahead; ++k) p = r.next(C.pool);
+    v.p = (int)p;
+    const int py = v.p / C.W, px = v.p - py * C.W;
+    for (int k = 0; k < 9; ++k) {
+        const int xx = px + (k % 3) - 1, yy = py + (k / 3) - 1;
+        v.c[k] = (xx < 0 || xx >= C.W || yy < 0 || yy >= C.H) ? 0 : ld_claim0(&C.px[yy * C.W + xx]);
+    }
+    v.valid = true;
+    return true;
+}
+OLF_HD void s3_view_patch(const Ctx3& C, View3& v, unsigned q, u64 mine) {
+    if (!v.valid) return;
+    const int py = v.p / C.W, px = v.p - py * C.W, qy = (int)q / C.W, qx = (int)q - qy * C.W;
+    const int ex = qx - px, ey = qy - py;
+    if (ex >= -1 && ex <= 1 && ey >= -1 && ey <= 1) v.c[(ey + 1) * 3 + ex + 1] = mine;
+}
+// view: the claim words to decide on (nullptr: read them now); claimed / n_claimed: the pixels this step claimed (at most 8), for s3_view_patch
+OLF_HD bool s3_step_view(const Ctx3& C, unsigned round, GrowSt3& s, const View3* view, unsigned* claimed, int* n_claimed) {
     const int p = (int)s.rd.next(C.pool);
     ++s.done;
+    if (n_claimed) *n_claimed = 0;
+    if (view && (!view->valid || view->p != p)) view = nullptr;
     const int py = p / C.W, px = p - py * C.W;
     // the entry itself: accepted a while ago with a fire-and-forget claim -- did it go to a higher-priority seed after all?
-    if (ld_claim0(&C.px[p]) != s.mine) mark_dirty_xy(C, round, px, py);
+    if ((view ? view->c[4] : ld_claim0(&C.px[p])) != s.mine) mark_dirty_xy(C, round, px, py);
     for (int k = 0; k < 9; ++k) {
         if (k == 4) continue;
         const int xx = px + (k % 3) - 1, yy = py + (k / 3) - 1;
@@ -197,7 +226,7 @@ OLF_HD bool s3_step(const Ctx3& C, unsigned round, GrowSt3& s) {
         float ang, cx, cy; unsigned b;
         ld_lo(&C.px[q], ang, cx, cy, b);
         if (ang < 0.f) continue;                                    // NOTDEF
-        const u64 c = ld_claim0(&C.px[q]);
+        const u64 c = view ? view->c[k] : ld_claim0(&C.px[q]);
         if ((c >> 40) == 0 || c == s.mine) continue;                // final / already in this region
         if (!s3_aligned(C, s, ang, cx, cy)) continue;
         if (c < s.mine) {                                           // aligned but held by a higher-priority seed
@@ -207,6 +236,7 @@ OLF_HD bool s3_step(const Ctx3& C, unsigned round, GrowSt3& s) {
         }
         if (claim_valid(C, c)) mark_dirty_xy(C, round, xx, yy);     // taken from a lower-priority region: it must re-verify
         red_min64(&C.px[q].claim[0], s.mine);
+        if (claimed && n_claimed) claimed[(*n_claimed)++] = (unsigned)q;
         s.wr.push(C.pool, C.pool_ctr, C.pool_chunks, (unsigned)q); if (s.wr.overflow) { s.overflow = true; return false; }
         ++s.count; s3_bbox(s, xx, yy);
         s.sumdx = f_add(s.sumdx, cx);
@@ -216,6 +246,7 @@ OLF_HD bool s3_step(const Ctx3& C, unsigned round, GrowSt3& s) {
     }
     return s.done < s.count;
 }
+OLF_HD bool s3_step(const Ctx3& C, unsigned round, GrowSt3& s) { return s3_step_view(C, round, s, nullptr, nullptr, nullptr); }
 OLF_HD void s3_end(const Ctx3& C, GrowSt3& s) {
     SeedRec3 r; r.pad0 = r.pad1 = 0;
     if (s.overflow) { r.head = kNull; r.cnt = 0; r.bhead = kNull; r.bcnt = 0; r.x0 = r.y0 = r.x1 = r.y1 = 0; C.srec[s.i] = r; return; }

@@ -28,6 +28,11 @@ static bool emul_pixel_tile_dirty(const Ctx3& C, unsigned round, int pix) {
     const int y = pix / C.W, x = pix - y * C.W, tx = x >> kTileShift, ty = y >> kTileShift;
     return (C.dirty[(round - 1) & 1][ty * C.tile_wpr + (tx >> 5)] >> (tx & 31)) & 1u;
 }
+// grow pass as k_lsd_grow<true> does it (emul_set_pipelined); g_stale_views counts the entries decided on an earlier view
+static int g_pipelined = 0; static long long g_stale_views = 0, g_rechecks = 0;
+extern "C" void emul_set_pipelined(int on) { g_pipelined = on; g_stale_views = 0; g_rechecks = 0; }
+extern "C" long long emul_rechecks() { return g_rechecks; }
+extern "C" long long emul_stale_views() { return g_stale_views; }
 extern "C" int emul_lsd_detect2(const uint8_t* img, int w, int h, const olf_line_params* P, unsigned rng_seed, int first_wave, int defer, int exact_align, int event_scan,
                                 float* segs, int cap, int* nseg, long long* stats /*[10]: waves, rounds, grown_px, final_px, regions, max_rounds_in_wave, carried, walked, live, skipped*/) {
     orc::Image8 im(w, h);
@@ -135,10 +140,12 @@ extern "C" int emul_lsd_detect2(const uint8_t* img, int w, int h, const olf_line
         for (int i = lo; i < hi; ++i) { SeedRec3 z; z.head = kNull; z.cnt = 0; z.bhead = kNull; z.bcnt = 0; z.x0 = z.y0 = z.x1 = z.y1 = 0; z.pad0 = z.pad1 = 0; srec[i] = z; }
         std::fill(dirty0.begin(), dirty0.end(), 0u); std::fill(dirty1.begin(), dirty1.end(), 0u);
         long long rw = 0;
-        bool first_round = true;
+        bool first_round = true, force_next = false;
         for (;;) {
             ++rounds; ++rw;
             bool changed = false;
+            const bool force = force_next;                     // the full verification of the wave failed: this round looks at everything (st->force in line.cu)
+            force_next = false;
             std::fill(C.dirty[round & 1], C.dirty[round & 1] + (size_t)tiles_y * wpr, 0u);     // events of THIS round
             // pass 1: scan
             if (first_round) { order.resize(hi - lo); std::iota(order.begin(), order.end(), lo); }
@@ -156,7 +163,7 @@ extern "C" int emul_lsd_detect2(const uint8_t* img, int w, int h, const olf_line
                 if (!event_scan) {
                     alive = s3_alive(C, seeds[i], prio[i]);
                     if (!alive && srec[i].cnt > 0) wl1.push_back({i, false});
-                } else if (first_round || emul_pixel_tile_dirty(C, round, seeds[i])) {
+                } else if (first_round || force || emul_pixel_tile_dirty(C, round, seeds[i])) {
                     alive = s3_alive(C, seeds[i], prio[i]);
                     sstate[i] = alive ? 1 : 0;
                     if (!alive && !first_round && srec[i].cnt > 0) wl1.push_back({i, false});       // died owning a region
@@ -168,8 +175,8 @@ extern "C" int emul_lsd_detect2(const uint8_t* img, int w, int h, const olf_line
             std::shuffle(wl1.begin(), wl1.end(), rng);
             for (auto& e : wl1) {
                 if (e.second && srec[e.first].cnt > 0) { live_px += srec[e.first].cnt; if (bbox_dirty(C, round, srec[e.first])) walked += srec[e.first].cnt; }
-                if (event_scan && e.second && tbox[e.first] < 0xFFFFFFFEu && !emul_tbox_dirty(C, round, tbox[e.first])) { ++carried; continue; }     // 4 bytes instead of the record
-                const Verify3 v = s3_verify(C, round, e.first, e.second, &changed);
+                if (event_scan && !force && e.second && tbox[e.first] < 0xFFFFFFFEu && !emul_tbox_dirty(C, round, tbox[e.first])) { ++carried; continue; }     // 4 bytes instead of the record
+                const Verify3 v = s3_verify(C, round, e.first, e.second, &changed, force);
                 if (v != kV3Carried) tbox[e.first] = kNull;
                 if (e.second && v == kV3Dead) sstate[e.first] = 0;
                 if (v == kV3Grow) wl2.push_back(e.first);
@@ -178,6 +185,7 @@ extern "C" int emul_lsd_detect2(const uint8_t* img, int w, int h, const olf_line
             // pass 3: grow, randomly interleaved
             {
                 std::vector<GrowSt3> act;
+                std::vector<View3> views;                    // pipelined walk: the view of the entry each thread expands next, sampled one turn earlier
                 size_t next = 0;
                 const size_t lanes = 1 + rng() % 48;
                 while (next < wl2.size() || !act.empty()) {
@@ -185,14 +193,27 @@ extern "C" int emul_lsd_detect2(const uint8_t* img, int w, int h, const olf_line
                         GrowSt3 st; s3_begin(C, wl2[next++], st);
                         if (st.overflow) return -3;
                         act.push_back(st);
+                        View3 v; v.valid = false; v.p = -1; views.push_back(v);
                     }
                     const size_t k = rng() % act.size();
-                    if (!s3_step(C, round, act[k])) {
+                    bool more;
+                    if (g_pipelined) {
+                        // k_lsd_grow<true>: the loads of the entry AFTER the one expanded now leave first (if the queue holds it already), then the
+                        // candidates of the current entry are decided on the view sampled a turn ago -- any number of other threads' turns ago
+                        View3 nv; s3_peek(C, act[k], 1, nv);
+                        unsigned claimed[8]; int nc = 0;
+                        more = s3_step_view(C, round, act[k], &views[k], claimed, &nc);
+                        for (int j = 0; j < nc; ++j) s3_view_patch(C, nv, claimed[j], act[k].mine);
+                        views[k] = nv;
+                        if (nv.valid) ++g_stale_views;
+                    } else more = s3_step(C, round, act[k]);
+                    if (!more) {
                         if (act[k].overflow) return -3;
                         grown += act[k].count;
                         s3_end(C, act[k]);
                         tbox[act[k].i] = emul_tbox_pack(srec[act[k].i]);
                         act[k] = act.back(); act.pop_back();
+                        views[k] = views.back(); views.pop_back();
                     }
                 }
             }
@@ -200,13 +221,30 @@ extern "C" int emul_lsd_detect2(const uint8_t* img, int w, int h, const olf_line
             if (!changed) {
                 // before the wave is finalised every live region is verified regardless of dirty tiles
                 bool clean = true;
-                for (int i : wl0) {
-                    if (srec[i].cnt <= 0 || !s3_alive(C, seeds[i], prio[i])) { if (srec[i].cnt > 0) clean = false; continue; }
-                    bool chg2 = false;
-                    if (s3_verify(C, round, i, true, &chg2, true) != kV3Carried) { clean = false; wl2.push_back(i); }
+                if (g_pipelined) {
+                    // as mode 3 of the kernels: look only, release nothing; a failure sends the wave back to the rounds with everything dirty.
+                    // (With views sampled turns ago the narrow race this pass exists for -- two parties each missing the other's claim -- does occur.)
+                    for (int i : wl0) {
+                        const SeedRec3 r = srec[i];
+                        if (r.cnt <= 0) continue;
+                        const u64 mine = key_of(C, prio[i]);
+                        ListReader rd; rd.init(r.head);
+                        for (int j = 0; j < r.cnt && clean; ++j) clean = ld_claim0(&C.px[rd.next(C.pool)]) == mine;
+                        ListReader rb; rb.init(r.bhead);
+                        for (int j = 0; j < r.bcnt && clean; ++j) clean = ld_claim0(&C.px[rb.next(C.pool)]) < mine;
+                        if (!clean) break;
+                    }
+                    if (clean) break;
+                    force_next = true; ++g_rechecks;
+                } else {
+                    for (int i : wl0) {
+                        if (srec[i].cnt <= 0 || !s3_alive(C, seeds[i], prio[i])) { if (srec[i].cnt > 0) clean = false; continue; }
+                        bool chg2 = false;
+                        if (s3_verify(C, round, i, true, &chg2, true) != kV3Carried) { clean = false; wl2.push_back(i); }
+                    }
+                    if (clean) break;
+                    return -5;                                      // cannot happen in a sequential emulation (steps are atomic)
                 }
-                if (clean) break;
-                return -5;                                      // cannot happen in a sequential emulation (steps are atomic)
             }
             ++round;
             if (rw > 4000) return -4;

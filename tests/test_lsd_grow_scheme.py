@@ -64,3 +64,43 @@ def test_fixed_point_equals_sequential_bench_image(emul):
         assert np.array_equal(segs[:n.value], ref)
         assert st[7] < st[8] // 2                              # most live pixel-rounds are never walked
         assert st[9] > 0                                       # event-driven scan: candidates skipped
+
+
+@pytest.mark.parametrize("w,h,seed,first_wave,nbins", [(320, 240, 11, 2048, 1024), (320, 240, 12, 64, 1024), (400, 300, 14, 512, 64), (640, 480, 16, 262144, 1024)])
+def test_pipelined_walk_tolerates_stale_views(emul, w, h, seed, first_wave, nbins):
+    """k_lsd_grow<true> decides the candidates of a queue entry on claim words it loaded BEFORE it decided the previous entry (its own claims made in
+    between are patched in).  Emulated with far staler views than the hardware produces: between the sample and its use any number of other
+    threads take their turns.  The segments must still equal the sequential LSD (s3_peek / s3_step_view / s3_view_patch in lsd_sticky.h)."""
+    o = oracle()
+    P = LineParams(lsd_n_bins=nbins)
+    img = random_image(w, h, seed)
+    hd = o.line_create(P); ref = o.lsd_detect(hd, img); o.line_destroy(hd)
+    emul.emul_stale_views.restype = C.c_longlong
+    emul.emul_set_pipelined(1)
+    try:
+        for sched, defer, exact, event in ((1, 1, 0, 1), (2, 0, 0, 1), (3, 1, 1, 0), (4, 1, 0, 1)):
+            segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
+            rc = emul.emul_lsd_detect2(ptr(img), w, h, C.byref(P), C.c_uint(seed * 10 + sched), first_wave, defer, exact, event, ptr(segs), 65536, C.byref(n), st)
+            assert rc == 0 and n.value == len(ref) and np.array_equal(segs[:n.value], ref)
+        assert emul.emul_stale_views() > 10000               # most entries were decided on an earlier view
+    finally:
+        emul.emul_set_pipelined(0)
+
+
+def test_pipelined_walk_recheck_path(emul):
+    """With stale views the narrow race the full verification exists for does occur in the emulation (two parties each missing the other's
+    claim, nobody marks a tile): the wave goes back to the rounds with everything dirty, as mode 3 of the kernels does, and the result is
+    still the sequential one.  (Found by tools/lsd_emul_stress.py pipelined: 1 of 450 runs; this is such a schedule.)"""
+    o = oracle()
+    P = LineParams(lsd_n_bins=16, lsd_scale=0.8)
+    img = random_image(329, 215, 1138)
+    hd = o.line_create(P); ref = o.lsd_detect(hd, img); o.line_destroy(hd)
+    emul.emul_rechecks.restype = C.c_longlong
+    emul.emul_set_pipelined(1)
+    try:
+        segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
+        rc = emul.emul_lsd_detect2(ptr(img), 329, 215, C.byref(P), C.c_uint(714), 1, 0, 0, 1, ptr(segs), 65536, C.byref(n), st)
+        assert rc == 0 and n.value == len(ref) and np.array_equal(segs[:n.value], ref)
+        assert emul.emul_rechecks() >= 1
+    finally:
+        emul.emul_set_pipelined(0)

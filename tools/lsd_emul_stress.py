@@ -2,7 +2,9 @@
 """CPU-only stress test of the parallel LSD region-growing scheme (orb_line_slam_b200/csrc/lsd_sticky.h through the host
 emulation tests/emul/lsd_emul.cpp): random image sizes, gradient-bin counts, wave plans, LSD scales, deferral / exact
 alignment on or off, three random schedules each; every run must equal the oracle's sequential LSD bit for bit.
-Round 1: 450 runs, 0 mismatches (114 s).    usage: python tools/lsd_emul_stress.py [n_images]"""
+Round 1: 450 runs, 0 mismatches (114 s).    usage: python tools/lsd_emul_stress.py [n_images] [pipelined]
+`pipelined`: the grow pass as k_lsd_grow<true> does it -- every queue entry is decided on claim words sampled one turn earlier
+(any number of other threads' turns ago), own claims patched in."""
 import ctypes as C, pathlib, subprocess, sys, time
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
@@ -14,6 +16,7 @@ from orb_line_slam_b200.synth import random_image
 so = ROOT / "tests" / "emul" / "_lsd_emul.so"
 subprocess.run(["g++", "-O2", "-march=native", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(ROOT / "tests" / "emul" / "lsd_emul.cpp")], check=True)
 em, o = C.CDLL(str(so)), oracle()
+em.emul_set_pipelined(1 if "pipelined" in sys.argv[2:] else 0)
 rng = np.random.RandomState(123)
 bad = runs = 0
 t0 = time.time()
