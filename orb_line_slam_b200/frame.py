@@ -160,7 +160,8 @@ class NativeFrontEnd:
 
     def __init__(self, api: FrontEndApi, params: FrontendParams, w, h, max_frames=1):
         self.api, self.params, self.w, self.h, self.max_frames = api, params, w, h, max_frames
-        self.off = api.frame_layout(params.cap_points, params.cap_lines)
+        self.layout = BlockLayout(api, params.cap_points, params.cap_lines, bool(params.has_lines))
+        self.off = self.layout.off
         self.handle = api.frontend_create(params, max_frames)
 
     def close(self):
@@ -180,16 +181,31 @@ class NativeFrontEnd:
 
     def view(self, block: np.ndarray, pose=None) -> StereoFrame:
         """Zero-copy numpy views into a result block."""
-        o, cp, cl = self.off, self.params.cap_points, self.params.cap_lines
-        hd = FrameHeader.from_buffer(block)
+        return self.layout.view(block, pose)
 
-        def arr(off, dtype, count, shape=None):
-            a = np.frombuffer(block, dtype=dtype, count=count, offset=int(off))
-            return a.reshape(shape) if shape else a
+
+class BlockLayout:
+    """The fixed-capacity POD block of one stereo frame (olf_frame_header + arrays at olf_frame_layout's offsets, include/olf_abi.h): what
+    olf_frontend_process fills, what the ranks of a sharded sequence exchange."""
+
+    def __init__(self, api: FrontEndApi, cap_points: int, cap_lines: int, has_lines: bool = True):
+        self.cap_points, self.cap_lines, self.has_lines = cap_points, cap_lines, has_lines
+        self.off = api.frame_layout(cap_points, cap_lines)          # host arithmetic inside libolf.so, no device needed
+        self.nbytes = int(self.off.total)
+
+    def _arr(self, block, off, dtype, count, shape=None):
+        a = np.frombuffer(block, dtype=dtype, count=count, offset=int(off))
+        return a.reshape(shape) if shape else a
+
+    def view(self, block: np.ndarray, pose=None) -> StereoFrame:
+        """Zero-copy numpy views into a result block."""
+        o, cp, cl = self.off, self.cap_points, self.cap_lines
+        hd = FrameHeader.from_buffer(block)
+        arr = lambda off, dtype, count, shape=None: self._arr(block, off, dtype, count, shape)      # noqa: E731
         f = StereoFrame(arr(o.kps_l, KEYPOINT, cp)[:hd.n_l], arr(o.desc_l, np.uint8, cp * 32, (cp, 32))[:hd.n_l],
                         arr(o.kps_r, KEYPOINT, cp)[:hd.n_r], arr(o.desc_r, np.uint8, cp * 32, (cp, 32))[:hd.n_r],
                         arr(o.u_right, np.float32, cp)[:hd.n_l], arr(o.depth, np.float32, cp)[:hd.n_l])
-        if self.params.has_lines:
+        if self.has_lines:
             f.kls = arr(o.kls_l, KEYLINE, cl)[:hd.m_l]; f.ldesc = arr(o.ldesc_l, np.uint8, cl * 32, (cl, 32))[:hd.m_l]
             f.kls_r = arr(o.kls_r, KEYLINE, cl)[:hd.m_r]; f.ldesc_r = arr(o.ldesc_r, np.uint8, cl * 32, (cl, 32))[:hd.m_r]
             f.line_matches = arr(o.lmatch, np.int32, cl)[:hd.m_l]
@@ -198,3 +214,26 @@ class NativeFrontEnd:
         if pose is not None:
             f.Rcw, f.tcw = pose
         return f
+
+    def pack(self, f: StereoFrame, block: np.ndarray | None = None) -> np.ndarray:
+        """The inverse of view(): a frame produced call by call (FrontEnd.process) laid out as olf_frontend_process would.  Raises when the
+        frame exceeds the capacities, as the native call reports OLF_ERR_CAPACITY."""
+        block = np.zeros(self.nbytes, np.uint8) if block is None else block
+        o, cp, cl = self.off, self.cap_points, self.cap_lines
+        n_l, n_r = len(f.kps), len(f.kps_r)
+        m_l, m_r = (len(f.kls), len(f.kls_r)) if self.has_lines and f.kls is not None else (0, 0)
+        if max(n_l, n_r) > cp or max(m_l, m_r) > cl:
+            raise RuntimeError("frame exceeds the block capacities")
+        block[:] = 0
+        hd = FrameHeader.from_buffer(block)
+        hd.n_l, hd.n_r, hd.m_l, hd.m_r, hd.cap_points, hd.cap_lines, hd.status = n_l, n_r, m_l, m_r, cp, cl, 0
+        self._arr(block, o.kps_l, KEYPOINT, cp)[:n_l] = f.kps; self._arr(block, o.desc_l, np.uint8, cp * 32, (cp, 32))[:n_l] = f.desc
+        self._arr(block, o.kps_r, KEYPOINT, cp)[:n_r] = f.kps_r; self._arr(block, o.desc_r, np.uint8, cp * 32, (cp, 32))[:n_r] = f.desc_r
+        self._arr(block, o.u_right, np.float32, cp)[:n_l] = f.u_right; self._arr(block, o.depth, np.float32, cp)[:n_l] = f.depth
+        if m_l or m_r:
+            self._arr(block, o.kls_l, KEYLINE, cl)[:m_l] = f.kls; self._arr(block, o.ldesc_l, np.uint8, cl * 32, (cl, 32))[:m_l] = f.ldesc
+            self._arr(block, o.kls_r, KEYLINE, cl)[:m_r] = f.kls_r; self._arr(block, o.ldesc_r, np.uint8, cl * 32, (cl, 32))[:m_r] = f.ldesc_r
+            self._arr(block, o.lmatch, np.int32, cl)[:m_l] = f.line_matches
+            self._arr(block, o.ldisp, np.float32, cl * 2, (cl, 2))[:m_l] = f.line_disp
+            self._arr(block, o.lle, np.float64, cl * 3, (cl, 3))[:m_l] = f.line_le
+        return block

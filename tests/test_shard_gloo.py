@@ -41,3 +41,56 @@ def test_two_rank_gather_matches_single_process():
         for r in range(2):
             assert np.array_equal(np.load(pathlib.Path(d) / f"rank{r}.npy"), ref)
     assert frames_for_rank(7, 0, 2) == [0, 2, 4, 6] and frames_for_rank(7, 1, 2) == [1, 3, 5]
+
+
+# ---- the whole sharded path (extraction on the owner, all-gather, frame-to-frame matching after the gather) on two gloo ranks -------------
+# The engine of this CPU test is the oracle (test infrastructure) behind the same FrontEnd / BlockLayout / ShardedSequence host code the GPU ranks run.
+SEQ_FRAMES, SEQ_FEAT, SEQ_LINES = 5, 400, 80
+
+
+def _sequence_engine():
+    import orb_line_slam_b200 as olf
+    from orc import oracle
+    from orb_line_slam_b200.frame import FrontEnd, BlockLayout
+    from orb_line_slam_b200.synth import Scene, CAMERAS, pose_f32
+    fe = FrontEnd(oracle(), CAMERAS["euroc"], SEQ_FEAT, SEQ_LINES, 0.025)
+    lay = BlockLayout(olf.api(0), SEQ_FEAT + 256, 256, True)           # olf_frame_layout is host arithmetic: no device needed
+    sc = Scene("euroc", 4)
+    poses = [pose_f32(f) for f in range(SEQ_FRAMES)]
+    process = lambda f: lay.pack(fe.process(*sc.stereo(f)))            # noqa: E731
+    return fe, lay, poses, process
+
+
+def _sequence_rank_main(rank, world, port, outdir):
+    import sys
+    sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent))
+    from orb_line_slam_b200.shard import ShardedSequence
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fe, lay, poses, process = _sequence_engine()
+    blocks, tracks = ShardedSequence(fe, lay, dist).run(SEQ_FRAMES, process, poses)
+    np.save(pathlib.Path(outdir) / f"blocks{rank}.npy", np.stack(blocks)); np.save(pathlib.Path(outdir) / f"tracks{rank}.npy", np.stack(tracks))
+    fe.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sequence_with_tracking_matches_single_process():
+    from orb_line_slam_b200.shard import pack_track, unpack_track
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_sequence_rank_main, args=(2, port, d), nprocs=2, join=True)
+        fe, lay, poses, process = _sequence_engine()
+        ref_blocks = [process(f) for f in range(SEQ_FRAMES)]
+        ref_tracks = [pack_track(0, None, lay.cap_points, lay.cap_lines)]
+        for f in range(1, SEQ_FRAMES):
+            ref_tracks.append(pack_track(f, fe.track(lay.view(ref_blocks[f], poses[f]), lay.view(ref_blocks[f - 1], poses[f - 1])), lay.cap_points, lay.cap_lines))
+        fe.close()
+        for r in range(2):
+            assert np.array_equal(np.load(pathlib.Path(d) / f"blocks{r}.npy"), np.stack(ref_blocks))
+            assert np.array_equal(np.load(pathlib.Path(d) / f"tracks{r}.npy"), np.stack(ref_tracks))
+        t = unpack_track(ref_tracks[3], lay.cap_points, lay.cap_lines)
+        assert t["frame"] == 3 and t["nmatches"] > 30 and t["n_line_matches"] > 5 and (t["cur_point"] >= 0).sum() == t["nmatches"]
+        assert unpack_track(ref_tracks[0], lay.cap_points, lay.cap_lines) is None
+        v = lay.view(ref_blocks[2])
+        assert len(v.kps) > SEQ_FEAT // 2 and len(v.kls) > 10 and np.array_equal(lay.pack(v), ref_blocks[2])          # pack is the inverse of view
