@@ -72,14 +72,15 @@ struct PinBuf {
     size_t n = 0;
     int ensure(size_t count) {
         if (count <= n) return OLF_OK;
-        if (p) { count = count + count / 2 + 4096; cudaFreeHost(p); }
-        p = nullptr; d = nullptr; n = 0;
+        if (p) count = count + count / 2 + 4096;
+        T* np = nullptr; T* nd = nullptr;
         count_allocs(1);
-        cudaError_t e = cudaHostAlloc((void**)&p, count * sizeof(T), cudaHostAllocMapped);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
-        e = cudaHostGetDevicePointer((void**)&d, p, 0);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer", __FILE__, __LINE__);
-        n = count;
+        cudaError_t e = cudaHostAlloc((void**)&np, count * sizeof(T), cudaHostAllocMapped);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);            // the old buffer stays valid
+        e = cudaHostGetDevicePointer((void**)&nd, np, 0);
+        if (e != cudaSuccess) { cudaFreeHost(np); return cuda_fail(e, "cudaHostGetDevicePointer", __FILE__, __LINE__); }
+        if (p) cudaFreeHost(p);
+        p = np; d = nd; n = count;
         return OLF_OK;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; d = nullptr; n = 0; }
