@@ -159,6 +159,18 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(const __grid_constant__ Pre
 // (non-cooperative) launches: no co-residency requirement, so the passes of several rigs in flight interleave freely with
 // every other kernel on the device.
 #define TRACE_REC 8
+// EXPERIMENT (-DOLF_PDL=1, tools/try_pdl.sh; off in the shipped library): programmatic dependent launch between the three pass kernels of the
+// plain-launch chain.  A pass waits for the grid before it (griddepcontrol.wait) and then lets the grid after it be launched; that grid's CTAs
+// sit at their own wait until this one has completed, so the start latency of a dependent launch is paid while the predecessor still runs.
+#ifndef OLF_PDL
+#define OLF_PDL 0
+#endif
+__device__ __forceinline__ void pdl_enter() {
+#if OLF_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 struct PhaseState {
     int wave; unsigned round; int mode; int done;           // mode 0: round passes, 2: converged, waiting for the batch, 3: full verification, 1: finalise
     int launches; unsigned wave_first_round;
@@ -274,6 +286,7 @@ __global__ void __launch_bounds__(256) k_lsd_reset(const __grid_constant__ PreBa
 // pass 1: every candidate of the wave -- dead or alive (+ first-round deferral); alive seeds and seeds that died owning a
 // region go to work list 1; the bitmap that collects THIS round's events is cleared
 __global__ void __launch_bounds__(256) k_lsd_scan(const __grid_constant__ GrowBatch B) {
+    pdl_enter();
     __shared__ GrowDev s_dev;
     PhaseState* st;
     const GrowDev& D = batch_image(B, &s_dev, st);
@@ -354,6 +367,7 @@ __device__ void release3_warp(const Ctx3& C, unsigned round, unsigned head, int 
 // In finalise mode: every alive seed of the converged wave is stamped for good.
 #define VERIFY_LONG 48
 __global__ void __launch_bounds__(128, 6) k_lsd_verify(const __grid_constant__ GrowBatch B) {
+    pdl_enter();
     __shared__ GrowDev s_dev;
     PhaseState* st;
     const GrowDev& D = batch_image(B, &s_dev, st);
@@ -502,6 +516,7 @@ struct GrowSmem { float2 nb[8][GROW_THREADS]; unsigned ring[GROW_RING][GROW_THRE
 // instance, a batch (throughput) the plain one with its smaller register footprint (114 vs 135).
 template <bool PIPE>
 __global__ void __launch_bounds__(GROW_THREADS, GROW_MIN_BLOCKS) k_lsd_grow(const __grid_constant__ GrowBatch B) {
+    pdl_enter();
     __shared__ GrowSmem sm;
     __shared__ GrowDev s_dev;
     __shared__ bool s_last;
@@ -1656,10 +1671,20 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     const bool pipelined = h0->pipeline < 0 ? n <= 2 : h0->pipeline != 0;           // single frame: latency; batch: throughput (see k_lsd_grow)
     auto enqueue_phases = [&](int count) {
         for (int k = 0; k < count; ++k) {
-            k_lsd_scan<<<dim3(n <= 2 ? h0->scan_blocks_wide : h0->scan_blocks, n), 256, 0, s>>>(B);
-            k_lsd_verify<<<dim3(n <= 2 ? h0->verify_blocks_wide : h0->verify_blocks, n), 128, 0, s>>>(B);
+            const dim3 gs(n <= 2 ? h0->scan_blocks_wide : h0->scan_blocks, n), gv(n <= 2 ? h0->verify_blocks_wide : h0->verify_blocks, n);
             const dim3 gg(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n);
+#if OLF_PDL
+            cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg = {}; cfg.stream = s; cfg.attrs = at; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
+            cfg.gridDim = gs; cfg.blockDim = dim3(256); cudaLaunchKernelEx(&cfg, k_lsd_scan, B);
+            cfg.gridDim = gv; cfg.blockDim = dim3(128); cudaLaunchKernelEx(&cfg, k_lsd_verify, B);
+            cfg.gridDim = gg; cfg.blockDim = dim3(GROW_THREADS);
+            if (pipelined) cudaLaunchKernelEx(&cfg, k_lsd_grow<true>, B); else cudaLaunchKernelEx(&cfg, k_lsd_grow<false>, B);
+#else
+            k_lsd_scan<<<gs, 256, 0, s>>>(B);
+            k_lsd_verify<<<gv, 128, 0, s>>>(B);
             if (pipelined) k_lsd_grow<true><<<gg, GROW_THREADS, 0, s>>>(B); else k_lsd_grow<false><<<gg, GROW_THREADS, 0, s>>>(B);
+#endif
         }
         count_launches(3 * count);
     };
@@ -1670,7 +1695,7 @@ static int lsd_run_batch(LineImpl* const* hs, int n, cudaStream_t s, std::vector
     const dim3 g_scan(n <= 2 ? h0->scan_blocks_wide : h0->scan_blocks, n), g_verify(n <= 2 ? h0->verify_blocks_wide : h0->verify_blocks, n),
                g_grow(n <= 2 ? h0->grow_blocks_wide : h0->grow_blocks_narrow, n);
     bool graph_ok = false;
-    if (h0->use_graph) {
+    if (h0->use_graph && !OLF_PDL) {
         unsigned long long key = 1469598103934665603ull;
         { const unsigned char* b = (const unsigned char*)&B; for (size_t i = 0; i < offsetof(GrowBatch, cond); ++i) { key ^= b[i]; key *= 1099511628211ull; } }
         if (!h0->graph_exec || h0->graph_key != key) {
