@@ -25,7 +25,8 @@ def line_params(nf=100, min_len=0.025):
 
 
 # (the reference itself aborts on images whose top pyramid level is narrower than its 32-px border: std::length_error in
-# ComputeKeyPointsOctTree; the oracle and the product return no keypoints for such levels)
+# ComputeKeyPointsOctTree; the oracle and the product return no keypoints for such levels.  It also crashes (division by zero, nIni = 0 in
+# DistributeOctTree) on levels more than twice as tall as wide, e.g. 271 x 631 images; oracle and product use one root cell there.)
 @pytest.mark.parametrize("w,h,nf,seed", [(320, 240, 500, 2), (640, 480, 1000, 1), (260, 200, 300, 4), (752, 480, 1200, 6)])
 def test_orbextractor_whole_file(w, h, nf, seed):
     img = random_image(w, h, seed)
