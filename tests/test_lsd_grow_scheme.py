@@ -57,9 +57,14 @@ def test_fixed_point_equals_sequential_bench_image(emul):
     hd = o.line_create(P)
     ref = o.lsd_detect(hd, img)
     o.line_destroy(hd)
-    for first_wave in (4096, 262144):
-        segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
-        rc = emul.emul_lsd_detect2(ptr(img), 1280, 720, C.byref(P), C.c_uint(first_wave), first_wave, 1, 0, 1, ptr(segs), 65536, C.byref(n), st)
+    # (plan, pipelined): the single-frame plan also with the pipelined walk of k_lsd_grow<true>, which is what a single frame runs
+    for first_wave, pipelined in ((4096, 0), (262144, 0), (262144, 1)):
+        emul.emul_set_pipelined(pipelined)
+        try:
+            segs = np.zeros((65536, 4), np.float32); n = C.c_int(); st = (C.c_longlong * 10)()
+            rc = emul.emul_lsd_detect2(ptr(img), 1280, 720, C.byref(P), C.c_uint(first_wave), first_wave, 1, 0, 1, ptr(segs), 65536, C.byref(n), st)
+        finally:
+            emul.emul_set_pipelined(0)
         assert rc == 0 and n.value == len(ref) == 2114
         assert np.array_equal(segs[:n.value], ref)
         assert st[7] < st[8] // 2                              # most live pixel-rounds are never walked
