@@ -94,3 +94,26 @@ def test_two_rank_sequence_with_tracking_matches_single_process():
         assert unpack_track(ref_tracks[0], lay.cap_points, lay.cap_lines) is None
         v = lay.view(ref_blocks[2])
         assert len(v.kps) > SEQ_FEAT // 2 and len(v.kls) > 10 and np.array_equal(lay.pack(v), ref_blocks[2])          # pack is the inverse of view
+
+
+def test_track_and_frame_blocks_refuse_what_does_not_fit():
+    import orb_line_slam_b200 as olf
+    from orb_line_slam_b200.frame import BlockLayout, StereoFrame
+    from orb_line_slam_b200.abi import KEYPOINT
+    from orb_line_slam_b200.shard import pack_track, unpack_track, track_block_size
+    t = dict(cur_point=np.arange(5, dtype=np.int32) - 1, nmatches=4, line_matches=np.array([2, -1, 0], np.int32), n_line_matches=2)
+    b = pack_track(7, t, 8, 4)
+    assert b.nbytes == track_block_size(8, 4)
+    u = unpack_track(b, 8, 4, n_last_lines=3)
+    assert u["frame"] == 7 and u["nmatches"] == 4 and u["n_line_matches"] == 2 and np.array_equal(u["cur_point"], t["cur_point"]) and np.array_equal(u["line_matches"], t["line_matches"])
+    with pytest.raises(RuntimeError):
+        pack_track(7, t, 4, 4)                                  # five keypoints do not fit four slots
+    with pytest.raises(RuntimeError):
+        pack_track(7, t, 8, 2)
+    lay = BlockLayout(olf.api(0), 16, 8, True)
+    big = StereoFrame(np.zeros(17, KEYPOINT), np.zeros((17, 32), np.uint8), np.zeros(3, KEYPOINT), np.zeros((3, 32), np.uint8), np.zeros(17, np.float32), np.zeros(17, np.float32))
+    with pytest.raises(RuntimeError):
+        lay.pack(big)                                           # as olf_frontend_process reports OLF_ERR_CAPACITY
+    ok = StereoFrame(np.zeros(4, KEYPOINT), np.zeros((4, 32), np.uint8), np.zeros(3, KEYPOINT), np.zeros((3, 32), np.uint8), np.ones(4, np.float32), np.ones(4, np.float32))
+    v = lay.view(lay.pack(ok))                                  # a frame without lines in a layout with line capacity
+    assert len(v.kps) == 4 and len(v.kps_r) == 3 and len(v.kls) == 0 and np.array_equal(v.depth, ok.depth)
